@@ -1,0 +1,401 @@
+"""ctypes binding of include/gm_capi.h (the C-ABI of csrc/libgm_b200.so).
+
+This is the only way Python reaches the product: there is no CPU implementation to fall back
+to.  A missing library is built with nvcc if possible (cross-compiles without a GPU), otherwise
+the import raises; a missing CUDA device makes `Context()` raise GmError(GM_ERR_NO_DEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+GM_OK = 0
+GM_ERR_INVALID_ARG = 1
+GM_ERR_NO_DEVICE = 2
+GM_ERR_CUDA = 3
+GM_ERR_CAPACITY = 4
+GM_ERR_STAGE_ORDER = 5
+GM_WARN_VOXEL_OVERFLOW = 6
+GM_ERR_NN_INDEX_RANGE = 7
+GM_ERR_INTERNAL = 8
+GM_ERR_NO_MODEL = 9
+
+GM_MODEL_PLANE = 0
+GM_MODEL_CYLINDER = 1
+
+
+class gm_params(C.Structure):
+    _fields_ = [
+        ("boxFilterBound", C.c_double),
+        ("voxelGridLeafSize", C.c_double),
+        ("neighborRadius", C.c_double),
+        ("weightingFactor", C.c_double),
+        ("displayCloud", C.c_int32),
+        ("displayNormals", C.c_int32),
+        ("displayCenterAxis", C.c_int32),
+        ("usePCLViz", C.c_int32),
+        ("is_dense", C.c_int32),
+        ("nn_index_mode", C.c_int32),
+        ("ransacThreshold", C.c_double),
+        ("cylinderRadiusMin", C.c_double),
+        ("cylinderRadiusMax", C.c_double),
+        ("refitIterations", C.c_int32),
+        ("maxSlices", C.c_int32),
+        ("sliceLength", C.c_double),
+    ]
+
+
+class gm_counts(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_input", "n_cropped", "n_valid", "n_voxels", "n_cells", "voxel_overflow", "nn_out_of_range", "device_error")]
+
+
+class gm_frame(C.Structure):
+    _fields_ = [("vals", C.c_float * 3), ("vecs", C.c_float * 9), ("scatter", C.c_float * 9)]
+
+
+class gm_arrow(C.Structure):
+    _fields_ = [("start", C.c_float * 3), ("end", C.c_float * 3), ("scale", C.c_float * 3),
+                ("color_argb", C.c_float * 4), ("id", C.c_int32)]
+
+
+class gm_model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("best_id", C.c_int32), ("best_count", C.c_int32), ("refit_count", C.c_int32),
+                ("hyp", C.c_float * 8), ("coef", C.c_float * 8), ("rms", C.c_float), ("pad_", C.c_float)]
+
+
+class gm_slice(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("dir", C.c_float * 3), ("radius", C.c_float), ("rms", C.c_float),
+                ("t_mid", C.c_float), ("count", C.c_int32)]
+
+
+SLICE_DTYPE = np.dtype([("center", "<f4", 3), ("dir", "<f4", 3), ("radius", "<f4"), ("rms", "<f4"),
+                        ("t_mid", "<f4"), ("count", "<i4")])
+ARROW_DTYPE = np.dtype([("start", "<f4", 3), ("end", "<f4", 3), ("scale", "<f4", 3), ("color_argb", "<f4", 4),
+                        ("id", "<i4")])
+
+
+class GmError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        msg = f"{where}: gm_status {status} ({_lib().gm_status_string(status).decode()})"
+        if detail:
+            msg += f": {detail}"
+        super().__init__(msg)
+
+
+_LIB = None
+
+# every symbol include/gm_capi.h declares; tests/test_abi.py checks the list against the header
+SYMBOLS = [
+    "gm_params_default", "gm_create", "gm_destroy", "gm_set_params", "gm_set_stream", "gm_last_error",
+    "gm_status_string", "gm_version", "gm_launch_count", "gm_reset_launch_count", "gm_synchronize",
+    "gm_upload_scan", "gm_set_scan_device", "gm_crop", "gm_normals", "gm_voxel", "gm_local_frame", "gm_ransac",
+    "gm_ransac_key_device_ptr", "gm_ransac_select", "gm_label", "gm_axis_polyline", "gm_process_scan",
+    "gm_get_counts", "gm_download_cloud", "gm_download_normals", "gm_download_neighbor_counts",
+    "gm_download_valid_map", "gm_download_voxel_assignment", "gm_download_voxels", "gm_get_voxel_grid",
+    "gm_get_frame", "gm_download_hypotheses", "gm_get_model", "gm_download_labels", "gm_download_polyline",
+    "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals",
+]
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build()  # raises if nvcc is missing: no CPU fallback
+    lib = C.CDLL(path)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    sig = {
+        "gm_params_default": (None, [C.POINTER(gm_params)]),
+        "gm_create": (i32, [C.POINTER(gm_params), sz, i32, C.POINTER(vp)]),
+        "gm_destroy": (None, [vp]),
+        "gm_set_params": (i32, [vp, C.POINTER(gm_params)]),
+        "gm_set_stream": (i32, [vp, vp]),
+        "gm_last_error": (C.c_char_p, [vp]),
+        "gm_status_string": (C.c_char_p, [i32]),
+        "gm_version": (i32, []),
+        "gm_launch_count": (i64, [vp]),
+        "gm_reset_launch_count": (None, [vp]),
+        "gm_synchronize": (i32, [vp]),
+        "gm_upload_scan": (i32, [vp, vp, sz, sz]),
+        "gm_set_scan_device": (i32, [vp, vp, sz]),
+        "gm_crop": (i32, [vp]),
+        "gm_normals": (i32, [vp]),
+        "gm_voxel": (i32, [vp]),
+        "gm_local_frame": (i32, [vp]),
+        "gm_ransac": (i32, [vp, i32, vp, i32, i32, i32]),
+        "gm_ransac_key_device_ptr": (i32, [vp, i32, C.POINTER(vp)]),
+        "gm_ransac_select": (i32, [vp, i32]),
+        "gm_label": (i32, [vp]),
+        "gm_axis_polyline": (i32, [vp]),
+        "gm_process_scan": (i32, [vp, vp, i32, vp, i32]),
+        "gm_get_counts": (i32, [vp, C.POINTER(gm_counts)]),
+        "gm_download_cloud": (i32, [vp, i32, vp, sz]),
+        "gm_download_normals": (i32, [vp, i32, vp, sz]),
+        "gm_download_neighbor_counts": (i32, [vp, vp, sz]),
+        "gm_download_valid_map": (i32, [vp, vp, sz]),
+        "gm_download_voxel_assignment": (i32, [vp, vp, vp, sz]),
+        "gm_download_voxels": (i32, [vp, vp, vp, vp, vp, vp, sz]),
+        "gm_get_voxel_grid": (i32, [vp, C.POINTER(i32 * 6)]),
+        "gm_get_frame": (i32, [vp, C.POINTER(gm_frame)]),
+        "gm_download_hypotheses": (i32, [vp, i32, vp, vp, vp, i32]),
+        "gm_get_model": (i32, [vp, i32, C.POINTER(gm_model)]),
+        "gm_download_labels": (i32, [vp, vp, sz]),
+        "gm_download_polyline": (i32, [vp, vp, i32, C.POINTER(i32)]),
+        "gm_inject_compacted": (i32, [vp, vp, vp, sz]),
+        "gm_markers_eigen": (None, [C.POINTER(gm_frame), vp]),
+        "gm_markers_normals": (None, [vp, vp, i32, vp]),
+    }
+    assert set(sig) == set(SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = the library does not export the ABI
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def default_params(**overrides) -> gm_params:
+    p = gm_params()
+    _lib().gm_params_default(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"gm_params has no field {k}")
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _as_xyzw(points: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(points, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (3, 4):
+        raise ValueError("points must be n x 3 or n x 4 float32")
+    if a.shape[1] == 3:
+        a = np.concatenate([a, np.ones((a.shape[0], 1), np.float32)], axis=1)
+    return a
+
+
+class Context:
+    """Owns one gm_ctx.  All heavy lifting happens in the CUDA library."""
+
+    def __init__(self, params: gm_params | None = None, max_points: int = 1 << 20, max_hypotheses: int = 4096):
+        lib = _lib()
+        self.params = params if params is not None else default_params()
+        self.max_points = int(max_points)
+        self.max_hypotheses = int(max_hypotheses)
+        h = C.c_void_p()
+        st = lib.gm_create(C.byref(self.params), self.max_points, self.max_hypotheses, C.byref(h))
+        if st != GM_OK:
+            raise GmError(st, "gm_create")
+        self._h = h
+        self._keepalive = None
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().gm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, st: int, where: str, ok=(GM_OK,)):
+        if st not in ok:
+            raise GmError(st, where, _lib().gm_last_error(self._h).decode())
+        return st
+
+    def set_params(self, params: gm_params):
+        self._ck(_lib().gm_set_params(self._h, C.byref(params)), "gm_set_params")
+        self.params = params
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(_lib().gm_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "gm_set_stream")
+
+    def synchronize(self):
+        self._ck(_lib().gm_synchronize(self._h), "gm_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib().gm_launch_count(self._h))
+
+    def reset_launch_count(self):
+        _lib().gm_reset_launch_count(self._h)
+
+    # -- input ------------------------------------------------------------------------------
+    def upload_scan(self, points: np.ndarray):
+        a = _as_xyzw(points)
+        self._keepalive = a
+        self._ck(_lib().gm_upload_scan(self._h, _ptr(a), a.shape[0], 16), "gm_upload_scan")
+
+    def upload_scan_raw(self, host_ptr: int, n: int, stride: int = 16):
+        self._ck(_lib().gm_upload_scan(self._h, C.c_void_p(host_ptr), n, stride), "gm_upload_scan")
+
+    def set_scan_device(self, device_ptr: int, n: int):
+        self._ck(_lib().gm_set_scan_device(self._h, C.c_void_p(device_ptr), n), "gm_set_scan_device")
+
+    # -- stages -----------------------------------------------------------------------------
+    def crop(self):
+        self._ck(_lib().gm_crop(self._h), "gm_crop")
+
+    def normals(self):
+        self._ck(_lib().gm_normals(self._h), "gm_normals")
+
+    def voxel(self):
+        self._ck(_lib().gm_voxel(self._h), "gm_voxel")
+
+    def local_frame(self):
+        self._ck(_lib().gm_local_frame(self._h), "gm_local_frame")
+
+    def ransac(self, kind: int, samples: np.ndarray, h_begin: int = 0, h_end: int | None = None):
+        s = np.ascontiguousarray(samples, dtype=np.int32)
+        H = s.shape[0]
+        self._ck(_lib().gm_ransac(self._h, kind, _ptr(s), H, h_begin, H if h_end is None else h_end), "gm_ransac")
+
+    def ransac_key_device_ptr(self, kind: int) -> int:
+        p = C.c_void_p()
+        self._ck(_lib().gm_ransac_key_device_ptr(self._h, kind, C.byref(p)), "gm_ransac_key_device_ptr")
+        return int(p.value)
+
+    def ransac_select(self, kind: int):
+        self._ck(_lib().gm_ransac_select(self._h, kind), "gm_ransac_select")
+
+    def label(self):
+        self._ck(_lib().gm_label(self._h), "gm_label")
+
+    def axis_polyline(self):
+        self._ck(_lib().gm_axis_polyline(self._h), "gm_axis_polyline")
+
+    def process_scan(self, plane_samples: np.ndarray | None, cyl_samples: np.ndarray | None):
+        ps = None if plane_samples is None else np.ascontiguousarray(plane_samples, dtype=np.int32)
+        cs = None if cyl_samples is None else np.ascontiguousarray(cyl_samples, dtype=np.int32)
+        self._ck(_lib().gm_process_scan(self._h, _ptr(ps), 0 if ps is None else ps.shape[0], _ptr(cs),
+                                        0 if cs is None else cs.shape[0]), "gm_process_scan")
+
+    def inject_compacted(self, points: np.ndarray, normals8: np.ndarray | None = None):
+        a = _as_xyzw(points)
+        nr = None if normals8 is None else np.ascontiguousarray(normals8, dtype=np.float32)
+        if nr is not None and nr.shape != (a.shape[0], 8):
+            raise ValueError("normals8 must be n x 8")
+        self._ck(_lib().gm_inject_compacted(self._h, _ptr(a), _ptr(nr), a.shape[0]), "gm_inject_compacted")
+
+    # -- results ----------------------------------------------------------------------------
+    def counts(self) -> gm_counts:
+        c = gm_counts()
+        self._ck(_lib().gm_get_counts(self._h, C.byref(c)), "gm_get_counts")
+        return c
+
+    def download_cloud(self, which: int = 1) -> np.ndarray:
+        c = self.counts()
+        n = c.n_cropped if which == 0 else c.n_valid
+        out = np.empty((max(n, 0), 4), np.float32)
+        self._ck(_lib().gm_download_cloud(self._h, which, _ptr(out), out.shape[0]), "gm_download_cloud")
+        return out
+
+    def download_normals(self, which: int = 1) -> np.ndarray:
+        c = self.counts()
+        n = c.n_cropped if which == 0 else c.n_valid
+        out = np.empty((max(n, 0), 8), np.float32)
+        self._ck(_lib().gm_download_normals(self._h, which, _ptr(out), out.shape[0]), "gm_download_normals")
+        return out
+
+    def download_neighbor_counts(self) -> np.ndarray:
+        out = np.empty(max(self.counts().n_cropped, 0), np.int32)
+        self._ck(_lib().gm_download_neighbor_counts(self._h, _ptr(out), out.shape[0]), "gm_download_neighbor_counts")
+        return out
+
+    def download_valid_map(self) -> np.ndarray:
+        out = np.empty(max(self.counts().n_cropped, 0), np.int32)
+        self._ck(_lib().gm_download_valid_map(self._h, _ptr(out), out.shape[0]), "gm_download_valid_map")
+        return out
+
+    def download_voxel_assignment(self):
+        n = max(self.counts().n_valid, 0)
+        keys, assign = np.empty(n, np.int32), np.empty(n, np.int32)
+        st = self._ck(_lib().gm_download_voxel_assignment(self._h, _ptr(keys), _ptr(assign), n),
+                      "gm_download_voxel_assignment", ok=(GM_OK, GM_WARN_VOXEL_OVERFLOW))
+        return keys, assign, st
+
+    def download_voxels(self, with_nn: bool = True):
+        V = max(self.counts().n_voxels, 0)
+        cen = np.empty((V, 4), np.float32)
+        keys, cnt = np.empty(V, np.int32), np.empty(V, np.int32)
+        nn = np.empty(V, np.int32) if with_nn else None
+        nnn = np.empty((V, 8), np.float32) if with_nn else None
+        st = self._ck(_lib().gm_download_voxels(self._h, _ptr(cen), _ptr(keys), _ptr(cnt), _ptr(nn), _ptr(nnn), V),
+                      "gm_download_voxels", ok=(GM_OK, GM_WARN_VOXEL_OVERFLOW, GM_ERR_NN_INDEX_RANGE))
+        return {"centroids": cen, "keys": keys, "counts": cnt, "nn_index": nn, "nn_normal": nnn, "status": st}
+
+    def voxel_grid(self) -> np.ndarray:
+        g = (C.c_int32 * 6)()
+        self._ck(_lib().gm_get_voxel_grid(self._h, C.byref(g)), "gm_get_voxel_grid")
+        return np.array(list(g), np.int32)
+
+    def frame(self):
+        f = gm_frame()
+        self._ck(_lib().gm_get_frame(self._h, C.byref(f)), "gm_get_frame")
+        return {"vals": np.array(f.vals, np.float32), "vecs": np.array(f.vecs, np.float32).reshape(3, 3),
+                "scatter": np.array(f.scatter, np.float32).reshape(3, 3), "_struct": f}
+
+    def download_hypotheses(self, kind: int, H: int):
+        coef = np.empty((H, 4 if kind == GM_MODEL_PLANE else 7), np.float32)
+        test = np.empty((H, 12), np.float32) if kind == GM_MODEL_CYLINDER else None
+        counts = np.empty(H, np.int32)
+        self._ck(_lib().gm_download_hypotheses(self._h, kind, _ptr(coef), _ptr(test), _ptr(counts), H), "gm_download_hypotheses")
+        return coef, test, counts
+
+    def model(self, kind: int):
+        m = gm_model()
+        st = self._ck(_lib().gm_get_model(self._h, kind, C.byref(m)), "gm_get_model", ok=(GM_OK, GM_ERR_NO_MODEL))
+        k = 4 if kind == GM_MODEL_PLANE else 7
+        return {"kind": m.kind, "best_id": m.best_id, "best_count": m.best_count, "refit_count": m.refit_count,
+                "hyp": np.array(m.hyp[:k], np.float32), "coef": np.array(m.coef[:k], np.float32), "rms": float(m.rms),
+                "status": st}
+
+    def download_labels(self) -> np.ndarray:
+        out = np.empty(max(self.counts().n_valid, 0), np.uint8)
+        self._ck(_lib().gm_download_labels(self._h, _ptr(out), out.shape[0]), "gm_download_labels")
+        return out
+
+    def download_polyline(self) -> np.ndarray:
+        cap = int(self.params.maxSlices)
+        out = np.zeros(cap, SLICE_DTYPE)
+        n = C.c_int32(0)
+        self._ck(_lib().gm_download_polyline(self._h, _ptr(out), cap, C.byref(n)), "gm_download_polyline")
+        return out[: n.value].copy()
+
+
+def markers_eigen(frame_struct: gm_frame) -> np.ndarray:
+    out = np.zeros(3, ARROW_DTYPE)
+    _lib().gm_markers_eigen(C.byref(frame_struct), _ptr(out))
+    return out
+
+
+def markers_normals(centroids: np.ndarray, nn_normal8: np.ndarray) -> np.ndarray:
+    cen = np.ascontiguousarray(centroids, np.float32)
+    nn = np.ascontiguousarray(nn_normal8, np.float32)
+    out = np.zeros(cen.shape[0], ARROW_DTYPE)
+    _lib().gm_markers_normals(_ptr(cen), _ptr(nn), cen.shape[0], _ptr(out))
+    return out

@@ -1,0 +1,823 @@
+// gm_capi.cu — context + C-ABI (include/gm_capi.h) of the B200-native per-scan hot path.
+// There is no CPU fallback anywhere in this file: every stage is a sequence of CUDA kernel
+// launches on the ctx stream, and gm_create() fails without a device.
+#include "../../include/gm_capi.h"
+#include "gm_ransac.cuh"
+#include "gm_polyline.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace gm;
+
+namespace {
+constexpr int GM_VERSION = 1;
+constexpr int FRAME_BLOCKS = 296;
+constexpr int REFIT_BLOCKS = 296;
+}  // namespace
+
+struct gm_ctx {
+  gm_params prm;
+  size_t cap = 0;   // max points
+  int hcap = 0;     // max hypotheses
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  // scan + stage flags
+  size_t n_input = 0;
+  const float4* d_scan = nullptr;  // points to d_in or to the caller's device buffer
+  bool have_scan = false, have_crop = false, have_normals = false, have_compacted = false, injected = false;
+  bool have_voxel = false, have_frame = false, have_labels = false, have_poly = false;
+  bool have_ransac[2] = {false, false}, have_model[2] = {false, false};
+  int ransac_H[2] = {0, 0};
+  GridSpec grid{};
+
+  // device buffers
+  float4 *d_in = nullptr, *d_crop = nullptr, *d_sorted = nullptr, *d_cloud_c = nullptr;
+  float4 *d_normals = nullptr, *d_normals_c = nullptr, *d_centroid = nullptr, *d_nn_normal = nullptr;
+  unsigned *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
+  unsigned* d_ucell_key = nullptr;
+  int *d_cell_id = nullptr, *d_ucell_start = nullptr, *d_nbr = nullptr, *d_valid_map = nullptr;
+  int2* d_runs = nullptr;
+  int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
+  unsigned char* d_labels = nullptr;
+  unsigned long long* d_state64 = nullptr;
+  unsigned *d_rs_state = nullptr, *d_rs_hist = nullptr, *d_rs_ticket = nullptr;
+  size_t rs_state_words = 0;
+  DevState* d_st = nullptr;
+  double* d_partials = nullptr;
+  FrameOut* d_frame = nullptr;
+  // ransac (index = kind)
+  int* d_samples[2] = {nullptr, nullptr};
+  int* h_samples[2] = {nullptr, nullptr};
+  cudaEvent_t ev_samples[2] = {nullptr, nullptr};
+  float4* d_plane_coef = nullptr;
+  float *d_model7 = nullptr, *d_test12 = nullptr;
+  int *d_hvalid[2] = {nullptr, nullptr}, *d_counts[2] = {nullptr, nullptr};
+  unsigned long long* d_key = nullptr;  // [2]
+  ModelState* d_model = nullptr;        // [2]
+  // polyline
+  PolyState* d_poly = nullptr;
+  long long* d_poly_acc = nullptr;
+  gm_slice* d_slices = nullptr;
+};
+
+#define GM_CUDA(call)                                                                            \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+      return GM_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+#define GM_LAUNCH(ctx, kernel, grid, block, ...)                                                 \
+  do {                                                                                           \
+    kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                  \
+    ++(ctx)->launches;                                                                           \
+  } while (0)
+
+#define GM_CHECK_LAUNCHES(ctx)                                                                   \
+  do {                                                                                           \
+    cudaError_t e_ = cudaGetLastError();                                                         \
+    if (e_ != cudaSuccess) {                                                                     \
+      (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e_);                      \
+      return GM_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+namespace {
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <class T>
+cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+int bits_for(unsigned long long max_value) {
+  int b = 0;
+  while (b < 64 && (max_value >> b) != 0ull) ++b;
+  return std::max(b, 1);
+}
+
+// Neighbour grid over the crop box: cell slightly larger than the search radius so that, with
+// float rounding of the cell coordinate, every d < r neighbour lies in the 27-cell neighbourhood.
+GridSpec make_grid(const gm_params& p) {
+  GridSpec g{};
+  float rf = (float)p.neighborRadius;
+  double bound = std::fabs(p.boxFilterBound);
+  double cell = (double)rf * (1.0 + 1.0 / 256.0);
+  if (!(cell > 0.0)) cell = 1e-3;
+  const int kMaxDim = 1023;
+  double span = 2.0 * bound;
+  if (span / cell + 1.0 > (double)kMaxDim) cell = span / (double)(kMaxDim - 1);
+  int dim = (int)std::floor(span / cell) + 1;
+  dim = std::min(std::max(dim, 1), kMaxDim);
+  g.origin = (float)(-bound);
+  g.cell = (float)cell;
+  g.inv_cell = (float)(1.0 / cell);
+  g.dim = dim;
+  g.ncells = (unsigned)dim * (unsigned)dim * (unsigned)dim;
+  return g;
+}
+
+// LSD radix sort of (d_keys[0], d_vals[0]) -> returns the buffer index holding the result.
+gm_status radix_sort(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int key_bits, int* result_buf) {
+  int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
+  int ntiles = div_up((long long)n_cap, RS_TILE);
+  size_t words = (size_t)passes * ntiles * 256;
+  if (words > ctx->rs_state_words) { ctx->err = "radix state capacity"; return GM_ERR_CAPACITY; }
+  GM_CUDA(cudaMemsetAsync(ctx->d_rs_state, 0, words * sizeof(unsigned), ctx->stream));
+  GM_CUDA(cudaMemsetAsync(ctx->d_rs_hist, 0, RS_MAX_PASSES * 256 * sizeof(unsigned), ctx->stream));
+  GM_CUDA(cudaMemsetAsync(ctx->d_rs_ticket, 0, RS_MAX_PASSES * sizeof(unsigned), ctx->stream));
+  int hist_grid = std::min(ntiles, ctx->num_sms * 8);
+  GM_LAUNCH(ctx, k_radix_hist, hist_grid, RS_BLOCK, ctx->d_keys[0], n_ptr, passes, ctx->d_rs_hist);
+  int cur = 0;
+  for (int p = 0; p < passes; ++p) {
+    GM_LAUNCH(ctx, k_radix_onesweep, ntiles, RS_BLOCK, ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1],
+              ctx->d_vals[cur ^ 1], n_ptr, p, ctx->d_rs_hist, ctx->d_rs_state + (size_t)p * ntiles * 256,
+              ctx->d_rs_ticket + p, &ctx->d_st->error);
+    cur ^= 1;
+  }
+  *result_buf = cur;
+  GM_CHECK_LAUNCHES(ctx);
+  return GM_OK;
+}
+
+gm_status reset_state64(gm_ctx* ctx, size_t n_cap) {
+  size_t tiles = (size_t)div_up((long long)n_cap, CP_TILE) + 1;
+  GM_CUDA(cudaMemsetAsync(ctx->d_state64, 0, tiles * sizeof(unsigned long long), ctx->stream));
+  return GM_OK;
+}
+
+gm_status sync_state(gm_ctx* ctx, DevState* host) {
+  GM_CUDA(cudaMemcpyAsync(host, ctx->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+void gm_params_default(gm_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->boxFilterBound = 5.0;     // include/geometric_mapping/paramHandler.hpp:26
+  p->voxelGridLeafSize = .1;   // :27
+  p->neighborRadius = .03;     // :28
+  p->weightingFactor = .2;     // :29
+  p->displayCloud = 1;         // :31
+  p->displayNormals = 1;       // :32
+  p->displayCenterAxis = 1;    // :33
+  p->usePCLViz = 0;            // :36
+  p->is_dense = 1;
+  p->nn_index_mode = 0;
+  p->ransacThreshold = 0.05;
+  p->cylinderRadiusMin = 0.5;
+  p->cylinderRadiusMax = 10.0;
+  p->refitIterations = 5;
+  p->maxSlices = 256;
+  p->sliceLength = 1.0;
+}
+
+const char* gm_status_string(gm_status s) {
+  switch (s) {
+    case GM_OK: return "ok";
+    case GM_ERR_INVALID_ARG: return "invalid argument";
+    case GM_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case GM_ERR_CUDA: return "CUDA error";
+    case GM_ERR_CAPACITY: return "capacity exceeded";
+    case GM_ERR_STAGE_ORDER: return "stage called before its input was produced";
+    case GM_WARN_VOXEL_OVERFLOW: return "VoxelGrid overflow rule: leaf too small, cloud returned unchanged";
+    case GM_ERR_NN_INDEX_RANGE: return "1-NN index beyond the compacted normals (reference quirk B.3)";
+    case GM_ERR_INTERNAL: return "device-side consistency check failed";
+    case GM_ERR_NO_MODEL: return "no valid RANSAC hypothesis";
+    default: return "unknown status";
+  }
+}
+
+int32_t gm_version(void) { return GM_VERSION; }
+
+static gm_status validate_params(const gm_params* p) {
+  if (!p) return GM_ERR_INVALID_ARG;
+  if (!(p->boxFilterBound > 0.0) || !(p->voxelGridLeafSize > 0.0) || !(p->neighborRadius > 0.0)) return GM_ERR_INVALID_ARG;
+  if (p->weightingFactor == 0.0) return GM_ERR_INVALID_ARG;
+  if (!(p->ransacThreshold > 0.0) || p->refitIterations < 0 || p->maxSlices < 1 || !(p->sliceLength > 0.0)) return GM_ERR_INVALID_ARG;
+  return GM_OK;
+}
+
+gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypotheses, gm_ctx** out) {
+  if (!out) return GM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (validate_params(p) != GM_OK || max_points == 0 || max_points >= (1ull << 30) || max_hypotheses < 0) return GM_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GM_ERR_NO_DEVICE; }
+  gm_ctx* ctx = new gm_ctx();
+  ctx->prm = *p;
+  ctx->cap = max_points;
+  ctx->hcap = std::max(max_hypotheses, 1);
+  const size_t N = max_points;
+  const size_t H = (size_t)ctx->hcap;
+  auto fail = [&](cudaError_t e, const char* what) {
+    std::fprintf(stderr, "gm_create: %s: %s\n", what, cudaGetErrorString(e));
+    gm_destroy(ctx);
+    return GM_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaGetDevice(&ctx->device)) != cudaSuccess) return fail(e, "cudaGetDevice");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+  ctx->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  ctx->stream = ctx->own_stream;
+#define A(ptr, count) if ((e = dmalloc(&ctx->ptr, (count))) != cudaSuccess) return fail(e, #ptr)
+  A(d_in, N); A(d_crop, N); A(d_sorted, N); A(d_cloud_c, N);
+  A(d_normals, 2 * N); A(d_normals_c, 2 * N); A(d_centroid, N); A(d_nn_normal, 2 * N);
+  A(d_keys[0], N); A(d_keys[1], N); A(d_vals[0], N); A(d_vals[1], N);
+  A(d_ucell_key, N + 1); A(d_cell_id, N); A(d_ucell_start, N + 1); A(d_nbr, N); A(d_valid_map, N);
+  A(d_runs, 9 * N);
+  A(d_vkey_pt, N); A(d_assign, N); A(d_vox_start, N + 1); A(d_vox_key, N); A(d_vox_count, N); A(d_nn_idx, N);
+  A(d_labels, N);
+  A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2);
+  ctx->rs_state_words = (size_t)RS_MAX_PASSES * div_up((long long)N, RS_TILE) * 256;
+  A(d_rs_state, ctx->rs_state_words); A(d_rs_hist, RS_MAX_PASSES * 256); A(d_rs_ticket, RS_MAX_PASSES);
+  A(d_st, 1);
+  A(d_partials, (size_t)std::max(FRAME_BLOCKS, REFIT_BLOCKS) * 32);
+  A(d_frame, 1);
+  A(d_samples[0], 3 * H); A(d_samples[1], 2 * H);
+  A(d_plane_coef, H); A(d_model7, 7 * H); A(d_test12, 12 * H);
+  A(d_hvalid[0], H); A(d_hvalid[1], H); A(d_counts[0], H); A(d_counts[1], H);
+  A(d_key, 2); A(d_model, 2);
+  A(d_poly, 1); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
+#undef A
+  if ((e = cudaMallocHost((void**)&ctx->h_samples[0], 3 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples0");
+  if ((e = cudaMallocHost((void**)&ctx->h_samples[1], 2 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples1");
+  for (int k = 0; k < 2; ++k)
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_samples[k], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+  if ((e = cudaMemset(ctx->d_st, 0, sizeof(DevState))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_model, 0, 2 * sizeof(ModelState))) != cudaSuccess) return fail(e, "memset");
+  ctx->grid = make_grid(ctx->prm);
+  *out = ctx;
+  return GM_OK;
+}
+
+void gm_destroy(gm_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
+                  ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
+                  ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
+                  ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64,
+                  ctx->d_rs_state, ctx->d_rs_hist, ctx->d_rs_ticket, ctx->d_st, ctx->d_partials, ctx->d_frame,
+                  ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
+                  ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
+                  ctx->d_poly_acc, ctx->d_slices};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (int k = 0; k < 2; ++k) {
+    if (ctx->h_samples[k]) cudaFreeHost(ctx->h_samples[k]);
+    if (ctx->ev_samples[k]) cudaEventDestroy(ctx->ev_samples[k]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+gm_status gm_set_params(gm_ctx* ctx, const gm_params* p) {
+  if (!ctx || validate_params(p) != GM_OK) return GM_ERR_INVALID_ARG;
+  if (p->maxSlices > ctx->prm.maxSlices) { ctx->err = "maxSlices cannot grow after gm_create"; return GM_ERR_CAPACITY; }
+  ctx->prm = *p;
+  ctx->grid = make_grid(ctx->prm);
+  return GM_OK;
+}
+
+gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return GM_OK;
+}
+
+const char* gm_last_error(const gm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+int64_t gm_launch_count(const gm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void gm_reset_launch_count(gm_ctx* ctx) { if (ctx) ctx->launches = 0; }
+gm_status gm_synchronize(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+static void clear_stages(gm_ctx* ctx) {
+  ctx->have_crop = ctx->have_normals = ctx->have_compacted = ctx->injected = false;
+  ctx->have_voxel = ctx->have_frame = ctx->have_labels = ctx->have_poly = false;
+  ctx->have_ransac[0] = ctx->have_ransac[1] = ctx->have_model[0] = ctx->have_model[1] = false;
+}
+
+static gm_status begin_scan(gm_ctx* ctx, size_t n) {
+  ctx->n_input = n;
+  ctx->have_scan = true;
+  clear_stages(ctx);
+  GM_LAUNCH(ctx, k_begin_scan, 1, 32, ctx->d_st, (int)n);
+  GM_CHECK_LAUNCHES(ctx);
+  return GM_OK;
+}
+
+gm_status gm_upload_scan(gm_ctx* ctx, const float* xyz_host, size_t n, size_t stride_bytes) {
+  if (!ctx || (n && !xyz_host) || stride_bytes < 12) return GM_ERR_INVALID_ARG;
+  if (n > ctx->cap) { ctx->err = "scan larger than max_points"; return GM_ERR_CAPACITY; }
+  if (n) {
+    if (stride_bytes == 16) {
+      GM_CUDA(cudaMemcpyAsync(ctx->d_in, xyz_host, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      size_t width = std::min<size_t>(stride_bytes, 16);
+      GM_CUDA(cudaMemcpy2DAsync(ctx->d_in, 16, xyz_host, stride_bytes, width, n, cudaMemcpyHostToDevice, ctx->stream));
+      GM_LAUNCH(ctx, k_set_w_one, div_up((long long)n, 256), 256, ctx->d_in, (int)n);
+    }
+  }
+  ctx->d_scan = ctx->d_in;
+  return begin_scan(ctx, n);
+}
+
+gm_status gm_set_scan_device(gm_ctx* ctx, const float* xyzw_device, size_t n) {
+  if (!ctx || (n && !xyzw_device)) return GM_ERR_INVALID_ARG;
+  if (n > ctx->cap) { ctx->err = "scan larger than max_points"; return GM_ERR_CAPACITY; }
+  ctx->d_scan = (const float4*)xyzw_device;
+  return begin_scan(ctx, n);
+}
+
+// ---- a1 --------------------------------------------------------------------------------------
+gm_status gm_crop(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
+  const size_t n = ctx->n_input;
+  if (n) {
+    gm_status s = reset_state64(ctx, n);
+    if (s != GM_OK) return s;
+    float hi = (float)ctx->prm.boxFilterBound, lo = (float)(-ctx->prm.boxFilterBound);
+    GM_LAUNCH(ctx, k_crop, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_scan, (int)n, lo, hi, ctx->prm.is_dense,
+              ctx->d_crop, ctx->d_state64, ctx->d_st);
+    GM_CHECK_LAUNCHES(ctx);
+  }
+  ctx->have_crop = true;
+  return GM_OK;
+}
+
+// ---- a2 + a3 ---------------------------------------------------------------------------------
+gm_status gm_normals(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_crop) return GM_ERR_STAGE_ORDER;
+  const size_t n = ctx->n_input;  // upper bound of M
+  if (n) {
+    const int* n_ptr = &ctx->d_st->n_crop;
+    const GridSpec g = ctx->grid;
+    int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
+    GM_LAUNCH(ctx, k_cell_keys, blocks, 256, ctx->d_crop, n_ptr, g, ctx->d_keys[0], ctx->d_vals[0]);
+    int buf = 0;
+    gm_status s = radix_sort(ctx, n_ptr, n, bits_for((unsigned long long)g.ncells), &buf);
+    if (s != GM_OK) return s;
+    if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    GM_LAUNCH(ctx, k_cell_heads, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_crop, n_ptr,
+              g.ncells, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_state64, ctx->d_st);
+    GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n * 9, 256), ctx->num_sms * 16), 256, ctx->d_ucell_key,
+              ctx->d_ucell_start, ctx->d_st, g, ctx->d_runs);
+    float rf = (float)ctx->prm.neighborRadius;
+    float r2 = rf * rf;
+    GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, n_ptr, r2,
+              ctx->d_normals, ctx->d_nbr);
+    if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
+              ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, ctx->d_st);
+    GM_CHECK_LAUNCHES(ctx);
+  }
+  ctx->have_normals = true;
+  ctx->have_compacted = true;
+  ctx->injected = false;
+  return GM_OK;
+}
+
+// ---- a4 --------------------------------------------------------------------------------------
+gm_status gm_voxel(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  const size_t n = ctx->injected ? (size_t)ctx->n_input : ctx->n_input;
+  if (n) {
+    const float leaf_f = (float)ctx->prm.voxelGridLeafSize;
+    const float inv = 1.0f / leaf_f;
+    GM_LAUNCH(ctx, k_voxel_setup, 1, 32, ctx->d_st, inv);
+    int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
+    GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt);
+    // static upper bound of the key range from the crop box (no host round trip for the bbox)
+    int key_bits = 32;
+    if (!ctx->injected) {
+      double b = std::fabs(ctx->prm.boxFilterBound) * (double)inv;
+      double div = std::floor(b) - std::floor(-b) + 2.0;
+      double total = div * div * div;
+      if (total < 2147483647.0 && (double)n < 2147483647.0) key_bits = bits_for((unsigned long long)total);
+    }
+    int buf = 0;
+    gm_status s = radix_sort(ctx, &ctx->d_st->n_valid, n, key_bits, &buf);
+    if (s != GM_OK) return s;
+    if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_assign,
+              ctx->d_vox_start, ctx->d_vox_key, ctx->d_state64, ctx->d_st);
+    GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_vals[buf], ctx->d_cloud_c,
+              ctx->d_vox_start, ctx->d_st, ctx->d_centroid, ctx->d_vox_count);
+    if (ctx->have_normals) {
+      GM_LAUNCH(ctx, k_voxel_nn, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_centroid, ctx->d_sorted,
+                ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_valid_map, ctx->d_normals_c, ctx->grid, ctx->prm.nn_index_mode,
+                ctx->d_st, ctx->d_nn_idx, ctx->d_nn_normal);
+    }
+    GM_CHECK_LAUNCHES(ctx);
+  }
+  ctx->have_voxel = true;
+  return GM_OK;
+}
+
+// ---- a5 --------------------------------------------------------------------------------------
+gm_status gm_local_frame(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  double shift = .001 / ctx->prm.weightingFactor;  // src/tunnel_processing.cpp:106 precedence
+  GM_LAUNCH(ctx, k_frame_partial, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, shift, ctx->d_partials);
+  GM_LAUNCH(ctx, k_frame_final, 1, 32, ctx->d_partials, FRAME_BLOCKS, ctx->d_frame);
+  GM_CHECK_LAUNCHES(ctx);
+  ctx->have_frame = true;
+  return GM_OK;
+}
+
+// ---- a8 --------------------------------------------------------------------------------------
+gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int32_t H, int32_t h_begin, int32_t h_end) {
+  if (!ctx || (kind != 0 && kind != 1) || H < 0 || (H > 0 && !samples_host)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  if (H > ctx->hcap) { ctx->err = "H larger than max_hypotheses"; return GM_ERR_CAPACITY; }
+  h_begin = std::max(h_begin, 0);
+  h_end = std::min(h_end, H);
+  const int per = kind == 0 ? 3 : 2;
+  const int* n_ptr = &ctx->d_st->n_valid;
+  if (H > 0) {
+    GM_CUDA(cudaEventSynchronize(ctx->ev_samples[kind]));
+    std::memcpy(ctx->h_samples[kind], samples_host, (size_t)H * per * sizeof(int));
+    GM_CUDA(cudaMemcpyAsync(ctx->d_samples[kind], ctx->h_samples[kind], (size_t)H * per * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GM_CUDA(cudaEventRecord(ctx->ev_samples[kind], ctx->stream));
+    int hb = div_up(H, 128);
+    if (kind == 0) {
+      GM_LAUNCH(ctx, k_plane_hypotheses, hb, 128, ctx->d_cloud_c, n_ptr, ctx->d_samples[0], H, ctx->d_plane_coef, ctx->d_hvalid[0]);
+    } else {
+      GM_LAUNCH(ctx, k_cyl_hypotheses, hb, 128, ctx->d_cloud_c, ctx->d_normals_c, n_ptr, ctx->d_samples[1], H,
+                (float)ctx->prm.cylinderRadiusMin, (float)ctx->prm.cylinderRadiusMax, (float)ctx->prm.ransacThreshold,
+                ctx->d_model7, ctx->d_test12, ctx->d_hvalid[1]);
+    }
+    GM_LAUNCH(ctx, k_counts_init, hb, 128, ctx->d_counts[kind], ctx->d_hvalid[kind], H, h_begin, h_end);
+    const int hloc = h_end - h_begin;
+    if (hloc > 0 && ctx->n_input > 0) {
+      const int K = kind == 0 ? 4 : 2;
+      int groups = div_up(hloc, RC_BLOCK * K);
+      int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE), div_up(ctx->num_sms * 4, groups)));
+      dim3 grid(slices, groups);
+      if (kind == 0) {
+        GM_LAUNCH(ctx, k_count_plane<4>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, h_begin, h_end,
+                  (float)ctx->prm.ransacThreshold, ctx->d_counts[0]);
+      } else {
+        GM_LAUNCH(ctx, k_count_cyl<2>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_test12, h_begin, h_end, ctx->d_counts[1]);
+      }
+    }
+  }
+  GM_LAUNCH(ctx, k_argmax, 1, AM_BLOCK, ctx->d_counts[kind], H, ctx->d_key + kind);
+  GM_CHECK_LAUNCHES(ctx);
+  ctx->have_ransac[kind] = true;
+  ctx->ransac_H[kind] = H;
+  ctx->have_model[kind] = false;
+  return GM_OK;
+}
+
+gm_status gm_ransac_key_device_ptr(gm_ctx* ctx, int32_t kind, void** key_dev) {
+  if (!ctx || !key_dev || (kind != 0 && kind != 1)) return GM_ERR_INVALID_ARG;
+  *key_dev = (void*)(ctx->d_key + kind);
+  return GM_OK;
+}
+
+gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
+  if (!ctx || (kind != 0 && kind != 1)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_ransac[kind]) return GM_ERR_STAGE_ORDER;
+  const int* n_ptr = &ctx->d_st->n_valid;
+  ModelState* ms = ctx->d_model + kind;
+  GM_LAUNCH(ctx, k_select, 1, 32, ctx->d_key + kind, kind, ctx->ransac_H[kind], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ms);
+  const float tau = (float)ctx->prm.ransacThreshold;
+  if (kind == 0) {
+    GM_LAUNCH(ctx, k_plane_refit_partial, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ms, tau, ctx->d_partials);
+    GM_LAUNCH(ctx, k_plane_refit_final, 1, 32, ctx->d_partials, REFIT_BLOCKS, ms);
+  } else {
+    for (int it = 0; it <= ctx->prm.refitIterations; ++it) {
+      GM_LAUNCH(ctx, k_cyl_gn_partial, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ms, ctx->d_partials);
+      GM_LAUNCH(ctx, k_cyl_gn_final, 1, 32, ctx->d_partials, REFIT_BLOCKS, it < ctx->prm.refitIterations ? 1 : 0, tau, ms);
+    }
+  }
+  GM_CHECK_LAUNCHES(ctx);
+  ctx->have_model[kind] = true;
+  return GM_OK;
+}
+
+gm_status gm_label(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  if (ctx->n_input) {
+    int blocks = std::min(div_up((long long)ctx->n_input, 256), ctx->num_sms * 16);
+    GM_LAUNCH(ctx, k_label, blocks, 256, ctx->d_cloud_c, &ctx->d_st->n_valid, ctx->d_model + 0, ctx->d_model + 1,
+              ctx->have_model[0] ? 1 : 0, ctx->have_model[1] ? 1 : 0, (float)ctx->prm.ransacThreshold, ctx->d_labels);
+    GM_CHECK_LAUNCHES(ctx);
+  }
+  ctx->have_labels = true;
+  return GM_OK;
+}
+
+gm_status gm_axis_polyline(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_frame || !ctx->have_labels) return GM_ERR_STAGE_ORDER;
+  const int S = ctx->prm.maxSlices;
+  const int* n_ptr = &ctx->d_st->n_valid;
+  double shift = .001 / ctx->prm.weightingFactor;
+  GM_CUDA(cudaMemsetAsync(ctx->d_poly_acc, 0, (size_t)POLY_NACC * S * sizeof(long long), ctx->stream));
+  GM_LAUNCH(ctx, k_poly_begin, 1, 32, ctx->d_poly, ctx->d_frame);
+  if (ctx->n_input) {
+    int blocks = std::min(div_up((long long)ctx->n_input, POLY_BLOCK), ctx->num_sms * 4);
+    GM_LAUNCH(ctx, k_poly_range, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_labels, n_ptr, ctx->d_poly);
+    GM_LAUNCH(ctx, k_poly_setup, 1, 32, ctx->d_poly, ctx->prm.sliceLength, S);
+    GM_LAUNCH(ctx, k_poly_pass<0>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift, ctx->d_poly_acc, ctx->d_slices);
+    GM_LAUNCH(ctx, k_poly_means, div_up(S, 64), 64, ctx->d_poly, ctx->d_poly_acc, ctx->d_slices);
+    GM_LAUNCH(ctx, k_poly_pass<1>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift, ctx->d_poly_acc, ctx->d_slices);
+    GM_LAUNCH(ctx, k_poly_fit, div_up(S, 64), 64, ctx->d_poly, ctx->d_poly_acc, ctx->d_slices);
+    GM_LAUNCH(ctx, k_poly_pass<2>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift, ctx->d_poly_acc, ctx->d_slices);
+    GM_LAUNCH(ctx, k_poly_finish, div_up(S, 64), 64, ctx->d_poly, ctx->d_poly_acc, ctx->d_slices);
+  }
+  GM_CHECK_LAUNCHES(ctx);
+  ctx->have_poly = true;
+  return GM_OK;
+}
+
+gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  gm_status s;
+  if ((s = gm_crop(ctx)) != GM_OK) return s;
+  if ((s = gm_normals(ctx)) != GM_OK) return s;
+  if ((s = gm_voxel(ctx)) != GM_OK) return s;
+  if ((s = gm_local_frame(ctx)) != GM_OK) return s;
+  if (Hp > 0) {
+    if ((s = gm_ransac(ctx, GM_MODEL_PLANE, plane_samples_host, Hp, 0, Hp)) != GM_OK) return s;
+    if ((s = gm_ransac_select(ctx, GM_MODEL_PLANE)) != GM_OK) return s;
+  }
+  if (Hc > 0) {
+    if ((s = gm_ransac(ctx, GM_MODEL_CYLINDER, cyl_samples_host, Hc, 0, Hc)) != GM_OK) return s;
+    if ((s = gm_ransac_select(ctx, GM_MODEL_CYLINDER)) != GM_OK) return s;
+  }
+  if ((s = gm_label(ctx)) != GM_OK) return s;
+  if ((s = gm_axis_polyline(ctx)) != GM_OK) return s;
+  return GM_OK;
+}
+
+// ---- results ---------------------------------------------------------------------------------
+gm_status gm_get_counts(gm_ctx* ctx, gm_counts* out) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  out->n_input = ctx->have_scan ? h.n_input : -1;
+  out->n_cropped = ctx->have_crop ? h.n_crop : -1;
+  out->n_valid = ctx->have_compacted ? h.n_valid : -1;
+  out->n_voxels = ctx->have_voxel ? h.n_voxels : -1;
+  out->n_cells = ctx->have_normals ? h.n_cells : -1;
+  out->voxel_overflow = h.voxel_overflow;
+  out->nn_out_of_range = h.nn_oor;
+  out->device_error = h.error;
+  if (h.error) { ctx->err = "device-side look-back spin bound hit"; return GM_ERR_INTERNAL; }
+  return GM_OK;
+}
+
+#define GM_D2H(dst, src, bytes)                                                                  \
+  do {                                                                                           \
+    if ((bytes) > 0) GM_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream)); \
+  } while (0)
+
+gm_status gm_download_cloud(gm_ctx* ctx, int32_t which, float* out, size_t capacity_points) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if ((which == 0 && !ctx->have_crop) || (which == 1 && !ctx->have_compacted) || which < 0 || which > 1) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  size_t n = (size_t)(which == 0 ? h.n_crop : h.n_valid);
+  if (n > capacity_points) return GM_ERR_CAPACITY;
+  GM_D2H(out, which == 0 ? ctx->d_crop : ctx->d_cloud_c, n * 16);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_download_normals(gm_ctx* ctx, int32_t which, float* out8, size_t capacity_points) {
+  if (!ctx || !out8) return GM_ERR_INVALID_ARG;
+  if ((which == 0 && !ctx->have_normals) || (which == 1 && !ctx->have_compacted) || which < 0 || which > 1) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  size_t n = (size_t)(which == 0 ? h.n_crop : h.n_valid);
+  if (n > capacity_points) return GM_ERR_CAPACITY;
+  GM_D2H(out8, which == 0 ? ctx->d_normals : ctx->d_normals_c, n * 32);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_download_neighbor_counts(gm_ctx* ctx, int32_t* out, size_t capacity_points) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_normals) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  if ((size_t)h.n_crop > capacity_points) return GM_ERR_CAPACITY;
+  GM_D2H(out, ctx->d_nbr, (size_t)h.n_crop * 4);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_download_valid_map(gm_ctx* ctx, int32_t* out, size_t capacity_points) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_normals) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  if ((size_t)h.n_crop > capacity_points) return GM_ERR_CAPACITY;
+  GM_D2H(out, ctx->d_valid_map, (size_t)h.n_crop * 4);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_download_voxel_assignment(gm_ctx* ctx, int32_t* keys, int32_t* assign, size_t capacity_points) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_voxel) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  if ((size_t)h.n_valid > capacity_points) return GM_ERR_CAPACITY;
+  if (keys) GM_D2H(keys, ctx->d_vkey_pt, (size_t)h.n_valid * 4);
+  if (assign) GM_D2H(assign, ctx->d_assign, (size_t)h.n_valid * 4);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return h.voxel_overflow ? GM_WARN_VOXEL_OVERFLOW : GM_OK;
+}
+
+gm_status gm_download_voxels(gm_ctx* ctx, float* centroids, int32_t* keys, int32_t* counts, int32_t* nn_index, float* nn_normal8,
+                             size_t capacity_voxels) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_voxel) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  size_t V = (size_t)h.n_voxels;
+  if (V > capacity_voxels) return GM_ERR_CAPACITY;
+  if (centroids) GM_D2H(centroids, ctx->d_centroid, V * 16);
+  if (keys) GM_D2H(keys, ctx->d_vox_key, V * 4);
+  if (counts) GM_D2H(counts, ctx->d_vox_count, V * 4);
+  if ((nn_index || nn_normal8) && !ctx->have_normals) return GM_ERR_STAGE_ORDER;
+  if (nn_index) GM_D2H(nn_index, ctx->d_nn_idx, V * 4);
+  if (nn_normal8) GM_D2H(nn_normal8, ctx->d_nn_normal, V * 32);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h.voxel_overflow) return GM_WARN_VOXEL_OVERFLOW;
+  if (h.nn_oor && ctx->have_normals) return GM_ERR_NN_INDEX_RANGE;
+  return GM_OK;
+}
+
+gm_status gm_get_voxel_grid(gm_ctx* ctx, int32_t grid6[6]) {
+  if (!ctx || !grid6) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_voxel) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  for (int a = 0; a < 3; ++a) { grid6[a] = h.min_b[a]; grid6[3 + a] = h.div_b[a]; }
+  return GM_OK;
+}
+
+gm_status gm_get_frame(gm_ctx* ctx, gm_frame* out) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_frame) return GM_ERR_STAGE_ORDER;
+  static_assert(sizeof(FrameOut) == sizeof(gm_frame), "frame layout");
+  GM_D2H(out, ctx->d_frame, sizeof(gm_frame));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_download_hypotheses(gm_ctx* ctx, int32_t kind, float* coef, float* test12, int32_t* counts, int32_t capacity_h) {
+  if (!ctx || (kind != 0 && kind != 1)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_ransac[kind]) return GM_ERR_STAGE_ORDER;
+  size_t H = (size_t)ctx->ransac_H[kind];
+  if ((int)H > capacity_h) return GM_ERR_CAPACITY;
+  if (coef) {
+    if (kind == 0) GM_D2H(coef, ctx->d_plane_coef, H * 16);
+    else GM_D2H(coef, ctx->d_model7, H * 28);
+  }
+  if (test12 && kind == 1) GM_D2H(test12, ctx->d_test12, H * 48);
+  if (counts) GM_D2H(counts, ctx->d_counts[kind], H * 4);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_get_model(gm_ctx* ctx, int32_t kind, gm_model* out) {
+  if (!ctx || !out || (kind != 0 && kind != 1)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_model[kind]) return GM_ERR_STAGE_ORDER;
+  ModelState h;
+  GM_D2H(&h, ctx->d_model + kind, sizeof(ModelState));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->kind = h.kind; out->best_id = h.best_id; out->best_count = h.best_count; out->refit_count = h.refit_count;
+  std::memcpy(out->hyp, h.hyp, sizeof(out->hyp));
+  std::memcpy(out->coef, h.coef, sizeof(out->coef));
+  out->rms = h.rms; out->pad_ = 0.f;
+  return h.best_id < 0 ? GM_ERR_NO_MODEL : GM_OK;
+}
+
+gm_status gm_download_labels(gm_ctx* ctx, uint8_t* out, size_t capacity_points) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_labels) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  if ((size_t)h.n_valid > capacity_points) return GM_ERR_CAPACITY;
+  GM_D2H(out, ctx->d_labels, (size_t)h.n_valid);
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_download_polyline(gm_ctx* ctx, gm_slice* out, int32_t capacity, int32_t* n_slices) {
+  if (!ctx || !n_slices) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_poly) return GM_ERR_STAGE_ORDER;
+  PolyState h;
+  GM_D2H(&h, ctx->d_poly, sizeof(PolyState));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_slices = h.S;
+  if (h.S > capacity) return GM_ERR_CAPACITY;
+  if (out && h.S > 0) {
+    GM_D2H(out, ctx->d_slices, (size_t)h.S * sizeof(gm_slice));
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return GM_OK;
+}
+
+// ---- test hook -------------------------------------------------------------------------------
+gm_status gm_inject_compacted(gm_ctx* ctx, const float* xyzw_host, const float* normals8_host, size_t n) {
+  if (!ctx || (n && !xyzw_host)) return GM_ERR_INVALID_ARG;
+  if (n > ctx->cap) return GM_ERR_CAPACITY;
+  ctx->n_input = n;
+  ctx->have_scan = true;
+  clear_stages(ctx);
+  GM_LAUNCH(ctx, k_begin_scan, 1, 32, ctx->d_st, (int)n);
+  if (n) {
+    GM_CUDA(cudaMemcpyAsync(ctx->d_cloud_c, xyzw_host, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (normals8_host) GM_CUDA(cudaMemcpyAsync(ctx->d_normals_c, normals8_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    else GM_CUDA(cudaMemsetAsync(ctx->d_normals_c, 0, n * 32, ctx->stream));
+  }
+  int nn = (int)n;
+  GM_CUDA(cudaMemcpyAsync(&ctx->d_st->n_valid, &nn, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(&ctx->d_st->n_crop, &nn, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));  // nn is a stack variable
+  if (n) GM_LAUNCH(ctx, k_bbox, std::min(div_up((long long)n, 256), ctx->num_sms * 8), 256, ctx->d_cloud_c, &ctx->d_st->n_valid, ctx->d_st);
+  GM_CHECK_LAUNCHES(ctx);
+  ctx->have_compacted = true;
+  ctx->injected = true;
+  return GM_OK;
+}
+
+// ---- a6: host-side formatting of the published numbers ------------------------------------------
+void gm_markers_eigen(const gm_frame* frame, gm_arrow out[3]) {
+  // src/tunnel_processing.cpp:265: eigenValNorms = (1/eigenVals.norm()) * eigenVals.cwiseAbs()
+  const float* v = frame->vals;
+  float nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  float inv = 1.0f / nrm;
+  for (int i = 0; i < 3; ++i) {
+    float e = inv * std::fabs(v[i]);
+    gm_arrow& a = out[i];
+    a.start[0] = a.start[1] = a.start[2] = 0.0f;
+    a.end[0] = frame->vecs[0 * 3 + i]; a.end[1] = frame->vecs[1 * 3 + i]; a.end[2] = frame->vecs[2 * 3 + i];
+    a.scale[0] = (float)(0.1 - (0.05 * e));     // :275
+    a.scale[1] = (float)(0.3 - (0.15 * e));     // :276
+    a.scale[2] = (float)(0.25 - (0.125 * e));   // :277
+    a.color_argb[0] = 1.0f;                     // :280-287, pushed as (a,r,g,b)
+    a.color_argb[1] = (i == 0) ? 1.0f : 0.0f;
+    a.color_argb[2] = (i == 1) ? 1.0f : 0.0f;
+    a.color_argb[3] = (i == 2) ? 1.0f : 0.0f;
+    a.id = i;
+  }
+}
+
+void gm_markers_normals(const float* centroids, const float* nn_normal8, int32_t V, gm_arrow* out) {
+  for (int32_t i = 0; i < V; ++i) {
+    gm_arrow& a = out[i];
+    for (int k = 0; k < 3; ++k) {
+      a.start[k] = centroids[(size_t)i * 4 + k];        // src/tunnel_processing.cpp:242-244
+      a.end[k] = nn_normal8[(size_t)i * 8 + k];         // :247-249: end = the normal itself (quirk B.4)
+    }
+    a.scale[0] = 0.025f; a.scale[1] = 0.075f; a.scale[2] = 0.0625f;  // :230
+    a.color_argb[0] = 1.0f; a.color_argb[1] = 0.0f; a.color_argb[2] = 0.0f; a.color_argb[3] = 1.0f;  // :231 -> a=1,b=1 (quirk B.5)
+    a.id = i;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// gm_device.cuh — device-side building blocks shared by the stage kernels (sm_100a).
+//   * ordered-int float min/max atomics
+//   * warp / block reductions (deterministic order)
+//   * single-pass stable stream compaction with decoupled look-back
+//   * onesweep LSD radix sort of (key,value) u32 pairs
+// Everything here is hand-written; no CUB / Thrust.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gm {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// Spin bound for every inter-block wait.  A predecessor tile is always resident or finished
+// (tiles are taken in launch order), so the bound is never reached in a correct run; if it is,
+// the kernel raises device_error instead of hanging the GPU.
+constexpr int SPIN_BOUND = 1 << 22;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ---- float <-> order-preserving int (for atomicMin/atomicMax on floats) -------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return (i >= 0) ? i : (i ^ 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ordered_to_float(int i) {
+  return __int_as_float((i >= 0) ? i : (i ^ 0x7FFFFFFF));
+}
+
+// ---- reductions ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// Sum NV doubles per thread across a block of BLOCK threads; result valid in thread 0.
+// Fixed shuffle tree + fixed warp order -> bitwise reproducible.
+template <int NV, int BLOCK>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV * BLOCK/32 */) {
+  constexpr int W = BLOCK / 32;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = warp_sum(v[k]);
+    if (l == 0) smem[k * W + w] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int i = 0; i < W; ++i) s += smem[k * W + i];
+      v[k] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- decoupled look-back tile state ---------------------------------------------------------
+// One 64-bit word per tile: (status << 32) | value, written/read with single 8-byte accesses so
+// status and value are always observed together.
+enum : unsigned { TS_EMPTY = 0u, TS_AGG = 1u, TS_PREFIX = 2u };
+
+__device__ __forceinline__ void ts_store(unsigned long long* p, unsigned status, unsigned value) {
+  unsigned long long w = ((unsigned long long)status << 32) | value;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ts_load(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+
+// Warp-cooperative look-back: returns the exclusive prefix of tile `tile` (sum of aggregates of
+// all earlier tiles).  Call with all 32 lanes of one warp.  `err` is raised on spin-bound.
+__device__ __forceinline__ unsigned lookback_exclusive(const unsigned long long* state, int tile, int* err) {
+  unsigned exclusive = 0;
+  int base = tile - 1;
+  while (base >= 0) {
+    int t = base - lane_id();
+    unsigned long long w = 0;
+    unsigned status = TS_PREFIX;  // lanes before tile 0 act as a zero prefix
+    unsigned value = 0;
+    if (t >= 0) {
+      int spins = 0;
+      do {
+        w = ts_load(state + t);
+        status = (unsigned)(w >> 32);
+      } while (status == TS_EMPTY && ++spins < SPIN_BOUND);
+      value = (unsigned)w;
+      if (status == TS_EMPTY) { atomicExch(err, 1); status = TS_PREFIX; value = 0; }
+    }
+    unsigned pref_mask = __ballot_sync(FULL, status == TS_PREFIX);
+    int first = __ffs(pref_mask) - 1;  // nearest predecessor that already holds a full prefix
+    unsigned contrib = (first < 0 || lane_id() <= first) ? value : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(FULL, contrib, o);
+    exclusive += contrib;
+    if (first >= 0) break;
+    base -= 32;
+  }
+  return exclusive;
+}
+
+// ---- stable stream compaction -------------------------------------------------------------
+// Tile = BLOCK threads x IPT items, striped (item j of thread t is tile_base + j*BLOCK + t) so
+// that global loads are coalesced.  flags[j] in, ranks[j] out (exclusive rank among the flagged
+// items of the whole input, i.e. the output position), plus the running total.
+// `state` must be zeroed (TS_EMPTY) before the launch; tiles are blockIdx.x.
+template <int BLOCK, int IPT>
+struct CompactSmem {
+  unsigned warp_cnt[IPT * (BLOCK / 32)];
+  unsigned tile_excl;
+  unsigned tile_total;
+};
+
+template <int BLOCK, int IPT>
+__device__ __forceinline__ void tile_compact_ranks(const bool (&flags)[IPT], unsigned (&ranks)[IPT],
+                                                   unsigned& total_inclusive, unsigned long long* state,
+                                                   int tile, int* err, CompactSmem<BLOCK, IPT>& sm) {
+  constexpr int W = BLOCK / 32;
+  const int w = threadIdx.x >> 5;
+  unsigned ball[IPT];
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    ball[j] = __ballot_sync(FULL, flags[j]);
+    if (lane_id() == 0) sm.warp_cnt[j * W + w] = __popc(ball[j]);
+  }
+  __syncthreads();
+  if (w == 0) {
+    // exclusive scan over IPT*W (<= 32*k) counts in (j, w) order
+    unsigned carry = 0;
+    for (int b = 0; b < IPT * W; b += 32) {
+      int i = b + lane_id();
+      unsigned v = (i < IPT * W) ? sm.warp_cnt[i] : 0u;
+      unsigned inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned n = __shfl_up_sync(FULL, inc, o);
+        if (lane_id() >= o) inc += n;
+      }
+      if (i < IPT * W) sm.warp_cnt[i] = carry + inc - v;
+      carry += __shfl_sync(FULL, inc, 31);
+    }
+    unsigned tile_total = carry;
+    if (lane_id() == 0) ts_store(state + tile, tile == 0 ? TS_PREFIX : TS_AGG, tile_total);
+    unsigned excl = lookback_exclusive(state, tile, err);
+    if (lane_id() == 0) {
+      if (tile != 0) ts_store(state + tile, TS_PREFIX, excl + tile_total);
+      sm.tile_excl = excl;
+      sm.tile_total = tile_total;
+    }
+  }
+  __syncthreads();
+  const unsigned excl = sm.tile_excl;
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) ranks[j] = excl + sm.warp_cnt[j * W + w] + __popc(ball[j] & lanemask_lt());
+  total_inclusive = excl + sm.tile_total;
+}
+
+// ---- onesweep radix sort ------------------------------------------------------------------
+constexpr int RS_BLOCK = 256;
+constexpr int RS_IPT = 8;
+constexpr int RS_TILE = RS_BLOCK * RS_IPT;
+constexpr int RS_WARPS = RS_BLOCK / 32;
+constexpr int RS_MAX_PASSES = 4;
+
+// 32-bit tile state for the sort: 2 status bits | 30 value bits (n < 2^30)
+__device__ __forceinline__ void rs_store(unsigned* p, unsigned status, unsigned value) {
+  unsigned w = (status << 30) | value;
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(w) : "memory");
+}
+__device__ __forceinline__ unsigned rs_load(const unsigned* p) {
+  unsigned w;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
+  return w;
+}
+
+// One read of the keys -> digit histograms of all passes.  hist[pass*256 + d] must be zeroed.
+__global__ void __launch_bounds__(RS_BLOCK) k_radix_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr,
+                                                         int passes, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[RS_MAX_PASSES * 256];
+  for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += RS_BLOCK) sh[i] = 0;
+  __syncthreads();
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * RS_BLOCK + threadIdx.x; i < n; i += gridDim.x * RS_BLOCK) {
+    unsigned k = keys[i];
+    for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + ((k >> (8 * p)) & 255u)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * 256; i += RS_BLOCK) {
+    unsigned v = sh[i];
+    if (v) atomicAdd(&hist[i], v);
+  }
+}
+
+// One LSD pass.  ticket/state zeroed before the sort (state: [tiles][256] u32 per pass).
+__global__ void __launch_bounds__(RS_BLOCK)
+k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
+                 unsigned* __restrict__ keys_out, unsigned* __restrict__ vals_out,
+                 const int* __restrict__ n_ptr, int pass, const unsigned* __restrict__ hist,
+                 unsigned* __restrict__ state, unsigned* __restrict__ ticket, int* __restrict__ err) {
+  __shared__ unsigned s_warp_hist[RS_WARPS][257];
+  __shared__ unsigned s_keys[RS_TILE];
+  __shared__ unsigned s_vals[RS_TILE];
+  __shared__ unsigned s_local_base[256];   // position of digit d in the tile-sorted order
+  __shared__ unsigned s_global_base[256];  // output position of the first key of digit d of this tile
+  __shared__ unsigned s_scan[RS_WARPS];
+  __shared__ int s_tile;
+
+  const int n = *n_ptr;
+  const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_BLOCK) (&s_warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= ntiles) return;
+
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int shift = 8 * pass;
+  const int chunk = tile * RS_TILE + w * (32 * RS_IPT);
+
+  unsigned key[RS_IPT], val[RS_IPT], rank[RS_IPT];
+  int dig[RS_IPT];
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    int g = chunk + i * 32 + l;
+    bool ok = g < n;
+    key[i] = ok ? keys_in[g] : 0xFFFFFFFFu;
+    val[i] = ok ? vals_in[g] : 0u;
+    dig[i] = ok ? (int)((key[i] >> shift) & 255u) : 256;
+  }
+  // stable ranks inside the warp chunk: order = (i, lane)
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    unsigned m = __match_any_sync(FULL, dig[i]);
+    unsigned before = s_warp_hist[w][dig[i]];
+    __syncwarp();
+    rank[i] = before + __popc(m & lanemask_lt());
+    if ((m & lanemask_lt()) == 0) s_warp_hist[w][dig[i]] = before + __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // per digit (thread d): exclusive offsets across warps, tile count, look-back
+  {
+    const int d = threadIdx.x;
+    unsigned run = 0;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ++ww) {
+      unsigned c = s_warp_hist[ww][d];
+      s_warp_hist[ww][d] = run;
+      run += c;
+    }
+    const unsigned tile_cnt = run;
+    unsigned* st = state + (size_t)tile * 256 + d;
+    rs_store(st, tile == 0 ? TS_PREFIX : TS_AGG, tile_cnt);
+
+    // global exclusive digit offset = sum(hist[pass][0..d))  (block scan over 256 digits)
+    unsigned hv = hist[pass * 256 + d];
+    unsigned inc = hv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(FULL, inc, o);
+      if (l >= o) inc += t;
+    }
+    if (l == 31) s_scan[w] = inc;
+    // tile-local digit base (scan of tile_cnt over d)
+    unsigned linc = tile_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(FULL, linc, o);
+      if (l >= o) linc += t;
+    }
+    __syncthreads();
+    unsigned hbase = 0;
+    for (int ww = 0; ww < w; ++ww) hbase += s_scan[ww];
+    const unsigned digit_global = hbase + inc - hv;
+    __syncthreads();
+    if (l == 31) s_scan[w] = linc;
+    __syncthreads();
+    unsigned lbase = 0;
+    for (int ww = 0; ww < w; ++ww) lbase += s_scan[ww];
+    s_local_base[d] = lbase + linc - tile_cnt;
+
+    // look back over earlier tiles for this digit
+    unsigned excl = 0;
+    for (int t = tile - 1; t >= 0; --t) {
+      const unsigned* ps = state + (size_t)t * 256 + d;
+      unsigned wv;
+      int spins = 0;
+      do { wv = rs_load(ps); } while ((wv >> 30) == TS_EMPTY && ++spins < SPIN_BOUND);
+      if ((wv >> 30) == TS_EMPTY) { atomicExch(err, 2); break; }
+      excl += wv & 0x3FFFFFFFu;
+      if ((wv >> 30) == TS_PREFIX) break;
+    }
+    if (tile != 0) rs_store(st, TS_PREFIX, excl + tile_cnt);
+    s_global_base[d] = digit_global + excl;
+  }
+  __syncthreads();
+
+  // scatter into tile-sorted order in shared memory
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    if (dig[i] < 256) {
+      unsigned pos = s_local_base[dig[i]] + s_warp_hist[w][dig[i]] + rank[i];
+      s_keys[pos] = key[i];
+      s_vals[pos] = val[i];
+    }
+  }
+  __syncthreads();
+  const int tile_n = min(RS_TILE, n - tile * RS_TILE);
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    int idx = i * RS_BLOCK + threadIdx.x;
+    if (idx < tile_n) {
+      unsigned k = s_keys[idx];
+      int d = (int)((k >> shift) & 255u);
+      unsigned g = s_global_base[d] + (unsigned)idx - s_local_base[d];
+      keys_out[g] = k;
+      vals_out[g] = s_vals[idx];
+    }
+  }
+}
+
+}  // namespace gm

@@ -1,0 +1,224 @@
+// gm_polyline.cuh — builder-defined center-axis polyline + cross-sections.
+// The reference produces one global axis direction (src/geometric_mapping.cpp:91-92); this stage
+// slices the cylinder-labelled points along that axis and fits, per slice, a circle in the
+// plane perpendicular to the axis (centre, radius) and a local axis direction (the a5 scatter
+// matrix restricted to the slice).
+//
+// Per-slice sums are accumulated as 64-bit fixed point (2^-32 resolution) with integer atomics:
+// integer addition is associative, so the result is bitwise reproducible regardless of the
+// order in which threads arrive (float/double atomics would not be).
+#pragma once
+#include "gm_ransac.cuh"
+#include "../../include/gm_capi.h"
+
+namespace gm {
+
+constexpr int POLY_BLOCK = 256;
+constexpr int POLY_NACC = 24;       // 8-byte slots per slice: 0..15 fixed-point sums, 16..21 doubles
+constexpr int POLY_SMEM_SLICES = 256;
+constexpr double POLY_FX = 4294967296.0;  // 2^32
+
+struct PolyState {
+  double axis[3], u[3], w[3];
+  unsigned long long tmin_ord, tmax_ord;
+  double t0, L;
+  int S, pad_;
+};
+
+__device__ __forceinline__ unsigned long long d_double_to_ordered(double d) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double d_ordered_to_double(unsigned long long o) {
+  unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ long long d_to_fx(double v) { return __double2ll_rn(v * POLY_FX); }
+__device__ __forceinline__ double d_from_fx(long long v) { return (double)v / POLY_FX; }
+
+__global__ void k_poly_begin(PolyState* ps, const FrameOut* __restrict__ frame) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double ax[3] = {(double)frame->vecs[0], (double)frame->vecs[3], (double)frame->vecs[6]};
+  double u[3], w[3];
+  d_perp_basis_d(ax, u, w);
+  for (int k = 0; k < 3; ++k) { ps->axis[k] = ax[k]; ps->u[k] = u[k]; ps->w[k] = w[k]; }
+  ps->tmin_ord = 0xFFFFFFFFFFFFFFFFull;
+  ps->tmax_ord = 0ull;
+  ps->t0 = 0.0; ps->L = 1.0; ps->S = 0; ps->pad_ = 0;
+}
+
+__global__ void __launch_bounds__(POLY_BLOCK)
+k_poly_range(const float4* __restrict__ pts, const unsigned char* __restrict__ labels, const int* __restrict__ n_ptr, PolyState* ps) {
+  const int n = *n_ptr;
+  const double a0 = ps->axis[0], a1 = ps->axis[1], a2 = ps->axis[2];
+  unsigned long long lo = 0xFFFFFFFFFFFFFFFFull, hi = 0ull;
+  for (int i = blockIdx.x * POLY_BLOCK + threadIdx.x; i < n; i += gridDim.x * POLY_BLOCK) {
+    if (labels[i] != 2) continue;
+    float4 p = pts[i];
+    double t = a0 * (double)p.x + a1 * (double)p.y + a2 * (double)p.z;
+    unsigned long long o = d_double_to_ordered(t);
+    lo = o < lo ? o : lo;
+    hi = o > hi ? o : hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long l2 = __shfl_xor_sync(FULL, lo, o), h2 = __shfl_xor_sync(FULL, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if (lane_id() == 0 && lo <= hi) {
+    atomicMin(&ps->tmin_ord, lo);
+    atomicMax(&ps->tmax_ord, hi);
+  }
+}
+
+__global__ void k_poly_setup(PolyState* ps, double L, int max_slices) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ps->L = L;
+  if (ps->tmin_ord > ps->tmax_ord) { ps->S = 0; return; }
+  double tmin = d_ordered_to_double(ps->tmin_ord), tmax = d_ordered_to_double(ps->tmax_ord);
+  double t0 = floor(tmin / L) * L;
+  int S = (int)floor((tmax - t0) / L) + 1;
+  ps->t0 = t0;
+  ps->S = S > max_slices ? max_slices : S;
+}
+
+// PASS 0: n, sum a, sum b, weighted normal scatter (slots 0..8)
+// PASS 1: centred second/third moments for the algebraic circle fit (slots 9..14)
+// PASS 2: squared residuals against the fitted circle (slot 15)
+template <int PASS>
+__global__ void __launch_bounds__(POLY_BLOCK)
+k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, const unsigned char* __restrict__ labels,
+            const int* __restrict__ n_ptr, const PolyState* __restrict__ ps, double shift, long long* __restrict__ acc,
+            const gm_slice* /*unused*/) {
+  constexpr int NS = PASS == 0 ? 9 : (PASS == 1 ? 6 : 1);
+  constexpr int SLOT0 = PASS == 0 ? 0 : (PASS == 1 ? 9 : 15);
+  __shared__ unsigned long long s_acc[POLY_SMEM_SLICES * NS];
+  const int n = *n_ptr;
+  const int S = ps->S;
+  if (S <= 0) return;
+  const bool use_smem = S <= POLY_SMEM_SLICES;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) s_acc[i] = 0ull;
+    __syncthreads();
+  }
+  const double a0 = ps->axis[0], a1 = ps->axis[1], a2 = ps->axis[2];
+  const double u0 = ps->u[0], u1 = ps->u[1], u2 = ps->u[2];
+  const double w0 = ps->w[0], w1 = ps->w[1], w2 = ps->w[2];
+  const double t0 = ps->t0, L = ps->L;
+  const double* aux = reinterpret_cast<const double*>(acc);
+  for (int i = blockIdx.x * POLY_BLOCK + threadIdx.x; i < n; i += gridDim.x * POLY_BLOCK) {
+    if (labels[i] != 2) continue;
+    float4 p = pts[i];
+    double x = p.x, y = p.y, z = p.z;
+    double t = a0 * x + a1 * y + a2 * z;
+    int s = (int)floor((t - t0) / L);
+    if (s < 0 || s >= S) continue;
+    long long v[NS];
+    if (PASS == 0) {
+      double a = u0 * x + u1 * y + u2 * z, b = w0 * x + w1 * y + w2 * z;
+      float4 n0 = normals[2 * (size_t)i];
+      float curv = normals[2 * (size_t)i + 1].x;
+      double tt = (double)curv + shift;
+      double wt = (double)(float)exp(tt * tt);
+      double na = wt * (double)n0.x, nb = wt * (double)n0.y, nc = wt * (double)n0.z;
+      v[0] = 1; v[1] = d_to_fx(a); v[2] = d_to_fx(b);
+      v[3] = d_to_fx(na * na); v[4] = d_to_fx(na * nb); v[5] = d_to_fx(na * nc);
+      v[6] = d_to_fx(nb * nb); v[7] = d_to_fx(nb * nc); v[8] = d_to_fx(nc * nc);
+    } else if (PASS == 1) {
+      double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
+      double a = u0 * x + u1 * y + u2 * z - ma, b = w0 * x + w1 * y + w2 * z - mb;
+      double zz = a * a + b * b;
+      v[0] = d_to_fx(a * a); v[1] = d_to_fx(a * b); v[2] = d_to_fx(b * b);
+      v[3] = d_to_fx(a * zz); v[4] = d_to_fx(b * zz); v[5] = d_to_fx(zz);
+    } else {
+      double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
+      double ca = aux[(size_t)s * POLY_NACC + 18], cb = aux[(size_t)s * POLY_NACC + 19], rad = aux[(size_t)s * POLY_NACC + 20];
+      double a = u0 * x + u1 * y + u2 * z - ma - ca, b = w0 * x + w1 * y + w2 * z - mb - cb;
+      double e = sqrt(a * a + b * b) - rad;
+      v[0] = d_to_fx(e * e);
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      if (use_smem) atomicAdd(&s_acc[s * NS + k], (unsigned long long)v[k]);
+      else atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)s * POLY_NACC + SLOT0 + k, (unsigned long long)v[k]);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) {
+      unsigned long long v = s_acc[i];
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)(i / NS) * POLY_NACC + SLOT0 + (i % NS), v);
+    }
+  }
+}
+
+__global__ void k_poly_means(const PolyState* __restrict__ ps, long long* acc, gm_slice* /*unused*/) {
+  const int S = ps->S;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double* aux = reinterpret_cast<double*>(acc);
+  double n = (double)acc[(size_t)s * POLY_NACC + 0];
+  double ma = 0.0, mb = 0.0;
+  if (n > 0) { ma = d_from_fx(acc[(size_t)s * POLY_NACC + 1]) / n; mb = d_from_fx(acc[(size_t)s * POLY_NACC + 2]) / n; }
+  aux[(size_t)s * POLY_NACC + 16] = ma;
+  aux[(size_t)s * POLY_NACC + 17] = mb;
+}
+
+__global__ void k_poly_fit(const PolyState* __restrict__ ps, long long* acc, gm_slice* /*unused*/) {
+  const int S = ps->S;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double* aux = reinterpret_cast<double*>(acc);
+  const long long* a = acc + (size_t)s * POLY_NACC;
+  double n = (double)a[0];
+  double ca = 0.0, cb = 0.0, rad = 0.0, ok = 0.0;
+  if (n >= 3) {
+    double Saa = d_from_fx(a[9]), Sab = d_from_fx(a[10]), Sbb = d_from_fx(a[11]);
+    double Saz = d_from_fx(a[12]), Sbz = d_from_fx(a[13]), Sz = d_from_fx(a[14]);
+    double det = Saa * Sbb - Sab * Sab;
+    if (fabs(det) > 1e-300) {
+      double Ac = (Saz * Sbb - Sbz * Sab) / det, Bc = (Sbz * Saa - Saz * Sab) / det;
+      ca = 0.5 * Ac; cb = 0.5 * Bc;
+      rad = sqrt(Sz / n + ca * ca + cb * cb);
+      ok = 1.0;
+    }
+  }
+  aux[(size_t)s * POLY_NACC + 18] = ca;
+  aux[(size_t)s * POLY_NACC + 19] = cb;
+  aux[(size_t)s * POLY_NACC + 20] = rad;
+  aux[(size_t)s * POLY_NACC + 21] = ok;
+}
+
+__global__ void k_poly_finish(const PolyState* __restrict__ ps, const long long* __restrict__ acc, gm_slice* __restrict__ out) {
+  const int S = ps->S;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const double* aux = reinterpret_cast<const double*>(acc);
+  const long long* a = acc + (size_t)s * POLY_NACC;
+  double n = (double)a[0];
+  gm_slice o;
+  for (int k = 0; k < 3; ++k) { o.center[k] = 0.f; o.dir[k] = 0.f; }
+  o.radius = 0.f; o.rms = 0.f;
+  double tm = ps->t0 + ((double)s + 0.5) * ps->L;
+  o.t_mid = (float)tm;
+  o.count = (int)a[0];
+  if (n >= 3 && aux[(size_t)s * POLY_NACC + 21] != 0.0) {
+    double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
+    double ca = aux[(size_t)s * POLY_NACC + 18], cb = aux[(size_t)s * POLY_NACC + 19], rad = aux[(size_t)s * POLY_NACC + 20];
+    double ctr_a = ma + ca, ctr_b = mb + cb;
+    for (int k = 0; k < 3; ++k) o.center[k] = (float)(ctr_a * ps->u[k] + ctr_b * ps->w[k] + tm * ps->axis[k]);
+    double N[9] = {d_from_fx(a[3]), d_from_fx(a[4]), d_from_fx(a[5]), 0, d_from_fx(a[6]), d_from_fx(a[7]), 0, 0, d_from_fx(a[8])};
+    N[3] = N[1]; N[6] = N[2]; N[7] = N[5];
+    double vals[3], vecs[9];
+    d_jacobi3(N, vals, vecs);
+    double d[3] = {vecs[0], vecs[3], vecs[6]};
+    if (d[0] * ps->axis[0] + d[1] * ps->axis[1] + d[2] * ps->axis[2] < 0) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
+    for (int k = 0; k < 3; ++k) o.dir[k] = (float)d[k];
+    o.radius = (float)rad;
+    o.rms = (float)sqrt(d_from_fx(a[15]) / n);
+  }
+  out[s] = o;
+}
+
+}  // namespace gm

@@ -1,0 +1,487 @@
+// gm_ransac.cuh — builder-defined stage a8: batched RANSAC plane / cylinder hypotheses from
+// injected sample indices, inlier counting, argmax, least-squares refit, labels.
+// The reference only stubs this stage (src/tunnel_processing.cpp:149-154); the definitions follow
+// pcl::SampleConsensusModelPlane / Cylinder / RandomSampleConsensus.
+// Compiled with -fmad=false: hypothesis generation is the plain unfused expression order that the
+// oracle uses (bit-identical coefficients); the inlier tests are explicit fmaf chains.
+#pragma once
+#include "gm_stages.cuh"
+
+namespace gm {
+
+// ---- hypothesis generation ------------------------------------------------------------------
+// plane: samples H x 3 -> coef float4 {a,b,c,d}, valid
+__global__ void k_plane_hypotheses(const float4* __restrict__ pts, const int* __restrict__ n_ptr,
+                                   const int* __restrict__ samples, int H, float4* __restrict__ coef,
+                                   int* __restrict__ valid) {
+  const int n = *n_ptr;
+  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+    int i0 = samples[h * 3], i1 = samples[h * 3 + 1], i2 = samples[h * 3 + 2];
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ok = 0;
+    if (i0 >= 0 && i1 >= 0 && i2 >= 0 && i0 < n && i1 < n && i2 < n && i0 != i1 && i0 != i2 && i1 != i2) {
+      float4 p0 = pts[i0], p1 = pts[i1], p2 = pts[i2];
+      float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+      float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+      float nx = ay * bz - az * by;
+      float ny = az * bx - ax * bz;
+      float nz = ax * by - ay * bx;
+      float len2 = (nx * nx + ny * ny) + nz * nz;
+      if (len2 > 0.0f && isfinite(len2)) {
+        float len = sqrtf(len2);
+        nx = nx / len; ny = ny / len; nz = nz / len;
+        float d = -((nx * p0.x + ny * p0.y) + nz * p0.z);
+        if (isfinite(d)) { c = make_float4(nx, ny, nz, d); ok = 1; }
+      }
+    }
+    coef[h] = c;
+    valid[h] = ok;
+  }
+}
+
+// canonical orthonormal basis perpendicular to unit dir (matches oracle perp_basis)
+__device__ __forceinline__ void d_perp_basis(const float dir[3], float u[3], float w[3]) {
+  float ax = fabsf(dir[0]), ay = fabsf(dir[1]), az = fabsf(dir[2]);
+  int k = 0; float m = ax;
+  if (ay < m) { k = 1; m = ay; }
+  if (az < m) { k = 2; m = az; }
+  float c[3];
+  if (k == 0) { c[0] = 0.0f; c[1] = dir[2]; c[2] = -dir[1]; }
+  else if (k == 1) { c[0] = -dir[2]; c[1] = 0.0f; c[2] = dir[0]; }
+  else { c[0] = dir[1]; c[1] = -dir[0]; c[2] = 0.0f; }
+  float l = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+  u[0] = c[0] / l; u[1] = c[1] / l; u[2] = c[2] / l;
+  w[0] = dir[1] * u[2] - dir[2] * u[1];
+  w[1] = dir[2] * u[0] - dir[0] * u[2];
+  w[2] = dir[0] * u[1] - dir[1] * u[0];
+}
+
+// model7 {q,dir,r} -> test12 {u,du, w,dw, mid,half,0,0}; returns false if any value is non-finite
+__device__ __forceinline__ bool d_cyl_test_params(const float* m7, float tau, float* t12) {
+  float u[3], w[3];
+  d_perp_basis(m7 + 3, u, w);
+  float du = -((u[0] * m7[0] + u[1] * m7[1]) + u[2] * m7[2]);
+  float dw = -((w[0] * m7[0] + w[1] * m7[1]) + w[2] * m7[2]);
+  float r = m7[6];
+  float hi = r + tau, lo = r - tau;
+  float hi2 = hi * hi, lo2 = lo * lo;
+  float mid, half;
+  if (lo >= 0.0f) { mid = 0.5f * (hi2 + lo2); half = 0.5f * (hi2 - lo2); }
+  else { mid = 0.0f; half = hi2; }
+  t12[0] = u[0]; t12[1] = u[1]; t12[2] = u[2]; t12[3] = du;
+  t12[4] = w[0]; t12[5] = w[1]; t12[6] = w[2]; t12[7] = dw;
+  t12[8] = mid; t12[9] = half; t12[10] = 0.0f; t12[11] = 0.0f;
+  bool fin = true;
+  for (int k = 0; k < 10; ++k) fin = fin && isfinite(t12[k]);
+  return fin;
+}
+
+// cylinder: samples H x 2 (+ normals) -> model7, test12, valid
+__global__ void k_cyl_hypotheses(const float4* __restrict__ pts, const float4* __restrict__ normals,
+                                 const int* __restrict__ n_ptr, const int* __restrict__ samples, int H,
+                                 float rmin, float rmax, float tau, float* __restrict__ model7,
+                                 float* __restrict__ test12, int* __restrict__ valid) {
+  const int n = *n_ptr;
+  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+    float m[7] = {0, 0, 0, 0, 0, 0, 0};
+    float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int ok = 0;
+    int i1 = samples[h * 2], i2 = samples[h * 2 + 1];
+    if (i1 >= 0 && i2 >= 0 && i1 < n && i2 < n && i1 != i2) {
+      float4 P1 = pts[i1], P2 = pts[i2];
+      float4 N1 = normals[2 * (size_t)i1], N2 = normals[2 * (size_t)i2];
+      float p1[3] = {P1.x, P1.y, P1.z}, p2[3] = {P2.x, P2.y, P2.z};
+      float n1[3] = {N1.x, N1.y, N1.z}, n2[3] = {N2.x, N2.y, N2.z};
+      const float eps = 1.1920928955078125e-07f;
+      bool coincident = fabsf(p1[0] - p2[0]) <= eps && fabsf(p1[1] - p2[1]) <= eps && fabsf(p1[2] - p2[2]) <= eps;
+      if (!coincident) {
+        float w[3] = {(n1[0] + p1[0]) - p2[0], (n1[1] + p1[1]) - p2[1], (n1[2] + p1[2]) - p2[2]};
+        float a = (n1[0] * n1[0] + n1[1] * n1[1]) + n1[2] * n1[2];
+        float b = (n1[0] * n2[0] + n1[1] * n2[1]) + n1[2] * n2[2];
+        float c = (n2[0] * n2[0] + n2[1] * n2[1]) + n2[2] * n2[2];
+        float d = (n1[0] * w[0] + n1[1] * w[1]) + n1[2] * w[2];
+        float e = (n2[0] * w[0] + n2[1] * w[1]) + n2[2] * w[2];
+        float den = a * c - b * b;
+        float sc, tc;
+        if (den < 1e-8f) { sc = 0.0f; tc = (b > c) ? (d / b) : (e / c); }
+        else { sc = (b * e - c * d) / den; tc = (a * e - b * d) / den; }
+        float q[3], dir[3];
+        for (int k = 0; k < 3; ++k) q[k] = (p1[k] + n1[k]) + sc * n1[k];
+        for (int k = 0; k < 3; ++k) dir[k] = (p2[k] + tc * n2[k]) - q[k];
+        float dl2 = (dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2];
+        if (dl2 > 0.0f && isfinite(dl2)) {
+          float dl = sqrtf(dl2);
+          dir[0] = dir[0] / dl; dir[1] = dir[1] / dl; dir[2] = dir[2] / dl;
+          float v[3] = {q[0] - p1[0], q[1] - p1[1], q[2] - p1[2]};
+          float cx = dir[1] * v[2] - dir[2] * v[1];
+          float cy = dir[2] * v[0] - dir[0] * v[2];
+          float cz = dir[0] * v[1] - dir[1] * v[0];
+          float c2 = (cx * cx + cy * cy) + cz * cz;
+          float d2 = (dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2];
+          float r = sqrtf(c2 / d2);
+          if (isfinite(r) && !(r > rmax) && !(r < rmin)) {
+            m[0] = q[0]; m[1] = q[1]; m[2] = q[2]; m[3] = dir[0]; m[4] = dir[1]; m[5] = dir[2]; m[6] = r;
+            if (d_cyl_test_params(m, tau, t)) ok = 1;
+            else { for (int k = 0; k < 12; ++k) t[k] = 0.0f; for (int k = 0; k < 7; ++k) m[k] = 0.0f; }
+          }
+        }
+      }
+    }
+    for (int k = 0; k < 7; ++k) model7[(size_t)h * 7 + k] = m[k];
+    for (int k = 0; k < 12; ++k) test12[(size_t)h * 12 + k] = t[k];
+    valid[h] = ok;
+  }
+}
+
+// ---- canonical inlier tests -----------------------------------------------------------------
+__device__ __forceinline__ bool d_plane_inlier(const float4 c, const float4 p, float tau) {
+  float d = fmaf(c.x, p.x, fmaf(c.y, p.y, fmaf(c.z, p.z, c.w)));
+  return fabsf(d) < tau;
+}
+struct CylTest { float4 u, w; float mid, half; };
+__device__ __forceinline__ bool d_cyl_inlier(const CylTest& t, const float4 p) {
+  float A = fmaf(t.u.x, p.x, fmaf(t.u.y, p.y, fmaf(t.u.z, p.z, t.u.w)));
+  float B = fmaf(t.w.x, p.x, fmaf(t.w.y, p.y, fmaf(t.w.z, p.z, t.w.w)));
+  float v = fmaf(A, A, fmaf(B, B, -t.mid));
+  return fabsf(v) < t.half;
+}
+__device__ __forceinline__ CylTest d_load_cyl_test(const float* __restrict__ t12) {
+  CylTest t;
+  t.u = make_float4(t12[0], t12[1], t12[2], t12[3]);
+  t.w = make_float4(t12[4], t12[5], t12[6], t12[7]);
+  t.mid = t12[8]; t.half = t12[9];
+  return t;
+}
+
+// ---- inlier counting ------------------------------------------------------------------------
+// Each thread owns K hypotheses in registers; the block streams its slice of the cloud through
+// shared memory and every thread reads each point as a broadcast LDS.128.  Counts stay in
+// registers for the whole slice: no per-test reduction.  grid = (point slices, hypothesis groups).
+constexpr int RC_BLOCK = 128;
+constexpr int RC_TILE = 512;  // points staged per iteration
+
+template <int K>
+__global__ void __launch_bounds__(RC_BLOCK)
+k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float4* __restrict__ coef,
+              int h_begin, int h_end, float tau, int* __restrict__ counts) {
+  __shared__ float4 s_pts[RC_TILE];
+  const int n = *n_ptr;
+  const int per = (((n + gridDim.x - 1) / gridDim.x) + RC_TILE - 1) / RC_TILE * RC_TILE;
+  const int p_begin = blockIdx.x * per, p_end = min(n, p_begin + per);
+  const int hbase = h_begin + blockIdx.y * (RC_BLOCK * K) + threadIdx.x;
+  float4 c[K];
+  int cnt[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int h = hbase + k * RC_BLOCK;
+    c[k] = (h < h_end) ? coef[h] : make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
+    cnt[k] = 0;
+  }
+  for (int base = p_begin; base < p_end; base += RC_TILE) {
+    const int m = min(RC_TILE, p_end - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RC_TILE; i += RC_BLOCK)
+      s_pts[i] = (i < m) ? pts[base + i] : make_float4(CUDART_INF_F, 0.f, 0.f, 0.f);  // never an inlier
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < RC_TILE; ++i) {
+      const float4 p = s_pts[i];
+#pragma unroll
+      for (int k = 0; k < K; ++k) cnt[k] += d_plane_inlier(c[k], p, tau) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int h = hbase + k * RC_BLOCK;
+    if (h < h_end && cnt[k]) atomicAdd(&counts[h], cnt[k]);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(RC_BLOCK)
+k_count_cyl(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float* __restrict__ test12,
+            int h_begin, int h_end, int* __restrict__ counts) {
+  __shared__ float4 s_pts[RC_TILE];
+  const int n = *n_ptr;
+  const int per = (((n + gridDim.x - 1) / gridDim.x) + RC_TILE - 1) / RC_TILE * RC_TILE;
+  const int p_begin = blockIdx.x * per, p_end = min(n, p_begin + per);
+  const int hbase = h_begin + blockIdx.y * (RC_BLOCK * K) + threadIdx.x;
+  CylTest c[K];
+  int cnt[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int h = hbase + k * RC_BLOCK;
+    if (h < h_end) c[k] = d_load_cyl_test(test12 + (size_t)h * 12);
+    else { c[k].u = make_float4(0, 0, 0, 0); c[k].w = make_float4(0, 0, 0, 0); c[k].mid = 0.f; c[k].half = 0.f; }
+    cnt[k] = 0;
+  }
+  for (int base = p_begin; base < p_end; base += RC_TILE) {
+    const int m = min(RC_TILE, p_end - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RC_TILE; i += RC_BLOCK)
+      s_pts[i] = (i < m) ? pts[base + i] : make_float4(CUDART_INF_F, 0.f, 0.f, 0.f);
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < RC_TILE; ++i) {
+      const float4 p = s_pts[i];
+#pragma unroll
+      for (int k = 0; k < K; ++k) cnt[k] += d_cyl_inlier(c[k], p) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int h = hbase + k * RC_BLOCK;
+    if (h < h_end && cnt[k]) atomicAdd(&counts[h], cnt[k]);
+  }
+}
+
+// counts[h] = -1 for degenerate hypotheses / ids outside this rank's range, 0 otherwise
+__global__ void k_counts_init(int* __restrict__ counts, const int* __restrict__ valid, int H, int h_begin, int h_end) {
+  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x)
+    counts[h] = (h >= h_begin && h < h_end && valid[h]) ? 0 : -1;
+}
+
+// best key = max over h of ((count+1) << 32) | (0xFFFFFFFF - h): max count, ties -> lowest id
+// (RandomSampleConsensus keeps a model only on a strictly larger count)
+constexpr int AM_BLOCK = 256;
+__global__ void __launch_bounds__(AM_BLOCK) k_argmax(const int* __restrict__ counts, int H, unsigned long long* key_out) {
+  __shared__ unsigned long long s[AM_BLOCK / 32];
+  unsigned long long best = 0ull;
+  for (int h = threadIdx.x; h < H; h += AM_BLOCK) {
+    unsigned long long k = ((unsigned long long)(unsigned)(counts[h] + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+    best = (k > best) ? k : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(FULL, best, o);
+    best = (t > best) ? t : best;
+  }
+  if (lane_id() == 0) s[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < AM_BLOCK / 32; ++w) best = (s[w] > best) ? s[w] : best;
+    *key_out = best;
+  }
+}
+
+// ---- selection + refit ----------------------------------------------------------------------
+// Device-resident model state (mirrors gm_model plus double-precision iterate of the cylinder).
+struct ModelState {
+  int kind, best_id, best_count, refit_count;
+  float hyp[8];
+  float coef[8];
+  float rms, pad_;
+  float test_hyp[12];   // cylinder: inlier test of the winning hypothesis (fixes the refit set)
+  float test_coef[12];  // cylinder: inlier test of the refined model (labels)
+  double q[3], dir[3], r;  // cylinder iterate
+};
+
+__global__ void k_select(const unsigned long long* __restrict__ key, int kind, int H,
+                         const float4* __restrict__ plane_coef, const float* __restrict__ model7,
+                         const float* __restrict__ test12, ModelState* ms) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long k = *key;
+  int count = (int)(unsigned)(k >> 32) - 1;
+  int id = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+  ms->kind = kind;
+  ms->refit_count = 0;
+  ms->rms = 0.f;
+  ms->pad_ = 0.f;
+  for (int i = 0; i < 8; ++i) { ms->hyp[i] = 0.f; ms->coef[i] = 0.f; }
+  for (int i = 0; i < 12; ++i) { ms->test_hyp[i] = 0.f; ms->test_coef[i] = 0.f; }
+  if (count < 0 || id < 0 || id >= H) { ms->best_id = -1; ms->best_count = -1; return; }
+  ms->best_id = id;
+  ms->best_count = count;
+  if (kind == 0) {
+    float4 c = plane_coef[id];
+    ms->hyp[0] = c.x; ms->hyp[1] = c.y; ms->hyp[2] = c.z; ms->hyp[3] = c.w;
+    for (int i = 0; i < 4; ++i) ms->coef[i] = ms->hyp[i];
+  } else {
+    for (int i = 0; i < 7; ++i) { ms->hyp[i] = model7[(size_t)id * 7 + i]; ms->coef[i] = ms->hyp[i]; }
+    for (int i = 0; i < 12; ++i) { ms->test_hyp[i] = test12[(size_t)id * 12 + i]; ms->test_coef[i] = ms->test_hyp[i]; }
+    for (int i = 0; i < 3; ++i) { ms->q[i] = ms->hyp[i]; ms->dir[i] = ms->hyp[3 + i]; }
+    ms->r = ms->hyp[6];
+  }
+}
+
+constexpr int RF_BLOCK = 256;
+
+// plane refit, pass 1: double sums {xx,xy,xz,yy,yz,zz,x,y,z,count} over the hypothesis inliers
+__global__ void __launch_bounds__(RF_BLOCK)
+k_plane_refit_partial(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const ModelState* __restrict__ ms,
+                      float tau, double* __restrict__ partials) {
+  __shared__ double sm[10 * (RF_BLOCK / 32)];
+  const int n = *n_ptr;
+  double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (ms->best_id >= 0) {
+    const float4 c = make_float4(ms->hyp[0], ms->hyp[1], ms->hyp[2], ms->hyp[3]);
+    for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += gridDim.x * RF_BLOCK) {
+      float4 p = pts[i];
+      if (d_plane_inlier(c, p, tau)) {
+        double x = p.x, y = p.y, z = p.z;
+        s[0] += x * x; s[1] += x * y; s[2] += x * z; s[3] += y * y; s[4] += y * z; s[5] += z * z;
+        s[6] += x; s[7] += y; s[8] += z; s[9] += 1.0;
+      }
+    }
+  }
+  block_sum<10, RF_BLOCK>(s, sm);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 10; ++k) partials[blockIdx.x * 10 + k] = s[k];
+}
+
+__global__ void k_plane_refit_final(const double* __restrict__ partials, int nblocks, ModelState* ms) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (ms->best_id < 0) return;
+  double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < nblocks; ++b)
+    for (int k = 0; k < 10; ++k) s[k] += partials[b * 10 + k];
+  long long cnt = (long long)(s[9] + 0.5);
+  ms->refit_count = (int)cnt;
+  if (cnt <= 3) return;
+  double c = (double)cnt, mx = s[6] / c, my = s[7] / c, mz = s[8] / c;
+  double C[9] = {s[0] / c - mx * mx, s[1] / c - mx * my, s[2] / c - mx * mz, 0, s[3] / c - my * my, s[4] / c - my * mz, 0, 0, s[5] / c - mz * mz};
+  C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+  double vals[3], vecs[9];
+  d_jacobi3(C, vals, vecs);
+  double nx = vecs[0], ny = vecs[3], nz = vecs[6];
+  if (nx * ms->hyp[0] + ny * ms->hyp[1] + nz * ms->hyp[2] < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+  ms->coef[0] = (float)nx; ms->coef[1] = (float)ny; ms->coef[2] = (float)nz;
+  ms->coef[3] = (float)(-(nx * mx + ny * my + nz * mz));
+  ms->rms = (float)sqrt(fmax(vals[0], 0.0));
+}
+
+__device__ __forceinline__ void d_perp_basis_d(const double dir[3], double u[3], double w[3]) {
+  double ax = fabs(dir[0]), ay = fabs(dir[1]), az = fabs(dir[2]);
+  int k = 0; double m = ax;
+  if (ay < m) { k = 1; m = ay; }
+  if (az < m) { k = 2; m = az; }
+  double c[3];
+  if (k == 0) { c[0] = 0; c[1] = dir[2]; c[2] = -dir[1]; }
+  else if (k == 1) { c[0] = -dir[2]; c[1] = 0; c[2] = dir[0]; }
+  else { c[0] = dir[1]; c[1] = -dir[0]; c[2] = 0; }
+  double l = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  u[0] = c[0] / l; u[1] = c[1] / l; u[2] = c[2] / l;
+  w[0] = dir[1] * u[2] - dir[2] * u[1]; w[1] = dir[2] * u[0] - dir[0] * u[2]; w[2] = dir[0] * u[1] - dir[1] * u[0];
+}
+
+// cylinder refit, one Gauss-Newton pass: sums of J^T J (15), J^T r (5), count, sum r^2 over the
+// FIXED inlier set of the winning hypothesis, evaluated at the current iterate (ms->q,dir,r).
+constexpr int GN_NV = 22;
+__global__ void __launch_bounds__(RF_BLOCK)
+k_cyl_gn_partial(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const ModelState* __restrict__ ms,
+                 double* __restrict__ partials) {
+  __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
+  const int n = *n_ptr;
+  double s[GN_NV];
+#pragma unroll
+  for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
+  if (ms->best_id >= 0) {
+    const CylTest t = d_load_cyl_test(ms->test_hyp);
+    const double q0 = ms->q[0], q1 = ms->q[1], q2 = ms->q[2], r = ms->r;
+    double dir[3] = {ms->dir[0], ms->dir[1], ms->dir[2]}, u[3], w[3];
+    d_perp_basis_d(dir, u, w);
+    for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += gridDim.x * RF_BLOCK) {
+      float4 p = pts[i];
+      if (!d_cyl_inlier(t, p)) continue;
+      s[20] += 1.0;
+      double vx = (double)p.x - q0, vy = (double)p.y - q1, vz = (double)p.z - q2;
+      double A = u[0] * vx + u[1] * vy + u[2] * vz;
+      double B = w[0] * vx + w[1] * vy + w[2] * vz;
+      double tt = dir[0] * vx + dir[1] * vy + dir[2] * vz;
+      double dist = sqrt(A * A + B * B);
+      if (!(dist > 1e-12)) continue;
+      double res = dist - r;
+      s[21] += res * res;
+      double J[5] = {-A / dist, -B / dist, -A * tt / dist, -B * tt / dist, -1.0};
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+#pragma unroll
+        for (int b = a; b < 5; ++b) s[idx++] += J[a] * J[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
+    }
+  }
+  block_sum<GN_NV, RF_BLOCK>(s, sm);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < GN_NV; ++k) partials[blockIdx.x * GN_NV + k] = s[k];
+}
+
+__device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
+  for (int c = 0; c < 5; ++c) {
+    int piv = c; double best = fabs(A[c][c]);
+    for (int r = c + 1; r < 5; ++r) if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
+    if (!(best > 1e-300)) return false;
+    if (piv != c) {
+      for (int k = 0; k < 5; ++k) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+      double t = b[c]; b[c] = b[piv]; b[piv] = t;
+    }
+    for (int r = c + 1; r < 5; ++r) {
+      double f = A[r][c] / A[c][c];
+      for (int k = c; k < 5; ++k) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = 4; r >= 0; --r) {
+    double s = b[r];
+    for (int k = r + 1; k < 5; ++k) s -= A[r][k] * x[k];
+    x[r] = s / A[r][r];
+  }
+  return true;
+}
+
+// update = 1: solve the normal equations and move the iterate; update = 0: final pass, only
+// publish count / rms / float coefficients / refined inlier test.
+__global__ void k_cyl_gn_final(const double* __restrict__ partials, int nblocks, int update, float tau, ModelState* ms) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (ms->best_id < 0) return;
+  double s[GN_NV];
+  for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
+  for (int b = 0; b < nblocks; ++b)
+    for (int k = 0; k < GN_NV; ++k) s[k] += partials[b * GN_NV + k];
+  long long cnt = (long long)(s[20] + 0.5);
+  ms->refit_count = (int)cnt;
+  if (cnt <= 5) return;  // model unchanged
+  if (update) {
+    double JTJ[5][5], rhs[5], x[5];
+    int idx = 0;
+    for (int a = 0; a < 5; ++a) for (int b = a; b < 5; ++b) { JTJ[a][b] = s[idx]; JTJ[b][a] = s[idx]; ++idx; }
+    for (int a = 0; a < 5; ++a) rhs[a] = -s[15 + a];
+    if (!d_solve5(JTJ, rhs, x)) return;
+    double dir[3] = {ms->dir[0], ms->dir[1], ms->dir[2]}, u[3], w[3];
+    d_perp_basis_d(dir, u, w);
+    for (int k = 0; k < 3; ++k) ms->q[k] += x[0] * u[k] + x[1] * w[k];
+    for (int k = 0; k < 3; ++k) dir[k] += x[2] * u[k] + x[3] * w[k];
+    double dl = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    for (int k = 0; k < 3; ++k) ms->dir[k] = dir[k] / dl;
+    ms->r += x[4];
+  } else {
+    ms->rms = (float)sqrt(s[21] / (double)cnt);
+    for (int k = 0; k < 3; ++k) { ms->coef[k] = (float)ms->q[k]; ms->coef[3 + k] = (float)ms->dir[k]; }
+    ms->coef[6] = (float)ms->r;
+    float t12[12];
+    if (d_cyl_test_params(ms->coef, tau, t12)) for (int k = 0; k < 12; ++k) ms->test_coef[k] = t12[k];
+  }
+}
+
+// labels from the refined models: 1 = plane inlier, else 2 = cylinder inlier, else 0
+__global__ void k_label(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const ModelState* __restrict__ plane,
+                        const ModelState* __restrict__ cyl, int have_plane, int have_cyl, float tau, unsigned char* __restrict__ labels) {
+  const int n = *n_ptr;
+  const bool hp = have_plane && plane->best_id >= 0, hc = have_cyl && cyl->best_id >= 0;
+  float4 pc = make_float4(0, 0, 0, 0);
+  CylTest ct;
+  ct.u = make_float4(0, 0, 0, 0); ct.w = ct.u; ct.mid = 0.f; ct.half = 0.f;
+  if (hp) pc = make_float4(plane->coef[0], plane->coef[1], plane->coef[2], plane->coef[3]);
+  if (hc) ct = d_load_cyl_test(cyl->test_coef);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    unsigned char l = 0;
+    if (hp && d_plane_inlier(pc, p, tau)) l = 1;
+    else if (hc && d_cyl_inlier(ct, p)) l = 2;
+    labels[i] = l;
+  }
+}
+
+}  // namespace gm

@@ -1,0 +1,624 @@
+// gm_stages.cuh — kernels of the reference-pinned stages a1..a5.
+// Compiled with -fmad=false: a*b+c is never contracted, so plain expressions reproduce the
+// unfused PCL/FLANN arithmetic that integer decisions depend on (neighbour sets, voxel keys);
+// fused multiply-adds appear only where fmaf() is written explicitly.
+#pragma once
+#include "gm_device.cuh"
+#include <math_constants.h>
+
+namespace gm {
+
+// Device-resident per-scan state: sizes flow from stage to stage without host round trips.
+struct DevState {
+  int n_input, n_crop, n_valid, n_voxels, n_cells, voxel_overflow, nn_oor, error;
+  int bbox_min[3], bbox_max[3];  // ordered-int encoded floats (compacted cloud)
+  int min_b[3], div_b[3], mul[3];
+  float v_inv;
+  int n_sorted_finite;  // cropped points with finite coordinates (sorted before the NaN tail)
+};
+
+struct GridSpec {
+  float origin;    // same for x,y,z: -bound
+  float inv_cell;  // 1/cell
+  float cell;
+  int dim;         // cells per axis
+  unsigned ncells; // dim^3 (sentinel key for non-finite points)
+};
+
+constexpr int CP_BLOCK = 256;
+constexpr int CP_IPT = 4;
+constexpr int CP_TILE = CP_BLOCK * CP_IPT;
+
+__device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_begin_scan(DevState* st, int n_input) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->n_input = n_input; st->n_crop = 0; st->n_valid = 0; st->n_voxels = 0; st->n_cells = 0;
+    st->voxel_overflow = 0; st->nn_oor = 0; st->error = 0; st->n_sorted_finite = 0;
+    for (int a = 0; a < 3; ++a) {
+      st->bbox_min[a] = float_to_ordered(CUDART_INF_F);
+      st->bbox_max[a] = float_to_ordered(-CUDART_INF_F);
+      st->min_b[a] = 0; st->div_b[a] = 0; st->mul[a] = 0;
+    }
+    st->v_inv = 0.f;
+  }
+}
+
+__global__ void k_set_w_one(float4* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i].w = 1.0f;
+}
+
+// a1 chopCloud / pcl::CropBox (src/tunnel_processing.cpp:39-49): stable compaction of
+// the points with every coordinate in [lo,hi]; NaN handling per is_dense.
+__global__ void __launch_bounds__(CP_BLOCK)
+k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, float4* __restrict__ out,
+       unsigned long long* state, DevState* st) {
+  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
+  const int tile = blockIdx.x, base = tile * CP_TILE;
+  if (base >= n) return;
+  float4 p[CP_IPT];
+  bool f[CP_IPT];
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    f[j] = false;
+    if (i < n) {
+      p[j] = in[i];
+      bool drop = (p[j].x < lo) || (p[j].y < lo) || (p[j].z < lo) || (p[j].x > hi) || (p[j].y > hi) || (p[j].z > hi);
+      if (!is_dense && !finite3(p[j].x, p[j].y, p[j].z)) drop = true;
+      f[j] = !drop;
+    }
+  }
+  unsigned ranks[CP_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j)
+    if (f[j]) out[ranks[j]] = p[j];
+  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_crop = (int)total;
+}
+
+// Neighbour-grid cell key of every cropped point (sentinel ncells for non-finite points, which
+// are never anyone's neighbour).
+__global__ void k_cell_keys(const float4* __restrict__ pts, const int* __restrict__ n_ptr, GridSpec g,
+                            unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    unsigned key = g.ncells;
+    if (finite3(p.x, p.y, p.z)) {
+      int cx = min(max((int)floorf((p.x - g.origin) * g.inv_cell), 0), g.dim - 1);
+      int cy = min(max((int)floorf((p.y - g.origin) * g.inv_cell), 0), g.dim - 1);
+      int cz = min(max((int)floorf((p.z - g.origin) * g.inv_cell), 0), g.dim - 1);
+      key = (unsigned)cx + (unsigned)g.dim * ((unsigned)cy + (unsigned)g.dim * (unsigned)cz);
+    }
+    keys[i] = key;
+    idx[i] = (unsigned)i;
+  }
+}
+
+// After the sort: gather points into cell order (w := original index), number the occupied cells
+// and record each cell's key and first sorted position (stable compaction of the "head" flags).
+__global__ void __launch_bounds__(CP_BLOCK)
+k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
+             const int* __restrict__ n_ptr, unsigned ncells, float4* __restrict__ sorted_pts, int* __restrict__ cell_id,
+             unsigned* __restrict__ ucell_key, int* __restrict__ ucell_start, unsigned long long* state, DevState* st) {
+  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
+  const int n = *n_ptr;
+  const int tile = blockIdx.x, base = tile * CP_TILE;
+  if (base >= n) return;
+  bool f[CP_IPT];
+  unsigned key[CP_IPT];
+  int nfinite_local = 0;
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    f[j] = false;
+    key[j] = 0;
+    if (i < n) {
+      key[j] = skeys[i];
+      unsigned prev = (i > 0) ? skeys[i - 1] : 0xFFFFFFFFu;
+      f[j] = (i == 0) || (key[j] != prev);
+      unsigned src = sidx[i];
+      float4 p = pts[src];
+      p.w = __int_as_float((int)src);
+      sorted_pts[i] = p;
+      if (key[j] < ncells) {
+        // last finite position + 1 == number of finite points (sentinel keys sort last)
+        if (i + 1 == n || skeys[i + 1] >= ncells) nfinite_local = i + 1;
+      }
+    }
+  }
+  if (nfinite_local) st->n_sorted_finite = nfinite_local;
+  unsigned ranks[CP_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    if (i < n) {
+      int id = f[j] ? (int)ranks[j] : (int)ranks[j] - 1;
+      cell_id[i] = id;
+      if (f[j]) { ucell_key[id] = key[j]; ucell_start[id] = i; }
+    }
+  }
+  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_cells = (int)total;
+}
+
+__device__ __forceinline__ int lower_bound_u32(const unsigned* __restrict__ a, int n, unsigned key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Sorted-position range [start,end) of the cells kx0..kx1 of row (cy,cz); empty if out of the grid.
+__device__ __forceinline__ int2 cell_run(const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
+                                         int U, int n_finite, int dim, int x0, int x1, int cy, int cz) {
+  if (cy < 0 || cz < 0 || cy >= dim || cz >= dim) return make_int2(0, 0);
+  x0 = max(x0, 0); x1 = min(x1, dim - 1);
+  if (x0 > x1) return make_int2(0, 0);
+  unsigned rowbase = (unsigned)dim * ((unsigned)cy + (unsigned)dim * (unsigned)cz);
+  int a = lower_bound_u32(ucell_key, U, rowbase + (unsigned)x0);
+  int b = lower_bound_u32(ucell_key, U, rowbase + (unsigned)x1 + 1u);
+  int s = (a < U) ? min(ucell_start[a], n_finite) : n_finite;
+  int e = (b < U) ? min(ucell_start[b], n_finite) : n_finite;
+  return make_int2(s, e);
+}
+
+// For every occupied cell: the 9 sorted-position runs (one per (dy,dz) row, x-1..x+1) that cover
+// its 27-cell neighbourhood.
+__global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
+                            const DevState* __restrict__ st, GridSpec g, int2* __restrict__ runs) {
+  const int U = st->n_cells, nf = st->n_sorted_finite;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < U * 9; t += gridDim.x * blockDim.x) {
+    int j = t / 9, k = t - j * 9;
+    unsigned key = ucell_key[j];
+    int2 r = make_int2(0, 0);
+    if (key < g.ncells) {
+      int cx = (int)(key % (unsigned)g.dim);
+      int cy = (int)((key / (unsigned)g.dim) % (unsigned)g.dim);
+      int cz = (int)(key / ((unsigned)g.dim * (unsigned)g.dim));
+      r = cell_run(ucell_key, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (k % 3) - 1, cz + (k / 3) - 1);
+    }
+    runs[t] = r;
+  }
+}
+
+// ---- pcl::eigen33 smallest eigenpair, float (common/impl/eigen.hpp) -------------
+__device__ __forceinline__ void d_compute_roots2(float b, float c, float roots[3]) {
+  roots[0] = 0.0f;
+  float d = b * b - 4.0f * c;
+  if (d < 0.0f) d = 0.0f;
+  float sd = sqrtf(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+__device__ __forceinline__ void d_swapf(float& a, float& b) { float t = a; a = b; b = t; }
+
+__device__ void d_compute_roots(float m00, float m01, float m02, float m11, float m12, float m22, float roots[3]) {
+  float c0 = m00 * m11 * m22 + 2.0f * m01 * m02 * m12 - m00 * m12 * m12 - m11 * m02 * m02 - m22 * m01 * m01;
+  float c1 = m00 * m11 - m01 * m01 + m00 * m22 - m02 * m02 + m11 * m22 - m12 * m12;
+  float c2 = m00 + m11 + m22;
+  if (fabsf(c0) < 1.1920928955078125e-07f) {
+    d_compute_roots2(c2, c1, roots);
+  } else {
+    const float s_inv3 = 1.0f / 3.0f;
+    const float s_sqrt3 = 1.7320508075688772f;
+    float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+    float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0f) q = 0.0f;
+    float rho = sqrtf(-a_over_3);
+    float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+    float sin_theta, cos_theta;
+    sincosf(theta, &sin_theta, &cos_theta);
+    roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    if (roots[0] >= roots[1]) d_swapf(roots[0], roots[1]);
+    if (roots[1] >= roots[2]) {
+      d_swapf(roots[1], roots[2]);
+      if (roots[0] >= roots[1]) d_swapf(roots[0], roots[1]);
+    }
+    if (roots[0] <= 0.0f) d_compute_roots2(c2, c1, roots);
+  }
+}
+
+__device__ void d_eigen33_smallest(float c00, float c01, float c02, float c11, float c12, float c22,
+                                   float& eigenvalue, float& ex, float& ey, float& ez) {
+  float scale = fmaxf(fmaxf(fmaxf(fabsf(c00), fabsf(c01)), fmaxf(fabsf(c02), fabsf(c11))), fmaxf(fabsf(c12), fabsf(c22)));
+  if (scale <= 1.17549435e-38f) scale = 1.0f;
+  float m00 = c00 / scale, m01 = c01 / scale, m02 = c02 / scale, m11 = c11 / scale, m12 = c12 / scale, m22 = c22 / scale;
+  float roots[3];
+  d_compute_roots(m00, m01, m02, m11, m12, m22, roots);
+  eigenvalue = roots[0] * scale;
+  m00 -= roots[0]; m11 -= roots[0]; m22 -= roots[0];
+  // rows r0=(m00,m01,m02) r1=(m01,m11,m12) r2=(m02,m12,m22)
+  float v1x = m01 * m12 - m02 * m11, v1y = m02 * m01 - m00 * m12, v1z = m00 * m11 - m01 * m01;
+  float v2x = m01 * m22 - m02 * m12, v2y = m02 * m02 - m00 * m22, v2z = m00 * m12 - m01 * m02;
+  float v3x = m11 * m22 - m12 * m12, v3y = m12 * m02 - m01 * m22, v3z = m01 * m12 - m11 * m02;
+  float l1 = v1x * v1x + v1y * v1y + v1z * v1z;
+  float l2 = v2x * v2x + v2y * v2y + v2z * v2z;
+  float l3 = v3x * v3x + v3y * v3y + v3z * v3z;
+  float vx, vy, vz, l;
+  if (l1 >= l2 && l1 >= l3) { vx = v1x; vy = v1y; vz = v1z; l = l1; }
+  else if (l2 >= l1 && l2 >= l3) { vx = v2x; vy = v2y; vz = v2z; l = l2; }
+  else { vx = v3x; vy = v3y; vz = v3z; l = l3; }
+  float s = sqrtf(l);
+  ex = vx / s; ey = vy / s; ez = vz / s;
+}
+
+// a2 pcl::NormalEstimation::compute, radius mode (src/tunnel_processing.cpp:58-70).
+// One thread per point in cell-sorted order: neighbouring lanes sit in the same or adjacent cells,
+// so their candidate runs coincide and the candidate loads are warp-coherent L1 hits.
+// The neighbour predicate is the exact FLANN L2_Simple form (unfused, strict <).
+constexpr int NRM_BLOCK = 128;
+__global__ void __launch_bounds__(NRM_BLOCK)
+k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs,
+          const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count) {
+  const int n = *n_ptr;
+  const int i = blockIdx.x * NRM_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = sp[i];
+  const int orig = __float_as_int(p.w);
+  const float qnan = CUDART_NAN_F;
+  float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  if (finite3(p.x, p.y, p.z)) {
+    const int2* rr = runs + (size_t)cell_id[i] * 9;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+      const int2 r = rr[k];
+#pragma unroll 4
+      for (int t = r.x; t < r.y; ++t) {
+        const float4 q = sp[t];
+        float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+        float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
+        if (d2 < r2) {
+          a0 = fmaf(q.x, q.x, a0); a1 = fmaf(q.x, q.y, a1); a2 = fmaf(q.x, q.z, a2);
+          a3 = fmaf(q.y, q.y, a3); a4 = fmaf(q.y, q.z, a4); a5 = fmaf(q.z, q.z, a5);
+          a6 += q.x; a7 += q.y; a8 += q.z;
+          ++cnt;
+        }
+      }
+    }
+    if (cnt >= 3) {
+      float c = (float)cnt;
+      a0 /= c; a1 /= c; a2 /= c; a3 /= c; a4 /= c; a5 /= c; a6 /= c; a7 /= c; a8 /= c;
+      float c00 = a0 - a6 * a6, c01 = a1 - a6 * a7, c02 = a2 - a6 * a8;
+      float c11 = a3 - a7 * a7, c12 = a4 - a7 * a8, c22 = a5 - a8 * a8;
+      float ev, nx, ny, nz;
+      d_eigen33_smallest(c00, c01, c02, c11, c12, c22, ev, nx, ny, nz);
+      float eig_sum = c00 + c11 + c22;
+      float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+      float vx = 0.0f - p.x, vy = 0.0f - p.y, vz = 0.0f - p.z;
+      float cos_theta = vx * nx + vy * ny + vz * nz;
+      if (cos_theta < 0.0f) { nx *= -1.0f; ny *= -1.0f; nz *= -1.0f; }
+      o0 = make_float4(nx, ny, nz, 0.f);
+      o1 = make_float4(curv, 0.f, 0.f, 0.f);
+    }
+  }
+  normals[2 * (size_t)orig] = o0;
+  normals[2 * (size_t)orig + 1] = o1;
+  nbr_count[orig] = cnt;
+}
+
+// a3 removeNaNNormalsFromPointCloud + ExtractIndices (src/tunnel_processing.cpp:74-85): stable
+// compaction of cloud and normals by isfinite(nx,ny,nz); also the bounding box of the survivors
+// (pcl::getMinMax3D of the VoxelGrid that follows).
+__global__ void __launch_bounds__(CP_BLOCK)
+k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ normals, const int* __restrict__ n_ptr,
+                float4* __restrict__ pts_c, float4* __restrict__ normals_c, int* __restrict__ valid_map,
+                unsigned long long* state, DevState* st) {
+  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
+  __shared__ float s_red[6][CP_BLOCK / 32];
+  const int n = *n_ptr;
+  const int tile = blockIdx.x, base = tile * CP_TILE;
+  if (base >= n) return;
+  bool f[CP_IPT];
+  float4 p[CP_IPT], n0[CP_IPT], n1[CP_IPT];
+  float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    f[j] = false;
+    if (i < n) {
+      p[j] = pts[i];
+      n0[j] = normals[2 * (size_t)i];
+      n1[j] = normals[2 * (size_t)i + 1];
+      f[j] = finite3(n0[j].x, n0[j].y, n0[j].z);
+      if (f[j]) {
+        mn[0] = fminf(mn[0], p[j].x); mn[1] = fminf(mn[1], p[j].y); mn[2] = fminf(mn[2], p[j].z);
+        mx[0] = fmaxf(mx[0], p[j].x); mx[1] = fmaxf(mx[1], p[j].y); mx[2] = fmaxf(mx[2], p[j].z);
+      }
+    }
+  }
+  unsigned ranks[CP_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    if (i < n) {
+      valid_map[i] = f[j] ? (int)ranks[j] : -1;
+      if (f[j]) {
+        pts_c[ranks[j]] = p[j];
+        normals_c[2 * (size_t)ranks[j]] = n0[j];
+        normals_c[2 * (size_t)ranks[j] + 1] = n1[j];
+      }
+    }
+  }
+  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_valid = (int)total;
+  // block bbox -> global (min/max are order independent: deterministic)
+  const int w = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = warp_min(mn[a]), hi = warp_max(mx[a]);
+    if (lane_id() == 0) { s_red[a][w] = lo; s_red[3 + a][w] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+    for (int ww = 0; ww < CP_BLOCK / 32; ++ww) { lo = fminf(lo, s_red[threadIdx.x][ww]); hi = fmaxf(hi, s_red[3 + threadIdx.x][ww]); }
+    if (lo <= hi) {
+      atomicMin(&st->bbox_min[threadIdx.x], float_to_ordered(lo));
+      atomicMax(&st->bbox_max[threadIdx.x], float_to_ordered(hi));
+    }
+  }
+}
+
+// Bounding box only (used when the compacted cloud was injected).
+__global__ void k_bbox(const float4* __restrict__ pts, const int* __restrict__ n_ptr, DevState* st) {
+  const int n = *n_ptr;
+  float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = warp_min(mn[a]), hi = warp_max(mx[a]);
+    if (lane_id() == 0 && lo <= hi) {
+      atomicMin(&st->bbox_min[a], float_to_ordered(lo));
+      atomicMax(&st->bbox_max[a], float_to_ordered(hi));
+    }
+  }
+}
+
+// a4 pcl::VoxelGrid lattice: min_b, div_b, divb_mul and the overflow rule.
+__global__ void k_voxel_setup(DevState* st, float inv) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->v_inv = inv;
+  if (st->n_valid <= 0) { st->n_voxels = 0; return; }
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; ++a) { mn[a] = ordered_to_float(st->bbox_min[a]); mx[a] = ordered_to_float(st->bbox_max[a]); }
+  long long dx = (long long)((mx[0] - mn[0]) * inv) + 1;
+  long long dy = (long long)((mx[1] - mn[1]) * inv) + 1;
+  long long dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > 2147483647LL) st->voxel_overflow = 1;
+  for (int a = 0; a < 3; ++a) {
+    int lo = (int)floorf(mn[a] * inv), hi = (int)floorf(mx[a] * inv);
+    st->min_b[a] = lo;
+    st->div_b[a] = hi - lo + 1;
+  }
+  st->mul[0] = 1; st->mul[1] = st->div_b[0]; st->mul[2] = st->div_b[0] * st->div_b[1];
+}
+
+// Voxel key per compacted point: ijk = int(floor(p*inv) - float(min_b)); key = ijk . divb_mul
+__global__ void k_voxel_keys(const float4* __restrict__ pts, const DevState* __restrict__ st,
+                             unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point) {
+  const int n = st->n_valid;
+  const float inv = st->v_inv;
+  const float mb0 = (float)st->min_b[0], mb1 = (float)st->min_b[1], mb2 = (float)st->min_b[2];
+  const int m1 = st->mul[1], m2 = st->mul[2];
+  const bool overflow = st->voxel_overflow != 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    int ijk0 = (int)(floorf(p.x * inv) - mb0);
+    int ijk1 = (int)(floorf(p.y * inv) - mb1);
+    int ijk2 = (int)(floorf(p.z * inv) - mb2);
+    int key = overflow ? i : (ijk0 + ijk1 * m1 + ijk2 * m2);
+    keys[i] = (unsigned)key;
+    idx[i] = (unsigned)i;
+    key_of_point[i] = key;
+  }
+}
+
+// After the voxel sort: number the voxels (ascending key), record their first sorted position and
+// the voxel rank of every point.
+__global__ void __launch_bounds__(CP_BLOCK)
+k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, int* __restrict__ assign,
+              int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, DevState* st) {
+  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
+  const int n = st->n_valid;
+  const int tile = blockIdx.x, base = tile * CP_TILE;
+  if (base >= n) return;
+  bool f[CP_IPT];
+  unsigned key[CP_IPT];
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    f[j] = false; key[j] = 0;
+    if (i < n) {
+      key[j] = skeys[i];
+      f[j] = (i == 0) || (key[j] != skeys[i - 1]);
+    }
+  }
+  unsigned ranks[CP_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    if (i < n) {
+      int id = f[j] ? (int)ranks[j] : (int)ranks[j] - 1;
+      assign[sidx[i]] = id;
+      if (f[j]) { vox_start[id] = i; vox_key[id] = (int)key[j]; }
+    }
+  }
+  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_voxels = (int)total;
+}
+
+// Centroid per voxel: float sum over the members in ascending original index (stable sort order),
+// divided by float(count)  (bit-reproducible, matches the oracle's canonical order).
+__global__ void k_voxel_centroids(const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
+                                  const int* __restrict__ vox_start, const DevState* __restrict__ st,
+                                  float4* __restrict__ centroids, int* __restrict__ vox_count) {
+  const int V = st->n_voxels, n = st->n_valid;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < V; j += gridDim.x * blockDim.x) {
+    int s = vox_start[j], e = (j + 1 < V) ? vox_start[j + 1] : n;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    int t = s;
+    for (; t + 4 <= e; t += 4) {
+      float4 q0 = pts[sidx[t]], q1 = pts[sidx[t + 1]], q2 = pts[sidx[t + 2]], q3 = pts[sidx[t + 3]];
+      sx += q0.x; sy += q0.y; sz += q0.z;
+      sx += q1.x; sy += q1.y; sz += q1.z;
+      sx += q2.x; sy += q2.y; sz += q2.z;
+      sx += q3.x; sy += q3.y; sz += q3.z;
+    }
+    for (; t < e; ++t) { float4 q = pts[sidx[t]]; sx += q.x; sy += q.y; sz += q.z; }
+    float c = (float)(e - s);
+    centroids[j] = make_float4(sx / c, sy / c, sz / c, 1.0f);
+    vox_count[j] = e - s;
+  }
+}
+
+// a4 second half: kdtree->nearestKSearch(centroid, 1) (src/tunnel_processing.cpp:239) as an exact
+// expanding-ring search over the neighbour grid of the PRE-compaction cloud (quirk B.3), FLANN
+// L2_Simple distance, ties -> lowest original index.  Then normals->at(index) (:247-249).
+// mode 0 (reference-faithful): index = pre-compaction index, looked up in the COMPACTED normals;
+// index >= n_valid is counted in nn_oor (the reference would throw).  mode 1 (fixed): only points
+// that survived compaction are candidates and the index is the compacted one.
+__global__ void k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
+                           const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
+                           const int* __restrict__ valid_map, const float4* __restrict__ normals_c, GridSpec g,
+                           int mode, DevState* st, int* __restrict__ nn_idx, float4* __restrict__ nn_normal) {
+  const int V = st->n_voxels, U = st->n_cells, nf = st->n_sorted_finite, nvalid = st->n_valid;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < V; j += gridDim.x * blockDim.x) {
+    const float4 c = centroids[j];
+    int cx = min(max((int)floorf((c.x - g.origin) * g.inv_cell), 0), g.dim - 1);
+    int cy = min(max((int)floorf((c.y - g.origin) * g.inv_cell), 0), g.dim - 1);
+    int cz = min(max((int)floorf((c.z - g.origin) * g.inv_cell), 0), g.dim - 1);
+    float best = CUDART_INF_F;
+    int bi = -1;
+    for (int k = 0; k <= g.dim; ++k) {
+      for (int dz = -k; dz <= k; ++dz)
+        for (int dy = -k; dy <= k; ++dy) {
+          const bool shell = (max(abs(dy), abs(dz)) == k);
+          // on the shell rows take the whole x span, inside only the two end cells
+          for (int part = 0; part < (shell || k == 0 ? 1 : 2); ++part) {
+            int x0 = shell ? cx - k : (part == 0 ? cx - k : cx + k);
+            int x1 = shell ? cx + k : x0;
+            int2 r = cell_run(ucell_key, ucell_start, U, nf, g.dim, x0, x1, cy + dy, cz + dz);
+            for (int t = r.x; t < r.y; ++t) {
+              const float4 q = sp[t];
+              int src = __float_as_int(q.w);
+              int id = src;
+              if (mode == 1) { id = valid_map[src]; if (id < 0) continue; }
+              float dx = c.x - q.x, dyy = c.y - q.y, dzz = c.z - q.z;
+              float d2 = (dx * dx + dyy * dyy) + dzz * dzz;
+              if (d2 < best || (d2 == best && id < bi)) { best = d2; bi = id; }
+            }
+          }
+        }
+      // every unexplored cell is at Chebyshev distance >= k+1 from the query cell, hence every
+      // point in it is at least k*cell away from the query
+      double lim = (double)k * (double)g.cell * 0.999;
+      if (bi >= 0 && (double)best <= lim * lim) break;
+    }
+    nn_idx[j] = bi;
+    const float qnan = CUDART_NAN_F;
+    float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
+    if (bi >= 0 && bi < nvalid) { o0 = normals_c[2 * (size_t)bi]; o1 = normals_c[2 * (size_t)bi + 1]; }
+    else atomicAdd(&st->nn_oor, 1);
+    nn_normal[2 * (size_t)j] = o0;
+    nn_normal[2 * (size_t)j + 1] = o1;
+  }
+}
+
+// ---- cyclic Jacobi, double, symmetric 3x3 -> ascending eigenvalues / column eigenvectors ------
+// Stand-in for Eigen::SelfAdjointEigenSolver (src/tunnel_processing.cpp:129).
+// Sign convention: largest-|component| of each eigenvector positive.
+__device__ void d_jacobi3(const double Ain[9], double vals[3], double vecs[9]) {
+  double A[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = Ain[i * 3 + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+      if (A[p][q] == 0.0) continue;
+      double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      double t = ((theta >= 0.0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      for (int k = 0; k < 3; ++k) { double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+      for (int k = 0; k < 3; ++k) { double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+      for (int k = 0; k < 3; ++k) { double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+    }
+  }
+  int order[3] = {0, 1, 2};
+  double d[3] = {A[0][0], A[1][1], A[2][2]};
+  // stable insertion sort by eigenvalue
+  for (int i = 1; i < 3; ++i) {
+    int o = order[i], j = i - 1;
+    while (j >= 0 && d[order[j]] > d[o]) { order[j + 1] = order[j]; --j; }
+    order[j + 1] = o;
+  }
+  for (int k = 0; k < 3; ++k) {
+    int c = order[k];
+    vals[k] = d[c];
+    double v[3] = {V[0][c], V[1][c], V[2][c]};
+    double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    int big = 0;
+    if (fabs(v[1]) > fabs(v[big])) big = 1;
+    if (fabs(v[2]) > fabs(v[big])) big = 2;
+    double sgn = (v[big] < 0.0) ? -1.0 : 1.0;
+    for (int r = 0; r < 3; ++r) vecs[r * 3 + k] = sgn * v[r] / n;
+  }
+}
+
+// a5 getLocalFrame (src/tunnel_processing.cpp:92-148), diagonal form of the dense weights*normals
+// product.  w_i = float(exp((double(curv_i) + 0.001/wf)^2)); Wn = w_i*n_i in float; the 3x3
+// scatter sum is accumulated in double (fixed grid, fixed tree -> reproducible).
+constexpr int FR_BLOCK = 256;
+__global__ void __launch_bounds__(FR_BLOCK)
+k_frame_partial(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, double shift, double* __restrict__ partials) {
+  __shared__ double sm[6 * (FR_BLOCK / 32)];
+  const int n = *n_ptr;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * FR_BLOCK + threadIdx.x; i < n; i += gridDim.x * FR_BLOCK) {
+    float4 n0 = normals_c[2 * (size_t)i];
+    float curv = normals_c[2 * (size_t)i + 1].x;
+    double t = (double)curv + shift;
+    float w = (float)exp(t * t);
+    float a = w * n0.x, b = w * n0.y, c = w * n0.z;
+    s[0] += (double)a * (double)a; s[1] += (double)a * (double)b; s[2] += (double)a * (double)c;
+    s[3] += (double)b * (double)b; s[4] += (double)b * (double)c; s[5] += (double)c * (double)c;
+  }
+  block_sum<6, FR_BLOCK>(s, sm);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 6; ++k) partials[blockIdx.x * 6 + k] = s[k];
+}
+
+struct FrameOut { float vals[3]; float vecs[9]; float scatter[9]; };
+
+__global__ void k_frame_final(const double* __restrict__ partials, int nblocks, FrameOut* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < nblocks; ++b)
+    for (int k = 0; k < 6; ++k) s[k] += partials[b * 6 + k];
+  float Sf[9] = {(float)s[0], (float)s[1], (float)s[2], (float)s[1], (float)s[3], (float)s[4], (float)s[2], (float)s[4], (float)s[5]};
+  double Sd[9], vals[3], vecs[9];
+  for (int k = 0; k < 9; ++k) { Sd[k] = Sf[k]; out->scatter[k] = Sf[k]; }
+  d_jacobi3(Sd, vals, vecs);
+  for (int k = 0; k < 3; ++k) out->vals[k] = (float)vals[k];
+  for (int k = 0; k < 9; ++k) out->vecs[k] = (float)vecs[k];
+}
+
+}  // namespace gm

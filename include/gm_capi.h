@@ -1,0 +1,227 @@
+/* gm_capi.h — C-ABI of the B200-native geometric_mapping per-scan hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / PCL / Eigen / ROS types.
+ * Each entry point replaces one reference seam (file:line relative to the reference repo
+ * wangqiaoli/geometric_mapping); INTEGRATION.md shows the binding the reference's
+ * src/geometric_mapping.cpp:cloud_cb would add.
+ *
+ * Conventions
+ *   - Every call returns gm_status (0 = ok).  Nothing throws across the ABI.
+ *   - A gm_ctx owns all device buffers for scans of up to max_points; no allocation per scan.
+ *     A ctx is not thread-safe and is bound to the CUDA device current at gm_create().
+ *   - Points are pcl::PointXYZ-compatible: 4 floats {x,y,z,pad}, 16-byte stride.
+ *     Normals are pcl::Normal-compatible: 8 floats {nx,ny,nz,0, curvature,0,0,0}, 32-byte stride.
+ *   - Calls are asynchronous on the ctx stream; gm_download_* / gm_get_* synchronise that stream.
+ *   - There is NO CPU fallback: without a CUDA device gm_create() fails with GM_ERR_NO_DEVICE.
+ */
+#ifndef GM_CAPI_H
+#define GM_CAPI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GM_API __attribute__((visibility("default")))
+#else
+#define GM_API
+#endif
+
+typedef int32_t gm_status;
+enum {
+  GM_OK = 0,
+  GM_ERR_INVALID_ARG = 1,
+  GM_ERR_NO_DEVICE = 2,       /* no CUDA device / driver: the product has no CPU path            */
+  GM_ERR_CUDA = 3,            /* a CUDA call failed; gm_last_error() has the text                */
+  GM_ERR_CAPACITY = 4,        /* n > max_points or H > max_hypotheses                            */
+  GM_ERR_STAGE_ORDER = 5,     /* a stage was called before the stage that produces its input     */
+  GM_WARN_VOXEL_OVERFLOW = 6, /* pcl::VoxelGrid overflow rule: output = input, unchanged (A.5)   */
+  GM_ERR_NN_INDEX_RANGE = 7,  /* reference quirk B.3: nn index >= compacted size (normals->at()
+                                 would throw at src/tunnel_processing.cpp:247)                   */
+  GM_ERR_INTERNAL = 8,        /* device-side consistency check failed (look-back spin bound)     */
+  GM_ERR_NO_MODEL = 9         /* every RANSAC hypothesis was degenerate                          */
+};
+
+/* Mirror of class Parameters (include/geometric_mapping/paramHandler.hpp:26-36; ROS keys at
+ * src/paramHandler.cpp:13,19,25,31,37,43,49,61) plus the builder-defined RANSAC / polyline
+ * fields for the stages the reference only stubs (src/tunnel_processing.cpp:149-154). */
+typedef struct gm_params {
+  double boxFilterBound;    /* "boxFilterBound"     default 5.0  */
+  double voxelGridLeafSize; /* "voxelGridLeafSize"  default 0.1  (field leafSize) */
+  double neighborRadius;    /* "neighborRadius"     default 0.03 */
+  double weightingFactor;   /* "weightingFactor"    default 0.2  */
+  int32_t displayCloud;     /* default 1 */
+  int32_t displayNormals;   /* default 1 */
+  int32_t displayCenterAxis;/* default 1 */
+  int32_t usePCLViz;        /* default 0; accepted and ignored (GUI, out of scope) */
+  /* --- input semantics --- */
+  int32_t is_dense;         /* default 1: pcl::CropBox keeps NaN points of a dense cloud (A.1) */
+  int32_t nn_index_mode;    /* 0 = reference-faithful (1-NN indexes the PRE-compaction cloud,
+                               quirk B.3), 1 = fixed (post-compaction index) */
+  /* --- builder-defined RANSAC --- */
+  double ransacThreshold;   /* tau, default 0.05 m */
+  double cylinderRadiusMin; /* default 0.5  */
+  double cylinderRadiusMax; /* default 10.0 */
+  int32_t refitIterations;  /* Gauss-Newton steps of the cylinder refit, default 5 */
+  int32_t maxSlices;        /* polyline capacity, default 256 */
+  double sliceLength;       /* polyline slice length along the center axis, default 1.0 m */
+} gm_params;
+
+typedef struct gm_ctx gm_ctx;
+
+/* Sizes produced by the stages (all int32; -1 = stage not run). */
+typedef struct gm_counts {
+  int32_t n_input;   /* points uploaded                                   */
+  int32_t n_cropped; /* M  after chopCloud                                */
+  int32_t n_valid;   /* M' after NaN-normal compaction                    */
+  int32_t n_voxels;  /* V                                                 */
+  int32_t n_cells;   /* occupied neighbour-grid cells (diagnostic)        */
+  int32_t voxel_overflow; /* 1 if the VoxelGrid overflow rule fired       */
+  int32_t nn_out_of_range;/* count of 1-NN indices >= n_valid (quirk B.3) */
+  int32_t device_error;   /* non-zero = internal device-side check failed */
+} gm_counts;
+
+/* Eigen frame of getLocalFrame: vals ascending; vecs[r*3+k] = component r of eigenvector k,
+ * so the center axis (src/geometric_mapping.cpp:91-92, eigenVecs.col(0)) is vecs[0],vecs[3],vecs[6]. */
+typedef struct gm_frame {
+  float vals[3];
+  float vecs[9];
+  float scatter[9]; /* the 3x3 "normal intensity" matrix, row-major */
+} gm_frame;
+
+/* One ARROW marker's numeric payload (rvizArrow, src/tunnel_processing.cpp:161-205). */
+typedef struct gm_arrow {
+  float start[3];
+  float end[3];
+  float scale[3];
+  float color_argb[4]; /* pushed as (a,r,g,b): src/tunnel_processing.cpp:199-202 */
+  int32_t id;
+} gm_arrow;
+
+typedef enum { GM_MODEL_PLANE = 0, GM_MODEL_CYLINDER = 1 } gm_model_kind;
+
+/* Result of one RANSAC + refit (builder-defined stage a8). */
+typedef struct gm_model {
+  int32_t kind;        /* gm_model_kind */
+  int32_t best_id;     /* winning hypothesis id, -1 if none */
+  int32_t best_count;  /* its inlier count */
+  int32_t refit_count; /* inliers used by the refit */
+  float hyp[8];        /* winning hypothesis: plane {a,b,c,d}; cylinder {q(3),dir(3),r} */
+  float coef[8];       /* refined model, same layout */
+  float rms;           /* RMS residual of the refit inliers against the refined model */
+  float pad_;
+} gm_model;
+
+/* One cross-section of the center-axis polyline (builder-defined). */
+typedef struct gm_slice {
+  float center[3];
+  float dir[3];
+  float radius;
+  float rms;
+  float t_mid;
+  int32_t count;
+} gm_slice;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+GM_API void gm_params_default(gm_params* p);
+GM_API gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypotheses, gm_ctx** out);
+GM_API void gm_destroy(gm_ctx* ctx);
+GM_API gm_status gm_set_params(gm_ctx* ctx, const gm_params* p);
+/* Use an existing cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own stream. */
+GM_API gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream);
+GM_API const char* gm_last_error(const gm_ctx* ctx);
+GM_API const char* gm_status_string(gm_status s);
+GM_API int32_t gm_version(void);
+/* Kernels launched by this ctx since creation (or since gm_reset_launch_count). */
+GM_API int64_t gm_launch_count(const gm_ctx* ctx);
+GM_API void gm_reset_launch_count(gm_ctx* ctx);
+GM_API gm_status gm_synchronize(gm_ctx* ctx);
+
+/* ---- input: replaces pcl::fromROSMsg(*input, *cloud), src/geometric_mapping.cpp:55 -------- */
+/* Host buffer -> device (async H2D on the ctx stream).  stride_bytes >= 12; 16 for PointXYZ. */
+GM_API gm_status gm_upload_scan(gm_ctx* ctx, const float* xyz_host, size_t n, size_t stride_bytes);
+/* Scan already resident in HBM as n x float4 (not copied; must outlive the processing calls). */
+GM_API gm_status gm_set_scan_device(gm_ctx* ctx, const float* xyzw_device, size_t n);
+
+/* ---- stages ---------------------------------------------------------------------------- */
+/* chopCloud(bound, cloud): src/tunnel_processing.cpp:39-49, called src/geometric_mapping.cpp:57 */
+GM_API gm_status gm_crop(gm_ctx* ctx);
+/* getNormals(neighborRadius, cloud, kdtree): src/tunnel_processing.cpp:52-89 — radius-search
+ * normals + curvature (pcl::NormalEstimation), then NaN-normal removal compacting cloud and
+ * normals.  The kd-tree out-param is replaced by the device neighbour grid kept in ctx. */
+GM_API gm_status gm_normals(gm_ctx* ctx);
+/* compute part of rvizNormals(leaf, cloud, kdtree, normals): src/tunnel_processing.cpp:215-220
+ * (pcl::VoxelGrid) and :233-249 (1-NN of each centroid -> normal). */
+GM_API gm_status gm_voxel(gm_ctx* ctx);
+/* getLocalFrame(n, weightingFactor, normals, vals, vecs): src/tunnel_processing.cpp:92-148 */
+GM_API gm_status gm_local_frame(gm_ctx* ctx);
+
+/* Builder-defined stages the reference stubs as getCylinder (src/tunnel_processing.cpp:149-154,
+ * include/geometric_mapping/tunnel_processing.hpp:56-59).
+ * gm_ransac: generate H hypotheses from injected sample indices (host array, H x 3 for planes,
+ * H x 2 for cylinders; indices into the compacted cloud), count inliers of ids [h_begin,h_end)
+ * over the compacted cloud, and reduce the local best into a packed key
+ *   key = (uint64(count + 1) << 32) | (0xFFFFFFFF - id)       (max = best, ties -> lowest id).
+ * Multi-GPU: each rank passes its own [h_begin,h_end); all-reduce(max) the keys between
+ * gm_ransac and gm_ransac_select. */
+GM_API gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int32_t H,
+                           int32_t h_begin, int32_t h_end);
+/* Device address of the 8-byte packed best key of `kind` (for an NCCL all-reduce in place). */
+GM_API gm_status gm_ransac_key_device_ptr(gm_ctx* ctx, int32_t kind, void** key_dev);
+/* Decode the (possibly all-reduced) key on device, refit the winning primitive (plane: PCA of
+ * inliers; cylinder: refitIterations Gauss-Newton steps) and keep the result in ctx. */
+GM_API gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind);
+/* Per-point labels from the refined models: 1 plane, 2 cylinder, 0 neither. */
+GM_API gm_status gm_label(gm_ctx* ctx);
+/* Center-axis polyline + cross-sections along the getLocalFrame axis over points with label 2. */
+GM_API gm_status gm_axis_polyline(gm_ctx* ctx);
+
+/* Fused per-scan path = the body of cloud_cb (src/geometric_mapping.cpp:48-125) plus the
+ * builder-defined segmentation: crop -> normals -> voxel -> local frame -> RANSAC plane(Hp)
+ * + cylinder(Hc) -> select/refit -> labels -> polyline.  samples may be NULL when H == 0. */
+GM_API gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp,
+                                 const int32_t* cyl_samples_host, int32_t Hc);
+
+/* ---- results (synchronise the ctx stream) ---------------------------------------------- */
+GM_API gm_status gm_get_counts(gm_ctx* ctx, gm_counts* out);
+/* cloud: which = 0 cropped (pre-compaction, M), 1 compacted (M'), written as n x float4 */
+GM_API gm_status gm_download_cloud(gm_ctx* ctx, int32_t which, float* out_xyzw, size_t capacity_points);
+/* normals: which = 0 pre-compaction (M, NaN rows included), 1 compacted (M'); n x 8 floats */
+GM_API gm_status gm_download_normals(gm_ctx* ctx, int32_t which, float* out8, size_t capacity_points);
+/* neighbour counts of the radius search per cropped point (M int32) */
+GM_API gm_status gm_download_neighbor_counts(gm_ctx* ctx, int32_t* out, size_t capacity_points);
+/* pre-compaction index -> compacted index or -1 (M int32) */
+GM_API gm_status gm_download_valid_map(gm_ctx* ctx, int32_t* out, size_t capacity_points);
+/* voxel keys and voxel rank of every compacted point (M' int32 each); either may be NULL */
+GM_API gm_status gm_download_voxel_assignment(gm_ctx* ctx, int32_t* keys, int32_t* assign, size_t capacity_points);
+/* per voxel: centroid (V x float4), key, member count, 1-NN index, 1-NN normal (V x 8 floats); any may be NULL */
+GM_API gm_status gm_download_voxels(gm_ctx* ctx, float* centroids_xyzw, int32_t* keys, int32_t* counts,
+                                    int32_t* nn_index, float* nn_normal8, size_t capacity_voxels);
+/* VoxelGrid lattice: min_b[3], div_b[3] */
+GM_API gm_status gm_get_voxel_grid(gm_ctx* ctx, int32_t grid6[6]);
+GM_API gm_status gm_get_frame(gm_ctx* ctx, gm_frame* out);
+/* hypothesis table of the last gm_ransac(kind): coef (plane H x 4, cylinder H x 7), inlier test
+ * parameters (cylinder only, H x 12, may be NULL), counts (H int32, -1 = degenerate or not in
+ * this rank's range) */
+GM_API gm_status gm_download_hypotheses(gm_ctx* ctx, int32_t kind, float* coef, float* test12, int32_t* counts, int32_t capacity_h);
+GM_API gm_status gm_get_model(gm_ctx* ctx, int32_t kind, gm_model* out);
+GM_API gm_status gm_download_labels(gm_ctx* ctx, uint8_t* out, size_t capacity_points);
+GM_API gm_status gm_download_polyline(gm_ctx* ctx, gm_slice* out, int32_t capacity, int32_t* n_slices);
+
+/* ---- test hooks: inject a stage's input so stages can be parity-checked in isolation ---- */
+/* Replace the compacted cloud (and normals, may be NULL) held in ctx: n x float4 / n x 8 floats. */
+GM_API gm_status gm_inject_compacted(gm_ctx* ctx, const float* xyzw_host, const float* normals8_host, size_t n);
+
+/* ---- host-side formatting of the published numbers (a6) --------------------------------- */
+/* rvizEigens(vals, vecs): src/tunnel_processing.cpp:260-300 -> 3 arrows */
+GM_API void gm_markers_eigen(const gm_frame* frame, gm_arrow out[3]);
+/* rvizNormals marker payload: src/tunnel_processing.cpp:228-252 -> V arrows from the voxel results */
+GM_API void gm_markers_normals(const float* centroids_xyzw, const float* nn_normal8, int32_t V, gm_arrow* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GM_CAPI_H */

@@ -1,0 +1,911 @@
+// gm_oracle.cpp — CPU ORACLE for the geometric_mapping per-scan hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+// (geometric_mapping_b200/csrc) never links, imports or calls anything in oracle/.
+//
+// PARITY STATUS: **parity unpinned**.  The reference (wangqiaoli/geometric_mapping) ships no
+// tests, fixtures or golden vectors, and its arithmetic lives in un-vendored third-party
+// libraries that are absent from /root/reference and from this image (PCL 1.7/1.8, Eigen 3.3,
+// FLANN 1.8; `find_package(PCL REQUIRED)` CMakeLists.txt:18, `Eigen3 3.3` CMakeLists.txt:19),
+// so neither the reference nor its dependencies can be compiled here.  This file restates
+// (a) the reference-owned math (src/tunnel_processing.cpp, cited per function) and
+// (b) the published PCL/FLANN/Eigen algorithms at the reference's call sites (SURVEY.md
+// Appendix A.1-A.6), and (c) builder-defined RANSAC / refit / polyline / compression
+// definitions (Appendix A.7-A.10) that the reference only stubs
+// (src/tunnel_processing.cpp:149-154).  It is pinned only by analytic known answers
+// (tests/test_oracle_known_answers.py) and by brute-force vs accelerated self-consistency.
+//
+// Build: see oracle/Makefile  (-O2 -ffp-contract=off: no implicit FMA contraction, matching the
+// reference build which has no -march/-mfma flags, CMakeLists.txt:5).  Explicit fmaf() calls
+// are the builder-defined canonical RANSAC test and are meant to be fused.
+//
+// All float arithmetic below is written in the documented operation order; do not "simplify".
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define GMO_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct P4 { float x, y, z, w; };
+
+inline int resolve_threads(int nthreads) {
+#ifdef _OPENMP
+  if (nthreads <= 0) return omp_get_max_threads();
+  return nthreads;
+#else
+  (void)nthreads;
+  return 1;
+#endif
+}
+
+// FLANN L2_Simple distance, 3 dims: result = 0; for d: diff = a[d]-b[d]; result += diff*diff
+// (SURVEY A.2).  Unfused.
+inline float flann_d2(const float* a, const float* b) {
+  float r = 0.0f;
+  float d0 = a[0] - b[0]; r = r + d0 * d0;
+  float d1 = a[1] - b[1]; r = r + d1 * d1;
+  float d2 = a[2] - b[2]; r = r + d2 * d2;
+  return r;
+}
+
+// ---- pcl::computeRoots2 / computeRoots / eigen33 (common/impl/eigen.hpp, PCL 1.8)
+inline void compute_roots2(float b, float c, float roots[3]) {
+  roots[0] = 0.0f;
+  float d = b * b - 4.0f * c;
+  if (d < 0.0f) d = 0.0f;
+  float sd = std::sqrt(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+inline void compute_roots(const float m[9], float roots[3]) {
+  // m row-major symmetric: m[0]=m00 m[1]=m01 m[2]=m02 m[4]=m11 m[5]=m12 m[8]=m22
+  float m00 = m[0], m01 = m[1], m02 = m[2], m11 = m[4], m12 = m[5], m22 = m[8];
+  float c0 = m00 * m11 * m22 + 2.0f * m01 * m02 * m12 - m00 * m12 * m12 - m11 * m02 * m02 -
+             m22 * m01 * m01;
+  float c1 = m00 * m11 - m01 * m01 + m00 * m22 - m02 * m02 + m11 * m22 - m12 * m12;
+  float c2 = m00 + m11 + m22;
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) {
+    compute_roots2(c2, c1, roots);
+  } else {
+    const float s_inv3 = 1.0f / 3.0f;
+    const float s_sqrt3 = std::sqrt(3.0f);
+    float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+    float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0f) q = 0.0f;
+    float rho = std::sqrt(-a_over_3);
+    float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+    float cos_theta = std::cos(theta);
+    float sin_theta = std::sin(theta);
+    roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+    if (roots[1] >= roots[2]) {
+      std::swap(roots[1], roots[2]);
+      if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+    }
+    if (roots[0] <= 0.0f) compute_roots2(c2, c1, roots);
+  }
+}
+
+// smallest eigenpair of a symmetric 3x3 (pcl::eigen33(mat, eigenvalue, eigenvector))
+inline void eigen33_smallest(const float cov[9], float& eigenvalue, float evec[3]) {
+  float scale = 0.0f;
+  for (int i = 0; i < 9; ++i) scale = std::max(scale, std::fabs(cov[i]));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+  float m[9];
+  for (int i = 0; i < 9; ++i) m[i] = cov[i] / scale;
+  float roots[3];
+  compute_roots(m, roots);
+  eigenvalue = roots[0] * scale;
+  m[0] -= roots[0]; m[4] -= roots[0]; m[8] -= roots[0];
+  const float* r0 = m; const float* r1 = m + 3; const float* r2 = m + 6;
+  float v1[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+  float v2[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+  float v3[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const float* v; float l;
+  if (l1 >= l2 && l1 >= l3) { v = v1; l = l1; }
+  else if (l2 >= l1 && l2 >= l3) { v = v2; l = l2; }
+  else { v = v3; l = l3; }
+  float s = std::sqrt(l);
+  evec[0] = v[0] / s; evec[1] = v[1] / s; evec[2] = v[2] / s;
+}
+
+// cyclic Jacobi on a symmetric 3x3 in double.  Stand-in for Eigen::SelfAdjointEigenSolver
+// (src/tunnel_processing.cpp:129): ascending eigenvalues, unit eigenvectors as
+// columns.  Sign convention is builder-defined (largest-|component| positive) because Eigen's
+// is unspecified.
+void jacobi3(const double Ain[9], double vals[3], double vecs[9] /* row-major, column k = vec k */) {
+  double A[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = Ain[i * 3 + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+      if (A[p][q] == 0.0) continue;
+      double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      double t = ((theta >= 0.0) ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+      double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+      for (int k = 0; k < 3; ++k) { double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+      for (int k = 0; k < 3; ++k) { double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+      for (int k = 0; k < 3; ++k) { double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+    }
+  }
+  int order[3] = {0, 1, 2};
+  double d[3] = {A[0][0], A[1][1], A[2][2]};
+  std::stable_sort(order, order + 3, [&](int a, int b) { return d[a] < d[b]; });
+  for (int k = 0; k < 3; ++k) {
+    int c = order[k];
+    vals[k] = d[c];
+    double v[3] = {V[0][c], V[1][c], V[2][c]};
+    double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    int big = 0;
+    if (std::fabs(v[1]) > std::fabs(v[big])) big = 1;
+    if (std::fabs(v[2]) > std::fabs(v[big])) big = 2;
+    double sgn = (v[big] < 0.0) ? -1.0 : 1.0;
+    for (int r = 0; r < 3; ++r) vecs[r * 3 + k] = sgn * v[r] / n;
+  }
+}
+
+// Spatial hash used ONLY to make the oracle's neighbour search finish at 1e6 points.
+// The neighbour set itself is defined by the brute-force predicate flann_d2 < r2; the
+// brute-force mode (mode=1) is compared against this in tests.
+struct HashGrid {
+  double cell, inv;
+  std::unordered_map<uint64_t, std::vector<int>> cells;
+  static uint64_t key(int64_t i, int64_t j, int64_t k) {
+    return (uint64_t)((i + (1 << 20)) & 0x1FFFFF) | ((uint64_t)((j + (1 << 20)) & 0x1FFFFF) << 21) |
+           ((uint64_t)((k + (1 << 20)) & 0x1FFFFF) << 42);
+  }
+  void build(const P4* p, int64_t n, double c) {
+    cell = c; inv = 1.0 / c;
+    cells.reserve((size_t)n / 4 + 16);
+    for (int64_t i = 0; i < n; ++i) {
+      if (!std::isfinite(p[i].x) || !std::isfinite(p[i].y) || !std::isfinite(p[i].z)) continue;
+      cells[key((int64_t)std::floor(p[i].x * inv), (int64_t)std::floor(p[i].y * inv), (int64_t)std::floor(p[i].z * inv))].push_back((int)i);
+    }
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// a1  chopCloud  (src/tunnel_processing.cpp:39-49; pcl::CropBox)
+// keep iff NOT (x<min || y<min || z<min || x>max || y>max || z>max); bounds = +-float(bound).
+// is_dense=1: NaN coordinates pass every comparison and are KEPT (reference quirk);
+// is_dense=0: non-finite points are skipped first.
+GMO_API int64_t gmo_crop(const float* pts4, int64_t n, double bound, int is_dense, float* out4,
+                         int32_t* src_index) {
+  const P4* p = (const P4*)pts4;
+  P4* o = (P4*)out4;
+  float hi = (float)bound, lo = (float)(-bound);
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (!is_dense && (!std::isfinite(p[i].x) || !std::isfinite(p[i].y) || !std::isfinite(p[i].z))) continue;
+    if (p[i].x < lo || p[i].y < lo || p[i].z < lo || p[i].x > hi || p[i].y > hi || p[i].z > hi) continue;
+    if (o) o[m] = p[i];
+    if (src_index) src_index[m] = (int32_t)i;
+    ++m;
+  }
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// a2  getNormals -> pcl::NormalEstimation::compute, radius mode
+// (src/tunnel_processing.cpp:58-70).
+//   normals8: n x 8 floats laid out as pcl::Normal {nx,ny,nz,0, curvature,0,0,0}
+//   nbr_count: neighbours found (self included), for exact comparison
+//   mode  0 = hash-grid accelerated, 1 = brute force O(n^2)
+//   order 0 = FLANN order (ascending d2, ties by index), 1 = ascending index
+//   covd  if non-null receives the double-precision "truth" normal (3) + curvature (1) per point
+GMO_API void gmo_normals(const float* pts4, int64_t n, double radius, float* normals8,
+                         int32_t* nbr_count, int mode, int order, double* truth4, int nthreads) {
+  const P4* p = (const P4*)pts4;
+  const float rf = (float)radius;
+  const float r2 = rf * rf;
+  HashGrid grid;
+  if (mode == 0) grid.build(p, n, (double)rf * 1.0009765625);
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<std::pair<float, int>> nb;
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; ++i) {
+      nb.clear();
+      const float* q = &p[i].x;
+      bool finite = std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]);
+      if (finite) {
+        if (mode == 1) {
+          for (int64_t j = 0; j < n; ++j) {
+            float d2 = flann_d2(q, &p[j].x);
+            if (d2 < r2) nb.emplace_back(d2, (int)j);
+          }
+        } else {
+          int64_t ci = (int64_t)std::floor(q[0] * grid.inv), cj = (int64_t)std::floor(q[1] * grid.inv), ck = (int64_t)std::floor(q[2] * grid.inv);
+          for (int64_t dk = -1; dk <= 1; ++dk) for (int64_t dj = -1; dj <= 1; ++dj) for (int64_t di = -1; di <= 1; ++di) {
+            auto it = grid.cells.find(HashGrid::key(ci + di, cj + dj, ck + dk));
+            if (it == grid.cells.end()) continue;
+            for (int j : it->second) {
+              float d2 = flann_d2(q, &p[j].x);
+              if (d2 < r2) nb.emplace_back(d2, j);
+            }
+          }
+        }
+      }
+      if (order == 0) std::sort(nb.begin(), nb.end());
+      else std::sort(nb.begin(), nb.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.second < b.second; });
+      float* out = normals8 + i * 8;
+      for (int k = 0; k < 8; ++k) out[k] = 0.0f;
+      if (nbr_count) nbr_count[i] = (int32_t)nb.size();
+      const float qnan = std::numeric_limits<float>::quiet_NaN();
+      if (nb.size() < 3) {
+        out[0] = out[1] = out[2] = qnan; out[4] = qnan;
+        if (truth4) { truth4[i * 4 + 0] = truth4[i * 4 + 1] = truth4[i * 4 + 2] = truth4[i * 4 + 3] = std::numeric_limits<double>::quiet_NaN(); }
+        continue;
+      }
+      // computeMeanAndCovarianceMatrix, Scalar=float, single pass, 9 accumulators (A.3)
+      float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (auto& e : nb) {
+        const P4& s = p[e.second];
+        a[0] += s.x * s.x; a[1] += s.x * s.y; a[2] += s.x * s.z;
+        a[3] += s.y * s.y; a[4] += s.y * s.z; a[5] += s.z * s.z;
+        a[6] += s.x; a[7] += s.y; a[8] += s.z;
+      }
+      float cnt = (float)nb.size();
+      for (int k = 0; k < 9; ++k) a[k] = a[k] / cnt;
+      float cov[9];
+      cov[0] = a[0] - a[6] * a[6];
+      cov[1] = a[1] - a[6] * a[7];
+      cov[2] = a[2] - a[6] * a[8];
+      cov[4] = a[3] - a[7] * a[7];
+      cov[5] = a[4] - a[7] * a[8];
+      cov[8] = a[5] - a[8] * a[8];
+      cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+      float ev, nrm[3];
+      eigen33_smallest(cov, ev, nrm);
+      float eig_sum = cov[0] + cov[4] + cov[8];
+      float curvature = (eig_sum != 0.0f) ? std::fabs(ev / eig_sum) : 0.0f;
+      // flipNormalTowardsViewpoint(point, 0,0,0, ...)
+      float vx = 0.0f - q[0], vy = 0.0f - q[1], vz = 0.0f - q[2];
+      float cos_theta = vx * nrm[0] + vy * nrm[1] + vz * nrm[2];
+      if (cos_theta < 0.0f) { nrm[0] *= -1.0f; nrm[1] *= -1.0f; nrm[2] *= -1.0f; }
+      out[0] = nrm[0]; out[1] = nrm[1]; out[2] = nrm[2]; out[4] = curvature;
+      if (truth4) {
+        // double "truth": two-pass centred covariance + Jacobi, same neighbour set
+        double mx = 0, my = 0, mz = 0;
+        for (auto& e : nb) { mx += p[e.second].x; my += p[e.second].y; mz += p[e.second].z; }
+        double c = (double)nb.size(); mx /= c; my /= c; mz /= c;
+        double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (auto& e : nb) {
+          double dx = p[e.second].x - mx, dy = p[e.second].y - my, dz = p[e.second].z - mz;
+          C[0] += dx * dx; C[1] += dx * dy; C[2] += dx * dz; C[4] += dy * dy; C[5] += dy * dz; C[8] += dz * dz;
+        }
+        C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+        for (int k = 0; k < 9; ++k) C[k] /= c;
+        double vals[3], vecs[9];
+        jacobi3(C, vals, vecs);
+        double tn[3] = {vecs[0], vecs[3], vecs[6]};
+        if ((-(double)q[0]) * tn[0] + (-(double)q[1]) * tn[1] + (-(double)q[2]) * tn[2] < 0) { tn[0] = -tn[0]; tn[1] = -tn[1]; tn[2] = -tn[2]; }
+        double tr = C[0] + C[4] + C[8];
+        truth4[i * 4 + 0] = tn[0]; truth4[i * 4 + 1] = tn[1]; truth4[i * 4 + 2] = tn[2];
+        truth4[i * 4 + 3] = (tr != 0.0) ? std::fabs(vals[0] / tr) : 0.0;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a3  removeNaNNormalsFromPointCloud + ExtractIndices (src/tunnel_processing.cpp:74-85)
+// Stable; keeps a point iff nx,ny,nz are all finite.  map[i] = compacted index or -1.
+GMO_API int64_t gmo_compact(const float* pts4, const float* normals8, int64_t n, float* pts_out,
+                            float* normals_out, int32_t* map) {
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float* nr = normals8 + i * 8;
+    bool ok = std::isfinite(nr[0]) && std::isfinite(nr[1]) && std::isfinite(nr[2]);
+    if (map) map[i] = ok ? (int32_t)m : -1;
+    if (!ok) continue;
+    if (pts_out) std::memcpy(pts_out + m * 4, pts4 + i * 4, 16);
+    if (normals_out) std::memcpy(normals_out + m * 8, nr, 32);
+    ++m;
+  }
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// a4  pcl::VoxelGrid<PointXYZ>::filter (src/tunnel_processing.cpp:217-220)
+//   keys[i]      int32 voxel key of point i (bit-exact contract)
+//   assign[i]    rank of point i's voxel in ascending-key order (bit-exact contract)
+//   centroids4   V x {x,y,z,1}: float sum in ascending ORIGINAL INDEX order within the voxel
+//                (std::sort is unstable in PCL, so any intra-voxel order is reference-valid;
+//                the stable order is the builder's canonical choice), divided by float(count)
+//   voxel_keys   V ascending keys,  voxel_count V member counts
+//   grid6        min_b[3], div_b[3]
+//   status       0 ok, 1 = overflow rule hit (dx*dy*dz > INT32_MAX): PCL warns and returns the
+//                input unchanged -> returns n and copies the input to centroids4.
+GMO_API int64_t gmo_voxel(const float* pts4, int64_t n, double leaf, int32_t* keys, int32_t* assign,
+                          float* centroids4, int32_t* voxel_keys, int32_t* voxel_count,
+                          int32_t* grid6, int32_t* status) {
+  const P4* p = (const P4*)pts4;
+  if (status) *status = 0;
+  if (n == 0) return 0;
+  const float leaf_f = (float)leaf;
+  const float inv = 1.0f / leaf_f;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int64_t i = 0; i < n; ++i) {
+    mn[0] = std::min(mn[0], p[i].x); mn[1] = std::min(mn[1], p[i].y); mn[2] = std::min(mn[2], p[i].z);
+    mx[0] = std::max(mx[0], p[i].x); mx[1] = std::max(mx[1], p[i].y); mx[2] = std::max(mx[2], p[i].z);
+  }
+  int64_t dx = (int64_t)((mx[0] - mn[0]) * inv) + 1;
+  int64_t dy = (int64_t)((mx[1] - mn[1]) * inv) + 1;
+  int64_t dz = (int64_t)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > (int64_t)INT32_MAX) {
+    if (status) *status = 1;
+    if (centroids4) std::memcpy(centroids4, pts4, (size_t)n * 16);
+    return n;
+  }
+  int32_t min_b[3], max_b[3], div_b[3];
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = (int32_t)std::floor(mn[a] * inv);
+    max_b[a] = (int32_t)std::floor(mx[a] * inv);
+    div_b[a] = max_b[a] - min_b[a] + 1;
+  }
+  int32_t mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  if (grid6) { for (int a = 0; a < 3; ++a) { grid6[a] = min_b[a]; grid6[3 + a] = div_b[a]; } }
+  std::vector<std::pair<uint32_t, int32_t>> order((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    int ijk0 = (int)(std::floor(p[i].x * inv) - (float)min_b[0]);
+    int ijk1 = (int)(std::floor(p[i].y * inv) - (float)min_b[1]);
+    int ijk2 = (int)(std::floor(p[i].z * inv) - (float)min_b[2]);
+    int32_t idx = ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2];
+    if (keys) keys[i] = idx;
+    order[(size_t)i] = {(uint32_t)idx, (int32_t)i};
+  }
+  std::sort(order.begin(), order.end());  // (key, index) pairs: equivalent to a stable sort by key
+  int64_t V = 0;
+  int64_t i = 0;
+  while (i < n) {
+    int64_t j = i;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    while (j < n && order[(size_t)j].first == order[(size_t)i].first) {
+      const P4& s = p[order[(size_t)j].second];
+      sx += s.x; sy += s.y; sz += s.z;
+      if (assign) assign[order[(size_t)j].second] = (int32_t)V;
+      ++j;
+    }
+    float c = (float)(j - i);
+    if (centroids4) { centroids4[V * 4 + 0] = sx / c; centroids4[V * 4 + 1] = sy / c; centroids4[V * 4 + 2] = sz / c; centroids4[V * 4 + 3] = 1.0f; }
+    if (voxel_keys) voxel_keys[V] = (int32_t)order[(size_t)i].first;
+    if (voxel_count) voxel_count[V] = (int32_t)(j - i);
+    ++V;
+    i = j;
+  }
+  return V;
+}
+
+// a4 (second half)  kdtree->nearestKSearch(centroid, 1)  (src/tunnel_processing.cpp:239)
+// Exact 1-NN in FLANN L2_Simple distance; ties -> lowest index (builder-defined, FLANN leaves it
+// unspecified).  Non-finite target points are never neighbours.  Brute force, O(nq*n).
+GMO_API void gmo_nn1(const float* query4, int64_t nq, const float* pts4, int64_t n, int32_t* idx_out,
+                     float* d2_out, int nthreads) {
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (int64_t q = 0; q < nq; ++q) {
+    float best = std::numeric_limits<float>::infinity();
+    int32_t bi = -1;
+    for (int64_t j = 0; j < n; ++j) {
+      float d2 = flann_d2(query4 + q * 4, pts4 + j * 4);
+      if (d2 < best) { best = d2; bi = (int32_t)j; }
+    }
+    idx_out[q] = bi;
+    if (d2_out) d2_out[q] = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a5  getLocalFrame (src/tunnel_processing.cpp:92-148), diagonal restatement of the dense
+// n x n product (bit-identical: SURVEY 8 a5).
+//   w_i  = float(exp((double(curv_i) + 0.001/wf)^2))          :106
+//   Wn   = w_i * n_i (float)                                    :119
+//   S    = Wn^T Wn, float, accumulated in ascending i           :124 (Eigen order unspecified)
+//   eig  = ascending eigenvalues / column eigenvectors          :129-137
+// S9 row-major float; vals3/vecs9 float (vecs9[r*3+k] = component r of eigenvector k);
+// S_truth9: same matrix accumulated in double from the float Wn products.
+GMO_API void gmo_local_frame(const float* normals8, int64_t n, double wf, float* S9, float* vals3,
+                             float* vecs9, double* S_truth9) {
+  float S[6] = {0, 0, 0, 0, 0, 0};
+  double T[6] = {0, 0, 0, 0, 0, 0};
+  const double shift = 0.001 / wf;
+  for (int64_t i = 0; i < n; ++i) {
+    const float* nr = normals8 + i * 8;
+    double t = (double)nr[4] + shift;
+    float w = (float)std::exp(t * t);
+    float a = w * nr[0], b = w * nr[1], c = w * nr[2];
+    S[0] += a * a; S[1] += a * b; S[2] += a * c; S[3] += b * b; S[4] += b * c; S[5] += c * c;
+    T[0] += (double)a * a; T[1] += (double)a * b; T[2] += (double)a * c; T[3] += (double)b * b; T[4] += (double)b * c; T[5] += (double)c * c;
+  }
+  float Sf[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
+  if (S9) std::memcpy(S9, Sf, sizeof(Sf));
+  if (S_truth9) { double Td[9] = {T[0], T[1], T[2], T[1], T[3], T[4], T[2], T[4], T[5]}; std::memcpy(S_truth9, Td, sizeof(Td)); }
+  double Sd[9]; for (int k = 0; k < 9; ++k) Sd[k] = Sf[k];
+  double vals[3], vecs[9];
+  jacobi3(Sd, vals, vecs);
+  for (int k = 0; k < 3; ++k) vals3[k] = (float)vals[k];
+  for (int k = 0; k < 9; ++k) vecs9[k] = (float)vecs[k];
+}
+
+// Literal restatement of lines :100-124 with the dense n x n weight matrix (tiny n only), used
+// to demonstrate that the diagonal form above is bit-identical.  Row i of weights*normals is
+// sum_k W(i,k)*N(k,j) accumulated over k in ascending order starting from 0.
+GMO_API void gmo_local_frame_dense(const float* normals8, int64_t n, double wf, float* S9) {
+  std::vector<float> W((size_t)(n * n), 0.0f), N((size_t)(n * 3)), WN((size_t)(n * 3));
+  for (int64_t i = 0; i < n; ++i) {
+    W[(size_t)(i * n + i)] = (float)std::exp(std::pow((double)normals8[i * 8 + 4] + .001 / wf, 2));
+    for (int c = 0; c < 3; ++c) N[(size_t)(i * 3 + c)] = normals8[i * 8 + c];
+  }
+  for (int64_t i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) {
+    float acc = 0.0f;
+    for (int64_t k = 0; k < n; ++k) acc += W[(size_t)(i * n + k)] * N[(size_t)(k * 3 + c)];
+    WN[(size_t)(i * 3 + c)] = acc;
+  }
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < n; ++i) acc += WN[(size_t)(i * 3 + a)] * WN[(size_t)(i * 3 + b)];
+    S9[a * 3 + b] = acc;
+  }
+}
+
+// a6  rvizEigens numeric payload (src/tunnel_processing.cpp:260-300): per arrow i
+//   out[i*10 + 0..2] start (0,0,0); 3..5 end = eigVecs.col(i); 6..8 scale; 9 = normalised |lambda_i|
+GMO_API void gmo_eigen_markers(const float* vals3, const float* vecs9, float* out30) {
+  float nrm = std::sqrt(vals3[0] * vals3[0] + vals3[1] * vals3[1] + vals3[2] * vals3[2]);
+  float inv = 1.0f / nrm;
+  for (int i = 0; i < 3; ++i) {
+    float e = inv * std::fabs(vals3[i]);
+    float* o = out30 + i * 10;
+    o[0] = o[1] = o[2] = 0.0f;
+    o[3] = vecs9[0 * 3 + i]; o[4] = vecs9[1 * 3 + i]; o[5] = vecs9[2 * 3 + i];
+    o[6] = (float)(0.1 - (0.05 * e));
+    o[7] = (float)(0.3 - (0.15 * e));
+    o[8] = (float)(0.25 - (0.125 * e));
+    o[9] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a8  BUILDER-DEFINED RANSAC (absent in the reference: stub at src/tunnel_processing.cpp:149-154).
+// Follows pcl::SampleConsensusModelPlane / Cylinder / RandomSampleConsensus semantics with the
+// documented deviations.  Every operation below is part of the canonical
+// definition: the CUDA kernels reproduce it bit for bit with __f*_rn intrinsics.
+
+// plane: samples3 = H x 3 indices; coef4 = H x {a,b,c,d}; valid[h] = 0 for degenerate samples.
+GMO_API void gmo_plane_hypotheses(const float* pts4, int64_t n, const int32_t* samples3, int32_t H,
+                                  float* coef4, int32_t* valid) {
+  const P4* p = (const P4*)pts4;
+  for (int32_t h = 0; h < H; ++h) {
+    int32_t i0 = samples3[h * 3], i1 = samples3[h * 3 + 1], i2 = samples3[h * 3 + 2];
+    float* c = coef4 + h * 4;
+    c[0] = c[1] = c[2] = c[3] = 0.0f;
+    valid[h] = 0;
+    if (i0 < 0 || i1 < 0 || i2 < 0 || i0 >= n || i1 >= n || i2 >= n) continue;
+    if (i0 == i1 || i0 == i2 || i1 == i2) continue;
+    float ax = p[i1].x - p[i0].x, ay = p[i1].y - p[i0].y, az = p[i1].z - p[i0].z;
+    float bx = p[i2].x - p[i0].x, by = p[i2].y - p[i0].y, bz = p[i2].z - p[i0].z;
+    float nx = ay * bz - az * by;
+    float ny = az * bx - ax * bz;
+    float nz = ax * by - ay * bx;
+    float len2 = (nx * nx + ny * ny) + nz * nz;
+    if (!(len2 > 0.0f) || !std::isfinite(len2)) continue;
+    float len = std::sqrt(len2);
+    nx = nx / len; ny = ny / len; nz = nz / len;
+    float d = -((nx * p[i0].x + ny * p[i0].y) + nz * p[i0].z);
+    if (!std::isfinite(d)) continue;
+    c[0] = nx; c[1] = ny; c[2] = nz; c[3] = d;
+    valid[h] = 1;
+  }
+}
+
+// canonical plane test: |fma(a,x, fma(b,y, fma(c,z,d)))| < tau
+static inline bool plane_inlier(const float* c, const P4& s, float tau) {
+  float d = std::fmaf(c[0], s.x, std::fmaf(c[1], s.y, std::fmaf(c[2], s.z, c[3])));
+  return std::fabs(d) < tau;
+}
+
+GMO_API void gmo_count_plane(const float* pts4, int64_t n, const float* coef4, const int32_t* valid,
+                             int32_t H, double tau, int32_t* counts, int nthreads) {
+  const P4* p = (const P4*)pts4;
+  const float tf = (float)tau;
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 4)
+  for (int32_t h = 0; h < H; ++h) {
+    if (!valid[h]) { counts[h] = -1; continue; }
+    const float* c = coef4 + h * 4;
+    int32_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) cnt += plane_inlier(c, p[i], tf) ? 1 : 0;
+    counts[h] = cnt;
+  }
+}
+
+// Orthonormal basis (u,w) perpendicular to unit `dir`, canonical construction:
+// k = argmin |dir_k| (ties -> lowest k); u = normalise(dir x e_k); w = dir x u.
+static inline void perp_basis(const float dir[3], float u[3], float w[3]) {
+  float ax = std::fabs(dir[0]), ay = std::fabs(dir[1]), az = std::fabs(dir[2]);
+  int k = 0; float m = ax;
+  if (ay < m) { k = 1; m = ay; }
+  if (az < m) { k = 2; m = az; }
+  float c[3];
+  if (k == 0) { c[0] = 0.0f; c[1] = dir[2]; c[2] = -dir[1]; }        // dir x e_x
+  else if (k == 1) { c[0] = -dir[2]; c[1] = 0.0f; c[2] = dir[0]; }   // dir x e_y
+  else { c[0] = dir[1]; c[1] = -dir[0]; c[2] = 0.0f; }               // dir x e_z
+  float l = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+  u[0] = c[0] / l; u[1] = c[1] / l; u[2] = c[2] / l;
+  w[0] = dir[1] * u[2] - dir[2] * u[1];
+  w[1] = dir[2] * u[0] - dir[0] * u[2];
+  w[2] = dir[0] * u[1] - dir[1] * u[0];
+}
+
+// model7 {qx,qy,qz, dx,dy,dz, r} -> test12 {ux,uy,uz,du, wx,wy,wz,dw, mid,half,0,0}
+// dist^2(p) = A^2 + B^2 with A = u.p + du, B = w.p + dw;  |dist - r| < tau  <=>
+// |A^2 + B^2 - mid| < half with mid = ((r+tau)^2 + (r-tau)^2)/2, half = ((r+tau)^2 - (r-tau)^2)/2
+// (r < tau: mid = 0, half = (r+tau)^2).
+static inline void cyl_test_params(const float* m7, float tau, float* t12) {
+  float u[3], w[3];
+  perp_basis(m7 + 3, u, w);
+  float du = -((u[0] * m7[0] + u[1] * m7[1]) + u[2] * m7[2]);
+  float dw = -((w[0] * m7[0] + w[1] * m7[1]) + w[2] * m7[2]);
+  float r = m7[6];
+  float hi = r + tau, lo = r - tau;
+  float hi2 = hi * hi, lo2 = lo * lo;
+  float mid, half;
+  if (lo >= 0.0f) { mid = 0.5f * (hi2 + lo2); half = 0.5f * (hi2 - lo2); }
+  else { mid = 0.0f; half = hi2; }
+  t12[0] = u[0]; t12[1] = u[1]; t12[2] = u[2]; t12[3] = du;
+  t12[4] = w[0]; t12[5] = w[1]; t12[6] = w[2]; t12[7] = dw;
+  t12[8] = mid; t12[9] = half; t12[10] = 0.0f; t12[11] = 0.0f;
+}
+
+GMO_API void gmo_cyl_test_params(const float* model7, int32_t H, double tau, float* test12) {
+  for (int32_t h = 0; h < H; ++h) cyl_test_params(model7 + h * 7, (float)tau, test12 + h * 12);
+}
+
+// cylinder: samples2 = H x 2 indices into pts/normals (SampleConsensusModelCylinder::
+// computeModelCoefficients).  model7 = {q, dir, r}; test12 as above.
+GMO_API void gmo_cyl_hypotheses(const float* pts4, const float* normals8, int64_t n,
+                                const int32_t* samples2, int32_t H, double rmin, double rmax,
+                                double tau, float* model7, float* test12, int32_t* valid) {
+  const P4* p = (const P4*)pts4;
+  const float rminf = (float)rmin, rmaxf = (float)rmax, tf = (float)tau;
+  for (int32_t h = 0; h < H; ++h) {
+    float* m = model7 + h * 7;
+    float* t = test12 + h * 12;
+    for (int k = 0; k < 7; ++k) m[k] = 0.0f;
+    for (int k = 0; k < 12; ++k) t[k] = 0.0f;
+    valid[h] = 0;
+    int32_t i1 = samples2[h * 2], i2 = samples2[h * 2 + 1];
+    if (i1 < 0 || i2 < 0 || i1 >= n || i2 >= n || i1 == i2) continue;
+    float p1[3] = {p[i1].x, p[i1].y, p[i1].z}, p2[3] = {p[i2].x, p[i2].y, p[i2].z};
+    const float eps = std::numeric_limits<float>::epsilon();
+    if (std::fabs(p1[0] - p2[0]) <= eps && std::fabs(p1[1] - p2[1]) <= eps && std::fabs(p1[2] - p2[2]) <= eps) continue;
+    const float* n1 = normals8 + (int64_t)i1 * 8;
+    const float* n2 = normals8 + (int64_t)i2 * 8;
+    float w[3] = {(n1[0] + p1[0]) - p2[0], (n1[1] + p1[1]) - p2[1], (n1[2] + p1[2]) - p2[2]};
+    float a = (n1[0] * n1[0] + n1[1] * n1[1]) + n1[2] * n1[2];
+    float b = (n1[0] * n2[0] + n1[1] * n2[1]) + n1[2] * n2[2];
+    float c = (n2[0] * n2[0] + n2[1] * n2[1]) + n2[2] * n2[2];
+    float d = (n1[0] * w[0] + n1[1] * w[1]) + n1[2] * w[2];
+    float e = (n2[0] * w[0] + n2[1] * w[1]) + n2[2] * w[2];
+    float den = a * c - b * b;
+    float sc, tc;
+    if (den < 1e-8f) { sc = 0.0f; tc = (b > c) ? (d / b) : (e / c); }
+    else { sc = (b * e - c * d) / den; tc = (a * e - b * d) / den; }
+    float q[3], dir[3];
+    for (int k = 0; k < 3; ++k) q[k] = (p1[k] + n1[k]) + sc * n1[k];
+    for (int k = 0; k < 3; ++k) dir[k] = (p2[k] + tc * n2[k]) - q[k];
+    float dl2 = (dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2];
+    if (!(dl2 > 0.0f) || !std::isfinite(dl2)) continue;
+    float dl = std::sqrt(dl2);
+    dir[0] = dir[0] / dl; dir[1] = dir[1] / dl; dir[2] = dir[2] / dl;
+    // r = sqrt(|dir x (q - p1)|^2 / |dir|^2)
+    float v[3] = {q[0] - p1[0], q[1] - p1[1], q[2] - p1[2]};
+    float cx = dir[1] * v[2] - dir[2] * v[1];
+    float cy = dir[2] * v[0] - dir[0] * v[2];
+    float cz = dir[0] * v[1] - dir[1] * v[0];
+    float c2 = (cx * cx + cy * cy) + cz * cz;
+    float d2 = (dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2];
+    float r = std::sqrt(c2 / d2);
+    if (!std::isfinite(r) || r > rmaxf || r < rminf) continue;
+    m[0] = q[0]; m[1] = q[1]; m[2] = q[2]; m[3] = dir[0]; m[4] = dir[1]; m[5] = dir[2]; m[6] = r;
+    cyl_test_params(m, tf, t);
+    bool fin = true;
+    for (int k = 0; k < 10; ++k) fin = fin && std::isfinite(t[k]);
+    if (!fin) { for (int k = 0; k < 12; ++k) t[k] = 0.0f; continue; }
+    valid[h] = 1;
+  }
+}
+
+// canonical cylinder test: A = fma chain with u, B = fma chain with w,
+// t = fma(A,A, fma(B,B,-mid)); inlier iff |t| < half
+static inline bool cyl_inlier(const float* t, const P4& s) {
+  float A = std::fmaf(t[0], s.x, std::fmaf(t[1], s.y, std::fmaf(t[2], s.z, t[3])));
+  float B = std::fmaf(t[4], s.x, std::fmaf(t[5], s.y, std::fmaf(t[6], s.z, t[7])));
+  float v = std::fmaf(A, A, std::fmaf(B, B, -t[8]));
+  return std::fabs(v) < t[9];
+}
+
+GMO_API void gmo_count_cyl(const float* pts4, int64_t n, const float* test12, const int32_t* valid,
+                           int32_t H, int32_t* counts, int nthreads) {
+  const P4* p = (const P4*)pts4;
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 4)
+  for (int32_t h = 0; h < H; ++h) {
+    if (!valid[h]) { counts[h] = -1; continue; }
+    const float* t = test12 + h * 12;
+    int32_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) cnt += cyl_inlier(t, p[i]) ? 1 : 0;
+    counts[h] = cnt;
+  }
+}
+
+// RandomSampleConsensus::computeModel over an injected sample list: strict '>' keeps
+// the first best -> max count, ties to the lowest id.  Returns -1 if every hypothesis is invalid.
+GMO_API int32_t gmo_argmax(const int32_t* counts, int32_t H) {
+  int32_t best = -1, bc = -1;
+  for (int32_t h = 0; h < H; ++h) if (counts[h] > bc) { bc = counts[h]; best = h; }
+  return best;
+}
+
+// Plane refit over the inliers of coef_in (optimizeModelCoefficients): centroid +
+// covariance in double, smallest eigenvector (Jacobi), oriented like the input normal,
+// d = -n.centroid.  Unchanged if <= 3 inliers.  Returns the inlier count.
+GMO_API int64_t gmo_refit_plane(const float* pts4, int64_t n, const float* coef_in, double tau,
+                                float* coef_out) {
+  const P4* p = (const P4*)pts4;
+  const float tf = (float)tau;
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t cnt = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (!plane_inlier(coef_in, p[i], tf)) continue;
+    double x = p[i].x, y = p[i].y, z = p[i].z;
+    s[0] += x * x; s[1] += x * y; s[2] += x * z; s[3] += y * y; s[4] += y * z; s[5] += z * z;
+    s[6] += x; s[7] += y; s[8] += z;
+    ++cnt;
+  }
+  for (int k = 0; k < 4; ++k) coef_out[k] = coef_in[k];
+  if (cnt <= 3) return cnt;
+  double c = (double)cnt, mx = s[6] / c, my = s[7] / c, mz = s[8] / c;
+  double C[9] = {s[0] / c - mx * mx, s[1] / c - mx * my, s[2] / c - mx * mz, 0, s[3] / c - my * my,
+                 s[4] / c - my * mz, 0, 0, s[5] / c - mz * mz};
+  C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+  double vals[3], vecs[9];
+  jacobi3(C, vals, vecs);
+  double nx = vecs[0], ny = vecs[3], nz = vecs[6];
+  if (nx * coef_in[0] + ny * coef_in[1] + nz * coef_in[2] < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+  coef_out[0] = (float)nx; coef_out[1] = (float)ny; coef_out[2] = (float)nz;
+  coef_out[3] = (float)(-(nx * mx + ny * my + nz * mz));
+  return cnt;
+}
+
+namespace {
+// double-precision basis with the same selection rule as perp_basis
+void perp_basis_d(const double dir[3], double u[3], double w[3]) {
+  double ax = std::fabs(dir[0]), ay = std::fabs(dir[1]), az = std::fabs(dir[2]);
+  int k = 0; double m = ax;
+  if (ay < m) { k = 1; m = ay; }
+  if (az < m) { k = 2; m = az; }
+  double c[3];
+  if (k == 0) { c[0] = 0; c[1] = dir[2]; c[2] = -dir[1]; }
+  else if (k == 1) { c[0] = -dir[2]; c[1] = 0; c[2] = dir[0]; }
+  else { c[0] = dir[1]; c[1] = -dir[0]; c[2] = 0; }
+  double l = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  u[0] = c[0] / l; u[1] = c[1] / l; u[2] = c[2] / l;
+  w[0] = dir[1] * u[2] - dir[2] * u[1]; w[1] = dir[2] * u[0] - dir[0] * u[2]; w[2] = dir[0] * u[1] - dir[1] * u[0];
+}
+
+// solve 5x5 SPD-ish system by Gaussian elimination with partial pivoting; returns false if singular
+bool solve5(double A[5][5], double b[5], double x[5]) {
+  int idx[5] = {0, 1, 2, 3, 4};
+  (void)idx;
+  for (int c = 0; c < 5; ++c) {
+    int piv = c; double best = std::fabs(A[c][c]);
+    for (int r = c + 1; r < 5; ++r) if (std::fabs(A[r][c]) > best) { best = std::fabs(A[r][c]); piv = r; }
+    if (!(best > 1e-300)) return false;
+    if (piv != c) { for (int k = 0; k < 5; ++k) std::swap(A[c][k], A[piv][k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < 5; ++r) {
+      double f = A[r][c] / A[c][c];
+      for (int k = c; k < 5; ++k) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = 4; r >= 0; --r) {
+    double s = b[r];
+    for (int k = r + 1; k < 5; ++k) s -= A[r][k] * x[k];
+    x[r] = s / A[r][r];
+  }
+  return true;
+}
+}  // namespace
+
+// Cylinder refit: fixed number of Gauss-Newton steps on sum (dist_i - r)^2 over the
+// FIXED inlier set of the input hypothesis (test12_in).  Local parametrisation per step:
+// q += al*u + be*w, dir += ga*u + de*w (renormalised), r += dr with (u,w) = perp_basis(dir).
+// All arithmetic in double on the float points.  Returns the inlier count; also the final RMS.
+GMO_API int64_t gmo_refit_cylinder(const float* pts4, int64_t n, const float* model7_in,
+                                   const float* test12_in, int32_t iters, float* model7_out,
+                                   double* rms_out) {
+  const P4* p = (const P4*)pts4;
+  double q[3] = {model7_in[0], model7_in[1], model7_in[2]};
+  double dir[3] = {model7_in[3], model7_in[4], model7_in[5]};
+  double r = model7_in[6];
+  std::vector<int32_t> inl;
+  for (int64_t i = 0; i < n; ++i) if (cyl_inlier(test12_in, p[i])) inl.push_back((int32_t)i);
+  for (int k = 0; k < 7; ++k) model7_out[k] = model7_in[k];
+  if (rms_out) *rms_out = 0.0;
+  if (inl.size() <= 5) return (int64_t)inl.size();
+  for (int32_t it = 0; it < iters; ++it) {
+    double u[3], w[3];
+    perp_basis_d(dir, u, w);
+    double JTJ[5][5] = {{0}}, JTr[5] = {0, 0, 0, 0, 0};
+    for (int32_t i : inl) {
+      double vx = p[i].x - q[0], vy = p[i].y - q[1], vz = p[i].z - q[2];
+      double A = u[0] * vx + u[1] * vy + u[2] * vz;
+      double B = w[0] * vx + w[1] * vy + w[2] * vz;
+      double t = dir[0] * vx + dir[1] * vy + dir[2] * vz;
+      double dist = std::sqrt(A * A + B * B);
+      if (!(dist > 1e-12)) continue;
+      double res = dist - r;
+      double J[5] = {-A / dist, -B / dist, -A * t / dist, -B * t / dist, -1.0};
+      for (int a = 0; a < 5; ++a) { JTr[a] += J[a] * res; for (int b = a; b < 5; ++b) JTJ[a][b] += J[a] * J[b]; }
+    }
+    for (int a = 0; a < 5; ++a) for (int b = 0; b < a; ++b) JTJ[a][b] = JTJ[b][a];
+    double rhs[5], x[5];
+    for (int a = 0; a < 5; ++a) rhs[a] = -JTr[a];
+    if (!solve5(JTJ, rhs, x)) break;
+    for (int k = 0; k < 3; ++k) q[k] += x[0] * u[k] + x[1] * w[k];
+    for (int k = 0; k < 3; ++k) dir[k] += x[2] * u[k] + x[3] * w[k];
+    double dl = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    for (int k = 0; k < 3; ++k) dir[k] /= dl;
+    r += x[4];
+  }
+  double ss = 0.0;
+  {
+    double u[3], w[3];
+    perp_basis_d(dir, u, w);
+    for (int32_t i : inl) {
+      double vx = p[i].x - q[0], vy = p[i].y - q[1], vz = p[i].z - q[2];
+      double A = u[0] * vx + u[1] * vy + u[2] * vz, B = w[0] * vx + w[1] * vy + w[2] * vz;
+      double res = std::sqrt(A * A + B * B) - r;
+      ss += res * res;
+    }
+  }
+  if (rms_out) *rms_out = std::sqrt(ss / (double)inl.size());
+  for (int k = 0; k < 3; ++k) { model7_out[k] = (float)q[k]; model7_out[3 + k] = (float)dir[k]; }
+  model7_out[6] = (float)r;
+  return (int64_t)inl.size();
+}
+
+// Segmentation labels from refined models: 1 = plane inlier, else 2 = cylinder inlier, else 0.
+// plane4 / cyl_test12 may be null (model absent).
+GMO_API void gmo_labels(const float* pts4, int64_t n, const float* plane4, double tau,
+                        const float* cyl_test12, uint8_t* labels) {
+  const P4* p = (const P4*)pts4;
+  const float tf = (float)tau;
+  for (int64_t i = 0; i < n; ++i) {
+    uint8_t l = 0;
+    if (plane4 && plane_inlier(plane4, p[i], tf)) l = 1;
+    else if (cyl_test12 && cyl_inlier(cyl_test12, p[i])) l = 2;
+    labels[i] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// A.10 BUILDER-DEFINED center-axis polyline + cross-sections.
+// Slices of length L along `axis` (unit, the a5 center axis) over t = axis.p, origin t0 =
+// floor(tmin/L)*L.  For points with labels[i]==want (or all if labels null) per slice s:
+//   count, algebraic (Kasa) circle fit of (a,b) = (u.p, w.p), (u,w) = perp_basis_d(axis):
+//   solve [Saa Sab Sa; Sab Sbb Sb; Sa Sb n] [A;B;C] = [Saz; Sbz; Sz], z=a^2+b^2 (centred on the
+//   slice mean), centre=(A/2,B/2), radius=sqrt(C + (A^2+B^2)/4)
+//   local axis = min eigenvector of sum w_i^2 n_i n_i^T over the slice (a5 math per slice),
+//   oriented along +axis.
+// out per slice (12 doubles): cx,cy,cz, dx,dy,dz, radius, count, rms, t_mid, 0, 0
+GMO_API int32_t gmo_polyline(const float* pts4, const float* normals8, const uint8_t* labels,
+                             int64_t n, int want, const float* axis3, double wf, double L,
+                             int32_t max_slices, double* out12, double* t0_out) {
+  const P4* p = (const P4*)pts4;
+  double ax[3] = {axis3[0], axis3[1], axis3[2]};
+  double u[3], w[3];
+  perp_basis_d(ax, u, w);
+  double tmin = 1e300, tmax = -1e300;
+  for (int64_t i = 0; i < n; ++i) {
+    if (labels && labels[i] != want) continue;
+    double t = ax[0] * p[i].x + ax[1] * p[i].y + ax[2] * p[i].z;
+    tmin = std::min(tmin, t); tmax = std::max(tmax, t);
+  }
+  if (tmin > tmax) return 0;
+  double t0 = std::floor(tmin / L) * L;
+  int32_t S = (int32_t)std::floor((tmax - t0) / L) + 1;
+  if (S > max_slices) S = max_slices;
+  if (t0_out) *t0_out = t0;
+  struct Acc { double n, a, b, aa, ab, bb, N[6]; std::vector<int32_t> idx; };
+  std::vector<Acc> acc((size_t)S);
+  for (auto& a : acc) { a.n = a.a = a.b = a.aa = a.ab = a.bb = 0; for (double& v : a.N) v = 0; }
+  const double shift = 0.001 / wf;
+  for (int64_t i = 0; i < n; ++i) {
+    if (labels && labels[i] != want) continue;
+    double t = ax[0] * p[i].x + ax[1] * p[i].y + ax[2] * p[i].z;
+    int32_t s = (int32_t)std::floor((t - t0) / L);
+    if (s < 0 || s >= S) continue;
+    Acc& A = acc[(size_t)s];
+    double a = u[0] * p[i].x + u[1] * p[i].y + u[2] * p[i].z;
+    double b = w[0] * p[i].x + w[1] * p[i].y + w[2] * p[i].z;
+    A.n += 1; A.a += a; A.b += b;
+    A.idx.push_back((int32_t)i);
+    const float* nr = normals8 + i * 8;
+    double tt = (double)nr[4] + shift;
+    double wt = (double)(float)std::exp(tt * tt);
+    double na = wt * nr[0], nb = wt * nr[1], nc = wt * nr[2];
+    A.N[0] += na * na; A.N[1] += na * nb; A.N[2] += na * nc; A.N[3] += nb * nb; A.N[4] += nb * nc; A.N[5] += nc * nc;
+  }
+  for (int32_t s = 0; s < S; ++s) {
+    Acc& A = acc[(size_t)s];
+    double* o = out12 + (size_t)s * 12;
+    for (int k = 0; k < 12; ++k) o[k] = 0.0;
+    o[7] = A.n; o[9] = t0 + (s + 0.5) * L;
+    if (A.n < 3) continue;
+    double ma = A.a / A.n, mb = A.b / A.n;
+    double Saa = 0, Sab = 0, Sbb = 0, Saz = 0, Sbz = 0, Sz = 0;
+    for (int32_t i : A.idx) {
+      double a = u[0] * p[i].x + u[1] * p[i].y + u[2] * p[i].z - ma;
+      double b = w[0] * p[i].x + w[1] * p[i].y + w[2] * p[i].z - mb;
+      double z = a * a + b * b;
+      Saa += a * a; Sab += a * b; Sbb += b * b; Saz += a * z; Sbz += b * z; Sz += z;
+    }
+    // centred data: Sa = Sb = 0  ->  [Saa Sab; Sab Sbb][A;B] = [Saz;Sbz], C = Sz/n
+    double det = Saa * Sbb - Sab * Sab;
+    if (!(std::fabs(det) > 1e-300)) continue;
+    double Ac = (Saz * Sbb - Sbz * Sab) / det, Bc = (Sbz * Saa - Saz * Sab) / det;
+    double ca = 0.5 * Ac, cb = 0.5 * Bc;
+    double rad = std::sqrt(Sz / A.n + ca * ca + cb * cb);
+    double ss = 0;
+    for (int32_t i : A.idx) {
+      double a = u[0] * p[i].x + u[1] * p[i].y + u[2] * p[i].z - ma - ca;
+      double b = w[0] * p[i].x + w[1] * p[i].y + w[2] * p[i].z - mb - cb;
+      double e = std::sqrt(a * a + b * b) - rad;
+      ss += e * e;
+    }
+    double ctr_a = ma + ca, ctr_b = mb + cb, tm = o[9];
+    o[0] = ctr_a * u[0] + ctr_b * w[0] + tm * ax[0];
+    o[1] = ctr_a * u[1] + ctr_b * w[1] + tm * ax[1];
+    o[2] = ctr_a * u[2] + ctr_b * w[2] + tm * ax[2];
+    double Nm[9] = {A.N[0], A.N[1], A.N[2], A.N[1], A.N[3], A.N[4], A.N[2], A.N[4], A.N[5]};
+    double vals[3], vecs[9];
+    jacobi3(Nm, vals, vecs);
+    double d[3] = {vecs[0], vecs[3], vecs[6]};
+    if (d[0] * ax[0] + d[1] * ax[1] + d[2] * ax[2] < 0) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
+    o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
+    o[6] = rad; o[8] = std::sqrt(ss / A.n);
+  }
+  return S;
+}
+
+GMO_API int32_t gmo_num_threads() { return resolve_threads(0); }
+GMO_API int32_t gmo_version() { return 1; }

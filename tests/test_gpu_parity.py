@@ -1,0 +1,413 @@
+"""GPU parity: the CUDA path (through the C-ABI, via ctypes) against the CPU oracle on the same
+seeded inputs.  Integer / index outputs are compared bit-exactly; floating-point outputs within
+the tolerance written next to each check (north_star: coefficients within 1e-4 relative).
+"""
+import numpy as np
+import pytest
+
+from geometric_mapping_b200 import capi, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TAU = 0.05
+
+
+def _angle(a, b):
+    a = a / np.linalg.norm(a, axis=-1, keepdims=True)
+    b = b / np.linalg.norm(b, axis=-1, keepdims=True)
+    return np.arccos(np.clip(np.abs((a * b).sum(-1)), -1.0, 1.0))
+
+
+def _ctx(n, **kw):
+    return capi.Context(capi.default_params(**kw), max_points=max(n, 1), max_hypotheses=4096)
+
+
+def _scan_with_junk(n=60_000, seed=11):
+    pts = synth.curved_tunnel(n, seed=seed, outlier_frac=0.02)
+    g = np.random.Generator(np.random.Philox(seed + 1))
+    # points outside the crop box, exactly on its faces, and NaN / inf coordinates
+    pts[g.choice(n, 500, replace=False), 0] += 20.0
+    pts[7] = [5.0, -5.0, 5.0, 1.0]
+    pts[8] = [np.nextafter(np.float32(5.0), np.float32(6.0)), 0.0, 0.0, 1.0]
+    pts[9] = [np.nan, 0.0, 0.0, 1.0]
+    pts[10] = [0.0, np.inf, 0.0, 1.0]
+    pts[11] = [0.0, 0.0, -np.inf, 1.0]
+    return pts
+
+
+# ---- a1 crop -------------------------------------------------------------------------------
+@pytest.mark.parametrize("is_dense", [1, 0])
+def test_crop_bit_exact(is_dense):
+    pts = _scan_with_junk()
+    ref, _ = O.crop(pts, 5.0, bool(is_dense))
+    with _ctx(len(pts), is_dense=is_dense) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        out = ctx.download_cloud(0)
+    assert out.shape == ref.shape
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))  # order and bits, NaN included
+
+
+def test_crop_empty_and_tiny():
+    with _ctx(16) as ctx:
+        ctx.upload_scan(np.zeros((0, 4), np.float32))
+        ctx.crop()
+        assert ctx.counts().n_cropped == 0
+        one = np.array([[1, 2, 3, 1]], np.float32)
+        ctx.upload_scan(one)
+        ctx.crop()
+        assert np.array_equal(ctx.download_cloud(0), one)
+        far = np.array([[100, 0, 0, 1]], np.float32)
+        ctx.upload_scan(far)
+        ctx.crop()
+        assert ctx.counts().n_cropped == 0
+
+
+# ---- a2/a3 normals + compaction ------------------------------------------------------------
+@pytest.mark.parametrize("radius", [0.15, 0.3])
+def test_normals_parity(radius):
+    pts = _scan_with_junk(40_000)
+    cropped, _ = O.crop(pts, 5.0, True)
+    ref, ref_cnt, truth = O.normals(cropped, radius, mode=0, order=0, truth=True)
+    with _ctx(len(pts), neighborRadius=radius) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        got = ctx.download_normals(0)
+        cnt = ctx.download_neighbor_counts()
+        vmap = ctx.download_valid_map()
+        cloud_c = ctx.download_cloud(1)
+        normals_c = ctx.download_normals(1)
+        assert ctx.counts().device_error == 0
+    # neighbour sets: exact (same strict d2 < r2 predicate in unfused float)
+    assert np.array_equal(cnt, ref_cnt)
+    # NaN pattern and compaction: exact
+    ref_nan = ~np.isfinite(ref[:, :3]).all(1)
+    assert np.array_equal(~np.isfinite(got[:, :3]).all(1), ref_nan)
+    rc, rn, rmap = O.compact(cropped, got)
+    assert np.array_equal(vmap, rmap)
+    assert np.array_equal(cloud_c.view(np.uint32), rc.view(np.uint32))
+    assert np.array_equal(normals_c.view(np.uint32), rn.view(np.uint32))
+    # normals / curvature: float, accumulation order differs (PCL sums in distance order) and the
+    # single-pass covariance is ill-conditioned, so compare against the double-precision truth:
+    # the GPU may not be further from it than the float oracle is, up to a small slack.
+    ok = ~ref_nan & (ref_cnt >= 8)
+    ang_gpu = _angle(got[ok, :3].astype(np.float64), truth[ok, :3])
+    ang_ref = _angle(ref[ok, :3].astype(np.float64), truth[ok, :3])
+    # well-conditioned neighbourhoods (curvature not tiny relative to float noise)
+    assert np.median(ang_gpu) <= 2.0 * np.median(ang_ref) + 1e-4
+    assert np.quantile(ang_gpu, 0.99) <= 2.0 * np.quantile(ang_ref, 0.99) + 2e-3
+    ang = _angle(got[ok, :3].astype(np.float64), ref[ok, :3].astype(np.float64))
+    assert np.quantile(ang, 0.99) < 2e-2  # rad, GPU vs float oracle
+    dc = np.abs(got[ok, 4] - ref[ok, 4])
+    assert np.quantile(dc, 0.99) < 5e-3
+    # orientation: flipped towards the viewpoint (origin)
+    dots = -(cropped[ok, :3] * got[ok, :3]).sum(1)
+    assert (dots >= -1e-6).all()
+    # pcl::Normal padding
+    assert (got[~ref_nan][:, [3, 5, 6, 7]] == 0).all()
+
+
+def test_normals_small_exact_brute_force():
+    pts = synth.straight_cylinder(3000, seed=3, noise=0.005)
+    ref, ref_cnt, _ = O.normals(pts, 0.4, mode=1, order=0)
+    with _ctx(len(pts), neighborRadius=0.4) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        cnt = ctx.download_neighbor_counts()
+        got = ctx.download_normals(0)
+    assert np.array_equal(cnt, ref_cnt)
+    ok = ref_cnt >= 3
+    assert np.quantile(_angle(got[ok, :3].astype(np.float64), ref[ok, :3].astype(np.float64)), 0.99) < 1e-2
+
+
+def test_normals_isolated_points_become_nan_and_are_dropped():
+    pts = np.array([[0, 0, 0, 1], [0.01, 0, 0, 1], [3, 3, 3, 1], [0, 0.01, 0, 1], [0.01, 0.01, 0.002, 1]], np.float32)
+    with _ctx(8, neighborRadius=0.05) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        cnt = ctx.download_neighbor_counts()
+        vmap = ctx.download_valid_map()
+        c = ctx.counts()
+    assert list(cnt) == [4, 4, 1, 4, 4]
+    assert list(vmap) == [0, 1, -1, 2, 3]
+    assert c.n_valid == 4
+
+
+# ---- a4 voxel grid + 1-NN --------------------------------------------------------------------
+@pytest.mark.parametrize("leaf,radius", [(0.1, 0.15), (0.5, 0.3), (0.07, 0.25)])
+def test_voxel_bit_exact(leaf, radius):
+    pts = _scan_with_junk(50_000, seed=21)
+    cropped, _ = O.crop(pts, 5.0, True)
+    with _ctx(len(pts), neighborRadius=radius, voxelGridLeafSize=leaf) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        ctx.voxel()
+        cloud_c = ctx.download_cloud(1)
+        normals_c = ctx.download_normals(1)
+        vmap = ctx.download_valid_map()
+        keys, assign, st = ctx.download_voxel_assignment()
+        vox = ctx.download_voxels()
+        grid6 = ctx.voxel_grid()
+        c = ctx.counts()
+    ref = O.voxel(cloud_c, leaf)
+    assert c.n_voxels == ref["V"] and st == capi.GM_OK
+    assert np.array_equal(grid6, ref["grid6"])
+    assert np.array_equal(keys, ref["keys"])          # voxel keys: bit-exact
+    assert np.array_equal(assign, ref["assign"])      # point -> voxel rank: bit-exact
+    assert np.array_equal(vox["keys"], ref["voxel_keys"])
+    assert np.array_equal(vox["counts"], ref["voxel_counts"])
+    # centroids: same summation order as the oracle's canonical (stable) order -> bit-exact
+    assert np.array_equal(vox["centroids"].view(np.uint32), ref["centroids"].view(np.uint32))
+    # 1-NN over the PRE-compaction cloud (quirk B.3), exact, ties -> lowest index
+    finite = np.isfinite(cropped[:, :3]).all(1)
+    search = cropped.copy()
+    search[~finite, :3] = 1e30  # never the nearest
+    ref_idx, _ = O.nn1(vox["centroids"], search)
+    assert np.array_equal(vox["nn_index"], ref_idx)
+    inr = ref_idx < c.n_valid
+    assert np.array_equal(vox["nn_normal"][inr].view(np.uint32), normals_c[ref_idx[inr]].view(np.uint32))
+    assert c.nn_out_of_range == int((~inr).sum())
+
+
+def test_voxel_fixed_nn_mode_indexes_compacted_cloud():
+    pts = _scan_with_junk(30_000, seed=5)
+    with _ctx(len(pts), neighborRadius=0.12, voxelGridLeafSize=0.2, nn_index_mode=1) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        ctx.voxel()
+        cloud_c = ctx.download_cloud(1)
+        normals_c = ctx.download_normals(1)
+        vox = ctx.download_voxels()
+        c = ctx.counts()
+    assert c.n_valid < c.n_cropped  # some normals were NaN, so the two modes differ
+    ref_idx, _ = O.nn1(vox["centroids"], cloud_c)
+    assert np.array_equal(vox["nn_index"], ref_idx)
+    assert np.array_equal(vox["nn_normal"].view(np.uint32), normals_c[ref_idx].view(np.uint32))
+    assert vox["status"] == capi.GM_OK
+
+
+def test_voxel_lattice_known_keys_and_overflow_rule():
+    # points on a lattice: known keys
+    g = np.arange(-2, 3, dtype=np.float32) * 0.25 + 0.01
+    xx, yy, zz = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel(), np.ones(xx.size)], 1).astype(np.float32)
+    with _ctx(len(pts), voxelGridLeafSize=0.25) as ctx:
+        ctx.inject_compacted(pts)
+        ctx.voxel()
+        keys, assign, st = ctx.download_voxel_assignment()
+        vox = ctx.download_voxels(with_nn=False)
+    ref = O.voxel(pts, 0.25)
+    assert np.array_equal(keys, ref["keys"]) and np.array_equal(assign, ref["assign"])
+    assert len(np.unique(keys)) == 125 and ref["V"] == 125
+    assert np.array_equal(vox["centroids"].view(np.uint32), ref["centroids"].view(np.uint32))
+    # overflow rule: leaf so small that dx*dy*dz > INT32_MAX -> cloud returned unchanged
+    big = synth.straight_cylinder(5000, seed=9)
+    with _ctx(len(big), voxelGridLeafSize=0.001) as ctx:
+        ctx.inject_compacted(big)
+        ctx.voxel()
+        vox = ctx.download_voxels(with_nn=False)
+        c = ctx.counts()
+    ref = O.voxel(big, 0.001)
+    assert ref["status"] == 1 and c.voxel_overflow == 1 and vox["status"] == capi.GM_WARN_VOXEL_OVERFLOW
+    assert c.n_voxels == len(big)
+    assert np.array_equal(vox["centroids"][:, :3], big[:, :3])
+
+
+# ---- a5 local frame + a6 markers -----------------------------------------------------------------
+def _frame_close(fr, ref):
+    scale = np.abs(ref["vals"]).max()
+    assert np.abs(fr["scatter"] - ref["scatter"]).max() <= 1e-4 * scale          # 1e-4 relative to ||S||
+    assert np.abs(fr["scatter"].astype(np.float64) - ref["scatter_truth"]).max() <= 2e-6 * scale
+    assert np.abs(fr["vals"] - ref["vals"]).max() <= 1e-4 * scale
+    # axis (eigenvector 0) up to sign; the other two only as a subspace (near-degenerate pair)
+    assert _angle(fr["vecs"][:, 0].astype(np.float64), ref["vecs"][:, 0].astype(np.float64)) < 1e-3
+    assert abs(np.dot(fr["vecs"][:, 0], ref["vecs"][:, 1])) < 2e-3 and abs(np.dot(fr["vecs"][:, 0], ref["vecs"][:, 2])) < 2e-3
+
+
+def test_local_frame_parity_and_known_answer():
+    pts = synth.straight_cylinder(50_000, seed=1, noise=0.01)
+    with _ctx(len(pts), neighborRadius=0.2) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        ctx.local_frame()
+        normals_c = ctx.download_normals(1)
+        fr = ctx.frame()
+    ref = O.local_frame(normals_c, 0.2)
+    _frame_close(fr, ref)
+    # known answer (src/tunnel_processing.cpp:91): min eigenvector = cylinder axis (x)
+    assert abs(abs(fr["vecs"][0, 0]) - 1.0) < 1e-3
+    assert fr["vals"][0] < 1e-2 * fr["vals"][2]
+    # a6: arrow payload of rvizEigens
+    arrows = capi.markers_eigen(fr["_struct"])
+    refm = O.eigen_markers(fr["vals"], fr["vecs"])
+    for i in range(3):
+        assert np.array_equal(arrows[i]["start"], refm[i, 0:3])
+        assert np.array_equal(arrows[i]["end"], refm[i, 3:6])
+        assert np.array_equal(arrows[i]["scale"], refm[i, 6:9])
+    assert arrows["color_argb"].tolist() == [[1, 1, 0, 0], [1, 0, 1, 0], [1, 0, 0, 1]]
+
+
+def test_local_frame_injected_normals():
+    g = np.random.Generator(np.random.Philox(4))
+    n = 200_000
+    nr = np.zeros((n, 8), np.float32)
+    v = g.normal(size=(n, 3))
+    v[:, 2] *= 0.05
+    nr[:, :3] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    nr[:, 4] = g.uniform(0, 0.3, n)
+    pts = np.ones((n, 4), np.float32)
+    with _ctx(n, weightingFactor=0.13) as ctx:
+        ctx.inject_compacted(pts, nr)
+        ctx.local_frame()
+        fr = ctx.frame()
+    _frame_close(fr, O.local_frame(nr, 0.13))
+
+
+# ---- a8 RANSAC (builder-defined; oracle = builder restatement of the PCL semantics) --------------
+def _compacted_scan(n=80_000, seed=31, radius=0.15):
+    pts = synth.curved_tunnel(n, seed=seed)
+    cropped, _ = O.crop(pts, 5.0, True)
+    nr, _, _ = O.normals(cropped, radius)
+    return O.compact(cropped, nr)[:2]
+
+
+def test_ransac_plane_counts_bit_exact_and_refit():
+    cloud, nrm = _compacted_scan()
+    H = 700
+    samples = synth.sample_indices(len(cloud), H, 3, seed=3)
+    samples[5] = [1, 1, 2]            # duplicate index -> degenerate
+    samples[6] = [0, 1, len(cloud)]   # out of range -> degenerate
+    coef, valid = O.plane_hypotheses(cloud, samples)
+    counts = O.count_plane(cloud, coef, valid, TAU)
+    with _ctx(len(cloud), ransacThreshold=TAU) as ctx:
+        ctx.inject_compacted(cloud, nrm)
+        ctx.ransac(capi.GM_MODEL_PLANE, samples)
+        gcoef, _, gcounts = ctx.download_hypotheses(capi.GM_MODEL_PLANE, H)
+        ctx.ransac_select(capi.GM_MODEL_PLANE)
+        m = ctx.model(capi.GM_MODEL_PLANE)
+    assert np.array_equal(gcoef.view(np.uint32), coef.view(np.uint32))  # hypothesis generation: bit-exact
+    assert np.array_equal(gcounts, counts)                                # inlier counts: bit-exact
+    assert counts[5] == -1 and counts[6] == -1
+    best = O.argmax(counts)
+    assert m["best_id"] == best and m["best_count"] == counts[best]
+    ref_coef, ref_cnt = O.refit_plane(cloud, coef[best], TAU)
+    assert m["refit_count"] == ref_cnt
+    assert np.abs(m["coef"] - ref_coef).max() <= 1e-4 * max(1.0, np.abs(ref_coef).max())
+    # the floor of the synthetic tunnel is z = -1.5
+    assert abs(abs(m["coef"][2]) - 1.0) < 1e-3 and abs(abs(m["coef"][3]) - 1.5) < 5e-3
+
+
+def test_ransac_cylinder_counts_bit_exact_and_refit():
+    cloud, nrm = _compacted_scan()
+    H = 600
+    samples = synth.sample_indices(len(cloud), H, 2, seed=4)
+    samples[3] = [9, 9]
+    m7, t12, valid = O.cyl_hypotheses(cloud, nrm, samples, 0.5, 10.0, TAU)
+    counts = O.count_cyl(cloud, t12, valid)
+    with _ctx(len(cloud), ransacThreshold=TAU) as ctx:
+        ctx.inject_compacted(cloud, nrm)
+        ctx.ransac(capi.GM_MODEL_CYLINDER, samples)
+        gm7, gt12, gcounts = ctx.download_hypotheses(capi.GM_MODEL_CYLINDER, H)
+        ctx.ransac_select(capi.GM_MODEL_CYLINDER)
+        m = ctx.model(capi.GM_MODEL_CYLINDER)
+    assert np.array_equal(gm7.view(np.uint32), m7.view(np.uint32))
+    assert np.array_equal(gt12.view(np.uint32), t12.view(np.uint32))
+    assert np.array_equal(gcounts, counts)
+    assert counts[3] == -1 and (counts >= 0).sum() > H // 4
+    best = O.argmax(counts)
+    assert m["best_id"] == best and m["best_count"] == counts[best]
+    ref_m, ref_cnt, ref_rms = O.refit_cylinder(cloud, m7[best], t12[best], 5)
+    assert m["refit_count"] == ref_cnt
+    # axis direction and radius within 1e-4 relative; the axis point q is only defined up to a
+    # shift along the axis, so compare its distance from the reference axis line
+    assert _angle(m["coef"][3:6].astype(np.float64), ref_m[3:6].astype(np.float64)) < 1e-4
+    assert abs(m["coef"][6] - ref_m[6]) <= 1e-4 * ref_m[6]
+    dq = (m["coef"][:3] - ref_m[:3]).astype(np.float64)
+    d = ref_m[3:6].astype(np.float64)
+    assert np.linalg.norm(dq - d * dq.dot(d)) <= 1e-4 * ref_m[6]
+    assert abs(m["rms"] - ref_rms) <= 1e-4 * max(ref_rms, 1e-3)
+    assert abs(m["coef"][6] - 2.5) < 0.05  # the synthetic tunnel radius
+
+
+def test_ransac_hypothesis_sharding_matches_single_range():
+    """Multi-GPU contract emulated on one device: two half-ranges, max of the packed keys."""
+    cloud, nrm = _compacted_scan(40_000, seed=41)
+    H = 512
+    samples = synth.sample_indices(len(cloud), H, 3, seed=8)
+    with _ctx(len(cloud)) as ctx:
+        ctx.inject_compacted(cloud, nrm)
+        ctx.ransac(capi.GM_MODEL_PLANE, samples)
+        _, _, full = ctx.download_hypotheses(capi.GM_MODEL_PLANE, H)
+        parts = []
+        for lo, hi in ((0, 256), (256, 512)):
+            ctx.ransac(capi.GM_MODEL_PLANE, samples, lo, hi)
+            _, _, c = ctx.download_hypotheses(capi.GM_MODEL_PLANE, H)
+            assert (c[:lo] == -1).all() and (c[hi:] == -1).all()
+            parts.append(c[lo:hi])
+    assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_ransac_all_degenerate_reports_no_model():
+    cloud, nrm = _compacted_scan(20_000, seed=43)
+    samples = np.zeros((64, 3), np.int32)
+    with _ctx(len(cloud)) as ctx:
+        ctx.inject_compacted(cloud, nrm)
+        ctx.ransac(capi.GM_MODEL_PLANE, samples)
+        ctx.ransac_select(capi.GM_MODEL_PLANE)
+        m = ctx.model(capi.GM_MODEL_PLANE)
+    assert m["status"] == capi.GM_ERR_NO_MODEL and m["best_id"] == -1
+
+
+# ---- fused path -----------------------------------------------------------------------------------
+def test_process_scan_end_to_end_against_oracle_chain():
+    n = 120_000
+    radius, leaf = 0.12, 0.1
+    pts = synth.curved_tunnel(n, seed=2)
+    with _ctx(n, neighborRadius=radius, voxelGridLeafSize=leaf, sliceLength=1.0) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        c0 = ctx.counts()
+        ps = synth.sample_indices(c0.n_valid, 512, 3, seed=3)
+        cs = synth.sample_indices(c0.n_valid, 512, 2, seed=4)
+        ctx.upload_scan(pts)
+        ctx.process_scan(ps, cs)
+        c = ctx.counts()
+        cloud_c, normals_c = ctx.download_cloud(1), ctx.download_normals(1)
+        fr = ctx.frame()
+        mp, mc = ctx.model(capi.GM_MODEL_PLANE), ctx.model(capi.GM_MODEL_CYLINDER)
+        labels = ctx.download_labels()
+        poly = ctx.download_polyline()
+        _, _, pc = ctx.download_hypotheses(capi.GM_MODEL_PLANE, 512)
+        _, _, cc = ctx.download_hypotheses(capi.GM_MODEL_CYLINDER, 512)
+    assert c.device_error == 0 and c.n_valid == c0.n_valid
+    # oracle chain on the GPU's own compacted cloud/normals (stage inputs identical)
+    coef, valid = O.plane_hypotheses(cloud_c, ps)
+    assert np.array_equal(pc, O.count_plane(cloud_c, coef, valid, TAU))
+    m7, t12, cvalid = O.cyl_hypotheses(cloud_c, normals_c, cs, 0.5, 10.0, TAU)
+    assert np.array_equal(cc, O.count_cyl(cloud_c, t12, cvalid))
+    # labels from the GPU's refined models, evaluated by the oracle: bit-exact
+    ref_labels = O.labels(cloud_c, mp["coef"], TAU, O.cyl_test_params(mc["coef"], TAU)[0])
+    assert np.array_equal(labels, ref_labels)
+    assert (labels == 1).mean() > 0.1 and (labels == 2).mean() > 0.2
+    # polyline vs oracle
+    ref_poly, _ = O.polyline(cloud_c, normals_c, labels, 2, fr["vecs"][:, 0], 0.2, 1.0, 256)
+    assert len(poly) == len(ref_poly) and len(poly) >= 8
+    for s in range(len(poly)):
+        assert poly["count"][s] == int(ref_poly[s, 7])
+        if ref_poly[s, 7] < 50:
+            continue
+        assert np.abs(poly["center"][s] - ref_poly[s, 0:3]).max() <= 1e-4 * 5.0
+        assert abs(poly["radius"][s] - ref_poly[s, 6]) <= 1e-4 * ref_poly[s, 6]
+        assert abs(poly["rms"][s] - ref_poly[s, 8]) <= 1e-4 * max(ref_poly[s, 8], 1e-2)
+        assert _angle(poly["dir"][s].astype(np.float64), ref_poly[s, 3:6]) < 1e-3
+    # cross-section radius ~ tunnel radius in well-populated slices
+    good = poly["count"] > 2000
+    assert np.abs(poly["radius"][good] - 2.5).max() < 0.1

@@ -481,7 +481,7 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
       int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE), div_up(ctx->num_sms * 4, groups)));
       dim3 grid(slices, groups);
       if (kind == 0) {
-        GM_LAUNCH(ctx, k_count_plane<4>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, h_begin, h_end,
+        GM_LAUNCH(ctx, k_count_plane<4>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, ctx->d_hvalid[0], h_begin, h_end,
                   (float)ctx->prm.ransacThreshold, ctx->d_counts[0]);
       } else {
         GM_LAUNCH(ctx, k_count_cyl<2>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_test12, h_begin, h_end, ctx->d_counts[1]);

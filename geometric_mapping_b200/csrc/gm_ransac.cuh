@@ -163,7 +163,7 @@ constexpr int RC_TILE = 512;  // points staged per iteration
 template <int K>
 __global__ void __launch_bounds__(RC_BLOCK)
 k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float4* __restrict__ coef,
-              int h_begin, int h_end, float tau, int* __restrict__ counts) {
+              const int* __restrict__ valid, int h_begin, int h_end, float tau, int* __restrict__ counts) {
   __shared__ float4 s_pts[RC_TILE];
   const int n = *n_ptr;
   const int per = (((n + gridDim.x - 1) / gridDim.x) + RC_TILE - 1) / RC_TILE * RC_TILE;
@@ -174,7 +174,8 @@ k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, con
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     int h = hbase + k * RC_BLOCK;
-    c[k] = (h < h_end) ? coef[h] : make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
+    // degenerate hypotheses (all-zero coefficients) must never match: d = +inf
+    c[k] = (h < h_end && valid[h]) ? coef[h] : make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
     cnt[k] = 0;
   }
   for (int base = p_begin; base < p_end; base += RC_TILE) {

@@ -422,6 +422,50 @@ GMO_API void gmo_nn1(const float* query4, int64_t nq, const float* pts4, int64_t
   }
 }
 
+
+// Same result as gmo_nn1 (exact 1-NN, ties -> lowest index) but accelerated with a hash grid and
+// an expanding-ring search, so that the CPU baseline finishes at 1e6 points.  tests/ checks it
+// against the brute-force form.  `cell` is the grid resolution (any positive value is correct).
+GMO_API void gmo_nn1_grid(const float* query4, int64_t nq, const float* pts4, int64_t n, double cell,
+                          int32_t* idx_out, float* d2_out, int nthreads) {
+  const P4* p = (const P4*)pts4;
+  HashGrid grid;
+  grid.build(p, n, cell);
+  int64_t lo[3] = {INT64_MAX, INT64_MAX, INT64_MAX}, hi[3] = {INT64_MIN, INT64_MIN, INT64_MIN};
+  for (int64_t i = 0; i < n; ++i) {
+    if (!std::isfinite(p[i].x) || !std::isfinite(p[i].y) || !std::isfinite(p[i].z)) continue;
+    int64_t c[3] = {(int64_t)std::floor(p[i].x * grid.inv), (int64_t)std::floor(p[i].y * grid.inv), (int64_t)std::floor(p[i].z * grid.inv)};
+    for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], c[a]); hi[a] = std::max(hi[a], c[a]); }
+  }
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 64)
+  for (int64_t q = 0; q < nq; ++q) {
+    const float* qq = query4 + q * 4;
+    float best = std::numeric_limits<float>::infinity();
+    int32_t bi = -1;
+    if (lo[0] <= hi[0]) {
+      int64_t c[3] = {(int64_t)std::floor(qq[0] * grid.inv), (int64_t)std::floor(qq[1] * grid.inv), (int64_t)std::floor(qq[2] * grid.inv)};
+      int64_t kmax = 0;
+      for (int a = 0; a < 3; ++a) kmax = std::max<int64_t>(kmax, std::max<int64_t>(std::llabs(c[a] - lo[a]), std::llabs(c[a] - hi[a])));
+      for (int64_t k = 0; k <= kmax; ++k) {
+        for (int64_t dz = -k; dz <= k; ++dz) for (int64_t dy = -k; dy <= k; ++dy) for (int64_t dx = -k; dx <= k; ++dx) {
+          if (std::max<int64_t>(std::llabs(dx), std::max<int64_t>(std::llabs(dy), std::llabs(dz))) != k) continue;
+          auto it = grid.cells.find(HashGrid::key(c[0] + dx, c[1] + dy, c[2] + dz));
+          if (it == grid.cells.end()) continue;
+          for (int j : it->second) {
+            float d2 = flann_d2(qq, &p[j].x);
+            if (d2 < best || (d2 == best && j < bi)) { best = d2; bi = j; }
+          }
+        }
+        double lim = (double)k * grid.cell * 0.999;
+        if (bi >= 0 && (double)best <= lim * lim) break;
+      }
+    }
+    idx_out[q] = bi;
+    if (d2_out) d2_out[q] = best;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // a5  getLocalFrame (src/tunnel_processing.cpp:92-148), diagonal restatement of the dense
 // n x n product (bit-identical: SURVEY 8 a5).

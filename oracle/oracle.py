@@ -106,6 +106,15 @@ def nn1(query, pts, nthreads=0):
     return idx, d2
 
 
+def nn1_grid(query, pts, cell, nthreads=0):
+    query, pts = _f32(query), _f32(pts)
+    idx = np.empty(query.shape[0], np.int32)
+    d2 = np.empty(query.shape[0], np.float32)
+    lib().gmo_nn1_grid(_p(query), C.c_int64(query.shape[0]), _p(pts), C.c_int64(pts.shape[0]), C.c_double(cell), _p(idx),
+                       _p(d2), C.c_int(nthreads))
+    return idx, d2
+
+
 def local_frame(normals8, wf):
     normals8 = _f32(normals8)
     S, vals, vecs = np.empty(9, np.float32), np.empty(3, np.float32), np.empty(9, np.float32)

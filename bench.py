@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — points/s of the per-scan hot path (crop -> normals -> voxel -> local frame -> RANSAC
+plane+cylinder -> refit -> labels -> polyline) on synthetic 1M-point curved-tunnel scans.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU oracle (reference arm)
+
+Contract (see the task statement): one JSON line on stdout from rank 0.
+  value     whole-job input points/s, scans already resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the C-ABI with HOST (pinned) buffers: H2D of the scan and D2H of the
+            published results inside the timed region (3 contexts pipelined on 3 streams)
+  roofline  the dominant kernel family, CUDA-event timed per segment inside this run
+  cpu_baseline  the CPU oracle on this box's host cores (rank 0, N=1)
+N>1: frame-parallel (each rank processes its own scans, no data-path collective; weak scaling) plus
+a hypothesis-sharded RANSAC leg (4096 hypotheses split across ranks, NCCL max-allreduce of the
+packed (count,id) key) reported under "ransac".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TAU = 0.05
+RING = 12  # distinct resident scans cycled through: 12 x 16 MB = 192 MB > 126 MB L2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--hyp", type=int, default=1024, help="total RANSAC hypotheses (half plane, half cylinder)")
+    ap.add_argument("--shard-hyp", type=int, default=4096, help="hypotheses of the sharded RANSAC leg (N>1)")
+    ap.add_argument("--radius", type=float, default=0.05)
+    ap.add_argument("--leaf", type=float, default=0.1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-points", type=int, default=0, help="points of the CPU baseline sample (0 = full scan)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C1 synthetic curved tunnel + floor + noise, {a.points} pts/scan, {a.hyp // 2} plane + {a.hyp - a.hyp // 2} "
+            f"cylinder hypotheses, r={a.radius} leaf={a.leaf} tau={TAU}")
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference path, stage by stage (used by cpu_baseline
+# and --impl reference; never by the product)
+def cpu_process_scan(O, pts, a, ps, cs, nthreads):
+    cropped, _ = O.crop(pts, 5.0, True)
+    nr, _, _ = O.normals(cropped, a.radius, mode=0, order=0, nthreads=nthreads)
+    cloud, nrm, _ = O.compact(cropped, nr)
+    vox = O.voxel(cloud, a.leaf)
+    O.nn1_grid(vox["centroids"], cropped, a.radius * 1.001, nthreads=nthreads)
+    fr = O.local_frame(nrm, 0.2)
+    out = {"n_valid": len(cloud), "V": vox["V"]}
+    if ps is not None and len(ps):
+        ps = np.minimum(ps, max(len(cloud) - 1, 0))
+        coef, valid = O.plane_hypotheses(cloud, ps)
+        counts = O.count_plane(cloud, coef, valid, TAU, nthreads=nthreads)
+        b = O.argmax(counts)
+        plane, _ = O.refit_plane(cloud, coef[b], TAU) if b >= 0 else (None, 0)
+    else:
+        plane = None
+    if cs is not None and len(cs):
+        cs = np.minimum(cs, max(len(cloud) - 1, 0))
+        m7, t12, cvalid = O.cyl_hypotheses(cloud, nrm, cs, 0.5, 10.0, TAU)
+        counts = O.count_cyl(cloud, t12, cvalid, nthreads=nthreads)
+        b = O.argmax(counts)
+        cyl = O.refit_cylinder(cloud, m7[b], t12[b], 5)[0] if b >= 0 else None
+    else:
+        cyl = None
+    lab = O.labels(cloud, plane, TAU, None if cyl is None else O.cyl_test_params(cyl, TAU)[0])
+    O.polyline(cloud, nrm, lab, 2, fr["vecs"][:, 0], 0.2, 1.0, 256)
+    return out
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    from geometric_mapping_b200 import synth
+    from oracle import oracle as O
+
+    threads = O.num_threads()
+    n = a.points
+    pts = synth.curved_tunnel(n, seed=2)
+    ps = synth.sample_indices(n, a.hyp // 2, 3, seed=3)
+    cs = synth.sample_indices(n, a.hyp - a.hyp // 2, 2, seed=4)
+    for _ in range(max(a.warmup, 1)):
+        cpu_process_scan(O, pts, a, ps, cs, threads)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_process_scan(O, pts, a, ps, cs, threads)
+    dt = time.perf_counter() - t0
+    v = n * a.steps / dt
+    line = {
+        "impl": "reference", "metric": "input points/s, per-scan segmentation+fit", "value": v, "unit": "points/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "l2": "host"},
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": f"{a.steps} full {n}-point scans per run; OpenMP over points (normals, 1-NN) and "
+                                   f"hypotheses (counting), serial elsewhere; parity unpinned"},
+        "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4,
+                 "hw_power_brake": 0x80}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from geometric_mapping_b200 import capi, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, Hp, Hc = a.points, a.hyp // 2, a.hyp - a.hyp // 2
+    params = capi.default_params(neighborRadius=a.radius, voxelGridLeafSize=a.leaf, ransacThreshold=TAU)
+    stream = torch.cuda.current_stream()
+
+    # ---- synthetic ring of scans: distinct per slot and per rank (frame-parallel = weak scaling)
+    host_scans, dev_scans = [], []
+    for s in range(RING):
+        pts = synth.curved_tunnel(n, seed=2 + s + 1000 * rank, advance=0.0)
+        hp = torch.from_numpy(pts).pin_memory()
+        host_scans.append(hp)
+        dev_scans.append(hp.to(dev, non_blocking=False))
+    ctx = capi.Context(params, max_points=n, max_hypotheses=max(4096, a.shard_hyp))
+    ctx.set_stream(stream.cuda_stream)
+
+    # sample indices need the compacted size of each scan: learn it once (untimed)
+    samples = []
+    n_valid = []
+    for s in range(RING):
+        ctx.set_scan_device(dev_scans[s].data_ptr(), n)
+        ctx.crop()
+        ctx.normals()
+        nv = ctx.counts().n_valid
+        n_valid.append(nv)
+        samples.append((synth.sample_indices(nv, Hp, 3, seed=3 + s), synth.sample_indices(nv, Hc, 2, seed=4 + s)))
+
+    def step(i):
+        s = i % RING
+        ctx.set_scan_device(dev_scans[s].data_ptr(), n)
+        ctx.process_scan(samples[s][0], samples[s][1])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    ctx.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(a.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count
+    clocks = sampler.stop()
+    c = ctx.counts()
+    if c.device_error:
+        raise SystemExit("device-side error flag set")
+    value = world * n * a.steps / (ms * 1e-3)
+
+    # ---- per-segment timing of the same steps (roofline) ------------------------------------------
+    ctx.profile_enable(True)
+    for i in range(a.steps):
+        step(i)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    seg_ms = {k: (v[0] / max(a.steps, 1)) for k, v in prof.items()}
+    M = float(np.mean(n_valid))
+    V = float(c.n_voxels)
+    hbm_peak, peak_src = load_peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    clk = clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965.0
+    fp32_peak_tflops = sms * 128 * 2 * clk * 1e6 / 1e12
+    count_ms = seg_ms["plane_count"] + seg_ms["cyl_count"]
+    count_flops = M * (Hp * 6.0 + Hc * 16.0)
+    count_tflops = count_flops / (count_ms * 1e-3) / 1e12 if count_ms > 0 else 0.0
+    P = 3
+    vox_bytes = 16.0 * n + (68.0 + 16.0 * P) * M + 20.0 * V
+    vox_ms = seg_ms["crop"] + seg_ms["voxel_keys"] + seg_ms["voxel_sort"] + seg_ms["voxel_reduce"]
+    vox_gbs = vox_bytes / (vox_ms * 1e-3) / 1e9 if vox_ms > 0 else 0.0
+    nbr_mean = 50.0
+    nrm_ms = seg_ms["normals"]
+    families = {
+        "inlier_count": {"bound": "fp32", "achieved": count_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                         "frac": count_tflops / fp32_peak_tflops, "traffic": None, "ms_per_step": count_ms,
+                         "kernels": "k_count_plane + k_count_cyl",
+                         "algorithmic": f"{M:.0f} pts x ({Hp} x 6 + {Hc} x 16) flop", "peak_source":
+                         f"{sms} SMs x 128 lanes x 2 x {clk:.0f} MHz observed"},
+        "voxel_sort": {"bound": "hbm", "achieved": vox_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": vox_gbs / hbm_peak,
+                       "traffic": None, "ms_per_step": vox_ms, "kernels": "k_crop + k_voxel_keys + radix sort + k_voxel_heads/centroids",
+                       "algorithmic": f"16N + (68+16P)M + 20V bytes, P={P}, working set L2-resident at 1M points",
+                       "peak_source": peak_src},
+        "normals": {"bound": "fp32", "ms_per_step": nrm_ms, "kernels": "k_normals",
+                    "points_per_s": M / (nrm_ms * 1e-3) if nrm_ms > 0 else 0.0},
+    }
+    dominant = max(("inlier_count", "voxel_sort", "normals"), key=lambda k: families[k]["ms_per_step"])
+    roofline = dict(families["inlier_count"] if dominant == "normals" else families[dominant])
+    roofline["dominant_segment"] = dominant
+
+    # ---- end to end through the C-ABI with host buffers (3 contexts pipelined) --------------------
+    NCTX = 3
+    ectx, outs, keep = [], [], []
+    for k in range(NCTX):
+        cx = capi.Context(params, max_points=n, max_hypotheses=4096)
+        ectx.append(cx)
+        summ = torch.empty(C.sizeof(capi.gm_scan_summary), dtype=torch.uint8).pin_memory()
+        cloud = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        labels = torch.empty(n, dtype=torch.uint8).pin_memory()
+        slices = torch.empty(256 * C.sizeof(capi.gm_slice), dtype=torch.uint8).pin_memory()
+        keep.append((summ, cloud, labels, slices))
+        o = capi.gm_host_outputs()
+        o.summary = summ.data_ptr()
+        o.cloud_xyzw, o.cloud_capacity = cloud.data_ptr(), n
+        o.labels, o.labels_capacity = labels.data_ptr(), n
+        o.slices, o.slices_capacity = slices.data_ptr(), 256
+        outs.append(o)
+    h2d = n * 16
+    d2h = C.sizeof(capi.gm_scan_summary) + n * 16 + n + 256 * C.sizeof(capi.gm_slice)
+
+    def e2e_step(i):
+        k, s = i % NCTX, i % RING
+        cx = ectx[k]
+        cx.synchronize()  # results of the scan this context processed 3 steps ago are now on the host
+        cx.upload_scan_raw(host_scans[s].data_ptr(), n, 16)
+        cx.process_scan(samples[s][0], samples[s][1])
+        cx.fetch_async(outs[k])
+
+    for i in range(max(a.warmup, 3)):
+        e2e_step(i)
+    for cx in ectx:
+        cx.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i)
+    for cx in ectx:
+        cx.synchronize()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    e2e_value = world * n * a.steps / e2e_s
+    last = capi.gm_scan_summary.from_buffer_copy(bytes(keep[(a.steps - 1) % NCTX][0].numpy()))
+    assert last.counts.n_input == n and last.counts.device_error == 0
+
+    # ---- hypothesis-sharded RANSAC leg (configs[2]) ----------------------------------------------
+    ransac = None
+    Hs = a.shard_hyp
+    shared = synth.curved_tunnel(n, seed=2)  # the same scan on every rank
+    d_shared = torch.from_numpy(shared).to(dev)
+    ctx.set_scan_device(d_shared.data_ptr(), n)
+    ctx.crop()
+    ctx.normals()
+    nv = ctx.counts().n_valid
+    sp, sc = synth.sample_indices(nv, Hs // 2, 3, seed=3), synth.sample_indices(nv, Hs - Hs // 2, 2, seed=4)
+    key_ptrs = [ctx.ransac_key_device_ptr(k) for k in (0, 1)]
+
+    class _Key:  # expose the 8-byte device key to torch without a copy
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    key_t = [torch.as_tensor(_Key(p), device=dev) for p in key_ptrs]
+
+    def shard(Hk):
+        per = (Hk + world - 1) // world
+        return min(rank * per, Hk), min((rank + 1) * per, Hk)
+
+    def ransac_step():
+        for kind, smp in ((0, sp), (1, sc)):
+            lo, hi = shard(smp.shape[0])
+            ctx.ransac(kind, smp, lo, hi)
+            if world > 1:
+                dist.all_reduce(key_t[kind], op=dist.ReduceOp.MAX)
+            ctx.ransac_select(kind)
+
+    for _ in range(3):
+        ransac_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(a.steps):
+        ransac_step()
+    e1.record(stream)
+    barrier()
+    rms = max_over_ranks(e0.elapsed_time(e1))
+    mp, mc = ctx.model(0), ctx.model(1)
+    ransac = {"hyp_pts_per_sec": Hs * nv * a.steps / (rms * 1e-3), "H": Hs, "points": nv, "ms_per_round": rms / a.steps,
+              "mode": "hypotheses sharded across ranks, NCCL max-allreduce of packed (count,id), refit on every rank",
+              "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle as O
+        ncpu = a.cpu_points or n
+        cp = np.ascontiguousarray(host_scans[0].numpy()[:ncpu])
+        t0 = time.perf_counter()
+        cpu_process_scan(O, cp, a, samples[0][0], samples[0][1], 1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": ncpu / dt, "unit": "points/s", "cores": 1, "kind": "port",
+               "sample": f"1 scan of {ncpu} points, full path, single thread as the reference is "
+                         f"(serial pcl::NormalEstimation + ros::spin); host has {os.cpu_count()} cores; parity unpinned",
+               "seconds": dt}
+
+    if rank == 0:
+        line = {
+            "metric": "input points/s, per-scan segmentation+fit", "value": value, "unit": "points/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "parallelism": f"frame-parallel x{world}" if world > 1 else "1 GPU",
+                       "l2": f"inputs larger than L2: ring of {RING} distinct resident scans ({RING * n * 16 / 1e6:.0f} MB) cycled",
+                       "mean_valid_points": M, "voxels": int(V)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / a.steps, "pipeline": f"{NCTX} contexts / streams, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "roofline_families": families,
+            "segments_ms_per_step": seg_ms,
+            "ransac": ransac,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

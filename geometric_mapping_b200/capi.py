@@ -73,6 +73,18 @@ class gm_slice(C.Structure):
                 ("t_mid", C.c_float), ("count", C.c_int32)]
 
 
+class gm_scan_summary(C.Structure):
+    _fields_ = [("counts", gm_counts), ("frame", gm_frame), ("plane", gm_model), ("cylinder", gm_model),
+                ("n_slices", C.c_int32), ("pad_", C.c_int32)]
+
+
+class gm_host_outputs(C.Structure):
+    _fields_ = [("summary", C.c_void_p), ("cloud_xyzw", C.c_void_p), ("cloud_capacity", C.c_size_t),
+                ("normals8", C.c_void_p), ("normals_capacity", C.c_size_t), ("labels", C.c_void_p),
+                ("labels_capacity", C.c_size_t), ("slices", C.c_void_p), ("slices_capacity", C.c_int32),
+                ("centroids_xyzw", C.c_void_p), ("nn_normal8", C.c_void_p), ("voxel_capacity", C.c_size_t)]
+
+
 SLICE_DTYPE = np.dtype([("center", "<f4", 3), ("dir", "<f4", 3), ("radius", "<f4"), ("rms", "<f4"),
                         ("t_mid", "<f4"), ("count", "<i4")])
 ARROW_DTYPE = np.dtype([("start", "<f4", 3), ("end", "<f4", 3), ("scale", "<f4", 3), ("color_argb", "<f4", 4),
@@ -99,7 +111,8 @@ SYMBOLS = [
     "gm_get_counts", "gm_download_cloud", "gm_download_normals", "gm_download_neighbor_counts",
     "gm_download_valid_map", "gm_download_voxel_assignment", "gm_download_voxels", "gm_get_voxel_grid",
     "gm_get_frame", "gm_download_hypotheses", "gm_get_model", "gm_download_labels", "gm_download_polyline",
-    "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals",
+    "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
+    "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read",
 ]
 
 
@@ -156,6 +169,11 @@ def _lib():
         "gm_inject_compacted": (i32, [vp, vp, vp, sz]),
         "gm_markers_eigen": (None, [C.POINTER(gm_frame), vp]),
         "gm_markers_normals": (None, [vp, vp, i32, vp]),
+        "gm_fetch_async": (i32, [vp, C.POINTER(gm_host_outputs)]),
+        "gm_profile_enable": (i32, [vp, i32]),
+        "gm_profile_num_segments": (i32, []),
+        "gm_profile_segment_name": (C.c_char_p, [i32]),
+        "gm_profile_read": (i32, [vp, vp, vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -385,6 +403,27 @@ class Context:
         n = C.c_int32(0)
         self._ck(_lib().gm_download_polyline(self._h, _ptr(out), cap, C.byref(n)), "gm_download_polyline")
         return out[: n.value].copy()
+
+
+def _ctx_fetch_async(self, outputs: gm_host_outputs):
+    self._ck(_lib().gm_fetch_async(self._h, C.byref(outputs)), "gm_fetch_async")
+
+
+def _ctx_profile_enable(self, on: bool = True):
+    self._ck(_lib().gm_profile_enable(self._h, 1 if on else 0), "gm_profile_enable")
+
+
+def _ctx_profile_read(self) -> dict:
+    """{segment: (ms_sum, calls)} since the last read."""
+    k = _lib().gm_profile_num_segments()
+    ms, calls = np.zeros(k, np.float32), np.zeros(k, np.int32)
+    self._ck(_lib().gm_profile_read(self._h, _ptr(ms), _ptr(calls)), "gm_profile_read")
+    return {_lib().gm_profile_segment_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(k)}
+
+
+Context.fetch_async = _ctx_fetch_async
+Context.profile_enable = _ctx_profile_enable
+Context.profile_read = _ctx_profile_read
 
 
 def markers_eigen(frame_struct: gm_frame) -> np.ndarray:

@@ -13,10 +13,52 @@
 
 using namespace gm;
 
+#include <vector>
+
 namespace {
 constexpr int GM_VERSION = 1;
 constexpr int FRAME_BLOCKS = 296;
 constexpr int REFIT_BLOCKS = 296;
+
+// profiling segments (gm_profile_*): one CUDA-event pair per segment per call
+enum Seg {
+  SEG_CROP, SEG_GRID_KEYS, SEG_GRID_SORT, SEG_GRID_BUILD, SEG_NORMALS, SEG_COMPACT, SEG_VOX_KEYS, SEG_VOX_SORT,
+  SEG_VOX_REDUCE, SEG_VOX_NN, SEG_FRAME, SEG_PLANE_HYP, SEG_PLANE_COUNT, SEG_PLANE_ARGMAX, SEG_PLANE_REFIT,
+  SEG_CYL_HYP, SEG_CYL_COUNT, SEG_CYL_ARGMAX, SEG_CYL_REFIT, SEG_LABEL, SEG_POLYLINE, SEG_COUNT
+};
+const char* kSegNames[SEG_COUNT] = {
+  "crop", "grid_keys", "grid_sort", "grid_build", "normals", "compact", "voxel_keys", "voxel_sort",
+  "voxel_reduce", "voxel_nn", "frame", "plane_hyp", "plane_count", "plane_argmax", "plane_refit",
+  "cyl_hyp", "cyl_count", "cyl_argmax", "cyl_refit", "label", "polyline"};
+
+struct SummaryDev {  // same layout as gm_scan_summary
+  gm_counts counts;
+  gm_frame frame;
+  gm_model plane, cylinder;
+  int32_t n_slices, pad_;
+};
+static_assert(sizeof(SummaryDev) == sizeof(gm_scan_summary), "summary layout");
+
+__global__ void k_pack_summary(const DevState* st, const FrameOut* fr, const ModelState* ms, const PolyState* ps,
+                               int have_mask, SummaryDev* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  out->counts.n_input = st->n_input; out->counts.n_cropped = st->n_crop; out->counts.n_valid = st->n_valid;
+  out->counts.n_voxels = st->n_voxels; out->counts.n_cells = st->n_cells; out->counts.voxel_overflow = st->voxel_overflow;
+  out->counts.nn_out_of_range = st->nn_oor; out->counts.device_error = st->error;
+  for (int k = 0; k < 3; ++k) out->frame.vals[k] = fr->vals[k];
+  for (int k = 0; k < 9; ++k) { out->frame.vecs[k] = fr->vecs[k]; out->frame.scatter[k] = fr->scatter[k]; }
+  for (int m = 0; m < 2; ++m) {
+    gm_model* o = m == 0 ? &out->plane : &out->cylinder;
+    const ModelState* i = ms + m;
+    const bool have = (have_mask >> m) & 1;
+    o->kind = m; o->best_id = have ? i->best_id : -1; o->best_count = have ? i->best_count : -1;
+    o->refit_count = have ? i->refit_count : 0;
+    for (int k = 0; k < 8; ++k) { o->hyp[k] = have ? i->hyp[k] : 0.f; o->coef[k] = have ? i->coef[k] : 0.f; }
+    o->rms = have ? i->rms : 0.f; o->pad_ = 0.f;
+  }
+  out->n_slices = ((have_mask >> 2) & 1) ? ps->S : 0;
+  out->pad_ = 0;
+}
 }  // namespace
 
 struct gm_ctx {
@@ -66,7 +108,29 @@ struct gm_ctx {
   PolyState* d_poly = nullptr;
   long long* d_poly_acc = nullptr;
   gm_slice* d_slices = nullptr;
+  SummaryDev* d_summary = nullptr;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> seg_events[SEG_COUNT];
 };
+
+namespace {
+struct SegTimer {
+  gm_ctx* ctx; cudaEvent_t e1 = nullptr; int seg;
+  static cudaEvent_t get(gm_ctx* c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+  }
+  SegTimer(gm_ctx* c, int s) : ctx(c), seg(s) {
+    if (!c->profiling) return;
+    cudaEvent_t e0 = get(c); e1 = get(c);
+    cudaEventRecord(e0, c->stream);
+    c->seg_events[s].push_back({e0, e1});
+  }
+  ~SegTimer() { if (e1) cudaEventRecord(e1, ctx->stream); }
+};
+}  // namespace
 
 #define GM_CUDA(call)                                                                            \
   do {                                                                                           \
@@ -255,7 +319,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_plane_coef, H); A(d_model7, 7 * H); A(d_test12, 12 * H);
   A(d_hvalid[0], H); A(d_hvalid[1], H); A(d_counts[0], H); A(d_counts[1], H);
   A(d_key, 2); A(d_model, 2);
-  A(d_poly, 1); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
+  A(d_poly, 1); A(d_summary, 1); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
 #undef A
   if ((e = cudaMallocHost((void**)&ctx->h_samples[0], 3 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples0");
   if ((e = cudaMallocHost((void**)&ctx->h_samples[1], 2 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples1");
@@ -279,12 +343,14 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_rs_state, ctx->d_rs_hist, ctx->d_rs_ticket, ctx->d_st, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
-                  ctx->d_poly_acc, ctx->d_slices};
+                  ctx->d_poly_acc, ctx->d_slices, ctx->d_summary};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 2; ++k) {
     if (ctx->h_samples[k]) cudaFreeHost(ctx->h_samples[k]);
     if (ctx->ev_samples[k]) cudaEventDestroy(ctx->ev_samples[k]);
   }
+  for (auto& v : ctx->seg_events) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -360,6 +426,7 @@ gm_status gm_crop(gm_ctx* ctx) {
     gm_status s = reset_state64(ctx, n);
     if (s != GM_OK) return s;
     float hi = (float)ctx->prm.boxFilterBound, lo = (float)(-ctx->prm.boxFilterBound);
+    SegTimer seg_(ctx, SEG_CROP);
     GM_LAUNCH(ctx, k_crop, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_scan, (int)n, lo, hi, ctx->prm.is_dense,
               ctx->d_crop, ctx->d_state64, ctx->d_st);
     GM_CHECK_LAUNCHES(ctx);
@@ -377,22 +444,28 @@ gm_status gm_normals(gm_ctx* ctx) {
     const int* n_ptr = &ctx->d_st->n_crop;
     const GridSpec g = ctx->grid;
     int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
-    GM_LAUNCH(ctx, k_cell_keys, blocks, 256, ctx->d_crop, n_ptr, g, ctx->d_keys[0], ctx->d_vals[0]);
+    { SegTimer seg_(ctx, SEG_GRID_KEYS);
+      GM_LAUNCH(ctx, k_cell_keys, blocks, 256, ctx->d_crop, n_ptr, g, ctx->d_keys[0], ctx->d_vals[0]); }
     int buf = 0;
-    gm_status s = radix_sort(ctx, n_ptr, n, bits_for((unsigned long long)g.ncells), &buf);
+    gm_status s;
+    { SegTimer seg_(ctx, SEG_GRID_SORT);
+      s = radix_sort(ctx, n_ptr, n, bits_for((unsigned long long)g.ncells), &buf); }
     if (s != GM_OK) return s;
     if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    { SegTimer seg_(ctx, SEG_GRID_BUILD);
     GM_LAUNCH(ctx, k_cell_heads, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_crop, n_ptr,
               g.ncells, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_state64, ctx->d_st);
     GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n * 9, 256), ctx->num_sms * 16), 256, ctx->d_ucell_key,
-              ctx->d_ucell_start, ctx->d_st, g, ctx->d_runs);
+              ctx->d_ucell_start, ctx->d_st, g, ctx->d_runs); }
     float rf = (float)ctx->prm.neighborRadius;
     float r2 = rf * rf;
-    GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, n_ptr, r2,
-              ctx->d_normals, ctx->d_nbr);
+    { SegTimer seg_(ctx, SEG_NORMALS);
+      GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, n_ptr, r2,
+                ctx->d_normals, ctx->d_nbr); }
     if ((s = reset_state64(ctx, n)) != GM_OK) return s;
-    GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
-              ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, ctx->d_st);
+    { SegTimer seg_(ctx, SEG_COMPACT);
+      GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
+                ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, ctx->d_st); }
     GM_CHECK_LAUNCHES(ctx);
   }
   ctx->have_normals = true;
@@ -409,9 +482,10 @@ gm_status gm_voxel(gm_ctx* ctx) {
   if (n) {
     const float leaf_f = (float)ctx->prm.voxelGridLeafSize;
     const float inv = 1.0f / leaf_f;
-    GM_LAUNCH(ctx, k_voxel_setup, 1, 32, ctx->d_st, inv);
     int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
-    GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt);
+    { SegTimer seg_(ctx, SEG_VOX_KEYS);
+      GM_LAUNCH(ctx, k_voxel_setup, 1, 32, ctx->d_st, inv);
+      GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt); }
     // static upper bound of the key range from the crop box (no host round trip for the bbox)
     int key_bits = 32;
     if (!ctx->injected) {
@@ -421,14 +495,18 @@ gm_status gm_voxel(gm_ctx* ctx) {
       if (total < 2147483647.0 && (double)n < 2147483647.0) key_bits = bits_for((unsigned long long)total);
     }
     int buf = 0;
-    gm_status s = radix_sort(ctx, &ctx->d_st->n_valid, n, key_bits, &buf);
+    gm_status s;
+    { SegTimer seg_(ctx, SEG_VOX_SORT);
+      s = radix_sort(ctx, &ctx->d_st->n_valid, n, key_bits, &buf); }
     if (s != GM_OK) return s;
     if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    { SegTimer seg_(ctx, SEG_VOX_REDUCE);
     GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_assign,
               ctx->d_vox_start, ctx->d_vox_key, ctx->d_state64, ctx->d_st);
     GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_vals[buf], ctx->d_cloud_c,
-              ctx->d_vox_start, ctx->d_st, ctx->d_centroid, ctx->d_vox_count);
+              ctx->d_vox_start, ctx->d_st, ctx->d_centroid, ctx->d_vox_count); }
     if (ctx->have_normals) {
+      SegTimer seg_(ctx, SEG_VOX_NN);
       GM_LAUNCH(ctx, k_voxel_nn, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_centroid, ctx->d_sorted,
                 ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_valid_map, ctx->d_normals_c, ctx->grid, ctx->prm.nn_index_mode,
                 ctx->d_st, ctx->d_nn_idx, ctx->d_nn_normal);
@@ -444,6 +522,7 @@ gm_status gm_local_frame(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
   double shift = .001 / ctx->prm.weightingFactor;  // src/tunnel_processing.cpp:106 precedence
+  SegTimer seg_(ctx, SEG_FRAME);
   GM_LAUNCH(ctx, k_frame_partial, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, shift, ctx->d_partials);
   GM_LAUNCH(ctx, k_frame_final, 1, 32, ctx->d_partials, FRAME_BLOCKS, ctx->d_frame);
   GM_CHECK_LAUNCHES(ctx);
@@ -466,6 +545,7 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
     GM_CUDA(cudaMemcpyAsync(ctx->d_samples[kind], ctx->h_samples[kind], (size_t)H * per * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     GM_CUDA(cudaEventRecord(ctx->ev_samples[kind], ctx->stream));
     int hb = div_up(H, 128);
+    { SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_HYP : SEG_CYL_HYP);
     if (kind == 0) {
       GM_LAUNCH(ctx, k_plane_hypotheses, hb, 128, ctx->d_cloud_c, n_ptr, ctx->d_samples[0], H, ctx->d_plane_coef, ctx->d_hvalid[0]);
     } else {
@@ -473,9 +553,10 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
                 (float)ctx->prm.cylinderRadiusMin, (float)ctx->prm.cylinderRadiusMax, (float)ctx->prm.ransacThreshold,
                 ctx->d_model7, ctx->d_test12, ctx->d_hvalid[1]);
     }
-    GM_LAUNCH(ctx, k_counts_init, hb, 128, ctx->d_counts[kind], ctx->d_hvalid[kind], H, h_begin, h_end);
+    GM_LAUNCH(ctx, k_counts_init, hb, 128, ctx->d_counts[kind], ctx->d_hvalid[kind], H, h_begin, h_end); }
     const int hloc = h_end - h_begin;
     if (hloc > 0 && ctx->n_input > 0) {
+      SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_COUNT : SEG_CYL_COUNT);
       const int K = kind == 0 ? 4 : 2;
       int groups = div_up(hloc, RC_BLOCK * K);
       int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE), div_up(ctx->num_sms * 4, groups)));
@@ -488,7 +569,8 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
       }
     }
   }
-  GM_LAUNCH(ctx, k_argmax, 1, AM_BLOCK, ctx->d_counts[kind], H, ctx->d_key + kind);
+  { SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_ARGMAX : SEG_CYL_ARGMAX);
+    GM_LAUNCH(ctx, k_argmax, 1, AM_BLOCK, ctx->d_counts[kind], H, ctx->d_key + kind); }
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_ransac[kind] = true;
   ctx->ransac_H[kind] = H;
@@ -507,6 +589,7 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
   if (!ctx->have_ransac[kind]) return GM_ERR_STAGE_ORDER;
   const int* n_ptr = &ctx->d_st->n_valid;
   ModelState* ms = ctx->d_model + kind;
+  SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_REFIT : SEG_CYL_REFIT);
   GM_LAUNCH(ctx, k_select, 1, 32, ctx->d_key + kind, kind, ctx->ransac_H[kind], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ms);
   const float tau = (float)ctx->prm.ransacThreshold;
   if (kind == 0) {
@@ -528,6 +611,7 @@ gm_status gm_label(gm_ctx* ctx) {
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
   if (ctx->n_input) {
     int blocks = std::min(div_up((long long)ctx->n_input, 256), ctx->num_sms * 16);
+    SegTimer seg_(ctx, SEG_LABEL);
     GM_LAUNCH(ctx, k_label, blocks, 256, ctx->d_cloud_c, &ctx->d_st->n_valid, ctx->d_model + 0, ctx->d_model + 1,
               ctx->have_model[0] ? 1 : 0, ctx->have_model[1] ? 1 : 0, (float)ctx->prm.ransacThreshold, ctx->d_labels);
     GM_CHECK_LAUNCHES(ctx);
@@ -542,6 +626,7 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   const int S = ctx->prm.maxSlices;
   const int* n_ptr = &ctx->d_st->n_valid;
   double shift = .001 / ctx->prm.weightingFactor;
+  SegTimer seg_(ctx, SEG_POLYLINE);
   GM_CUDA(cudaMemsetAsync(ctx->d_poly_acc, 0, (size_t)POLY_NACC * S * sizeof(long long), ctx->stream));
   GM_LAUNCH(ctx, k_poly_begin, 1, 32, ctx->d_poly, ctx->d_frame);
   if (ctx->n_input) {
@@ -758,6 +843,53 @@ gm_status gm_download_polyline(gm_ctx* ctx, gm_slice* out, int32_t capacity, int
     GM_D2H(out, ctx->d_slices, (size_t)h.S * sizeof(gm_slice));
     GM_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  return GM_OK;
+}
+
+// ---- pipelined fetch + profiling ---------------------------------------------------------------
+gm_status gm_fetch_async(gm_ctx* ctx, const gm_host_outputs* out) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
+  const size_t n = ctx->n_input;
+  if (out->summary) {
+    int mask = (ctx->have_model[0] ? 1 : 0) | (ctx->have_model[1] ? 2 : 0) | (ctx->have_poly ? 4 : 0);
+    GM_LAUNCH(ctx, k_pack_summary, 1, 32, ctx->d_st, ctx->d_frame, ctx->d_model, ctx->d_poly, mask, ctx->d_summary);
+    GM_CHECK_LAUNCHES(ctx);
+    GM_CUDA(cudaMemcpyAsync(out->summary, ctx->d_summary, sizeof(SummaryDev), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (out->cloud_xyzw && ctx->have_compacted) GM_D2H(out->cloud_xyzw, ctx->d_cloud_c, std::min(n, out->cloud_capacity) * 16);
+  if (out->normals8 && ctx->have_compacted) GM_D2H(out->normals8, ctx->d_normals_c, std::min(n, out->normals_capacity) * 32);
+  if (out->labels && ctx->have_labels) GM_D2H(out->labels, ctx->d_labels, std::min(n, out->labels_capacity));
+  if (out->slices && ctx->have_poly)
+    GM_D2H(out->slices, ctx->d_slices, (size_t)std::min(ctx->prm.maxSlices, out->slices_capacity) * sizeof(gm_slice));
+  if (ctx->have_voxel) {
+    if (out->centroids_xyzw) GM_D2H(out->centroids_xyzw, ctx->d_centroid, std::min(n, out->voxel_capacity) * 16);
+    if (out->nn_normal8 && ctx->have_normals) GM_D2H(out->nn_normal8, ctx->d_nn_normal, std::min(n, out->voxel_capacity) * 32);
+  }
+  return GM_OK;
+}
+
+gm_status gm_profile_enable(gm_ctx* ctx, int32_t on) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->profiling = on != 0;
+  return GM_OK;
+}
+int32_t gm_profile_num_segments(void) { return SEG_COUNT; }
+const char* gm_profile_segment_name(int32_t i) { return (i >= 0 && i < SEG_COUNT) ? kSegNames[i] : ""; }
+gm_status gm_profile_read(gm_ctx* ctx, float* ms_sum, int32_t* calls) {
+  if (!ctx || !ms_sum || !calls) return GM_ERR_INVALID_ARG;
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < SEG_COUNT; ++s) {
+    for (auto& pr : ctx->seg_events[s]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { ms_sum[s] += ms; calls[s] += 1; }
+      ctx->ev_pool.push_back(pr.first);
+      ctx->ev_pool.push_back(pr.second);
+    }
+    ctx->seg_events[s].clear();
+  }
+  cudaGetLastError();
   return GM_OK;
 }
 

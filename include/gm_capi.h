@@ -211,6 +211,40 @@ GM_API gm_status gm_get_model(gm_ctx* ctx, int32_t kind, gm_model* out);
 GM_API gm_status gm_download_labels(gm_ctx* ctx, uint8_t* out, size_t capacity_points);
 GM_API gm_status gm_download_polyline(gm_ctx* ctx, gm_slice* out, int32_t capacity, int32_t* n_slices);
 
+/* ---- pipelined end-to-end use: enqueue all result copies, synchronise once ---------------- */
+/* Fixed-size summary of one scan (filled by gm_fetch_async). */
+typedef struct gm_scan_summary {
+  gm_counts counts;
+  gm_frame frame;
+  gm_model plane;
+  gm_model cylinder;
+  int32_t n_slices;
+  int32_t pad_;
+} gm_scan_summary;
+
+/* Caller-provided (ideally pinned) host destinations; NULL = skip.  Copies are enqueued on the ctx
+ * stream without a host round trip, so variable-size outputs are copied up to the number of
+ * INPUT points (an upper bound of every later size); read the true sizes from summary->counts
+ * after gm_synchronize().  cloud_xyzw is the cloud that cloud_cb publishes on cloudOutput
+ * (src/geometric_mapping.cpp:100-107): cropped and NaN-normal-compacted. */
+typedef struct gm_host_outputs {
+  gm_scan_summary* summary;
+  float* cloud_xyzw;      size_t cloud_capacity;    /* points */
+  float* normals8;        size_t normals_capacity;  /* points */
+  uint8_t* labels;        size_t labels_capacity;   /* points */
+  gm_slice* slices;       int32_t slices_capacity;
+  float* centroids_xyzw;  float* nn_normal8; size_t voxel_capacity; /* voxels */
+} gm_host_outputs;
+GM_API gm_status gm_fetch_async(gm_ctx* ctx, const gm_host_outputs* out);
+
+/* ---- per-stage device timing (CUDA events on the ctx stream) -------------------------------- */
+GM_API gm_status gm_profile_enable(gm_ctx* ctx, int32_t on);
+GM_API int32_t gm_profile_num_segments(void);
+GM_API const char* gm_profile_segment_name(int32_t i);
+/* Synchronises; adds the elapsed ms and call counts since the last reset into ms_sum/calls
+ * (arrays of gm_profile_num_segments()), then resets. */
+GM_API gm_status gm_profile_read(gm_ctx* ctx, float* ms_sum, int32_t* calls);
+
 /* ---- test hooks: inject a stage's input so stages can be parity-checked in isolation ---- */
 /* Replace the compacted cloud (and normals, may be NULL) held in ctx: n x float4 / n x 8 floats. */
 GM_API gm_status gm_inject_compacted(gm_ctx* ctx, const float* xyzw_host, const float* normals8_host, size_t n);

@@ -1,0 +1,161 @@
+// Microbenchmark: which inlier-counting idiom gets closest to the FP32 peak on sm_100a?
+// Plane test d = fma(a,x,fma(b,y,fma(c,z,d0))), 6 flop, one thread owns K hypotheses, points are
+// broadcast from shared memory.  Variants differ only in packing (scalar FFMA vs FFMA2 over a
+// pair of points) and in how the |d| < tau outcome is accumulated.
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo -o count_variants count_variants.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+#include <algorithm>
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+enum { V_SCALAR_C = 0, V_SCALAR_PRED = 1, V_F2_PRED = 2, V_F2_SEL = 3, V_F2_SIGN = 4, V_SCALAR_SIGN = 5 };
+
+__device__ __forceinline__ void count_pred(float d, float tau, int& cnt) {
+  asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(cnt) : "f"(fabsf(d)), "f"(tau));
+}
+__device__ __forceinline__ void count_sign(float e, int& cnt) {  // cnt += sign bit of e (outliers)
+  cnt += (int)(__float_as_uint(e) >> 31);
+}
+
+constexpr int TILE = 512;
+constexpr int BLOCK = 64;
+
+template <int V, int K, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_count(const float4* __restrict__ pts, int n, const float4* __restrict__ coef,
+                                                 int H, float tau, int* __restrict__ counts) {
+  __shared__ __align__(16) float sx[TILE], sy[TILE], sz[TILE];
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(n, p0 + per);
+  const int hbase = blockIdx.y * BLOCK * K + threadIdx.x;
+  float4 c[K]; int cnt[K];
+  const float tau2 = tau * tau;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { c[k] = coef[min(hbase + k * BLOCK, H - 1)]; cnt[k] = 0; }
+  for (int base = p0; base < p1; base += TILE) {
+    const int m = min(TILE, p1 - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < TILE; i += BLOCK) {
+      float4 p = (i < m) ? pts[base + i] : make_float4(3e37f, 3e37f, 3e37f, 0.f);
+      sx[i] = p.x; sy[i] = p.y; sz[i] = p.z;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int i = 0; i < TILE; i += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(&sx[i]);
+      const float4 y = *reinterpret_cast<const float4*>(&sy[i]);
+      const float4 z = *reinterpret_cast<const float4*>(&sz[i]);
+      if (V == V_SCALAR_C || V == V_SCALAR_PRED || V == V_SCALAR_SIGN) {
+        const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w}, zs[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float d = fmaf(c[k].x, xs[j], fmaf(c[k].y, ys[j], fmaf(c[k].z, zs[j], c[k].w)));
+            if (V == V_SCALAR_C) cnt[k] += (fabsf(d) < tau) ? 1 : 0;
+            else if (V == V_SCALAR_PRED) count_pred(d, tau, cnt[k]);
+            else count_sign(fmaf(-d, d, tau2), cnt[k]);
+          }
+        }
+      } else {
+        const u64 x01 = pack2(x.x, x.y), x23 = pack2(x.z, x.w), y01 = pack2(y.x, y.y), y23 = pack2(y.z, y.w);
+        const u64 z01 = pack2(z.x, z.y), z23 = pack2(z.z, z.w);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const u64 A = pack2(c[k].x, c[k].x), B = pack2(c[k].y, c[k].y), Cz = pack2(c[k].z, c[k].z), D = pack2(c[k].w, c[k].w);
+          u64 t0 = fma2(A, x01, fma2(B, y01, fma2(Cz, z01, D)));
+          u64 t1 = fma2(A, x23, fma2(B, y23, fma2(Cz, z23, D)));
+          if (V == V_F2_SIGN) {
+            const u64 T2 = pack2(tau2, tau2);
+            u64 e0 = fma2(t0 ^ 0x8000000080000000ull, t0, T2), e1 = fma2(t1 ^ 0x8000000080000000ull, t1, T2);
+            float a0, a1, a2, a3; unpack2(e0, a0, a1); unpack2(e1, a2, a3);
+            count_sign(a0, cnt[k]); count_sign(a1, cnt[k]); count_sign(a2, cnt[k]); count_sign(a3, cnt[k]);
+          } else {
+            float d0, d1, d2, d3; unpack2(t0, d0, d1); unpack2(t1, d2, d3);
+            if (V == V_F2_PRED) { count_pred(d0, tau, cnt[k]); count_pred(d1, tau, cnt[k]); count_pred(d2, tau, cnt[k]); count_pred(d3, tau, cnt[k]); }
+            else {
+              unsigned m0, m1, m2, m3;
+              asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m0) : "f"(fabsf(d0)), "f"(tau));
+              asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m1) : "f"(fabsf(d1)), "f"(tau));
+              asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m2) : "f"(fabsf(d2)), "f"(tau));
+              asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m3) : "f"(fabsf(d3)), "f"(tau));
+              cnt[k] = cnt[k] - (int)m0 - (int)m1;
+              cnt[k] = cnt[k] - (int)m2 - (int)m3;
+            }
+          }
+        }
+      }
+    }
+  }
+  const int npts = ((p1 - p0 + TILE - 1) / TILE) * TILE;  // padded points were counted as outliers by the sign variants
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int h = hbase + k * BLOCK;
+    int v = (V == V_F2_SIGN || V == V_SCALAR_SIGN) ? (npts - cnt[k]) : cnt[k];
+    if (h < H && p1 > p0) atomicAdd(&counts[h], v);
+  }
+}
+
+template <int V, int K, int MINB>
+float run(const float4* d_pts, int n, const float4* d_coef, int H, float tau, int* d_counts, int slices, int iters, std::vector<int>& out) {
+  dim3 grid(slices, (H + BLOCK * K - 1) / (BLOCK * K));
+  cudaMemset(d_counts, 0, H * sizeof(int));
+  k_count<V, K, MINB><<<grid, BLOCK>>>(d_pts, n, d_coef, H, tau, d_counts);
+  out.resize(H);
+  cudaMemcpy(out.data(), d_counts, H * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) k_count<V, K, MINB><<<grid, BLOCK>>>(d_pts, n, d_coef, H, tau, d_counts);
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) k_count<V, K, MINB><<<grid, BLOCK>>>(d_pts, n, d_coef, H, tau, d_counts);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  return ms / iters;
+}
+
+int main(int argc, char** argv) {
+  int n = argc > 1 ? atoi(argv[1]) : 1000000, H = argc > 2 ? atoi(argv[2]) : 512;
+  std::vector<float4> pts(n), coef(H);
+  srand(1);
+  auto rnd = []() { return (float)rand() / RAND_MAX * 2.f - 1.f; };
+  for (auto& p : pts) p = make_float4(5 * rnd(), 2.5f * rnd(), 2.5f * rnd(), 1.f);
+  for (auto& c : coef) { float a = rnd(), b = rnd(), cc = rnd(); float l = sqrtf(a * a + b * b + cc * cc); c = make_float4(a / l, b / l, cc / l, rnd()); }
+  float4 *d_pts, *d_coef; int* d_counts;
+  cudaMalloc(&d_pts, n * sizeof(float4)); cudaMalloc(&d_coef, H * sizeof(float4)); cudaMalloc(&d_counts, H * sizeof(int));
+  cudaMemcpy(d_pts, pts.data(), n * sizeof(float4), cudaMemcpyHostToDevice);
+  cudaMemcpy(d_coef, coef.data(), H * sizeof(float4), cudaMemcpyHostToDevice);
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+  int sms = prop.multiProcessorCount;
+  const float tau = 0.05f;
+  const double flop = 6.0 * n * (double)H;
+  const double peak = sms * 128.0 * 2.0 * 1.965e9;
+  std::vector<int> ref, got;
+  printf("n=%d H=%d sms=%d peak(1965MHz)=%.1f TFLOP/s\n", n, H, sms, peak / 1e12);
+  run<0, 8, 1>(d_pts, n, d_coef, H, tau, d_counts, sms * 8, 2, ref);
+  if (argc > 3) {  // single configuration for ncu
+    int groups = (H + BLOCK * 8 - 1) / (BLOCK * 8);
+    float ms = run<2, 8, 1>(d_pts, n, d_coef, H, tau, d_counts, sms * 12 / groups, 3, got);
+    printf("single V=2 K=8: %.4f ms %.1f%%\n", ms, 100.0 * flop / (ms * 1e-3) / peak);
+    return 0;
+  }
+#define RUN(V, K, MINB, MULT)                                                                      \
+  {                                                                                                \
+    int groups = (H + BLOCK * K - 1) / (BLOCK * K);                                                \
+    int SL = std::max(1, sms * MULT / groups);                                                     \
+    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_count<V, K, MINB>, BLOCK, 0);   \
+    float ms = run<V, K, MINB>(d_pts, n, d_coef, H, tau, d_counts, SL, 20, got);                  \
+    int bad = 0; for (int h = 0; h < H; ++h) bad += (got[h] != ref[h]);                            \
+    printf("V=%d K=%2d minb=%2d occ=%2d blk/SM grid=%4dx%d (%2d/SM)  %.4f ms  %.2f TFLOP/s  %.1f%%  mism=%d\n", V, K, MINB, nb, SL, groups, MULT, ms, flop / ms / 1e9, 100.0 * flop / (ms * 1e-3) / peak, bad); \
+  }
+  RUN(2, 8, 1, 6) RUN(2, 8, 1, 8) RUN(2, 8, 1, 10) RUN(2, 8, 1, 12) RUN(2, 8, 1, 14) RUN(2, 8, 1, 28)
+  RUN(2, 8, 16, 8) RUN(2, 8, 16, 12) RUN(2, 8, 16, 16) RUN(2, 8, 16, 32)
+  RUN(2, 4, 1, 8) RUN(2, 4, 1, 16) RUN(2, 4, 24, 24) RUN(2, 4, 1, 32) RUN(2, 4, 1, 48)
+  RUN(2, 16, 1, 4) RUN(2, 16, 1, 6) RUN(2, 16, 1, 8)
+  RUN(1, 8, 1, 12) RUN(0, 8, 1, 12)
+  return 0;
+}

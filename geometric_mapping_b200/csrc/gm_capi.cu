@@ -109,6 +109,8 @@ struct gm_ctx {
   long long* d_poly_acc = nullptr;
   gm_slice* d_slices = nullptr;
   SummaryDev* d_summary = nullptr;
+  unsigned* d_counters = nullptr;  // last-block tickets: [0] frame, [1] plane refit, [2] cylinder GN
+  float4* d_inl = nullptr;          // compacted cylinder inliers
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -319,7 +321,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_plane_coef, H); A(d_model7, 7 * H); A(d_test12, 12 * H);
   A(d_hvalid[0], H); A(d_hvalid[1], H); A(d_counts[0], H); A(d_counts[1], H);
   A(d_key, 2); A(d_model, 2);
-  A(d_poly, 1); A(d_summary, 1); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
+  A(d_poly, 1); A(d_summary, 1); A(d_counters, 8); A(d_inl, N); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
 #undef A
   if ((e = cudaMallocHost((void**)&ctx->h_samples[0], 3 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples0");
   if ((e = cudaMallocHost((void**)&ctx->h_samples[1], 2 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples1");
@@ -327,6 +329,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
     if ((e = cudaEventCreateWithFlags(&ctx->ev_samples[k], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
   if ((e = cudaMemset(ctx->d_st, 0, sizeof(DevState))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_model, 0, 2 * sizeof(ModelState))) != cudaSuccess) return fail(e, "memset");
   ctx->grid = make_grid(ctx->prm);
   *out = ctx;
@@ -343,7 +346,7 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_rs_state, ctx->d_rs_hist, ctx->d_rs_ticket, ctx->d_st, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
-                  ctx->d_poly_acc, ctx->d_slices, ctx->d_summary};
+                  ctx->d_poly_acc, ctx->d_slices, ctx->d_summary, ctx->d_counters, ctx->d_inl};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 2; ++k) {
     if (ctx->h_samples[k]) cudaFreeHost(ctx->h_samples[k]);
@@ -507,7 +510,7 @@ gm_status gm_voxel(gm_ctx* ctx) {
               ctx->d_vox_start, ctx->d_st, ctx->d_centroid, ctx->d_vox_count); }
     if (ctx->have_normals) {
       SegTimer seg_(ctx, SEG_VOX_NN);
-      GM_LAUNCH(ctx, k_voxel_nn, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_centroid, ctx->d_sorted,
+      GM_LAUNCH(ctx, k_voxel_nn, std::min(div_up((long long)n * 32, NN_BLOCK), ctx->num_sms * 16), NN_BLOCK, ctx->d_centroid, ctx->d_sorted,
                 ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_valid_map, ctx->d_normals_c, ctx->grid, ctx->prm.nn_index_mode,
                 ctx->d_st, ctx->d_nn_idx, ctx->d_nn_normal);
     }
@@ -523,8 +526,8 @@ gm_status gm_local_frame(gm_ctx* ctx) {
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
   double shift = .001 / ctx->prm.weightingFactor;  // src/tunnel_processing.cpp:106 precedence
   SegTimer seg_(ctx, SEG_FRAME);
-  GM_LAUNCH(ctx, k_frame_partial, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, shift, ctx->d_partials);
-  GM_LAUNCH(ctx, k_frame_final, 1, 32, ctx->d_partials, FRAME_BLOCKS, ctx->d_frame);
+  GM_LAUNCH(ctx, k_frame, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, shift, ctx->d_partials, ctx->d_counters + 0,
+            ctx->d_frame);
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_frame = true;
   return GM_OK;
@@ -557,15 +560,16 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
     const int hloc = h_end - h_begin;
     if (hloc > 0 && ctx->n_input > 0) {
       SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_COUNT : SEG_CYL_COUNT);
-      const int K = kind == 0 ? 4 : 2;
+      const int K = kind == 0 ? RC_KP : RC_KC;
       int groups = div_up(hloc, RC_BLOCK * K);
-      int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE), div_up(ctx->num_sms * 4, groups)));
+      // ~8 co-resident 64-thread blocks per SM (register limited), every slice at least half a tile
+      int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE / 2), div_up(ctx->num_sms * 8, groups)));
       dim3 grid(slices, groups);
       if (kind == 0) {
-        GM_LAUNCH(ctx, k_count_plane<4>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, ctx->d_hvalid[0], h_begin, h_end,
+        GM_LAUNCH(ctx, k_count_plane<RC_KP>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, ctx->d_hvalid[0], h_begin, h_end,
                   (float)ctx->prm.ransacThreshold, ctx->d_counts[0]);
       } else {
-        GM_LAUNCH(ctx, k_count_cyl<2>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_test12, h_begin, h_end, ctx->d_counts[1]);
+        GM_LAUNCH(ctx, k_count_cyl<RC_KC>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_test12, h_begin, h_end, ctx->d_counts[1]);
       }
     }
   }
@@ -593,13 +597,15 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
   GM_LAUNCH(ctx, k_select, 1, 32, ctx->d_key + kind, kind, ctx->ransac_H[kind], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ms);
   const float tau = (float)ctx->prm.ransacThreshold;
   if (kind == 0) {
-    GM_LAUNCH(ctx, k_plane_refit_partial, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ms, tau, ctx->d_partials);
-    GM_LAUNCH(ctx, k_plane_refit_final, 1, 32, ctx->d_partials, REFIT_BLOCKS, ms);
-  } else {
-    for (int it = 0; it <= ctx->prm.refitIterations; ++it) {
-      GM_LAUNCH(ctx, k_cyl_gn_partial, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ms, ctx->d_partials);
-      GM_LAUNCH(ctx, k_cyl_gn_final, 1, 32, ctx->d_partials, REFIT_BLOCKS, it < ctx->prm.refitIterations ? 1 : 0, tau, ms);
-    }
+    GM_LAUNCH(ctx, k_plane_refit, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ms, tau, ctx->d_partials, ctx->d_counters + 1);
+  } else if (ctx->n_input) {
+    gm_status s = reset_state64(ctx, ctx->n_input);
+    if (s != GM_OK) return s;
+    GM_LAUNCH(ctx, k_cyl_inlier_compact, div_up((long long)ctx->n_input, CP_TILE), CP_BLOCK, ctx->d_cloud_c, n_ptr, ms, ctx->d_inl,
+              ctx->d_state64, &ctx->d_st->error);
+    for (int it = 0; it <= ctx->prm.refitIterations; ++it)
+      GM_LAUNCH(ctx, k_cyl_gn, ctx->num_sms, RF_BLOCK, ctx->d_inl, ms, it < ctx->prm.refitIterations ? 1 : 0, tau, ctx->d_partials,
+                ctx->d_counters + 2);
   }
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_model[kind] = true;

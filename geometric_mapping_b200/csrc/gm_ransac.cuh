@@ -155,19 +155,46 @@ __device__ __forceinline__ CylTest d_load_cyl_test(const float* __restrict__ t12
 
 // ---- inlier counting ------------------------------------------------------------------------
 // Each thread owns K hypotheses in registers; the block streams its slice of the cloud through
-// shared memory and every thread reads each point as a broadcast LDS.128.  Counts stay in
-// registers for the whole slice: no per-test reduction.  grid = (point slices, hypothesis groups).
-constexpr int RC_BLOCK = 128;
-constexpr int RC_TILE = 512;  // points staged per iteration
+// shared memory (transposed to SoA while staging) and every thread reads 4 points per LDS.128
+// triple as warp-wide broadcasts.  Two points are evaluated per instruction with the packed
+// fma.rn.f32x2 (SASS FFMA2, coefficient broadcast as the scalar operand); each half is an IEEE
+// fma, so the result is bit-identical to the scalar chain of the oracle.  The |d| < tau outcome
+// is accumulated with setp + predicated add (2 non-FMA issue slots per test; measured best of the
+// idioms in tools/microbench/count_variants.cu, profiles/r01_microbench_count.md).
+// Counts stay in registers for the whole slice; one integer atomicAdd per (thread, hypothesis).
+// grid = (point slices, hypothesis groups).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 d_pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void d_unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 d_fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// cnt += (v < thr)   [v is already |.|; NaN compares false]
+__device__ __forceinline__ void d_count_lt(float v, float thr, int& cnt) {
+  asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(cnt) : "f"(v), "f"(thr));
+}
+
+constexpr int RC_BLOCK = 64;
+constexpr int RC_TILE = 512;   // points staged per iteration (6 KB of shared memory)
+constexpr int RC_KP = 8;       // plane hypotheses per thread
+constexpr int RC_KC = 4;       // cylinder hypotheses per thread
+
+// Stage points [base, base+m) into SoA shared arrays; entries m..m4 are NaN (never inliers).
+__device__ __forceinline__ void d_stage_tile(const float4* __restrict__ pts, int base, int m, int m4,
+                                             float* sx, float* sy, float* sz) {
+  for (int i = threadIdx.x; i < m4; i += RC_BLOCK) {
+    float4 p = (i < m) ? pts[base + i] : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
+    sx[i] = p.x; sy[i] = p.y; sz[i] = p.z;
+  }
+}
 
 template <int K>
 __global__ void __launch_bounds__(RC_BLOCK)
 k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float4* __restrict__ coef,
               const int* __restrict__ valid, int h_begin, int h_end, float tau, int* __restrict__ counts) {
-  __shared__ float4 s_pts[RC_TILE];
+  __shared__ __align__(16) float sx[RC_TILE], sy[RC_TILE], sz[RC_TILE];
   const int n = *n_ptr;
-  const int per = (((n + gridDim.x - 1) / gridDim.x) + RC_TILE - 1) / RC_TILE * RC_TILE;
+  const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
   const int p_begin = blockIdx.x * per, p_end = min(n, p_begin + per);
+  if (p_begin >= p_end) return;
   const int hbase = h_begin + blockIdx.y * (RC_BLOCK * K) + threadIdx.x;
   float4 c[K];
   int cnt[K];
@@ -179,16 +206,27 @@ k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, con
     cnt[k] = 0;
   }
   for (int base = p_begin; base < p_end; base += RC_TILE) {
-    const int m = min(RC_TILE, p_end - base);
+    const int m = min(RC_TILE, p_end - base), m4 = (m + 3) & ~3;
     __syncthreads();
-    for (int i = threadIdx.x; i < RC_TILE; i += RC_BLOCK)
-      s_pts[i] = (i < m) ? pts[base + i] : make_float4(CUDART_INF_F, 0.f, 0.f, 0.f);  // never an inlier
+    d_stage_tile(pts, base, m, m4, sx, sy, sz);
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < RC_TILE; ++i) {
-      const float4 p = s_pts[i];
+#pragma unroll 2
+    for (int i = 0; i < m4; i += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(&sx[i]);
+      const float4 y = *reinterpret_cast<const float4*>(&sy[i]);
+      const float4 z = *reinterpret_cast<const float4*>(&sz[i]);
+      const u64 x01 = d_pack2(x.x, x.y), x23 = d_pack2(x.z, x.w), y01 = d_pack2(y.x, y.y), y23 = d_pack2(y.z, y.w);
+      const u64 z01 = d_pack2(z.x, z.y), z23 = d_pack2(z.z, z.w);
 #pragma unroll
-      for (int k = 0; k < K; ++k) cnt[k] += d_plane_inlier(c[k], p, tau) ? 1 : 0;
+      for (int k = 0; k < K; ++k) {
+        const u64 A = d_pack2(c[k].x, c[k].x), B = d_pack2(c[k].y, c[k].y), Cz = d_pack2(c[k].z, c[k].z), D = d_pack2(c[k].w, c[k].w);
+        const u64 t0 = d_fma2(A, x01, d_fma2(B, y01, d_fma2(Cz, z01, D)));
+        const u64 t1 = d_fma2(A, x23, d_fma2(B, y23, d_fma2(Cz, z23, D)));
+        float d0, d1, d2, d3;
+        d_unpack2(t0, d0, d1); d_unpack2(t1, d2, d3);
+        d_count_lt(fabsf(d0), tau, cnt[k]); d_count_lt(fabsf(d1), tau, cnt[k]);
+        d_count_lt(fabsf(d2), tau, cnt[k]); d_count_lt(fabsf(d3), tau, cnt[k]);
+      }
     }
   }
 #pragma unroll
@@ -202,31 +240,55 @@ template <int K>
 __global__ void __launch_bounds__(RC_BLOCK)
 k_count_cyl(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float* __restrict__ test12,
             int h_begin, int h_end, int* __restrict__ counts) {
-  __shared__ float4 s_pts[RC_TILE];
+  __shared__ __align__(16) float sx[RC_TILE], sy[RC_TILE], sz[RC_TILE];
   const int n = *n_ptr;
-  const int per = (((n + gridDim.x - 1) / gridDim.x) + RC_TILE - 1) / RC_TILE * RC_TILE;
+  const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
   const int p_begin = blockIdx.x * per, p_end = min(n, p_begin + per);
+  if (p_begin >= p_end) return;
   const int hbase = h_begin + blockIdx.y * (RC_BLOCK * K) + threadIdx.x;
-  CylTest c[K];
+  float4 u[K], w[K];
+  float negmid[K], half[K];
   int cnt[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     int h = hbase + k * RC_BLOCK;
-    if (h < h_end) c[k] = d_load_cyl_test(test12 + (size_t)h * 12);
-    else { c[k].u = make_float4(0, 0, 0, 0); c[k].w = make_float4(0, 0, 0, 0); c[k].mid = 0.f; c[k].half = 0.f; }
+    // invalid hypotheses have an all-zero test (half = 0): |v| < 0 is never true
+    const float* t = test12 + (size_t)min(h, h_end - 1) * 12;
+    const bool ok = h < h_end;
+    u[k] = ok ? make_float4(t[0], t[1], t[2], t[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w[k] = ok ? make_float4(t[4], t[5], t[6], t[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    negmid[k] = ok ? -t[8] : 0.f;
+    half[k] = ok ? t[9] : 0.f;
     cnt[k] = 0;
   }
   for (int base = p_begin; base < p_end; base += RC_TILE) {
-    const int m = min(RC_TILE, p_end - base);
+    const int m = min(RC_TILE, p_end - base), m4 = (m + 3) & ~3;
     __syncthreads();
-    for (int i = threadIdx.x; i < RC_TILE; i += RC_BLOCK)
-      s_pts[i] = (i < m) ? pts[base + i] : make_float4(CUDART_INF_F, 0.f, 0.f, 0.f);
+    d_stage_tile(pts, base, m, m4, sx, sy, sz);
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < RC_TILE; ++i) {
-      const float4 p = s_pts[i];
+#pragma unroll 2
+    for (int i = 0; i < m4; i += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(&sx[i]);
+      const float4 y = *reinterpret_cast<const float4*>(&sy[i]);
+      const float4 z = *reinterpret_cast<const float4*>(&sz[i]);
+      const u64 x01 = d_pack2(x.x, x.y), x23 = d_pack2(x.z, x.w), y01 = d_pack2(y.x, y.y), y23 = d_pack2(y.z, y.w);
+      const u64 z01 = d_pack2(z.x, z.y), z23 = d_pack2(z.z, z.w);
 #pragma unroll
-      for (int k = 0; k < K; ++k) cnt[k] += d_cyl_inlier(c[k], p) ? 1 : 0;
+      for (int k = 0; k < K; ++k) {
+        const u64 UX = d_pack2(u[k].x, u[k].x), UY = d_pack2(u[k].y, u[k].y), UZ = d_pack2(u[k].z, u[k].z), UD = d_pack2(u[k].w, u[k].w);
+        const u64 WX = d_pack2(w[k].x, w[k].x), WY = d_pack2(w[k].y, w[k].y), WZ = d_pack2(w[k].z, w[k].z), WD = d_pack2(w[k].w, w[k].w);
+        const u64 NM = d_pack2(negmid[k], negmid[k]);
+        const u64 A0 = d_fma2(UX, x01, d_fma2(UY, y01, d_fma2(UZ, z01, UD)));
+        const u64 B0 = d_fma2(WX, x01, d_fma2(WY, y01, d_fma2(WZ, z01, WD)));
+        const u64 A1 = d_fma2(UX, x23, d_fma2(UY, y23, d_fma2(UZ, z23, UD)));
+        const u64 B1 = d_fma2(WX, x23, d_fma2(WY, y23, d_fma2(WZ, z23, WD)));
+        const u64 v0 = d_fma2(A0, A0, d_fma2(B0, B0, NM));
+        const u64 v1 = d_fma2(A1, A1, d_fma2(B1, B1, NM));
+        float e0, e1, e2, e3;
+        d_unpack2(v0, e0, e1); d_unpack2(v1, e2, e3);
+        d_count_lt(fabsf(e0), half[k], cnt[k]); d_count_lt(fabsf(e1), half[k], cnt[k]);
+        d_count_lt(fabsf(e2), half[k], cnt[k]); d_count_lt(fabsf(e3), half[k], cnt[k]);
+      }
     }
   }
 #pragma unroll
@@ -275,6 +337,7 @@ struct ModelState {
   float test_hyp[12];   // cylinder: inlier test of the winning hypothesis (fixes the refit set)
   float test_coef[12];  // cylinder: inlier test of the refined model (labels)
   double q[3], dir[3], r;  // cylinder iterate
+  int n_inl, pad2_;        // size of the compacted inlier array (cylinder)
 };
 
 __global__ void k_select(const unsigned long long* __restrict__ key, int kind, int H,
@@ -288,6 +351,7 @@ __global__ void k_select(const unsigned long long* __restrict__ key, int kind, i
   ms->refit_count = 0;
   ms->rms = 0.f;
   ms->pad_ = 0.f;
+  ms->n_inl = 0; ms->pad2_ = 0;
   for (int i = 0; i < 8; ++i) { ms->hyp[i] = 0.f; ms->coef[i] = 0.f; }
   for (int i = 0; i < 12; ++i) { ms->test_hyp[i] = 0.f; ms->test_coef[i] = 0.f; }
   if (count < 0 || id < 0 || id >= H) { ms->best_id = -1; ms->best_count = -1; return; }
@@ -307,14 +371,42 @@ __global__ void k_select(const unsigned long long* __restrict__ key, int kind, i
 
 constexpr int RF_BLOCK = 256;
 
-// plane refit, pass 1: double sums {xx,xy,xz,yy,yz,zz,x,y,z,count} over the hypothesis inliers
+// Returns true (block-uniformly) in the last block of the grid to get here, after every block's
+// earlier global writes are visible.  The counter is reset for the next launch.  Combined with a
+// fixed-order sum over per-block partials this gives a single-launch, bitwise reproducible
+// grid reduction (the result does not depend on which block happens to be last).
+__device__ __forceinline__ bool d_last_block(unsigned* counter) {
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) { *counter = 0u; __threadfence(); }
+  }
+  __syncthreads();
+  return s_last;
+}
+
+// column k of the per-block partials summed over blocks in block order (thread k < NV)
+template <int NV>
+__device__ __forceinline__ double d_sum_partials(const double* partials, int nblocks, int k) {
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += __ldcg(partials + (size_t)b * NV + k);
+  return s;
+}
+
+// plane refit: double sums {xx,xy,xz,yy,yz,zz,x,y,z,count} over the hypothesis inliers, then
+// (last block) covariance -> Jacobi -> coefficients
 __global__ void __launch_bounds__(RF_BLOCK)
-k_plane_refit_partial(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const ModelState* __restrict__ ms,
-                      float tau, double* __restrict__ partials) {
+k_plane_refit(const float4* __restrict__ pts, const int* __restrict__ n_ptr, ModelState* ms, float tau,
+              double* __restrict__ partials, unsigned* counter) {
   __shared__ double sm[10 * (RF_BLOCK / 32)];
+  __shared__ double fin[10];
   const int n = *n_ptr;
   double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (ms->best_id >= 0) {
+  const bool have = ms->best_id >= 0;
+  if (have) {
     const float4 c = make_float4(ms->hyp[0], ms->hyp[1], ms->hyp[2], ms->hyp[3]);
     for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += gridDim.x * RF_BLOCK) {
       float4 p = pts[i];
@@ -328,19 +420,15 @@ k_plane_refit_partial(const float4* __restrict__ pts, const int* __restrict__ n_
   block_sum<10, RF_BLOCK>(s, sm);
   if (threadIdx.x == 0)
     for (int k = 0; k < 10; ++k) partials[blockIdx.x * 10 + k] = s[k];
-}
-
-__global__ void k_plane_refit_final(const double* __restrict__ partials, int nblocks, ModelState* ms) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (ms->best_id < 0) return;
-  double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int b = 0; b < nblocks; ++b)
-    for (int k = 0; k < 10; ++k) s[k] += partials[b * 10 + k];
-  long long cnt = (long long)(s[9] + 0.5);
+  if (!d_last_block(counter)) return;
+  if (threadIdx.x < 10) fin[threadIdx.x] = d_sum_partials<10>(partials, gridDim.x, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x != 0 || !have) return;
+  long long cnt = (long long)(fin[9] + 0.5);
   ms->refit_count = (int)cnt;
   if (cnt <= 3) return;
-  double c = (double)cnt, mx = s[6] / c, my = s[7] / c, mz = s[8] / c;
-  double C[9] = {s[0] / c - mx * mx, s[1] / c - mx * my, s[2] / c - mx * mz, 0, s[3] / c - my * my, s[4] / c - my * mz, 0, 0, s[5] / c - mz * mz};
+  double c = (double)cnt, mx = fin[6] / c, my = fin[7] / c, mz = fin[8] / c;
+  double C[9] = {fin[0] / c - mx * mx, fin[1] / c - mx * my, fin[2] / c - mx * mz, 0, fin[3] / c - my * my, fin[4] / c - my * mz, 0, 0, fin[5] / c - mz * mz};
   C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
   double vals[3], vecs[9];
   d_jacobi3(C, vals, vecs);
@@ -365,48 +453,31 @@ __device__ __forceinline__ void d_perp_basis_d(const double dir[3], double u[3],
   w[0] = dir[1] * u[2] - dir[2] * u[1]; w[1] = dir[2] * u[0] - dir[0] * u[2]; w[2] = dir[0] * u[1] - dir[1] * u[0];
 }
 
-// cylinder refit, one Gauss-Newton pass: sums of J^T J (15), J^T r (5), count, sum r^2 over the
-// FIXED inlier set of the winning hypothesis, evaluated at the current iterate (ms->q,dir,r).
-constexpr int GN_NV = 22;
-__global__ void __launch_bounds__(RF_BLOCK)
-k_cyl_gn_partial(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const ModelState* __restrict__ ms,
-                 double* __restrict__ partials) {
-  __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
+// The refit set is FIXED (inliers of the winning hypothesis), so it is compacted once (stable
+// look-back compaction) and the Gauss-Newton passes run over the dense array.
+__global__ void __launch_bounds__(CP_BLOCK)
+k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_ptr, ModelState* ms,
+                     float4* __restrict__ inl, unsigned long long* state, int* err) {
+  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
   const int n = *n_ptr;
-  double s[GN_NV];
+  const int tile = blockIdx.x, base = tile * CP_TILE;
+  if (base >= n) return;
+  const bool have = ms->best_id >= 0;
+  const CylTest t = d_load_cyl_test(ms->test_hyp);
+  bool f[CP_IPT];
+  float4 p[CP_IPT];
 #pragma unroll
-  for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
-  if (ms->best_id >= 0) {
-    const CylTest t = d_load_cyl_test(ms->test_hyp);
-    const double q0 = ms->q[0], q1 = ms->q[1], q2 = ms->q[2], r = ms->r;
-    double dir[3] = {ms->dir[0], ms->dir[1], ms->dir[2]}, u[3], w[3];
-    d_perp_basis_d(dir, u, w);
-    for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += gridDim.x * RF_BLOCK) {
-      float4 p = pts[i];
-      if (!d_cyl_inlier(t, p)) continue;
-      s[20] += 1.0;
-      double vx = (double)p.x - q0, vy = (double)p.y - q1, vz = (double)p.z - q2;
-      double A = u[0] * vx + u[1] * vy + u[2] * vz;
-      double B = w[0] * vx + w[1] * vy + w[2] * vz;
-      double tt = dir[0] * vx + dir[1] * vy + dir[2] * vz;
-      double dist = sqrt(A * A + B * B);
-      if (!(dist > 1e-12)) continue;
-      double res = dist - r;
-      s[21] += res * res;
-      double J[5] = {-A / dist, -B / dist, -A * tt / dist, -B * tt / dist, -1.0};
-      int idx = 0;
-#pragma unroll
-      for (int a = 0; a < 5; ++a) {
-#pragma unroll
-        for (int b = a; b < 5; ++b) s[idx++] += J[a] * J[b];
-      }
-#pragma unroll
-      for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
-    }
+  for (int j = 0; j < CP_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    f[j] = false;
+    if (i < n) { p[j] = pts[i]; f[j] = have && d_cyl_inlier(t, p[j]); }
   }
-  block_sum<GN_NV, RF_BLOCK>(s, sm);
-  if (threadIdx.x == 0)
-    for (int k = 0; k < GN_NV; ++k) partials[blockIdx.x * GN_NV + k] = s[k];
+  unsigned ranks[CP_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, err, sm);
+#pragma unroll
+  for (int j = 0; j < CP_IPT; ++j)
+    if (f[j]) inl[ranks[j]] = p[j];
+  if (base + CP_TILE >= n && threadIdx.x == 0) ms->n_inl = (int)total;
 }
 
 __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
@@ -432,23 +503,60 @@ __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
   return true;
 }
 
-// update = 1: solve the normal equations and move the iterate; update = 0: final pass, only
-// publish count / rms / float coefficients / refined inlier test.
-__global__ void k_cyl_gn_final(const double* __restrict__ partials, int nblocks, int update, float tau, ModelState* ms) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (ms->best_id < 0) return;
+// One Gauss-Newton pass over the compacted inliers: sums of J^T J (15), J^T r (5), count, sum r^2
+// at the current iterate; the last block solves the 5x5 system and moves the iterate (update = 1)
+// or publishes count / rms / float coefficients / refined inlier test (update = 0).
+constexpr int GN_NV = 22;
+__global__ void __launch_bounds__(RF_BLOCK)
+k_cyl_gn(const float4* __restrict__ inl, ModelState* ms, int update, float tau, double* __restrict__ partials, unsigned* counter) {
+  __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
+  __shared__ double fin[GN_NV];
+  const bool have = ms->best_id >= 0;
+  const int n = have ? ms->n_inl : 0;
   double s[GN_NV];
+#pragma unroll
   for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
-  for (int b = 0; b < nblocks; ++b)
-    for (int k = 0; k < GN_NV; ++k) s[k] += partials[b * GN_NV + k];
-  long long cnt = (long long)(s[20] + 0.5);
+  {
+    const double q0 = ms->q[0], q1 = ms->q[1], q2 = ms->q[2], r = ms->r;
+    double dir[3] = {ms->dir[0], ms->dir[1], ms->dir[2]}, u[3], w[3];
+    d_perp_basis_d(dir, u, w);
+    for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += gridDim.x * RF_BLOCK) {
+      float4 p = inl[i];
+      s[20] += 1.0;
+      double vx = (double)p.x - q0, vy = (double)p.y - q1, vz = (double)p.z - q2;
+      double A = u[0] * vx + u[1] * vy + u[2] * vz;
+      double B = w[0] * vx + w[1] * vy + w[2] * vz;
+      double tt = dir[0] * vx + dir[1] * vy + dir[2] * vz;
+      double dist = sqrt(A * A + B * B);
+      if (!(dist > 1e-12)) continue;
+      double res = dist - r;
+      s[21] += res * res;
+      double J[5] = {-A / dist, -B / dist, -A * tt / dist, -B * tt / dist, -1.0};
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+#pragma unroll
+        for (int b = a; b < 5; ++b) s[idx++] += J[a] * J[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
+    }
+  }
+  block_sum<GN_NV, RF_BLOCK>(s, sm);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < GN_NV; ++k) partials[blockIdx.x * GN_NV + k] = s[k];
+  if (!d_last_block(counter)) return;
+  if (threadIdx.x < GN_NV) fin[threadIdx.x] = d_sum_partials<GN_NV>(partials, gridDim.x, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x != 0 || !have) return;
+  long long cnt = (long long)(fin[20] + 0.5);
   ms->refit_count = (int)cnt;
   if (cnt <= 5) return;  // model unchanged
   if (update) {
     double JTJ[5][5], rhs[5], x[5];
     int idx = 0;
-    for (int a = 0; a < 5; ++a) for (int b = a; b < 5; ++b) { JTJ[a][b] = s[idx]; JTJ[b][a] = s[idx]; ++idx; }
-    for (int a = 0; a < 5; ++a) rhs[a] = -s[15 + a];
+    for (int a = 0; a < 5; ++a) for (int b = a; b < 5; ++b) { JTJ[a][b] = fin[idx]; JTJ[b][a] = fin[idx]; ++idx; }
+    for (int a = 0; a < 5; ++a) rhs[a] = -fin[15 + a];
     if (!d_solve5(JTJ, rhs, x)) return;
     double dir[3] = {ms->dir[0], ms->dir[1], ms->dir[2]}, u[3], w[3];
     d_perp_basis_d(dir, u, w);
@@ -458,7 +566,7 @@ __global__ void k_cyl_gn_final(const double* __restrict__ partials, int nblocks,
     for (int k = 0; k < 3; ++k) ms->dir[k] = dir[k] / dl;
     ms->r += x[4];
   } else {
-    ms->rms = (float)sqrt(s[21] / (double)cnt);
+    ms->rms = (float)sqrt(fin[21] / (double)cnt);
     for (int k = 0; k < 3; ++k) { ms->coef[k] = (float)ms->q[k]; ms->coef[3 + k] = (float)ms->dir[k]; }
     ms->coef[6] = (float)ms->r;
     float t12[12];

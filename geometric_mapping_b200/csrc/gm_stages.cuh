@@ -490,55 +490,91 @@ __global__ void k_voxel_centroids(const unsigned* __restrict__ sidx, const float
 }
 
 // a4 second half: kdtree->nearestKSearch(centroid, 1) (src/tunnel_processing.cpp:239) as an exact
-// expanding-ring search over the neighbour grid of the PRE-compaction cloud (quirk B.3), FLANN
+// expanding search over the neighbour grid of the PRE-compaction cloud (quirk B.3), FLANN
 // L2_Simple distance, ties -> lowest original index.  Then normals->at(index) (:247-249).
 // mode 0 (reference-faithful): index = pre-compaction index, looked up in the COMPACTED normals;
 // index >= n_valid is counted in nn_oor (the reference would throw).  mode 1 (fixed): only points
 // that survived compaction are candidates and the index is the compacted one.
-__global__ void k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
-                           const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
-                           const int* __restrict__ valid_map, const float4* __restrict__ normals_c, GridSpec g,
-                           int mode, DevState* st, int* __restrict__ nn_idx, float4* __restrict__ nn_normal) {
+// One warp per voxel: lanes take the x-runs of the cube shells as tasks (two binary searches + a
+// short scan each), then a lexicographic (d2, index) warp minimum.
+constexpr int NN_BLOCK = 128;
+
+__device__ __forceinline__ void d_nn_scan(const float4* __restrict__ sp, const int* __restrict__ valid_map, int mode,
+                                          int2 r, const float4 c, float& best, int& bi) {
+  for (int t = r.x; t < r.y; ++t) {
+    const float4 q = sp[t];
+    int id = __float_as_int(q.w);
+    if (mode == 1) { id = valid_map[id]; if (id < 0) continue; }
+    float dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
+    float d2 = (dx * dx + dy * dy) + dz * dz;
+    if (d2 < best || (d2 == best && id < bi)) { best = d2; bi = id; }
+  }
+}
+
+__global__ void __launch_bounds__(NN_BLOCK)
+k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
+           const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
+           const int* __restrict__ valid_map, const float4* __restrict__ normals_c, GridSpec g,
+           int mode, DevState* st, int* __restrict__ nn_idx, float4* __restrict__ nn_normal) {
   const int V = st->n_voxels, U = st->n_cells, nf = st->n_sorted_finite, nvalid = st->n_valid;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < V; j += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * NN_BLOCK) >> 5;
+  for (int j = (blockIdx.x * NN_BLOCK + threadIdx.x) >> 5; j < V; j += warps_total) {
     const float4 c = centroids[j];
-    int cx = min(max((int)floorf((c.x - g.origin) * g.inv_cell), 0), g.dim - 1);
-    int cy = min(max((int)floorf((c.y - g.origin) * g.inv_cell), 0), g.dim - 1);
-    int cz = min(max((int)floorf((c.z - g.origin) * g.inv_cell), 0), g.dim - 1);
+    const int cx = min(max((int)floorf((c.x - g.origin) * g.inv_cell), 0), g.dim - 1);
+    const int cy = min(max((int)floorf((c.y - g.origin) * g.inv_cell), 0), g.dim - 1);
+    const int cz = min(max((int)floorf((c.z - g.origin) * g.inv_cell), 0), g.dim - 1);
     float best = CUDART_INF_F;
-    int bi = -1;
-    for (int k = 0; k <= g.dim; ++k) {
-      for (int dz = -k; dz <= k; ++dz)
-        for (int dy = -k; dy <= k; ++dy) {
-          const bool shell = (max(abs(dy), abs(dz)) == k);
-          // on the shell rows take the whole x span, inside only the two end cells
-          for (int part = 0; part < (shell || k == 0 ? 1 : 2); ++part) {
-            int x0 = shell ? cx - k : (part == 0 ? cx - k : cx + k);
-            int x1 = shell ? cx + k : x0;
-            int2 r = cell_run(ucell_key, ucell_start, U, nf, g.dim, x0, x1, cy + dy, cz + dz);
-            for (int t = r.x; t < r.y; ++t) {
-              const float4 q = sp[t];
-              int src = __float_as_int(q.w);
-              int id = src;
-              if (mode == 1) { id = valid_map[src]; if (id < 0) continue; }
-              float dx = c.x - q.x, dyy = c.y - q.y, dzz = c.z - q.z;
-              float d2 = (dx * dx + dyy * dyy) + dzz * dzz;
-              if (d2 < best || (d2 == best && id < bi)) { best = d2; bi = id; }
-            }
-          }
+    int bi = 0x7FFFFFFF;
+    for (int k = 1; k <= g.dim; ++k) {
+      if (k == 1) {
+        // the 27-cell cube as 9 rows of 3 cells
+        if (lane < 9) {
+          int2 r = cell_run(ucell_key, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1);
+          d_nn_scan(sp, valid_map, mode, r, c, best, bi);
         }
+      } else {
+        // shell k: 8k perimeter rows with the full x span + (2k-1)^2 inner rows with two end cells
+        const int inner = 2 * k - 1, T = 8 * k + 2 * inner * inner;
+        for (int t = lane; t < T; t += 32) {
+          int dy, dz, x0, x1;
+          if (t < 8 * k) {
+            if (t < 2 * k + 1) { dz = -k; dy = t - k; }
+            else if (t < 4 * k + 2) { dz = k; dy = t - (2 * k + 1) - k; }
+            else if (t < 6 * k + 1) { dy = -k; dz = t - (4 * k + 2) - (k - 1); }
+            else { dy = k; dz = t - (6 * k + 1) - (k - 1); }
+            x0 = cx - k; x1 = cx + k;
+          } else {
+            int u2 = t - 8 * k, cell = u2 >> 1;
+            dy = cell % inner - (k - 1); dz = cell / inner - (k - 1);
+            x0 = x1 = (u2 & 1) ? cx + k : cx - k;
+          }
+          int2 r = cell_run(ucell_key, ucell_start, U, nf, g.dim, x0, x1, cy + dy, cz + dz);
+          d_nn_scan(sp, valid_map, mode, r, c, best, bi);
+        }
+      }
+      // lexicographic (d2, index) minimum over the warp
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(FULL, best, o);
+        int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
       // every unexplored cell is at Chebyshev distance >= k+1 from the query cell, hence every
       // point in it is at least k*cell away from the query
       double lim = (double)k * (double)g.cell * 0.999;
-      if (bi >= 0 && (double)best <= lim * lim) break;
+      if (bi != 0x7FFFFFFF && (double)best <= lim * lim) break;
     }
-    nn_idx[j] = bi;
-    const float qnan = CUDART_NAN_F;
-    float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
-    if (bi >= 0 && bi < nvalid) { o0 = normals_c[2 * (size_t)bi]; o1 = normals_c[2 * (size_t)bi + 1]; }
-    else atomicAdd(&st->nn_oor, 1);
-    nn_normal[2 * (size_t)j] = o0;
-    nn_normal[2 * (size_t)j + 1] = o1;
+    if (lane == 0) {
+      if (bi == 0x7FFFFFFF) bi = -1;
+      nn_idx[j] = bi;
+      const float qnan = CUDART_NAN_F;
+      float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
+      if (bi >= 0 && bi < nvalid) { o0 = normals_c[2 * (size_t)bi]; o1 = normals_c[2 * (size_t)bi + 1]; }
+      else atomicAdd(&st->nn_oor, 1);
+      nn_normal[2 * (size_t)j] = o0;
+      nn_normal[2 * (size_t)j + 1] = o1;
+    }
   }
 }
 
@@ -585,11 +621,17 @@ __device__ void d_jacobi3(const double Ain[9], double vals[3], double vecs[9]) {
 
 // a5 getLocalFrame (src/tunnel_processing.cpp:92-148), diagonal form of the dense weights*normals
 // product.  w_i = float(exp((double(curv_i) + 0.001/wf)^2)); Wn = w_i*n_i in float; the 3x3
-// scatter sum is accumulated in double (fixed grid, fixed tree -> reproducible).
+// scatter sum is accumulated in double (fixed grid, fixed tree -> reproducible); the last block to
+// finish sums the per-block partials in block order and runs the eigen solve.
 constexpr int FR_BLOCK = 256;
+struct FrameOut { float vals[3]; float vecs[9]; float scatter[9]; };
+
 __global__ void __launch_bounds__(FR_BLOCK)
-k_frame_partial(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, double shift, double* __restrict__ partials) {
+k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, double shift, double* __restrict__ partials,
+        unsigned* counter, FrameOut* out) {
   __shared__ double sm[6 * (FR_BLOCK / 32)];
+  __shared__ double fin[6];
+  __shared__ bool s_last;
   const int n = *n_ptr;
   double s[6] = {0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * FR_BLOCK + threadIdx.x; i < n; i += gridDim.x * FR_BLOCK) {
@@ -602,18 +644,23 @@ k_frame_partial(const float4* __restrict__ normals_c, const int* __restrict__ n_
     s[3] += (double)b * (double)b; s[4] += (double)b * (double)c; s[5] += (double)c * (double)c;
   }
   block_sum<6, FR_BLOCK>(s, sm);
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     for (int k = 0; k < 6; ++k) partials[blockIdx.x * 6 + k] = s[k];
-}
-
-struct FrameOut { float vals[3]; float vecs[9]; float scatter[9]; };
-
-__global__ void k_frame_final(const double* __restrict__ partials, int nblocks, FrameOut* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s[6] = {0, 0, 0, 0, 0, 0};
-  for (int b = 0; b < nblocks; ++b)
-    for (int k = 0; k < 6; ++k) s[k] += partials[b * 6 + k];
-  float Sf[9] = {(float)s[0], (float)s[1], (float)s[2], (float)s[1], (float)s[3], (float)s[4], (float)s[2], (float)s[4], (float)s[5]};
+    __threadfence();
+    unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) { *counter = 0u; __threadfence(); }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x < 6) {
+    double acc = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) acc += __ldcg(partials + (size_t)b * 6 + threadIdx.x);
+    fin[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  float Sf[9] = {(float)fin[0], (float)fin[1], (float)fin[2], (float)fin[1], (float)fin[3], (float)fin[4], (float)fin[2], (float)fin[4], (float)fin[5]};
   double Sd[9], vals[3], vecs[9];
   for (int k = 0; k < 9; ++k) { Sd[k] = Sf[k]; out->scatter[k] = Sf[k]; }
   d_jacobi3(Sd, vals, vecs);

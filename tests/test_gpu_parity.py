@@ -411,3 +411,81 @@ def test_process_scan_end_to_end_against_oracle_chain():
     # cross-section radius ~ tunnel radius in well-populated slices
     good = poly["count"] > 2000
     assert np.abs(poly["radius"][good] - 2.5).max() < 0.1
+
+
+# ---- the reference's own call sequence through the mirrored host API --------------------------------
+def test_cloud_cb_sequence_through_the_mirror_api():
+    """src/geometric_mapping.cpp:48-125 with the four L1 calls swapped for the mirror functions."""
+    from geometric_mapping_b200 import tunnel_processing as tp
+    from geometric_mapping_b200.params import LAUNCH_FILE_VALUES, Parameters
+
+    params = Parameters({**LAUNCH_FILE_VALUES, "neighborRadius": 0.3, "voxelGridLeafSize": 0.5})
+    assert params.getBoxFilterBound() == 5.0 and params.displayNormals() is False
+    cloud = _scan_with_junk(30_000, seed=13)
+    with capi.Context(params.to_gm_params(), max_points=len(cloud)) as ctx:
+        cloudChopped = tp.chopCloud(params.getBoxFilterBound(), cloud, ctx)                    # :57
+        cloudNormals, cloudChopped = tp.getNormals(params.getNeighborRadius(), cloudChopped, ctx)   # :63
+        normalsDisp = tp.rvizNormals(params.getLeafSize(), cloudChopped, ctx, cloudNormals)    # :70
+        eigenVals, eigenVecs = tp.getLocalFrame(len(cloudChopped), params.getWeightingFactor(), cloudNormals, ctx)  # :82
+        centerAxis = eigenVecs[:, 0]                                                           # :91-92
+        eigenBasis = tp.rvizEigens(eigenVals, eigenVecs)                                       # :96
+    ref_crop, _ = O.crop(cloud, 5.0, True)
+    ref_n, _, _ = O.normals(ref_crop, 0.3)
+    ref_cloud, ref_nc, _ = O.compact(ref_crop, ref_n)
+    assert np.array_equal(cloudChopped.view(np.uint32), ref_cloud.view(np.uint32))
+    assert cloudNormals.shape == ref_nc.shape
+    ref_f = O.local_frame(cloudNormals, 0.2)
+    assert np.abs(eigenVals - ref_f["vals"]).max() <= 1e-4 * ref_f["vals"].max()
+    assert _angle(centerAxis.astype(np.float64), ref_f["vecs"][:, 0].astype(np.float64)) < 1e-3
+    ref_v = O.voxel(cloudChopped, 0.5)
+    assert len(normalsDisp) == ref_v["V"]
+    m0 = normalsDisp[0]
+    assert m0["ns"] == "normals" and m0["header"]["frame_id"] == "/velodyne" and m0["type"] == "ARROW"
+    assert m0["color"] == {"a": 1.0, "r": 0.0, "g": 0.0, "b": 1.0}                  # quirk B.5: (1,0,0,1) pushed as a,r,g,b
+    assert np.allclose(m0["points"][0], ref_v["centroids"][0, :3]) and m0["scale"] == (0.025, 0.07500000298023224, 0.0625)
+    assert [m["ns"] for m in eigenBasis] == ["eigenBasis"] * 3 and [m["id"] for m in eigenBasis] == [0, 1, 2]
+    assert eigenBasis[0]["points"][0] == (0.0, 0.0, 0.0) and np.allclose(eigenBasis[0]["points"][1], centerAxis)
+    assert eigenBasis[1]["color"] == {"a": 1.0, "r": 0.0, "g": 1.0, "b": 0.0}
+
+
+def test_stage_order_and_capacity_errors():
+    with _ctx(100) as ctx:
+        with pytest.raises(capi.GmError) as e:
+            ctx.crop()
+        assert e.value.status == capi.GM_ERR_STAGE_ORDER
+        with pytest.raises(capi.GmError) as e:
+            ctx.upload_scan(np.zeros((101, 4), np.float32))
+        assert e.value.status == capi.GM_ERR_CAPACITY
+        ctx.upload_scan(np.zeros((10, 4), np.float32))
+        with pytest.raises(capi.GmError) as e:
+            ctx.normals()
+        assert e.value.status == capi.GM_ERR_STAGE_ORDER
+        ctx.crop()
+        ctx.normals()
+        with pytest.raises(capi.GmError) as e:
+            ctx.axis_polyline()
+        assert e.value.status == capi.GM_ERR_STAGE_ORDER
+
+
+def test_strided_upload_and_results_are_reproducible():
+    """PointCloud2-like point_step of 32 bytes (x,y,z,+intensity,ring...) and run-to-run determinism."""
+    pts = synth.curved_tunnel(40_000, seed=3)
+    wide = np.zeros((len(pts), 8), np.float32)
+    wide[:, :3] = pts[:, :3]
+    wide[:, 3:] = 123.0
+    outs = []
+    with _ctx(len(pts), neighborRadius=0.15) as ctx:
+        for rep in range(2):
+            if rep == 0:
+                ctx.upload_scan_raw(wide.ctypes.data, len(wide), 32)
+            else:
+                ctx.upload_scan(pts)
+            ps = synth.sample_indices(30_000, 256, 3, seed=3)
+            cs = synth.sample_indices(30_000, 256, 2, seed=4)
+            ctx.process_scan(ps, cs)
+            outs.append((ctx.download_normals(1), ctx.frame()["scatter"], ctx.model(0)["coef"], ctx.model(1)["coef"],
+                         ctx.download_polyline(), ctx.download_labels()))
+    a, b = outs
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))     # normals bitwise reproducible
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert a[4].tobytes() == b[4].tobytes() and np.array_equal(a[5], b[5])

@@ -58,5 +58,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_BIN = os.path.join(HOST_DIR, "geometric_mapping_node")
+HOST_SOURCES = ["geometric_mapping_node.cpp", "tunnel_processing.cpp", "paramHandler.cpp"]
+
+
+def build_host(force: bool = False) -> str:
+    """C++ host shim + ROS-free node harness (mirrors the reference's node) linked against the library."""
+    build()
+    deps = [os.path.join(HOST_DIR, f) for f in HOST_SOURCES + ["tunnel_processing.hpp", "paramHandler.hpp", "gm_types.hpp"]]
+    if not force and os.path.exists(HOST_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_BIN) for d in deps + [LIB]):
+        return HOST_BIN
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_BIN] + HOST_SOURCES + [
+        "-L" + CSRC, "-lgm_b200", "-Wl,-rpath,$ORIGIN/../csrc"]
+    res = subprocess.run(cmd, cwd=HOST_DIR, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

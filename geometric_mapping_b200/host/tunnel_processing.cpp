@@ -1,0 +1,103 @@
+#include "tunnel_processing.hpp"
+
+#include <cstring>
+
+namespace gmhost {
+namespace {
+void ck(gm_status s, const char* where, gm_status also_ok = GM_OK) {
+  if (s != GM_OK && s != also_ok) throw GmError(s, where);
+}
+void setParam(gm_ctx* ctx, double gm_params::*field, double value) {
+  // the reference passes these per call; the ctx caches them, so only touch it on change
+  static thread_local gm_params cur;
+  static thread_local gm_ctx* owner = nullptr;
+  if (owner != ctx) { gm_params_default(&cur); owner = ctx; }
+  if (cur.*field != value) { cur.*field = value; ck(gm_set_params(ctx, &cur), "gm_set_params"); }
+}
+}  // namespace
+
+CloudPtr chopCloud(const double& bound, const CloudPtr& cloud, const SearchPtr& gm) {
+  setParam(gm->ctx, &gm_params::boxFilterBound, bound);
+  ck(gm_upload_scan(gm->ctx, &cloud->data()->x, cloud->size(), sizeof(PointXYZ)), "gm_upload_scan");
+  ck(gm_crop(gm->ctx), "gm_crop");
+  gm_counts c;
+  ck(gm_get_counts(gm->ctx, &c), "gm_get_counts");
+  auto out = std::make_shared<Cloud>((size_t)c.n_cropped);
+  ck(gm_download_cloud(gm->ctx, 0, out->empty() ? nullptr : &out->data()->x, out->size()), "gm_download_cloud",
+     out->empty() ? GM_ERR_INVALID_ARG : GM_OK);
+  return out;
+}
+
+NormalsPtr getNormals(const double& neighborRadius, CloudPtr& cloud, SearchPtr& kdtree) {
+  gm_ctx* ctx = kdtree->ctx;
+  setParam(ctx, &gm_params::neighborRadius, neighborRadius);
+  ck(gm_normals(ctx), "gm_normals");
+  gm_counts c;
+  ck(gm_get_counts(ctx, &c), "gm_get_counts");
+  auto normals = std::make_shared<Normals>((size_t)c.n_valid);
+  cloud->resize((size_t)c.n_valid);  // in-place compaction of the caller's cloud, as the reference does
+  if (c.n_valid > 0) {
+    ck(gm_download_normals(ctx, 1, normals->data()->normal, normals->size()), "gm_download_normals");
+    ck(gm_download_cloud(ctx, 1, &cloud->data()->x, cloud->size()), "gm_download_cloud");
+  }
+  return normals;
+}
+
+void getLocalFrame(const int& cloudSize, const double& weightingFactor, const NormalsPtr& cloud_normals, const SearchPtr& gm,
+                   Vector3f& eigenVals, Matrix3f& eigenVecs) {
+  if ((size_t)cloudSize != cloud_normals->size()) throw GmError(GM_ERR_INVALID_ARG, "getLocalFrame: cloudSize");
+  setParam(gm->ctx, &gm_params::weightingFactor, weightingFactor);
+  ck(gm_local_frame(gm->ctx), "gm_local_frame");
+  gm_frame f;
+  ck(gm_get_frame(gm->ctx, &f), "gm_get_frame");
+  std::memcpy(eigenVals.data(), f.vals, sizeof(f.vals));
+  std::memcpy(eigenVecs.m, f.vecs, sizeof(f.vecs));
+}
+
+Marker rvizArrow(const Vector3f& start, const Vector3f& end, const Vector3f& scale, const Vector4f& color,
+                 const std::string& ns, const int& id, const std::string& frame) {
+  Marker m;
+  m.frame_id = frame; m.ns = ns; m.id = id;
+  for (int k = 0; k < 3; ++k) { m.points[0][k] = start[k]; m.points[1][k] = end[k]; m.scale[k] = scale[k]; }
+  m.a = color[0]; m.r = color[1]; m.g = color[2]; m.b = color[3];  // pushed as (a,r,g,b)
+  return m;
+}
+
+namespace {
+Marker fromArrow(const gm_arrow& a, const char* ns) {
+  return rvizArrow({a.start[0], a.start[1], a.start[2]}, {a.end[0], a.end[1], a.end[2]}, {a.scale[0], a.scale[1], a.scale[2]},
+                   {a.color_argb[0], a.color_argb[1], a.color_argb[2], a.color_argb[3]}, ns, a.id);
+}
+}  // namespace
+
+MarkerArray rvizNormals(const double& leafSize, const CloudPtr& cloud, const SearchPtr& kdtree, const NormalsPtr& normals) {
+  (void)cloud; (void)normals;  // both are resident on the device from getNormals
+  gm_ctx* ctx = kdtree->ctx;
+  setParam(ctx, &gm_params::voxelGridLeafSize, leafSize);
+  ck(gm_voxel(ctx), "gm_voxel");
+  gm_counts c;
+  ck(gm_get_counts(ctx, &c), "gm_get_counts");
+  const size_t V = (size_t)c.n_voxels;
+  std::vector<float> cen(V * 4), nn(V * 8);
+  MarkerArray out;
+  if (V == 0) return out;
+  gm_status s = gm_download_voxels(ctx, cen.data(), nullptr, nullptr, nullptr, nn.data(), V);
+  if (s == GM_ERR_NN_INDEX_RANGE) throw GmError(s, "rvizNormals: normals->at(index) out of range (reference quirk B.3)");
+  ck(s, "gm_download_voxels", GM_WARN_VOXEL_OVERFLOW);
+  std::vector<gm_arrow> arrows(V);
+  gm_markers_normals(cen.data(), nn.data(), (int32_t)V, arrows.data());
+  out.reserve(V);
+  for (const gm_arrow& a : arrows) out.push_back(fromArrow(a, "normals"));
+  return out;
+}
+
+MarkerArray rvizEigens(const Vector3f& eigenVals, const Matrix3f& eigenVecs) {
+  gm_frame f{};
+  std::memcpy(f.vals, eigenVals.data(), sizeof(f.vals));
+  std::memcpy(f.vecs, eigenVecs.m, sizeof(f.vecs));
+  gm_arrow arrows[3];
+  gm_markers_eigen(&f, arrows);
+  return {fromArrow(arrows[0], "eigenBasis"), fromArrow(arrows[1], "eigenBasis"), fromArrow(arrows[2], "eigenBasis")};
+}
+
+}  // namespace gmhost

@@ -489,3 +489,30 @@ def test_strided_upload_and_results_are_reproducible():
     assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))     # normals bitwise reproducible
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert a[4].tobytes() == b[4].tobytes() and np.array_equal(a[5], b[5])
+
+
+def test_cpp_host_shim_node_harness_runs_cloud_cb():
+    """The compiled C++ mirror of the node (geometric_mapping_b200/host) through the C-ABI."""
+    import subprocess
+
+    from geometric_mapping_b200 import build as gm_build
+
+    exe = gm_build.build_host()
+    pts = synth.straight_cylinder(50_000, seed=1, noise=0.01)
+    path = "/tmp/gm_scan_test.f32x4"
+    pts.tofile(path)
+    res = subprocess.run([exe, "--set", "neighborRadius=0.2", "--set", "voxelGridLeafSize=0.5", "--set", "displayNormals=true",
+                          "--scan", path], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.splitlines()
+    axis = np.array([float(v) for v in lines[lines.index("Center Axis is:") + 1].split()])
+    vals = np.array([float(v) for v in lines[lines.index("Eigenvalues are:") + 1].split()])
+    assert abs(abs(axis[0]) - 1.0) < 1e-3 and vals[0] < 1e-2 * vals[2]
+    with _ctx(len(pts), neighborRadius=0.2, voxelGridLeafSize=0.5) as ctx:
+        ctx.upload_scan(pts)
+        ctx.process_scan(None, None)
+        fr = ctx.frame()
+        c = ctx.counts()
+    assert np.allclose(vals, fr["vals"], rtol=1e-5) and np.allclose(axis, fr["vecs"][:, 0], atol=1e-5)
+    assert f"publish cloudOutput: {c.n_valid} points" in res.stdout
+    assert f"publish normalsOutput: {c.n_voxels} markers" in res.stdout

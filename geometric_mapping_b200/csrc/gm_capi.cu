@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -562,8 +563,9 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
       SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_COUNT : SEG_CYL_COUNT);
       const int K = kind == 0 ? RC_KP : RC_KC;
       int groups = div_up(hloc, RC_BLOCK * K);
-      // ~8 co-resident 64-thread blocks per SM (register limited), every slice at least half a tile
-      int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE / 2), div_up(ctx->num_sms * 8, groups)));
+      // co-resident 64-thread blocks per SM (register limited to 14), every slice at least half a tile
+      static const int kBlocksPerSm = [] { const char* e = std::getenv("GM_COUNT_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 8; }();
+      int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE / 2), div_up(ctx->num_sms * kBlocksPerSm, groups)));
       dim3 grid(slices, groups);
       if (kind == 0) {
         GM_LAUNCH(ctx, k_count_plane<RC_KP>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, ctx->d_hvalid[0], h_begin, h_end,

@@ -442,7 +442,8 @@ def test_cloud_cb_sequence_through_the_mirror_api():
     m0 = normalsDisp[0]
     assert m0["ns"] == "normals" and m0["header"]["frame_id"] == "/velodyne" and m0["type"] == "ARROW"
     assert m0["color"] == {"a": 1.0, "r": 0.0, "g": 0.0, "b": 1.0}                  # quirk B.5: (1,0,0,1) pushed as a,r,g,b
-    assert np.allclose(m0["points"][0], ref_v["centroids"][0, :3]) and m0["scale"] == (0.025, 0.07500000298023224, 0.0625)
+    assert np.allclose(m0["points"][0], ref_v["centroids"][0, :3])
+    assert m0["scale"] == tuple(float(np.float32(v)) for v in (0.025, 0.075, 0.0625))        # :230 stored as floats
     assert [m["ns"] for m in eigenBasis] == ["eigenBasis"] * 3 and [m["id"] for m in eigenBasis] == [0, 1, 2]
     assert eigenBasis[0]["points"][0] == (0.0, 0.0, 0.0) and np.allclose(eigenBasis[0]["points"][1], centerAxis)
     assert eigenBasis[1]["color"] == {"a": 1.0, "r": 0.0, "g": 1.0, "b": 0.0}

@@ -68,6 +68,7 @@ struct gm_ctx {
   int hcap = 0;     // max hypotheses
   int device = 0;
   int num_sms = 148;
+  int gn_blocks = 148;  // cooperative grid of the cylinder refit
   cudaStream_t own_stream = nullptr, stream = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -332,6 +333,12 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_model, 0, 2 * sizeof(ModelState))) != cudaSuccess) return fail(e, "memset");
+  {
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cyl_gn_all, RF_BLOCK, 0)) != cudaSuccess) return fail(e, "occupancy");
+    ctx->gn_blocks = std::max(1, std::min(ctx->num_sms, per_sm * ctx->num_sms));
+    if ((size_t)ctx->gn_blocks * 2 * GN_NV > (size_t)std::max(FRAME_BLOCKS, REFIT_BLOCKS) * 32) return fail(cudaErrorInvalidValue, "partials capacity");
+  }
   ctx->grid = make_grid(ctx->prm);
   *out = ctx;
   return GM_OK;
@@ -431,7 +438,7 @@ gm_status gm_crop(gm_ctx* ctx) {
     if (s != GM_OK) return s;
     float hi = (float)ctx->prm.boxFilterBound, lo = (float)(-ctx->prm.boxFilterBound);
     SegTimer seg_(ctx, SEG_CROP);
-    GM_LAUNCH(ctx, k_crop, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_scan, (int)n, lo, hi, ctx->prm.is_dense,
+    GM_LAUNCH(ctx, k_crop, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_scan, (int)n, lo, hi, ctx->prm.is_dense,
               ctx->d_crop, ctx->d_state64, ctx->d_st);
     GM_CHECK_LAUNCHES(ctx);
   }
@@ -457,7 +464,7 @@ gm_status gm_normals(gm_ctx* ctx) {
     if (s != GM_OK) return s;
     if ((s = reset_state64(ctx, n)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_GRID_BUILD);
-    GM_LAUNCH(ctx, k_cell_heads, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_crop, n_ptr,
+    GM_LAUNCH(ctx, k_cell_heads, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_crop, n_ptr,
               g.ncells, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_state64, ctx->d_st);
     GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n * 9, 256), ctx->num_sms * 16), 256, ctx->d_ucell_key,
               ctx->d_ucell_start, ctx->d_st, g, ctx->d_runs); }
@@ -505,14 +512,14 @@ gm_status gm_voxel(gm_ctx* ctx) {
     if (s != GM_OK) return s;
     if ((s = reset_state64(ctx, n)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_VOX_REDUCE);
-    GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_assign,
+    GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_assign,
               ctx->d_vox_start, ctx->d_vox_key, ctx->d_state64, ctx->d_st);
     GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_vals[buf], ctx->d_cloud_c,
               ctx->d_vox_start, ctx->d_st, ctx->d_centroid, ctx->d_vox_count); }
     if (ctx->have_normals) {
       SegTimer seg_(ctx, SEG_VOX_NN);
       GM_LAUNCH(ctx, k_voxel_nn, std::min(div_up((long long)n * 32, NN_BLOCK), ctx->num_sms * 16), NN_BLOCK, ctx->d_centroid, ctx->d_sorted,
-                ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_valid_map, ctx->d_normals_c, ctx->grid, ctx->prm.nn_index_mode,
+                ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_runs, ctx->d_valid_map, ctx->d_normals_c, ctx->grid, ctx->prm.nn_index_mode,
                 ctx->d_st, ctx->d_nn_idx, ctx->d_nn_normal);
     }
     GM_CHECK_LAUNCHES(ctx);
@@ -603,11 +610,20 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
   } else if (ctx->n_input) {
     gm_status s = reset_state64(ctx, ctx->n_input);
     if (s != GM_OK) return s;
-    GM_LAUNCH(ctx, k_cyl_inlier_compact, div_up((long long)ctx->n_input, CP_TILE), CP_BLOCK, ctx->d_cloud_c, n_ptr, ms, ctx->d_inl,
+    GM_LAUNCH(ctx, k_cyl_inlier_compact, div_up((long long)ctx->n_input, CPL_TILE), CP_BLOCK, ctx->d_cloud_c, n_ptr, ms, ctx->d_inl,
               ctx->d_state64, &ctx->d_st->error);
-    for (int it = 0; it <= ctx->prm.refitIterations; ++it)
-      GM_LAUNCH(ctx, k_cyl_gn, ctx->num_sms, RF_BLOCK, ctx->d_inl, ms, it < ctx->prm.refitIterations ? 1 : 0, tau, ctx->d_partials,
-                ctx->d_counters + 2);
+    // all Gauss-Newton passes in one cooperative launch (grid barrier between passes)
+    GM_CUDA(cudaMemsetAsync(ctx->d_counters + 2, 0, sizeof(unsigned), ctx->stream));
+    {
+      const float4* inl = ctx->d_inl;
+      int iters = ctx->prm.refitIterations;
+      double* partials = ctx->d_partials;
+      unsigned* bar = ctx->d_counters + 2;
+      int* err = &ctx->d_st->error;
+      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bar, (void*)&err};
+      GM_CUDA(cudaLaunchCooperativeKernel((const void*)k_cyl_gn_all, dim3(ctx->gn_blocks), dim3(RF_BLOCK), args, 0, ctx->stream));
+      ++ctx->launches;
+    }
   }
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_model[kind] = true;

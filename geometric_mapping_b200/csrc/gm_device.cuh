@@ -90,31 +90,43 @@ __device__ __forceinline__ unsigned long long ts_load(const unsigned long long* 
 
 // Warp-cooperative look-back: returns the exclusive prefix of tile `tile` (sum of aggregates of
 // all earlier tiles).  Call with all 32 lanes of one warp.  `err` is raised on spin-bound.
+// Each round inspects a window of 128 predecessor tiles: every lane issues 4 independent loads
+// (L2 latency is paid once per round, not once per tile), then the four 32-tile groups are
+// folded in order, nearest first.  In a single-wave launch nobody but tile 0 holds a full prefix
+// early on, so the walk length, not bandwidth, is what bounds these kernels.
 __device__ __forceinline__ unsigned lookback_exclusive(const unsigned long long* state, int tile, int* err) {
   unsigned exclusive = 0;
   int base = tile - 1;
+  const unsigned long long zero_prefix = (unsigned long long)TS_PREFIX << 32;
   while (base >= 0) {
-    int t = base - lane_id();
-    unsigned long long w = 0;
-    unsigned status = TS_PREFIX;  // lanes before tile 0 act as a zero prefix
-    unsigned value = 0;
-    if (t >= 0) {
-      int spins = 0;
-      do {
-        w = ts_load(state + t);
-        status = (unsigned)(w >> 32);
-      } while (status == TS_EMPTY && ++spins < SPIN_BOUND);
-      value = (unsigned)w;
-      if (status == TS_EMPTY) { atomicExch(err, 1); status = TS_PREFIX; value = 0; }
-    }
-    unsigned pref_mask = __ballot_sync(FULL, status == TS_PREFIX);
-    int first = __ffs(pref_mask) - 1;  // nearest predecessor that already holds a full prefix
-    unsigned contrib = (first < 0 || lane_id() <= first) ? value : 0u;
+    unsigned long long w[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(FULL, contrib, o);
-    exclusive += contrib;
-    if (first >= 0) break;
-    base -= 32;
+    for (int q = 0; q < 4; ++q) {
+      int t = base - q * 32 - lane_id();
+      w[q] = (t >= 0) ? ts_load(state + t) : zero_prefix;  // tiles before 0 act as a zero prefix
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int t = base - q * 32 - lane_id();
+      unsigned status = (unsigned)(w[q] >> 32);
+      if (t >= 0 && status == TS_EMPTY) {
+        int spins = 0;
+        do {
+          w[q] = ts_load(state + t);
+          status = (unsigned)(w[q] >> 32);
+        } while (status == TS_EMPTY && ++spins < SPIN_BOUND);
+        if (status == TS_EMPTY) { atomicExch(err, 1); status = TS_PREFIX; w[q] = zero_prefix; }
+      }
+      unsigned value = (unsigned)w[q];
+      unsigned pref_mask = __ballot_sync(FULL, status == TS_PREFIX);
+      int first = __ffs(pref_mask) - 1;  // nearest predecessor in this group that holds a full prefix
+      unsigned contrib = (first < 0 || lane_id() <= first) ? value : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(FULL, contrib, o);
+      exclusive += contrib;
+      if (first >= 0) return exclusive;
+    }
+    base -= 128;
   }
   return exclusive;
 }
@@ -300,16 +312,26 @@ k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restric
     for (int ww = 0; ww < w; ++ww) lbase += s_scan[ww];
     s_local_base[d] = lbase + linc - tile_cnt;
 
-    // look back over earlier tiles for this digit
+    // look back over earlier tiles for this digit: 8 independent loads per step (one L2 round trip
+    // per 8 tiles), folded nearest first until a tile with a full prefix is met
     unsigned excl = 0;
-    for (int t = tile - 1; t >= 0; --t) {
-      const unsigned* ps = state + (size_t)t * 256 + d;
-      unsigned wv;
-      int spins = 0;
-      do { wv = rs_load(ps); } while ((wv >> 30) == TS_EMPTY && ++spins < SPIN_BOUND);
-      if ((wv >> 30) == TS_EMPTY) { atomicExch(err, 2); break; }
-      excl += wv & 0x3FFFFFFFu;
-      if ((wv >> 30) == TS_PREFIX) break;
+    bool done = false;
+    for (int t0 = tile - 1; t0 >= 0 && !done; t0 -= 8) {
+      unsigned wv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wv[q] = (t0 - q >= 0) ? rs_load(state + (size_t)(t0 - q) * 256 + d) : ((unsigned)TS_PREFIX << 30);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (done) break;
+        if ((wv[q] >> 30) == TS_EMPTY) {
+          const unsigned* ps = state + (size_t)(t0 - q) * 256 + d;
+          int spins = 0;
+          do { wv[q] = rs_load(ps); } while ((wv[q] >> 30) == TS_EMPTY && ++spins < SPIN_BOUND);
+          if ((wv[q] >> 30) == TS_EMPTY) { atomicExch(err, 2); done = true; break; }
+        }
+        excl += wv[q] & 0x3FFFFFFFu;
+        if ((wv[q] >> 30) == TS_PREFIX) done = true;
+      }
     }
     if (tile != 0) rs_store(st, TS_PREFIX, excl + tile_cnt);
     s_global_base[d] = digit_global + excl;

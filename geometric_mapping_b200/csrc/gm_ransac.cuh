@@ -458,26 +458,26 @@ __device__ __forceinline__ void d_perp_basis_d(const double dir[3], double u[3],
 __global__ void __launch_bounds__(CP_BLOCK)
 k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_ptr, ModelState* ms,
                      float4* __restrict__ inl, unsigned long long* state, int* err) {
-  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
+  __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = *n_ptr;
-  const int tile = blockIdx.x, base = tile * CP_TILE;
+  const int tile = blockIdx.x, base = tile * CPL_TILE;
   if (base >= n) return;
   const bool have = ms->best_id >= 0;
   const CylTest t = d_load_cyl_test(ms->test_hyp);
-  bool f[CP_IPT];
-  float4 p[CP_IPT];
+  bool f[CPL_IPT];
+  float4 p[CPL_IPT];
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j) {
+  for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
     f[j] = false;
     if (i < n) { p[j] = pts[i]; f[j] = have && d_cyl_inlier(t, p[j]); }
   }
-  unsigned ranks[CP_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, err, sm);
+  unsigned ranks[CPL_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, err, sm);
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j)
+  for (int j = 0; j < CPL_IPT; ++j)
     if (f[j]) inl[ranks[j]] = p[j];
-  if (base + CP_TILE >= n && threadIdx.x == 0) ms->n_inl = (int)total;
+  if (base + CPL_TILE >= n && threadIdx.x == 0) ms->n_inl = (int)total;
 }
 
 __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
@@ -503,74 +503,109 @@ __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
   return true;
 }
 
-// One Gauss-Newton pass over the compacted inliers: sums of J^T J (15), J^T r (5), count, sum r^2
-// at the current iterate; the last block solves the 5x5 system and moves the iterate (update = 1)
-// or publishes count / rms / float coefficients / refined inlier test (update = 0).
+// All Gauss-Newton passes of the cylinder refit in ONE cooperative launch (grid <= co-resident
+// capacity, guaranteed by cudaLaunchCooperativeKernel).  Per pass every block reduces its share of
+// the compacted inliers to 22 doubles (J^T J: 15, J^T r: 5, count, sum r^2), publishes them, crosses
+// a grid barrier, and then EVERY block sums the per-block partials in block order and solves the
+// same 5x5 system (redundant but deterministic: no second barrier, no broadcast).  The last pass
+// (update = 0) publishes count / rms / float coefficients / the refined inlier test.
 constexpr int GN_NV = 22;
+
+__device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(count, 1u);
+    int spins = 0;
+    while (*((volatile unsigned*)count) < target && ++spins < SPIN_BOUND) {}
+    if (spins >= SPIN_BOUND) atomicExch(err, 3);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(RF_BLOCK)
-k_cyl_gn(const float4* __restrict__ inl, ModelState* ms, int update, float tau, double* __restrict__ partials, unsigned* counter) {
+k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float tau, double* __restrict__ partials /* 2 x grid x 22 */,
+             unsigned* barrier_count, int* err) {
   __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
   __shared__ double fin[GN_NV];
+  __shared__ double it_q[3], it_dir[3], it_r;
   const bool have = ms->best_id >= 0;
   const int n = have ? ms->n_inl : 0;
-  double s[GN_NV];
-#pragma unroll
-  for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
-  {
-    const double q0 = ms->q[0], q1 = ms->q[1], q2 = ms->q[2], r = ms->r;
-    double dir[3] = {ms->dir[0], ms->dir[1], ms->dir[2]}, u[3], w[3];
-    d_perp_basis_d(dir, u, w);
-    for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += gridDim.x * RF_BLOCK) {
-      float4 p = inl[i];
-      s[20] += 1.0;
-      double vx = (double)p.x - q0, vy = (double)p.y - q1, vz = (double)p.z - q2;
-      double A = u[0] * vx + u[1] * vy + u[2] * vz;
-      double B = w[0] * vx + w[1] * vy + w[2] * vz;
-      double tt = dir[0] * vx + dir[1] * vy + dir[2] * vz;
-      double dist = sqrt(A * A + B * B);
-      if (!(dist > 1e-12)) continue;
-      double res = dist - r;
-      s[21] += res * res;
-      double J[5] = {-A / dist, -B / dist, -A * tt / dist, -B * tt / dist, -1.0};
-      int idx = 0;
-#pragma unroll
-      for (int a = 0; a < 5; ++a) {
-#pragma unroll
-        for (int b = a; b < 5; ++b) s[idx++] += J[a] * J[b];
-      }
-#pragma unroll
-      for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
-    }
+  const int nb = gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) { it_q[k] = ms->q[k]; it_dir[k] = ms->dir[k]; }
+    it_r = ms->r;
   }
-  block_sum<GN_NV, RF_BLOCK>(s, sm);
-  if (threadIdx.x == 0)
-    for (int k = 0; k < GN_NV; ++k) partials[blockIdx.x * GN_NV + k] = s[k];
-  if (!d_last_block(counter)) return;
-  if (threadIdx.x < GN_NV) fin[threadIdx.x] = d_sum_partials<GN_NV>(partials, gridDim.x, threadIdx.x);
   __syncthreads();
-  if (threadIdx.x != 0 || !have) return;
-  long long cnt = (long long)(fin[20] + 0.5);
-  ms->refit_count = (int)cnt;
-  if (cnt <= 5) return;  // model unchanged
-  if (update) {
-    double JTJ[5][5], rhs[5], x[5];
-    int idx = 0;
-    for (int a = 0; a < 5; ++a) for (int b = a; b < 5; ++b) { JTJ[a][b] = fin[idx]; JTJ[b][a] = fin[idx]; ++idx; }
-    for (int a = 0; a < 5; ++a) rhs[a] = -fin[15 + a];
-    if (!d_solve5(JTJ, rhs, x)) return;
-    double dir[3] = {ms->dir[0], ms->dir[1], ms->dir[2]}, u[3], w[3];
-    d_perp_basis_d(dir, u, w);
-    for (int k = 0; k < 3; ++k) ms->q[k] += x[0] * u[k] + x[1] * w[k];
-    for (int k = 0; k < 3; ++k) dir[k] += x[2] * u[k] + x[3] * w[k];
-    double dl = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-    for (int k = 0; k < 3; ++k) ms->dir[k] = dir[k] / dl;
-    ms->r += x[4];
-  } else {
-    ms->rms = (float)sqrt(fin[21] / (double)cnt);
-    for (int k = 0; k < 3; ++k) { ms->coef[k] = (float)ms->q[k]; ms->coef[3 + k] = (float)ms->dir[k]; }
-    ms->coef[6] = (float)ms->r;
-    float t12[12];
-    if (d_cyl_test_params(ms->coef, tau, t12)) for (int k = 0; k < 12; ++k) ms->test_coef[k] = t12[k];
+  bool frozen = false;  // block-uniform: singular system or too few inliers -> iterate no longer moves
+  for (int it = 0; it <= iters; ++it) {
+    const int update = it < iters;
+    double s[GN_NV];
+#pragma unroll
+    for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
+    {
+      const double q0 = it_q[0], q1 = it_q[1], q2 = it_q[2], r = it_r;
+      double dir[3] = {it_dir[0], it_dir[1], it_dir[2]}, u[3], w[3];
+      d_perp_basis_d(dir, u, w);
+      for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += nb * RF_BLOCK) {
+        float4 p = inl[i];
+        s[20] += 1.0;
+        double vx = (double)p.x - q0, vy = (double)p.y - q1, vz = (double)p.z - q2;
+        double A = u[0] * vx + u[1] * vy + u[2] * vz;
+        double B = w[0] * vx + w[1] * vy + w[2] * vz;
+        double tt = dir[0] * vx + dir[1] * vy + dir[2] * vz;
+        double dist = sqrt(A * A + B * B);
+        if (!(dist > 1e-12)) continue;
+        double res = dist - r;
+        s[21] += res * res;
+        double J[5] = {-A / dist, -B / dist, -A * tt / dist, -B * tt / dist, -1.0};
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+#pragma unroll
+          for (int b = a; b < 5; ++b) s[idx++] += J[a] * J[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
+      }
+    }
+    block_sum<GN_NV, RF_BLOCK>(s, sm);
+    double* buf = partials + (size_t)(it & 1) * nb * GN_NV;
+    if (threadIdx.x == 0)
+      for (int k = 0; k < GN_NV; ++k) buf[blockIdx.x * GN_NV + k] = s[k];
+    d_grid_barrier(barrier_count, (unsigned)(it + 1) * (unsigned)nb, err);
+    if (threadIdx.x < GN_NV) fin[threadIdx.x] = d_sum_partials<GN_NV>(buf, nb, threadIdx.x);
+    __syncthreads();
+    const long long cnt = (long long)(fin[20] + 0.5);
+    if (cnt <= 5) frozen = true;  // model unchanged (same rule as the oracle)
+    if (threadIdx.x == 0 && have) {
+      if (blockIdx.x == 0) ms->refit_count = (int)cnt;
+      if (!frozen && update) {
+        double JTJ[5][5], rhs[5], x[5];
+        int idx = 0;
+        for (int a = 0; a < 5; ++a) for (int b = a; b < 5; ++b) { JTJ[a][b] = fin[idx]; JTJ[b][a] = fin[idx]; ++idx; }
+        for (int a = 0; a < 5; ++a) rhs[a] = -fin[15 + a];
+        if (d_solve5(JTJ, rhs, x)) {
+          double dir[3] = {it_dir[0], it_dir[1], it_dir[2]}, u[3], w[3];
+          d_perp_basis_d(dir, u, w);
+          for (int k = 0; k < 3; ++k) it_q[k] += x[0] * u[k] + x[1] * w[k];
+          for (int k = 0; k < 3; ++k) dir[k] += x[2] * u[k] + x[3] * w[k];
+          double dl = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+          for (int k = 0; k < 3; ++k) it_dir[k] = dir[k] / dl;
+          it_r += x[4];
+        }
+      }
+      if (!update && blockIdx.x == 0 && cnt > 5) {
+        ms->rms = (float)sqrt(fin[21] / (double)cnt);
+        for (int k = 0; k < 3; ++k) { ms->q[k] = it_q[k]; ms->dir[k] = it_dir[k]; ms->coef[k] = (float)it_q[k]; ms->coef[3 + k] = (float)it_dir[k]; }
+        ms->r = it_r;
+        ms->coef[6] = (float)it_r;
+        float t12[12];
+        if (d_cyl_test_params(ms->coef, tau, t12)) for (int k = 0; k < 12; ++k) ms->test_coef[k] = t12[k];
+      }
+    }
+    __syncthreads();
   }
 }
 

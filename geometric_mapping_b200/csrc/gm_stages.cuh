@@ -26,8 +26,10 @@ struct GridSpec {
 };
 
 constexpr int CP_BLOCK = 256;
-constexpr int CP_IPT = 4;
+constexpr int CP_IPT = 4;                      // items per thread where each item is register heavy
 constexpr int CP_TILE = CP_BLOCK * CP_IPT;
+constexpr int CPL_IPT = 8;                     // light items: fewer, larger tiles -> shorter look-back walks
+constexpr int CPL_TILE = CP_BLOCK * CPL_IPT;
 
 __device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
 
@@ -55,13 +57,13 @@ __global__ void k_set_w_one(float4* p, int n) {
 __global__ void __launch_bounds__(CP_BLOCK)
 k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, float4* __restrict__ out,
        unsigned long long* state, DevState* st) {
-  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
-  const int tile = blockIdx.x, base = tile * CP_TILE;
+  __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
+  const int tile = blockIdx.x, base = tile * CPL_TILE;
   if (base >= n) return;
-  float4 p[CP_IPT];
-  bool f[CP_IPT];
+  float4 p[CPL_IPT];
+  bool f[CPL_IPT];
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j) {
+  for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
     f[j] = false;
     if (i < n) {
@@ -71,12 +73,12 @@ k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, f
       f[j] = !drop;
     }
   }
-  unsigned ranks[CP_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+  unsigned ranks[CPL_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, &st->error, sm);
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j)
+  for (int j = 0; j < CPL_IPT; ++j)
     if (f[j]) out[ranks[j]] = p[j];
-  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_crop = (int)total;
+  if (base + CPL_TILE >= n && threadIdx.x == 0) st->n_crop = (int)total;
 }
 
 // Neighbour-grid cell key of every cropped point (sentinel ncells for non-finite points, which
@@ -104,15 +106,15 @@ __global__ void __launch_bounds__(CP_BLOCK)
 k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
              const int* __restrict__ n_ptr, unsigned ncells, float4* __restrict__ sorted_pts, int* __restrict__ cell_id,
              unsigned* __restrict__ ucell_key, int* __restrict__ ucell_start, unsigned long long* state, DevState* st) {
-  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
+  __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = *n_ptr;
-  const int tile = blockIdx.x, base = tile * CP_TILE;
+  const int tile = blockIdx.x, base = tile * CPL_TILE;
   if (base >= n) return;
-  bool f[CP_IPT];
-  unsigned key[CP_IPT];
+  bool f[CPL_IPT];
+  unsigned key[CPL_IPT];
   int nfinite_local = 0;
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j) {
+  for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
     f[j] = false;
     key[j] = 0;
@@ -131,10 +133,10 @@ k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ si
     }
   }
   if (nfinite_local) st->n_sorted_finite = nfinite_local;
-  unsigned ranks[CP_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+  unsigned ranks[CPL_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, &st->error, sm);
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j) {
+  for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
     if (i < n) {
       int id = f[j] ? (int)ranks[j] : (int)ranks[j] - 1;
@@ -142,7 +144,7 @@ k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ si
       if (f[j]) { ucell_key[id] = key[j]; ucell_start[id] = i; }
     }
   }
-  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_cells = (int)total;
+  if (base + CPL_TILE >= n && threadIdx.x == 0) st->n_cells = (int)total;
 }
 
 __device__ __forceinline__ int lower_bound_u32(const unsigned* __restrict__ a, int n, unsigned key) {
@@ -436,14 +438,14 @@ __global__ void k_voxel_keys(const float4* __restrict__ pts, const DevState* __r
 __global__ void __launch_bounds__(CP_BLOCK)
 k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, int* __restrict__ assign,
               int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, DevState* st) {
-  __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
+  __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = st->n_valid;
-  const int tile = blockIdx.x, base = tile * CP_TILE;
+  const int tile = blockIdx.x, base = tile * CPL_TILE;
   if (base >= n) return;
-  bool f[CP_IPT];
-  unsigned key[CP_IPT];
+  bool f[CPL_IPT];
+  unsigned key[CPL_IPT];
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j) {
+  for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
     f[j] = false; key[j] = 0;
     if (i < n) {
@@ -451,10 +453,10 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
       f[j] = (i == 0) || (key[j] != skeys[i - 1]);
     }
   }
-  unsigned ranks[CP_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+  unsigned ranks[CPL_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, &st->error, sm);
 #pragma unroll
-  for (int j = 0; j < CP_IPT; ++j) {
+  for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
     if (i < n) {
       int id = f[j] ? (int)ranks[j] : (int)ranks[j] - 1;
@@ -462,7 +464,7 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
       if (f[j]) { vox_start[id] = i; vox_key[id] = (int)key[j]; }
     }
   }
-  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_voxels = (int)total;
+  if (base + CPL_TILE >= n && threadIdx.x == 0) st->n_voxels = (int)total;
 }
 
 // Centroid per voxel: float sum over the members in ascending original index (stable sort order),
@@ -513,7 +515,7 @@ __device__ __forceinline__ void d_nn_scan(const float4* __restrict__ sp, const i
 
 __global__ void __launch_bounds__(NN_BLOCK)
 k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
-           const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
+           const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start, const int2* __restrict__ runs,
            const int* __restrict__ valid_map, const float4* __restrict__ normals_c, GridSpec g,
            int mode, DevState* st, int* __restrict__ nn_idx, float4* __restrict__ nn_normal) {
   const int V = st->n_voxels, U = st->n_cells, nf = st->n_sorted_finite, nvalid = st->n_valid;
@@ -528,9 +530,14 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
     int bi = 0x7FFFFFFF;
     for (int k = 1; k <= g.dim; ++k) {
       if (k == 1) {
-        // the 27-cell cube as 9 rows of 3 cells
+        // the 27-cell cube as 9 rows of 3 cells; if the centroid's own cell is occupied (the usual
+        // case) its runs were already computed for the normals stage: one search instead of 18
+        const unsigned ckey = (unsigned)cx + (unsigned)g.dim * ((unsigned)cy + (unsigned)g.dim * (unsigned)cz);
+        const int jc = lower_bound_u32(ucell_key, U, ckey);
+        const bool occupied = jc < U && ucell_key[jc] == ckey;
         if (lane < 9) {
-          int2 r = cell_run(ucell_key, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1);
+          int2 r = occupied ? runs[(size_t)jc * 9 + lane]
+                            : cell_run(ucell_key, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1);
           d_nn_scan(sp, valid_map, mode, r, c, best, bi);
         }
       } else {

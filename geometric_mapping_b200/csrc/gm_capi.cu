@@ -92,7 +92,10 @@ struct gm_ctx {
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
   unsigned char* d_labels = nullptr;
   unsigned long long* d_state64 = nullptr;
-  unsigned *d_rs_state = nullptr, *d_rs_hist = nullptr, *d_rs_ticket = nullptr;
+  unsigned long long* d_rs_state = nullptr;
+  unsigned *d_rs_hist = nullptr, *d_rs_ticket = nullptr;
+  unsigned epoch = 0;            // per-launch tag of the look-back tile states (never cleared)
+  unsigned gn_barrier_base = 0;  // cumulative arrivals at the cooperative GN barrier
   size_t rs_state_words = 0;
   DevState* d_st = nullptr;
   double* d_partials = nullptr;
@@ -194,32 +197,40 @@ GridSpec make_grid(const gm_params& p) {
   return g;
 }
 
+// A fresh epoch for the tile states of one launch (30-bit; on wrap the arrays are cleared once).
+gm_status next_epoch(gm_ctx* ctx, unsigned* out) {
+  ctx->epoch = (ctx->epoch + 1) & TS_EPOCH_MASK;
+  if (ctx->epoch == 0) {
+    GM_CUDA(cudaMemsetAsync(ctx->d_state64, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long), ctx->stream));
+    GM_CUDA(cudaMemsetAsync(ctx->d_rs_state, 0, ctx->rs_state_words * sizeof(unsigned long long), ctx->stream));
+    ctx->epoch = 1;
+  }
+  *out = ctx->epoch;
+  return GM_OK;
+}
+
 // LSD radix sort of (d_keys[0], d_vals[0]) -> returns the buffer index holding the result.
+// The histogram was cleared by the kernel that produced the keys; tickets reset themselves; tile
+// states are epoch tagged: no memset nodes.
 gm_status radix_sort(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int key_bits, int* result_buf) {
   int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
   int ntiles = div_up((long long)n_cap, RS_TILE);
   size_t words = (size_t)passes * ntiles * 256;
   if (words > ctx->rs_state_words) { ctx->err = "radix state capacity"; return GM_ERR_CAPACITY; }
-  GM_CUDA(cudaMemsetAsync(ctx->d_rs_state, 0, words * sizeof(unsigned), ctx->stream));
-  GM_CUDA(cudaMemsetAsync(ctx->d_rs_hist, 0, RS_MAX_PASSES * 256 * sizeof(unsigned), ctx->stream));
-  GM_CUDA(cudaMemsetAsync(ctx->d_rs_ticket, 0, RS_MAX_PASSES * sizeof(unsigned), ctx->stream));
+  unsigned epoch = 0;
+  gm_status st = next_epoch(ctx, &epoch);
+  if (st != GM_OK) return st;
   int hist_grid = std::min(ntiles, ctx->num_sms * 8);
   GM_LAUNCH(ctx, k_radix_hist, hist_grid, RS_BLOCK, ctx->d_keys[0], n_ptr, passes, ctx->d_rs_hist);
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
     GM_LAUNCH(ctx, k_radix_onesweep, ntiles, RS_BLOCK, ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1],
-              ctx->d_vals[cur ^ 1], n_ptr, p, ctx->d_rs_hist, ctx->d_rs_state + (size_t)p * ntiles * 256,
+              ctx->d_vals[cur ^ 1], n_ptr, p, ctx->d_rs_hist, ctx->d_rs_state + (size_t)p * ntiles * 256, epoch,
               ctx->d_rs_ticket + p, &ctx->d_st->error);
     cur ^= 1;
   }
   *result_buf = cur;
   GM_CHECK_LAUNCHES(ctx);
-  return GM_OK;
-}
-
-gm_status reset_state64(gm_ctx* ctx, size_t n_cap) {
-  size_t tiles = (size_t)div_up((long long)n_cap, CP_TILE) + 1;
-  GM_CUDA(cudaMemsetAsync(ctx->d_state64, 0, tiles * sizeof(unsigned long long), ctx->stream));
   return GM_OK;
 }
 
@@ -330,6 +341,10 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   for (int k = 0; k < 2; ++k)
     if ((e = cudaEventCreateWithFlags(&ctx->ev_samples[k], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
   if ((e = cudaMemset(ctx->d_st, 0, sizeof(DevState))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)N, CP_TILE) + 2) * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_rs_state, 0, ctx->rs_state_words * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_rs_hist, 0, RS_MAX_PASSES * 256 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_rs_ticket, 0, RS_MAX_PASSES * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_model, 0, 2 * sizeof(ModelState))) != cudaSuccess) return fail(e, "memset");
@@ -434,12 +449,13 @@ gm_status gm_crop(gm_ctx* ctx) {
   if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
   const size_t n = ctx->n_input;
   if (n) {
-    gm_status s = reset_state64(ctx, n);
+    unsigned epoch = 0;
+    gm_status s = next_epoch(ctx, &epoch);
     if (s != GM_OK) return s;
     float hi = (float)ctx->prm.boxFilterBound, lo = (float)(-ctx->prm.boxFilterBound);
     SegTimer seg_(ctx, SEG_CROP);
     GM_LAUNCH(ctx, k_crop, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_scan, (int)n, lo, hi, ctx->prm.is_dense,
-              ctx->d_crop, ctx->d_state64, ctx->d_st);
+              ctx->d_crop, ctx->d_state64, epoch, ctx->d_st);
     GM_CHECK_LAUNCHES(ctx);
   }
   ctx->have_crop = true;
@@ -456,16 +472,17 @@ gm_status gm_normals(gm_ctx* ctx) {
     const GridSpec g = ctx->grid;
     int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
     { SegTimer seg_(ctx, SEG_GRID_KEYS);
-      GM_LAUNCH(ctx, k_cell_keys, blocks, 256, ctx->d_crop, n_ptr, g, ctx->d_keys[0], ctx->d_vals[0]); }
+      GM_LAUNCH(ctx, k_cell_keys, blocks, 256, ctx->d_crop, n_ptr, g, ctx->d_keys[0], ctx->d_vals[0], ctx->d_rs_hist); }
     int buf = 0;
     gm_status s;
     { SegTimer seg_(ctx, SEG_GRID_SORT);
       s = radix_sort(ctx, n_ptr, n, bits_for((unsigned long long)g.ncells), &buf); }
     if (s != GM_OK) return s;
-    if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    unsigned epoch = 0;
+    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_GRID_BUILD);
     GM_LAUNCH(ctx, k_cell_heads, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_crop, n_ptr,
-              g.ncells, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_state64, ctx->d_st);
+              g.ncells, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_state64, epoch, ctx->d_st);
     GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n * 9, 256), ctx->num_sms * 16), 256, ctx->d_ucell_key,
               ctx->d_ucell_start, ctx->d_st, g, ctx->d_runs); }
     float rf = (float)ctx->prm.neighborRadius;
@@ -473,10 +490,10 @@ gm_status gm_normals(gm_ctx* ctx) {
     { SegTimer seg_(ctx, SEG_NORMALS);
       GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, n_ptr, r2,
                 ctx->d_normals, ctx->d_nbr); }
-    if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_COMPACT);
       GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
-                ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, ctx->d_st); }
+                ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, epoch, ctx->d_st); }
     GM_CHECK_LAUNCHES(ctx);
   }
   ctx->have_normals = true;
@@ -495,8 +512,7 @@ gm_status gm_voxel(gm_ctx* ctx) {
     const float inv = 1.0f / leaf_f;
     int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
     { SegTimer seg_(ctx, SEG_VOX_KEYS);
-      GM_LAUNCH(ctx, k_voxel_setup, 1, 32, ctx->d_st, inv);
-      GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt); }
+      GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, inv, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt, ctx->d_rs_hist); }
     // static upper bound of the key range from the crop box (no host round trip for the bbox)
     int key_bits = 32;
     if (!ctx->injected) {
@@ -510,11 +526,12 @@ gm_status gm_voxel(gm_ctx* ctx) {
     { SegTimer seg_(ctx, SEG_VOX_SORT);
       s = radix_sort(ctx, &ctx->d_st->n_valid, n, key_bits, &buf); }
     if (s != GM_OK) return s;
-    if ((s = reset_state64(ctx, n)) != GM_OK) return s;
+    unsigned epoch = 0;
+    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_VOX_REDUCE);
     GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_assign,
-              ctx->d_vox_start, ctx->d_vox_key, ctx->d_state64, ctx->d_st);
-    GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_vals[buf], ctx->d_cloud_c,
+              ctx->d_vox_start, ctx->d_vox_key, ctx->d_state64, epoch, ctx->d_st);
+    GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n * 32, VC_BLOCK), ctx->num_sms * 16), VC_BLOCK, ctx->d_vals[buf], ctx->d_cloud_c,
               ctx->d_vox_start, ctx->d_st, ctx->d_centroid, ctx->d_vox_count); }
     if (ctx->have_normals) {
       SegTimer seg_(ctx, SEG_VOX_NN);
@@ -558,15 +575,17 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
     int hb = div_up(H, 128);
     { SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_HYP : SEG_CYL_HYP);
     if (kind == 0) {
-      GM_LAUNCH(ctx, k_plane_hypotheses, hb, 128, ctx->d_cloud_c, n_ptr, ctx->d_samples[0], H, ctx->d_plane_coef, ctx->d_hvalid[0]);
+      GM_LAUNCH(ctx, k_plane_hypotheses, hb, 128, ctx->d_cloud_c, n_ptr, ctx->d_samples[0], H, ctx->d_plane_coef, ctx->d_hvalid[0],
+                ctx->d_counts[0], h_begin, h_end);
     } else {
       GM_LAUNCH(ctx, k_cyl_hypotheses, hb, 128, ctx->d_cloud_c, ctx->d_normals_c, n_ptr, ctx->d_samples[1], H,
                 (float)ctx->prm.cylinderRadiusMin, (float)ctx->prm.cylinderRadiusMax, (float)ctx->prm.ransacThreshold,
-                ctx->d_model7, ctx->d_test12, ctx->d_hvalid[1]);
-    }
-    GM_LAUNCH(ctx, k_counts_init, hb, 128, ctx->d_counts[kind], ctx->d_hvalid[kind], H, h_begin, h_end); }
+                ctx->d_model7, ctx->d_test12, ctx->d_hvalid[1], ctx->d_counts[1], h_begin, h_end);
+    } }
     const int hloc = h_end - h_begin;
+    bool argmax_done = false;
     if (hloc > 0 && ctx->n_input > 0) {
+      argmax_done = true;  // folded into the count kernel's last block
       SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_COUNT : SEG_CYL_COUNT);
       const int K = kind == 0 ? RC_KP : RC_KC;
       int groups = div_up(hloc, RC_BLOCK * K);
@@ -576,14 +595,19 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
       dim3 grid(slices, groups);
       if (kind == 0) {
         GM_LAUNCH(ctx, k_count_plane<RC_KP>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, ctx->d_hvalid[0], h_begin, h_end,
-                  (float)ctx->prm.ransacThreshold, ctx->d_counts[0]);
+                  (float)ctx->prm.ransacThreshold, ctx->d_counts[0], H, ctx->d_key + 0, ctx->d_counters + 3);
       } else {
-        GM_LAUNCH(ctx, k_count_cyl<RC_KC>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_test12, h_begin, h_end, ctx->d_counts[1]);
+        GM_LAUNCH(ctx, k_count_cyl<RC_KC>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_test12, h_begin, h_end, ctx->d_counts[1], H,
+                  ctx->d_key + 1, ctx->d_counters + 4);
       }
     }
+    if (!argmax_done) {
+      SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_ARGMAX : SEG_CYL_ARGMAX);
+      GM_LAUNCH(ctx, k_argmax, 1, AM_BLOCK, ctx->d_counts[kind], H, ctx->d_key + kind);
+    }
+  } else {
+    GM_CUDA(cudaMemsetAsync(ctx->d_key + kind, 0, sizeof(unsigned long long), ctx->stream));
   }
-  { SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_ARGMAX : SEG_CYL_ARGMAX);
-    GM_LAUNCH(ctx, k_argmax, 1, AM_BLOCK, ctx->d_counts[kind], H, ctx->d_key + kind); }
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_ransac[kind] = true;
   ctx->ransac_H[kind] = H;
@@ -603,24 +627,27 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
   const int* n_ptr = &ctx->d_st->n_valid;
   ModelState* ms = ctx->d_model + kind;
   SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_REFIT : SEG_CYL_REFIT);
-  GM_LAUNCH(ctx, k_select, 1, 32, ctx->d_key + kind, kind, ctx->ransac_H[kind], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ms);
+  const int H = ctx->ransac_H[kind];
   const float tau = (float)ctx->prm.ransacThreshold;
   if (kind == 0) {
-    GM_LAUNCH(ctx, k_plane_refit, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ms, tau, ctx->d_partials, ctx->d_counters + 1);
-  } else if (ctx->n_input) {
-    gm_status s = reset_state64(ctx, ctx->n_input);
+    GM_LAUNCH(ctx, k_plane_refit, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_key + 0, H, ctx->d_plane_coef, ms, tau,
+              ctx->d_partials, ctx->d_counters + 1);
+  } else {
+    unsigned epoch = 0;
+    gm_status s = next_epoch(ctx, &epoch);
     if (s != GM_OK) return s;
-    GM_LAUNCH(ctx, k_cyl_inlier_compact, div_up((long long)ctx->n_input, CPL_TILE), CP_BLOCK, ctx->d_cloud_c, n_ptr, ms, ctx->d_inl,
-              ctx->d_state64, &ctx->d_st->error);
+    GM_LAUNCH(ctx, k_cyl_inlier_compact, std::max(1, div_up((long long)ctx->n_input, CPL_TILE)), CP_BLOCK, ctx->d_cloud_c, n_ptr,
+              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64, epoch, &ctx->d_st->error);
     // all Gauss-Newton passes in one cooperative launch (grid barrier between passes)
-    GM_CUDA(cudaMemsetAsync(ctx->d_counters + 2, 0, sizeof(unsigned), ctx->stream));
     {
       const float4* inl = ctx->d_inl;
       int iters = ctx->prm.refitIterations;
       double* partials = ctx->d_partials;
       unsigned* bar = ctx->d_counters + 2;
+      unsigned bar_base = ctx->gn_barrier_base;  // the counter is never reset: arrivals accumulate across launches
+      ctx->gn_barrier_base += (unsigned)(iters + 1) * (unsigned)ctx->gn_blocks;
       int* err = &ctx->d_st->error;
-      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bar, (void*)&err};
+      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bar, (void*)&bar_base, (void*)&err};
       GM_CUDA(cudaLaunchCooperativeKernel((const void*)k_cyl_gn_all, dim3(ctx->gn_blocks), dim3(RF_BLOCK), args, 0, ctx->stream));
       ++ctx->launches;
     }
@@ -651,8 +678,7 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   const int* n_ptr = &ctx->d_st->n_valid;
   double shift = .001 / ctx->prm.weightingFactor;
   SegTimer seg_(ctx, SEG_POLYLINE);
-  GM_CUDA(cudaMemsetAsync(ctx->d_poly_acc, 0, (size_t)POLY_NACC * S * sizeof(long long), ctx->stream));
-  GM_LAUNCH(ctx, k_poly_begin, 1, 32, ctx->d_poly, ctx->d_frame);
+  GM_LAUNCH(ctx, k_poly_begin, 1, 256, ctx->d_poly, ctx->d_frame, ctx->d_poly_acc, POLY_NACC * S);
   if (ctx->n_input) {
     int blocks = std::min(div_up((long long)ctx->n_input, POLY_BLOCK), ctx->num_sms * 4);
     GM_LAUNCH(ctx, k_poly_range, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_labels, n_ptr, ctx->d_poly);

@@ -73,19 +73,67 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV * 
   __syncthreads();
 }
 
-// ---- decoupled look-back tile state ---------------------------------------------------------
-// One 64-bit word per tile: (status << 32) | value, written/read with single 8-byte accesses so
-// status and value are always observed together.
-enum : unsigned { TS_EMPTY = 0u, TS_AGG = 1u, TS_PREFIX = 2u };
-
-__device__ __forceinline__ void ts_store(unsigned long long* p, unsigned status, unsigned value) {
-  unsigned long long w = ((unsigned long long)status << 32) | value;
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+// ---- single-launch grid reductions -----------------------------------------------------------
+// Returns true (block-uniformly) in the last block of the grid to get here, after every block's
+// earlier global writes are visible.  The counter is reset for the next launch.  Combined with a
+// fixed-order sum over per-block partials this gives a single-launch, bitwise reproducible grid
+// reduction (the result does not depend on which block happens to be last).
+__device__ __forceinline__ bool d_last_block(unsigned* counter, unsigned nblocks) {
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == nblocks - 1);
+    if (s_last) { *counter = 0u; __threadfence(); }
+  }
+  __syncthreads();
+  return s_last;
 }
-__device__ __forceinline__ unsigned long long ts_load(const unsigned long long* p) {
+
+// fin[k] = sum over blocks b of partials[b*NV + k], k < NV, for the whole calling block.
+// Warp w owns columns w, w+W, ...; lane l adds blocks l, l+32, ... in order, then a fixed shuffle
+// tree: the loads of a column are independent (one L2 latency, not nblocks of them) and the
+// summation order depends only on (nblocks, blockDim), never on scheduling.
+template <int NV>
+__device__ __forceinline__ void d_reduce_partials(const double* partials, int nblocks, double* fin) {
+  const int W = blockDim.x >> 5, w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int k = w; k < NV; k += W) {
+    double s = 0.0;
+    for (int b = l; b < nblocks; b += 32) s += __ldcg(partials + (size_t)b * NV + k);
+    s = warp_sum(s);
+    if (l == 0) fin[k] = s;
+  }
+  __syncthreads();
+}
+
+// ---- decoupled look-back tile state ---------------------------------------------------------
+// One 64-bit word per tile: epoch (30 bits) | status (2 bits) | value (32 bits), read and written
+// with single 8-byte accesses so all three are always observed together.
+//  * The EPOCH is a per-launch number chosen by the host: a word whose epoch differs from the
+//    launch's is "empty", so the state arrays never have to be cleared (a cudaMemsetAsync node costs
+//    ~5 us, and a scan would need 13 of them).
+//  * Words are PUBLISHED with atomicExch, not a plain store: measured on B200
+//    (tools/microbench/compact_variants.cu) a relaxed store takes ~1 us to become visible to the
+//    spinning readers of other SMs, an atomic goes straight to L2; this alone halves the kernel.
+//  * Readers use ld.relaxed.gpu (served by L2).  ld.cg must NOT be used to spin: it never observed
+//    the update in the same test.
+enum : unsigned { TS_EMPTY = 0u, TS_AGG = 1u, TS_PREFIX = 2u };
+constexpr unsigned TS_EPOCH_MASK = 0x3FFFFFFFu;
+
+__device__ __forceinline__ unsigned long long ts_pack(unsigned epoch, unsigned status, unsigned value) {
+  return ((unsigned long long)((epoch << 2) | status) << 32) | value;
+}
+__device__ __forceinline__ void ts_store(unsigned long long* p, unsigned epoch, unsigned status, unsigned value) {
+  atomicExch(p, ts_pack(epoch, status, value));
+}
+// -> status (TS_EMPTY if the word belongs to another epoch) and value
+__device__ __forceinline__ unsigned ts_load(const unsigned long long* p, unsigned epoch, unsigned& value) {
   unsigned long long w;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-  return w;
+  value = (unsigned)w;
+  unsigned hi = (unsigned)(w >> 32);
+  return ((hi >> 2) == (epoch & TS_EPOCH_MASK)) ? (hi & 3u) : TS_EMPTY;
 }
 
 // Warp-cooperative look-back: returns the exclusive prefix of tile `tile` (sum of aggregates of
@@ -94,30 +142,26 @@ __device__ __forceinline__ unsigned long long ts_load(const unsigned long long* 
 // (L2 latency is paid once per round, not once per tile), then the four 32-tile groups are
 // folded in order, nearest first.  In a single-wave launch nobody but tile 0 holds a full prefix
 // early on, so the walk length, not bandwidth, is what bounds these kernels.
-__device__ __forceinline__ unsigned lookback_exclusive(const unsigned long long* state, int tile, int* err) {
+__device__ __forceinline__ unsigned lookback_exclusive(const unsigned long long* state, unsigned epoch, int tile, int* err) {
   unsigned exclusive = 0;
   int base = tile - 1;
-  const unsigned long long zero_prefix = (unsigned long long)TS_PREFIX << 32;
   while (base >= 0) {
-    unsigned long long w[4];
+    unsigned st4[4], val4[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       int t = base - q * 32 - lane_id();
-      w[q] = (t >= 0) ? ts_load(state + t) : zero_prefix;  // tiles before 0 act as a zero prefix
+      val4[q] = 0u;
+      st4[q] = (t >= 0) ? ts_load(state + t, epoch, val4[q]) : (unsigned)TS_PREFIX;  // tiles before 0 act as a zero prefix
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       int t = base - q * 32 - lane_id();
-      unsigned status = (unsigned)(w[q] >> 32);
+      unsigned status = st4[q], value = val4[q];
       if (t >= 0 && status == TS_EMPTY) {
         int spins = 0;
-        do {
-          w[q] = ts_load(state + t);
-          status = (unsigned)(w[q] >> 32);
-        } while (status == TS_EMPTY && ++spins < SPIN_BOUND);
-        if (status == TS_EMPTY) { atomicExch(err, 1); status = TS_PREFIX; w[q] = zero_prefix; }
+        do { status = ts_load(state + t, epoch, value); } while (status == TS_EMPTY && ++spins < SPIN_BOUND);
+        if (status == TS_EMPTY) { atomicExch(err, 1); status = TS_PREFIX; value = 0u; }
       }
-      unsigned value = (unsigned)w[q];
       unsigned pref_mask = __ballot_sync(FULL, status == TS_PREFIX);
       int first = __ffs(pref_mask) - 1;  // nearest predecessor in this group that holds a full prefix
       unsigned contrib = (first < 0 || lane_id() <= first) ? value : 0u;
@@ -135,7 +179,7 @@ __device__ __forceinline__ unsigned lookback_exclusive(const unsigned long long*
 // Tile = BLOCK threads x IPT items, striped (item j of thread t is tile_base + j*BLOCK + t) so
 // that global loads are coalesced.  flags[j] in, ranks[j] out (exclusive rank among the flagged
 // items of the whole input, i.e. the output position), plus the running total.
-// `state` must be zeroed (TS_EMPTY) before the launch; tiles are blockIdx.x.
+// `epoch` must differ from the epoch of the previous launch that used `state`; tiles are blockIdx.x.
 template <int BLOCK, int IPT>
 struct CompactSmem {
   unsigned warp_cnt[IPT * (BLOCK / 32)];
@@ -145,7 +189,7 @@ struct CompactSmem {
 
 template <int BLOCK, int IPT>
 __device__ __forceinline__ void tile_compact_ranks(const bool (&flags)[IPT], unsigned (&ranks)[IPT],
-                                                   unsigned& total_inclusive, unsigned long long* state,
+                                                   unsigned& total_inclusive, unsigned long long* state, unsigned epoch,
                                                    int tile, int* err, CompactSmem<BLOCK, IPT>& sm) {
   constexpr int W = BLOCK / 32;
   const int w = threadIdx.x >> 5;
@@ -172,10 +216,10 @@ __device__ __forceinline__ void tile_compact_ranks(const bool (&flags)[IPT], uns
       carry += __shfl_sync(FULL, inc, 31);
     }
     unsigned tile_total = carry;
-    if (lane_id() == 0) ts_store(state + tile, tile == 0 ? TS_PREFIX : TS_AGG, tile_total);
-    unsigned excl = lookback_exclusive(state, tile, err);
+    if (lane_id() == 0) ts_store(state + tile, epoch, tile == 0 ? TS_PREFIX : TS_AGG, tile_total);
+    unsigned excl = lookback_exclusive(state, epoch, tile, err);
     if (lane_id() == 0) {
-      if (tile != 0) ts_store(state + tile, TS_PREFIX, excl + tile_total);
+      if (tile != 0) ts_store(state + tile, epoch, TS_PREFIX, excl + tile_total);
       sm.tile_excl = excl;
       sm.tile_total = tile_total;
     }
@@ -189,23 +233,17 @@ __device__ __forceinline__ void tile_compact_ranks(const bool (&flags)[IPT], uns
 
 // ---- onesweep radix sort ------------------------------------------------------------------
 constexpr int RS_BLOCK = 256;
-constexpr int RS_IPT = 8;
+constexpr int RS_IPT = 16;  // 4096 keys per tile: half as many tiles -> half as long look-back walks in a single-wave launch
 constexpr int RS_TILE = RS_BLOCK * RS_IPT;
 constexpr int RS_WARPS = RS_BLOCK / 32;
 constexpr int RS_MAX_PASSES = 4;
 
-// 32-bit tile state for the sort: 2 status bits | 30 value bits (n < 2^30)
-__device__ __forceinline__ void rs_store(unsigned* p, unsigned status, unsigned value) {
-  unsigned w = (status << 30) | value;
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(w) : "memory");
-}
-__device__ __forceinline__ unsigned rs_load(const unsigned* p) {
-  unsigned w;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
-  return w;
+// One read of the keys -> digit histograms of all passes.  hist[pass*256 + d] must be zero on entry:
+// the kernel that PRODUCES the keys clears it (d_zero_hist), so no memset node is needed.
+__device__ __forceinline__ void d_zero_hist(unsigned* hist) {
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += blockDim.x) hist[i] = 0u;
 }
 
-// One read of the keys -> digit histograms of all passes.  hist[pass*256 + d] must be zeroed.
 __global__ void __launch_bounds__(RS_BLOCK) k_radix_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr,
                                                          int passes, unsigned* __restrict__ hist) {
   __shared__ unsigned sh[RS_MAX_PASSES * 256];
@@ -223,12 +261,13 @@ __global__ void __launch_bounds__(RS_BLOCK) k_radix_hist(const unsigned* __restr
   }
 }
 
-// One LSD pass.  ticket/state zeroed before the sort (state: [tiles][256] u32 per pass).
+// One LSD pass.  state: [tiles][256] epoch-tagged words per pass (never cleared); the ticket counter
+// is reset by whichever block draws the last ticket.
 __global__ void __launch_bounds__(RS_BLOCK)
 k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
                  unsigned* __restrict__ keys_out, unsigned* __restrict__ vals_out,
                  const int* __restrict__ n_ptr, int pass, const unsigned* __restrict__ hist,
-                 unsigned* __restrict__ state, unsigned* __restrict__ ticket, int* __restrict__ err) {
+                 unsigned long long* __restrict__ state, unsigned epoch, unsigned* __restrict__ ticket, int* __restrict__ err) {
   __shared__ unsigned s_warp_hist[RS_WARPS][257];
   __shared__ unsigned s_keys[RS_TILE];
   __shared__ unsigned s_vals[RS_TILE];
@@ -239,7 +278,11 @@ k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restric
 
   const int n = *n_ptr;
   const int ntiles = (n + RS_TILE - 1) / RS_TILE;
-  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) *ticket = 0u;  // everybody has drawn: ready for the next launch
+    s_tile = (int)t;
+  }
   for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_BLOCK) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
   const int tile = s_tile;
@@ -282,8 +325,8 @@ k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restric
       run += c;
     }
     const unsigned tile_cnt = run;
-    unsigned* st = state + (size_t)tile * 256 + d;
-    rs_store(st, tile == 0 ? TS_PREFIX : TS_AGG, tile_cnt);
+    unsigned long long* st = state + (size_t)tile * 256 + d;
+    ts_store(st, epoch, tile == 0 ? TS_PREFIX : TS_AGG, tile_cnt);
 
     // global exclusive digit offset = sum(hist[pass][0..d))  (block scan over 256 digits)
     unsigned hv = hist[pass * 256 + d];
@@ -312,28 +355,31 @@ k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restric
     for (int ww = 0; ww < w; ++ww) lbase += s_scan[ww];
     s_local_base[d] = lbase + linc - tile_cnt;
 
-    // look back over earlier tiles for this digit: 8 independent loads per step (one L2 round trip
-    // per 8 tiles), folded nearest first until a tile with a full prefix is met
+    // look back over earlier tiles for this digit: 16 independent loads per step (one L2 round
+    // trip per 16 tiles), folded nearest first until a tile with a full prefix is met
     unsigned excl = 0;
     bool done = false;
-    for (int t0 = tile - 1; t0 >= 0 && !done; t0 -= 8) {
-      unsigned wv[8];
+    for (int t0 = tile - 1; t0 >= 0 && !done; t0 -= 16) {
+      unsigned wst[16], wval[16];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) wv[q] = (t0 - q >= 0) ? rs_load(state + (size_t)(t0 - q) * 256 + d) : ((unsigned)TS_PREFIX << 30);
+      for (int q = 0; q < 16; ++q) {
+        wval[q] = 0u;
+        wst[q] = (t0 - q >= 0) ? ts_load(state + (size_t)(t0 - q) * 256 + d, epoch, wval[q]) : (unsigned)TS_PREFIX;
+      }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 16; ++q) {
         if (done) break;
-        if ((wv[q] >> 30) == TS_EMPTY) {
-          const unsigned* ps = state + (size_t)(t0 - q) * 256 + d;
+        if (wst[q] == TS_EMPTY) {
+          const unsigned long long* ps = state + (size_t)(t0 - q) * 256 + d;
           int spins = 0;
-          do { wv[q] = rs_load(ps); } while ((wv[q] >> 30) == TS_EMPTY && ++spins < SPIN_BOUND);
-          if ((wv[q] >> 30) == TS_EMPTY) { atomicExch(err, 2); done = true; break; }
+          do { wst[q] = ts_load(ps, epoch, wval[q]); } while (wst[q] == TS_EMPTY && ++spins < SPIN_BOUND);
+          if (wst[q] == TS_EMPTY) { atomicExch(err, 2); done = true; break; }
         }
-        excl += wv[q] & 0x3FFFFFFFu;
-        if ((wv[q] >> 30) == TS_PREFIX) done = true;
+        excl += wval[q];
+        if (wst[q] == TS_PREFIX) done = true;
       }
     }
-    if (tile != 0) rs_store(st, TS_PREFIX, excl + tile_cnt);
+    if (tile != 0) ts_store(st, epoch, TS_PREFIX, excl + tile_cnt);
     s_global_base[d] = digit_global + excl;
   }
   __syncthreads();

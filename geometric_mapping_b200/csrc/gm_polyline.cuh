@@ -36,7 +36,8 @@ __device__ __forceinline__ double d_ordered_to_double(unsigned long long o) {
 __device__ __forceinline__ long long d_to_fx(double v) { return __double2ll_rn(v * POLY_FX); }
 __device__ __forceinline__ double d_from_fx(long long v) { return (double)v / POLY_FX; }
 
-__global__ void k_poly_begin(PolyState* ps, const FrameOut* __restrict__ frame) {
+__global__ void k_poly_begin(PolyState* ps, const FrameOut* __restrict__ frame, long long* acc, int n_acc) {
+  for (int i = threadIdx.x; i < n_acc; i += blockDim.x) acc[i] = 0;  // replaces a memset node
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double ax[3] = {(double)frame->vecs[0], (double)frame->vecs[3], (double)frame->vecs[6]};
   double u[3], w[3];

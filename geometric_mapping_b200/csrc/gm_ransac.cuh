@@ -13,7 +13,7 @@ namespace gm {
 // plane: samples H x 3 -> coef float4 {a,b,c,d}, valid
 __global__ void k_plane_hypotheses(const float4* __restrict__ pts, const int* __restrict__ n_ptr,
                                    const int* __restrict__ samples, int H, float4* __restrict__ coef,
-                                   int* __restrict__ valid) {
+                                   int* __restrict__ valid, int* __restrict__ counts, int h_begin, int h_end) {
   const int n = *n_ptr;
   for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
     int i0 = samples[h * 3], i1 = samples[h * 3 + 1], i2 = samples[h * 3 + 2];
@@ -36,6 +36,7 @@ __global__ void k_plane_hypotheses(const float4* __restrict__ pts, const int* __
     }
     coef[h] = c;
     valid[h] = ok;
+    counts[h] = (h >= h_begin && h < h_end && ok) ? 0 : -1;  // -1: degenerate or not this rank's id
   }
 }
 
@@ -80,7 +81,8 @@ __device__ __forceinline__ bool d_cyl_test_params(const float* m7, float tau, fl
 __global__ void k_cyl_hypotheses(const float4* __restrict__ pts, const float4* __restrict__ normals,
                                  const int* __restrict__ n_ptr, const int* __restrict__ samples, int H,
                                  float rmin, float rmax, float tau, float* __restrict__ model7,
-                                 float* __restrict__ test12, int* __restrict__ valid) {
+                                 float* __restrict__ test12, int* __restrict__ valid, int* __restrict__ counts,
+                                 int h_begin, int h_end) {
   const int n = *n_ptr;
   for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
     float m[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -130,6 +132,7 @@ __global__ void k_cyl_hypotheses(const float4* __restrict__ pts, const float4* _
     for (int k = 0; k < 7; ++k) model7[(size_t)h * 7 + k] = m[k];
     for (int k = 0; k < 12; ++k) test12[(size_t)h * 12 + k] = t[k];
     valid[h] = ok;
+    counts[h] = (h >= h_begin && h < h_end && ok) ? 0 : -1;
   }
 }
 
@@ -172,6 +175,33 @@ __device__ __forceinline__ void d_count_lt(float v, float thr, int& cnt) {
   asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(cnt) : "f"(v), "f"(thr));
 }
 
+// best key = max over h of ((count+1) << 32) | (0xFFFFFFFF - h): max count, ties -> lowest id
+// (RandomSampleConsensus keeps a model only on a strictly larger count, SURVEY A.9)
+__device__ __forceinline__ unsigned long long d_key_of(int count, int h) {
+  return ((unsigned long long)(unsigned)(count + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+}
+// block-wide argmax over counts[0..H) (read through L2: other blocks produced them with atomics)
+template <int BLOCK>
+__device__ __forceinline__ void d_block_argmax(const int* counts, int H, unsigned long long* key_out) {
+  __shared__ unsigned long long s_best[BLOCK / 32];
+  unsigned long long best = 0ull;
+  for (int h = threadIdx.x; h < H; h += BLOCK) {
+    unsigned long long k = d_key_of(__ldcg(counts + h), h);
+    best = (k > best) ? k : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(FULL, best, o);
+    best = (t > best) ? t : best;
+  }
+  if (lane_id() == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < BLOCK / 32; ++w) best = (s_best[w] > best) ? s_best[w] : best;
+    *key_out = best;
+  }
+}
+
 constexpr int RC_BLOCK = 64;
 constexpr int RC_TILE = 512;   // points staged per iteration (6 KB of shared memory)
 constexpr int RC_KP = 8;       // plane hypotheses per thread
@@ -189,12 +219,12 @@ __device__ __forceinline__ void d_stage_tile(const float4* __restrict__ pts, int
 template <int K>
 __global__ void __launch_bounds__(RC_BLOCK)
 k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float4* __restrict__ coef,
-              const int* __restrict__ valid, int h_begin, int h_end, float tau, int* __restrict__ counts) {
+              const int* __restrict__ valid, int h_begin, int h_end, float tau, int* __restrict__ counts,
+              int H, unsigned long long* key_out, unsigned* ticket) {
   __shared__ __align__(16) float sx[RC_TILE], sy[RC_TILE], sz[RC_TILE];
   const int n = *n_ptr;
   const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
   const int p_begin = blockIdx.x * per, p_end = min(n, p_begin + per);
-  if (p_begin >= p_end) return;
   const int hbase = h_begin + blockIdx.y * (RC_BLOCK * K) + threadIdx.x;
   float4 c[K];
   int cnt[K];
@@ -234,17 +264,18 @@ k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, con
     int h = hbase + k * RC_BLOCK;
     if (h < h_end && cnt[k]) atomicAdd(&counts[h], cnt[k]);
   }
+  // the last block to finish reduces the local best model (saves a launch)
+  if (d_last_block(ticket, gridDim.x * gridDim.y)) d_block_argmax<RC_BLOCK>(counts, H, key_out);
 }
 
 template <int K>
 __global__ void __launch_bounds__(RC_BLOCK)
 k_count_cyl(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float* __restrict__ test12,
-            int h_begin, int h_end, int* __restrict__ counts) {
+            int h_begin, int h_end, int* __restrict__ counts, int H, unsigned long long* key_out, unsigned* ticket) {
   __shared__ __align__(16) float sx[RC_TILE], sy[RC_TILE], sz[RC_TILE];
   const int n = *n_ptr;
   const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
   const int p_begin = blockIdx.x * per, p_end = min(n, p_begin + per);
-  if (p_begin >= p_end) return;
   const int hbase = h_begin + blockIdx.y * (RC_BLOCK * K) + threadIdx.x;
   float4 u[K], w[K];
   float negmid[K], half[K];
@@ -296,35 +327,13 @@ k_count_cyl(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const
     int h = hbase + k * RC_BLOCK;
     if (h < h_end && cnt[k]) atomicAdd(&counts[h], cnt[k]);
   }
+  // the last block to finish reduces the local best model (saves a launch)
+  if (d_last_block(ticket, gridDim.x * gridDim.y)) d_block_argmax<RC_BLOCK>(counts, H, key_out);
 }
 
-// counts[h] = -1 for degenerate hypotheses / ids outside this rank's range, 0 otherwise
-__global__ void k_counts_init(int* __restrict__ counts, const int* __restrict__ valid, int H, int h_begin, int h_end) {
-  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x)
-    counts[h] = (h >= h_begin && h < h_end && valid[h]) ? 0 : -1;
-}
-
-// best key = max over h of ((count+1) << 32) | (0xFFFFFFFF - h): max count, ties -> lowest id
-// (RandomSampleConsensus keeps a model only on a strictly larger count, SURVEY A.9)
 constexpr int AM_BLOCK = 256;
 __global__ void __launch_bounds__(AM_BLOCK) k_argmax(const int* __restrict__ counts, int H, unsigned long long* key_out) {
-  __shared__ unsigned long long s[AM_BLOCK / 32];
-  unsigned long long best = 0ull;
-  for (int h = threadIdx.x; h < H; h += AM_BLOCK) {
-    unsigned long long k = ((unsigned long long)(unsigned)(counts[h] + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
-    best = (k > best) ? k : best;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long t = __shfl_xor_sync(FULL, best, o);
-    best = (t > best) ? t : best;
-  }
-  if (lane_id() == 0) s[threadIdx.x >> 5] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < AM_BLOCK / 32; ++w) best = (s[w] > best) ? s[w] : best;
-    *key_out = best;
-  }
+  d_block_argmax<AM_BLOCK>(counts, H, key_out);
 }
 
 // ---- selection + refit ----------------------------------------------------------------------
@@ -340,10 +349,11 @@ struct ModelState {
   int n_inl, pad2_;        // size of the compacted inlier array (cylinder)
 };
 
-__global__ void k_select(const unsigned long long* __restrict__ key, int kind, int H,
+// decode the (possibly all-reduced) key and initialise the model state from the hypothesis table;
+// called by ONE thread (the refit kernels fold this in instead of a 1-thread launch)
+__device__ void d_select(const unsigned long long* __restrict__ key, int kind, int H,
                          const float4* __restrict__ plane_coef, const float* __restrict__ model7,
                          const float* __restrict__ test12, ModelState* ms) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   unsigned long long k = *key;
   int count = (int)(unsigned)(k >> 32) - 1;
   int id = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
@@ -371,43 +381,22 @@ __global__ void k_select(const unsigned long long* __restrict__ key, int kind, i
 
 constexpr int RF_BLOCK = 256;
 
-// Returns true (block-uniformly) in the last block of the grid to get here, after every block's
-// earlier global writes are visible.  The counter is reset for the next launch.  Combined with a
-// fixed-order sum over per-block partials this gives a single-launch, bitwise reproducible
-// grid reduction (the result does not depend on which block happens to be last).
-__device__ __forceinline__ bool d_last_block(unsigned* counter) {
-  __shared__ bool s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned t = atomicAdd(counter, 1u);
-    s_last = (t == gridDim.x - 1);
-    if (s_last) { *counter = 0u; __threadfence(); }
-  }
-  __syncthreads();
-  return s_last;
-}
-
-// column k of the per-block partials summed over blocks in block order (thread k < NV)
-template <int NV>
-__device__ __forceinline__ double d_sum_partials(const double* partials, int nblocks, int k) {
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += __ldcg(partials + (size_t)b * NV + k);
-  return s;
-}
-
 // plane refit: double sums {xx,xy,xz,yy,yz,zz,x,y,z,count} over the hypothesis inliers, then
 // (last block) covariance -> Jacobi -> coefficients
 __global__ void __launch_bounds__(RF_BLOCK)
-k_plane_refit(const float4* __restrict__ pts, const int* __restrict__ n_ptr, ModelState* ms, float tau,
-              double* __restrict__ partials, unsigned* counter) {
+k_plane_refit(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const unsigned long long* __restrict__ key, int H,
+              const float4* __restrict__ plane_coef, ModelState* ms, float tau, double* __restrict__ partials, unsigned* counter) {
   __shared__ double sm[10 * (RF_BLOCK / 32)];
   __shared__ double fin[10];
   const int n = *n_ptr;
   double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const bool have = ms->best_id >= 0;
+  // every block decodes the winner itself (k_select folded in)
+  const unsigned long long kk = *key;
+  const int best_count = (int)(unsigned)(kk >> 32) - 1;
+  const int best_id = (int)(0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull));
+  const bool have = best_count >= 0 && best_id >= 0 && best_id < H;
   if (have) {
-    const float4 c = make_float4(ms->hyp[0], ms->hyp[1], ms->hyp[2], ms->hyp[3]);
+    const float4 c = plane_coef[best_id];
     for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += gridDim.x * RF_BLOCK) {
       float4 p = pts[i];
       if (d_plane_inlier(c, p, tau)) {
@@ -420,10 +409,11 @@ k_plane_refit(const float4* __restrict__ pts, const int* __restrict__ n_ptr, Mod
   block_sum<10, RF_BLOCK>(s, sm);
   if (threadIdx.x == 0)
     for (int k = 0; k < 10; ++k) partials[blockIdx.x * 10 + k] = s[k];
-  if (!d_last_block(counter)) return;
-  if (threadIdx.x < 10) fin[threadIdx.x] = d_sum_partials<10>(partials, gridDim.x, threadIdx.x);
-  __syncthreads();
-  if (threadIdx.x != 0 || !have) return;
+  if (!d_last_block(counter, gridDim.x)) return;
+  d_reduce_partials<10>(partials, gridDim.x, fin);
+  if (threadIdx.x != 0) return;
+  d_select(key, 0, H, plane_coef, nullptr, nullptr, ms);
+  if (!have) return;
   long long cnt = (long long)(fin[9] + 0.5);
   ms->refit_count = (int)cnt;
   if (cnt <= 3) return;
@@ -455,15 +445,24 @@ __device__ __forceinline__ void d_perp_basis_d(const double dir[3], double u[3],
 
 // The refit set is FIXED (inliers of the winning hypothesis), so it is compacted once (stable
 // look-back compaction) and the Gauss-Newton passes run over the dense array.
-__global__ void __launch_bounds__(CP_BLOCK)
-k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_ptr, ModelState* ms,
-                     float4* __restrict__ inl, unsigned long long* state, int* err) {
+__global__ void __launch_bounds__(CP_BLOCK, 4)
+k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const unsigned long long* __restrict__ key, int H,
+                     const float* __restrict__ model7, const float* __restrict__ test12, ModelState* ms,
+                     float4* __restrict__ inl, unsigned long long* state, unsigned epoch, int* err) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = *n_ptr;
   const int tile = blockIdx.x, base = tile * CPL_TILE;
-  if (base >= n) return;
-  const bool have = ms->best_id >= 0;
-  const CylTest t = d_load_cyl_test(ms->test_hyp);
+  if (base >= n) {
+    // empty cloud: tile 0 still has to publish the (empty) model state
+    if (tile == 0 && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = 0; }
+    return;
+  }
+  // every block decodes the winner itself (k_select folded in)
+  const unsigned long long kk = *key;
+  const int best_count = (int)(unsigned)(kk >> 32) - 1;
+  const int best_id = (int)(0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull));
+  const bool have = best_count >= 0 && best_id >= 0 && best_id < H;
+  const CylTest t = d_load_cyl_test(test12 + (size_t)(have ? best_id : 0) * 12);
   bool f[CPL_IPT];
   float4 p[CPL_IPT];
 #pragma unroll
@@ -473,11 +472,11 @@ k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_p
     if (i < n) { p[j] = pts[i]; f[j] = have && d_cyl_inlier(t, p[j]); }
   }
   unsigned ranks[CPL_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, err, sm);
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, err, sm);
 #pragma unroll
   for (int j = 0; j < CPL_IPT; ++j)
     if (f[j]) inl[ranks[j]] = p[j];
-  if (base + CPL_TILE >= n && threadIdx.x == 0) ms->n_inl = (int)total;
+  if (base + CPL_TILE >= n && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = (int)total; }
 }
 
 __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
@@ -517,7 +516,7 @@ __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target,
     __threadfence();
     atomicAdd(count, 1u);
     int spins = 0;
-    while (*((volatile unsigned*)count) < target && ++spins < SPIN_BOUND) {}
+    while ((int)(*((volatile unsigned*)count) - target) < 0 && ++spins < SPIN_BOUND) {}  // wrap-safe
     if (spins >= SPIN_BOUND) atomicExch(err, 3);
     __threadfence();
   }
@@ -526,7 +525,7 @@ __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target,
 
 __global__ void __launch_bounds__(RF_BLOCK)
 k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float tau, double* __restrict__ partials /* 2 x grid x 22 */,
-             unsigned* barrier_count, int* err) {
+             unsigned* barrier_count, unsigned barrier_base, int* err) {
   __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
   __shared__ double fin[GN_NV];
   __shared__ double it_q[3], it_dir[3], it_r;
@@ -574,9 +573,8 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
     double* buf = partials + (size_t)(it & 1) * nb * GN_NV;
     if (threadIdx.x == 0)
       for (int k = 0; k < GN_NV; ++k) buf[blockIdx.x * GN_NV + k] = s[k];
-    d_grid_barrier(barrier_count, (unsigned)(it + 1) * (unsigned)nb, err);
-    if (threadIdx.x < GN_NV) fin[threadIdx.x] = d_sum_partials<GN_NV>(buf, nb, threadIdx.x);
-    __syncthreads();
+    d_grid_barrier(barrier_count, barrier_base + (unsigned)(it + 1) * (unsigned)nb, err);
+    d_reduce_partials<GN_NV>(buf, nb, fin);
     const long long cnt = (long long)(fin[20] + 0.5);
     if (cnt <= 5) frozen = true;  // model unchanged (same rule as the oracle)
     if (threadIdx.x == 0 && have) {

@@ -54,9 +54,9 @@ __global__ void k_set_w_one(float4* p, int n) {
 
 // a1 chopCloud / pcl::CropBox (src/tunnel_processing.cpp:39-49): stable compaction of
 // the points with every coordinate in [lo,hi]; NaN handling per is_dense.
-__global__ void __launch_bounds__(CP_BLOCK)
+__global__ void __launch_bounds__(CP_BLOCK, 4)
 k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, float4* __restrict__ out,
-       unsigned long long* state, DevState* st) {
+       unsigned long long* state, unsigned epoch, DevState* st) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int tile = blockIdx.x, base = tile * CPL_TILE;
   if (base >= n) return;
@@ -74,7 +74,7 @@ k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, f
     }
   }
   unsigned ranks[CPL_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, &st->error, sm);
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, &st->error, sm);
 #pragma unroll
   for (int j = 0; j < CPL_IPT; ++j)
     if (f[j]) out[ranks[j]] = p[j];
@@ -84,8 +84,9 @@ k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, f
 // Neighbour-grid cell key of every cropped point (sentinel ncells for non-finite points, which
 // are never anyone's neighbour).
 __global__ void k_cell_keys(const float4* __restrict__ pts, const int* __restrict__ n_ptr, GridSpec g,
-                            unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
+                            unsigned* __restrict__ keys, unsigned* __restrict__ idx, unsigned* __restrict__ sort_hist) {
   const int n = *n_ptr;
+  d_zero_hist(sort_hist);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
     unsigned key = g.ncells;
@@ -105,7 +106,7 @@ __global__ void k_cell_keys(const float4* __restrict__ pts, const int* __restric
 __global__ void __launch_bounds__(CP_BLOCK)
 k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
              const int* __restrict__ n_ptr, unsigned ncells, float4* __restrict__ sorted_pts, int* __restrict__ cell_id,
-             unsigned* __restrict__ ucell_key, int* __restrict__ ucell_start, unsigned long long* state, DevState* st) {
+             unsigned* __restrict__ ucell_key, int* __restrict__ ucell_start, unsigned long long* state, unsigned epoch, DevState* st) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = *n_ptr;
   const int tile = blockIdx.x, base = tile * CPL_TILE;
@@ -134,7 +135,7 @@ k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ si
   }
   if (nfinite_local) st->n_sorted_finite = nfinite_local;
   unsigned ranks[CPL_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, &st->error, sm);
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, &st->error, sm);
 #pragma unroll
   for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
@@ -318,7 +319,7 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 __global__ void __launch_bounds__(CP_BLOCK)
 k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ normals, const int* __restrict__ n_ptr,
                 float4* __restrict__ pts_c, float4* __restrict__ normals_c, int* __restrict__ valid_map,
-                unsigned long long* state, DevState* st) {
+                unsigned long long* state, unsigned epoch, DevState* st) {
   __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
   __shared__ float s_red[6][CP_BLOCK / 32];
   const int n = *n_ptr;
@@ -343,7 +344,7 @@ k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ norma
     }
   }
   unsigned ranks[CP_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, tile, &st->error, sm);
+  tile_compact_ranks<CP_BLOCK, CP_IPT>(f, ranks, total, state, epoch, tile, &st->error, sm);
 #pragma unroll
   for (int j = 0; j < CP_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
@@ -394,33 +395,42 @@ __global__ void k_bbox(const float4* __restrict__ pts, const int* __restrict__ n
   }
 }
 
-// a4 pcl::VoxelGrid lattice: min_b, div_b, divb_mul and the overflow rule.
-__global__ void k_voxel_setup(DevState* st, float inv) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  st->v_inv = inv;
-  if (st->n_valid <= 0) { st->n_voxels = 0; return; }
-  float mn[3], mx[3];
-  for (int a = 0; a < 3; ++a) { mn[a] = ordered_to_float(st->bbox_min[a]); mx[a] = ordered_to_float(st->bbox_max[a]); }
-  long long dx = (long long)((mx[0] - mn[0]) * inv) + 1;
-  long long dy = (long long)((mx[1] - mn[1]) * inv) + 1;
-  long long dz = (long long)((mx[2] - mn[2]) * inv) + 1;
-  if (dx * dy * dz > 2147483647LL) st->voxel_overflow = 1;
-  for (int a = 0; a < 3; ++a) {
-    int lo = (int)floorf(mn[a] * inv), hi = (int)floorf(mx[a] * inv);
-    st->min_b[a] = lo;
-    st->div_b[a] = hi - lo + 1;
-  }
-  st->mul[0] = 1; st->mul[1] = st->div_b[0]; st->mul[2] = st->div_b[0] * st->div_b[1];
-}
-
+// a4 pcl::VoxelGrid lattice: min_b, div_b, divb_mul and the overflow rule, derived
+// from the bounding box by every block (cheap, avoids a 1-thread kernel); block 0 publishes it.
 // Voxel key per compacted point: ijk = int(floor(p*inv) - float(min_b)); key = ijk . divb_mul
-__global__ void k_voxel_keys(const float4* __restrict__ pts, const DevState* __restrict__ st,
-                             unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point) {
+__global__ void k_voxel_keys(const float4* __restrict__ pts, DevState* st, float inv,
+                             unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point,
+                             unsigned* __restrict__ sort_hist) {
+  __shared__ int s_minb[3], s_mul[3], s_overflow;
   const int n = st->n_valid;
-  const float inv = st->v_inv;
-  const float mb0 = (float)st->min_b[0], mb1 = (float)st->min_b[1], mb2 = (float)st->min_b[2];
-  const int m1 = st->mul[1], m2 = st->mul[2];
-  const bool overflow = st->voxel_overflow != 0;
+  d_zero_hist(sort_hist);
+  if (threadIdx.x == 0) {
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) { mn[a] = ordered_to_float(st->bbox_min[a]); mx[a] = ordered_to_float(st->bbox_max[a]); }
+    int div[3] = {0, 0, 0}, minb[3] = {0, 0, 0}, overflow = 0;
+    if (n > 0) {
+      long long dx = (long long)((mx[0] - mn[0]) * inv) + 1;
+      long long dy = (long long)((mx[1] - mn[1]) * inv) + 1;
+      long long dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+      if (dx * dy * dz > 2147483647LL) overflow = 1;
+      for (int a = 0; a < 3; ++a) {
+        int lo = (int)floorf(mn[a] * inv), hi = (int)floorf(mx[a] * inv);
+        minb[a] = lo; div[a] = hi - lo + 1;
+      }
+    }
+    for (int a = 0; a < 3; ++a) s_minb[a] = minb[a];
+    s_mul[0] = 1; s_mul[1] = div[0]; s_mul[2] = div[0] * div[1];
+    s_overflow = overflow;
+    if (blockIdx.x == 0) {
+      st->v_inv = inv;
+      st->voxel_overflow = overflow;
+      for (int a = 0; a < 3; ++a) { st->min_b[a] = minb[a]; st->div_b[a] = div[a]; st->mul[a] = s_mul[a]; }
+    }
+  }
+  __syncthreads();
+  const float mb0 = (float)s_minb[0], mb1 = (float)s_minb[1], mb2 = (float)s_minb[2];
+  const int m1 = s_mul[1], m2 = s_mul[2];
+  const bool overflow = s_overflow != 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
     int ijk0 = (int)(floorf(p.x * inv) - mb0);
@@ -437,7 +447,7 @@ __global__ void k_voxel_keys(const float4* __restrict__ pts, const DevState* __r
 // the voxel rank of every point.
 __global__ void __launch_bounds__(CP_BLOCK)
 k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, int* __restrict__ assign,
-              int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, DevState* st) {
+              int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, unsigned epoch, DevState* st) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = st->n_valid;
   const int tile = blockIdx.x, base = tile * CPL_TILE;
@@ -454,7 +464,7 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
     }
   }
   unsigned ranks[CPL_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, tile, &st->error, sm);
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, &st->error, sm);
 #pragma unroll
   for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
@@ -469,25 +479,36 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
 
 // Centroid per voxel: float sum over the members in ascending original index (stable sort order),
 // divided by float(count)  (bit-reproducible, matches the oracle's canonical order).
-__global__ void k_voxel_centroids(const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
-                                  const int* __restrict__ vox_start, const DevState* __restrict__ st,
-                                  float4* __restrict__ centroids, int* __restrict__ vox_count) {
+// One warp per voxel: the 32 lanes gather 32 member points at once (the gathers are the cost), then
+// the sum is formed in member order from lane-broadcast shuffles, so the float result is the same
+// sequential sum a single thread would produce.
+constexpr int VC_BLOCK = 128;
+__global__ void __launch_bounds__(VC_BLOCK)
+k_voxel_centroids(const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
+                  const int* __restrict__ vox_start, const DevState* __restrict__ st,
+                  float4* __restrict__ centroids, int* __restrict__ vox_count) {
   const int V = st->n_voxels, n = st->n_valid;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < V; j += gridDim.x * blockDim.x) {
-    int s = vox_start[j], e = (j + 1 < V) ? vox_start[j + 1] : n;
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * VC_BLOCK) >> 5;
+  for (int j = (blockIdx.x * VC_BLOCK + threadIdx.x) >> 5; j < V; j += warps_total) {
+    const int s = vox_start[j], e = (j + 1 < V) ? vox_start[j + 1] : n;
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    int t = s;
-    for (; t + 4 <= e; t += 4) {
-      float4 q0 = pts[sidx[t]], q1 = pts[sidx[t + 1]], q2 = pts[sidx[t + 2]], q3 = pts[sidx[t + 3]];
-      sx += q0.x; sy += q0.y; sz += q0.z;
-      sx += q1.x; sy += q1.y; sz += q1.z;
-      sx += q2.x; sy += q2.y; sz += q2.z;
-      sx += q3.x; sy += q3.y; sz += q3.z;
+    for (int base = s; base < e; base += 32) {
+      const int t = base + lane;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < e) q = pts[sidx[t]];
+      const int cnt = min(32, e - base);
+      for (int l = 0; l < cnt; ++l) {
+        sx += __shfl_sync(FULL, q.x, l);
+        sy += __shfl_sync(FULL, q.y, l);
+        sz += __shfl_sync(FULL, q.z, l);
+      }
     }
-    for (; t < e; ++t) { float4 q = pts[sidx[t]]; sx += q.x; sy += q.y; sz += q.z; }
-    float c = (float)(e - s);
-    centroids[j] = make_float4(sx / c, sy / c, sz / c, 1.0f);
-    vox_count[j] = e - s;
+    if (lane == 0) {
+      float c = (float)(e - s);
+      centroids[j] = make_float4(sx / c, sy / c, sz / c, 1.0f);
+      vox_count[j] = e - s;
+    }
   }
 }
 
@@ -638,7 +659,6 @@ k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, dou
         unsigned* counter, FrameOut* out) {
   __shared__ double sm[6 * (FR_BLOCK / 32)];
   __shared__ double fin[6];
-  __shared__ bool s_last;
   const int n = *n_ptr;
   double s[6] = {0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * FR_BLOCK + threadIdx.x; i < n; i += gridDim.x * FR_BLOCK) {
@@ -651,21 +671,10 @@ k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, dou
     s[3] += (double)b * (double)b; s[4] += (double)b * (double)c; s[5] += (double)c * (double)c;
   }
   block_sum<6, FR_BLOCK>(s, sm);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0)
     for (int k = 0; k < 6; ++k) partials[blockIdx.x * 6 + k] = s[k];
-    __threadfence();
-    unsigned t = atomicAdd(counter, 1u);
-    s_last = (t == gridDim.x - 1);
-    if (s_last) { *counter = 0u; __threadfence(); }
-  }
-  __syncthreads();
-  if (!s_last) return;
-  if (threadIdx.x < 6) {
-    double acc = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) acc += __ldcg(partials + (size_t)b * 6 + threadIdx.x);
-    fin[threadIdx.x] = acc;
-  }
-  __syncthreads();
+  if (!d_last_block(counter, gridDim.x)) return;
+  d_reduce_partials<6>(partials, gridDim.x, fin);
   if (threadIdx.x != 0) return;
   float Sf[9] = {(float)fin[0], (float)fin[1], (float)fin[2], (float)fin[1], (float)fin[3], (float)fin[4], (float)fin[2], (float)fin[4], (float)fin[5]};
   double Sd[9], vals[3], vecs[9];

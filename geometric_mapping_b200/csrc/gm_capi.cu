@@ -95,7 +95,7 @@ struct gm_ctx {
   unsigned long long* d_rs_state = nullptr;
   unsigned *d_rs_hist = nullptr, *d_rs_ticket = nullptr;
   unsigned epoch = 0;            // per-launch tag of the look-back tile states (never cleared)
-  unsigned gn_barrier_base = 0;  // cumulative arrivals at the cooperative GN barrier
+  unsigned gn_launches = 0;      // parity selects which of the two GN barrier counters a launch uses
   size_t rs_state_words = 0;
   DevState* d_st = nullptr;
   double* d_partials = nullptr;
@@ -112,6 +112,7 @@ struct gm_ctx {
   // polyline
   PolyState* d_poly = nullptr;
   long long* d_poly_acc = nullptr;
+  unsigned long long* d_poly_part = nullptr;  // per-block (min,max) of the polyline range pass
   gm_slice* d_slices = nullptr;
   SummaryDev* d_summary = nullptr;
   unsigned* d_counters = nullptr;  // last-block tickets: [0] frame, [1] plane refit, [2] cylinder GN
@@ -334,7 +335,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_plane_coef, H); A(d_model7, 7 * H); A(d_test12, 12 * H);
   A(d_hvalid[0], H); A(d_hvalid[1], H); A(d_counts[0], H); A(d_counts[1], H);
   A(d_key, 2); A(d_model, 2);
-  A(d_poly, 1); A(d_summary, 1); A(d_counters, 8); A(d_inl, N); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
+  A(d_poly, 1); A(d_summary, 1); A(d_counters, 16); A(d_poly_part, 2 * 4096); A(d_inl, N); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
 #undef A
   if ((e = cudaMallocHost((void**)&ctx->h_samples[0], 3 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples0");
   if ((e = cudaMallocHost((void**)&ctx->h_samples[1], 2 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples1");
@@ -346,7 +347,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   if ((e = cudaMemset(ctx->d_rs_hist, 0, RS_MAX_PASSES * 256 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_rs_ticket, 0, RS_MAX_PASSES * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
-  if ((e = cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_model, 0, 2 * sizeof(ModelState))) != cudaSuccess) return fail(e, "memset");
   {
     int per_sm = 0;
@@ -369,7 +370,7 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_rs_state, ctx->d_rs_hist, ctx->d_rs_ticket, ctx->d_st, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
-                  ctx->d_poly_acc, ctx->d_slices, ctx->d_summary, ctx->d_counters, ctx->d_inl};
+                  ctx->d_poly_acc, ctx->d_slices, ctx->d_summary, ctx->d_counters, ctx->d_inl, ctx->d_poly_part};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 2; ++k) {
     if (ctx->h_samples[k]) cudaFreeHost(ctx->h_samples[k]);
@@ -643,11 +644,11 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
       const float4* inl = ctx->d_inl;
       int iters = ctx->prm.refitIterations;
       double* partials = ctx->d_partials;
-      unsigned* bar = ctx->d_counters + 2;
-      unsigned bar_base = ctx->gn_barrier_base;  // the counter is never reset: arrivals accumulate across launches
-      ctx->gn_barrier_base += (unsigned)(iters + 1) * (unsigned)ctx->gn_blocks;
+      unsigned* bar = ctx->d_counters + 5 + (ctx->gn_launches & 1);       // counters [5],[6]: ping-pong
+      unsigned* bar_next = ctx->d_counters + 5 + ((ctx->gn_launches + 1) & 1);
+      ++ctx->gn_launches;
       int* err = &ctx->d_st->error;
-      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bar, (void*)&bar_base, (void*)&err};
+      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bar, (void*)&bar_next, (void*)&err};
       GM_CUDA(cudaLaunchCooperativeKernel((const void*)k_cyl_gn_all, dim3(ctx->gn_blocks), dim3(RF_BLOCK), args, 0, ctx->stream));
       ++ctx->launches;
     }
@@ -678,17 +679,18 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   const int* n_ptr = &ctx->d_st->n_valid;
   double shift = .001 / ctx->prm.weightingFactor;
   SegTimer seg_(ctx, SEG_POLYLINE);
-  GM_LAUNCH(ctx, k_poly_begin, 1, 256, ctx->d_poly, ctx->d_frame, ctx->d_poly_acc, POLY_NACC * S);
-  if (ctx->n_input) {
-    int blocks = std::min(div_up((long long)ctx->n_input, POLY_BLOCK), ctx->num_sms * 4);
-    GM_LAUNCH(ctx, k_poly_range, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_labels, n_ptr, ctx->d_poly);
-    GM_LAUNCH(ctx, k_poly_setup, 1, 32, ctx->d_poly, ctx->prm.sliceLength, S);
-    GM_LAUNCH(ctx, k_poly_pass<0>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift, ctx->d_poly_acc, ctx->d_slices);
-    GM_LAUNCH(ctx, k_poly_means, div_up(S, 64), 64, ctx->d_poly, ctx->d_poly_acc, ctx->d_slices);
-    GM_LAUNCH(ctx, k_poly_pass<1>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift, ctx->d_poly_acc, ctx->d_slices);
-    GM_LAUNCH(ctx, k_poly_fit, div_up(S, 64), 64, ctx->d_poly, ctx->d_poly_acc, ctx->d_slices);
-    GM_LAUNCH(ctx, k_poly_pass<2>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift, ctx->d_poly_acc, ctx->d_slices);
-    GM_LAUNCH(ctx, k_poly_finish, div_up(S, 64), 64, ctx->d_poly, ctx->d_poly_acc, ctx->d_slices);
+  {
+    // 4 launches: range (+basis, +zeroing, +slice layout) and three accumulation passes, each with the
+    // per-slice step that consumes it folded into its last block
+    int blocks = std::max(1, std::min(div_up((long long)std::max<size_t>(ctx->n_input, 1), POLY_BLOCK), ctx->num_sms * 4));
+    GM_LAUNCH(ctx, k_poly_range, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_labels, n_ptr, ctx->d_frame, ctx->d_poly, ctx->d_poly_acc,
+              POLY_NACC * S, ctx->d_poly_part, ctx->d_counters + 8, ctx->prm.sliceLength, S);
+    GM_LAUNCH(ctx, k_poly_pass<0>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift,
+              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 9);
+    GM_LAUNCH(ctx, k_poly_pass<1>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift,
+              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 10);
+    GM_LAUNCH(ctx, k_poly_pass<2>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift,
+              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 11);
   }
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_poly = true;

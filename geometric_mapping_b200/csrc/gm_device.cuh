@@ -50,11 +50,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Sum NV doubles per thread across a block of BLOCK threads; result valid in thread 0.
-// Fixed shuffle tree + fixed warp order -> bitwise reproducible.
+// Sum NV doubles per thread across a block of BLOCK threads and store the NV block totals to
+// out[0..NV) (global or shared).  Warp shuffle tree, then thread k adds the W warp totals of value k
+// in warp order: fixed order -> bitwise reproducible, and no single-thread serial tail.
 template <int NV, int BLOCK>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV * BLOCK/32 */) {
+__device__ __forceinline__ void block_sum_store(const double (&v)[NV], double* smem /* NV * BLOCK/32 */, double* out) {
   constexpr int W = BLOCK / 32;
+  static_assert(NV <= BLOCK, "one thread per value");
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -62,15 +64,13 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV * 
     if (l == 0) smem[k * W + w] = s;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < NV) {
+    double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      double s = 0.0;
-      for (int i = 0; i < W; ++i) s += smem[k * W + i];
-      v[k] = s;
-    }
+    for (int i = 0; i < W; ++i) s += smem[threadIdx.x * W + i];
+    out[threadIdx.x] = s;
+    __threadfence();  // the block totals are consumed by other blocks (last-block / grid-barrier reductions)
   }
-  __syncthreads();
 }
 
 // ---- single-launch grid reductions -----------------------------------------------------------

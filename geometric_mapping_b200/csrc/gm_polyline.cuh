@@ -36,22 +36,86 @@ __device__ __forceinline__ double d_ordered_to_double(unsigned long long o) {
 __device__ __forceinline__ long long d_to_fx(double v) { return __double2ll_rn(v * POLY_FX); }
 __device__ __forceinline__ double d_from_fx(long long v) { return (double)v / POLY_FX; }
 
-__global__ void k_poly_begin(PolyState* ps, const FrameOut* __restrict__ frame, long long* acc, int n_acc) {
-  for (int i = threadIdx.x; i < n_acc; i += blockDim.x) acc[i] = 0;  // replaces a memset node
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double ax[3] = {(double)frame->vecs[0], (double)frame->vecs[3], (double)frame->vecs[6]};
-  double u[3], w[3];
-  d_perp_basis_d(ax, u, w);
-  for (int k = 0; k < 3; ++k) { ps->axis[k] = ax[k]; ps->u[k] = u[k]; ps->w[k] = w[k]; }
-  ps->tmin_ord = 0xFFFFFFFFFFFFFFFFull;
-  ps->tmax_ord = 0ull;
-  ps->t0 = 0.0; ps->L = 1.0; ps->S = 0; ps->pad_ = 0;
+// Per-slice epilogues, run by the last block of the pass that produced their inputs.
+__device__ __forceinline__ void d_poly_means(const PolyState* ps, long long* acc) {
+  double* aux = reinterpret_cast<double*>(acc);
+  for (int s = threadIdx.x; s < ps->S; s += blockDim.x) {
+    long long* a = acc + (size_t)s * POLY_NACC;
+    double n = (double)__ldcg(a + 0);
+    double ma = 0.0, mb = 0.0;
+    if (n > 0) { ma = d_from_fx(__ldcg(a + 1)) / n; mb = d_from_fx(__ldcg(a + 2)) / n; }
+    aux[(size_t)s * POLY_NACC + 16] = ma;
+    aux[(size_t)s * POLY_NACC + 17] = mb;
+  }
 }
 
+__device__ __forceinline__ void d_poly_fit(const PolyState* ps, long long* acc) {
+  double* aux = reinterpret_cast<double*>(acc);
+  for (int s = threadIdx.x; s < ps->S; s += blockDim.x) {
+    const long long* a = acc + (size_t)s * POLY_NACC;
+    double n = (double)__ldcg(a + 0);
+    double ca = 0.0, cb = 0.0, rad = 0.0, ok = 0.0;
+    if (n >= 3) {
+      double Saa = d_from_fx(__ldcg(a + 9)), Sab = d_from_fx(__ldcg(a + 10)), Sbb = d_from_fx(__ldcg(a + 11));
+      double Saz = d_from_fx(__ldcg(a + 12)), Sbz = d_from_fx(__ldcg(a + 13)), Sz = d_from_fx(__ldcg(a + 14));
+      double det = Saa * Sbb - Sab * Sab;
+      if (fabs(det) > 1e-300) {
+        double Ac = (Saz * Sbb - Sbz * Sab) / det, Bc = (Sbz * Saa - Saz * Sab) / det;
+        ca = 0.5 * Ac; cb = 0.5 * Bc;
+        rad = sqrt(Sz / n + ca * ca + cb * cb);
+        ok = 1.0;
+      }
+    }
+    aux[(size_t)s * POLY_NACC + 18] = ca;
+    aux[(size_t)s * POLY_NACC + 19] = cb;
+    aux[(size_t)s * POLY_NACC + 20] = rad;
+    aux[(size_t)s * POLY_NACC + 21] = ok;
+  }
+}
+
+__device__ __forceinline__ void d_poly_finish(const PolyState* ps, const long long* acc, gm_slice* out) {
+  const double* aux = reinterpret_cast<const double*>(acc);
+  for (int s = threadIdx.x; s < ps->S; s += blockDim.x) {
+    const long long* a = acc + (size_t)s * POLY_NACC;
+    long long cnt = __ldcg(a + 0);
+    double n = (double)cnt;
+    gm_slice o;
+    for (int k = 0; k < 3; ++k) { o.center[k] = 0.f; o.dir[k] = 0.f; }
+    o.radius = 0.f; o.rms = 0.f;
+    double tm = ps->t0 + ((double)s + 0.5) * ps->L;
+    o.t_mid = (float)tm;
+    o.count = (int)cnt;
+    if (n >= 3 && aux[(size_t)s * POLY_NACC + 21] != 0.0) {
+      double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
+      double ca = aux[(size_t)s * POLY_NACC + 18], cb = aux[(size_t)s * POLY_NACC + 19], rad = aux[(size_t)s * POLY_NACC + 20];
+      double ctr_a = ma + ca, ctr_b = mb + cb;
+      for (int k = 0; k < 3; ++k) o.center[k] = (float)(ctr_a * ps->u[k] + ctr_b * ps->w[k] + tm * ps->axis[k]);
+      double N[9] = {d_from_fx(__ldcg(a + 3)), d_from_fx(__ldcg(a + 4)), d_from_fx(__ldcg(a + 5)), 0, d_from_fx(__ldcg(a + 6)),
+                     d_from_fx(__ldcg(a + 7)), 0, 0, d_from_fx(__ldcg(a + 8))};
+      N[3] = N[1]; N[6] = N[2]; N[7] = N[5];
+      double vals[3], vecs[9];
+      d_jacobi3(N, vals, vecs);
+      double d[3] = {vecs[0], vecs[3], vecs[6]};
+      if (d[0] * ps->axis[0] + d[1] * ps->axis[1] + d[2] * ps->axis[2] < 0) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
+      for (int k = 0; k < 3; ++k) o.dir[k] = (float)d[k];
+      o.radius = (float)rad;
+      o.rms = (float)sqrt(d_from_fx(__ldcg(a + 15)) / n);
+    }
+    out[s] = o;
+  }
+}
+
+// Launch 1 of 4: axis basis from the local frame, zero the accumulators, range of t = axis.p over
+// the cylinder-labelled points (per-block min/max, reduced by the last block, which also lays out
+// the slices).  No atomics on the range, so nothing needs initialising.
 __global__ void __launch_bounds__(POLY_BLOCK)
-k_poly_range(const float4* __restrict__ pts, const unsigned char* __restrict__ labels, const int* __restrict__ n_ptr, PolyState* ps) {
+k_poly_range(const float4* __restrict__ pts, const unsigned char* __restrict__ labels, const int* __restrict__ n_ptr,
+             const FrameOut* __restrict__ frame, PolyState* ps, long long* acc, int n_acc,
+             unsigned long long* part /* 2 x gridDim */, unsigned* ticket, double L, int max_slices) {
+  __shared__ unsigned long long s_lo[POLY_BLOCK / 32], s_hi[POLY_BLOCK / 32];
   const int n = *n_ptr;
-  const double a0 = ps->axis[0], a1 = ps->axis[1], a2 = ps->axis[2];
+  const double a0 = (double)frame->vecs[0], a1 = (double)frame->vecs[3], a2 = (double)frame->vecs[6];
+  for (int i = blockIdx.x * POLY_BLOCK + threadIdx.x; i < n_acc; i += gridDim.x * POLY_BLOCK) acc[i] = 0;
   unsigned long long lo = 0xFFFFFFFFFFFFFFFFull, hi = 0ull;
   for (int i = blockIdx.x * POLY_BLOCK + threadIdx.x; i < n; i += gridDim.x * POLY_BLOCK) {
     if (labels[i] != 2) continue;
@@ -67,159 +131,121 @@ k_poly_range(const float4* __restrict__ pts, const unsigned char* __restrict__ l
     lo = l2 < lo ? l2 : lo;
     hi = h2 > hi ? h2 : hi;
   }
-  if (lane_id() == 0 && lo <= hi) {
-    atomicMin(&ps->tmin_ord, lo);
-    atomicMax(&ps->tmax_ord, hi);
+  if (lane_id() == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < POLY_BLOCK / 32; ++w) { lo = s_lo[w] < lo ? s_lo[w] : lo; hi = s_hi[w] > hi ? s_hi[w] : hi; }
+    part[2 * blockIdx.x] = lo;
+    part[2 * blockIdx.x + 1] = hi;
+    __threadfence();
+  }
+  if (!d_last_block(ticket, gridDim.x)) return;
+  lo = 0xFFFFFFFFFFFFFFFFull; hi = 0ull;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += POLY_BLOCK) {
+    unsigned long long l2 = __ldcg(part + 2 * b), h2 = __ldcg(part + 2 * b + 1);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long l2 = __shfl_xor_sync(FULL, lo, o), h2 = __shfl_xor_sync(FULL, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if (lane_id() == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < POLY_BLOCK / 32; ++w) { lo = s_lo[w] < lo ? s_lo[w] : lo; hi = s_hi[w] > hi ? s_hi[w] : hi; }
+  double ax[3] = {a0, a1, a2}, u[3], w[3];
+  d_perp_basis_d(ax, u, w);
+  for (int k = 0; k < 3; ++k) { ps->axis[k] = ax[k]; ps->u[k] = u[k]; ps->w[k] = w[k]; }
+  ps->tmin_ord = lo; ps->tmax_ord = hi;
+  ps->L = L; ps->t0 = 0.0; ps->S = 0; ps->pad_ = 0;
+  if (lo <= hi) {
+    double tmin = d_ordered_to_double(lo), tmax = d_ordered_to_double(hi);
+    double t0 = floor(tmin / L) * L;
+    int S = (int)floor((tmax - t0) / L) + 1;
+    ps->t0 = t0;
+    ps->S = S > max_slices ? max_slices : S;
   }
 }
 
-__global__ void k_poly_setup(PolyState* ps, double L, int max_slices) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  ps->L = L;
-  if (ps->tmin_ord > ps->tmax_ord) { ps->S = 0; return; }
-  double tmin = d_ordered_to_double(ps->tmin_ord), tmax = d_ordered_to_double(ps->tmax_ord);
-  double t0 = floor(tmin / L) * L;
-  int S = (int)floor((tmax - t0) / L) + 1;
-  ps->t0 = t0;
-  ps->S = S > max_slices ? max_slices : S;
-}
-
-// PASS 0: n, sum a, sum b, weighted normal scatter (slots 0..8)
-// PASS 1: centred second/third moments for the algebraic circle fit (slots 9..14)
-// PASS 2: squared residuals against the fitted circle (slot 15)
+// Launches 2-4: one accumulation pass each, followed (in the last block to finish) by the
+// per-slice step that consumes it.
+// PASS 0: n, sum a, sum b, weighted normal scatter (slots 0..8)            -> slice means
+// PASS 1: centred second/third moments for the algebraic circle fit (9..14)  -> circle fit
+// PASS 2: squared residuals against the fitted circle (slot 15)              -> output slices
 template <int PASS>
 __global__ void __launch_bounds__(POLY_BLOCK)
 k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, const unsigned char* __restrict__ labels,
             const int* __restrict__ n_ptr, const PolyState* __restrict__ ps, double shift, long long* __restrict__ acc,
-            const gm_slice* /*unused*/) {
+            gm_slice* __restrict__ out, unsigned* ticket) {
   constexpr int NS = PASS == 0 ? 9 : (PASS == 1 ? 6 : 1);
   constexpr int SLOT0 = PASS == 0 ? 0 : (PASS == 1 ? 9 : 15);
   __shared__ unsigned long long s_acc[POLY_SMEM_SLICES * NS];
   const int n = *n_ptr;
   const int S = ps->S;
-  if (S <= 0) return;
   const bool use_smem = S <= POLY_SMEM_SLICES;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) s_acc[i] = 0ull;
-    __syncthreads();
-  }
-  const double a0 = ps->axis[0], a1 = ps->axis[1], a2 = ps->axis[2];
-  const double u0 = ps->u[0], u1 = ps->u[1], u2 = ps->u[2];
-  const double w0 = ps->w[0], w1 = ps->w[1], w2 = ps->w[2];
-  const double t0 = ps->t0, L = ps->L;
-  const double* aux = reinterpret_cast<const double*>(acc);
-  for (int i = blockIdx.x * POLY_BLOCK + threadIdx.x; i < n; i += gridDim.x * POLY_BLOCK) {
-    if (labels[i] != 2) continue;
-    float4 p = pts[i];
-    double x = p.x, y = p.y, z = p.z;
-    double t = a0 * x + a1 * y + a2 * z;
-    int s = (int)floor((t - t0) / L);
-    if (s < 0 || s >= S) continue;
-    long long v[NS];
-    if (PASS == 0) {
-      double a = u0 * x + u1 * y + u2 * z, b = w0 * x + w1 * y + w2 * z;
-      float4 n0 = normals[2 * (size_t)i];
-      float curv = normals[2 * (size_t)i + 1].x;
-      double tt = (double)curv + shift;
-      double wt = (double)(float)exp(tt * tt);
-      double na = wt * (double)n0.x, nb = wt * (double)n0.y, nc = wt * (double)n0.z;
-      v[0] = 1; v[1] = d_to_fx(a); v[2] = d_to_fx(b);
-      v[3] = d_to_fx(na * na); v[4] = d_to_fx(na * nb); v[5] = d_to_fx(na * nc);
-      v[6] = d_to_fx(nb * nb); v[7] = d_to_fx(nb * nc); v[8] = d_to_fx(nc * nc);
-    } else if (PASS == 1) {
-      double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
-      double a = u0 * x + u1 * y + u2 * z - ma, b = w0 * x + w1 * y + w2 * z - mb;
-      double zz = a * a + b * b;
-      v[0] = d_to_fx(a * a); v[1] = d_to_fx(a * b); v[2] = d_to_fx(b * b);
-      v[3] = d_to_fx(a * zz); v[4] = d_to_fx(b * zz); v[5] = d_to_fx(zz);
-    } else {
-      double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
-      double ca = aux[(size_t)s * POLY_NACC + 18], cb = aux[(size_t)s * POLY_NACC + 19], rad = aux[(size_t)s * POLY_NACC + 20];
-      double a = u0 * x + u1 * y + u2 * z - ma - ca, b = w0 * x + w1 * y + w2 * z - mb - cb;
-      double e = sqrt(a * a + b * b) - rad;
-      v[0] = d_to_fx(e * e);
+  if (S > 0) {
+    if (use_smem) {
+      for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) s_acc[i] = 0ull;
+      __syncthreads();
     }
+    const double a0 = ps->axis[0], a1 = ps->axis[1], a2 = ps->axis[2];
+    const double u0 = ps->u[0], u1 = ps->u[1], u2 = ps->u[2];
+    const double w0 = ps->w[0], w1 = ps->w[1], w2 = ps->w[2];
+    const double t0 = ps->t0, L = ps->L;
+    const double* aux = reinterpret_cast<const double*>(acc);
+    for (int i = blockIdx.x * POLY_BLOCK + threadIdx.x; i < n; i += gridDim.x * POLY_BLOCK) {
+      if (labels[i] != 2) continue;
+      float4 p = pts[i];
+      double x = p.x, y = p.y, z = p.z;
+      double t = a0 * x + a1 * y + a2 * z;
+      int s = (int)floor((t - t0) / L);
+      if (s < 0 || s >= S) continue;
+      long long v[NS];
+      if (PASS == 0) {
+        double a = u0 * x + u1 * y + u2 * z, b = w0 * x + w1 * y + w2 * z;
+        float4 n0 = normals[2 * (size_t)i];
+        float curv = normals[2 * (size_t)i + 1].x;
+        double tt = (double)curv + shift;
+        double wt = (double)(float)exp(tt * tt);
+        double na = wt * (double)n0.x, nb = wt * (double)n0.y, nc = wt * (double)n0.z;
+        v[0] = 1; v[1] = d_to_fx(a); v[2] = d_to_fx(b);
+        v[3] = d_to_fx(na * na); v[4] = d_to_fx(na * nb); v[5] = d_to_fx(na * nc);
+        v[6] = d_to_fx(nb * nb); v[7] = d_to_fx(nb * nc); v[8] = d_to_fx(nc * nc);
+      } else if (PASS == 1) {
+        double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
+        double a = u0 * x + u1 * y + u2 * z - ma, b = w0 * x + w1 * y + w2 * z - mb;
+        double zz = a * a + b * b;
+        v[0] = d_to_fx(a * a); v[1] = d_to_fx(a * b); v[2] = d_to_fx(b * b);
+        v[3] = d_to_fx(a * zz); v[4] = d_to_fx(b * zz); v[5] = d_to_fx(zz);
+      } else {
+        double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
+        double ca = aux[(size_t)s * POLY_NACC + 18], cb = aux[(size_t)s * POLY_NACC + 19], rad = aux[(size_t)s * POLY_NACC + 20];
+        double a = u0 * x + u1 * y + u2 * z - ma - ca, b = w0 * x + w1 * y + w2 * z - mb - cb;
+        double e = sqrt(a * a + b * b) - rad;
+        v[0] = d_to_fx(e * e);
+      }
 #pragma unroll
-    for (int k = 0; k < NS; ++k) {
-      if (use_smem) atomicAdd(&s_acc[s * NS + k], (unsigned long long)v[k]);
-      else atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)s * POLY_NACC + SLOT0 + k, (unsigned long long)v[k]);
+      for (int k = 0; k < NS; ++k) {
+        if (use_smem) atomicAdd(&s_acc[s * NS + k], (unsigned long long)v[k]);
+        else atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)s * POLY_NACC + SLOT0 + k, (unsigned long long)v[k]);
+      }
+    }
+    if (use_smem) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) {
+        unsigned long long v = s_acc[i];
+        if (v) atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)(i / NS) * POLY_NACC + SLOT0 + (i % NS), v);
+      }
     }
   }
-  if (use_smem) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) {
-      unsigned long long v = s_acc[i];
-      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)(i / NS) * POLY_NACC + SLOT0 + (i % NS), v);
-    }
-  }
-}
-
-__global__ void k_poly_means(const PolyState* __restrict__ ps, long long* acc, gm_slice* /*unused*/) {
-  const int S = ps->S;
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  double* aux = reinterpret_cast<double*>(acc);
-  double n = (double)acc[(size_t)s * POLY_NACC + 0];
-  double ma = 0.0, mb = 0.0;
-  if (n > 0) { ma = d_from_fx(acc[(size_t)s * POLY_NACC + 1]) / n; mb = d_from_fx(acc[(size_t)s * POLY_NACC + 2]) / n; }
-  aux[(size_t)s * POLY_NACC + 16] = ma;
-  aux[(size_t)s * POLY_NACC + 17] = mb;
-}
-
-__global__ void k_poly_fit(const PolyState* __restrict__ ps, long long* acc, gm_slice* /*unused*/) {
-  const int S = ps->S;
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  double* aux = reinterpret_cast<double*>(acc);
-  const long long* a = acc + (size_t)s * POLY_NACC;
-  double n = (double)a[0];
-  double ca = 0.0, cb = 0.0, rad = 0.0, ok = 0.0;
-  if (n >= 3) {
-    double Saa = d_from_fx(a[9]), Sab = d_from_fx(a[10]), Sbb = d_from_fx(a[11]);
-    double Saz = d_from_fx(a[12]), Sbz = d_from_fx(a[13]), Sz = d_from_fx(a[14]);
-    double det = Saa * Sbb - Sab * Sab;
-    if (fabs(det) > 1e-300) {
-      double Ac = (Saz * Sbb - Sbz * Sab) / det, Bc = (Sbz * Saa - Saz * Sab) / det;
-      ca = 0.5 * Ac; cb = 0.5 * Bc;
-      rad = sqrt(Sz / n + ca * ca + cb * cb);
-      ok = 1.0;
-    }
-  }
-  aux[(size_t)s * POLY_NACC + 18] = ca;
-  aux[(size_t)s * POLY_NACC + 19] = cb;
-  aux[(size_t)s * POLY_NACC + 20] = rad;
-  aux[(size_t)s * POLY_NACC + 21] = ok;
-}
-
-__global__ void k_poly_finish(const PolyState* __restrict__ ps, const long long* __restrict__ acc, gm_slice* __restrict__ out) {
-  const int S = ps->S;
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  const double* aux = reinterpret_cast<const double*>(acc);
-  const long long* a = acc + (size_t)s * POLY_NACC;
-  double n = (double)a[0];
-  gm_slice o;
-  for (int k = 0; k < 3; ++k) { o.center[k] = 0.f; o.dir[k] = 0.f; }
-  o.radius = 0.f; o.rms = 0.f;
-  double tm = ps->t0 + ((double)s + 0.5) * ps->L;
-  o.t_mid = (float)tm;
-  o.count = (int)a[0];
-  if (n >= 3 && aux[(size_t)s * POLY_NACC + 21] != 0.0) {
-    double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
-    double ca = aux[(size_t)s * POLY_NACC + 18], cb = aux[(size_t)s * POLY_NACC + 19], rad = aux[(size_t)s * POLY_NACC + 20];
-    double ctr_a = ma + ca, ctr_b = mb + cb;
-    for (int k = 0; k < 3; ++k) o.center[k] = (float)(ctr_a * ps->u[k] + ctr_b * ps->w[k] + tm * ps->axis[k]);
-    double N[9] = {d_from_fx(a[3]), d_from_fx(a[4]), d_from_fx(a[5]), 0, d_from_fx(a[6]), d_from_fx(a[7]), 0, 0, d_from_fx(a[8])};
-    N[3] = N[1]; N[6] = N[2]; N[7] = N[5];
-    double vals[3], vecs[9];
-    d_jacobi3(N, vals, vecs);
-    double d[3] = {vecs[0], vecs[3], vecs[6]};
-    if (d[0] * ps->axis[0] + d[1] * ps->axis[1] + d[2] * ps->axis[2] < 0) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
-    for (int k = 0; k < 3; ++k) o.dir[k] = (float)d[k];
-    o.radius = (float)rad;
-    o.rms = (float)sqrt(d_from_fx(a[15]) / n);
-  }
-  out[s] = o;
+  __threadfence();
+  if (!d_last_block(ticket, gridDim.x)) return;
+  if (PASS == 0) d_poly_means(ps, acc);
+  else if (PASS == 1) d_poly_fit(ps, acc);
+  else d_poly_finish(ps, acc, out);
 }
 
 }  // namespace gm

@@ -406,9 +406,7 @@ k_plane_refit(const float4* __restrict__ pts, const int* __restrict__ n_ptr, con
       }
     }
   }
-  block_sum<10, RF_BLOCK>(s, sm);
-  if (threadIdx.x == 0)
-    for (int k = 0; k < 10; ++k) partials[blockIdx.x * 10 + k] = s[k];
+  block_sum_store<10, RF_BLOCK>(s, sm, partials + (size_t)blockIdx.x * 10);
   if (!d_last_block(counter, gridDim.x)) return;
   d_reduce_partials<10>(partials, gridDim.x, fin);
   if (threadIdx.x != 0) return;
@@ -525,20 +523,27 @@ __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target,
 
 __global__ void __launch_bounds__(RF_BLOCK)
 k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float tau, double* __restrict__ partials /* 2 x grid x 22 */,
-             unsigned* barrier_count, unsigned barrier_base, int* err) {
+             unsigned* barrier_count, unsigned* barrier_next, int* err) {
   __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
   __shared__ double fin[GN_NV];
   __shared__ double it_q[3], it_dir[3], it_r;
+  __shared__ int s_converged;
+  // two barrier counters used alternately by consecutive launches: this launch counts on
+  // barrier_count from 0 and clears the other one for the next launch (the number of passes is
+  // data dependent, so the host cannot pre-compute a cumulative target)
+  if (blockIdx.x == 0 && threadIdx.x == 0) *barrier_next = 0u;
   const bool have = ms->best_id >= 0;
   const int n = have ? ms->n_inl : 0;
   const int nb = gridDim.x;
   if (threadIdx.x == 0) {
     for (int k = 0; k < 3; ++k) { it_q[k] = ms->q[k]; it_dir[k] = ms->dir[k]; }
     it_r = ms->r;
+    s_converged = 0;
   }
   __syncthreads();
   bool frozen = false;  // block-uniform: singular system or too few inliers -> iterate no longer moves
-  for (int it = 0; it <= iters; ++it) {
+  int pass = 0;         // barriers crossed so far in this launch
+  for (int it = 0; it <= iters; ++it, ++pass) {
     const int update = it < iters;
     double s[GN_NV];
 #pragma unroll
@@ -569,11 +574,9 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
         for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
       }
     }
-    block_sum<GN_NV, RF_BLOCK>(s, sm);
-    double* buf = partials + (size_t)(it & 1) * nb * GN_NV;
-    if (threadIdx.x == 0)
-      for (int k = 0; k < GN_NV; ++k) buf[blockIdx.x * GN_NV + k] = s[k];
-    d_grid_barrier(barrier_count, barrier_base + (unsigned)(it + 1) * (unsigned)nb, err);
+    double* buf = partials + (size_t)(pass & 1) * nb * GN_NV;
+    block_sum_store<GN_NV, RF_BLOCK>(s, sm, buf + (size_t)blockIdx.x * GN_NV);
+    d_grid_barrier(barrier_count, (unsigned)(pass + 1) * (unsigned)nb, err);
     d_reduce_partials<GN_NV>(buf, nb, fin);
     const long long cnt = (long long)(fin[20] + 0.5);
     if (cnt <= 5) frozen = true;  // model unchanged (same rule as the oracle)
@@ -592,6 +595,8 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
           double dl = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
           for (int k = 0; k < 3; ++k) it_dir[k] = dir[k] / dl;
           it_r += x[4];
+          // converged (same rule as the oracle): skip the remaining update passes
+          if (x[0] * x[0] + x[1] * x[1] + x[4] * x[4] < 1e-16 && x[2] * x[2] + x[3] * x[3] < 1e-16) s_converged = 1;
         }
       }
       if (!update && blockIdx.x == 0 && cnt > 5) {
@@ -604,6 +609,8 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
       }
     }
     __syncthreads();
+    // every block computed the same step from the same partials, so this is grid-uniform
+    if (update && s_converged && it < iters - 1) it = iters - 1;
   }
 }
 

@@ -261,6 +261,9 @@ __device__ void d_eigen33_smallest(float c00, float c01, float c02, float c11, f
 // One thread per point in cell-sorted order: neighbouring lanes sit in the same or adjacent cells,
 // so their candidate runs coincide and the candidate loads are warp-coherent L1 hits.
 // The neighbour predicate is the exact FLANN L2_Simple form (unfused, strict <).
+// (A variant testing candidate pairs with the packed sub/mul/add.f32x2 ops was measured 22 % SLOWER:
+// packed ops hold the FP32 pipe two cycles, so only issue slots are saved, and ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, which breaks the exact predicate.)
 constexpr int NRM_BLOCK = 128;
 __global__ void __launch_bounds__(NRM_BLOCK)
 k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs,
@@ -670,9 +673,7 @@ k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, dou
     s[0] += (double)a * (double)a; s[1] += (double)a * (double)b; s[2] += (double)a * (double)c;
     s[3] += (double)b * (double)b; s[4] += (double)b * (double)c; s[5] += (double)c * (double)c;
   }
-  block_sum<6, FR_BLOCK>(s, sm);
-  if (threadIdx.x == 0)
-    for (int k = 0; k < 6; ++k) partials[blockIdx.x * 6 + k] = s[k];
+  block_sum_store<6, FR_BLOCK>(s, sm, partials + (size_t)blockIdx.x * 6);
   if (!d_last_block(counter, gridDim.x)) return;
   d_reduce_partials<6>(partials, gridDim.x, fin);
   if (threadIdx.x != 0) return;

@@ -20,6 +20,7 @@ namespace {
 constexpr int GM_VERSION = 1;
 constexpr int FRAME_BLOCKS = 296;
 constexpr int REFIT_BLOCKS = 296;
+constexpr size_t kPartialsRegion = (size_t)296 * 32;  // doubles per concurrent reduction
 
 // profiling segments (gm_profile_*): one CUDA-event pair per segment per call
 enum Seg {
@@ -70,6 +71,10 @@ struct gm_ctx {
   int num_sms = 148;
   int gn_blocks = 148;  // cooperative grid of the cylinder refit
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // gm_process_scan forks the independent stages of one scan onto these (joined before labels)
+  cudaStream_t branch[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  bool concurrent = true;
   std::string err;
   int64_t launches = 0;
 
@@ -92,11 +97,11 @@ struct gm_ctx {
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
   unsigned char* d_labels = nullptr;
   unsigned long long* d_state64 = nullptr;
-  unsigned long long* d_rs_state = nullptr;
-  unsigned *d_rs_hist = nullptr, *d_rs_ticket = nullptr;
+  unsigned long long* d_state64_b = nullptr;  // tile states of the cylinder-refit compaction (may run concurrently with the voxel branch)
+  unsigned *d_rs_hist = nullptr, *d_rs_totals = nullptr;  // [256][tiles] tile histograms / row prefixes, [256] row totals
+  size_t rs_hist_words = 0;
   unsigned epoch = 0;            // per-launch tag of the look-back tile states (never cleared)
   unsigned gn_launches = 0;      // parity selects which of the two GN barrier counters a launch uses
-  size_t rs_state_words = 0;
   DevState* d_st = nullptr;
   double* d_partials = nullptr;
   FrameOut* d_frame = nullptr;
@@ -202,8 +207,9 @@ GridSpec make_grid(const gm_params& p) {
 gm_status next_epoch(gm_ctx* ctx, unsigned* out) {
   ctx->epoch = (ctx->epoch + 1) & TS_EPOCH_MASK;
   if (ctx->epoch == 0) {
-    GM_CUDA(cudaMemsetAsync(ctx->d_state64, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long), ctx->stream));
-    GM_CUDA(cudaMemsetAsync(ctx->d_rs_state, 0, ctx->rs_state_words * sizeof(unsigned long long), ctx->stream));
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    GM_CUDA(cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
+    GM_CUDA(cudaMemset(ctx->d_state64_b, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
     ctx->epoch = 1;
   }
   *out = ctx->epoch;
@@ -211,23 +217,17 @@ gm_status next_epoch(gm_ctx* ctx, unsigned* out) {
 }
 
 // LSD radix sort of (d_keys[0], d_vals[0]) -> returns the buffer index holding the result.
-// The histogram was cleared by the kernel that produced the keys; tickets reset themselves; tile
-// states are epoch tagged: no memset nodes.
+// Three wait-free kernels per 8-bit pass (see gm_device.cuh); no memsets, no inter-block spinning.
 gm_status radix_sort(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int key_bits, int* result_buf) {
   int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
   int ntiles = div_up((long long)n_cap, RS_TILE);
-  size_t words = (size_t)passes * ntiles * 256;
-  if (words > ctx->rs_state_words) { ctx->err = "radix state capacity"; return GM_ERR_CAPACITY; }
-  unsigned epoch = 0;
-  gm_status st = next_epoch(ctx, &epoch);
-  if (st != GM_OK) return st;
-  int hist_grid = std::min(ntiles, ctx->num_sms * 8);
-  GM_LAUNCH(ctx, k_radix_hist, hist_grid, RS_BLOCK, ctx->d_keys[0], n_ptr, passes, ctx->d_rs_hist);
+  if ((size_t)ntiles * 256 > ctx->rs_hist_words) { ctx->err = "radix histogram capacity"; return GM_ERR_CAPACITY; }
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
-    GM_LAUNCH(ctx, k_radix_onesweep, ntiles, RS_BLOCK, ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1],
-              ctx->d_vals[cur ^ 1], n_ptr, p, ctx->d_rs_hist, ctx->d_rs_state + (size_t)p * ntiles * 256, epoch,
-              ctx->d_rs_ticket + p, &ctx->d_st->error);
+    GM_LAUNCH(ctx, k_rs_upsweep, ntiles, RS_BLOCK, ctx->d_keys[cur], n_ptr, p, ntiles, ctx->d_rs_hist);
+    GM_LAUNCH(ctx, k_rs_scan, 256, RS_BLOCK, ctx->d_rs_hist, n_ptr, ntiles, ctx->d_rs_totals);
+    GM_LAUNCH(ctx, k_rs_downsweep, ntiles, RS_BLOCK, ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1], ctx->d_vals[cur ^ 1], n_ptr,
+              p, ntiles, ctx->d_rs_hist, ctx->d_rs_totals);
     cur ^= 1;
   }
   *result_buf = cur;
@@ -325,11 +325,11 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_runs, 9 * N);
   A(d_vkey_pt, N); A(d_assign, N); A(d_vox_start, N + 1); A(d_vox_key, N); A(d_vox_count, N); A(d_nn_idx, N);
   A(d_labels, N);
-  A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2);
-  ctx->rs_state_words = (size_t)RS_MAX_PASSES * div_up((long long)N, RS_TILE) * 256;
-  A(d_rs_state, ctx->rs_state_words); A(d_rs_hist, RS_MAX_PASSES * 256); A(d_rs_ticket, RS_MAX_PASSES);
+  A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
+  ctx->rs_hist_words = (size_t)div_up((long long)N, RS_TILE) * 256;
+  A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256);
   A(d_st, 1);
-  A(d_partials, (size_t)std::max(FRAME_BLOCKS, REFIT_BLOCKS) * 32);
+  A(d_partials, 3 * kPartialsRegion);  // 3 regions: frame | plane refit | cylinder GN (may run concurrently)
   A(d_frame, 1);
   A(d_samples[0], 3 * H); A(d_samples[1], 2 * H);
   A(d_plane_coef, H); A(d_model7, 7 * H); A(d_test12, 12 * H);
@@ -343,9 +343,14 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
     if ((e = cudaEventCreateWithFlags(&ctx->ev_samples[k], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
   if ((e = cudaMemset(ctx->d_st, 0, sizeof(DevState))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)N, CP_TILE) + 2) * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
-  if ((e = cudaMemset(ctx->d_rs_state, 0, ctx->rs_state_words * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
-  if ((e = cudaMemset(ctx->d_rs_hist, 0, RS_MAX_PASSES * 256 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
-  if ((e = cudaMemset(ctx->d_rs_ticket, 0, RS_MAX_PASSES * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_state64_b, 0, ((size_t)div_up((long long)N, CP_TILE) + 2) * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
+  for (int b = 0; b < 3; ++b) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->branch[b], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "branch stream");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join[b], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+  }
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+  { const char* env = std::getenv("GM_SERIAL"); ctx->concurrent = !(env && env[0] == '1'); }
+
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_model, 0, 2 * sizeof(ModelState))) != cudaSuccess) return fail(e, "memset");
@@ -353,7 +358,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cyl_gn_all, RF_BLOCK, 0)) != cudaSuccess) return fail(e, "occupancy");
     ctx->gn_blocks = std::max(1, std::min(ctx->num_sms, per_sm * ctx->num_sms));
-    if ((size_t)ctx->gn_blocks * 2 * GN_NV > (size_t)std::max(FRAME_BLOCKS, REFIT_BLOCKS) * 32) return fail(cudaErrorInvalidValue, "partials capacity");
+    if ((size_t)ctx->gn_blocks * 2 * GN_NV > kPartialsRegion) return fail(cudaErrorInvalidValue, "partials capacity");
   }
   ctx->grid = make_grid(ctx->prm);
   *out = ctx;
@@ -366,8 +371,8 @@ void gm_destroy(gm_ctx* ctx) {
   void* ptrs[] = {ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
-                  ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64,
-                  ctx->d_rs_state, ctx->d_rs_hist, ctx->d_rs_ticket, ctx->d_st, ctx->d_partials, ctx->d_frame,
+                  ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
+                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
                   ctx->d_poly_acc, ctx->d_slices, ctx->d_summary, ctx->d_counters, ctx->d_inl, ctx->d_poly_part};
@@ -378,6 +383,8 @@ void gm_destroy(gm_ctx* ctx) {
   }
   for (auto& v : ctx->seg_events) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (int b = 0; b < 3; ++b) { if (ctx->branch[b]) cudaStreamDestroy(ctx->branch[b]); if (ctx->ev_join[b]) cudaEventDestroy(ctx->ev_join[b]); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -473,7 +480,7 @@ gm_status gm_normals(gm_ctx* ctx) {
     const GridSpec g = ctx->grid;
     int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
     { SegTimer seg_(ctx, SEG_GRID_KEYS);
-      GM_LAUNCH(ctx, k_cell_keys, blocks, 256, ctx->d_crop, n_ptr, g, ctx->d_keys[0], ctx->d_vals[0], ctx->d_rs_hist); }
+      GM_LAUNCH(ctx, k_cell_keys, blocks, 256, ctx->d_crop, n_ptr, g, ctx->d_keys[0], ctx->d_vals[0]); }
     int buf = 0;
     gm_status s;
     { SegTimer seg_(ctx, SEG_GRID_SORT);
@@ -513,7 +520,7 @@ gm_status gm_voxel(gm_ctx* ctx) {
     const float inv = 1.0f / leaf_f;
     int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
     { SegTimer seg_(ctx, SEG_VOX_KEYS);
-      GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, inv, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt, ctx->d_rs_hist); }
+      GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, inv, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt); }
     // static upper bound of the key range from the crop box (no host round trip for the bbox)
     int key_bits = 32;
     if (!ctx->injected) {
@@ -552,7 +559,7 @@ gm_status gm_local_frame(gm_ctx* ctx) {
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
   double shift = .001 / ctx->prm.weightingFactor;  // src/tunnel_processing.cpp:106 precedence
   SegTimer seg_(ctx, SEG_FRAME);
-  GM_LAUNCH(ctx, k_frame, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, shift, ctx->d_partials, ctx->d_counters + 0,
+  GM_LAUNCH(ctx, k_frame, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, shift, ctx->d_partials + 0 * kPartialsRegion, ctx->d_counters + 0,
             ctx->d_frame);
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_frame = true;
@@ -632,18 +639,18 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
   const float tau = (float)ctx->prm.ransacThreshold;
   if (kind == 0) {
     GM_LAUNCH(ctx, k_plane_refit, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_key + 0, H, ctx->d_plane_coef, ms, tau,
-              ctx->d_partials, ctx->d_counters + 1);
+              ctx->d_partials + 1 * kPartialsRegion, ctx->d_counters + 1);
   } else {
     unsigned epoch = 0;
     gm_status s = next_epoch(ctx, &epoch);
     if (s != GM_OK) return s;
     GM_LAUNCH(ctx, k_cyl_inlier_compact, std::max(1, div_up((long long)ctx->n_input, CPL_TILE)), CP_BLOCK, ctx->d_cloud_c, n_ptr,
-              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64, epoch, &ctx->d_st->error);
+              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64_b, epoch, &ctx->d_st->error);
     // all Gauss-Newton passes in one cooperative launch (grid barrier between passes)
     {
       const float4* inl = ctx->d_inl;
       int iters = ctx->prm.refitIterations;
-      double* partials = ctx->d_partials;
+      double* partials = ctx->d_partials + 2 * kPartialsRegion;
       unsigned* bar = ctx->d_counters + 5 + (ctx->gn_launches & 1);       // counters [5],[6]: ping-pong
       unsigned* bar_next = ctx->d_counters + 5 + ((ctx->gn_launches + 1) & 1);
       ++ctx->gn_launches;
@@ -697,20 +704,56 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   return GM_OK;
 }
 
+}  // extern "C" (templates need C++ linkage)
+
+// Runs `body` with ctx->stream temporarily replaced by branch stream `b` (which first waits for
+// the fork event), then records the branch's join event.
+template <class F>
+static gm_status run_branch(gm_ctx* ctx, int b, F&& body) {
+  cudaStream_t main_stream = ctx->stream;
+  cudaError_t e = cudaStreamWaitEvent(ctx->branch[b], ctx->ev_fork, 0);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return GM_ERR_CUDA; }
+  ctx->stream = ctx->branch[b];
+  gm_status s = body();
+  ctx->stream = main_stream;
+  if (s != GM_OK) return s;
+  e = cudaEventRecord(ctx->ev_join[b], ctx->branch[b]);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return GM_ERR_CUDA; }
+  return GM_OK;
+}
+
+extern "C" {
+
 gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   gm_status s;
   if ((s = gm_crop(ctx)) != GM_OK) return s;
   if ((s = gm_normals(ctx)) != GM_OK) return s;
-  if ((s = gm_voxel(ctx)) != GM_OK) return s;
-  if ((s = gm_local_frame(ctx)) != GM_OK) return s;
-  if (Hp > 0) {
-    if ((s = gm_ransac(ctx, GM_MODEL_PLANE, plane_samples_host, Hp, 0, Hp)) != GM_OK) return s;
-    if ((s = gm_ransac_select(ctx, GM_MODEL_PLANE)) != GM_OK) return s;
-  }
-  if (Hc > 0) {
-    if ((s = gm_ransac(ctx, GM_MODEL_CYLINDER, cyl_samples_host, Hc, 0, Hc)) != GM_OK) return s;
-    if ((s = gm_ransac_select(ctx, GM_MODEL_CYLINDER)) != GM_OK) return s;
+  // After the NaN compaction four stages only READ the compacted cloud / normals and write disjoint
+  // outputs: voxel grid + 1-NN, local frame, plane RANSAC + refit, cylinder RANSAC + refit.  They are
+  // forked onto separate streams so the latency-bound small kernels overlap the FP32-bound inlier
+  // counting (which runs at ~20 % warp occupancy); labels and the polyline need all of them.
+  auto plane = [&]() -> gm_status {
+    if (Hp <= 0) return GM_OK;
+    gm_status r = gm_ransac(ctx, GM_MODEL_PLANE, plane_samples_host, Hp, 0, Hp);
+    return r != GM_OK ? r : gm_ransac_select(ctx, GM_MODEL_PLANE);
+  };
+  auto cylinder = [&]() -> gm_status {
+    if (Hc <= 0) return GM_OK;
+    gm_status r = gm_ransac(ctx, GM_MODEL_CYLINDER, cyl_samples_host, Hc, 0, Hc);
+    return r != GM_OK ? r : gm_ransac_select(ctx, GM_MODEL_CYLINDER);
+  };
+  if (ctx->concurrent && !ctx->profiling) {
+    GM_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if ((s = run_branch(ctx, 0, [&] { return gm_voxel(ctx); })) != GM_OK) return s;
+    if ((s = run_branch(ctx, 1, [&]() -> gm_status { gm_status r = gm_local_frame(ctx); return r != GM_OK ? r : plane(); })) != GM_OK) return s;
+    if ((s = cylinder()) != GM_OK) return s;  // the longest branch stays on the main stream
+    for (int b = 0; b < 2; ++b) GM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[b], 0));
+  } else {
+    if ((s = gm_voxel(ctx)) != GM_OK) return s;
+    if ((s = gm_local_frame(ctx)) != GM_OK) return s;
+    if ((s = plane()) != GM_OK) return s;
+    if ((s = cylinder()) != GM_OK) return s;
   }
   if ((s = gm_label(ctx)) != GM_OK) return s;
   if ((s = gm_axis_polyline(ctx)) != GM_OK) return s;

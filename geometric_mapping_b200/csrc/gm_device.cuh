@@ -231,62 +231,87 @@ __device__ __forceinline__ void tile_compact_ranks(const bool (&flags)[IPT], uns
   total_inclusive = excl + sm.tile_total;
 }
 
-// ---- onesweep radix sort ------------------------------------------------------------------
+// ---- LSD radix sort of (key, value) u32 pairs, 8-bit digits ----------------------------------
+// Three wait-free kernels per pass (no inter-block spinning at all):
+//   k_rs_upsweep    tile t -> 256-bin digit histogram, stored digit-major  hist[d][t]
+//   k_rs_scan       block d: exclusive scan of row d over the tiles (in place) + row total
+//   k_rs_downsweep  tile t: stable in-tile ranking, then scatter to
+//                   digit_base[d] (scan of the 256 totals) + row_prefix[d][t] + rank-in-tile
+// History (tools/microbench/sort_phases.cu, B200): a single-pass "onesweep" with decoupled look-back
+// was measured at 17 us per 4096-key tile = 6.4 us of __match_any_sync ranking (~760 cycles per
+// round with many distinct digits) + 4-5 us of look-back (resident tiles advance in lockstep, so
+// every tile walks ~300 predecessors x 256 digits = 600 KB of L2 reads) + 3.3 us scatter, i.e.
+// 1.4 TB/s.  Ranking here uses 8 ballots per key (fixed latency) instead of match_any.
 constexpr int RS_BLOCK = 256;
-constexpr int RS_IPT = 16;  // 4096 keys per tile: half as many tiles -> half as long look-back walks in a single-wave launch
-constexpr int RS_TILE = RS_BLOCK * RS_IPT;
+constexpr int RS_IPT = 8;
+constexpr int RS_TILE = RS_BLOCK * RS_IPT;  // 2048 keys per tile: ~60 registers -> 4 blocks per SM
 constexpr int RS_WARPS = RS_BLOCK / 32;
 constexpr int RS_MAX_PASSES = 4;
 
-// One read of the keys -> digit histograms of all passes.  hist[pass*256 + d] must be zero on entry:
-// the kernel that PRODUCES the keys clears it (d_zero_hist), so no memset node is needed.
-__device__ __forceinline__ void d_zero_hist(unsigned* hist) {
-  if (blockIdx.x == 0) for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += blockDim.x) hist[i] = 0u;
-}
-
-__global__ void __launch_bounds__(RS_BLOCK) k_radix_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr,
-                                                         int passes, unsigned* __restrict__ hist) {
-  __shared__ unsigned sh[RS_MAX_PASSES * 256];
-  for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += RS_BLOCK) sh[i] = 0;
-  __syncthreads();
-  const int n = *n_ptr;
-  for (int i = blockIdx.x * RS_BLOCK + threadIdx.x; i < n; i += gridDim.x * RS_BLOCK) {
-    unsigned k = keys[i];
-    for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + ((k >> (8 * p)) & 255u)], 1u);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < passes * 256; i += RS_BLOCK) {
-    unsigned v = sh[i];
-    if (v) atomicAdd(&hist[i], v);
-  }
-}
-
-// One LSD pass.  state: [tiles][256] epoch-tagged words per pass (never cleared); the ticket counter
-// is reset by whichever block draws the last ticket.
 __global__ void __launch_bounds__(RS_BLOCK)
-k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
-                 unsigned* __restrict__ keys_out, unsigned* __restrict__ vals_out,
-                 const int* __restrict__ n_ptr, int pass, const unsigned* __restrict__ hist,
-                 unsigned long long* __restrict__ state, unsigned epoch, unsigned* __restrict__ ticket, int* __restrict__ err) {
+k_rs_upsweep(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int pass, int tile_stride,
+             unsigned* __restrict__ hist /* [256][tile_stride] */) {
+  __shared__ unsigned sh[256];
+  const int n = *n_ptr;
+  const int tile = blockIdx.x, base = tile * RS_TILE;
+  if (base >= n) return;
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int shift = 8 * pass;
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    int g = base + i * RS_BLOCK + threadIdx.x;
+    if (g < n) atomicAdd(&sh[(keys[g] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * tile_stride + tile] = sh[threadIdx.x];
+}
+
+// grid = 256 blocks (one per digit)
+__global__ void __launch_bounds__(RS_BLOCK)
+k_rs_scan(unsigned* __restrict__ hist, const int* __restrict__ n_ptr, int tile_stride, unsigned* __restrict__ totals /* [256] */) {
+  __shared__ unsigned s_warp[RS_WARPS];
+  __shared__ unsigned s_carry;
+  const int n = *n_ptr;
+  const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+  unsigned* row = hist + (size_t)blockIdx.x * tile_stride;
+  const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < ntiles; base += RS_BLOCK) {
+    const int t = base + threadIdx.x;
+    const unsigned v = (t < ntiles) ? row[t] : 0u;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned x = __shfl_up_sync(FULL, inc, o); if (l >= o) inc += x; }
+    if (l == 31) s_warp[w] = inc;
+    __syncthreads();
+    unsigned off = s_carry;
+    for (int ww = 0; ww < w; ++ww) off += s_warp[ww];
+    if (t < ntiles) row[t] = off + inc - v;
+    __syncthreads();
+    if (threadIdx.x == RS_BLOCK - 1) s_carry = off + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__(RS_BLOCK)
+k_rs_downsweep(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned* __restrict__ keys_out,
+               unsigned* __restrict__ vals_out, const int* __restrict__ n_ptr, int pass, int tile_stride,
+               const unsigned* __restrict__ hist /* row prefixes */, const unsigned* __restrict__ totals) {
   __shared__ unsigned s_warp_hist[RS_WARPS][257];
   __shared__ unsigned s_keys[RS_TILE];
   __shared__ unsigned s_vals[RS_TILE];
   __shared__ unsigned s_local_base[256];   // position of digit d in the tile-sorted order
   __shared__ unsigned s_global_base[256];  // output position of the first key of digit d of this tile
   __shared__ unsigned s_scan[RS_WARPS];
-  __shared__ int s_tile;
 
   const int n = *n_ptr;
-  const int ntiles = (n + RS_TILE - 1) / RS_TILE;
-  if (threadIdx.x == 0) {
-    unsigned t = atomicAdd(ticket, 1u);
-    if (t == gridDim.x - 1) *ticket = 0u;  // everybody has drawn: ready for the next launch
-    s_tile = (int)t;
-  }
+  const int tile = blockIdx.x;
+  if (tile * RS_TILE >= n) return;
   for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_BLOCK) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
-  const int tile = s_tile;
-  if (tile >= ntiles) return;
 
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int shift = 8 * pass;
@@ -302,19 +327,30 @@ k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restric
     val[i] = ok ? vals_in[g] : 0u;
     dig[i] = ok ? (int)((key[i] >> shift) & 255u) : 256;
   }
-  // stable ranks inside the warp chunk: order = (i, lane)
+  // stable ranks inside the warp chunk, order = (i, lane).  peers = lanes holding the same digit,
+  // found with one ballot per digit bit (invalid tail items form their own group via bit 8).
+  // The lowest peer adds the group size to the warp's digit counter with a shared-memory atomic and
+  // broadcasts the old value: rounds have no register dependence on one another, and same-warp
+  // atomics on one address execute in program order, so all RS_IPT rounds pipeline (the former
+  // read -> __syncwarp -> write chain cost ~350 cycles per round).
 #pragma unroll
   for (int i = 0; i < RS_IPT; ++i) {
-    unsigned m = __match_any_sync(FULL, dig[i]);
-    unsigned before = s_warp_hist[w][dig[i]];
-    __syncwarp();
-    rank[i] = before + __popc(m & lanemask_lt());
-    if ((m & lanemask_lt()) == 0) s_warp_hist[w][dig[i]] = before + __popc(m);
-    __syncwarp();
+    unsigned peers = FULL;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+      const bool bit = (dig[i] >> b) & 1;
+      const unsigned vote = __ballot_sync(FULL, bit);
+      peers &= bit ? vote : ~vote;
+    }
+    const int leader = __ffs(peers) - 1;
+    unsigned before = 0;
+    if (l == leader) before = atomicAdd(&s_warp_hist[w][dig[i]], (unsigned)__popc(peers));
+    before = __shfl_sync(FULL, before, leader);
+    rank[i] = before + __popc(peers & lanemask_lt());
   }
   __syncthreads();
 
-  // per digit (thread d): exclusive offsets across warps, tile count, look-back
+  // per digit (thread d): exclusive offsets across warps, tile count, bases
   {
     const int d = threadIdx.x;
     unsigned run = 0;
@@ -325,66 +361,30 @@ k_radix_onesweep(const unsigned* __restrict__ keys_in, const unsigned* __restric
       run += c;
     }
     const unsigned tile_cnt = run;
-    unsigned long long* st = state + (size_t)tile * 256 + d;
-    ts_store(st, epoch, tile == 0 ? TS_PREFIX : TS_AGG, tile_cnt);
-
-    // global exclusive digit offset = sum(hist[pass][0..d))  (block scan over 256 digits)
-    unsigned hv = hist[pass * 256 + d];
-    unsigned inc = hv;
+    const unsigned row_prefix = hist[(size_t)d * tile_stride + tile];
+    // digit base = exclusive scan of the 256 row totals; tile-local digit base = scan of tile_cnt
+    unsigned hv = totals[d];
+    unsigned inc = hv, linc = tile_cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(FULL, inc, o);
-      if (l >= o) inc += t;
+      unsigned t = __shfl_up_sync(FULL, inc, o), t2 = __shfl_up_sync(FULL, linc, o);
+      if (l >= o) { inc += t; linc += t2; }
     }
     if (l == 31) s_scan[w] = inc;
-    // tile-local digit base (scan of tile_cnt over d)
-    unsigned linc = tile_cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(FULL, linc, o);
-      if (l >= o) linc += t;
-    }
     __syncthreads();
     unsigned hbase = 0;
     for (int ww = 0; ww < w; ++ww) hbase += s_scan[ww];
-    const unsigned digit_global = hbase + inc - hv;
     __syncthreads();
     if (l == 31) s_scan[w] = linc;
     __syncthreads();
     unsigned lbase = 0;
     for (int ww = 0; ww < w; ++ww) lbase += s_scan[ww];
     s_local_base[d] = lbase + linc - tile_cnt;
-
-    // look back over earlier tiles for this digit: 16 independent loads per step (one L2 round
-    // trip per 16 tiles), folded nearest first until a tile with a full prefix is met
-    unsigned excl = 0;
-    bool done = false;
-    for (int t0 = tile - 1; t0 >= 0 && !done; t0 -= 16) {
-      unsigned wst[16], wval[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        wval[q] = 0u;
-        wst[q] = (t0 - q >= 0) ? ts_load(state + (size_t)(t0 - q) * 256 + d, epoch, wval[q]) : (unsigned)TS_PREFIX;
-      }
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        if (done) break;
-        if (wst[q] == TS_EMPTY) {
-          const unsigned long long* ps = state + (size_t)(t0 - q) * 256 + d;
-          int spins = 0;
-          do { wst[q] = ts_load(ps, epoch, wval[q]); } while (wst[q] == TS_EMPTY && ++spins < SPIN_BOUND);
-          if (wst[q] == TS_EMPTY) { atomicExch(err, 2); done = true; break; }
-        }
-        excl += wval[q];
-        if (wst[q] == TS_PREFIX) done = true;
-      }
-    }
-    if (tile != 0) ts_store(st, epoch, TS_PREFIX, excl + tile_cnt);
-    s_global_base[d] = digit_global + excl;
+    s_global_base[d] = hbase + inc - hv + row_prefix;
   }
   __syncthreads();
 
-  // scatter into tile-sorted order in shared memory
+  // scatter into tile-sorted order in shared memory, then coalesced-run writes
 #pragma unroll
   for (int i = 0; i < RS_IPT; ++i) {
     if (dig[i] < 256) {

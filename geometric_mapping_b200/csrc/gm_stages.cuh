@@ -84,9 +84,8 @@ k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, f
 // Neighbour-grid cell key of every cropped point (sentinel ncells for non-finite points, which
 // are never anyone's neighbour).
 __global__ void k_cell_keys(const float4* __restrict__ pts, const int* __restrict__ n_ptr, GridSpec g,
-                            unsigned* __restrict__ keys, unsigned* __restrict__ idx, unsigned* __restrict__ sort_hist) {
+                            unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
   const int n = *n_ptr;
-  d_zero_hist(sort_hist);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
     unsigned key = g.ncells;
@@ -402,11 +401,9 @@ __global__ void k_bbox(const float4* __restrict__ pts, const int* __restrict__ n
 // from the bounding box by every block (cheap, avoids a 1-thread kernel); block 0 publishes it.
 // Voxel key per compacted point: ijk = int(floor(p*inv) - float(min_b)); key = ijk . divb_mul
 __global__ void k_voxel_keys(const float4* __restrict__ pts, DevState* st, float inv,
-                             unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point,
-                             unsigned* __restrict__ sort_hist) {
+                             unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point) {
   __shared__ int s_minb[3], s_mul[3], s_overflow;
   const int n = st->n_valid;
-  d_zero_hist(sort_hist);
   if (threadIdx.x == 0) {
     float mn[3], mx[3];
     for (int a = 0; a < 3; ++a) { mn[a] = ordered_to_float(st->bbox_min[a]); mx[a] = ordered_to_float(st->bbox_max[a]); }

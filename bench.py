@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--shard-hyp", type=int, default=4096, help="hypotheses of the sharded RANSAC leg (N>1)")
     ap.add_argument("--radius", type=float, default=0.05)
     ap.add_argument("--leaf", type=float, default=0.1)
+    ap.add_argument("--refit-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-points", type=int, default=0, help="points of the CPU baseline sample (0 = full scan)")
     return ap.parse_args()
@@ -212,7 +213,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n, Hp, Hc = a.points, a.hyp // 2, a.hyp - a.hyp // 2
-    params = capi.default_params(neighborRadius=a.radius, voxelGridLeafSize=a.leaf, ransacThreshold=TAU)
+    params = capi.default_params(neighborRadius=a.radius, voxelGridLeafSize=a.leaf, ransacThreshold=TAU, refitIterations=a.refit_iters)
     stream = torch.cuda.current_stream()
 
     # ---- synthetic ring of scans: distinct per slot and per rank (frame-parallel = weak scaling)

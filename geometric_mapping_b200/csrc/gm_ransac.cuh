@@ -596,7 +596,7 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
           for (int k = 0; k < 3; ++k) it_dir[k] = dir[k] / dl;
           it_r += x[4];
           // converged (same rule as the oracle): skip the remaining update passes
-          if (x[0] * x[0] + x[1] * x[1] + x[4] * x[4] < 1e-16 && x[2] * x[2] + x[3] * x[3] < 1e-16) s_converged = 1;
+          if (x[0] * x[0] + x[1] * x[1] + x[4] * x[4] < 1e-10 && x[2] * x[2] + x[3] * x[3] < 1e-10) s_converged = 1;
         }
       }
       if (!update && blockIdx.x == 0 && cnt > 5) {

@@ -171,19 +171,33 @@ __device__ __forceinline__ int2 cell_run(const unsigned* __restrict__ ucell_key,
 }
 
 // For every occupied cell: the 9 sorted-position runs (one per (dy,dz) row, x-1..x+1) that cover
-// its 27-cell neighbourhood.
+// its 27-cell neighbourhood.  The cell's own row needs no search (its neighbours in x are the
+// adjacent entries of the sorted cell list); every other row takes ONE binary search for the first
+// cell >= (x-1) and a walk over at most 3 entries for the end of the run.
 __global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
                             const DevState* __restrict__ st, GridSpec g, int2* __restrict__ runs) {
   const int U = st->n_cells, nf = st->n_sorted_finite;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < U * 9; t += gridDim.x * blockDim.x) {
-    int j = t / 9, k = t - j * 9;
-    unsigned key = ucell_key[j];
+    const int j = t / 9, k = t - j * 9;
+    const unsigned key = ucell_key[j];
     int2 r = make_int2(0, 0);
     if (key < g.ncells) {
-      int cx = (int)(key % (unsigned)g.dim);
-      int cy = (int)((key / (unsigned)g.dim) % (unsigned)g.dim);
-      int cz = (int)(key / ((unsigned)g.dim * (unsigned)g.dim));
-      r = cell_run(ucell_key, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (k % 3) - 1, cz + (k / 3) - 1);
+      const int cx = (int)(key % (unsigned)g.dim);
+      const int cy = (int)((key / (unsigned)g.dim) % (unsigned)g.dim) + (k % 3) - 1;
+      const int cz = (int)(key / ((unsigned)g.dim * (unsigned)g.dim)) + (k / 3) - 1;
+      if (cy >= 0 && cz >= 0 && cy < g.dim && cz < g.dim) {
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim - 1);
+        const unsigned rowbase = (unsigned)g.dim * ((unsigned)cy + (unsigned)g.dim * (unsigned)cz);
+        const unsigned klo = rowbase + (unsigned)x0, khi = rowbase + (unsigned)x1;
+        int a;
+        if (k == 4) a = (j > 0 && ucell_key[j - 1] >= klo) ? j - 1 : j;  // own row: previous entry is x-1 or another row
+        else a = lower_bound_u32(ucell_key, U, klo);
+        int b2 = a;
+        while (b2 < U && b2 < a + 3 && ucell_key[b2] <= khi) ++b2;       // at most 3 cells in the run
+        const int s0 = (a < U) ? min(ucell_start[a], nf) : nf;
+        const int e0 = (b2 < U) ? min(ucell_start[b2], nf) : nf;
+        r = make_int2(s0, e0);
+      }
     }
     runs[t] = r;
   }

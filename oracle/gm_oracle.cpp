@@ -790,7 +790,7 @@ bool solve5(double A[5][5], double b[5], double x[5]) {
 }  // namespace
 
 // Cylinder refit: at most `iters` Gauss-Newton steps (early exit once the step is below
-// 1e-8) on sum (dist_i - r)^2 over the
+// 1e-5) on sum (dist_i - r)^2 over the
 // FIXED inlier set of the input hypothesis (test12_in).  Local parametrisation per step:
 // q += al*u + be*w, dir += ga*u + de*w (renormalised), r += dr with (u,w) = perp_basis(dir).
 // All arithmetic in double on the float points.  Returns the inlier count; also the final RMS.
@@ -830,8 +830,9 @@ GMO_API int64_t gmo_refit_cylinder(const float* pts4, int64_t n, const float* mo
     double dl = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
     for (int k = 0; k < 3; ++k) dir[k] /= dl;
     r += x[4];
-    // converged: position/radius step below 1e-8 m and direction step below 1e-8 rad
-    if (x[0] * x[0] + x[1] * x[1] + x[4] * x[4] < 1e-16 && x[2] * x[2] + x[3] * x[3] < 1e-16) break;
+    // converged: position/radius step below 1e-5 m and direction step below 1e-5 rad (the next step is then ~1e-7,
+    // below the float resolution of the published coefficients)
+    if (x[0] * x[0] + x[1] * x[1] + x[4] * x[4] < 1e-10 && x[2] * x[2] + x[3] * x[3] < 1e-10) break;
   }
   double ss = 0.0;
   {

@@ -1,4 +1,7 @@
-// Where do the ~20 us of the 1M-point stream-compaction kernels go?  Times k_crop (the product
+// Where do the ~20 us of the 1M-point stream-compaction kernels go?  (Result, B200: publishing the tile
+// state with a plain st.relaxed.gpu made the look-back ~1 us per round; atomicExch publishes cut the
+// kernel from 18 to 12 us, and every cudaMemsetAsync of the state array cost another ~4.8 us, hence
+// the epoch-tagged states of gm_device.cuh.  ld.cg spinning never observed the update at all.)  Times k_crop (the product
 // kernel, decoupled look-back) against (a) a plain float4 copy with the same tiling and (b) the
 // same kernel with the look-back replaced by one atomicAdd per tile (unordered output; timing only).
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -I../../geometric_mapping_b200/csrc -o compact_variants compact_variants.cu
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(CP_BLOCK) k_crop_atomic(const float4* __restri
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __global__ void __launch_bounds__(CP_BLOCK, 4)
 k_crop_timed(const float4* __restrict__ in, int n, float lo, float hi, float4* __restrict__ out, unsigned long long* state, DevState* st,
-             unsigned long long* ts /* 6 per tile */) {
+             unsigned epoch, unsigned long long* ts /* 6 per tile */) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int tile = blockIdx.x, base = tile * CPL_TILE;
   unsigned long long t0 = gtime();
@@ -75,11 +78,11 @@ k_crop_timed(const float4* __restrict__ in, int n, float lo, float hi, float4* _
       carry += __shfl_sync(FULL, inc, 31);
     }
     unsigned tile_total = carry;
-    if (lane_id() == 0) ts_store(state + tile, tile == 0 ? TS_PREFIX : TS_AGG, tile_total);
+    if (lane_id() == 0) ts_store(state + tile, epoch, tile == 0 ? TS_PREFIX : TS_AGG, tile_total);
     t2 = gtime();
-    unsigned excl = lookback_exclusive(state, tile, &st->error);
+    unsigned excl = lookback_exclusive(state, epoch, tile, &st->error);
     t3 = gtime();
-    if (lane_id() == 0) { if (tile != 0) ts_store(state + tile, TS_PREFIX, excl + tile_total); sm.tile_excl = excl; sm.tile_total = tile_total; }
+    if (lane_id() == 0) { if (tile != 0) ts_store(state + tile, epoch, TS_PREFIX, excl + tile_total); sm.tile_excl = excl; sm.tile_total = tile_total; }
   }
   __syncthreads();
   const unsigned excl = sm.tile_excl;
@@ -96,7 +99,7 @@ int main() {
   srand(1);
   for (auto& p : h) p = make_float4(rand() % 1100 / 100.f - 5.5f, rand() % 500 / 100.f - 2.5f, rand() % 500 / 100.f - 2.5f, 1.f);
   float4 *d_in, *d_out; unsigned long long* d_state; DevState* d_st; unsigned* d_cnt;
-  cudaMalloc(&d_in, n * 16); cudaMalloc(&d_out, n * 16); cudaMalloc(&d_state, 8 * 4096); cudaMalloc(&d_st, sizeof(DevState)); cudaMalloc(&d_cnt, 4);
+  cudaMalloc(&d_in, n * 16); cudaMalloc(&d_out, n * 16); cudaMalloc(&d_state, 8 * 4096); cudaMemset(d_state, 0, 8 * 4096); cudaMalloc(&d_st, sizeof(DevState)); cudaMalloc(&d_cnt, 4);
   cudaMemcpy(d_in, h.data(), n * 16, cudaMemcpyHostToDevice);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto time = [&](const char* name, auto&& launch) {
@@ -109,13 +112,14 @@ int main() {
   time("copy IPT=4 (977 blocks)", [&] { k_copy<4><<<(n + 1023) / 1024, 256>>>(d_in, n, d_out); });
   time("copy IPT=8 (489 blocks)", [&] { k_copy<8><<<(n + 2047) / 2048, 256>>>(d_in, n, d_out); });
   time("memset state only", [&] { cudaMemsetAsync(d_state, 0, 8 * 1024); });
-  time("k_crop look-back (product, memset + kernel)", [&] { cudaMemsetAsync(d_state, 0, 8 * 1024); k_crop<<<(n + CPL_TILE - 1) / CPL_TILE, CP_BLOCK>>>(d_in, n, -5.f, 5.f, 1, d_out, d_state, d_st); });
+  unsigned epoch = 0;
+  time("k_crop look-back (product, epoch-tagged)", [&] { k_crop<<<(n + CPL_TILE - 1) / CPL_TILE, CP_BLOCK>>>(d_in, n, -5.f, 5.f, 1, d_out, d_state, ++epoch, d_st); });
   time("k_crop atomic IPT=8 (memset + kernel)", [&] { cudaMemsetAsync(d_cnt, 0, 4); k_crop_atomic<8><<<(n + 2047) / 2048, 256>>>(d_in, n, -5.f, 5.f, d_out, d_cnt); });
   time("k_crop atomic IPT=4 (memset + kernel)", [&] { cudaMemsetAsync(d_cnt, 0, 4); k_crop_atomic<4><<<(n + 1023) / 1024, 256>>>(d_in, n, -5.f, 5.f, d_out, d_cnt); });
   {
     int tiles = (n + CPL_TILE - 1) / CPL_TILE;
     unsigned long long* d_ts; cudaMalloc(&d_ts, tiles * 6 * 8);
-    for (int rep = 0; rep < 3; ++rep) { cudaMemsetAsync(d_state, 0, 8 * 1024); k_crop_timed<<<tiles, CP_BLOCK>>>(d_in, n, -5.f, 5.f, d_out, d_state, d_st, d_ts); }
+    for (int rep = 0; rep < 3; ++rep) k_crop_timed<<<tiles, CP_BLOCK>>>(d_in, n, -5.f, 5.f, d_out, d_state, d_st, ++epoch, d_ts);
     cudaDeviceSynchronize();
     std::vector<unsigned long long> ts(tiles * 6);
     cudaMemcpy(ts.data(), d_ts, tiles * 6 * 8, cudaMemcpyDeviceToHost);

@@ -15,7 +15,7 @@ __device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
-enum { V_SCALAR_C = 0, V_SCALAR_PRED = 1, V_F2_PRED = 2, V_F2_SEL = 3, V_F2_SIGN = 4, V_SCALAR_SIGN = 5 };
+enum { V_SCALAR_C = 0, V_SCALAR_PRED = 1, V_F2_PRED = 2, V_F2_SEL = 3, V_F2_SIGN = 4, V_SCALAR_SIGN = 5, V_F2_SIGN2 = 6 };
 
 __device__ __forceinline__ void count_pred(float d, float tau, int& cnt) {
   asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(cnt) : "f"(fabsf(d)), "f"(tau));
@@ -71,7 +71,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_count(const float4* __restrict_
           const u64 A = pack2(c[k].x, c[k].x), B = pack2(c[k].y, c[k].y), Cz = pack2(c[k].z, c[k].z), D = pack2(c[k].w, c[k].w);
           u64 t0 = fma2(A, x01, fma2(B, y01, fma2(Cz, z01, D)));
           u64 t1 = fma2(A, x23, fma2(B, y23, fma2(Cz, z23, D)));
-          if (V == V_F2_SIGN) {
+          if (V == V_F2_SIGN2) {
+            // e = d*d - tau^2 : sign bit set <=> inlier; cnt += sign bit (one shift-add per value)
+            const u64 NT2 = pack2(-tau2, -tau2);
+            u64 e0 = fma2(t0, t0, NT2), e1 = fma2(t1, t1, NT2);
+            float a0, a1, a2, a3; unpack2(e0, a0, a1); unpack2(e1, a2, a3);
+            cnt[k] += (int)(__float_as_uint(a0) >> 31) + (int)(__float_as_uint(a1) >> 31);
+            cnt[k] += (int)(__float_as_uint(a2) >> 31) + (int)(__float_as_uint(a3) >> 31);
+          } else if (V == V_F2_SIGN) {
             const u64 T2 = pack2(tau2, tau2);
             u64 e0 = fma2(t0 ^ 0x8000000080000000ull, t0, T2), e1 = fma2(t1 ^ 0x8000000080000000ull, t1, T2);
             float a0, a1, a2, a3; unpack2(e0, a0, a1); unpack2(e1, a2, a3);
@@ -152,7 +159,7 @@ int main(int argc, char** argv) {
     int bad = 0; for (int h = 0; h < H; ++h) bad += (got[h] != ref[h]);                            \
     printf("V=%d K=%2d minb=%2d occ=%2d blk/SM grid=%4dx%d (%2d/SM)  %.4f ms  %.2f TFLOP/s  %.1f%%  mism=%d\n", V, K, MINB, nb, SL, groups, MULT, ms, flop / ms / 1e9, 100.0 * flop / (ms * 1e-3) / peak, bad); \
   }
-  RUN(2, 8, 1, 6) RUN(2, 8, 1, 8) RUN(2, 8, 1, 10) RUN(2, 8, 1, 12) RUN(2, 8, 1, 14) RUN(2, 8, 1, 28)
+  RUN(2, 8, 1, 8) RUN(2, 8, 1, 12) RUN(6, 8, 1, 8) RUN(6, 8, 1, 12) RUN(6, 4, 1, 12) RUN(6, 16, 1, 8)
   RUN(2, 8, 16, 8) RUN(2, 8, 16, 12) RUN(2, 8, 16, 16) RUN(2, 8, 16, 32)
   RUN(2, 4, 1, 8) RUN(2, 4, 1, 16) RUN(2, 4, 24, 24) RUN(2, 4, 1, 32) RUN(2, 4, 1, 48)
   RUN(2, 16, 1, 4) RUN(2, 16, 1, 6) RUN(2, 16, 1, 8)

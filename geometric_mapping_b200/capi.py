@@ -73,6 +73,15 @@ class gm_slice(C.Structure):
                 ("t_mid", C.c_float), ("count", C.c_int32)]
 
 
+class gm_compression(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("n_plane", C.c_int32), ("n_cylinder", C.c_int32), ("n_residual", C.c_int32),
+                ("n_residual_voxels", C.c_int32), ("n_slices", C.c_int32), ("plane_coef", C.c_float * 4),
+                ("plane_u", C.c_float * 3), ("plane_v", C.c_float * 3), ("plane_bounds", C.c_float * 4), ("plane_rms", C.c_float),
+                ("cyl_coef", C.c_float * 7), ("cyl_t_range", C.c_float * 2), ("cyl_rms", C.c_float), ("residual_rms", C.c_float),
+                ("total_rms", C.c_float), ("leaf", C.c_float), ("ratio", C.c_float), ("bytes_in", C.c_uint64),
+                ("bytes_out", C.c_uint64)]
+
+
 class gm_scan_summary(C.Structure):
     _fields_ = [("counts", gm_counts), ("frame", gm_frame), ("plane", gm_model), ("cylinder", gm_model),
                 ("n_slices", C.c_int32), ("pad_", C.c_int32)]
@@ -112,7 +121,8 @@ SYMBOLS = [
     "gm_download_valid_map", "gm_download_voxel_assignment", "gm_download_voxels", "gm_get_voxel_grid",
     "gm_get_frame", "gm_download_hypotheses", "gm_get_model", "gm_download_labels", "gm_download_polyline",
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
-    "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read",
+    "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
+    "gm_download_compressed",
 ]
 
 
@@ -174,6 +184,9 @@ def _lib():
         "gm_profile_num_segments": (i32, []),
         "gm_profile_segment_name": (C.c_char_p, [i32]),
         "gm_profile_read": (i32, [vp, vp, vp]),
+        "gm_compress": (i32, [vp]),
+        "gm_get_compression": (i32, [vp, C.POINTER(gm_compression)]),
+        "gm_download_compressed": (i32, [vp, vp, sz, C.POINTER(sz)]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -421,6 +434,27 @@ def _ctx_profile_read(self) -> dict:
     return {_lib().gm_profile_segment_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(k)}
 
 
+def _ctx_compress(self):
+    self._ck(_lib().gm_compress(self._h), "gm_compress")
+
+
+def _ctx_compression(self) -> gm_compression:
+    c = gm_compression()
+    self._ck(_lib().gm_get_compression(self._h, C.byref(c)), "gm_get_compression")
+    return c
+
+
+def _ctx_download_compressed(self) -> bytes:
+    n = C.c_size_t(0)
+    self._ck(_lib().gm_download_compressed(self._h, None, 0, C.byref(n)), "gm_download_compressed")
+    buf = np.empty(n.value, np.uint8)
+    self._ck(_lib().gm_download_compressed(self._h, _ptr(buf), buf.shape[0], C.byref(n)), "gm_download_compressed")
+    return buf.tobytes()
+
+
+Context.compress = _ctx_compress
+Context.compression = _ctx_compression
+Context.download_compressed = _ctx_download_compressed
 Context.fetch_async = _ctx_fetch_async
 Context.profile_enable = _ctx_profile_enable
 Context.profile_read = _ctx_profile_read

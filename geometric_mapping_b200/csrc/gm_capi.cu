@@ -4,6 +4,7 @@
 #include "../../include/gm_capi.h"
 #include "gm_ransac.cuh"
 #include "gm_polyline.cuh"
+#include "gm_compress.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -45,7 +46,7 @@ __global__ void k_pack_summary(const DevState* st, const FrameOut* fr, const Mod
                                int have_mask, SummaryDev* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   out->counts.n_input = st->n_input; out->counts.n_cropped = st->n_crop; out->counts.n_valid = st->n_valid;
-  out->counts.n_voxels = st->n_voxels; out->counts.n_cells = st->n_cells; out->counts.voxel_overflow = st->voxel_overflow;
+  out->counts.n_voxels = st->vox.n_voxels; out->counts.n_cells = st->n_cells; out->counts.voxel_overflow = st->vox.overflow;
   out->counts.nn_out_of_range = st->nn_oor; out->counts.device_error = st->error;
   for (int k = 0; k < 3; ++k) out->frame.vals[k] = fr->vals[k];
   for (int k = 0; k < 9; ++k) { out->frame.vecs[k] = fr->vecs[k]; out->frame.scatter[k] = fr->scatter[k]; }
@@ -120,6 +121,14 @@ struct gm_ctx {
   unsigned long long* d_poly_part = nullptr;  // per-block (min,max) of the polyline range pass
   gm_slice* d_slices = nullptr;
   SummaryDev* d_summary = nullptr;
+  // compression stage: residual (label 0) cloud and its voxel grid
+  VoxState* d_res_vs = nullptr;
+  CompStats* d_comp = nullptr;
+  float4 *d_res_pts = nullptr, *d_res_centroid = nullptr;
+  int *d_res_key_pt = nullptr, *d_res_assign = nullptr, *d_res_vox_start = nullptr, *d_res_vox_key = nullptr, *d_res_vox_count = nullptr;
+  double* d_comp_part = nullptr;
+  unsigned long long* d_comp_mm = nullptr;
+  bool have_comp = false;
   unsigned* d_counters = nullptr;  // last-block tickets: [0] frame, [1] plane refit, [2] cylinder GN
   float4* d_inl = nullptr;          // compacted cylinder inliers
   // profiling
@@ -335,7 +344,8 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_plane_coef, H); A(d_model7, 7 * H); A(d_test12, 12 * H);
   A(d_hvalid[0], H); A(d_hvalid[1], H); A(d_counts[0], H); A(d_counts[1], H);
   A(d_key, 2); A(d_model, 2);
-  A(d_poly, 1); A(d_summary, 1); A(d_counters, 16); A(d_poly_part, 2 * 4096); A(d_inl, N); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
+  A(d_poly, 1); A(d_summary, 1); A(d_res_vs, 1); A(d_comp, 1); A(d_res_pts, N); A(d_res_centroid, N); A(d_res_key_pt, N); A(d_res_assign, N);
+  A(d_res_vox_start, N + 1); A(d_res_vox_key, N); A(d_res_vox_count, N); A(d_comp_part, (size_t)CS_NV * (div_up((long long)N, CP_TILE) + 1) + 1024); A(d_comp_mm, (size_t)6 * (div_up((long long)N, CP_TILE) + 1)); A(d_counters, 16); A(d_poly_part, 2 * 4096); A(d_inl, N); A(d_poly_acc, (size_t)POLY_NACC * (size_t)std::max(p->maxSlices, 1)); A(d_slices, (size_t)std::max(p->maxSlices, 1));
 #undef A
   if ((e = cudaMallocHost((void**)&ctx->h_samples[0], 3 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples0");
   if ((e = cudaMallocHost((void**)&ctx->h_samples[1], 2 * H * sizeof(int))) != cudaSuccess) return fail(e, "h_samples1");
@@ -375,7 +385,8 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
-                  ctx->d_poly_acc, ctx->d_slices, ctx->d_summary, ctx->d_counters, ctx->d_inl, ctx->d_poly_part};
+                  ctx->d_res_vs, ctx->d_comp, ctx->d_res_pts, ctx->d_res_centroid, ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start,
+                  ctx->d_res_vox_key, ctx->d_res_vox_count, ctx->d_comp_part, ctx->d_comp_mm, ctx->d_poly_acc, ctx->d_slices, ctx->d_summary, ctx->d_counters, ctx->d_inl, ctx->d_poly_part};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 2; ++k) {
     if (ctx->h_samples[k]) cudaFreeHost(ctx->h_samples[k]);
@@ -415,7 +426,7 @@ gm_status gm_synchronize(gm_ctx* ctx) {
 
 static void clear_stages(gm_ctx* ctx) {
   ctx->have_crop = ctx->have_normals = ctx->have_compacted = ctx->injected = false;
-  ctx->have_voxel = ctx->have_frame = ctx->have_labels = ctx->have_poly = false;
+  ctx->have_voxel = ctx->have_frame = ctx->have_labels = ctx->have_poly = ctx->have_comp = false;
   ctx->have_ransac[0] = ctx->have_ransac[1] = ctx->have_model[0] = ctx->have_model[1] = false;
 }
 
@@ -511,36 +522,54 @@ gm_status gm_normals(gm_ctx* ctx) {
 }
 
 // ---- a4 --------------------------------------------------------------------------------------
+namespace {
+struct VoxBuffers { int *key_pt, *assign, *vox_start, *vox_key, *vox_count; float4* centroid; };
+
+// pcl::VoxelGrid of `pts` (vs->n points, bbox already in vs): keys -> sort -> heads -> centroids.
+gm_status voxel_downsample(gm_ctx* ctx, const float4* pts, VoxState* vs, size_t n_cap, int key_bits, const VoxBuffers& o, int* sorted_buf) {
+  const float leaf_f = (float)ctx->prm.voxelGridLeafSize;
+  const float inv = 1.0f / leaf_f;
+  int blocks = std::min(div_up((long long)n_cap, 256), ctx->num_sms * 16);
+  { SegTimer seg_(ctx, SEG_VOX_KEYS);
+    GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, pts, vs, inv, ctx->d_keys[0], ctx->d_vals[0], o.key_pt); }
+  int buf = 0;
+  gm_status s;
+  { SegTimer seg_(ctx, SEG_VOX_SORT);
+    s = radix_sort(ctx, &vs->n, n_cap, key_bits, &buf); }
+  if (s != GM_OK) return s;
+  unsigned epoch = 0;
+  if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
+  { SegTimer seg_(ctx, SEG_VOX_REDUCE);
+    GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n_cap, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], o.assign, o.vox_start, o.vox_key,
+              ctx->d_state64, epoch, vs, &ctx->d_st->error);
+    GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n_cap * 32, VC_BLOCK), ctx->num_sms * 16), VC_BLOCK, ctx->d_vals[buf], pts,
+              o.vox_start, vs, o.centroid, o.vox_count); }
+  *sorted_buf = buf;
+  GM_CHECK_LAUNCHES(ctx);
+  return GM_OK;
+}
+
+// static upper bound of the voxel key range from the crop box (no host round trip for the bbox)
+int voxel_key_bits(const gm_ctx* ctx, size_t n) {
+  if (ctx->injected) return 32;
+  const float inv = 1.0f / (float)ctx->prm.voxelGridLeafSize;
+  double b = std::fabs(ctx->prm.boxFilterBound) * (double)inv;
+  double div = std::floor(b) - std::floor(-b) + 2.0;
+  double total = div * div * div;
+  if (total < 2147483647.0 && (double)n < 2147483647.0) return bits_for((unsigned long long)total);
+  return 32;
+}
+}  // namespace
+
 gm_status gm_voxel(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
-  const size_t n = ctx->injected ? (size_t)ctx->n_input : ctx->n_input;
+  const size_t n = ctx->n_input;
   if (n) {
-    const float leaf_f = (float)ctx->prm.voxelGridLeafSize;
-    const float inv = 1.0f / leaf_f;
-    int blocks = std::min(div_up((long long)n, 256), ctx->num_sms * 16);
-    { SegTimer seg_(ctx, SEG_VOX_KEYS);
-      GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, ctx->d_cloud_c, ctx->d_st, inv, ctx->d_keys[0], ctx->d_vals[0], ctx->d_vkey_pt); }
-    // static upper bound of the key range from the crop box (no host round trip for the bbox)
-    int key_bits = 32;
-    if (!ctx->injected) {
-      double b = std::fabs(ctx->prm.boxFilterBound) * (double)inv;
-      double div = std::floor(b) - std::floor(-b) + 2.0;
-      double total = div * div * div;
-      if (total < 2147483647.0 && (double)n < 2147483647.0) key_bits = bits_for((unsigned long long)total);
-    }
+    VoxBuffers o{ctx->d_vkey_pt, ctx->d_assign, ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_centroid};
     int buf = 0;
-    gm_status s;
-    { SegTimer seg_(ctx, SEG_VOX_SORT);
-      s = radix_sort(ctx, &ctx->d_st->n_valid, n, key_bits, &buf); }
+    gm_status s = voxel_downsample(ctx, ctx->d_cloud_c, &ctx->d_st->vox, n, voxel_key_bits(ctx, n), o, &buf);
     if (s != GM_OK) return s;
-    unsigned epoch = 0;
-    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
-    { SegTimer seg_(ctx, SEG_VOX_REDUCE);
-    GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_assign,
-              ctx->d_vox_start, ctx->d_vox_key, ctx->d_state64, epoch, ctx->d_st);
-    GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n * 32, VC_BLOCK), ctx->num_sms * 16), VC_BLOCK, ctx->d_vals[buf], ctx->d_cloud_c,
-              ctx->d_vox_start, ctx->d_st, ctx->d_centroid, ctx->d_vox_count); }
     if (ctx->have_normals) {
       SegTimer seg_(ctx, SEG_VOX_NN);
       GM_LAUNCH(ctx, k_voxel_nn, std::min(div_up((long long)n * 32, NN_BLOCK), ctx->num_sms * 16), NN_BLOCK, ctx->d_centroid, ctx->d_sorted,
@@ -704,6 +733,83 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   return GM_OK;
 }
 
+gm_status gm_compress(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_labels || !ctx->have_poly) return GM_ERR_STAGE_ORDER;
+  const size_t n = std::max<size_t>(ctx->n_input, 1);
+  unsigned epoch = 0;
+  gm_status s = next_epoch(ctx, &epoch);
+  if (s != GM_OK) return s;
+  GM_LAUNCH(ctx, k_vox_reset, 1, 32, ctx->d_res_vs);
+  const int tiles = div_up((long long)n, CP_TILE);
+  GM_LAUNCH(ctx, k_comp_split, tiles, CP_BLOCK, ctx->d_cloud_c, ctx->d_labels, &ctx->d_st->n_valid, ctx->d_model + 0, ctx->d_model + 1,
+            ctx->have_model[0] ? 1 : 0, ctx->have_model[1] ? 1 : 0, ctx->d_res_pts, ctx->d_res_vs, ctx->d_state64, epoch, &ctx->d_st->error,
+            ctx->d_comp_part, ctx->d_comp_mm, ctx->d_counters + 12, ctx->d_comp);
+  VoxBuffers o{ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start, ctx->d_res_vox_key, ctx->d_res_vox_count, ctx->d_res_centroid};
+  int buf = 0;
+  if ((s = voxel_downsample(ctx, ctx->d_res_pts, ctx->d_res_vs, n, voxel_key_bits(ctx, n), o, &buf)) != GM_OK) return s;
+  GM_LAUNCH(ctx, k_comp_residual_error, ctx->num_sms * 2, CR_BLOCK, ctx->d_res_pts, ctx->d_res_assign, ctx->d_res_centroid, ctx->d_res_vs,
+            ctx->d_comp_part, ctx->d_counters + 13, ctx->d_comp);
+  GM_CHECK_LAUNCHES(ctx);
+  ctx->have_comp = true;
+  return GM_OK;
+}
+
+namespace {
+gm_status fetch_compression(gm_ctx* ctx, gm_compression* out, VoxState* vs_host) {
+  CompStats c;
+  PolyState ps;
+  GM_CUDA(cudaMemcpyAsync(&c, ctx->d_comp, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(vs_host, ctx->d_res_vs, sizeof(VoxState), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(&ps, ctx->d_poly, sizeof(ps), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memset(out, 0, sizeof(*out));
+  out->n_points = c.n_points; out->n_plane = c.n_plane; out->n_cylinder = c.n_cyl; out->n_residual = c.n_residual;
+  out->n_residual_voxels = vs_host->n_voxels; out->n_slices = ps.S;
+  std::memcpy(out->plane_coef, c.plane_coef, sizeof(out->plane_coef));
+  std::memcpy(out->plane_u, c.plane_u, sizeof(out->plane_u));
+  std::memcpy(out->plane_v, c.plane_v, sizeof(out->plane_v));
+  std::memcpy(out->plane_bounds, c.plane_bounds, sizeof(out->plane_bounds));
+  out->plane_rms = c.plane_rms;
+  std::memcpy(out->cyl_coef, c.cyl_coef, sizeof(out->cyl_coef));
+  std::memcpy(out->cyl_t_range, c.cyl_t_range, sizeof(out->cyl_t_range));
+  out->cyl_rms = c.cyl_rms; out->residual_rms = c.residual_rms; out->total_rms = c.total_rms;
+  out->leaf = (float)ctx->prm.voxelGridLeafSize;
+  out->bytes_in = 16ull * (uint64_t)std::max(c.n_points, 0);
+  out->bytes_out = 8 + sizeof(gm_compression) + (uint64_t)std::max(ps.S, 0) * sizeof(gm_slice) + 12ull * (uint64_t)std::max(vs_host->n_voxels, 0);
+  out->ratio = out->bytes_out ? (float)((double)out->bytes_in / (double)out->bytes_out) : 0.f;
+  return GM_OK;
+}
+}  // namespace
+
+gm_status gm_get_compression(gm_ctx* ctx, gm_compression* out) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_comp) return GM_ERR_STAGE_ORDER;
+  VoxState vs;
+  return fetch_compression(ctx, out, &vs);
+}
+
+gm_status gm_download_compressed(gm_ctx* ctx, void* buf, size_t capacity, size_t* bytes) {
+  if (!ctx || !bytes) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_comp) return GM_ERR_STAGE_ORDER;
+  gm_compression h;
+  VoxState vs;
+  gm_status s = fetch_compression(ctx, &h, &vs);
+  if (s != GM_OK) return s;
+  *bytes = (size_t)h.bytes_out;
+  if (!buf) return GM_OK;
+  if (capacity < h.bytes_out) return GM_ERR_CAPACITY;
+  unsigned char* p = (unsigned char*)buf;
+  const uint32_t magic = 0x31434D47u /* 'GMC1' */, version = 1;
+  std::memcpy(p, &magic, 4); std::memcpy(p + 4, &version, 4); p += 8;
+  std::memcpy(p, &h, sizeof(h)); p += sizeof(h);
+  if (h.n_slices > 0) { GM_CUDA(cudaMemcpyAsync(p, ctx->d_slices, (size_t)h.n_slices * sizeof(gm_slice), cudaMemcpyDeviceToHost, ctx->stream)); p += (size_t)h.n_slices * sizeof(gm_slice); }
+  if (h.n_residual_voxels > 0)  // strided copy: float4 centroids -> packed xyz
+    GM_CUDA(cudaMemcpy2DAsync(p, 12, ctx->d_res_centroid, 16, 12, (size_t)h.n_residual_voxels, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
 }  // extern "C" (templates need C++ linkage)
 
 // Runs `body` with ctx->stream temporarily replaced by branch stream `b` (which first waits for
@@ -769,9 +875,9 @@ gm_status gm_get_counts(gm_ctx* ctx, gm_counts* out) {
   out->n_input = ctx->have_scan ? h.n_input : -1;
   out->n_cropped = ctx->have_crop ? h.n_crop : -1;
   out->n_valid = ctx->have_compacted ? h.n_valid : -1;
-  out->n_voxels = ctx->have_voxel ? h.n_voxels : -1;
+  out->n_voxels = ctx->have_voxel ? h.vox.n_voxels : -1;
   out->n_cells = ctx->have_normals ? h.n_cells : -1;
-  out->voxel_overflow = h.voxel_overflow;
+  out->voxel_overflow = h.vox.overflow;
   out->nn_out_of_range = h.nn_oor;
   out->device_error = h.error;
   if (h.error) { ctx->err = "device-side look-back spin bound hit"; return GM_ERR_INTERNAL; }
@@ -843,7 +949,7 @@ gm_status gm_download_voxel_assignment(gm_ctx* ctx, int32_t* keys, int32_t* assi
   if (keys) GM_D2H(keys, ctx->d_vkey_pt, (size_t)h.n_valid * 4);
   if (assign) GM_D2H(assign, ctx->d_assign, (size_t)h.n_valid * 4);
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
-  return h.voxel_overflow ? GM_WARN_VOXEL_OVERFLOW : GM_OK;
+  return h.vox.overflow ? GM_WARN_VOXEL_OVERFLOW : GM_OK;
 }
 
 gm_status gm_download_voxels(gm_ctx* ctx, float* centroids, int32_t* keys, int32_t* counts, int32_t* nn_index, float* nn_normal8,
@@ -853,7 +959,7 @@ gm_status gm_download_voxels(gm_ctx* ctx, float* centroids, int32_t* keys, int32
   DevState h;
   gm_status s = sync_state(ctx, &h);
   if (s != GM_OK) return s;
-  size_t V = (size_t)h.n_voxels;
+  size_t V = (size_t)h.vox.n_voxels;
   if (V > capacity_voxels) return GM_ERR_CAPACITY;
   if (centroids) GM_D2H(centroids, ctx->d_centroid, V * 16);
   if (keys) GM_D2H(keys, ctx->d_vox_key, V * 4);
@@ -862,7 +968,7 @@ gm_status gm_download_voxels(gm_ctx* ctx, float* centroids, int32_t* keys, int32
   if (nn_index) GM_D2H(nn_index, ctx->d_nn_idx, V * 4);
   if (nn_normal8) GM_D2H(nn_normal8, ctx->d_nn_normal, V * 32);
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h.voxel_overflow) return GM_WARN_VOXEL_OVERFLOW;
+  if (h.vox.overflow) return GM_WARN_VOXEL_OVERFLOW;
   if (h.nn_oor && ctx->have_normals) return GM_ERR_NN_INDEX_RANGE;
   return GM_OK;
 }
@@ -873,7 +979,7 @@ gm_status gm_get_voxel_grid(gm_ctx* ctx, int32_t grid6[6]) {
   DevState h;
   gm_status s = sync_state(ctx, &h);
   if (s != GM_OK) return s;
-  for (int a = 0; a < 3; ++a) { grid6[a] = h.min_b[a]; grid6[3 + a] = h.div_b[a]; }
+  for (int a = 0; a < 3; ++a) { grid6[a] = h.vox.min_b[a]; grid6[3 + a] = h.vox.div_b[a]; }
   return GM_OK;
 }
 
@@ -1004,8 +1110,9 @@ gm_status gm_inject_compacted(gm_ctx* ctx, const float* xyzw_host, const float* 
   int nn = (int)n;
   GM_CUDA(cudaMemcpyAsync(&ctx->d_st->n_valid, &nn, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   GM_CUDA(cudaMemcpyAsync(&ctx->d_st->n_crop, &nn, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(&ctx->d_st->vox.n, &nn, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   GM_CUDA(cudaStreamSynchronize(ctx->stream));  // nn is a stack variable
-  if (n) GM_LAUNCH(ctx, k_bbox, std::min(div_up((long long)n, 256), ctx->num_sms * 8), 256, ctx->d_cloud_c, &ctx->d_st->n_valid, ctx->d_st);
+  if (n) GM_LAUNCH(ctx, k_bbox, std::min(div_up((long long)n, 256), ctx->num_sms * 8), 256, ctx->d_cloud_c, &ctx->d_st->vox);
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_compacted = true;
   ctx->injected = true;

@@ -9,12 +9,27 @@
 namespace gm {
 
 // Device-resident per-scan state: sizes flow from stage to stage without host round trips.
-struct DevState {
-  int n_input, n_crop, n_valid, n_voxels, n_cells, voxel_overflow, nn_oor, error;
-  int bbox_min[3], bbox_max[3];  // ordered-int encoded floats (compacted cloud)
+// State of one VoxelGrid run (the compacted cloud, or the residual cloud of the compression stage).
+struct VoxState {
+  int n, n_voxels, overflow, pad_;
+  int bbox_min[3], bbox_max[3];  // ordered-int encoded floats
   int min_b[3], div_b[3], mul[3];
   float v_inv;
+};
+__device__ __forceinline__ void d_vox_reset(VoxState* v) {
+  v->n = 0; v->n_voxels = 0; v->overflow = 0; v->pad_ = 0; v->v_inv = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    v->bbox_min[a] = float_to_ordered(CUDART_INF_F);
+    v->bbox_max[a] = float_to_ordered(-CUDART_INF_F);
+    v->min_b[a] = 0; v->div_b[a] = 0; v->mul[a] = 0;
+  }
+}
+
+struct DevState {
+  int n_input, n_crop, n_valid, n_cells, nn_oor, error;
   int n_sorted_finite;  // cropped points with finite coordinates (sorted before the NaN tail)
+  int pad_;
+  VoxState vox;         // VoxelGrid of the compacted cloud (vox.n mirrors n_valid)
 };
 
 struct GridSpec {
@@ -36,14 +51,9 @@ __device__ __forceinline__ bool finite3(float x, float y, float z) { return isfi
 // ---------------------------------------------------------------------------------------------
 __global__ void k_begin_scan(DevState* st, int n_input) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    st->n_input = n_input; st->n_crop = 0; st->n_valid = 0; st->n_voxels = 0; st->n_cells = 0;
-    st->voxel_overflow = 0; st->nn_oor = 0; st->error = 0; st->n_sorted_finite = 0;
-    for (int a = 0; a < 3; ++a) {
-      st->bbox_min[a] = float_to_ordered(CUDART_INF_F);
-      st->bbox_max[a] = float_to_ordered(-CUDART_INF_F);
-      st->min_b[a] = 0; st->div_b[a] = 0; st->mul[a] = 0;
-    }
-    st->v_inv = 0.f;
+    st->n_input = n_input; st->n_crop = 0; st->n_valid = 0; st->n_cells = 0;
+    st->nn_oor = 0; st->error = 0; st->n_sorted_finite = 0; st->pad_ = 0;
+    d_vox_reset(&st->vox);
   }
 }
 
@@ -373,7 +383,7 @@ k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ norma
       }
     }
   }
-  if (base + CP_TILE >= n && threadIdx.x == 0) st->n_valid = (int)total;
+  if (base + CP_TILE >= n && threadIdx.x == 0) { st->n_valid = (int)total; st->vox.n = (int)total; }
   // block bbox -> global (min/max are order independent: deterministic)
   const int w = threadIdx.x >> 5;
 #pragma unroll
@@ -386,15 +396,15 @@ k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ norma
     float lo = CUDART_INF_F, hi = -CUDART_INF_F;
     for (int ww = 0; ww < CP_BLOCK / 32; ++ww) { lo = fminf(lo, s_red[threadIdx.x][ww]); hi = fmaxf(hi, s_red[3 + threadIdx.x][ww]); }
     if (lo <= hi) {
-      atomicMin(&st->bbox_min[threadIdx.x], float_to_ordered(lo));
-      atomicMax(&st->bbox_max[threadIdx.x], float_to_ordered(hi));
+      atomicMin(&st->vox.bbox_min[threadIdx.x], float_to_ordered(lo));
+      atomicMax(&st->vox.bbox_max[threadIdx.x], float_to_ordered(hi));
     }
   }
 }
 
 // Bounding box only (used when the compacted cloud was injected).
-__global__ void k_bbox(const float4* __restrict__ pts, const int* __restrict__ n_ptr, DevState* st) {
-  const int n = *n_ptr;
+__global__ void k_bbox(const float4* __restrict__ pts, VoxState* vs) {
+  const int n = vs->n;
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
@@ -405,8 +415,8 @@ __global__ void k_bbox(const float4* __restrict__ pts, const int* __restrict__ n
   for (int a = 0; a < 3; ++a) {
     float lo = warp_min(mn[a]), hi = warp_max(mx[a]);
     if (lane_id() == 0 && lo <= hi) {
-      atomicMin(&st->bbox_min[a], float_to_ordered(lo));
-      atomicMax(&st->bbox_max[a], float_to_ordered(hi));
+      atomicMin(&vs->bbox_min[a], float_to_ordered(lo));
+      atomicMax(&vs->bbox_max[a], float_to_ordered(hi));
     }
   }
 }
@@ -414,10 +424,10 @@ __global__ void k_bbox(const float4* __restrict__ pts, const int* __restrict__ n
 // a4 pcl::VoxelGrid lattice: min_b, div_b, divb_mul and the overflow rule, derived
 // from the bounding box by every block (cheap, avoids a 1-thread kernel); block 0 publishes it.
 // Voxel key per compacted point: ijk = int(floor(p*inv) - float(min_b)); key = ijk . divb_mul
-__global__ void k_voxel_keys(const float4* __restrict__ pts, DevState* st, float inv,
+__global__ void k_voxel_keys(const float4* __restrict__ pts, VoxState* st, float inv,
                              unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point) {
   __shared__ int s_minb[3], s_mul[3], s_overflow;
-  const int n = st->n_valid;
+  const int n = st->n;
   if (threadIdx.x == 0) {
     float mn[3], mx[3];
     for (int a = 0; a < 3; ++a) { mn[a] = ordered_to_float(st->bbox_min[a]); mx[a] = ordered_to_float(st->bbox_max[a]); }
@@ -437,7 +447,7 @@ __global__ void k_voxel_keys(const float4* __restrict__ pts, DevState* st, float
     s_overflow = overflow;
     if (blockIdx.x == 0) {
       st->v_inv = inv;
-      st->voxel_overflow = overflow;
+      st->overflow = overflow;
       for (int a = 0; a < 3; ++a) { st->min_b[a] = minb[a]; st->div_b[a] = div[a]; st->mul[a] = s_mul[a]; }
     }
   }
@@ -461,9 +471,10 @@ __global__ void k_voxel_keys(const float4* __restrict__ pts, DevState* st, float
 // the voxel rank of every point.
 __global__ void __launch_bounds__(CP_BLOCK)
 k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, int* __restrict__ assign,
-              int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, unsigned epoch, DevState* st) {
+              int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, unsigned epoch, VoxState* st,
+              int* err) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
-  const int n = st->n_valid;
+  const int n = st->n;
   const int tile = blockIdx.x, base = tile * CPL_TILE;
   if (base >= n) return;
   bool f[CPL_IPT];
@@ -478,7 +489,7 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
     }
   }
   unsigned ranks[CPL_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, &st->error, sm);
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, err, sm);
 #pragma unroll
   for (int j = 0; j < CPL_IPT; ++j) {
     int i = base + j * CP_BLOCK + threadIdx.x;
@@ -499,9 +510,9 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
 constexpr int VC_BLOCK = 128;
 __global__ void __launch_bounds__(VC_BLOCK)
 k_voxel_centroids(const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
-                  const int* __restrict__ vox_start, const DevState* __restrict__ st,
+                  const int* __restrict__ vox_start, const VoxState* __restrict__ st,
                   float4* __restrict__ centroids, int* __restrict__ vox_count) {
-  const int V = st->n_voxels, n = st->n_valid;
+  const int V = st->n_voxels, n = st->n;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * VC_BLOCK) >> 5;
   for (int j = (blockIdx.x * VC_BLOCK + threadIdx.x) >> 5; j < V; j += warps_total) {
@@ -553,7 +564,7 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
            const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start, const int2* __restrict__ runs,
            const int* __restrict__ valid_map, const float4* __restrict__ normals_c, GridSpec g,
            int mode, DevState* st, int* __restrict__ nn_idx, float4* __restrict__ nn_normal) {
-  const int V = st->n_voxels, U = st->n_cells, nf = st->n_sorted_finite, nvalid = st->n_valid;
+  const int V = st->vox.n_voxels, U = st->n_cells, nf = st->n_sorted_finite, nvalid = st->n_valid;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * NN_BLOCK) >> 5;
   for (int j = (blockIdx.x * NN_BLOCK + threadIdx.x) >> 5; j < V; j += warps_total) {

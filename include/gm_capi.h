@@ -125,6 +125,25 @@ typedef struct gm_slice {
   int32_t count;
 } gm_slice;
 
+/* Result of the builder-defined compression stage: the segmented cloud represented
+ * by its refined primitives, the polyline and the voxel-downsampled residual (label 0) points. */
+typedef struct gm_compression {
+  int32_t n_points, n_plane, n_cylinder, n_residual, n_residual_voxels, n_slices;
+  float plane_coef[4];    /* refined plane                                              */
+  float plane_u[3], plane_v[3]; /* orthonormal in-plane basis (canonical, from the normal)   */
+  float plane_bounds[4];  /* umin, umax, vmin, vmax of the plane inliers in that basis  */
+  float plane_rms;
+  float cyl_coef[7];      /* refined cylinder {q, dir, r}                               */
+  float cyl_t_range[2];   /* extent of the cylinder inliers along dir, from q           */
+  float cyl_rms;
+  float residual_rms;     /* RMS distance of a residual point to its voxel centroid     */
+  float total_rms;        /* reconstruction RMS over all n_points                        */
+  float leaf;             /* residual voxel size (voxelGridLeafSize)                    */
+  float ratio;            /* bytes_in / bytes_out                                       */
+  uint64_t bytes_in;      /* 16 * n_points                                              */
+  uint64_t bytes_out;     /* size of the blob gm_download_compressed writes             */
+} gm_compression;
+
 /* ---- lifecycle ------------------------------------------------------------------------- */
 GM_API void gm_params_default(gm_params* p);
 GM_API gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypotheses, gm_ctx** out);
@@ -178,6 +197,14 @@ GM_API gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind);
 GM_API gm_status gm_label(gm_ctx* ctx);
 /* Center-axis polyline + cross-sections along the getLocalFrame axis over points with label 2. */
 GM_API gm_status gm_axis_polyline(gm_ctx* ctx);
+
+/* Geometric approximation (compression) of the segmented cloud; needs labels and the polyline.
+ * The name the north-star gives this stage has no counterpart in the reference sources. */
+GM_API gm_status gm_compress(gm_ctx* ctx);
+GM_API gm_status gm_get_compression(gm_ctx* ctx, gm_compression* out);
+/* Packed little-endian blob: 'GMC1' header (gm_compression) | n_slices x gm_slice | n_residual_voxels
+ * x {x,y,z} float.  Pass buf = NULL to query the size. */
+GM_API gm_status gm_download_compressed(gm_ctx* ctx, void* buf, size_t capacity, size_t* bytes);
 
 /* Fused per-scan path = the body of cloud_cb (src/geometric_mapping.cpp:48-125) plus the
  * builder-defined segmentation: crop -> normals -> voxel -> local frame -> RANSAC plane(Hp)

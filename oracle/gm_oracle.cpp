@@ -955,5 +955,69 @@ GMO_API int32_t gmo_polyline(const float* pts4, const float* normals8, const uin
   return S;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// A.10 BUILDER-DEFINED geometric approximation (compression) of the segmented cloud.
+//   plane part:    refined plane, canonical in-plane basis (perp_basis_d of the normal), bounds of
+//                  the label-1 points in that basis, rms of the canonical plane distance
+//   cylinder part: refined cylinder, extent t = dir.(p-q) of the label-2 points, rms of (dist - r)
+//                  with dist = sqrt(A^2+B^2) from the canonical float test parameters
+//   residual:      label-0 points, voxel-downsampled (gmo_voxel) at `leaf`; rms distance of each
+//                  residual point to the centroid of its voxel
+// ints6   : n_points, n_plane, n_cyl, n_residual, n_residual_voxels, (unused)
+// floats32: plane_u[3], plane_v[3], plane_bounds[4], plane_rms, cyl_t_range[2], cyl_rms, residual_rms, total_rms
+// res_centroids4: capacity n x 4
+GMO_API void gmo_compress(const float* pts4, const uint8_t* labels, int64_t n, const float* plane4, const float* cyl7,
+                          double tau, double leaf, int32_t* ints6, float* floats32, float* res_centroids4) {
+  const P4* p = (const P4*)pts4;
+  double pu[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
+  if (plane4) { double nrm[3] = {plane4[0], plane4[1], plane4[2]}; perp_basis_d(nrm, pu, pv); }
+  float t12[12] = {0};
+  if (cyl7) cyl_test_params(cyl7, (float)tau, t12);
+  double sqp = 0, sqc = 0;
+  int64_t np_ = 0, nc = 0;
+  double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300, tmin = 1e300, tmax = -1e300;
+  std::vector<float> res;
+  for (int64_t i = 0; i < n; ++i) {
+    const double x = p[i].x, y = p[i].y, z = p[i].z;
+    if (labels[i] == 1 && plane4) {
+      float d = std::fmaf(plane4[0], p[i].x, std::fmaf(plane4[1], p[i].y, std::fmaf(plane4[2], p[i].z, plane4[3])));
+      sqp += (double)d * (double)d; ++np_;
+      double u = pu[0] * x + pu[1] * y + pu[2] * z, v = pv[0] * x + pv[1] * y + pv[2] * z;
+      umin = std::min(umin, u); umax = std::max(umax, u); vmin = std::min(vmin, v); vmax = std::max(vmax, v);
+    } else if (labels[i] == 2 && cyl7) {
+      float A = std::fmaf(t12[0], p[i].x, std::fmaf(t12[1], p[i].y, std::fmaf(t12[2], p[i].z, t12[3])));
+      float B = std::fmaf(t12[4], p[i].x, std::fmaf(t12[5], p[i].y, std::fmaf(t12[6], p[i].z, t12[7])));
+      double e = std::sqrt((double)A * (double)A + (double)B * (double)B) - (double)cyl7[6];
+      sqc += e * e; ++nc;
+      double t = (double)cyl7[3] * (x - (double)cyl7[0]) + (double)cyl7[4] * (y - (double)cyl7[1]) + (double)cyl7[5] * (z - (double)cyl7[2]);
+      tmin = std::min(tmin, t); tmax = std::max(tmax, t);
+    } else {
+      res.push_back(p[i].x); res.push_back(p[i].y); res.push_back(p[i].z); res.push_back(p[i].w);
+    }
+  }
+  const int64_t nr = (int64_t)res.size() / 4;
+  std::vector<int32_t> assign((size_t)std::max<int64_t>(nr, 1));
+  std::vector<float> cen((size_t)std::max<int64_t>(nr, 1) * 4);
+  int32_t status = 0;
+  int64_t V = gmo_voxel(res.data(), nr, leaf, nullptr, assign.data(), cen.data(), nullptr, nullptr, nullptr, &status);
+  double sqr = 0;
+  for (int64_t i = 0; i < nr; ++i) {
+    const float* c = &cen[(size_t)assign[(size_t)i] * 4];
+    double dx = (double)res[(size_t)i * 4] - c[0], dy = (double)res[(size_t)i * 4 + 1] - c[1], dz = (double)res[(size_t)i * 4 + 2] - c[2];
+    sqr += dx * dx + dy * dy + dz * dz;
+  }
+  if (res_centroids4 && V > 0) std::memcpy(res_centroids4, cen.data(), (size_t)V * 16);
+  ints6[0] = (int32_t)n; ints6[1] = (int32_t)np_; ints6[2] = (int32_t)nc; ints6[3] = (int32_t)nr; ints6[4] = (int32_t)V; ints6[5] = status;
+  float* f = floats32;
+  for (int k = 0; k < 3; ++k) { f[k] = (float)pu[k]; f[3 + k] = (float)pv[k]; }
+  f[6] = np_ ? (float)umin : 0.f; f[7] = np_ ? (float)umax : 0.f; f[8] = np_ ? (float)vmin : 0.f; f[9] = np_ ? (float)vmax : 0.f;
+  f[10] = np_ ? (float)std::sqrt(sqp / (double)np_) : 0.f;
+  f[11] = nc ? (float)tmin : 0.f; f[12] = nc ? (float)tmax : 0.f;
+  f[13] = nc ? (float)std::sqrt(sqc / (double)nc) : 0.f;
+  f[14] = nr ? (float)std::sqrt(sqr / (double)nr) : 0.f;
+  f[15] = n ? (float)std::sqrt((sqp + sqc + sqr) / (double)n) : 0.f;
+}
+
 GMO_API int32_t gmo_num_threads() { return resolve_threads(0); }
 GMO_API int32_t gmo_version() { return 1; }

@@ -221,3 +221,19 @@ def polyline(pts, normals8, labels_u8, want, axis3, wf, L, max_slices):
     S = lib().gmo_polyline(_p(pts), _p(normals8), _p(lab), C.c_int64(pts.shape[0]), C.c_int(want), _p(ax), C.c_double(wf),
                            C.c_double(L), C.c_int32(max_slices), _p(out), C.byref(t0))
     return out[:S].copy(), t0.value
+
+
+def compress(pts, labels_u8, plane4, cyl7, tau, leaf):
+    pts = _f32(pts)
+    lab = np.ascontiguousarray(labels_u8, np.uint8)
+    p4 = None if plane4 is None else _f32(plane4)
+    c7 = None if cyl7 is None else _f32(cyl7)
+    ints = np.zeros(6, np.int32)
+    fl = np.zeros(32, np.float32)
+    cen = np.zeros((max(pts.shape[0], 1), 4), np.float32)
+    lib().gmo_compress(_p(pts), _p(lab), C.c_int64(pts.shape[0]), _p(p4), _p(c7), C.c_double(tau), C.c_double(leaf), _p(ints), _p(fl),
+                       _p(cen))
+    return {"n_points": int(ints[0]), "n_plane": int(ints[1]), "n_cylinder": int(ints[2]), "n_residual": int(ints[3]),
+            "n_residual_voxels": int(ints[4]), "plane_u": fl[0:3].copy(), "plane_v": fl[3:6].copy(), "plane_bounds": fl[6:10].copy(),
+            "plane_rms": float(fl[10]), "cyl_t_range": fl[11:13].copy(), "cyl_rms": float(fl[13]), "residual_rms": float(fl[14]),
+            "total_rms": float(fl[15]), "residual_centroids": cen[: int(ints[4])].copy()}

@@ -517,3 +517,65 @@ def test_cpp_host_shim_node_harness_runs_cloud_cb():
     assert np.allclose(vals, fr["vals"], rtol=1e-5) and np.allclose(axis, fr["vecs"][:, 0], atol=1e-5)
     assert f"publish cloudOutput: {c.n_valid} points" in res.stdout
     assert f"publish normalsOutput: {c.n_voxels} markers" in res.stdout
+
+
+# ---- compression (builder-defined) ----------------------------------------------------
+def test_compression_parity_and_blob_layout():
+    import ctypes as C
+    import struct
+
+    n = 150_000
+    pts = synth.curved_tunnel(n, seed=6, outlier_frac=0.02)
+    with _ctx(n, neighborRadius=0.1, voxelGridLeafSize=0.2) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        nv = ctx.counts().n_valid
+        ps, cs = synth.sample_indices(nv, 512, 3, seed=3), synth.sample_indices(nv, 512, 2, seed=4)
+        ctx.upload_scan(pts)
+        ctx.process_scan(ps, cs)
+        ctx.compress()
+        c = ctx.compression()
+        blob = ctx.download_compressed()
+        cloud_c, labels = ctx.download_cloud(1), ctx.download_labels()
+        mp, mc = ctx.model(0), ctx.model(1)
+        poly = ctx.download_polyline()
+        assert ctx.counts().device_error == 0
+    ref = O.compress(cloud_c, labels, mp["coef"], mc["coef"], TAU, 0.2)
+    # counts: exact
+    assert (c.n_points, c.n_plane, c.n_cylinder, c.n_residual, c.n_residual_voxels) == \
+        (ref["n_points"], ref["n_plane"], ref["n_cylinder"], ref["n_residual"], ref["n_residual_voxels"])
+    assert c.n_plane == int((labels == 1).sum()) and c.n_cylinder == int((labels == 2).sum()) and c.n_slices == len(poly)
+    # primitives: 1e-4 relative (bounds relative to the 10 m box)
+    assert np.allclose(np.array(c.plane_u), ref["plane_u"], atol=1e-6) and np.allclose(np.array(c.plane_v), ref["plane_v"], atol=1e-6)
+    assert np.abs(np.array(c.plane_bounds) - ref["plane_bounds"]).max() <= 1e-4 * 10
+    assert np.abs(np.array(c.cyl_t_range) - ref["cyl_t_range"]).max() <= 1e-4 * 10
+    for k in ("plane_rms", "cyl_rms", "residual_rms", "total_rms"):
+        assert abs(getattr(c, k) - ref[k]) <= 1e-4 * max(ref[k], 1e-3), k
+    assert np.array_equal(np.array(c.plane_coef), mp["coef"]) and np.array_equal(np.array(c.cyl_coef), mc["coef"])
+    # it actually compresses, and the error is bounded by the leaf / inlier threshold
+    assert c.bytes_in == 16 * c.n_points and c.bytes_out == len(blob) and c.ratio > 4.0
+    assert c.total_rms < 0.2 and c.plane_rms < TAU and c.cyl_rms < TAU
+    # blob: 'GMC1' | version | gm_compression | slices | residual centroids (bit-exact vs the oracle voxel grid)
+    magic, version = struct.unpack_from("<II", blob, 0)
+    assert magic == 0x31434D47 and version == 1
+    hdr = capi.gm_compression.from_buffer_copy(blob[8:8 + C.sizeof(capi.gm_compression)])
+    assert hdr.n_residual_voxels == c.n_residual_voxels and hdr.bytes_out == c.bytes_out
+    off = 8 + C.sizeof(capi.gm_compression)
+    sl = np.frombuffer(blob, capi.SLICE_DTYPE, count=c.n_slices, offset=off)
+    assert sl.tobytes() == poly.tobytes()
+    cen = np.frombuffer(blob, np.float32, count=3 * c.n_residual_voxels, offset=off + 40 * c.n_slices).reshape(-1, 3)
+    assert np.array_equal(cen.view(np.uint32), ref["residual_centroids"][:, :3].copy().view(np.uint32))
+
+
+def test_compression_without_models_keeps_everything_as_residual():
+    pts = synth.straight_cylinder(20_000, seed=2)
+    with _ctx(len(pts), neighborRadius=0.2, voxelGridLeafSize=0.25) as ctx:
+        ctx.upload_scan(pts)
+        ctx.process_scan(None, None)
+        ctx.compress()
+        c = ctx.compression()
+        cloud_c = ctx.download_cloud(1)
+    ref = O.voxel(cloud_c, 0.25)
+    assert c.n_plane == 0 and c.n_cylinder == 0 and c.n_residual == c.n_points == len(cloud_c)
+    assert c.n_residual_voxels == ref["V"] and c.n_slices == 0

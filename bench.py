@@ -405,6 +405,24 @@ def main():
               "mode": "hypotheses sharded across ranks, NCCL max-allreduce of packed (count,id), refit on every rank",
               "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
 
+    # ---- compression of the segmented cloud (extra stage, reported separately) -------------------------
+    for i in range(3):
+        step(i)
+        ctx.compress()
+    barrier()
+    e0.record(stream)
+    for i in range(a.steps):
+        step(i)
+        ctx.compress()
+    e1.record(stream)
+    barrier()
+    cms = max_over_ranks(e0.elapsed_time(e1)) / a.steps
+    cc = ctx.compression()
+    compress = {"ms_per_scan_with_compression": cms, "added_ms": cms - ms / a.steps, "ratio": float(cc.ratio),
+                "bytes_in": int(cc.bytes_in), "bytes_out": int(cc.bytes_out), "total_rms_m": float(cc.total_rms),
+                "n_plane": cc.n_plane, "n_cylinder": cc.n_cylinder, "n_residual": cc.n_residual,
+                "n_residual_voxels": cc.n_residual_voxels}
+
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -435,6 +453,7 @@ def main():
             "roofline_families": families,
             "segments_ms_per_step": seg_ms,
             "ransac": ransac,
+            "compress": compress,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

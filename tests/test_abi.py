@@ -43,6 +43,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.gm_model) == 88
     assert C.sizeof(capi.gm_slice) == 40 and capi.SLICE_DTYPE.itemsize == 40
     assert C.sizeof(capi.gm_scan_summary) == 32 + 84 + 88 + 88 + 8
+    assert C.sizeof(capi.gm_compression) == 160 and capi.gm_compression.bytes_in.offset == 144
 
 
 def test_defaults_mirror_paramhandler():

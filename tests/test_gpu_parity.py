@@ -579,3 +579,115 @@ def test_compression_without_models_keeps_everything_as_residual():
     ref = O.voxel(cloud_c, 0.25)
     assert c.n_plane == 0 and c.n_cylinder == 0 and c.n_residual == c.n_points == len(cloud_c)
     assert c.n_residual_voxels == ref["V"] and c.n_slices == 0
+
+
+# ---- BASELINE.json full size (1M points): size-independent properties -------------------------------
+def test_full_size_properties_1m_points():
+    n = 1_000_000
+    pts = synth.curved_tunnel(n, seed=2)
+    H = 1024
+    with capi.Context(capi.default_params(neighborRadius=0.05, voxelGridLeafSize=0.1), max_points=n, max_hypotheses=4096) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        cropped = ctx.download_cloud(0)
+        ctx.normals()
+        nv = ctx.counts().n_valid
+        ps, cs = synth.sample_indices(nv, H // 2, 3, seed=3), synth.sample_indices(nv, H // 2, 2, seed=4)
+        ctx.upload_scan(pts)
+        ctx.process_scan(ps, cs)
+        c = ctx.counts()
+        cloud_c, normals_c = ctx.download_cloud(1), ctx.download_normals(1)
+        keys, assign, _ = ctx.download_voxel_assignment()
+        vox = ctx.download_voxels()
+        pcoef, _, pcounts = ctx.download_hypotheses(capi.GM_MODEL_PLANE, H // 2)
+        _, ct12, ccounts = ctx.download_hypotheses(capi.GM_MODEL_CYLINDER, H // 2)
+        mp, mc = ctx.model(0), ctx.model(1)
+        labels = ctx.download_labels()
+        # crop is idempotent: cropping the cropped cloud changes nothing
+        ctx.upload_scan(cropped)
+        ctx.crop()
+        assert np.array_equal(ctx.download_cloud(0).view(np.uint32), cropped.view(np.uint32))
+    assert c.device_error == 0 and c.n_cropped == len(cropped) and c.n_valid == len(cloud_c) == nv
+    # crop: every kept point is inside the box, order preserved (a subsequence of the input)
+    assert (np.abs(cropped[:, :3]) <= 5.0).all()
+    inside = (np.abs(pts[:, :3]) <= 5.0).all(1)
+    assert np.array_equal(cropped.view(np.uint32), pts[inside].view(np.uint32))
+    # normals: unit length, flipped towards the sensor, curvature in [0, 1/3]
+    assert np.abs(np.linalg.norm(normals_c[:, :3], axis=1) - 1.0).max() < 1e-4
+    assert (-(cloud_c[:, :3] * normals_c[:, :3]).sum(1) >= -1e-5).all()
+    assert (normals_c[:, 4] >= 0).all() and (normals_c[:, 4] <= 1 / 3 + 1e-4).all()
+    # voxel grid: voxel keys strictly ascending, assignment consistent with the per-point keys, counts conserve points
+    assert (np.diff(vox["keys"].astype(np.int64)) > 0).all() and c.n_voxels == len(vox["keys"])
+    assert np.array_equal(vox["keys"][assign], keys)
+    assert vox["counts"].sum() == len(cloud_c) and np.array_equal(np.bincount(assign, minlength=c.n_voxels), vox["counts"])
+    # centroid of a voxel lies inside that voxel's cell of the lattice (leaf 0.1)
+    inv = np.float32(1.0) / np.float32(0.1)
+    assert np.array_equal(np.floor(vox["centroids"][:, :3] * inv).astype(np.int64), np.floor(cloud_c[np.unique(assign, return_index=True)[1], :3] * inv).astype(np.int64))
+    # the 1-NN of a centroid is at most one voxel diagonal away
+    nn = vox["nn_index"]
+    ok = (nn >= 0) & (nn < len(cropped))
+    assert ok.all()
+    assert (np.linalg.norm(cropped[nn, :3] - vox["centroids"][:, :3], axis=1) <= 0.1 * np.sqrt(3) + 1e-5).all()
+    # RANSAC: counts bounded by the cloud size, argmax/tie rule, labels consistent with the refined models
+    assert pcounts.max() <= len(cloud_c) and ccounts.max() <= len(cloud_c) and pcounts.min() >= -1
+    assert mp["best_count"] == pcounts.max() and mp["best_id"] == int(np.argmax(pcounts))
+    assert mc["best_count"] == ccounts.max() and mc["best_id"] == int(np.argmax(ccounts))
+    d = (cloud_c[:, :3].astype(np.float64) @ mp["coef"][:3].astype(np.float64)) + float(mp["coef"][3])
+    assert (np.abs(d[labels == 1]) < TAU + 1e-5).all() and (np.abs(d[labels != 1]) > TAU - 1e-5).all()
+    # exact linearity with numpy: the winning plane's count equals the number of points passing the canonical test
+    best = pcoef[mp["best_id"]]
+    dd = np.abs((cloud_c[:, :3].astype(np.float64) @ best[:3].astype(np.float64)) + float(best[3]))
+    assert abs(int((dd < TAU).sum()) - mp["best_count"]) <= 4          # float vs double only at the boundary
+    assert abs(abs(mp["coef"][3]) - 1.5) < 5e-3 and abs(mc["coef"][6] - 2.5) < 0.3   # straight cylinder on a curved tunnel
+
+
+def test_count_linearity_over_a_split_cloud():
+    """counts(cloud) == counts(first half) + counts(second half) for fixed hypotheses: exact."""
+    cloud, nrm = _compacted_scan(60_000, seed=51)
+    H = 256
+    g = np.random.Generator(np.random.Philox(5))
+    half = len(cloud) // 2
+    # samples drawn from the first half only, so both runs build the same hypotheses
+    ps = g.integers(0, half, size=(H, 3)).astype(np.int32)
+    cs = g.integers(0, half, size=(H, 2)).astype(np.int32)
+    out = {}
+    with _ctx(len(cloud)) as ctx:
+        for name, sl in (("all", slice(None)), ("a", slice(0, half))):
+            ctx.inject_compacted(cloud[sl], nrm[sl])
+            ctx.ransac(capi.GM_MODEL_PLANE, ps)
+            ctx.ransac(capi.GM_MODEL_CYLINDER, cs)
+            out[name] = (ctx.download_hypotheses(0, H), ctx.download_hypotheses(1, H))
+    (pc_all, _, pn_all), (cm_all, ct_all, cn_all) = out["all"]
+    (pc_a, _, pn_a), (cm_a, ct_a, cn_a) = out["a"]
+    assert np.array_equal(pc_all.view(np.uint32), pc_a.view(np.uint32)) and np.array_equal(ct_all.view(np.uint32), ct_a.view(np.uint32))
+    # second half evaluated by the oracle with the same coefficients
+    pn_b = O.count_plane(cloud[half:], pc_all, (pn_all >= 0).astype(np.int32), TAU)
+    cn_b = O.count_cyl(cloud[half:], ct_all, (cn_all >= 0).astype(np.int32))
+    v = pn_all >= 0
+    assert np.array_equal(pn_all[v], pn_a[v] + pn_b[v])
+    v = cn_all >= 0
+    assert np.array_equal(cn_all[v], cn_a[v] + cn_b[v])
+
+
+def test_frame_sequence_polyline_per_frame():
+    """Config C3 in miniature: consecutive frames of the same tunnel through one context."""
+    n, frames = 60_000, 4
+    with _ctx(n, neighborRadius=0.15, voxelGridLeafSize=0.2) as ctx:
+        for f in range(frames):
+            pts = synth.curved_tunnel(n, seed=100 + f, advance=1.0 * f)
+            ctx.upload_scan(pts)
+            ctx.crop()
+            ctx.normals()
+            nv = ctx.counts().n_valid
+            ps, cs = synth.sample_indices(nv, 256, 3, seed=3 + f), synth.sample_indices(nv, 256, 2, seed=4 + f)
+            ctx.upload_scan(pts)
+            ctx.process_scan(ps, cs)
+            cloud_c, normals_c, labels = ctx.download_cloud(1), ctx.download_normals(1), ctx.download_labels()
+            fr, poly = ctx.frame(), ctx.download_polyline()
+            ref_poly, _ = O.polyline(cloud_c, normals_c, labels, 2, fr["vecs"][:, 0], 0.2, 1.0, 256)
+            assert len(poly) == len(ref_poly) and len(poly) >= 5
+            assert np.array_equal(poly["count"], ref_poly[:, 7].astype(np.int32))
+            big = ref_poly[:, 7] > 200
+            assert np.abs(poly["center"][big] - ref_poly[big, 0:3]).max() <= 5e-4
+            assert np.abs(poly["radius"][big] - ref_poly[big, 6]).max() <= 1e-4 * 2.5
+            assert ctx.counts().device_error == 0

@@ -256,25 +256,60 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ------------------------------------------------------------
+    # (a) one scan at a time on one context: per-scan latency
     for i in range(max(a.warmup, 3)):
         step(i)
     barrier()
-    sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
-    ctx.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(a.steps):
         step(i)
     e1.record(stream)
     barrier()
+    latency_ms = max_over_ranks(e0.elapsed_time(e1)) / a.steps
+
+    # (b) throughput: NFLIGHT scans in flight, one context (and CUDA stream) each, round robin, the way
+    # a stream of scans is processed.  Timed with CUDA events: e0 on the first context's stream before
+    # the first step, e1 on a stream that has waited for every context's last step.
+    NFLIGHT = 3
+    tctx = [ctx] + [capi.Context(params, max_points=n, max_hypotheses=max(4096, a.shard_hyp)) for _ in range(NFLIGHT - 1)]
+    tstreams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NFLIGHT - 1)]
+    for cx, st_ in zip(tctx[1:], tstreams[1:]):
+        cx.set_stream(st_.cuda_stream)
+
+    def tstep(i):
+        s, cx = i % RING, tctx[i % NFLIGHT]
+        cx.set_scan_device(dev_scans[s].data_ptr(), n)
+        cx.process_scan(samples[s][0], samples[s][1])
+
+    for i in range(max(a.warmup, 3) * NFLIGHT):
+        tstep(i)
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    for cx in tctx:
+        cx.reset_launch_count()
+    for st_ in tstreams[1:]:
+        st_.wait_stream(stream)
+    e0.record(stream)
+    for st_ in tstreams[1:]:
+        st_.wait_event(e0)
+    for i in range(a.steps):
+        tstep(i)
+    for st_ in tstreams[1:]:
+        stream.wait_stream(st_)
+    e1.record(stream)
+    barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ctx.launch_count
+    launches = sum(cx.launch_count for cx in tctx)
     clocks = sampler.stop()
+    for cx in tctx:
+        if cx.counts().device_error:
+            raise SystemExit("device-side error flag set")
     c = ctx.counts()
-    if c.device_error:
-        raise SystemExit("device-side error flag set")
     value = world * n * a.steps / (ms * 1e-3)
+    for cx in tctx[1:]:
+        cx.close()
 
     # ---- per-segment timing of the same steps (roofline) ------------------------------------------
     ctx.profile_enable(True)
@@ -315,8 +350,8 @@ def main():
     roofline = dict(families["inlier_count"] if dominant == "normals" else families[dominant])
     roofline["dominant_segment"] = dominant
 
-    # ---- end to end through the C-ABI with host buffers (3 contexts pipelined) --------------------
-    NCTX = 3
+    # ---- end to end through the C-ABI with host buffers (NCTX contexts pipelined) --------------------
+    NCTX = int(os.environ.get("GM_E2E_CONTEXTS", "4"))
     ectx, outs, keep = [], [], []
     for k in range(NCTX):
         cx = capi.Context(params, max_points=n, max_hypotheses=4096)
@@ -444,7 +479,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "parallelism": f"frame-parallel x{world}" if world > 1 else "1 GPU",
                        "l2": f"inputs larger than L2: ring of {RING} distinct resident scans ({RING * n * 16 / 1e6:.0f} MB) cycled",
+                       "in_flight": "3 scans in flight (one context + CUDA stream each); single-scan latency in latency_ms_per_scan",
                        "mean_valid_points": M, "voxels": int(V)},
+            "latency_ms_per_scan": latency_ms,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / a.steps, "pipeline": f"{NCTX} contexts / streams, pinned host buffers"},

@@ -122,7 +122,7 @@ SYMBOLS = [
     "gm_get_frame", "gm_download_hypotheses", "gm_get_model", "gm_download_labels", "gm_download_polyline",
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
     "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
-    "gm_download_compressed",
+    "gm_download_compressed", "gm_upload_pointcloud2",
 ]
 
 
@@ -187,6 +187,7 @@ def _lib():
         "gm_compress": (i32, [vp]),
         "gm_get_compression": (i32, [vp, C.POINTER(gm_compression)]),
         "gm_download_compressed": (i32, [vp, vp, sz, C.POINTER(sz)]),
+        "gm_upload_pointcloud2": (i32, [vp, vp, sz, sz, sz, sz, sz]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -283,6 +284,12 @@ class Context:
 
     def upload_scan_raw(self, host_ptr: int, n: int, stride: int = 16):
         self._ck(_lib().gm_upload_scan(self._h, C.c_void_p(host_ptr), n, stride), "gm_upload_scan")
+
+    def upload_pointcloud2(self, data: np.ndarray, n: int, point_step: int, offset_x: int, offset_y: int, offset_z: int):
+        """data: contiguous uint8 payload of a sensor_msgs/PointCloud2 (n * point_step bytes)."""
+        raw = np.ascontiguousarray(data, dtype=np.uint8)
+        self._keepalive = raw
+        self._ck(_lib().gm_upload_pointcloud2(self._h, _ptr(raw), n, point_step, offset_x, offset_y, offset_z), "gm_upload_pointcloud2")
 
     def set_scan_device(self, device_ptr: int, n: int):
         self._ck(_lib().gm_set_scan_device(self._h, C.c_void_p(device_ptr), n), "gm_set_scan_device")

@@ -89,6 +89,8 @@ struct gm_ctx {
   GridSpec grid{};
 
   // device buffers
+  unsigned char* d_raw = nullptr;  // PointCloud2 staging (grown on demand)
+  size_t raw_cap = 0;
   float4 *d_in = nullptr, *d_crop = nullptr, *d_sorted = nullptr, *d_cloud_c = nullptr;
   float4 *d_normals = nullptr, *d_normals_c = nullptr, *d_centroid = nullptr, *d_nn_normal = nullptr;
   unsigned *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
@@ -378,7 +380,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
 void gm_destroy(gm_ctx* ctx) {
   if (!ctx) return;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
+  void* ptrs[] = {ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
@@ -450,6 +452,25 @@ gm_status gm_upload_scan(gm_ctx* ctx, const float* xyz_host, size_t n, size_t st
       GM_CUDA(cudaMemcpy2DAsync(ctx->d_in, 16, xyz_host, stride_bytes, width, n, cudaMemcpyHostToDevice, ctx->stream));
       GM_LAUNCH(ctx, k_set_w_one, div_up((long long)n, 256), 256, ctx->d_in, (int)n);
     }
+  }
+  ctx->d_scan = ctx->d_in;
+  return begin_scan(ctx, n);
+}
+
+gm_status gm_upload_pointcloud2(gm_ctx* ctx, const void* data_host, size_t n, size_t point_step, size_t ox, size_t oy, size_t oz) {
+  if (!ctx || (n && !data_host) || point_step < 4 || ox + 4 > point_step || oy + 4 > point_step || oz + 4 > point_step) return GM_ERR_INVALID_ARG;
+  if (n > ctx->cap) { ctx->err = "scan larger than max_points"; return GM_ERR_CAPACITY; }
+  if (n) {
+    const size_t bytes = n * point_step;
+    if (bytes > ctx->raw_cap) {  // not on the per-scan fast path: only when a larger message arrives
+      GM_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->d_raw) cudaFree(ctx->d_raw);
+      ctx->d_raw = nullptr; ctx->raw_cap = 0;
+      GM_CUDA(cudaMalloc((void**)&ctx->d_raw, ctx->cap * point_step));
+      ctx->raw_cap = ctx->cap * point_step;
+    }
+    GM_CUDA(cudaMemcpyAsync(ctx->d_raw, data_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GM_LAUNCH(ctx, k_decode_pointcloud2, div_up((long long)n, 256), 256, ctx->d_raw, (int)n, (int)point_step, (int)ox, (int)oy, (int)oz, ctx->d_in);
   }
   ctx->d_scan = ctx->d_in;
   return begin_scan(ctx, n);

@@ -57,6 +57,22 @@ __global__ void k_begin_scan(DevState* st, int n_input) {
   }
 }
 
+// PointCloud2 decode: gather the float32 x,y,z fields (byte offsets, arbitrary point_step) into PointXYZ
+__global__ void k_decode_pointcloud2(const unsigned char* __restrict__ raw, int n, int point_step, int ox, int oy, int oz,
+                                     float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = raw + (size_t)i * point_step;
+  float v[3];
+  const int off[3] = {ox, oy, oz};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {  // byte-wise: fields need not be 4-byte aligned inside the record
+    unsigned u = (unsigned)p[off[k]] | ((unsigned)p[off[k] + 1] << 8) | ((unsigned)p[off[k] + 2] << 16) | ((unsigned)p[off[k] + 3] << 24);
+    v[k] = __uint_as_float(u);
+  }
+  out[i] = make_float4(v[0], v[1], v[2], 1.0f);
+}
+
 __global__ void k_set_w_one(float4* p, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i].w = 1.0f;

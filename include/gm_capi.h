@@ -162,6 +162,11 @@ GM_API gm_status gm_synchronize(gm_ctx* ctx);
 /* ---- input: replaces pcl::fromROSMsg(*input, *cloud), src/geometric_mapping.cpp:55 -------- */
 /* Host buffer -> device (async H2D on the ctx stream).  stride_bytes >= 12; 16 for PointXYZ. */
 GM_API gm_status gm_upload_scan(gm_ctx* ctx, const float* xyz_host, size_t n, size_t stride_bytes);
+/* sensor_msgs/PointCloud2 payload as pcl::fromROSMsg reads it (src/geometric_mapping.cpp:55): n points of
+ * point_step bytes, float32 x/y/z fields at the given byte offsets (any other fields are ignored),
+ * little endian.  The raw bytes are copied to the device and gathered there. */
+GM_API gm_status gm_upload_pointcloud2(gm_ctx* ctx, const void* data_host, size_t n, size_t point_step,
+                                       size_t offset_x, size_t offset_y, size_t offset_z);
 /* Scan already resident in HBM as n x float4 (not copied; must outlive the processing calls). */
 GM_API gm_status gm_set_scan_device(gm_ctx* ctx, const float* xyzw_device, size_t n);
 

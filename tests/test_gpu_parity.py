@@ -691,3 +691,63 @@ def test_frame_sequence_polyline_per_frame():
             assert np.abs(poly["center"][big] - ref_poly[big, 0:3]).max() <= 5e-4
             assert np.abs(poly["radius"][big] - ref_poly[big, 6]).max() <= 1e-4 * 2.5
             assert ctx.counts().device_error == 0
+
+
+# ---- I/O seams ---------------------------------------------------------------------------------------
+def test_pointcloud2_decode_velodyne_layout():
+    """sensor_msgs/PointCloud2 as the Velodyne driver publishes it: point_step 22 (x,y,z,intensity f32 +
+    ring u16 + time f32 would be 22 bytes, unaligned records) and a padded 32-byte layout."""
+    pts = _scan_with_junk(20_000, seed=61)
+    n = len(pts)
+    for step, (ox, oy, oz) in ((22, (0, 4, 8)), (32, (4, 12, 20)), (12, (0, 4, 8))):
+        raw = np.full((n, step), 0xAB, np.uint8)
+        for k, o in enumerate((ox, oy, oz)):
+            raw[:, o:o + 4] = pts[:, k].copy().view(np.uint8).reshape(n, 4)
+        with _ctx(n, neighborRadius=0.2) as ctx:
+            ctx.upload_pointcloud2(raw, n, step, ox, oy, oz)
+            ctx.crop()
+            got = ctx.download_cloud(0)
+        ref, _ = O.crop(pts, 5.0, True)
+        assert np.array_equal(got[:, :3].view(np.uint32), ref[:, :3].view(np.uint32)) and (got[:, 3] == 1.0).all()
+
+
+def test_fetch_async_matches_synchronous_downloads():
+    import ctypes as C
+
+    n = 80_000
+    pts = synth.curved_tunnel(n, seed=9)
+    with _ctx(n, neighborRadius=0.12, voxelGridLeafSize=0.2) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        nv = ctx.counts().n_valid
+        ps, cs = synth.sample_indices(nv, 256, 3, seed=3), synth.sample_indices(nv, 256, 2, seed=4)
+        ctx.upload_scan(pts)
+        ctx.process_scan(ps, cs)
+        summ = capi.gm_scan_summary()
+        cloud = np.zeros((n, 4), np.float32)
+        normals = np.zeros((n, 8), np.float32)
+        labels = np.zeros(n, np.uint8)
+        slices = np.zeros(256, capi.SLICE_DTYPE)
+        cen = np.zeros((n, 4), np.float32)
+        nnn = np.zeros((n, 8), np.float32)
+        o = capi.gm_host_outputs()
+        o.summary = C.addressof(summ)
+        o.cloud_xyzw, o.cloud_capacity = cloud.ctypes.data, n
+        o.normals8, o.normals_capacity = normals.ctypes.data, n
+        o.labels, o.labels_capacity = labels.ctypes.data, n
+        o.slices, o.slices_capacity = slices.ctypes.data, 256
+        o.centroids_xyzw, o.nn_normal8, o.voxel_capacity = cen.ctypes.data, nnn.ctypes.data, n
+        ctx.fetch_async(o)
+        ctx.synchronize()
+        c = ctx.counts()
+        assert (summ.counts.n_input, summ.counts.n_cropped, summ.counts.n_valid, summ.counts.n_voxels) == (c.n_input, c.n_cropped, c.n_valid, c.n_voxels)
+        assert np.array_equal(cloud[:c.n_valid], ctx.download_cloud(1)) and np.array_equal(labels[:c.n_valid], ctx.download_labels())
+        assert np.array_equal(normals[:c.n_valid].view(np.uint32), ctx.download_normals(1).view(np.uint32))
+        vox = ctx.download_voxels()
+        assert np.array_equal(cen[:c.n_voxels], vox["centroids"]) and np.array_equal(nnn[:c.n_voxels].view(np.uint32), vox["nn_normal"].view(np.uint32))
+        fr, mp, mc, poly = ctx.frame(), ctx.model(0), ctx.model(1), ctx.download_polyline()
+        assert np.array_equal(np.array(summ.frame.vals), fr["vals"]) and np.array_equal(np.array(summ.frame.vecs).reshape(3, 3), fr["vecs"])
+        assert (summ.plane.best_id, summ.plane.best_count, summ.plane.refit_count) == (mp["best_id"], mp["best_count"], mp["refit_count"])
+        assert np.array_equal(np.array(summ.plane.coef[:4]), mp["coef"]) and np.array_equal(np.array(summ.cylinder.coef[:7]), mc["coef"])
+        assert summ.n_slices == len(poly) and slices[:len(poly)].tobytes() == poly.tobytes()

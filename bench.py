@@ -208,13 +208,15 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     n, Hp, Hc = a.points, a.hyp // 2, a.hyp - a.hyp // 2
     params = capi.default_params(neighborRadius=a.radius, voxelGridLeafSize=a.leaf, ransacThreshold=TAU, refitIterations=a.refit_iters)
-    stream = torch.cuda.current_stream()
+    # an explicit non-default stream for everything (context work, copies, CUDA events, NCCL): the
+    # default stream's handle is 0, which would not order the context's work with torch's
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     # ---- synthetic ring of scans: distinct per slot and per rank (frame-parallel = weak scaling)
     host_scans, dev_scans = [], []
@@ -406,25 +408,12 @@ def main():
     ctx.normals()
     nv = ctx.counts().n_valid
     sp, sc = synth.sample_indices(nv, Hs // 2, 3, seed=3), synth.sample_indices(nv, Hs - Hs // 2, 2, seed=4)
-    key_ptrs = [ctx.ransac_key_device_ptr(k) for k in (0, 1)]
-
-    class _Key:  # expose the 8-byte device key to torch without a copy
-        def __init__(self, ptr):
-            self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-
-    key_t = [torch.as_tensor(_Key(p), device=dev) for p in key_ptrs]
-
-    def shard(Hk):
-        per = (Hk + world - 1) // world
-        return min(rank * per, Hk), min((rank + 1) * per, Hk)
+    from geometric_mapping_b200 import distributed as gmd
+    key_t = torch.zeros(1, dtype=torch.int64, device=dev)  # torch-owned buffer for the 8-byte collective
 
     def ransac_step():
         for kind, smp in ((0, sp), (1, sc)):
-            lo, hi = shard(smp.shape[0])
-            ctx.ransac(kind, smp, lo, hi)
-            if world > 1:
-                dist.all_reduce(key_t[kind], op=dist.ReduceOp.MAX)
-            ctx.ransac_select(kind)
+            gmd.sharded_ransac(ctx, kind, smp, rank, world, key_t)
 
     for _ in range(3):
         ransac_step()

@@ -122,7 +122,7 @@ SYMBOLS = [
     "gm_get_frame", "gm_download_hypotheses", "gm_get_model", "gm_download_labels", "gm_download_polyline",
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
     "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
-    "gm_download_compressed", "gm_upload_pointcloud2",
+    "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key",
 ]
 
 
@@ -188,6 +188,8 @@ def _lib():
         "gm_get_compression": (i32, [vp, C.POINTER(gm_compression)]),
         "gm_download_compressed": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "gm_upload_pointcloud2": (i32, [vp, vp, sz, sz, sz, sz, sz]),
+        "gm_ransac_export_key": (i32, [vp, i32, vp]),
+        "gm_ransac_import_key": (i32, [vp, i32, vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -264,7 +266,16 @@ class Context:
         self.params = params
 
     def set_stream(self, cuda_stream: int | None):
-        self._ck(_lib().gm_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "gm_set_stream")
+        """cuda_stream: a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None = the
+        context's own stream.  The handle 0 names CUDA's legacy default stream (what torch's default
+        stream is), which the C-ABI spells cudaStreamLegacy (0x1) because NULL means "own stream" there."""
+        if cuda_stream is None:
+            h = 0
+        elif cuda_stream == 0:
+            h = 1  # cudaStreamLegacy
+        else:
+            h = cuda_stream
+        self._ck(_lib().gm_set_stream(self._h, C.c_void_p(h)), "gm_set_stream")
 
     def synchronize(self):
         self._ck(_lib().gm_synchronize(self._h), "gm_synchronize")
@@ -316,6 +327,12 @@ class Context:
         p = C.c_void_p()
         self._ck(_lib().gm_ransac_key_device_ptr(self._h, kind, C.byref(p)), "gm_ransac_key_device_ptr")
         return int(p.value)
+
+    def ransac_export_key(self, kind: int, dst_device_ptr: int):
+        self._ck(_lib().gm_ransac_export_key(self._h, kind, C.c_void_p(dst_device_ptr)), "gm_ransac_export_key")
+
+    def ransac_import_key(self, kind: int, src_device_ptr: int):
+        self._ck(_lib().gm_ransac_import_key(self._h, kind, C.c_void_p(src_device_ptr)), "gm_ransac_import_key")
 
     def ransac_select(self, kind: int):
         self._ck(_lib().gm_ransac_select(self._h, kind), "gm_ransac_select")

@@ -679,6 +679,20 @@ gm_status gm_ransac_key_device_ptr(gm_ctx* ctx, int32_t kind, void** key_dev) {
   return GM_OK;
 }
 
+gm_status gm_ransac_export_key(gm_ctx* ctx, int32_t kind, void* dst_device) {
+  if (!ctx || !dst_device || (kind != 0 && kind != 1)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_ransac[kind]) return GM_ERR_STAGE_ORDER;
+  GM_CUDA(cudaMemcpyAsync(dst_device, ctx->d_key + kind, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+  return GM_OK;
+}
+
+gm_status gm_ransac_import_key(gm_ctx* ctx, int32_t kind, const void* src_device) {
+  if (!ctx || !src_device || (kind != 0 && kind != 1)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_ransac[kind]) return GM_ERR_STAGE_ORDER;
+  GM_CUDA(cudaMemcpyAsync(ctx->d_key + kind, src_device, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+  return GM_OK;
+}
+
 gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
   if (!ctx || (kind != 0 && kind != 1)) return GM_ERR_INVALID_ARG;
   if (!ctx->have_ransac[kind]) return GM_ERR_STAGE_ORDER;

@@ -63,13 +63,14 @@ def allreduce_best_key(key_tensor, group=None):
     return key_tensor
 
 
-class DeviceKey:
-    """Zero-copy torch view of the 8-byte best-key slot inside a gm_ctx (gm_ransac_key_device_ptr)."""
-
-    def __init__(self, ptr: int):
-        self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
-
-    def tensor(self, device):
-        import torch
-
-        return torch.as_tensor(self, device=device)
+def sharded_ransac(ctx, kind: int, samples, rank: int, world: int, key_tensor, group=None):
+    """One hypothesis-sharded RANSAC round on `ctx` (all ranks hold the same scan and sample list):
+    count this rank's shard, all-reduce(MAX) the packed key through `key_tensor` (a 1-element int64
+    tensor on the ctx's device and stream), refit the global winner on every rank."""
+    lo, hi = shard_range(len(samples), rank, world)
+    ctx.ransac(kind, samples, lo, hi)
+    if world > 1:
+        ctx.ransac_export_key(kind, key_tensor.data_ptr())
+        allreduce_best_key(key_tensor, group)
+        ctx.ransac_import_key(kind, key_tensor.data_ptr())
+    ctx.ransac_select(kind)

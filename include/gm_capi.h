@@ -149,7 +149,8 @@ GM_API void gm_params_default(gm_params* p);
 GM_API gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypotheses, gm_ctx** out);
 GM_API void gm_destroy(gm_ctx* ctx);
 GM_API gm_status gm_set_params(gm_ctx* ctx, const gm_params* p);
-/* Use an existing cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own stream. */
+/* Use an existing cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own (non-blocking)
+ * stream; to run on CUDA's legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1). */
 GM_API gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream);
 GM_API const char* gm_last_error(const gm_ctx* ctx);
 GM_API const char* gm_status_string(gm_status s);
@@ -195,6 +196,10 @@ GM_API gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_hos
                            int32_t h_begin, int32_t h_end);
 /* Device address of the 8-byte packed best key of `kind` (for an NCCL all-reduce in place). */
 GM_API gm_status gm_ransac_key_device_ptr(gm_ctx* ctx, int32_t kind, void** key_dev);
+/* Copy the 8-byte key to / from a caller-owned device buffer (e.g. the int64 tensor handed to the
+ * collective), asynchronously on the ctx stream: export -> all-reduce(MAX) -> import -> select. */
+GM_API gm_status gm_ransac_export_key(gm_ctx* ctx, int32_t kind, void* dst_device);
+GM_API gm_status gm_ransac_import_key(gm_ctx* ctx, int32_t kind, const void* src_device);
 /* Decode the (possibly all-reduced) key on device, refit the winning primitive (plane: PCA of
  * inliers; cylinder: refitIterations Gauss-Newton steps) and keep the result in ctx. */
 GM_API gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind);

@@ -122,7 +122,7 @@ SYMBOLS = [
     "gm_get_frame", "gm_download_hypotheses", "gm_get_model", "gm_download_labels", "gm_download_polyline",
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
     "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
-    "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key",
+    "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode",
 ]
 
 
@@ -190,6 +190,7 @@ def _lib():
         "gm_upload_pointcloud2": (i32, [vp, vp, sz, sz, sz, sz, sz]),
         "gm_ransac_export_key": (i32, [vp, i32, vp]),
         "gm_ransac_import_key": (i32, [vp, i32, vp]),
+        "gm_set_count_mode": (i32, [vp, i32]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -276,6 +277,10 @@ class Context:
         else:
             h = cuda_stream
         self._ck(_lib().gm_set_stream(self._h, C.c_void_p(h)), "gm_set_stream")
+
+    def set_count_mode(self, mode: int):
+        """0 = tile-culled inlier counting (default), 1 = brute-force FP32 kernels; identical counts."""
+        self._ck(_lib().gm_set_count_mode(self._h, mode), "gm_set_count_mode")
 
     def synchronize(self):
         self._ck(_lib().gm_synchronize(self._h), "gm_synchronize")

@@ -92,6 +92,8 @@ struct gm_ctx {
   unsigned char* d_raw = nullptr;  // PointCloud2 staging (grown on demand)
   size_t raw_cap = 0;
   float4 *d_in = nullptr, *d_crop = nullptr, *d_sorted = nullptr, *d_cloud_c = nullptr;
+  float4 *d_sorted_valid = nullptr, *d_leaf_bounds = nullptr;  // inputs of the tile-culled counting (written by k_normals)
+  int count_mode = 0;  // 0 = tile-culled when the cell-sorted cloud exists, 1 = always brute force
   float4 *d_normals = nullptr, *d_normals_c = nullptr, *d_centroid = nullptr, *d_nn_normal = nullptr;
   unsigned *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
   unsigned* d_ucell_key = nullptr;
@@ -330,6 +332,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   ctx->stream = ctx->own_stream;
 #define A(ptr, count) if ((e = dmalloc(&ctx->ptr, (count))) != cudaSuccess) return fail(e, #ptr)
   A(d_in, N); A(d_crop, N); A(d_sorted, N); A(d_cloud_c, N);
+  A(d_sorted_valid, N); A(d_leaf_bounds, 2 * ((N + 31) / 32));
   A(d_normals, 2 * N); A(d_normals_c, 2 * N); A(d_centroid, N); A(d_nn_normal, 2 * N);
   A(d_keys[0], N); A(d_keys[1], N); A(d_vals[0], N); A(d_vals[1], N);
   A(d_ucell_key, N + 1); A(d_cell_id, N); A(d_ucell_start, N + 1); A(d_nbr, N); A(d_valid_map, N);
@@ -362,6 +365,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   }
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
   { const char* env = std::getenv("GM_SERIAL"); ctx->concurrent = !(env && env[0] == '1'); }
+  { const char* env = std::getenv("GM_COUNT_MODE"); ctx->count_mode = (env && env[0] == '1') ? 1 : 0; }
 
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
@@ -380,7 +384,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
 void gm_destroy(gm_ctx* ctx) {
   if (!ctx) return;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
+  void* ptrs[] = {ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
@@ -414,6 +418,12 @@ gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return GM_OK;
+}
+
+gm_status gm_set_count_mode(gm_ctx* ctx, int32_t mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  ctx->count_mode = mode;
   return GM_OK;
 }
 
@@ -529,7 +539,7 @@ gm_status gm_normals(gm_ctx* ctx) {
     float r2 = rf * rf;
     { SegTimer seg_(ctx, SEG_NORMALS);
       GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, n_ptr, r2,
-                ctx->d_normals, ctx->d_nbr); }
+                ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds); }
     if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_COMPACT);
       GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
@@ -642,7 +652,21 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
     } }
     const int hloc = h_end - h_begin;
     bool argmax_done = false;
-    if (hloc > 0 && ctx->n_input > 0) {
+    if (hloc > 0 && ctx->n_input > 0 && ctx->count_mode == 0 && ctx->have_normals && !ctx->injected) {
+      // tile-culled counting over the cell-sorted cloud of this scan (same counts, see gm_ransac.cuh)
+      argmax_done = true;
+      SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_COUNT : SEG_CYL_COUNT);
+      const int blocks = std::max(1, div_up((long long)ctx->n_input, TC_SUPER));
+      if (kind == 0) {
+        GM_LAUNCH(ctx, k_count_tiles<0>, blocks, TC_BLOCK, ctx->d_sorted_valid, ctx->d_leaf_bounds, &ctx->d_st->n_crop, ctx->d_plane_coef,
+                  ctx->d_test12, ctx->d_hvalid[0], h_begin, h_end, (float)ctx->prm.ransacThreshold, ctx->d_counts[0], H, ctx->d_key + 0,
+                  ctx->d_counters + 3);
+      } else {
+        GM_LAUNCH(ctx, k_count_tiles<1>, blocks, TC_BLOCK, ctx->d_sorted_valid, ctx->d_leaf_bounds, &ctx->d_st->n_crop, ctx->d_plane_coef,
+                  ctx->d_test12, ctx->d_hvalid[1], h_begin, h_end, (float)ctx->prm.ransacThreshold, ctx->d_counts[1], H, ctx->d_key + 1,
+                  ctx->d_counters + 4);
+      }
+    } else if (hloc > 0 && ctx->n_input > 0) {
       argmax_done = true;  // folded into the count kernel's last block
       SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_COUNT : SEG_CYL_COUNT);
       const int K = kind == 0 ? RC_KP : RC_KC;

@@ -303,19 +303,25 @@ __device__ void d_eigen33_smallest(float c00, float c01, float c02, float c11, f
 // (A variant testing candidate pairs with the packed sub/mul/add.f32x2 ops was measured 22 % SLOWER:
 // packed ops hold the FP32 pipe two cycles, so only issue slots are saved, and ptxas 12.9 contracts
 // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, which breaks the exact predicate.)
+// Side outputs for the tile-culled inlier counting (gm_ransac.cuh): the cloud in cell-sorted order
+// with the points that the NaN compaction will drop blanked to NaN (`sorted_valid`), and the bounding
+// box of the surviving points of every 32-point leaf (= one warp here): leaf_bounds[2*leaf] = min,
+// [2*leaf+1] = max; an empty leaf has min = +inf, max = -inf.
 constexpr int NRM_BLOCK = 128;
 __global__ void __launch_bounds__(NRM_BLOCK)
 k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs,
-          const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count) {
+          const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count,
+          float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds) {
   const int n = *n_ptr;
   const int i = blockIdx.x * NRM_BLOCK + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = sp[i];
-  const int orig = __float_as_int(p.w);
+  if ((i & ~31) >= n) return;  // warp-uniform: the whole leaf is past the end
+  const bool active = i < n;
   const float qnan = CUDART_NAN_F;
+  const float4 p = active ? sp[i] : make_float4(qnan, qnan, qnan, 0.f);
+  const int orig = __float_as_int(p.w);
   float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
   int cnt = 0;
-  if (finite3(p.x, p.y, p.z)) {
+  if (active && finite3(p.x, p.y, p.z)) {
     const int2* rr = runs + (size_t)cell_id[i] * 9;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
 #pragma unroll 1
@@ -350,9 +356,19 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
       o1 = make_float4(curv, 0.f, 0.f, 0.f);
     }
   }
-  normals[2 * (size_t)orig] = o0;
-  normals[2 * (size_t)orig + 1] = o1;
-  nbr_count[orig] = cnt;
+  const bool keep = active && finite3(o0.x, o0.y, o0.z);  // the predicate of k_compact_valid
+  if (active) {
+    normals[2 * (size_t)orig] = o0;
+    normals[2 * (size_t)orig + 1] = o1;
+    nbr_count[orig] = cnt;
+    sorted_valid[i] = keep ? p : make_float4(qnan, qnan, qnan, p.w);
+  }
+  const float lx = warp_min(keep ? p.x : CUDART_INF_F), ly = warp_min(keep ? p.y : CUDART_INF_F), lz = warp_min(keep ? p.z : CUDART_INF_F);
+  const float hx = warp_max(keep ? p.x : -CUDART_INF_F), hy = warp_max(keep ? p.y : -CUDART_INF_F), hz = warp_max(keep ? p.z : -CUDART_INF_F);
+  if (lane_id() == 0) {
+    leaf_bounds[2 * (size_t)(i >> 5)] = make_float4(lx, ly, lz, 0.f);
+    leaf_bounds[2 * (size_t)(i >> 5) + 1] = make_float4(hx, hy, hz, 0.f);
+  }
 }
 
 // a3 removeNaNNormalsFromPointCloud + ExtractIndices (src/tunnel_processing.cpp:74-85): stable

@@ -152,6 +152,10 @@ GM_API gm_status gm_set_params(gm_ctx* ctx, const gm_params* p);
 /* Use an existing cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own (non-blocking)
  * stream; to run on CUDA's legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1). */
 GM_API gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream);
+/* Inlier-counting strategy of gm_ransac: 0 (default) = tile-culled over the cell-sorted cloud of the
+ * scan whenever gm_normals produced one (identical counts, hypotheses whose inlier band provably
+ * misses a 32-point tile are skipped for it); 1 = always the brute-force FP32 kernels. */
+GM_API gm_status gm_set_count_mode(gm_ctx* ctx, int32_t mode);
 GM_API const char* gm_last_error(const gm_ctx* ctx);
 GM_API const char* gm_status_string(gm_status s);
 GM_API int32_t gm_version(void);

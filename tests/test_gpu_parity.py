@@ -641,6 +641,48 @@ def test_full_size_properties_1m_points():
     assert abs(abs(mp["coef"][3]) - 1.5) < 5e-3 and abs(mc["coef"][6] - 2.5) < 0.3   # straight cylinder on a curved tunnel
 
 
+@pytest.mark.parametrize("n,radius,tau", [(90_000, 0.1, 0.05), (30_000, 0.3, 0.2), (700, 0.5, 0.05), (20, 1.0, 0.05)])
+def test_tile_culled_counts_equal_brute_force_and_oracle(n, radius, tau):
+    """gm_ransac counts over the cell-sorted cloud with tile culling (mode 0, the default after
+    gm_normals) == the brute-force kernels (mode 1) == the oracle, bit for bit: junk points (NaN, inf,
+    outliers), more hypotheses than one chunk, a sharded hypothesis range, tiny clouds."""
+    pts = _scan_with_junk(n, seed=77) if n >= 1000 else synth.curved_tunnel(n, seed=78, outlier_frac=0.1)
+    Hp, Hc = 1300, 1100
+    with _ctx(n, neighborRadius=radius, ransacThreshold=tau) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        nv = ctx.counts().n_valid
+        cloud_c, normals_c = ctx.download_cloud(1), ctx.download_normals(1)
+        ps = synth.sample_indices(nv, Hp, 3, seed=13)
+        cs = synth.sample_indices(nv, Hc, 2, seed=14)
+        ps[3] = [0, 0, 1]
+        got = {}
+        for mode in (0, 1):
+            ctx.set_count_mode(mode)
+            ctx.ransac(capi.GM_MODEL_PLANE, ps)
+            ctx.ransac(capi.GM_MODEL_CYLINDER, cs)
+            got[mode] = (ctx.download_hypotheses(0, Hp)[2], ctx.download_hypotheses(1, Hc)[2])
+            ctx.ransac_select(0)
+            ctx.ransac_select(1)
+            got[mode] += (ctx.model(0)["best_id"], ctx.model(1)["best_id"])
+        ctx.set_count_mode(0)
+        ctx.ransac(capi.GM_MODEL_PLANE, ps, 517, 1203)   # a rank's shard: ids outside score -1
+        shard = ctx.download_hypotheses(0, Hp)[2]
+        assert ctx.counts().device_error == 0
+    coef, valid = O.plane_hypotheses(cloud_c, ps)
+    ref_p = O.count_plane(cloud_c, coef, valid, tau)
+    m7, t12, cvalid = O.cyl_hypotheses(cloud_c, normals_c, cs, 0.5, 10.0, tau)
+    ref_c = O.count_cyl(cloud_c, t12, cvalid)
+    for mode in (0, 1):
+        assert np.array_equal(got[mode][0], ref_p), f"plane counts, mode {mode}"
+        assert np.array_equal(got[mode][1], ref_c), f"cylinder counts, mode {mode}"
+    assert got[0][2:] == got[1][2:]
+    assert np.array_equal(shard[517:1203], ref_p[517:1203]) and (shard[:517] == -1).all() and (shard[1203:] == -1).all()
+    if n >= 30_000:
+        assert ref_p.max() > 0.1 * nv and ref_c.max() > 0.1 * nv   # the test is not vacuous
+
+
 def test_count_linearity_over_a_split_cloud():
     """counts(cloud) == counts(first half) + counts(second half) for fixed hypotheses: exact."""
     cloud, nrm = _compacted_scan(60_000, seed=51)

@@ -99,6 +99,9 @@ struct gm_ctx {
   unsigned* d_ucell_key = nullptr;
   int *d_cell_id = nullptr, *d_ucell_start = nullptr, *d_nbr = nullptr, *d_valid_map = nullptr;
   int2* d_runs = nullptr;
+  int* d_cell_nruns = nullptr;
+  BlockEntry* d_tab = nullptr;  // dense block table of the neighbour grid (1 << (key_bits - 6) entries)
+  size_t tab_entries = 0;
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
   unsigned char* d_labels = nullptr;
   unsigned long long* d_state64 = nullptr;
@@ -203,7 +206,7 @@ GridSpec make_grid(const gm_params& p) {
   double bound = std::fabs(p.boxFilterBound);
   double cell = (double)rf * (1.0 + 1.0 / 256.0);
   if (!(cell > 0.0)) cell = 1e-3;
-  const int kMaxDim = 1023;
+  const int kMaxDim = 1020;  // 255 blocks of 4 cells per axis: 8 block bits, all-ones block code stays unused
   double span = 2.0 * bound;
   if (span / cell + 1.0 > (double)kMaxDim) cell = span / (double)(kMaxDim - 1);
   int dim = (int)std::floor(span / cell) + 1;
@@ -212,8 +215,26 @@ GridSpec make_grid(const gm_params& p) {
   g.cell = (float)cell;
   g.inv_cell = (float)(1.0 / cell);
   g.dim = dim;
-  g.ncells = (unsigned)dim * (unsigned)dim * (unsigned)dim;
+  const int nb = (dim + 3) / 4;
+  int bpa = 1;
+  while ((1 << bpa) <= nb) ++bpa;  // (1 << bpa) > nb: block coordinate 2^bpa - 1 is never used
+  g.key_bits = 3 * bpa + 6;
+  g.sentinel = g.key_bits >= 32 ? 0xFFFFFFFFu : ((1u << g.key_bits) - 1u);
   return g;
+}
+
+// (Re)allocate and zero the dense block table for the current grid.
+gm_status ensure_block_table(gm_ctx* ctx) {
+  const size_t need = (size_t)1 << (ctx->grid.key_bits - 6);
+  if (need != ctx->tab_entries) {
+    if (ctx->d_tab) cudaFree(ctx->d_tab);
+    ctx->d_tab = nullptr;
+    GM_CUDA(cudaMalloc((void**)&ctx->d_tab, need * sizeof(BlockEntry)));
+    ctx->tab_entries = need;
+  }
+  GM_CUDA(cudaMemset(ctx->d_tab, 0, need * sizeof(BlockEntry)));
+  GM_CUDA(cudaMemset(&ctx->d_st->tab_cells, 0, sizeof(int)));
+  return GM_OK;
 }
 
 // A fresh epoch for the tile states of one launch (30-bit; on wrap the arrays are cleared once).
@@ -336,7 +357,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_normals, 2 * N); A(d_normals_c, 2 * N); A(d_centroid, N); A(d_nn_normal, 2 * N);
   A(d_keys[0], N); A(d_keys[1], N); A(d_vals[0], N); A(d_vals[1], N);
   A(d_ucell_key, N + 1); A(d_cell_id, N); A(d_ucell_start, N + 1); A(d_nbr, N); A(d_valid_map, N);
-  A(d_runs, 9 * N);
+  A(d_runs, GRID_RUNS * N); A(d_cell_nruns, N);
   A(d_vkey_pt, N); A(d_assign, N); A(d_vox_start, N + 1); A(d_vox_key, N); A(d_vox_count, N); A(d_nn_idx, N);
   A(d_labels, N);
   A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
@@ -377,6 +398,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
     if ((size_t)ctx->gn_blocks * 2 * GN_NV > kPartialsRegion) return fail(cudaErrorInvalidValue, "partials capacity");
   }
   ctx->grid = make_grid(ctx->prm);
+  if (ensure_block_table(ctx) != GM_OK) { std::fprintf(stderr, "gm_create: %s\n", ctx->err.c_str()); gm_destroy(ctx); return GM_ERR_CUDA; }
   *out = ctx;
   return GM_OK;
 }
@@ -384,7 +406,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
 void gm_destroy(gm_ctx* ctx) {
   if (!ctx) return;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
+  void* ptrs[] = {ctx->d_tab, ctx->d_cell_nruns, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
@@ -409,8 +431,16 @@ void gm_destroy(gm_ctx* ctx) {
 gm_status gm_set_params(gm_ctx* ctx, const gm_params* p) {
   if (!ctx || validate_params(p) != GM_OK) return GM_ERR_INVALID_ARG;
   if (p->maxSlices > ctx->prm.maxSlices) { ctx->err = "maxSlices cannot grow after gm_create"; return GM_ERR_CAPACITY; }
+  const GridSpec old = ctx->grid;
   ctx->prm = *p;
   ctx->grid = make_grid(ctx->prm);
+  if (old.key_bits != ctx->grid.key_bits || old.dim != ctx->grid.dim || old.cell != ctx->grid.cell) {
+    // a different neighbour grid: the block table of the old one is meaningless (rare path, synchronous)
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->tab_entries = 0;  // forces the clear below even when the size is unchanged
+    gm_status s = ensure_block_table(ctx);
+    if (s != GM_OK) return s;
+  }
   return GM_OK;
 }
 
@@ -526,19 +556,20 @@ gm_status gm_normals(gm_ctx* ctx) {
     int buf = 0;
     gm_status s;
     { SegTimer seg_(ctx, SEG_GRID_SORT);
-      s = radix_sort(ctx, n_ptr, n, bits_for((unsigned long long)g.ncells), &buf); }
+      s = radix_sort(ctx, n_ptr, n, g.key_bits, &buf); }
     if (s != GM_OK) return s;
     unsigned epoch = 0;
     if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_GRID_BUILD);
+    GM_LAUNCH(ctx, k_clear_blocks, std::min(div_up((long long)n, 256), ctx->num_sms * 8), 256, ctx->d_ucell_key, ctx->d_st, g.sentinel, ctx->d_tab);
     GM_LAUNCH(ctx, k_cell_heads, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_crop, n_ptr,
-              g.ncells, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_state64, epoch, ctx->d_st);
-    GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n * 9, 256), ctx->num_sms * 16), 256, ctx->d_ucell_key,
-              ctx->d_ucell_start, ctx->d_st, g, ctx->d_runs); }
+              g.sentinel, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_tab, ctx->d_state64, epoch, ctx->d_st);
+    GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_ucell_key,
+              ctx->d_ucell_start, ctx->d_tab, ctx->d_st, g, ctx->d_runs, ctx->d_cell_nruns); }
     float rf = (float)ctx->prm.neighborRadius;
     float r2 = rf * rf;
     { SegTimer seg_(ctx, SEG_NORMALS);
-      GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, n_ptr, r2,
+      GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
                 ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds); }
     if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_COMPACT);
@@ -604,7 +635,7 @@ gm_status gm_voxel(gm_ctx* ctx) {
     if (ctx->have_normals) {
       SegTimer seg_(ctx, SEG_VOX_NN);
       GM_LAUNCH(ctx, k_voxel_nn, std::min(div_up((long long)n * 32, NN_BLOCK), ctx->num_sms * 16), NN_BLOCK, ctx->d_centroid, ctx->d_sorted,
-                ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_runs, ctx->d_valid_map, ctx->d_normals_c, ctx->grid, ctx->prm.nn_index_mode,
+                ctx->d_tab, ctx->d_ucell_start, ctx->d_runs, ctx->d_cell_nruns, ctx->d_valid_map, ctx->d_normals_c, ctx->grid, ctx->prm.nn_index_mode,
                 ctx->d_st, ctx->d_nn_idx, ctx->d_nn_normal);
     }
     GM_CHECK_LAUNCHES(ctx);

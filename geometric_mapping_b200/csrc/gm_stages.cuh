@@ -28,17 +28,59 @@ __device__ __forceinline__ void d_vox_reset(VoxState* v) {
 struct DevState {
   int n_input, n_crop, n_valid, n_cells, nn_oor, error;
   int n_sorted_finite;  // cropped points with finite coordinates (sorted before the NaN tail)
-  int pad_;
+  int tab_cells;        // occupied cells currently recorded in the block table (cleared by the next build)
   VoxState vox;         // VoxelGrid of the compacted cloud (vox.n mirrors n_valid)
 };
 
 struct GridSpec {
-  float origin;    // same for x,y,z: -bound
-  float inv_cell;  // 1/cell
+  float origin;      // same for x,y,z: -bound
+  float inv_cell;    // 1/cell
   float cell;
-  int dim;         // cells per axis
-  unsigned ncells; // dim^3 (sentinel key for non-finite points)
+  int dim;           // cells per axis
+  int key_bits;      // bits of a cell key (3 * block bits + 6); the block table has 1 << (key_bits - 6) entries
+  unsigned sentinel; // key of non-finite points: all ones in key_bits, never a real cell
 };
+
+// Cell key = Morton code of the 4x4x4-cell BLOCK the cell lies in, then the cell's row-major
+// position inside the block (x fastest).  Sorting by it keeps two properties at once:
+//   * cells adjacent in x inside a block are adjacent keys, so the 3-cell x-neighbourhood of a cell
+//     is one contiguous run of the sorted cloud, or two when it crosses a block face;
+//   * consecutive points are spatially compact in all three axes (a 512-point tile of the C1 scan is
+//     a ~0.3 m blob instead of a 6 m long row), which is what makes the tile-culled inlier counting
+//     (gm_ransac.cuh) effective.
+constexpr int GRID_RUNS = 18;  // per occupied cell: 9 (dy,dz) rows x up to 2 x-segments
+
+// Dense table over the blocks (index = Morton block code): which of the 64 cells of the block are
+// occupied and the rank of its first occupied cell in the sorted cell list.  The rank of any cell is
+// then first + popc(mask below its local code): neighbour lookups need no search at all.  Only the
+// entries of occupied blocks are ever written, and the next build clears exactly those (O(cells)).
+struct __align__(16) BlockEntry { unsigned long long mask; int first; int pad_; };
+__host__ __device__ __forceinline__ unsigned gm_spread3(unsigned x) {  // 10 bits -> every third bit
+  x &= 0x3FFu;
+  x = (x | (x << 16)) & 0x030000FFu;
+  x = (x | (x << 8)) & 0x0300F00Fu;
+  x = (x | (x << 4)) & 0x030C30C3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+__host__ __device__ __forceinline__ unsigned gm_compact3(unsigned x) {
+  x &= 0x09249249u;
+  x = (x | (x >> 2)) & 0x030C30C3u;
+  x = (x | (x >> 4)) & 0x0300F00Fu;
+  x = (x | (x >> 8)) & 0x030000FFu;
+  x = (x | (x >> 16)) & 0x3FFu;
+  return x;
+}
+__host__ __device__ __forceinline__ unsigned gm_cell_key(int cx, int cy, int cz) {
+  const unsigned m = gm_spread3((unsigned)cx >> 2) | (gm_spread3((unsigned)cy >> 2) << 1) | (gm_spread3((unsigned)cz >> 2) << 2);
+  return (m << 6) | (((unsigned)cz & 3u) << 4) | (((unsigned)cy & 3u) << 2) | ((unsigned)cx & 3u);
+}
+__host__ __device__ __forceinline__ void gm_cell_coords(unsigned key, int& cx, int& cy, int& cz) {
+  const unsigned m = key >> 6;
+  cx = (int)((gm_compact3(m) << 2) | (key & 3u));
+  cy = (int)((gm_compact3(m >> 1) << 2) | ((key >> 2) & 3u));
+  cz = (int)((gm_compact3(m >> 2) << 2) | ((key >> 4) & 3u));
+}
 
 constexpr int CP_BLOCK = 256;
 constexpr int CP_IPT = 4;                      // items per thread where each item is register heavy
@@ -52,7 +94,7 @@ __device__ __forceinline__ bool finite3(float x, float y, float z) { return isfi
 __global__ void k_begin_scan(DevState* st, int n_input) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->n_input = n_input; st->n_crop = 0; st->n_valid = 0; st->n_cells = 0;
-    st->nn_oor = 0; st->error = 0; st->n_sorted_finite = 0; st->pad_ = 0;
+    st->nn_oor = 0; st->error = 0; st->n_sorted_finite = 0;  // tab_cells survives: it describes the block table
     d_vox_reset(&st->vox);
   }
 }
@@ -114,12 +156,12 @@ __global__ void k_cell_keys(const float4* __restrict__ pts, const int* __restric
   const int n = *n_ptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
-    unsigned key = g.ncells;
+    unsigned key = g.sentinel;
     if (finite3(p.x, p.y, p.z)) {
       int cx = min(max((int)floorf((p.x - g.origin) * g.inv_cell), 0), g.dim - 1);
       int cy = min(max((int)floorf((p.y - g.origin) * g.inv_cell), 0), g.dim - 1);
       int cz = min(max((int)floorf((p.z - g.origin) * g.inv_cell), 0), g.dim - 1);
-      key = (unsigned)cx + (unsigned)g.dim * ((unsigned)cy + (unsigned)g.dim * (unsigned)cz);
+      key = gm_cell_key(cx, cy, cz);
     }
     keys[i] = key;
     idx[i] = (unsigned)i;
@@ -130,13 +172,14 @@ __global__ void k_cell_keys(const float4* __restrict__ pts, const int* __restric
 // and record each cell's key and first sorted position (stable compaction of the "head" flags).
 __global__ void __launch_bounds__(CP_BLOCK)
 k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
-             const int* __restrict__ n_ptr, unsigned ncells, float4* __restrict__ sorted_pts, int* __restrict__ cell_id,
-             unsigned* __restrict__ ucell_key, int* __restrict__ ucell_start, unsigned long long* state, unsigned epoch, DevState* st) {
+             const int* __restrict__ n_ptr, unsigned sentinel, float4* __restrict__ sorted_pts, int* __restrict__ cell_id,
+             unsigned* __restrict__ ucell_key, int* __restrict__ ucell_start, BlockEntry* __restrict__ tab,
+             unsigned long long* state, unsigned epoch, DevState* st) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = *n_ptr;
   const int tile = blockIdx.x, base = tile * CPL_TILE;
   if (base >= n) return;
-  bool f[CPL_IPT];
+  bool f[CPL_IPT], bh[CPL_IPT];
   unsigned key[CPL_IPT];
   int nfinite_local = 0;
 #pragma unroll
@@ -148,13 +191,14 @@ k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ si
       key[j] = skeys[i];
       unsigned prev = (i > 0) ? skeys[i - 1] : 0xFFFFFFFFu;
       f[j] = (i == 0) || (key[j] != prev);
+      bh[j] = (i == 0) || ((key[j] >> 6) != (prev >> 6));  // first cell of its block
       unsigned src = sidx[i];
       float4 p = pts[src];
       p.w = __int_as_float((int)src);
       sorted_pts[i] = p;
-      if (key[j] < ncells) {
+      if (key[j] != sentinel) {
         // last finite position + 1 == number of finite points (sentinel keys sort last)
-        if (i + 1 == n || skeys[i + 1] >= ncells) nfinite_local = i + 1;
+        if (i + 1 == n || skeys[i + 1] == sentinel) nfinite_local = i + 1;
       }
     }
   }
@@ -167,10 +211,26 @@ k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ si
     if (i < n) {
       int id = f[j] ? (int)ranks[j] : (int)ranks[j] - 1;
       cell_id[i] = id;
-      if (f[j]) { ucell_key[id] = key[j]; ucell_start[id] = i; }
+      if (f[j]) {
+        ucell_key[id] = key[j]; ucell_start[id] = i;
+        if (key[j] != sentinel) {
+          BlockEntry* e = tab + (key[j] >> 6);
+          atomicOr(&e->mask, 1ull << (key[j] & 63u));
+          if (bh[j]) e->first = id;
+        }
+      }
     }
   }
-  if (base + CPL_TILE >= n && threadIdx.x == 0) st->n_cells = (int)total;
+  if (base + CPL_TILE >= n && threadIdx.x == 0) { st->n_cells = (int)total; st->tab_cells = (int)total; }
+}
+
+// Clear the block-table entries of the previous build (its sorted cell list is still in ucell_key).
+__global__ void k_clear_blocks(const unsigned* __restrict__ ucell_key, DevState* st, unsigned sentinel, BlockEntry* __restrict__ tab) {
+  const int U = st->tab_cells;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < U; j += gridDim.x * blockDim.x) {
+    const unsigned key = ucell_key[j];
+    if (key != sentinel) { BlockEntry z; z.mask = 0ull; z.first = 0; z.pad_ = 0; tab[key >> 6] = z; }
+  }
 }
 
 __device__ __forceinline__ int lower_bound_u32(const unsigned* __restrict__ a, int n, unsigned key) {
@@ -182,50 +242,55 @@ __device__ __forceinline__ int lower_bound_u32(const unsigned* __restrict__ a, i
   return lo;
 }
 
-// Sorted-position range [start,end) of the cells kx0..kx1 of row (cy,cz); empty if out of the grid.
-__device__ __forceinline__ int2 cell_run(const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
-                                         int U, int n_finite, int dim, int x0, int x1, int cy, int cz) {
-  if (cy < 0 || cz < 0 || cy >= dim || cz >= dim) return make_int2(0, 0);
-  x0 = max(x0, 0); x1 = min(x1, dim - 1);
-  if (x0 > x1) return make_int2(0, 0);
-  unsigned rowbase = (unsigned)dim * ((unsigned)cy + (unsigned)dim * (unsigned)cz);
-  int a = lower_bound_u32(ucell_key, U, rowbase + (unsigned)x0);
-  int b = lower_bound_u32(ucell_key, U, rowbase + (unsigned)x1 + 1u);
-  int s = (a < U) ? min(ucell_start[a], n_finite) : n_finite;
-  int e = (b < U) ? min(ucell_start[b], n_finite) : n_finite;
-  return make_int2(s, e);
+// Sorted-position range [start,end) of the cells x0..x1 of row (cy,cz), all inside ONE 4-cell x-block
+// (consecutive local codes): two popcounts on the block's occupancy mask, no search.
+__device__ __forceinline__ int2 cell_segment(const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start,
+                                             int U, int n_finite, int x0, int x1, int cy, int cz) {
+  const unsigned key = gm_cell_key(x0, cy, cz);
+  const BlockEntry e = tab[key >> 6];
+  const unsigned c0 = key & 63u, c1 = c0 + (unsigned)(x1 - x0);
+  const int a = e.first + __popcll(e.mask & ((1ull << c0) - 1ull));
+  const int b = e.first + __popcll(e.mask & ((2ull << c1) - 1ull));
+  if (a == b) return make_int2(0, 0);
+  const int s = min(ucell_start[a], n_finite);
+  const int t = (b < U) ? min(ucell_start[b], n_finite) : n_finite;
+  return make_int2(s, t);
 }
 
-// For every occupied cell: the 9 sorted-position runs (one per (dy,dz) row, x-1..x+1) that cover
-// its 27-cell neighbourhood.  The cell's own row needs no search (its neighbours in x are the
-// adjacent entries of the sorted cell list); every other row takes ONE binary search for the first
-// cell >= (x-1) and a walk over at most 3 entries for the end of the run.
-__global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start,
-                            const DevState* __restrict__ st, GridSpec g, int2* __restrict__ runs) {
+// For every occupied cell: the non-empty sorted-position runs that cover its 27-cell neighbourhood
+// (per (dy,dz) row the part of x-1..x+1 in the first x-block it touches and the part in the next one),
+// runs that happen to be adjacent in the sorted cloud merged; at most GRID_RUNS of them.
+__global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start, const BlockEntry* __restrict__ tab,
+                            const DevState* __restrict__ st, GridSpec g, int2* __restrict__ runs, int* __restrict__ nruns) {
   const int U = st->n_cells, nf = st->n_sorted_finite;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < U * 9; t += gridDim.x * blockDim.x) {
-    const int j = t / 9, k = t - j * 9;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < U; j += gridDim.x * blockDim.x) {
     const unsigned key = ucell_key[j];
-    int2 r = make_int2(0, 0);
-    if (key < g.ncells) {
-      const int cx = (int)(key % (unsigned)g.dim);
-      const int cy = (int)((key / (unsigned)g.dim) % (unsigned)g.dim) + (k % 3) - 1;
-      const int cz = (int)(key / ((unsigned)g.dim * (unsigned)g.dim)) + (k / 3) - 1;
-      if (cy >= 0 && cz >= 0 && cy < g.dim && cz < g.dim) {
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim - 1);
-        const unsigned rowbase = (unsigned)g.dim * ((unsigned)cy + (unsigned)g.dim * (unsigned)cz);
-        const unsigned klo = rowbase + (unsigned)x0, khi = rowbase + (unsigned)x1;
-        int a;
-        if (k == 4) a = (j > 0 && ucell_key[j - 1] >= klo) ? j - 1 : j;  // own row: previous entry is x-1 or another row
-        else a = lower_bound_u32(ucell_key, U, klo);
-        int b2 = a;
-        while (b2 < U && b2 < a + 3 && ucell_key[b2] <= khi) ++b2;       // at most 3 cells in the run
-        const int s0 = (a < U) ? min(ucell_start[a], nf) : nf;
-        const int e0 = (b2 < U) ? min(ucell_start[b2], nf) : nf;
-        r = make_int2(s0, e0);
+    int2* out = runs + (size_t)j * GRID_RUNS;
+    int m = 0;
+    int2 cur = make_int2(0, 0);
+    if (key != g.sentinel) {
+      int cx, cy0, cz0;
+      gm_cell_coords(key, cx, cy0, cz0);
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim - 1);
+      const int split = x0 | 3;  // last cell of x0's block
+#pragma unroll 1
+      for (int k = 0; k < 9; ++k) {
+        const int cy = cy0 + (k % 3) - 1, cz = cz0 + (k / 3) - 1;
+        if (cy < 0 || cz < 0 || cy >= g.dim || cz >= g.dim) continue;
+#pragma unroll
+        for (int seg = 0; seg < 2; ++seg) {
+          if (seg == 1 && x1 <= split) break;
+          const int2 r = (seg == 0) ? cell_segment(tab, ucell_start, U, nf, x0, min(x1, split), cy, cz)
+                                    : cell_segment(tab, ucell_start, U, nf, split + 1, x1, cy, cz);
+          if (r.y <= r.x) continue;
+          if (cur.y == r.x && cur.y > cur.x) { cur.y = r.y; continue; }  // contiguous with the pending run
+          if (cur.y > cur.x) out[m++] = cur;
+          cur = r;
+        }
       }
+      if (cur.y > cur.x) out[m++] = cur;
     }
-    runs[t] = r;
+    nruns[j] = m;
   }
 }
 
@@ -309,7 +374,7 @@ __device__ void d_eigen33_smallest(float c00, float c01, float c02, float c11, f
 // [2*leaf+1] = max; an empty leaf has min = +inf, max = -inf.
 constexpr int NRM_BLOCK = 128;
 __global__ void __launch_bounds__(NRM_BLOCK)
-k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs,
+k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs, const int* __restrict__ nruns,
           const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count,
           float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds) {
   const int n = *n_ptr;
@@ -322,22 +387,32 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
   float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
   int cnt = 0;
   if (active && finite3(p.x, p.y, p.z)) {
-    const int2* rr = runs + (size_t)cell_id[i] * 9;
+    const int cid = cell_id[i];
+    const int2* rr = runs + (size_t)cid * GRID_RUNS;
+    const int nr = nruns[cid];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
-#pragma unroll 1
-    for (int k = 0; k < 9; ++k) {
-      const int2 r = rr[k];
-#pragma unroll 4
-      for (int t = r.x; t < r.y; ++t) {
-        const float4 q = sp[t];
-        float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-        float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
-        if (d2 < r2) {
-          a0 = fmaf(q.x, q.x, a0); a1 = fmaf(q.x, q.y, a1); a2 = fmaf(q.x, q.z, a2);
-          a3 = fmaf(q.y, q.y, a3); a4 = fmaf(q.y, q.z, a4); a5 = fmaf(q.z, q.z, a5);
-          a6 += q.x; a7 += q.y; a8 += q.z;
-          ++cnt;
-        }
+    // ONE flat loop over the candidates of all runs (not a loop over runs with a loop over candidates
+    // inside): lanes of a warp are points of neighbouring cells whose run lists differ, and the warp
+    // pays max-over-lanes of the TOTAL candidate count instead of the sum of per-run maxima.
+    // The next run is fetched one switch ahead so the switch itself does not wait on memory.
+    int k = 0, t = 0, end = 0;
+    int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
+    for (;;) {
+      if (t >= end) {
+        if (k >= nr) break;
+        t = nxt.x; end = nxt.y;
+        ++k;
+        if (k < nr) nxt = rr[k];
+      }
+      const float4 q = sp[t];
+      ++t;
+      float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+      float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
+      if (d2 < r2) {
+        a0 = fmaf(q.x, q.x, a0); a1 = fmaf(q.x, q.y, a1); a2 = fmaf(q.x, q.z, a2);
+        a3 = fmaf(q.y, q.y, a3); a4 = fmaf(q.y, q.z, a4); a5 = fmaf(q.z, q.z, a5);
+        a6 += q.x; a7 += q.y; a8 += q.z;
+        ++cnt;
       }
     }
     if (cnt >= 3) {
@@ -591,9 +666,22 @@ __device__ __forceinline__ void d_nn_scan(const float4* __restrict__ sp, const i
   }
 }
 
+// scan the cells x0..x1 of row (cy,cz): one segment per 4-cell x-block the span touches
+__device__ __forceinline__ void d_nn_scan_row(const float4* __restrict__ sp, const int* __restrict__ valid_map, int mode,
+                                              const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start,
+                                              int U, int nf, int dim, int x0, int x1, int cy, int cz, const float4 c, float& best, int& bi) {
+  if (cy < 0 || cz < 0 || cy >= dim || cz >= dim) return;
+  x0 = max(x0, 0); x1 = min(x1, dim - 1);
+  for (int xs = x0; xs <= x1;) {
+    const int xe = min(x1, xs | 3);
+    d_nn_scan(sp, valid_map, mode, cell_segment(tab, ucell_start, U, nf, xs, xe, cy, cz), c, best, bi);
+    xs = xe + 1;
+  }
+}
+
 __global__ void __launch_bounds__(NN_BLOCK)
 k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
-           const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start, const int2* __restrict__ runs,
+           const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start, const int2* __restrict__ runs, const int* __restrict__ nruns,
            const int* __restrict__ valid_map, const float4* __restrict__ normals_c, GridSpec g,
            int mode, DevState* st, int* __restrict__ nn_idx, float4* __restrict__ nn_normal) {
   const int V = st->vox.n_voxels, U = st->n_cells, nf = st->n_sorted_finite, nvalid = st->n_valid;
@@ -610,13 +698,13 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
       if (k == 1) {
         // the 27-cell cube as 9 rows of 3 cells; if the centroid's own cell is occupied (the usual
         // case) its runs were already computed for the normals stage: one search instead of 18
-        const unsigned ckey = (unsigned)cx + (unsigned)g.dim * ((unsigned)cy + (unsigned)g.dim * (unsigned)cz);
-        const int jc = lower_bound_u32(ucell_key, U, ckey);
-        const bool occupied = jc < U && ucell_key[jc] == ckey;
-        if (lane < 9) {
-          int2 r = occupied ? runs[(size_t)jc * 9 + lane]
-                            : cell_run(ucell_key, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1);
-          d_nn_scan(sp, valid_map, mode, r, c, best, bi);
+        const unsigned ckey = gm_cell_key(cx, cy, cz);
+        const BlockEntry e = tab[ckey >> 6];
+        if ((e.mask >> (ckey & 63u)) & 1ull) {
+          const int jc = e.first + __popcll(e.mask & ((1ull << (ckey & 63u)) - 1ull));
+          if (lane < nruns[jc]) d_nn_scan(sp, valid_map, mode, runs[(size_t)jc * GRID_RUNS + lane], c, best, bi);
+        } else if (lane < 9) {
+          d_nn_scan_row(sp, valid_map, mode, tab, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1, c, best, bi);
         }
       } else {
         // shell k: 8k perimeter rows with the full x span + (2k-1)^2 inner rows with two end cells
@@ -634,8 +722,7 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
             dy = cell % inner - (k - 1); dz = cell / inner - (k - 1);
             x0 = x1 = (u2 & 1) ? cx + k : cx - k;
           }
-          int2 r = cell_run(ucell_key, ucell_start, U, nf, g.dim, x0, x1, cy + dy, cz + dz);
-          d_nn_scan(sp, valid_map, mode, r, c, best, bi);
+          d_nn_scan_row(sp, valid_map, mode, tab, ucell_start, U, nf, g.dim, x0, x1, cy + dy, cz + dz, c, best, bi);
         }
       }
       // lexicographic (d2, index) minimum over the warp

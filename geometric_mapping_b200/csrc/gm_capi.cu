@@ -99,7 +99,7 @@ struct gm_ctx {
   unsigned* d_ucell_key = nullptr;
   int *d_cell_id = nullptr, *d_ucell_start = nullptr, *d_nbr = nullptr, *d_valid_map = nullptr;
   int2* d_runs = nullptr;
-  int* d_cell_nruns = nullptr;
+  int2* d_cell_nruns = nullptr;  // per occupied cell: {number of runs, number of candidates}
   BlockEntry* d_tab = nullptr;  // dense block table of the neighbour grid (1 << (key_bits - 6) entries)
   size_t tab_entries = 0;
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;

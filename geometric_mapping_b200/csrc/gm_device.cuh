@@ -24,6 +24,14 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
+// ---- packed f32x2 arithmetic (sm_100: SASS FFMA2 / FADD2) --------------------------------------
+// Each half is an IEEE round-to-nearest operation, bit-identical to the scalar fmaf / add.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 d_pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void d_unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 d_fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 d_add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // ---- float <-> order-preserving int (for atomicMin/atomicMax on floats) -------------------
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);

@@ -166,10 +166,6 @@ __device__ __forceinline__ CylTest d_load_cyl_test(const float* __restrict__ t12
 // idioms in tools/microbench/count_variants.cu, profiles/r01_microbench_count.md).
 // Counts stay in registers for the whole slice; one integer atomicAdd per (thread, hypothesis).
 // grid = (point slices, hypothesis groups).
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 d_pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void d_unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 d_fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 // cnt += (v < thr)   [v is already |.|; NaN compares false]
 __device__ __forceinline__ void d_count_lt(float v, float thr, int& cnt) {
   asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(cnt) : "f"(v), "f"(thr));

@@ -261,7 +261,7 @@ __device__ __forceinline__ int2 cell_segment(const BlockEntry* __restrict__ tab,
 // (per (dy,dz) row the part of x-1..x+1 in the first x-block it touches and the part in the next one),
 // runs that happen to be adjacent in the sorted cloud merged; at most GRID_RUNS of them.
 __global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* __restrict__ ucell_start, const BlockEntry* __restrict__ tab,
-                            const DevState* __restrict__ st, GridSpec g, int2* __restrict__ runs, int* __restrict__ nruns) {
+                            const DevState* __restrict__ st, GridSpec g, int2* __restrict__ runs, int2* __restrict__ cell_info) {
   const int U = st->n_cells, nf = st->n_sorted_finite;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < U; j += gridDim.x * blockDim.x) {
     const unsigned key = ucell_key[j];
@@ -290,7 +290,9 @@ __global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* _
       }
       if (cur.y > cur.x) out[m++] = cur;
     }
-    nruns[j] = m;
+    int total = 0;
+    for (int i = 0; i < m; ++i) total += out[i].y - out[i].x;
+    cell_info[j] = make_int2(m, total);  // number of runs, number of candidates
   }
 }
 
@@ -374,7 +376,7 @@ __device__ void d_eigen33_smallest(float c00, float c01, float c02, float c11, f
 // [2*leaf+1] = max; an empty leaf has min = +inf, max = -inf.
 constexpr int NRM_BLOCK = 128;
 __global__ void __launch_bounds__(NRM_BLOCK)
-k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs, const int* __restrict__ nruns,
+k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs, const int2* __restrict__ cell_info,
           const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count,
           float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds) {
   const int n = *n_ptr;
@@ -389,17 +391,21 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
   if (active && finite3(p.x, p.y, p.z)) {
     const int cid = cell_id[i];
     const int2* rr = runs + (size_t)cid * GRID_RUNS;
-    const int nr = nruns[cid];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+    const int2 info = cell_info[cid];
+    const int nr = info.x, total = info.y;
+    // accumulators as f32x2 pairs: (xx,xy) (xz,yz) (zz,-) (x,y); yy and z stay scalar
+    u64 a01 = 0ull, a24 = 0ull, a5w = 0ull, a67 = 0ull;
+    float a3 = 0.f, a8 = 0.f;
     // ONE flat loop over the candidates of all runs (not a loop over runs with a loop over candidates
     // inside): lanes of a warp are points of neighbouring cells whose run lists differ, and the warp
     // pays max-over-lanes of the TOTAL candidate count instead of the sum of per-run maxima.
-    // The next run is fetched one switch ahead so the switch itself does not wait on memory.
+    // The next run is fetched one switch ahead so the switch itself does not wait on memory.  A hit
+    // adds the candidate, a miss adds +0 (masked operands, no branch): same sums as a skipped add.
     int k = 0, t = 0, end = 0;
     int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
-    for (;;) {
-      if (t >= end) {
-        if (k >= nr) break;
+#pragma unroll 2
+    for (int i = 0; i < total; ++i) {
+      if (t == end) {  // runs are non-empty by construction
         t = nxt.x; end = nxt.y;
         ++k;
         if (k < nr) nxt = rr[k];
@@ -408,13 +414,19 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
       ++t;
       float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
       float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
-      if (d2 < r2) {
-        a0 = fmaf(q.x, q.x, a0); a1 = fmaf(q.x, q.y, a1); a2 = fmaf(q.x, q.z, a2);
-        a3 = fmaf(q.y, q.y, a3); a4 = fmaf(q.y, q.z, a4); a5 = fmaf(q.z, q.z, a5);
-        a6 += q.x; a7 += q.y; a8 += q.z;
-        ++cnt;
-      }
+      const bool hit = d2 < r2;
+      const float mx = hit ? q.x : 0.f, my = hit ? q.y : 0.f, mz = hit ? q.z : 0.f;
+      const u64 qxy = d_pack2(q.x, q.y);
+      a01 = d_fma2(d_pack2(mx, mx), qxy, a01);                 // xx, xy
+      a24 = d_fma2(d_pack2(mz, mz), qxy, a24);                 // xz, yz
+      a5w = d_fma2(d_pack2(mz, 0.f), d_pack2(q.z, 0.f), a5w);  // zz
+      a3 = fmaf(my, q.y, a3);
+      a67 = d_add2(a67, d_pack2(mx, my));
+      a8 += mz;
+      cnt += hit ? 1 : 0;
     }
+    float a0, a1, a2, a4, a5, a6, a7, junk;
+    d_unpack2(a01, a0, a1); d_unpack2(a24, a2, a4); d_unpack2(a5w, a5, junk); d_unpack2(a67, a6, a7);
     if (cnt >= 3) {
       float c = (float)cnt;
       a0 /= c; a1 /= c; a2 /= c; a3 /= c; a4 /= c; a5 /= c; a6 /= c; a7 /= c; a8 /= c;
@@ -681,7 +693,7 @@ __device__ __forceinline__ void d_nn_scan_row(const float4* __restrict__ sp, con
 
 __global__ void __launch_bounds__(NN_BLOCK)
 k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
-           const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start, const int2* __restrict__ runs, const int* __restrict__ nruns,
+           const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start, const int2* __restrict__ runs, const int2* __restrict__ cell_info,
            const int* __restrict__ valid_map, const float4* __restrict__ normals_c, GridSpec g,
            int mode, DevState* st, int* __restrict__ nn_idx, float4* __restrict__ nn_normal) {
   const int V = st->vox.n_voxels, U = st->n_cells, nf = st->n_sorted_finite, nvalid = st->n_valid;
@@ -702,7 +714,7 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
         const BlockEntry e = tab[ckey >> 6];
         if ((e.mask >> (ckey & 63u)) & 1ull) {
           const int jc = e.first + __popcll(e.mask & ((1ull << (ckey & 63u)) - 1ull));
-          if (lane < nruns[jc]) d_nn_scan(sp, valid_map, mode, runs[(size_t)jc * GRID_RUNS + lane], c, best, bi);
+          if (lane < cell_info[jc].x) d_nn_scan(sp, valid_map, mode, runs[(size_t)jc * GRID_RUNS + lane], c, best, bi);
         } else if (lane < 9) {
           d_nn_scan_row(sp, valid_map, mode, tab, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1, c, best, bi);
         }

@@ -122,7 +122,7 @@ SYMBOLS = [
     "gm_get_frame", "gm_download_hypotheses", "gm_get_model", "gm_download_labels", "gm_download_polyline",
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
     "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
-    "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode",
+    "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode", "gm_set_grid_box", "gm_set_owned_range", "gm_get_voxel_bbox", "gm_set_voxel_bbox",
 ]
 
 
@@ -191,6 +191,10 @@ def _lib():
         "gm_ransac_export_key": (i32, [vp, i32, vp]),
         "gm_ransac_import_key": (i32, [vp, i32, vp]),
         "gm_set_count_mode": (i32, [vp, i32]),
+        "gm_set_grid_box": (i32, [vp, vp, vp]),
+        "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
+        "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
+        "gm_set_voxel_bbox": (i32, [vp, vp, vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -281,6 +285,31 @@ class Context:
     def set_count_mode(self, mode: int):
         """0 = tile-culled inlier counting (default), 1 = brute-force FP32 kernels; identical counts."""
         self._ck(_lib().gm_set_count_mode(self._h, mode), "gm_set_count_mode")
+
+    def set_grid_box(self, mn=None, mx=None):
+        """Neighbour grid over [mn, mx] instead of the crop cube (map slabs); None clears."""
+        if mn is None:
+            self._ck(_lib().gm_set_grid_box(self._h, None, None), "gm_set_grid_box")
+        else:
+            a, b = np.ascontiguousarray(mn, np.float32), np.ascontiguousarray(mx, np.float32)
+            self._ck(_lib().gm_set_grid_box(self._h, _ptr(a), _ptr(b)), "gm_set_grid_box")
+
+    def set_owned_range(self, axis: int = -1, lo: float = 0.0, hi: float = 0.0):
+        """Points with coord[axis] outside [lo, hi) are halo: searched, then dropped with the NaN normals."""
+        self._ck(_lib().gm_set_owned_range(self._h, axis, lo, hi), "gm_set_owned_range")
+
+    def voxel_bbox(self):
+        a, b = np.empty(3, np.float32), np.empty(3, np.float32)
+        self._ck(_lib().gm_get_voxel_bbox(self._h, _ptr(a), _ptr(b)), "gm_get_voxel_bbox")
+        return a, b
+
+    def set_voxel_bbox(self, mn=None, mx=None):
+        """Override pcl::getMinMax3D before voxel() (global lattice of a multi-slab map); None clears."""
+        if mn is None:
+            self._ck(_lib().gm_set_voxel_bbox(self._h, None, None), "gm_set_voxel_bbox")
+        else:
+            a, b = np.ascontiguousarray(mn, np.float32), np.ascontiguousarray(mx, np.float32)
+            self._ck(_lib().gm_set_voxel_bbox(self._h, _ptr(a), _ptr(b)), "gm_set_voxel_bbox")
 
     def synchronize(self):
         self._ck(_lib().gm_synchronize(self._h), "gm_synchronize")

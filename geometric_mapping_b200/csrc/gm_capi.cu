@@ -87,6 +87,11 @@ struct gm_ctx {
   bool have_ransac[2] = {false, false}, have_model[2] = {false, false};
   int ransac_H[2] = {0, 0};
   GridSpec grid{};
+  bool have_grid_box = false;
+  double grid_box_min[3] = {0, 0, 0}, grid_box_max[3] = {0, 0, 0};
+  OwnedRange own{-1, 0.f, 0.f};
+  bool have_vox_bbox = false;
+  float vox_bbox[6] = {0, 0, 0, 0, 0, 0};
 
   // device buffers
   unsigned char* d_raw = nullptr;  // PointCloud2 staging (grown on demand)
@@ -198,29 +203,63 @@ int bits_for(unsigned long long max_value) {
   return std::max(b, 1);
 }
 
-// Neighbour grid over the crop box: cell slightly larger than the search radius so that, with
-// float rounding of the cell coordinate, every d < r neighbour lies in the 27-cell neighbourhood.
-GridSpec make_grid(const gm_params& p) {
+// Neighbour grid over a box (default: the crop cube; gm_set_grid_box narrows it to the region a map
+// slab actually occupies): cell slightly larger than the search radius so that, with float rounding of
+// the cell coordinate, every d < r neighbour lies in the 27-cell neighbourhood.  The cell grows when
+// the box would need more than 2^24 blocks (dense block table) or 1020 cells on an axis.
+GridSpec make_grid(const gm_params& p, const double* box_min, const double* box_max) {
   GridSpec g{};
   float rf = (float)p.neighborRadius;
   double bound = std::fabs(p.boxFilterBound);
+  double lo[3], span[3];
+  for (int a = 0; a < 3; ++a) {
+    double mn = box_min ? std::max(box_min[a], -bound) : -bound, mx = box_max ? std::min(box_max[a], bound) : bound;
+    if (!(mx > mn)) { mn = -bound; mx = bound; }
+    lo[a] = mn; span[a] = mx - mn;
+  }
   double cell = (double)rf * (1.0 + 1.0 / 256.0);
   if (!(cell > 0.0)) cell = 1e-3;
   const int kMaxDim = 1020;  // 255 blocks of 4 cells per axis: 8 block bits, all-ones block code stays unused
-  double span = 2.0 * bound;
-  if (span / cell + 1.0 > (double)kMaxDim) cell = span / (double)(kMaxDim - 1);
-  int dim = (int)std::floor(span / cell) + 1;
-  dim = std::min(std::max(dim, 1), kMaxDim);
-  g.origin = (float)(-bound);
+  for (;;) {
+    int total_bits = 0;
+    bool ok = true;
+    for (int a = 0; a < 3; ++a) {
+      int dim = (int)std::floor(span[a] / cell) + 1;
+      if (dim > kMaxDim) { ok = false; break; }
+      dim = std::max(dim, 1);
+      const int nb = (dim + 3) / 4;
+      int bits = 1;
+      while ((1 << bits) <= nb) ++bits;  // (1 << bits) > nb: block coordinate 2^bits - 1 is never used
+      g.dim[a] = dim; g.bits[a] = bits;
+      total_bits += bits;
+    }
+    if (ok && total_bits <= 24) break;
+    cell *= 1.25;
+  }
+  g.bmin = std::min(g.bits[0], std::min(g.bits[1], g.bits[2]));
+  for (int a = 0; a < 3; ++a) g.origin[a] = (float)lo[a];
   g.cell = (float)cell;
   g.inv_cell = (float)(1.0 / cell);
-  g.dim = dim;
-  const int nb = (dim + 3) / 4;
-  int bpa = 1;
-  while ((1 << bpa) <= nb) ++bpa;  // (1 << bpa) > nb: block coordinate 2^bpa - 1 is never used
-  g.key_bits = 3 * bpa + 6;
+  g.key_bits = g.bits[0] + g.bits[1] + g.bits[2] + 6;
   g.sentinel = g.key_bits >= 32 ? 0xFFFFFFFFu : ((1u << g.key_bits) - 1u);
   return g;
+}
+
+bool same_grid(const GridSpec& a, const GridSpec& b) { return std::memcmp(&a, &b, sizeof(GridSpec)) == 0; }
+
+gm_status ensure_block_table(gm_ctx* ctx);
+
+// Recompute the neighbour grid from the params / grid box; a different grid invalidates the block
+// table of the old one (rare path, synchronous).
+gm_status regrid(gm_ctx* ctx) {
+  const GridSpec old = ctx->grid;
+  ctx->grid = make_grid(ctx->prm, ctx->have_grid_box ? ctx->grid_box_min : nullptr, ctx->have_grid_box ? ctx->grid_box_max : nullptr);
+  if (!same_grid(old, ctx->grid)) {
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->tab_entries = 0;  // forces reallocation + clear
+    return ensure_block_table(ctx);
+  }
+  return GM_OK;
 }
 
 // (Re)allocate and zero the dense block table for the current grid.
@@ -397,7 +436,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
     ctx->gn_blocks = std::max(1, std::min(ctx->num_sms, per_sm * ctx->num_sms));
     if ((size_t)ctx->gn_blocks * 2 * GN_NV > kPartialsRegion) return fail(cudaErrorInvalidValue, "partials capacity");
   }
-  ctx->grid = make_grid(ctx->prm);
+  ctx->grid = make_grid(ctx->prm, nullptr, nullptr);
   if (ensure_block_table(ctx) != GM_OK) { std::fprintf(stderr, "gm_create: %s\n", ctx->err.c_str()); gm_destroy(ctx); return GM_ERR_CUDA; }
   *out = ctx;
   return GM_OK;
@@ -431,16 +470,44 @@ void gm_destroy(gm_ctx* ctx) {
 gm_status gm_set_params(gm_ctx* ctx, const gm_params* p) {
   if (!ctx || validate_params(p) != GM_OK) return GM_ERR_INVALID_ARG;
   if (p->maxSlices > ctx->prm.maxSlices) { ctx->err = "maxSlices cannot grow after gm_create"; return GM_ERR_CAPACITY; }
-  const GridSpec old = ctx->grid;
   ctx->prm = *p;
-  ctx->grid = make_grid(ctx->prm);
-  if (old.key_bits != ctx->grid.key_bits || old.dim != ctx->grid.dim || old.cell != ctx->grid.cell) {
-    // a different neighbour grid: the block table of the old one is meaningless (rare path, synchronous)
-    GM_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->tab_entries = 0;  // forces the clear below even when the size is unchanged
-    gm_status s = ensure_block_table(ctx);
-    if (s != GM_OK) return s;
+  return regrid(ctx);
+}
+
+gm_status gm_set_grid_box(gm_ctx* ctx, const float* min3, const float* max3) {
+  if (!ctx || ((min3 == nullptr) != (max3 == nullptr))) return GM_ERR_INVALID_ARG;
+  ctx->have_grid_box = min3 != nullptr;
+  if (min3) {
+    for (int a = 0; a < 3; ++a) {
+      if (!(max3[a] >= min3[a])) return GM_ERR_INVALID_ARG;
+      ctx->grid_box_min[a] = min3[a]; ctx->grid_box_max[a] = max3[a];
+    }
   }
+  return regrid(ctx);
+}
+
+gm_status gm_set_owned_range(gm_ctx* ctx, int32_t axis, float lo, float hi) {
+  if (!ctx || axis > 2 || (axis >= 0 && !(hi >= lo))) return GM_ERR_INVALID_ARG;
+  ctx->own.axis = axis < 0 ? -1 : axis;
+  ctx->own.lo = lo; ctx->own.hi = hi;
+  return GM_OK;
+}
+
+gm_status gm_set_voxel_bbox(gm_ctx* ctx, const float* min3, const float* max3) {
+  if (!ctx || ((min3 == nullptr) != (max3 == nullptr))) return GM_ERR_INVALID_ARG;
+  ctx->have_vox_bbox = min3 != nullptr;
+  if (min3) for (int a = 0; a < 3; ++a) { ctx->vox_bbox[a] = min3[a]; ctx->vox_bbox[3 + a] = max3[a]; }
+  return GM_OK;
+}
+
+gm_status gm_get_voxel_bbox(gm_ctx* ctx, float* min3, float* max3) {
+  if (!ctx || !min3 || !max3) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  auto dec = [](int i) { int b = (i >= 0) ? i : (i ^ 0x7FFFFFFF); float f; std::memcpy(&f, &b, 4); return f; };
+  for (int a = 0; a < 3; ++a) { min3[a] = dec(h.vox.bbox_min[a]); max3[a] = dec(h.vox.bbox_max[a]); }
   return GM_OK;
 }
 
@@ -570,11 +637,11 @@ gm_status gm_normals(gm_ctx* ctx) {
     float r2 = rf * rf;
     { SegTimer seg_(ctx, SEG_NORMALS);
       GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
-                ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds); }
+                ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own); }
     if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_COMPACT);
       GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
-                ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, epoch, ctx->d_st); }
+                ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, epoch, ctx->d_st, ctx->own); }
     GM_CHECK_LAUNCHES(ctx);
   }
   ctx->have_normals = true;
@@ -630,7 +697,17 @@ gm_status gm_voxel(gm_ctx* ctx) {
   if (n) {
     VoxBuffers o{ctx->d_vkey_pt, ctx->d_assign, ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_centroid};
     int buf = 0;
-    gm_status s = voxel_downsample(ctx, ctx->d_cloud_c, &ctx->d_st->vox, n, voxel_key_bits(ctx, n), o, &buf);
+    int key_bits = voxel_key_bits(ctx, n);
+    if (ctx->have_vox_bbox) {
+      const float* b = ctx->vox_bbox;
+      GM_LAUNCH(ctx, k_set_bbox, 1, 32, &ctx->d_st->vox, b[0], b[1], b[2], b[3], b[4], b[5]);
+      // exact key range of the given lattice (same float expressions as k_voxel_keys)
+      const float inv = 1.0f / (float)ctx->prm.voxelGridLeafSize;
+      double total = 1.0;
+      for (int a = 0; a < 3; ++a) total *= (double)((long long)std::floor(b[3 + a] * inv) - (long long)std::floor(b[a] * inv) + 1);
+      if (total < 2147483647.0) key_bits = std::min(key_bits, bits_for((unsigned long long)total));
+    }
+    gm_status s = voxel_downsample(ctx, ctx->d_cloud_c, &ctx->d_st->vox, n, key_bits, o, &buf);
     if (s != GM_OK) return s;
     if (ctx->have_normals) {
       SegTimer seg_(ctx, SEG_VOX_NN);

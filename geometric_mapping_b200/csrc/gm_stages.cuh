@@ -33,16 +33,20 @@ struct DevState {
 };
 
 struct GridSpec {
-  float origin;      // same for x,y,z: -bound
+  float origin[3];   // lower corner of the grid box (default: -bound on every axis)
   float inv_cell;    // 1/cell
   float cell;
-  int dim;           // cells per axis
-  int key_bits;      // bits of a cell key (3 * block bits + 6); the block table has 1 << (key_bits - 6) entries
+  int dim[3];        // cells per axis (points outside the box are clamped into the border cells)
+  int bits[3];       // bits of the BLOCK coordinate per axis (blocks are 4x4x4 cells)
+  int bmin;          // min(bits): the low bmin bits of the three block coordinates are Morton-interleaved
+  int key_bits;      // bits of a cell key (bits[0]+bits[1]+bits[2] + 6); the block table has 1 << (key_bits - 6) entries
   unsigned sentinel; // key of non-finite points: all ones in key_bits, never a real cell
 };
 
-// Cell key = Morton code of the 4x4x4-cell BLOCK the cell lies in, then the cell's row-major
-// position inside the block (x fastest).  Sorting by it keeps two properties at once:
+// Cell key = code of the 4x4x4-cell BLOCK the cell lies in, then the cell's row-major position inside
+// the block (x fastest).  Block code = Morton interleave of the low bmin bits of the block coordinates
+// with the remaining high bits of the longer axes stacked on top (a plain Morton code when the grid is
+// a cube).  Sorting by it keeps two properties at once:
 //   * cells adjacent in x inside a block are adjacent keys, so the 3-cell x-neighbourhood of a cell
 //     is one contiguous run of the sorted cloud, or two when it crosses a block face;
 //   * consecutive points are spatially compact in all three axes (a 512-point tile of the C1 scan is
@@ -50,11 +54,12 @@ struct GridSpec {
 //     (gm_ransac.cuh) effective.
 constexpr int GRID_RUNS = 18;  // per occupied cell: 9 (dy,dz) rows x up to 2 x-segments
 
-// Dense table over the blocks (index = Morton block code): which of the 64 cells of the block are
+// Dense table over the blocks (index = block code): which of the 64 cells of the block are
 // occupied and the rank of its first occupied cell in the sorted cell list.  The rank of any cell is
 // then first + popc(mask below its local code): neighbour lookups need no search at all.  Only the
 // entries of occupied blocks are ever written, and the next build clears exactly those (O(cells)).
 struct __align__(16) BlockEntry { unsigned long long mask; int first; int pad_; };
+
 __host__ __device__ __forceinline__ unsigned gm_spread3(unsigned x) {  // 10 bits -> every third bit
   x &= 0x3FFu;
   x = (x | (x << 16)) & 0x030000FFu;
@@ -71,15 +76,39 @@ __host__ __device__ __forceinline__ unsigned gm_compact3(unsigned x) {
   x = (x | (x >> 16)) & 0x3FFu;
   return x;
 }
-__host__ __device__ __forceinline__ unsigned gm_cell_key(int cx, int cy, int cz) {
-  const unsigned m = gm_spread3((unsigned)cx >> 2) | (gm_spread3((unsigned)cy >> 2) << 1) | (gm_spread3((unsigned)cz >> 2) << 2);
-  return (m << 6) | (((unsigned)cz & 3u) << 4) | (((unsigned)cy & 3u) << 2) | ((unsigned)cx & 3u);
+__host__ __device__ __forceinline__ unsigned gm_cell_key(const GridSpec& g, int cx, int cy, int cz) {
+  const unsigned bx = (unsigned)cx >> 2, by = (unsigned)cy >> 2, bz = (unsigned)cz >> 2;
+  const unsigned lowmask = (1u << g.bmin) - 1u;
+  const unsigned m = gm_spread3(bx & lowmask) | (gm_spread3(by & lowmask) << 1) | (gm_spread3(bz & lowmask) << 2);
+  const int hx = g.bits[0] - g.bmin, hy = g.bits[1] - g.bmin;
+  const unsigned hi = ((bz >> g.bmin) << (hx + hy)) | ((by >> g.bmin) << hx) | (bx >> g.bmin);
+  const unsigned code = (hi << (3 * g.bmin)) | m;
+  return (code << 6) | (((unsigned)cz & 3u) << 4) | (((unsigned)cy & 3u) << 2) | ((unsigned)cx & 3u);
 }
-__host__ __device__ __forceinline__ void gm_cell_coords(unsigned key, int& cx, int& cy, int& cz) {
-  const unsigned m = key >> 6;
-  cx = (int)((gm_compact3(m) << 2) | (key & 3u));
-  cy = (int)((gm_compact3(m >> 1) << 2) | ((key >> 2) & 3u));
-  cz = (int)((gm_compact3(m >> 2) << 2) | ((key >> 4) & 3u));
+__host__ __device__ __forceinline__ void gm_cell_coords(const GridSpec& g, unsigned key, int& cx, int& cy, int& cz) {
+  const unsigned code = key >> 6;
+  const unsigned m = code & ((1u << (3 * g.bmin)) - 1u), hi = code >> (3 * g.bmin);
+  const int hx = g.bits[0] - g.bmin, hy = g.bits[1] - g.bmin;
+  const unsigned bx = gm_compact3(m) | ((hi & ((1u << hx) - 1u)) << g.bmin);
+  const unsigned by = gm_compact3(m >> 1) | (((hi >> hx) & ((1u << hy) - 1u)) << g.bmin);
+  const unsigned bz = gm_compact3(m >> 2) | ((hi >> (hx + hy)) << g.bmin);
+  cx = (int)((bx << 2) | (key & 3u));
+  cy = (int)((by << 2) | ((key >> 2) & 3u));
+  cz = (int)((bz << 2) | ((key >> 4) & 3u));
+}
+__device__ __forceinline__ void gm_cell_of(const GridSpec& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+  cx = min(max((int)floorf((x - g.origin[0]) * g.inv_cell), 0), g.dim[0] - 1);
+  cy = min(max((int)floorf((y - g.origin[1]) * g.inv_cell), 0), g.dim[1] - 1);
+  cz = min(max((int)floorf((z - g.origin[2]) * g.inv_cell), 0), g.dim[2] - 1);
+}
+
+// Points of a map slab that this context does not own (halo points given to it for the neighbour
+// search only): dropped together with the NaN normals.  axis < 0: everything is owned.
+struct OwnedRange { int axis; float lo, hi; };
+__device__ __forceinline__ bool d_owned(const OwnedRange& o, const float4 p) {
+  if (o.axis < 0) return true;
+  const float v = (o.axis == 0) ? p.x : ((o.axis == 1) ? p.y : p.z);
+  return v >= o.lo && v < o.hi;
 }
 
 constexpr int CP_BLOCK = 256;
@@ -158,10 +187,9 @@ __global__ void k_cell_keys(const float4* __restrict__ pts, const int* __restric
     float4 p = pts[i];
     unsigned key = g.sentinel;
     if (finite3(p.x, p.y, p.z)) {
-      int cx = min(max((int)floorf((p.x - g.origin) * g.inv_cell), 0), g.dim - 1);
-      int cy = min(max((int)floorf((p.y - g.origin) * g.inv_cell), 0), g.dim - 1);
-      int cz = min(max((int)floorf((p.z - g.origin) * g.inv_cell), 0), g.dim - 1);
-      key = gm_cell_key(cx, cy, cz);
+      int cx, cy, cz;
+      gm_cell_of(g, p.x, p.y, p.z, cx, cy, cz);
+      key = gm_cell_key(g, cx, cy, cz);
     }
     keys[i] = key;
     idx[i] = (unsigned)i;
@@ -244,9 +272,9 @@ __device__ __forceinline__ int lower_bound_u32(const unsigned* __restrict__ a, i
 
 // Sorted-position range [start,end) of the cells x0..x1 of row (cy,cz), all inside ONE 4-cell x-block
 // (consecutive local codes): two popcounts on the block's occupancy mask, no search.
-__device__ __forceinline__ int2 cell_segment(const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start,
+__device__ __forceinline__ int2 cell_segment(const GridSpec& g, const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start,
                                              int U, int n_finite, int x0, int x1, int cy, int cz) {
-  const unsigned key = gm_cell_key(x0, cy, cz);
+  const unsigned key = gm_cell_key(g, x0, cy, cz);
   const BlockEntry e = tab[key >> 6];
   const unsigned c0 = key & 63u, c1 = c0 + (unsigned)(x1 - x0);
   const int a = e.first + __popcll(e.mask & ((1ull << c0) - 1ull));
@@ -270,18 +298,18 @@ __global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* _
     int2 cur = make_int2(0, 0);
     if (key != g.sentinel) {
       int cx, cy0, cz0;
-      gm_cell_coords(key, cx, cy0, cz0);
-      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim - 1);
+      gm_cell_coords(g, key, cx, cy0, cz0);
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
       const int split = x0 | 3;  // last cell of x0's block
 #pragma unroll 1
       for (int k = 0; k < 9; ++k) {
         const int cy = cy0 + (k % 3) - 1, cz = cz0 + (k / 3) - 1;
-        if (cy < 0 || cz < 0 || cy >= g.dim || cz >= g.dim) continue;
+        if (cy < 0 || cz < 0 || cy >= g.dim[1] || cz >= g.dim[2]) continue;
 #pragma unroll
         for (int seg = 0; seg < 2; ++seg) {
           if (seg == 1 && x1 <= split) break;
-          const int2 r = (seg == 0) ? cell_segment(tab, ucell_start, U, nf, x0, min(x1, split), cy, cz)
-                                    : cell_segment(tab, ucell_start, U, nf, split + 1, x1, cy, cz);
+          const int2 r = (seg == 0) ? cell_segment(g, tab, ucell_start, U, nf, x0, min(x1, split), cy, cz)
+                                    : cell_segment(g, tab, ucell_start, U, nf, split + 1, x1, cy, cz);
           if (r.y <= r.x) continue;
           if (cur.y == r.x && cur.y > cur.x) { cur.y = r.y; continue; }  // contiguous with the pending run
           if (cur.y > cur.x) out[m++] = cur;
@@ -378,7 +406,7 @@ constexpr int NRM_BLOCK = 128;
 __global__ void __launch_bounds__(NRM_BLOCK)
 k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs, const int2* __restrict__ cell_info,
           const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count,
-          float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds) {
+          float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds, OwnedRange own) {
   const int n = *n_ptr;
   const int i = blockIdx.x * NRM_BLOCK + threadIdx.x;
   if ((i & ~31) >= n) return;  // warp-uniform: the whole leaf is past the end
@@ -443,7 +471,7 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
       o1 = make_float4(curv, 0.f, 0.f, 0.f);
     }
   }
-  const bool keep = active && finite3(o0.x, o0.y, o0.z);  // the predicate of k_compact_valid
+  const bool keep = active && finite3(o0.x, o0.y, o0.z) && d_owned(own, p);  // the predicate of k_compact_valid
   if (active) {
     normals[2 * (size_t)orig] = o0;
     normals[2 * (size_t)orig + 1] = o1;
@@ -464,7 +492,7 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 __global__ void __launch_bounds__(CP_BLOCK)
 k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ normals, const int* __restrict__ n_ptr,
                 float4* __restrict__ pts_c, float4* __restrict__ normals_c, int* __restrict__ valid_map,
-                unsigned long long* state, unsigned epoch, DevState* st) {
+                unsigned long long* state, unsigned epoch, DevState* st, OwnedRange own) {
   __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
   __shared__ float s_red[6][CP_BLOCK / 32];
   const int n = *n_ptr;
@@ -481,7 +509,7 @@ k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ norma
       p[j] = pts[i];
       n0[j] = normals[2 * (size_t)i];
       n1[j] = normals[2 * (size_t)i + 1];
-      f[j] = finite3(n0[j].x, n0[j].y, n0[j].z);
+      f[j] = finite3(n0[j].x, n0[j].y, n0[j].z) && d_owned(own, p[j]);
       if (f[j]) {
         mn[0] = fminf(mn[0], p[j].x); mn[1] = fminf(mn[1], p[j].y); mn[2] = fminf(mn[2], p[j].z);
         mx[0] = fmaxf(mx[0], p[j].x); mx[1] = fmaxf(mx[1], p[j].y); mx[2] = fmaxf(mx[2], p[j].z);
@@ -518,6 +546,14 @@ k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ norma
       atomicMin(&st->vox.bbox_min[threadIdx.x], float_to_ordered(lo));
       atomicMax(&st->vox.bbox_max[threadIdx.x], float_to_ordered(hi));
     }
+  }
+}
+
+// Replace the bounding box of the compacted cloud (all-reduced box of all map slabs -> one global lattice).
+__global__ void k_set_bbox(VoxState* vs, float x0, float y0, float z0, float x1, float y1, float z1) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    vs->bbox_min[0] = float_to_ordered(x0); vs->bbox_min[1] = float_to_ordered(y0); vs->bbox_min[2] = float_to_ordered(z0);
+    vs->bbox_max[0] = float_to_ordered(x1); vs->bbox_max[1] = float_to_ordered(y1); vs->bbox_max[2] = float_to_ordered(z1);
   }
 }
 
@@ -680,13 +716,13 @@ __device__ __forceinline__ void d_nn_scan(const float4* __restrict__ sp, const i
 
 // scan the cells x0..x1 of row (cy,cz): one segment per 4-cell x-block the span touches
 __device__ __forceinline__ void d_nn_scan_row(const float4* __restrict__ sp, const int* __restrict__ valid_map, int mode,
-                                              const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start,
-                                              int U, int nf, int dim, int x0, int x1, int cy, int cz, const float4 c, float& best, int& bi) {
-  if (cy < 0 || cz < 0 || cy >= dim || cz >= dim) return;
-  x0 = max(x0, 0); x1 = min(x1, dim - 1);
+                                              const GridSpec& g, const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start,
+                                              int U, int nf, int x0, int x1, int cy, int cz, const float4 c, float& best, int& bi) {
+  if (cy < 0 || cz < 0 || cy >= g.dim[1] || cz >= g.dim[2]) return;
+  x0 = max(x0, 0); x1 = min(x1, g.dim[0] - 1);
   for (int xs = x0; xs <= x1;) {
     const int xe = min(x1, xs | 3);
-    d_nn_scan(sp, valid_map, mode, cell_segment(tab, ucell_start, U, nf, xs, xe, cy, cz), c, best, bi);
+    d_nn_scan(sp, valid_map, mode, cell_segment(g, tab, ucell_start, U, nf, xs, xe, cy, cz), c, best, bi);
     xs = xe + 1;
   }
 }
@@ -701,22 +737,22 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
   const int warps_total = (gridDim.x * NN_BLOCK) >> 5;
   for (int j = (blockIdx.x * NN_BLOCK + threadIdx.x) >> 5; j < V; j += warps_total) {
     const float4 c = centroids[j];
-    const int cx = min(max((int)floorf((c.x - g.origin) * g.inv_cell), 0), g.dim - 1);
-    const int cy = min(max((int)floorf((c.y - g.origin) * g.inv_cell), 0), g.dim - 1);
-    const int cz = min(max((int)floorf((c.z - g.origin) * g.inv_cell), 0), g.dim - 1);
+    int cx, cy, cz;
+    gm_cell_of(g, c.x, c.y, c.z, cx, cy, cz);
     float best = CUDART_INF_F;
     int bi = 0x7FFFFFFF;
-    for (int k = 1; k <= g.dim; ++k) {
+    const int kmax = max(g.dim[0], max(g.dim[1], g.dim[2]));
+    for (int k = 1; k <= kmax; ++k) {
       if (k == 1) {
         // the 27-cell cube as 9 rows of 3 cells; if the centroid's own cell is occupied (the usual
         // case) its runs were already computed for the normals stage: one search instead of 18
-        const unsigned ckey = gm_cell_key(cx, cy, cz);
+        const unsigned ckey = gm_cell_key(g, cx, cy, cz);
         const BlockEntry e = tab[ckey >> 6];
         if ((e.mask >> (ckey & 63u)) & 1ull) {
           const int jc = e.first + __popcll(e.mask & ((1ull << (ckey & 63u)) - 1ull));
           if (lane < cell_info[jc].x) d_nn_scan(sp, valid_map, mode, runs[(size_t)jc * GRID_RUNS + lane], c, best, bi);
         } else if (lane < 9) {
-          d_nn_scan_row(sp, valid_map, mode, tab, ucell_start, U, nf, g.dim, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1, c, best, bi);
+          d_nn_scan_row(sp, valid_map, mode, g, tab, ucell_start, U, nf, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1, c, best, bi);
         }
       } else {
         // shell k: 8k perimeter rows with the full x span + (2k-1)^2 inner rows with two end cells
@@ -734,7 +770,7 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
             dy = cell % inner - (k - 1); dz = cell / inner - (k - 1);
             x0 = x1 = (u2 & 1) ? cx + k : cx - k;
           }
-          d_nn_scan_row(sp, valid_map, mode, tab, ucell_start, U, nf, g.dim, x0, x1, cy + dy, cz + dz, c, best, bi);
+          d_nn_scan_row(sp, valid_map, mode, g, tab, ucell_start, U, nf, x0, x1, cy + dy, cz + dz, c, best, bi);
         }
       }
       // lexicographic (d2, index) minimum over the warp

@@ -74,3 +74,113 @@ def sharded_ransac(ctx, kind: int, samples, rank: int, world: int, key_tensor, g
         allreduce_best_key(key_tensor, group)
         ctx.ransac_import_key(kind, key_tensor.data_ptr())
     ctx.ransac_select(kind)
+
+
+# ---------------------------------------------------------------------------------------------
+# Map slabs: one large map cut along an axis, one slab per rank.
+#
+# A slab owns the points whose VOXEL index along the axis lies in [K_lo, K_hi): cuts sit on voxel faces
+# of the pcl::VoxelGrid lattice (floor(p * inv_leaf) is independent of the lattice origin), so no
+# voxel is shared by two ranks and, with one global bounding box (all-reduce MIN/MAX of 6 floats, the
+# only collective on this path), the per-slab voxel keys and centroids are exactly those of the
+# whole map.  Each rank is also handed a halo of >= neighborRadius on both sides: halo points take part
+# in the radius search and are then dropped (gm_set_owned_range), so an owned point sees its complete
+# neighbourhood and gets the normal a single context would compute.
+def voxel_cut(K: int, leaf: float):
+    """Smallest float32 c with floor(fl32(c * inv_leaf)) >= K, inv_leaf = fl32(1 / fl32(leaf)): the
+    coordinate test `x >= c` is then exactly the voxel-index test `floor(x * inv_leaf) >= K`."""
+    import numpy as np
+
+    f = np.float32
+    inv = f(1.0) / f(leaf)
+
+    def idx(c):
+        return int(np.floor(f(c) * inv))
+
+    c = f(K) / inv
+    for _ in range(64):
+        if idx(c) < K:
+            break
+        c = np.nextafter(c, f(-np.inf))
+    for _ in range(128):
+        if idx(c) >= K:
+            return float(c)
+        c = np.nextafter(c, f(np.inf))
+    raise ValueError("voxel_cut did not converge")
+
+
+def slab_cuts(coord, world: int, leaf: float):
+    """Balanced cuts of the finite values of `coord` (the points' coordinate along the split axis) into
+    `world` slabs, snapped to voxel faces.  -> list of (lo, hi) float pairs, lo/hi = -/+3e38 at the ends;
+    slab g owns lo <= x < hi.  Slabs tile the axis; a slab may be empty when the data are narrow."""
+    import numpy as np
+
+    if world < 1:
+        raise ValueError("world < 1")
+    x = np.asarray(coord, np.float32)
+    x = x[np.isfinite(x)]
+    big = 3.0e38
+    if world == 1 or x.size == 0:
+        return [(-big, big)] + [(big, big)] * (world - 1)
+    inv = np.float32(1.0) / np.float32(leaf)
+    qs = np.quantile(x.astype(np.float64), np.linspace(0.0, 1.0, world + 1)[1:-1])
+    ks = [int(np.floor(np.float32(q) * inv)) for q in qs]
+    for i in range(1, len(ks)):
+        ks[i] = max(ks[i], ks[i - 1])
+    edges = [-big] + [voxel_cut(k, leaf) for k in ks] + [big]
+    return [(edges[g], edges[g + 1]) for g in range(world)]
+
+
+def slab_select(points, axis: int, lo: float, hi: float, halo: float):
+    """Rows of `points` (n x 4 float32) a rank is handed: its slab plus the halo (order preserved)."""
+    import numpy as np
+
+    v = points[:, axis]
+    keep = (v >= np.float32(lo) - np.float32(halo)) & (v < np.float32(hi) + np.float32(halo))
+    return np.ascontiguousarray(points[keep])
+
+
+def allreduce_bbox(mn, mx, group=None):
+    """Global bounding box over ranks (MIN / MAX all-reduce of 3 + 3 floats; identity when not distributed)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return mn, mx
+    import numpy as np
+
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    a = torch.tensor(np.asarray(mn, np.float32), device=dev)
+    b = torch.tensor(np.asarray(mx, np.float32), device=dev)
+    dist.all_reduce(a, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(b, op=dist.ReduceOp.MAX, group=group)
+    return a.cpu().numpy(), b.cpu().numpy()
+
+
+def process_map_slab(ctx, slab_points, axis: int, lo: float, hi: float, plane_samples=None, cyl_samples=None, group=None,
+                     grid_box=None, compress: bool = True):
+    """One rank's share of a large map: normals with halo, owned-point compaction, VoxelGrid on the global
+    lattice, local frame, RANSAC primitives of THIS slab (multi-primitive approximation: one plane + one
+    cylinder per slab), labels, polyline, compression.  `slab_points` = slab_select(...) of the map."""
+    ctx.set_owned_range(axis, lo, hi)
+    if grid_box is not None:
+        ctx.set_grid_box(grid_box[0], grid_box[1])
+    ctx.upload_scan(slab_points)
+    ctx.crop()
+    ctx.normals()
+    mn, mx = ctx.voxel_bbox()
+    gmn, gmx = allreduce_bbox(mn, mx, group)
+    ctx.set_voxel_bbox(gmn, gmx)
+    ctx.voxel()
+    ctx.local_frame()
+    if plane_samples is not None and len(plane_samples):
+        ctx.ransac(0, plane_samples)
+        ctx.ransac_select(0)
+    if cyl_samples is not None and len(cyl_samples):
+        ctx.ransac(1, cyl_samples)
+        ctx.ransac_select(1)
+    ctx.label()
+    ctx.axis_polyline()
+    if compress:
+        ctx.compress()
+    return gmn, gmx

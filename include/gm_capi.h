@@ -156,6 +156,20 @@ GM_API gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream);
  * scan whenever gm_normals produced one (identical counts, hypotheses whose inlier band provably
  * misses a 32-point tile are skipped for it); 1 = always the brute-force FP32 kernels. */
 GM_API gm_status gm_set_count_mode(gm_ctx* ctx, int32_t mode);
+/* ---- map slabs (one large map split along an axis over several contexts / GPUs) ----
+ * gm_set_grid_box: build the neighbour grid over this box instead of the whole crop cube (the region
+ *   the slab occupies, halo included; points outside it stay correct, only slower).  NULL,NULL = cube.
+ * gm_set_owned_range: the context was given the slab lo <= coord[axis] < hi PLUS a halo (>= neighborRadius)
+ *   of its neighbours.  Halo points take part in the neighbour search, then leave with the NaN normals:
+ *   every later stage (voxels, frame, RANSAC, labels, compression) sees owned points only, with the same
+ *   normals a single context would compute for them.  axis = -1: everything is owned.
+ * gm_get_voxel_bbox / gm_set_voxel_bbox: pcl::getMinMax3D of the compacted cloud, and its override before
+ *   gm_voxel: with the all-reduced (min/max) box of all slabs every slab uses ONE VoxelGrid lattice, so voxel
+ *   keys are those of the whole map; slabs cut at multiples of the leaf own disjoint voxels.  NULL,NULL = own box. */
+GM_API gm_status gm_set_grid_box(gm_ctx* ctx, const float* min3, const float* max3);
+GM_API gm_status gm_set_owned_range(gm_ctx* ctx, int32_t axis, float lo, float hi);
+GM_API gm_status gm_get_voxel_bbox(gm_ctx* ctx, float* min3, float* max3);
+GM_API gm_status gm_set_voxel_bbox(gm_ctx* ctx, const float* min3, const float* max3);
 GM_API const char* gm_last_error(const gm_ctx* ctx);
 GM_API const char* gm_status_string(gm_status s);
 GM_API int32_t gm_version(void);

@@ -70,3 +70,66 @@ def test_sharded_ransac_allreduce_matches_single_rank(world):
         keys = [out[r] for r in range(world)]
         assert len(set(keys)) == 1                        # every rank ends with the same winner
         assert D.unpack_key(keys[0]) == tuple(out["ref"])
+
+
+# ---- map slabs (config C4): cuts on voxel faces, halo selection, bbox all-reduce -------------------
+@pytest.mark.parametrize("leaf", [0.1, 0.25, 0.07])
+def test_voxel_cut_is_the_exact_voxel_face(leaf):
+    f = np.float32
+    inv = f(1.0) / f(leaf)
+    for K in (-700, -37, -1, 0, 1, 3, 251, 4999):
+        c = f(D.voxel_cut(K, leaf))
+        below = np.nextafter(c, f(-np.inf))
+        assert int(np.floor(c * inv)) >= K > int(np.floor(below * inv))
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_slab_cuts_tile_the_axis_on_voxel_faces_and_own_every_point_once(world):
+    leaf, radius = 0.1, 0.05
+    pts = synth.curved_tunnel(50_000, seed=9, arc_length=60.0, arc_radius=200.0, bound=40.0)
+    pts[5, 0] = np.nan
+    cuts = D.slab_cuts(pts[:, 0], world, leaf)
+    assert len(cuts) == world and cuts[0][0] < -1e38 and cuts[-1][1] > 1e38
+    assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    x = pts[:, 0]
+    owned = np.zeros(len(pts), np.int32)
+    inv = np.float32(1.0) / np.float32(leaf)
+    vox = np.floor(x * inv)
+    for lo, hi in cuts:
+        m = (x >= np.float32(lo)) & (x < np.float32(hi))
+        owned += m
+        if m.any() and hi < 1e38:
+            # a voxel never straddles a cut: every owned point's voxel index is below every index right of the cut
+            assert vox[m].max() < vox[np.isfinite(x) & (x >= np.float32(hi))].min()
+        sel = D.slab_select(pts, 0, lo, hi, halo=1.01 * radius)
+        assert m.sum() <= len(sel) <= len(pts)
+        # the halo holds every point within `radius` (along x) of an owned point
+        if m.any():
+            near = np.isfinite(x) & (x >= x[m].min() - np.float32(radius)) & (x <= x[m].max() + np.float32(radius))
+            assert near.sum() <= len(sel)
+    assert np.array_equal(owned[np.isfinite(x)], np.ones(np.isfinite(x).sum(), np.int32)) and owned[5] == 0
+    if world > 1:
+        sizes = [int(((x >= np.float32(a)) & (x < np.float32(b))).sum()) for a, b in cuts]
+        assert max(sizes) < 1.2 * len(pts) / world        # balanced
+
+
+def _bbox_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pts = synth.curved_tunnel(30_000, seed=9, arc_length=40.0, arc_radius=200.0, bound=30.0)
+    lo, hi = D.slab_cuts(pts[:, 0], world, 0.1)[rank]
+    mine = pts[(pts[:, 0] >= np.float32(lo)) & (pts[:, 0] < np.float32(hi)), :3]
+    mn, mx = D.allreduce_bbox(mine.min(0), mine.max(0))
+    out[rank] = (mn.tolist(), mx.tolist())
+    if rank == 0:
+        out["ref"] = (pts[:, :3].min(0).tolist(), pts[:, :3].max(0).tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bbox_allreduce_gives_every_rank_the_whole_map_box():
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_bbox_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert out[0] == out[1] == out["ref"]

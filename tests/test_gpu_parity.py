@@ -735,6 +735,74 @@ def test_frame_sequence_polyline_per_frame():
             assert ctx.counts().device_error == 0
 
 
+# ---- map slabs ---------------------------------------------------------------
+def test_map_slabs_reproduce_the_whole_map():
+    """A map cut into 3 slabs at voxel faces, each processed with a halo on its own context, gives for
+    its owned points exactly the compacted cloud, normals, voxel keys and centroids of the whole map."""
+    from geometric_mapping_b200 import distributed as D
+
+    n, bound, radius, leaf = 150_000, 20.0, 0.2, 0.25
+    pts = synth.curved_tunnel(n, seed=5, arc_length=30.0, arc_radius=100.0, bound=bound, outlier_frac=0.02)
+    pts[11] = [np.nan, 0.0, 0.0, 1.0]
+    kw = dict(boxFilterBound=bound, neighborRadius=radius, voxelGridLeafSize=leaf)
+    with _ctx(n, **kw) as ctx:
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        ctx.voxel()
+        ctx.local_frame()
+        w_cloud, w_nrm = ctx.download_cloud(1), ctx.download_normals(1)
+        w_vox = ctx.download_voxels()
+        w_bbox = ctx.voxel_bbox()
+        w_scatter = ctx.frame()["scatter"].astype(np.float64).reshape(-1)
+    cuts = D.slab_cuts(pts[:, 0], 3, leaf)
+    assert cuts[0][1] < cuts[1][1] < cuts[2][1]
+    got_keys, got_cen, got_cnt, scatter, n_owned = [], [], [], np.zeros((3, 3)), 0
+    boxes = []
+    with _ctx(n, **kw) as ctx:
+        for variant in ("cube", "box"):
+            for lo, hi in cuts:
+                sl = D.slab_select(pts, 0, lo, hi, halo=1.01 * radius)
+                assert len(sl) < 0.5 * n
+                ctx.set_owned_range(0, lo, hi)
+                if variant == "box":   # the grid a production rank would use: its own region only
+                    fin = np.isfinite(sl[:, :3]).all(1)
+                    ctx.set_grid_box(sl[fin, :3].min(0), sl[fin, :3].max(0))
+                ctx.upload_scan(sl)
+                ctx.crop()
+                ctx.normals()
+                cloud, nrm = ctx.download_cloud(1), ctx.download_normals(1)
+                own = (w_cloud[:, 0] >= np.float32(lo)) & (w_cloud[:, 0] < np.float32(hi))
+                assert np.array_equal(cloud.view(np.uint32), w_cloud[own].view(np.uint32))       # same points, same order
+                if variant == "cube":
+                    assert np.array_equal(nrm.view(np.uint32), w_nrm[own].view(np.uint32))       # bit-identical normals
+                    boxes.append(ctx.voxel_bbox())
+                    ctx.set_voxel_bbox(*w_bbox)     # what the MIN/MAX all-reduce delivers (checked below)
+                    ctx.voxel()
+                    ctx.local_frame()
+                    v = ctx.download_voxels()
+                    got_keys.append(v["keys"]); got_cen.append(v["centroids"]); got_cnt.append(v["counts"])
+                    scatter += ctx.frame()["scatter"].astype(np.float64).reshape(3, 3)
+                    n_owned += len(cloud)
+                else:
+                    ang = _angle(nrm[:, :3].astype(np.float64), w_nrm[own][:, :3].astype(np.float64))
+                    assert np.percentile(ang, 99) < 2e-2   # other cell boundaries -> other summation order only
+                assert ctx.counts().device_error == 0
+            ctx.set_voxel_bbox(None)
+        ctx.set_owned_range(-1)
+        ctx.set_grid_box(None)
+    assert n_owned == len(w_cloud)
+    mn = np.min([b[0] for b in boxes if np.isfinite(b[0]).all()], axis=0)
+    mx = np.max([b[1] for b in boxes if np.isfinite(b[1]).all()], axis=0)
+    assert np.array_equal(mn, w_bbox[0]) and np.array_equal(mx, w_bbox[1])                       # the all-reduced box
+    keys, cen, cnt = np.concatenate(got_keys), np.concatenate(got_cen), np.concatenate(got_cnt)
+    o = np.argsort(keys, kind="stable")
+    assert np.array_equal(keys[o], w_vox["keys"]) and len(np.unique(keys)) == len(keys)           # disjoint, complete
+    assert np.array_equal(cnt[o], w_vox["counts"])
+    assert np.array_equal(cen[o].view(np.uint32), w_vox["centroids"].view(np.uint32))             # bit-identical centroids
+    assert np.abs(scatter.reshape(-1) - w_scatter).max() <= 1e-5 * np.abs(w_scatter).max()        # sum of the partial scatters
+
+
 # ---- I/O seams ---------------------------------------------------------------------------------------
 def test_pointcloud2_decode_velodyne_layout():
     """sensor_msgs/PointCloud2 as the Velodyne driver publishes it: point_step 22 (x,y,z,intensity f32 +

@@ -286,7 +286,7 @@ def main():
     # (b) throughput: NFLIGHT scans in flight, one context (and CUDA stream) each, round robin, the way
     # a stream of scans is processed.  Timed with CUDA events: e0 on the first context's stream before
     # the first step, e1 on a stream that has waited for every context's last step.
-    NFLIGHT = 3
+    NFLIGHT = max(1, int(os.environ.get("GM_BENCH_NFLIGHT", "3")))
     tctx = [ctx] + [capi.Context(params, max_points=n, max_hypotheses=max(4096, a.shard_hyp)) for _ in range(NFLIGHT - 1)]
     tstreams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NFLIGHT - 1)]
     for cx, st_ in zip(tctx[1:], tstreams[1:]):
@@ -505,7 +505,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "parallelism": f"frame-parallel x{world}" if world > 1 else "1 GPU",
                        "l2": f"inputs larger than L2: ring of {RING} distinct resident scans ({RING * n * 16 / 1e6:.0f} MB) cycled",
-                       "in_flight": "3 scans in flight (one context + CUDA stream each); single-scan latency in latency_ms_per_scan",
+                       "in_flight": f"{NFLIGHT} scans in flight (one context + CUDA stream each); single-scan latency in latency_ms_per_scan",
                        "mean_valid_points": M, "voxels": int(V)},
             "latency_ms_per_scan": latency_ms,
             "clocks": clocks,

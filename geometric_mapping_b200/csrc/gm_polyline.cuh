@@ -186,9 +186,14 @@ k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, 
   const int n = *n_ptr;
   const int S = ps->S;
   const bool use_smem = S <= POLY_SMEM_SLICES;
+  // a tunnel scan has few slices (10 at 1 m over a 10 m scan) and every thread adds to one of them: keep
+  // up to 16 interleaved copies of the accumulators so that same-address shared-memory atomics are rare
+  int copies = 1;
+  while (copies < 16 && 2 * copies * S <= POLY_SMEM_SLICES) copies *= 2;
+  const int my_copy = threadIdx.x & (copies - 1);
   if (S > 0) {
     if (use_smem) {
-      for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) s_acc[i] = 0ull;
+      for (int i = threadIdx.x; i < copies * S * NS; i += POLY_BLOCK) s_acc[i] = 0ull;
       __syncthreads();
     }
     const double a0 = ps->axis[0], a1 = ps->axis[1], a2 = ps->axis[2];
@@ -229,14 +234,15 @@ k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, 
       }
 #pragma unroll
       for (int k = 0; k < NS; ++k) {
-        if (use_smem) atomicAdd(&s_acc[s * NS + k], (unsigned long long)v[k]);
+        if (use_smem) atomicAdd(&s_acc[(my_copy * S + s) * NS + k], (unsigned long long)v[k]);
         else atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)s * POLY_NACC + SLOT0 + k, (unsigned long long)v[k]);
       }
     }
     if (use_smem) {
       __syncthreads();
       for (int i = threadIdx.x; i < S * NS; i += POLY_BLOCK) {
-        unsigned long long v = s_acc[i];
+        unsigned long long v = 0ull;
+        for (int c = 0; c < copies; ++c) v += s_acc[c * S * NS + i];  // integer sums: any order, same result
         if (v) atomicAdd(reinterpret_cast<unsigned long long*>(acc) + (size_t)(i / NS) * POLY_NACC + SLOT0 + (i % NS), v);
       }
     }

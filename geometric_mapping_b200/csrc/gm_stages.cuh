@@ -421,9 +421,10 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
     const int2* rr = runs + (size_t)cid * GRID_RUNS;
     const int2 info = cell_info[cid];
     const int nr = info.x, total = info.y;
-    // accumulators as f32x2 pairs: (xx,xy) (xz,yz) (zz,-) (x,y); yy and z stay scalar
-    u64 a01 = 0ull, a24 = 0ull, a5w = 0ull, a67 = 0ull;
-    float a3 = 0.f, a8 = 0.f;
+    // accumulators as f32x2 pairs: (xx,xy) (xz,yz) (x,y) (z,count); yy and zz stay scalar.  The count is
+    // carried as a float (exact below 2^24 neighbours) so that it shares an instruction with the z sum.
+    u64 a01 = 0ull, a24 = 0ull, a67 = 0ull, a8c = 0ull;
+    float a3 = 0.f, a5 = 0.f;
     // ONE flat loop over the candidates of all runs (not a loop over runs with a loop over candidates
     // inside): lanes of a warp are points of neighbouring cells whose run lists differ, and the warp
     // pays max-over-lanes of the TOTAL candidate count instead of the sum of per-run maxima.
@@ -443,18 +444,18 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
       float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
       float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
       const bool hit = d2 < r2;
-      const float mx = hit ? q.x : 0.f, my = hit ? q.y : 0.f, mz = hit ? q.z : 0.f;
+      const float mx = hit ? q.x : 0.f, my = hit ? q.y : 0.f, mz = hit ? q.z : 0.f, m1 = hit ? 1.0f : 0.f;
       const u64 qxy = d_pack2(q.x, q.y);
-      a01 = d_fma2(d_pack2(mx, mx), qxy, a01);                 // xx, xy
-      a24 = d_fma2(d_pack2(mz, mz), qxy, a24);                 // xz, yz
-      a5w = d_fma2(d_pack2(mz, 0.f), d_pack2(q.z, 0.f), a5w);  // zz
+      a01 = d_fma2(d_pack2(mx, mx), qxy, a01);  // xx, xy
+      a24 = d_fma2(d_pack2(mz, mz), qxy, a24);  // xz, yz
       a3 = fmaf(my, q.y, a3);
+      a5 = fmaf(mz, q.z, a5);
       a67 = d_add2(a67, d_pack2(mx, my));
-      a8 += mz;
-      cnt += hit ? 1 : 0;
+      a8c = d_add2(a8c, d_pack2(mz, m1));
     }
-    float a0, a1, a2, a4, a5, a6, a7, junk;
-    d_unpack2(a01, a0, a1); d_unpack2(a24, a2, a4); d_unpack2(a5w, a5, junk); d_unpack2(a67, a6, a7);
+    float a0, a1, a2, a4, a6, a7, a8, cntf;
+    d_unpack2(a01, a0, a1); d_unpack2(a24, a2, a4); d_unpack2(a67, a6, a7); d_unpack2(a8c, a8, cntf);
+    cnt = (int)cntf;
     if (cnt >= 3) {
       float c = (float)cnt;
       a0 /= c; a1 /= c; a2 /= c; a3 /= c; a4 /= c; a5 /= c; a6 /= c; a7 /= c; a8 /= c;

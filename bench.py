@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--radius", type=float, default=0.05)
     ap.add_argument("--leaf", type=float, default=0.1)
     ap.add_argument("--refit-iters", type=int, default=5)
+    ap.add_argument("--map-points", type=int, default=10_000_000, help="points of the aggregated-map leg (configs[4]); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-points", type=int, default=0, help="points of the CPU baseline sample (0 = full scan)")
     return ap.parse_args()
@@ -323,6 +324,34 @@ def main():
             raise SystemExit("device-side error flag set")
     c = ctx.counts()
     value = world * n * a.steps / (ms * 1e-3)
+    # the same throughput measurement at the north-star's hypothesis count (2048 plane + 2048 cylinder)
+    H4 = 4096
+    samples4 = [(synth.sample_indices(n_valid[s], H4 // 2, 3, seed=30 + s), synth.sample_indices(n_valid[s], H4 // 2, 2, seed=40 + s))
+                for s in range(RING)]
+
+    def tstep4(i):
+        s, cx = i % RING, tctx[i % NFLIGHT]
+        cx.set_scan_device(dev_scans[s].data_ptr(), n)
+        cx.process_scan(samples4[s][0], samples4[s][1])
+
+    steps4 = max(6, a.steps // 4)
+    for i in range(2 * NFLIGHT):
+        tstep4(i)
+    barrier()
+    for st_ in tstreams[1:]:
+        st_.wait_stream(stream)
+    e0.record(stream)
+    for st_ in tstreams[1:]:
+        st_.wait_event(e0)
+    for i in range(steps4):
+        tstep4(i)
+    for st_ in tstreams[1:]:
+        stream.wait_stream(st_)
+    e1.record(stream)
+    barrier()
+    ms4 = max_over_ranks(e0.elapsed_time(e1)) / steps4
+    h4096 = {"hypotheses": H4, "ms_per_step": ms4, "points_per_s": world * n / (ms4 * 1e-3), "steps": steps4,
+             "note": "same workload with 2048 plane + 2048 cylinder hypotheses per scan (north-star target count)"}
     for cx in tctx[1:]:
         cx.close()
 
@@ -484,6 +513,76 @@ def main():
                 "n_plane": cc.n_plane, "n_cylinder": cc.n_cylinder, "n_residual": cc.n_residual,
                 "n_residual_voxels": cc.n_residual_voxels}
 
+    # ---- aggregated map cut into slabs, one per rank (configs[4]; strong scaling of ONE map) -------------
+    map_leg = None
+    if a.map_points > 0:
+        for cx in ectx:
+            cx.close()
+        ctx.close()
+        del dev_scans, d_shared
+        torch.cuda.empty_cache()
+        mbound, mleaf, mrad = 60.0, a.leaf, a.radius
+        mp_all = synth.tunnel_map(a.map_points, seed=4, bound=mbound)
+        lo, hi = gmd.slab_cuts(mp_all[:, 0], world, mleaf)[rank]
+        slab = gmd.slab_select(mp_all, 0, lo, hi, halo=1.01 * mrad)
+        del mp_all
+        ns = len(slab)
+        fin = np.isfinite(slab[:, :3]).all(1)
+        # grid box = where the slab's points actually are (1 % of them are outliers spread over the whole crop
+        # cube: those fall outside the box and are clamped into its border cells, which is correct, only slower)
+        box = gmd.robust_box(slab[fin, :3]) if fin.any() else (np.zeros(3, np.float32), np.ones(3, np.float32))
+        mparams = capi.default_params(boxFilterBound=mbound, neighborRadius=mrad, voxelGridLeafSize=mleaf, ransacThreshold=TAU,
+                                      refitIterations=a.refit_iters)
+        mctx = capi.Context(mparams, max_points=max(ns, 1), max_hypotheses=4096)
+        mctx.set_stream(stream.cuda_stream)
+        mctx.set_grid_box(box[0], box[1])
+        mctx.set_owned_range(0, lo, hi)
+        d_slab = torch.from_numpy(slab).to(dev)
+
+        def map_pass(sp_, sc_):
+            mctx.set_scan_device(d_slab.data_ptr(), ns)
+            mctx.crop()
+            mctx.normals()
+            gmn, gmx = gmd.allreduce_bbox(*mctx.voxel_bbox())   # the one collective of this path (6 floats)
+            mctx.set_voxel_bbox(gmn, gmx)
+            mctx.voxel()
+            mctx.local_frame()
+            for kind, smp in ((0, sp_), (1, sc_)):
+                if smp is not None:
+                    mctx.ransac(kind, smp)
+                    mctx.ransac_select(kind)
+            mctx.label()
+            mctx.axis_polyline()
+            mctx.compress()
+
+        map_pass(None, None)
+        mnv = mctx.counts().n_valid
+        msp = synth.sample_indices(mnv, Hp, 3, seed=3 + rank) if mnv >= 3 else None
+        msc = synth.sample_indices(mnv, Hc, 2, seed=4 + rank) if mnv >= 3 else None
+        map_pass(msp, msc)
+        barrier()
+        reps = 3
+        e0.record(stream)
+        for _ in range(reps):
+            map_pass(msp, msc)
+        e1.record(stream)
+        barrier()
+        mms = max_over_ranks(e0.elapsed_time(e1)) / reps
+        mc, mcc = mctx.counts(), mctx.compression()
+        if mc.device_error:
+            raise SystemExit("device-side error flag set (map leg)")
+        tot_valid = mnv
+        if world > 1:
+            t = torch.tensor([mnv], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            tot_valid = int(t.item())
+        map_leg = {"points": a.map_points, "ms_per_map": mms, "points_per_s": a.map_points / (mms * 1e-3),
+                   "valid_points_all_ranks": tot_valid, "slab_points_rank0": ns, "owned_valid_rank0": mnv, "halo_m": 1.01 * mrad,
+                   "voxels_rank0": mc.n_voxels, "compression_ratio_rank0": float(mcc.ratio), "rms_m_rank0": float(mcc.total_rms),
+                   "mode": f"100 m tunnel map cut into {world} slab(s) at voxel faces, halo = neighbour radius, one plane + one "
+                           f"cylinder per slab ({Hp}+{Hc} hypotheses each), VoxelGrid on the all-reduced global lattice; strong scaling"}
+        mctx.close()
+
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -515,8 +614,10 @@ def main():
             "roofline": roofline,
             "roofline_families": families,
             "segments_ms_per_step": seg_ms,
+            "h4096": h4096,
             "ransac": ransac,
             "compress": compress,
+            "map_slabs": map_leg,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -206,7 +206,7 @@ int bits_for(unsigned long long max_value) {
 // Neighbour grid over a box (default: the crop cube; gm_set_grid_box narrows it to the region a map
 // slab actually occupies): cell slightly larger than the search radius so that, with float rounding of
 // the cell coordinate, every d < r neighbour lies in the 27-cell neighbourhood.  The cell grows when
-// the box would need more than 2^24 blocks (dense block table) or 1020 cells on an axis.
+// the box would need more than 2^24 blocks (dense block table) or 4092 cells on an axis.
 GridSpec make_grid(const gm_params& p, const double* box_min, const double* box_max) {
   GridSpec g{};
   float rf = (float)p.neighborRadius;
@@ -219,7 +219,7 @@ GridSpec make_grid(const gm_params& p, const double* box_min, const double* box_
   }
   double cell = (double)rf * (1.0 + 1.0 / 256.0);
   if (!(cell > 0.0)) cell = 1e-3;
-  const int kMaxDim = 1020;  // 255 blocks of 4 cells per axis: 8 block bits, all-ones block code stays unused
+  const int kMaxDim = 4092;  // 1023 blocks of 4 cells: at most 10 block bits per axis (the sum is capped at 24 below)
   for (;;) {
     int total_bits = 0;
     bool ok = true;

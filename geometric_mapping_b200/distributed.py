@@ -140,6 +140,18 @@ def slab_select(points, axis: int, lo: float, hi: float, halo: float):
     return np.ascontiguousarray(points[keep])
 
 
+def robust_box(xyz, q: float = 0.02, margin: float = 1.0):
+    """Box holding all but a fraction ~2q per axis of the points, grown by `margin` metres: the region to hand to
+    gm_set_grid_box when a few far outliers would otherwise stretch the neighbour grid over the whole crop cube."""
+    import numpy as np
+
+    step = max(1, len(xyz) // 200_000)            # quantiles of a subsample are plenty for a box
+    sub = np.asarray(xyz[::step], np.float64)
+    lo = np.quantile(sub, q, axis=0) - margin
+    hi = np.quantile(sub, 1.0 - q, axis=0) + margin
+    return lo.astype(np.float32), hi.astype(np.float32)
+
+
 def allreduce_bbox(mn, mx, group=None):
     """Global bounding box over ranks (MIN / MAX all-reduce of 3 + 3 floats; identity when not distributed)."""
     import torch

@@ -56,6 +56,13 @@ def curved_tunnel(n: int = 1_000_000, seed: int = 2, radius: float = 2.5, arc_ra
     return _xyzw(x, y, z)
 
 
+def tunnel_map(n: int = 10_000_000, seed: int = 4, length: float = 100.0, arc_radius: float = 200.0, bound: float = 60.0,
+               **kw) -> np.ndarray:
+    """C4: dense aggregated map of `length` metres of gently curved tunnel (same section, floor and noise as
+    curved_tunnel), centred on the origin; needs boxFilterBound >= bound."""
+    return curved_tunnel(n, seed=seed, arc_radius=arc_radius, arc_length=length, bound=bound, **kw)
+
+
 def plane_patch(n: int = 10_000, seed: int = 5, normal=(0.0, 0.0, 1.0), offset: float = -1.5, half: float = 2.0,
                 noise: float = 0.0) -> np.ndarray:
     g = _rng(seed)

@@ -123,6 +123,8 @@ SYMBOLS = [
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
     "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
     "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode", "gm_set_grid_box", "gm_set_owned_range", "gm_get_voxel_bbox", "gm_set_voxel_bbox",
+    "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
+    "gm_map_load", "gm_map_leaf",
 ]
 
 
@@ -195,6 +197,15 @@ def _lib():
         "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
         "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
         "gm_set_voxel_bbox": (i32, [vp, vp, vp]),
+        "gm_map_create": (i32, [C.c_double, sz, C.POINTER(vp)]),
+        "gm_map_destroy": (None, [vp]),
+        "gm_map_clear": (i32, [vp]),
+        "gm_map_insert": (i32, [vp, vp, vp, i32]),
+        "gm_map_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "gm_map_download": (i32, [vp, vp, vp, vp, sz, C.POINTER(sz)]),
+        "gm_map_save": (i32, [vp, C.c_char_p]),
+        "gm_map_load": (i32, [C.c_char_p, sz, C.POINTER(vp)]),
+        "gm_map_leaf": (C.c_double, [vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -530,3 +541,76 @@ def markers_normals(centroids: np.ndarray, nn_normal8: np.ndarray) -> np.ndarray
     out = np.zeros(cen.shape[0], ARROW_DTYPE)
     _lib().gm_markers_normals(_ptr(cen), _ptr(nn), cen.shape[0], _ptr(out))
     return out
+
+
+class VoxelMap:
+    """Aggregated voxel map across scans (gm_map_*): insertion-order independent."""
+
+    def __init__(self, leaf: float = 0.1, capacity_voxels: int = 1 << 20, _handle=None):
+        if _handle is not None:
+            self._h = _handle
+            return
+        h = C.c_void_p()
+        st = _lib().gm_map_create(C.c_double(leaf), capacity_voxels, C.byref(h))
+        if st != GM_OK:
+            raise GmError(st, "gm_map_create")
+        self._h = h
+
+    @classmethod
+    def load(cls, path: str, min_capacity_voxels: int = 0) -> "VoxelMap":
+        h = C.c_void_p()
+        st = _lib().gm_map_load(path.encode(), min_capacity_voxels, C.byref(h))
+        if st != GM_OK:
+            raise GmError(st, "gm_map_load")
+        return cls(_handle=h)
+
+    def _ck(self, st, where, ok=(GM_OK,)):
+        if st not in ok:
+            raise GmError(st, where)
+        return st
+
+    @property
+    def leaf(self) -> float:
+        return float(_lib().gm_map_leaf(self._h))
+
+    def insert(self, ctx: "Context", pose34=None, label_filter: int = -1):
+        pose = None if pose34 is None else np.ascontiguousarray(np.asarray(pose34, np.float32).reshape(12))
+        self._ck(_lib().gm_map_insert(self._h, ctx._h, _ptr(pose) if pose is not None else None, label_filter), "gm_map_insert")
+
+    def stats(self):
+        """-> (n_voxels, n_points, n_out_of_range, full) ; full = an insert found the table full"""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        st = self._ck(_lib().gm_map_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "gm_map_stats", ok=(GM_OK, GM_ERR_CAPACITY))
+        return int(a.value), int(b.value), int(c.value), st == GM_ERR_CAPACITY
+
+    def download(self):
+        n = C.c_size_t(0)
+        self._ck(_lib().gm_map_download(self._h, None, None, None, 0, C.byref(n)), "gm_map_download", ok=(GM_OK, GM_ERR_CAPACITY))
+        V = int(n.value)
+        ijk, cnt, cen = np.empty((V, 3), np.int32), np.empty(V, np.int32), np.empty((V, 4), np.float32)
+        self._ck(_lib().gm_map_download(self._h, _ptr(ijk), _ptr(cnt), _ptr(cen), V, C.byref(n)), "gm_map_download", ok=(GM_OK, GM_ERR_CAPACITY))
+        return {"ijk": ijk, "counts": cnt, "centroids": cen}
+
+    def clear(self):
+        self._ck(_lib().gm_map_clear(self._h), "gm_map_clear")
+
+    def save(self, path: str):
+        self._ck(_lib().gm_map_save(self._h, path.encode()), "gm_map_save")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().gm_map_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+

@@ -5,6 +5,7 @@
 #include "gm_ransac.cuh"
 #include "gm_polyline.cuh"
 #include "gm_compress.cuh"
+#include "gm_map.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1322,3 +1323,203 @@ void gm_markers_normals(const float* centroids, const float* nn_normal8, int32_t
 }
 
 }  // extern "C"
+
+// ---- aggregated voxel map across scans -------------------------------------------------
+struct gm_map {
+  double leaf = 0.1;
+  float inv_leaf = 10.f;
+  unsigned long long n_slots = 0;
+  unsigned long long* d_keys = nullptr;
+  int* d_cnt = nullptr;
+  long long* d_sums = nullptr;
+  MapState* d_st = nullptr;
+  int* d_cursor = nullptr;
+  int num_sms = 148;
+  std::string err;
+};
+
+namespace {
+struct MapDump { std::vector<unsigned long long> keys; std::vector<int> cnt; std::vector<long long> sums; };
+
+gm_status map_clear_device(gm_map* m) {
+  if (cudaMemset(m->d_keys, 0xFF, m->n_slots * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(m->d_cnt, 0, m->n_slots * sizeof(int)) != cudaSuccess ||
+      cudaMemset(m->d_sums, 0, 3 * m->n_slots * sizeof(long long)) != cudaSuccess ||
+      cudaMemset(m->d_st, 0, sizeof(MapState)) != cudaSuccess) { m->err = "cudaMemset"; return GM_ERR_CUDA; }
+  return GM_OK;
+}
+
+// all voxels, sorted by key (z-major, then y, then x): a deterministic order whatever the insertion history
+gm_status map_dump(gm_map* m, MapDump* out, MapState* st_out) {
+  if (cudaDeviceSynchronize() != cudaSuccess) { m->err = "sync"; return GM_ERR_CUDA; }
+  MapState st;
+  if (cudaMemcpy(&st, m->d_st, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) { m->err = "memcpy"; return GM_ERR_CUDA; }
+  if (st_out) *st_out = st;
+  const size_t V = (size_t)std::max(st.n_voxels, 0);
+  unsigned long long* dk = nullptr; int* dc = nullptr; long long* ds = nullptr;
+  if (dmalloc(&dk, V) != cudaSuccess || dmalloc(&dc, V) != cudaSuccess || dmalloc(&ds, 3 * V) != cudaSuccess) {
+    cudaFree(dk); cudaFree(dc); cudaFree(ds); m->err = "cudaMalloc"; return GM_ERR_CUDA;
+  }
+  cudaMemset(m->d_cursor, 0, sizeof(int));
+  if (V) k_map_export<<<std::min<unsigned long long>((m->n_slots + 255) / 256, (unsigned long long)m->num_sms * 16), 256>>>(
+      m->d_keys, m->d_cnt, m->d_sums, m->n_slots, dk, dc, ds, (int)V, m->d_cursor);
+  std::vector<unsigned long long> k(V); std::vector<int> c(V); std::vector<long long> su(3 * V);
+  cudaError_t e = cudaMemcpy(k.data(), dk, V * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(c.data(), dc, V * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(su.data(), ds, 3 * V * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(dk); cudaFree(dc); cudaFree(ds);
+  if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return GM_ERR_CUDA; }
+  std::vector<size_t> order(V);
+  for (size_t i = 0; i < V; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return k[a] < k[b]; });
+  out->keys.resize(V); out->cnt.resize(V); out->sums.resize(3 * V);
+  for (size_t i = 0; i < V; ++i) {
+    const size_t j = order[i];
+    out->keys[i] = k[j]; out->cnt[i] = c[j];
+    for (int a = 0; a < 3; ++a) out->sums[3 * i + a] = su[3 * j + a];
+  }
+  return GM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+gm_status gm_map_create(double leaf, size_t capacity_voxels, gm_map** out) {
+  if (!out) return GM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!(leaf > 0.0) || capacity_voxels == 0 || capacity_voxels > (1ull << 31)) return GM_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GM_ERR_NO_DEVICE; }
+  gm_map* m = new gm_map();
+  m->leaf = leaf;
+  m->inv_leaf = 1.0f / (float)leaf;  // as pcl::VoxelGrid: inverse_leaf_size = 1 / leaf_size (float)
+  unsigned long long slots = 64;
+  while (slots < 2ull * capacity_voxels) slots <<= 1;  // load factor <= 0.5
+  m->n_slots = slots;
+  int dev = 0; cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount;
+  if (dmalloc(&m->d_keys, slots) != cudaSuccess || dmalloc(&m->d_cnt, slots) != cudaSuccess || dmalloc(&m->d_sums, 3 * slots) != cudaSuccess ||
+      dmalloc(&m->d_st, 1) != cudaSuccess || dmalloc(&m->d_cursor, 1) != cudaSuccess || map_clear_device(m) != GM_OK) {
+    gm_map_destroy(m);
+    return GM_ERR_CUDA;
+  }
+  *out = m;
+  return GM_OK;
+}
+
+void gm_map_destroy(gm_map* m) {
+  if (!m) return;
+  cudaDeviceSynchronize();
+  cudaFree(m->d_keys); cudaFree(m->d_cnt); cudaFree(m->d_sums); cudaFree(m->d_st); cudaFree(m->d_cursor);
+  delete m;
+}
+
+gm_status gm_map_clear(gm_map* m) {
+  if (!m) return GM_ERR_INVALID_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return GM_ERR_CUDA;
+  return map_clear_device(m);
+}
+
+gm_status gm_map_insert(gm_map* m, gm_ctx* ctx, const float* pose34, int32_t label_filter) {
+  if (!m || !ctx || label_filter > 255) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_compacted || (label_filter >= 0 && !ctx->have_labels)) return GM_ERR_STAGE_ORDER;
+  if (ctx->n_input == 0) return GM_OK;
+  Pose34 T{};
+  if (pose34) std::memcpy(T.r, pose34, sizeof(T.r));
+  int blocks = std::min(div_up((long long)ctx->n_input, 256), ctx->num_sms * 16);
+  GM_LAUNCH(ctx, k_map_insert, blocks, 256, ctx->d_cloud_c, ctx->d_labels, &ctx->d_st->n_valid, label_filter < 0 ? -1 : label_filter, T,
+            pose34 ? 1 : 0, m->inv_leaf, m->d_keys, m->d_cnt, m->d_sums, m->n_slots - 1ull, m->d_st);
+  GM_CHECK_LAUNCHES(ctx);
+  return GM_OK;
+}
+
+gm_status gm_map_stats(gm_map* m, int64_t* n_voxels, int64_t* n_points, int64_t* n_out_of_range) {
+  if (!m) return GM_ERR_INVALID_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return GM_ERR_CUDA;
+  MapState st;
+  if (cudaMemcpy(&st, m->d_st, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return GM_ERR_CUDA;
+  if (n_voxels) *n_voxels = st.n_voxels;
+  if (n_points) *n_points = (int64_t)st.n_points;
+  if (n_out_of_range) *n_out_of_range = st.out_of_range;
+  return st.overflow ? GM_ERR_CAPACITY : GM_OK;
+}
+
+gm_status gm_map_download(gm_map* m, int32_t* ijk, int32_t* counts, float* centroids_xyzw, size_t capacity, size_t* n) {
+  if (!m || !n) return GM_ERR_INVALID_ARG;
+  MapDump d; MapState st;
+  gm_status s = map_dump(m, &d, &st);
+  if (s != GM_OK) return s;
+  *n = d.keys.size();
+  if (!ijk && !counts && !centroids_xyzw) return st.overflow ? GM_ERR_CAPACITY : GM_OK;
+  if (capacity < d.keys.size()) return GM_ERR_CAPACITY;
+  for (size_t i = 0; i < d.keys.size(); ++i) {
+    if (ijk) { int x, y, z; map_unpack(d.keys[i], x, y, z); ijk[3 * i] = x; ijk[3 * i + 1] = y; ijk[3 * i + 2] = z; }
+    if (counts) counts[i] = d.cnt[i];
+    if (centroids_xyzw) {
+      const double c = (double)d.cnt[i];
+      for (int a = 0; a < 3; ++a) centroids_xyzw[4 * i + a] = (float)((double)d.sums[3 * i + a] / 1048576.0 / c);
+      centroids_xyzw[4 * i + 3] = 1.0f;
+    }
+  }
+  return st.overflow ? GM_ERR_CAPACITY : GM_OK;
+}
+
+gm_status gm_map_save(gm_map* m, const char* path) {
+  if (!m || !path) return GM_ERR_INVALID_ARG;
+  MapDump d; MapState st;
+  gm_status s = map_dump(m, &d, &st);
+  if (s != GM_OK) return s;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) { m->err = "cannot open file"; return GM_ERR_INVALID_ARG; }
+  const uint32_t magic = 0x314D4D47u /* 'GMM1' */, version = 1;
+  const uint64_t V = d.keys.size();
+  bool ok = std::fwrite(&magic, 4, 1, f) == 1 && std::fwrite(&version, 4, 1, f) == 1 && std::fwrite(&m->leaf, 8, 1, f) == 1 &&
+            std::fwrite(&V, 8, 1, f) == 1;
+  if (ok && V) ok = std::fwrite(d.keys.data(), 8, V, f) == V && std::fwrite(d.cnt.data(), 4, V, f) == V && std::fwrite(d.sums.data(), 8, 3 * V, f) == 3 * V;
+  ok = (std::fclose(f) == 0) && ok;
+  return ok ? GM_OK : GM_ERR_INVALID_ARG;
+}
+
+gm_status gm_map_load(const char* path, size_t min_capacity_voxels, gm_map** out) {
+  if (!path || !out) return GM_ERR_INVALID_ARG;
+  *out = nullptr;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return GM_ERR_INVALID_ARG;
+  uint32_t magic = 0, version = 0; double leaf = 0; uint64_t V = 0;
+  bool ok = std::fread(&magic, 4, 1, f) == 1 && std::fread(&version, 4, 1, f) == 1 && std::fread(&leaf, 8, 1, f) == 1 && std::fread(&V, 8, 1, f) == 1 &&
+            magic == 0x314D4D47u && version == 1 && leaf > 0.0 && V < (1ull << 31);
+  std::vector<unsigned long long> k; std::vector<int> c; std::vector<long long> su;
+  if (ok && V) {
+    k.resize(V); c.resize(V); su.resize(3 * V);
+    ok = std::fread(k.data(), 8, V, f) == V && std::fread(c.data(), 4, V, f) == V && std::fread(su.data(), 8, 3 * V, f) == 3 * V;
+  }
+  std::fclose(f);
+  if (!ok) return GM_ERR_INVALID_ARG;
+  gm_map* m = nullptr;
+  gm_status s = gm_map_create(leaf, std::max<size_t>(std::max<size_t>(min_capacity_voxels, (size_t)V), 1), &m);
+  if (s != GM_OK) return s;
+  if (V) {
+    unsigned long long* dk = nullptr; int* dc = nullptr; long long* ds = nullptr;
+    cudaError_t e = dmalloc(&dk, (size_t)V);
+    if (e == cudaSuccess) e = dmalloc(&dc, (size_t)V);
+    if (e == cudaSuccess) e = dmalloc(&ds, 3 * (size_t)V);
+    if (e == cudaSuccess) e = cudaMemcpy(dk, k.data(), V * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc, c.data(), V * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ds, su.data(), 3 * V * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      k_map_restore<<<std::min<unsigned long long>((V + 255) / 256, (unsigned long long)m->num_sms * 16), 256>>>(dk, dc, ds, (int)V, m->d_keys, m->d_cnt, m->d_sums,
+                                                                                                     m->n_slots - 1ull, m->d_st);
+      e = cudaDeviceSynchronize();
+    }
+    cudaFree(dk); cudaFree(dc); cudaFree(ds);
+    if (e != cudaSuccess) { gm_map_destroy(m); return GM_ERR_CUDA; }
+  }
+  *out = m;
+  return GM_OK;
+}
+
+double gm_map_leaf(const gm_map* m) { return m ? m->leaf : 0.0; }
+
+}  // extern "C"
+

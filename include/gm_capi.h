@@ -310,6 +310,27 @@ GM_API void gm_markers_eigen(const gm_frame* frame, gm_arrow out[3]);
 /* rvizNormals marker payload: src/tunnel_processing.cpp:228-252 -> V arrows from the voxel results */
 GM_API void gm_markers_normals(const float* centroids_xyzw, const float* nn_normal8, int32_t V, gm_arrow* out);
 
+/* ---- aggregated voxel map across scans (builder-defined, the reference keeps nothing between
+ * callbacks, src/geometric_mapping.cpp:48-125) --------------------------------------------------------
+ * A device hash table keyed by the GLOBAL VoxelGrid cell floor(p * inv_leaf) of every inserted point, holding the
+ * point count and the coordinate sums in 2^-20 m fixed point: insertion order (scans, contexts, streams) does
+ * not change the result.  gm_map_insert adds the compacted cloud of `ctx` (after gm_normals; asynchronous on
+ * the ctx stream), optionally only the points with label == label_filter (after gm_label; -1 = all), after the
+ * rigid transform pose34 = row-major [R|t] (NULL = identity; p' = R p + t as fmaf chains).  gm_map_download
+ * returns the voxels sorted by (z, y, x) index: integer cell, count, centroid = sum / count.  gm_map_save / load:
+ * little-endian file 'GMM1' | leaf f64 | V u64 | keys u64[V] | counts i32[V] | sums i64[3V] (exact state). */
+typedef struct gm_map gm_map;
+GM_API gm_status gm_map_create(double leaf, size_t capacity_voxels, gm_map** out);
+GM_API void gm_map_destroy(gm_map* map);
+GM_API gm_status gm_map_clear(gm_map* map);
+GM_API gm_status gm_map_insert(gm_map* map, gm_ctx* ctx, const float* pose34, int32_t label_filter);
+/* GM_ERR_CAPACITY if an insert found the table full (those points were dropped) */
+GM_API gm_status gm_map_stats(gm_map* map, int64_t* n_voxels, int64_t* n_points, int64_t* n_out_of_range);
+GM_API gm_status gm_map_download(gm_map* map, int32_t* ijk, int32_t* counts, float* centroids_xyzw, size_t capacity, size_t* n);
+GM_API gm_status gm_map_save(gm_map* map, const char* path);
+GM_API gm_status gm_map_load(const char* path, size_t min_capacity_voxels, gm_map** out);
+GM_API double gm_map_leaf(const gm_map* map);
+
 #ifdef __cplusplus
 }
 #endif

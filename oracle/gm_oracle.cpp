@@ -1021,3 +1021,58 @@ GMO_API void gmo_compress(const float* pts4, const uint8_t* labels, int64_t n, c
 
 GMO_API int32_t gmo_num_threads() { return resolve_threads(0); }
 GMO_API int32_t gmo_version() { return 1; }
+
+// ---- aggregated voxel map across scans (builder-defined; csrc/gm_map.cuh) ------------------
+// The reference keeps nothing between callbacks (src/geometric_mapping.cpp:48-125).  Definition: every
+// inserted point p' = R p + t (fmaf chains) falls in the global VoxelGrid cell floor(p' * inv_leaf),
+// inv_leaf = 1.0f / float(leaf) as in pcl::VoxelGrid; per cell the count and the sums of
+// llrint(coord * 2^20) (exact integers, order independent); centroid = float(double(sum) / 2^20 / count).
+// State is carried by the caller as sorted arrays so that the oracle stays a pure function:
+//   in : keys[V] (packed 21-bit biased x|y<<21|z<<42), cnt[V], sums[3V]   (V may be 0)
+//   out: the merged, key-sorted arrays (capacity V + n); returns the new V.  out_of_range counts skipped points.
+#include <map>
+GMO_API int64_t gmo_map_insert(const uint64_t* keys, const int32_t* cnt, const int64_t* sums, int64_t V, const float* pts4,
+                               const uint8_t* labels, int64_t n, int32_t label_filter, const float* pose34, double leaf,
+                               uint64_t* out_keys, int32_t* out_cnt, int64_t* out_sums, float* out_centroids4, int64_t* out_of_range) {
+  struct Acc { int32_t c; int64_t s[3]; };
+  std::map<uint64_t, Acc> m;
+  for (int64_t i = 0; i < V; ++i) m[keys[i]] = Acc{cnt[i], {sums[3 * i], sums[3 * i + 1], sums[3 * i + 2]}};
+  const P4* p = (const P4*)pts4;
+  const float inv = 1.0f / (float)leaf;
+  int64_t oor = 0;
+  const int lim = 1 << 20;
+  for (int64_t i = 0; i < n; ++i) {
+    if (label_filter >= 0 && labels[i] != (uint8_t)label_filter) continue;
+    float x = p[i].x, y = p[i].y, z = p[i].z;
+    if (pose34) {
+      const float* T = pose34;
+      x = std::fmaf(T[0], p[i].x, std::fmaf(T[1], p[i].y, std::fmaf(T[2], p[i].z, T[3])));
+      y = std::fmaf(T[4], p[i].x, std::fmaf(T[5], p[i].y, std::fmaf(T[6], p[i].z, T[7])));
+      z = std::fmaf(T[8], p[i].x, std::fmaf(T[9], p[i].y, std::fmaf(T[10], p[i].z, T[11])));
+    }
+    if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z)) { ++oor; continue; }
+    const float fx = std::floor(x * inv), fy = std::floor(y * inv), fz = std::floor(z * inv);
+    if (!(std::fabs(fx) < 2.0e6f && std::fabs(fy) < 2.0e6f && std::fabs(fz) < 2.0e6f)) { ++oor; continue; }
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    if (ix < -lim || ix >= lim || iy < -lim || iy >= lim || iz < -lim || iz >= lim) { ++oor; continue; }
+    const uint64_t key = (uint64_t)(uint32_t)(ix + lim) | ((uint64_t)(uint32_t)(iy + lim) << 21) | ((uint64_t)(uint32_t)(iz + lim) << 42);
+    Acc& a = m[key];  // value-initialised to zero on first use
+    a.c += 1;
+    a.s[0] += (int64_t)std::llrint((double)(x * 1048576.0f));
+    a.s[1] += (int64_t)std::llrint((double)(y * 1048576.0f));
+    a.s[2] += (int64_t)std::llrint((double)(z * 1048576.0f));
+  }
+  int64_t o = 0;
+  for (const auto& kv : m) {
+    out_keys[o] = kv.first; out_cnt[o] = kv.second.c;
+    for (int a = 0; a < 3; ++a) {
+      out_sums[3 * o + a] = kv.second.s[a];
+      if (out_centroids4) out_centroids4[4 * o + a] = (float)((double)kv.second.s[a] / 1048576.0 / (double)kv.second.c);
+    }
+    if (out_centroids4) out_centroids4[4 * o + 3] = 1.0f;
+    ++o;
+  }
+  if (out_of_range) *out_of_range = oor;
+  return o;
+}
+

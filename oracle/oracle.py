@@ -41,6 +41,7 @@ def lib():
         _L.gmo_argmax.restype = C.c_int32
         _L.gmo_polyline.restype = C.c_int32
         _L.gmo_num_threads.restype = C.c_int32
+        _L.gmo_map_insert.restype = C.c_int64
     return _L
 
 
@@ -237,3 +238,32 @@ def compress(pts, labels_u8, plane4, cyl7, tau, leaf):
             "n_residual_voxels": int(ints[4]), "plane_u": fl[0:3].copy(), "plane_v": fl[3:6].copy(), "plane_bounds": fl[6:10].copy(),
             "plane_rms": float(fl[10]), "cyl_t_range": fl[11:13].copy(), "cyl_rms": float(fl[13]), "residual_rms": float(fl[14]),
             "total_rms": float(fl[15]), "residual_centroids": cen[: int(ints[4])].copy()}
+
+
+def map_insert(state, pts, leaf, labels=None, label_filter=-1, pose34=None):
+    """Aggregated voxel map (gmo_map_insert).  state = None or the dict returned by a previous call;
+    -> {"keys" u64, "ijk" int32 Vx3, "counts", "sums" int64 Vx3, "centroids" Vx4, "out_of_range"} sorted by key."""
+    pts = _f32(pts)
+    n = pts.shape[0]
+    if state is None:
+        k0, c0, s0 = np.empty(0, np.uint64), np.empty(0, np.int32), np.empty((0, 3), np.int64)
+        oor0 = 0
+    else:
+        k0, c0, s0, oor0 = state["keys"], state["counts"], state["sums"], state["out_of_range"]
+    V = len(k0)
+    cap = V + n + 1
+    ko, co, so = np.empty(cap, np.uint64), np.empty(cap, np.int32), np.empty((cap, 3), np.int64)
+    ceo = np.empty((cap, 4), np.float32)
+    oor = C.c_int64(0)
+    lab = None if labels is None else np.ascontiguousarray(labels, np.uint8)
+    pose = None if pose34 is None else _f32(np.asarray(pose34).reshape(12))
+    Vn = lib().gmo_map_insert(_p(np.ascontiguousarray(k0)), _p(np.ascontiguousarray(c0)), _p(np.ascontiguousarray(s0)), C.c_int64(V),
+                              _p(pts), _p(lab), C.c_int64(n), C.c_int32(label_filter if lab is not None else -1), _p(pose),
+                              C.c_double(leaf), _p(ko), _p(co), _p(so), _p(ceo), C.byref(oor))
+    keys = ko[:Vn].copy()
+    m = np.uint64((1 << 21) - 1)
+    ijk = np.stack([(keys & m).astype(np.int64) - (1 << 20), ((keys >> np.uint64(21)) & m).astype(np.int64) - (1 << 20),
+                    ((keys >> np.uint64(42)) & m).astype(np.int64) - (1 << 20)], axis=1).astype(np.int32)
+    return {"keys": keys, "ijk": ijk, "counts": co[:Vn].copy(), "sums": so[:Vn].copy(), "centroids": ceo[:Vn].copy(),
+            "out_of_range": oor0 + int(oor.value)}
+

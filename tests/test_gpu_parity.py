@@ -803,6 +803,77 @@ def test_map_slabs_reproduce_the_whole_map():
     assert np.abs(scatter.reshape(-1) - w_scatter).max() <= 1e-5 * np.abs(w_scatter).max()        # sum of the partial scatters
 
 
+# ---- aggregated voxel map across scans ----------------------------------------------------
+def _pose(yaw, t):
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    return np.array([[c, -s_, 0, t[0]], [s_, c, 0, t[1]], [0, 0, 1, t[2]]], np.float32)
+
+
+def test_voxel_map_matches_oracle_and_is_order_independent(tmp_path):
+    n, frames, leaf = 40_000, 4, 0.1
+    poses = [_pose(0.02 * f, (1.0 * f, 0.05 * f, 0.0)) for f in range(frames)]
+    clouds, labels = [], []
+    with _ctx(n, neighborRadius=0.15) as ctx, capi.VoxelMap(leaf, 1 << 18) as vm, capi.VoxelMap(leaf, 1 << 18) as vm_rev, \
+            capi.VoxelMap(leaf, 1 << 18) as vm_cyl:
+        for f in range(frames):
+            pts = _scan_with_junk(n, seed=200 + f)
+            ctx.upload_scan(pts)
+            ctx.crop()
+            ctx.normals()
+            nv = ctx.counts().n_valid
+            ctx.upload_scan(pts)
+            ctx.process_scan(synth.sample_indices(nv, 128, 3, seed=3), synth.sample_indices(nv, 128, 2, seed=4))
+            clouds.append(ctx.download_cloud(1)); labels.append(ctx.download_labels())
+            vm.insert(ctx, poses[f])
+            vm_cyl.insert(ctx, None, label_filter=2)
+        for f in reversed(range(frames)):                      # same scans, other order, through injection
+            ctx.inject_compacted(clouds[f], None)
+            vm_rev.insert(ctx, poses[f])
+        got, got_rev, got_cyl = vm.download(), vm_rev.download(), vm_cyl.download()
+        stats = vm.stats()
+        path = str(tmp_path / "map.gmm")
+        vm.save(path)
+        with capi.VoxelMap.load(path) as vm2:
+            again = vm2.download()
+            assert abs(vm2.leaf - leaf) < 1e-12 and vm2.stats()[:2] == stats[:2]
+            ctx.inject_compacted(clouds[0], None)              # a loaded map keeps aggregating
+            vm2.insert(ctx, poses[1])
+            more = vm2.download()
+    ref, ref_cyl = None, None
+    for f in range(frames):
+        ref = O.map_insert(ref, clouds[f], leaf, pose34=poses[f])
+        ref_cyl = O.map_insert(ref_cyl, clouds[f], leaf, labels=labels[f], label_filter=2)
+    assert stats[0] == len(ref["ijk"]) and stats[1] == sum(len(c) for c in clouds) - ref["out_of_range"] and not stats[3]
+    for g in (got, got_rev, again):
+        assert np.array_equal(g["ijk"], ref["ijk"]) and np.array_equal(g["counts"], ref["counts"])       # cells, counts: exact
+        assert np.array_equal(g["centroids"].view(np.uint32), ref["centroids"].view(np.uint32))         # fixed-point sums: exact
+    assert np.array_equal(got_cyl["ijk"], ref_cyl["ijk"]) and np.array_equal(got_cyl["counts"], ref_cyl["counts"])
+    assert np.array_equal(got_cyl["centroids"].view(np.uint32), ref_cyl["centroids"].view(np.uint32))
+    ref_more = O.map_insert(ref, clouds[0], leaf, pose34=poses[1])
+    assert np.array_equal(more["ijk"], ref_more["ijk"]) and np.array_equal(more["counts"], ref_more["counts"])
+    # one identity-pose frame: same cells and counts as pcl::VoxelGrid of that frame, centroids within the fixed-point step
+    vg = O.voxel(clouds[0], leaf)
+    one = O.map_insert(None, clouds[0], leaf)
+    lin = (one["ijk"] - vg["grid6"][:3]) @ np.array([1, vg["grid6"][3], vg["grid6"][3] * vg["grid6"][4]])
+    assert np.array_equal(lin, vg["voxel_keys"]) and np.array_equal(one["counts"], vg["voxel_counts"])
+    assert np.abs(one["centroids"][:, :3] - vg["centroids"][:, :3]).max() < 1e-5
+
+
+def test_voxel_map_capacity_and_range_are_reported():
+    n = 20_000
+    pts = synth.curved_tunnel(n, seed=9)
+    with _ctx(n, neighborRadius=0.2) as ctx, capi.VoxelMap(0.1, 64) as small, capi.VoxelMap(1e-6, 1 << 16) as fine:
+        ctx.upload_scan(pts); ctx.crop(); ctx.normals()
+        small.insert(ctx)
+        v, p, oor, full = small.stats()
+        assert full and v == 128 and p < n                     # 128 slots, every slot taken, the rest dropped and flagged
+        fine.insert(ctx)                                       # 1 um voxels: indices beyond +-2^20 are counted, not wrapped
+        v, p, oor, full = fine.stats()
+        assert oor > 0 and p + oor == ctx.counts().n_valid and not full
+        fine.clear()
+        assert fine.stats()[:3] == (0, 0, 0)
+
+
 # ---- I/O seams ---------------------------------------------------------------------------------------
 def test_pointcloud2_decode_velodyne_layout():
     """sensor_msgs/PointCloud2 as the Velodyne driver publishes it: point_step 22 (x,y,z,intensity f32 +

@@ -233,3 +233,32 @@ def test_golden_vectors():
         assert a.shape == b.shape, k
         both_nan = np.isnan(a) & np.isnan(b)
         assert np.allclose(np.where(both_nan, 0, a), np.where(both_nan, 0, b), rtol=1e-5, atol=1e-6), k
+
+
+def test_map_insert_known_answers_and_order_independence():
+    """Aggregated voxel map oracle: lattice points land in the expected global cells; inserting the same
+    clouds in another order, or split differently, gives the identical state (integer sums)."""
+    leaf = 0.1
+    pts = np.array([[0.05, 0.05, 0.05, 1], [0.06, 0.01, 0.09, 1], [-0.01, 0.0, 0.0, 1], [1.234, -5.678, 0.25, 1], [np.nan, 0, 0, 1]],
+                   np.float32)
+    st = O.map_insert(None, pts, leaf)
+    assert st["out_of_range"] == 1
+    assert st["ijk"].tolist() == [[-1, 0, 0], [0, 0, 0], [12, -57, 2]]           # sorted by (z, y, x)
+    by_cell = {tuple(c): k for c, k in zip(st["ijk"].tolist(), st["counts"].tolist())}
+    assert by_cell == {(0, 0, 0): 2, (-1, 0, 0): 1, (12, -57, 2): 1}
+    c000 = st["centroids"][[tuple(c) == (0, 0, 0) for c in st["ijk"].tolist()].index(True)]
+    assert np.abs(c000[:3] - np.array([0.055, 0.03, 0.07])).max() < 2e-6
+    g = np.random.Generator(np.random.Philox(3))
+    a = g.uniform(-3, 3, (5000, 4)).astype(np.float32)
+    b = g.uniform(-3, 3, (7000, 4)).astype(np.float32)
+    pose = np.array([[0.6, -0.8, 0, 1.5], [0.8, 0.6, 0, -2.0], [0, 0, 1, 0.25]], np.float32)
+    s1 = O.map_insert(O.map_insert(None, a, leaf, pose34=pose), b, leaf)
+    s2 = O.map_insert(O.map_insert(None, b, leaf), a, leaf, pose34=pose)
+    s3 = O.map_insert(O.map_insert(O.map_insert(None, b[:100], leaf), a[::-1], leaf, pose34=pose), b[100:], leaf)
+    for s in (s2, s3):
+        assert np.array_equal(s1["keys"], s["keys"]) and np.array_equal(s1["counts"], s["counts"]) and np.array_equal(s1["sums"], s["sums"])
+    assert s1["counts"].sum() == 12000
+    lab = (np.arange(5000) % 3).astype(np.uint8)
+    only = O.map_insert(None, a, leaf, labels=lab, label_filter=2)
+    assert only["counts"].sum() == (lab == 2).sum()
+

@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--hyp", type=int, default=1024, help="total RANSAC hypotheses (half plane, half cylinder)")
     ap.add_argument("--shard-hyp", type=int, default=4096, help="hypotheses of the sharded RANSAC leg (N>1)")
+    ap.add_argument("--shard-hyp-large", type=int, default=65536, help="second sharded RANSAC leg, large enough to amortise the "
+                    "fixed cost of a round (0 = skip)")
     ap.add_argument("--radius", type=float, default=0.05)
     ap.add_argument("--leaf", type=float, default=0.1)
     ap.add_argument("--refit-iters", type=int, default=5)
@@ -180,6 +182,35 @@ def physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank (and therefore its pinned host buffers, first touch) to the CPUs of the NUMA node its GPU
+    hangs off: with 8 ranks streaming 33 MB per scan each way, cross-socket traffic caps the end-to-end rate."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:      # nvml: 00000000:1B:00.0 -> sysfs: 0000:1b:00.0
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def load_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the main kernels from the
     committed ncu --set full capture (profiles/r01_traffic.json: {kernel: bytes, "_source": command})."""
@@ -217,6 +248,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(physical_gpu_index(local_rank)) if world > 1 else None
     if world > 1:
         # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -236,7 +268,7 @@ def main():
         hp = torch.from_numpy(pts).pin_memory()
         host_scans.append(hp)
         dev_scans.append(hp.to(dev, non_blocking=False))
-    ctx = capi.Context(params, max_points=n, max_hypotheses=max(4096, a.shard_hyp))
+    ctx = capi.Context(params, max_points=n, max_hypotheses=max(4096, a.shard_hyp, a.shard_hyp_large))
     ctx.set_stream(stream.cuda_stream)
 
     # sample indices need the compacted size of each scan: learn it once (untimed)
@@ -494,6 +526,21 @@ def main():
     ransac = {"hyp_pts_per_sec": Hs * nv * a.steps / (rms * 1e-3), "H": Hs, "points": nv, "ms_per_round": rms / a.steps,
               "mode": "hypotheses sharded across ranks, NCCL max-allreduce of packed (count,id), refit on every rank",
               "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
+    if a.shard_hyp_large > 0:
+        Hl = a.shard_hyp_large
+        sp, sc = synth.sample_indices(nv, Hl // 2, 3, seed=5), synth.sample_indices(nv, Hl - Hl // 2, 2, seed=6)
+        reps_l = max(3, min(a.steps, 10))
+        ransac_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(reps_l):
+            ransac_step()
+        e1.record(stream)
+        barrier()
+        rms_l = max_over_ranks(e0.elapsed_time(e1))
+        mp, mc = ctx.model(0), ctx.model(1)
+        ransac["large"] = {"hyp_pts_per_sec": Hl * nv * reps_l / (rms_l * 1e-3), "H": Hl, "ms_per_round": rms_l / reps_l,
+                           "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
 
     # ---- compression of the segmented cloud (extra stage, reported separately) -------------------------
     for i in range(3):
@@ -609,7 +656,8 @@ def main():
             "latency_ms_per_scan": latency_ms,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / a.steps, "pipeline": f"{NCTX} contexts / streams, pinned host buffers"},
+                    "ms_per_step": 1e3 * e2e_s / a.steps, "pipeline": f"{NCTX} contexts / streams, pinned host buffers",
+                    "numa_node_rank0": numa_node},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_families": families,

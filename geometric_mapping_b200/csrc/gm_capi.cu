@@ -292,21 +292,30 @@ gm_status next_epoch(gm_ctx* ctx, unsigned* out) {
 
 // LSD radix sort of (d_keys[0], d_vals[0]) -> returns the buffer index holding the result.
 // Three wait-free kernels per 8-bit pass (see gm_device.cuh); no memsets, no inter-block spinning.
-gm_status radix_sort(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int key_bits, int* result_buf) {
-  int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
-  int ntiles = div_up((long long)n_cap, RS_TILE);
+constexpr int kSmallSortKeys = 0;  // 1024-key tiles were measured SLOWER at 1M keys (73.6 vs 70.6 us per 3-pass sort): the passes are
+                                   // bound by the fixed cost of three dependent launches, not by the per-block chain; kept selectable (GM_SORT_IPT=4)
+template <int IPT>
+gm_status radix_sort_t(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int passes, int* result_buf) {
+  constexpr int TILE = RS_BLOCK * IPT;
+  int ntiles = div_up((long long)n_cap, TILE);
   if ((size_t)ntiles * 256 > ctx->rs_hist_words) { ctx->err = "radix histogram capacity"; return GM_ERR_CAPACITY; }
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
-    GM_LAUNCH(ctx, k_rs_upsweep, ntiles, RS_BLOCK, ctx->d_keys[cur], n_ptr, p, ntiles, ctx->d_rs_hist);
-    GM_LAUNCH(ctx, k_rs_scan, 256, RS_BLOCK, ctx->d_rs_hist, n_ptr, ntiles, ctx->d_rs_totals);
-    GM_LAUNCH(ctx, k_rs_downsweep, ntiles, RS_BLOCK, ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1], ctx->d_vals[cur ^ 1], n_ptr,
+    GM_LAUNCH(ctx, k_rs_upsweep<IPT>, ntiles, RS_BLOCK, ctx->d_keys[cur], n_ptr, p, ntiles, ctx->d_rs_hist);
+    GM_LAUNCH(ctx, k_rs_scan, 256, RS_BLOCK, ctx->d_rs_hist, n_ptr, TILE, ntiles, ctx->d_rs_totals);
+    GM_LAUNCH(ctx, k_rs_downsweep<IPT>, ntiles, RS_BLOCK, ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1], ctx->d_vals[cur ^ 1], n_ptr,
               p, ntiles, ctx->d_rs_hist, ctx->d_rs_totals);
     cur ^= 1;
   }
   *result_buf = cur;
   GM_CHECK_LAUNCHES(ctx);
   return GM_OK;
+}
+gm_status radix_sort(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int key_bits, int* result_buf) {
+  int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
+  static const int kForce = [] { const char* e = std::getenv("GM_SORT_IPT"); return e ? std::atoi(e) : 0; }();
+  const bool small = kForce ? kForce == 4 : n_cap <= (size_t)kSmallSortKeys;
+  return small ? radix_sort_t<4>(ctx, n_ptr, n_cap, passes, result_buf) : radix_sort_t<8>(ctx, n_ptr, n_cap, passes, result_buf);
 }
 
 gm_status sync_state(gm_ctx* ctx, DevState* host) {
@@ -401,7 +410,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_vkey_pt, N); A(d_assign, N); A(d_vox_start, N + 1); A(d_vox_key, N); A(d_vox_count, N); A(d_nn_idx, N);
   A(d_labels, N);
   A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
-  ctx->rs_hist_words = (size_t)div_up((long long)N, RS_TILE) * 256;
+  ctx->rs_hist_words = (size_t)div_up((long long)N, RS_BLOCK * 4) * 256;  // sized for the smaller tile
   A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256);
   A(d_st, 1);
   A(d_partials, 3 * kPartialsRegion);  // 3 regions: frame | plane refit | cylinder GN (may run concurrently)

@@ -250,15 +250,17 @@ __device__ __forceinline__ void tile_compact_ranks(const bool (&flags)[IPT], uns
 // round with many distinct digits) + 4-5 us of look-back (resident tiles advance in lockstep, so
 // every tile walks ~300 predecessors x 256 digits = 600 KB of L2 reads) + 3.3 us scatter, i.e.
 // 1.4 TB/s.  Ranking here uses 8 ballots per key (fixed latency) instead of match_any.
+// Keys per thread (RS_IPT) is a template parameter: 8 (2048-key tiles) is the default; 4 was tried for ~1M-key
+// inputs (more, shorter blocks) and measured slightly slower (see gm_capi.cu:radix_sort).
 constexpr int RS_BLOCK = 256;
-constexpr int RS_IPT = 8;
-constexpr int RS_TILE = RS_BLOCK * RS_IPT;  // 2048 keys per tile: ~60 registers -> 4 blocks per SM
 constexpr int RS_WARPS = RS_BLOCK / 32;
 constexpr int RS_MAX_PASSES = 4;
 
+template <int RS_IPT>
 __global__ void __launch_bounds__(RS_BLOCK)
 k_rs_upsweep(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int pass, int tile_stride,
              unsigned* __restrict__ hist /* [256][tile_stride] */) {
+  constexpr int RS_TILE = RS_BLOCK * RS_IPT;
   __shared__ unsigned sh[256];
   const int n = *n_ptr;
   const int tile = blockIdx.x, base = tile * RS_TILE;
@@ -277,11 +279,11 @@ k_rs_upsweep(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, i
 
 // grid = 256 blocks (one per digit)
 __global__ void __launch_bounds__(RS_BLOCK)
-k_rs_scan(unsigned* __restrict__ hist, const int* __restrict__ n_ptr, int tile_stride, unsigned* __restrict__ totals /* [256] */) {
+k_rs_scan(unsigned* __restrict__ hist, const int* __restrict__ n_ptr, int tile_keys, int tile_stride, unsigned* __restrict__ totals /* [256] */) {
   __shared__ unsigned s_warp[RS_WARPS];
   __shared__ unsigned s_carry;
   const int n = *n_ptr;
-  const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+  const int ntiles = (n + tile_keys - 1) / tile_keys;
   unsigned* row = hist + (size_t)blockIdx.x * tile_stride;
   const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = 0;
@@ -304,10 +306,12 @@ k_rs_scan(unsigned* __restrict__ hist, const int* __restrict__ n_ptr, int tile_s
   if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
 }
 
+template <int RS_IPT>
 __global__ void __launch_bounds__(RS_BLOCK)
 k_rs_downsweep(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned* __restrict__ keys_out,
                unsigned* __restrict__ vals_out, const int* __restrict__ n_ptr, int pass, int tile_stride,
                const unsigned* __restrict__ hist /* row prefixes */, const unsigned* __restrict__ totals) {
+  constexpr int RS_TILE = RS_BLOCK * RS_IPT;
   __shared__ unsigned s_warp_hist[RS_WARPS][257];
   __shared__ unsigned s_keys[RS_TILE];
   __shared__ unsigned s_vals[RS_TILE];

@@ -282,7 +282,7 @@ def main():
         nv = ctx.counts().n_valid
         n_valid.append(nv)
         if s < 2:
-            nbr_sum.append(float(ctx.download_neighbor_counts().astype(np.int64).sum()))
+            nbr_sum.append(ctx.search_stats())
         samples.append((synth.sample_indices(nv, Hp, 3, seed=3 + s), synth.sample_indices(nv, Hc, 2, seed=4 + s)))
 
     def step(i):
@@ -417,19 +417,22 @@ def main():
     vox_gbs = vox_bytes / (vox_ms * 1e-3) / 1e9 if vox_ms > 0 else 0.0
     traffic = load_traffic()
     fp32_src = f"{sms} SMs x 128 lanes x 2 x {clk:.0f} MHz observed"
-    nbr_per_scan = float(np.mean(nbr_sum)) if nbr_sum else 50.0 * M
+    cand_per_scan = float(np.mean([c_ for c_, _ in nbr_sum])) if nbr_sum else 150.0 * M
+    nbr_per_scan = float(np.mean([n_ for _, n_ in nbr_sum])) if nbr_sum else 40.0 * M
     nrm_ms = seg_ms["normals"]
-    # k_normals: a perfect neighbour search would touch only the true neighbours: 8 flop for the exact
-    # FLANN distance + 15 flop for the 9-accumulator update per neighbour, ~150 flop of eigen33 per point
-    nrm_flops = 23.0 * nbr_per_scan + 150.0 * M
+    # k_normals, grid-hashed radius search (cell = radius, 27-cell stencil): every point of the stencil takes the
+    # exact FLANN distance test (8 flop), every neighbour the 9-accumulator update (15 flop), every point ~150 flop of
+    # eigen33.  The counts are measured by the kernel itself (gm_get_search_stats).
+    nrm_flops = 8.0 * cand_per_scan + 15.0 * nbr_per_scan + 150.0 * M
     nrm_tflops = nrm_flops / (nrm_ms * 1e-3) / 1e12 if nrm_ms > 0 else 0.0
     brute_tflops = count_flops / (brute_ms * 1e-3) / 1e12 if brute_ms > 0 else 0.0
     families = {
         "normals": {"bound": "fp32", "achieved": nrm_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                     "frac": nrm_tflops / fp32_peak_tflops, "traffic": traffic.get("k_normals"), "ms_per_step": nrm_ms,
                     "kernels": "k_normals",
-                    "algorithmic": f"23 flop x {nbr_per_scan:.0f} true neighbours + 150 flop x {M:.0f} points (a search that tests "
-                                   f"~3 candidates per neighbour executes more; ncu: 77 % of issue slots active)",
+                    "algorithmic": f"8 flop x {cand_per_scan:.0f} stencil candidates + 15 flop x {nbr_per_scan:.0f} neighbours + 150 flop x "
+                                   f"{M:.0f} points; the kernel is instruction-issue bound (ncu: 77 % of issue slots active, ~30 "
+                                   f"instructions per candidate of which 8 are these flops)",
                     "points_per_s": M / (nrm_ms * 1e-3) if nrm_ms > 0 else 0.0, "peak_source": fp32_src},
         "inlier_count": {"bound": "fp32", "achieved": count_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": count_tflops / fp32_peak_tflops, "traffic": traffic.get("k_count_tiles"), "ms_per_step": count_ms,

@@ -123,7 +123,7 @@ SYMBOLS = [
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
     "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
     "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode", "gm_set_grid_box", "gm_set_owned_range", "gm_get_voxel_bbox", "gm_set_voxel_bbox",
-    "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
+    "gm_get_search_stats", "gm_set_voxel_mode", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
     "gm_map_load", "gm_map_leaf",
 ]
 
@@ -197,6 +197,8 @@ def _lib():
         "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
         "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
         "gm_set_voxel_bbox": (i32, [vp, vp, vp]),
+        "gm_get_search_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "gm_set_voxel_mode": (i32, [vp, i32]),
         "gm_map_create": (i32, [C.c_double, sz, C.POINTER(vp)]),
         "gm_map_destroy": (None, [vp]),
         "gm_map_clear": (i32, [vp]),
@@ -308,6 +310,16 @@ class Context:
     def set_owned_range(self, axis: int = -1, lo: float = 0.0, hi: float = 0.0):
         """Points with coord[axis] outside [lo, hi) are halo: searched, then dropped with the NaN normals."""
         self._ck(_lib().gm_set_owned_range(self._h, axis, lo, hi), "gm_set_owned_range")
+
+    def set_voxel_mode(self, mode: int):
+        """0 = sort-free dense VoxelGrid when the lattice fits (default), 1 = always sort-based; identical results."""
+        self._ck(_lib().gm_set_voxel_mode(self._h, mode), "gm_set_voxel_mode")
+
+    def search_stats(self):
+        """-> (distance tests executed, neighbours found) of the last normals()"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(_lib().gm_get_search_stats(self._h, C.byref(a), C.byref(b)), "gm_get_search_stats")
+        return int(a.value), int(b.value)
 
     def voxel_bbox(self):
         a, b = np.empty(3, np.float32), np.empty(3, np.float32)

@@ -106,6 +106,12 @@ struct gm_ctx {
   int *d_cell_id = nullptr, *d_ucell_start = nullptr, *d_nbr = nullptr, *d_valid_map = nullptr;
   int2* d_runs = nullptr;
   int2* d_cell_nruns = nullptr;  // per occupied cell: {number of runs, number of candidates}
+  // dense VoxelGrid tables (sort-free path): count, voxel id and 3 fixed-point sums per key
+  int *d_dense_cnt = nullptr, *d_dense_id = nullptr;
+  long long* d_dense_sum = nullptr;
+  unsigned long long* d_dense_state = nullptr;  // look-back tile states of the scan over the tables
+  size_t dense_cap = 0;
+  int voxel_mode = 0;  // 0 = dense tables when the key range fits, 1 = always sort
   BlockEntry* d_tab = nullptr;  // dense block table of the neighbour grid (1 << (key_bits - 6) entries)
   size_t tab_entries = 0;
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
@@ -284,6 +290,7 @@ gm_status next_epoch(gm_ctx* ctx, unsigned* out) {
     GM_CUDA(cudaStreamSynchronize(ctx->stream));
     GM_CUDA(cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
     GM_CUDA(cudaMemset(ctx->d_state64_b, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
+    if (ctx->d_dense_state) GM_CUDA(cudaMemset(ctx->d_dense_state, 0, ((size_t)div_up((long long)ctx->dense_cap, CPL_TILE) + 2) * sizeof(unsigned long long)));
     ctx->epoch = 1;
   }
   *out = ctx->epoch;
@@ -436,6 +443,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
   { const char* env = std::getenv("GM_SERIAL"); ctx->concurrent = !(env && env[0] == '1'); }
   { const char* env = std::getenv("GM_COUNT_MODE"); ctx->count_mode = (env && env[0] == '1') ? 1 : 0; }
+  { const char* env = std::getenv("GM_VOXEL_MODE"); ctx->voxel_mode = (env && env[0] == '1') ? 1 : 0; }
 
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
@@ -455,7 +463,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
 void gm_destroy(gm_ctx* ctx) {
   if (!ctx) return;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->d_tab, ctx->d_cell_nruns, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
+  void* ptrs[] = {ctx->d_dense_state, ctx->d_dense_cnt, ctx->d_dense_id, ctx->d_dense_sum, ctx->d_tab, ctx->d_cell_nruns, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
@@ -510,6 +518,17 @@ gm_status gm_set_voxel_bbox(gm_ctx* ctx, const float* min3, const float* max3) {
   return GM_OK;
 }
 
+gm_status gm_get_search_stats(gm_ctx* ctx, int64_t* candidates, int64_t* neighbors) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_normals) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  if (candidates) *candidates = (int64_t)h.n_candidates;
+  if (neighbors) *neighbors = (int64_t)h.n_neighbors;
+  return GM_OK;
+}
+
 gm_status gm_get_voxel_bbox(gm_ctx* ctx, float* min3, float* max3) {
   if (!ctx || !min3 || !max3) return GM_ERR_INVALID_ARG;
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
@@ -525,6 +544,12 @@ gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return GM_OK;
+}
+
+gm_status gm_set_voxel_mode(gm_ctx* ctx, int32_t mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  ctx->voxel_mode = mode;
   return GM_OK;
 }
 
@@ -647,7 +672,7 @@ gm_status gm_normals(gm_ctx* ctx) {
     float r2 = rf * rf;
     { SegTimer seg_(ctx, SEG_NORMALS);
       GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
-                ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own); }
+                ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st); }
     if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_COMPACT);
       GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
@@ -664,19 +689,64 @@ gm_status gm_normals(gm_ctx* ctx) {
 namespace {
 struct VoxBuffers { int *key_pt, *assign, *vox_start, *vox_key, *vox_count; float4* centroid; };
 
-// pcl::VoxelGrid of `pts` (vs->n points, bbox already in vs): keys -> sort -> heads -> centroids.
-gm_status voxel_downsample(gm_ctx* ctx, const float4* pts, VoxState* vs, size_t n_cap, int key_bits, const VoxBuffers& o, int* sorted_buf) {
+constexpr size_t kDenseMaxKeys = (size_t)1 << 23;  // 8M keys x 32 B = 256 MB of tables at most
+
+// Make the dense tables hold `range` keys (zero-initialised; they clean themselves afterwards).  Rare path.
+gm_status ensure_dense(gm_ctx* ctx, size_t range) {
+  if (range <= ctx->dense_cap) return GM_OK;
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < 3; ++b) if (ctx->branch[b]) GM_CUDA(cudaStreamSynchronize(ctx->branch[b]));
+  cudaFree(ctx->d_dense_cnt); cudaFree(ctx->d_dense_id); cudaFree(ctx->d_dense_sum); cudaFree(ctx->d_dense_state);
+  ctx->d_dense_cnt = ctx->d_dense_id = nullptr; ctx->d_dense_sum = nullptr; ctx->d_dense_state = nullptr; ctx->dense_cap = 0;
+  const size_t ntiles = (size_t)div_up((long long)range, CPL_TILE) + 2;
+  GM_CUDA(dmalloc(&ctx->d_dense_state, ntiles));
+  GM_CUDA(cudaMemset(ctx->d_dense_state, 0, ntiles * sizeof(unsigned long long)));
+  GM_CUDA(dmalloc(&ctx->d_dense_cnt, range));
+  GM_CUDA(dmalloc(&ctx->d_dense_id, range));
+  GM_CUDA(dmalloc(&ctx->d_dense_sum, 3 * range));
+  GM_CUDA(cudaMemset(ctx->d_dense_cnt, 0, range * sizeof(int)));
+  GM_CUDA(cudaMemset(ctx->d_dense_id, 0, range * sizeof(int)));
+  GM_CUDA(cudaMemset(ctx->d_dense_sum, 0, 3 * range * sizeof(long long)));
+  ctx->dense_cap = range;
+  return GM_OK;
+}
+
+// pcl::VoxelGrid of `pts` (vs->n points, bbox already in vs).  `key_range` = host-side upper bound of the number
+// of lattice cells (0 = unknown).  Small enough: dense tables, no sort (3 launches); else keys -> sort -> heads
+// -> centroids.  Both give the same voxels in the same order with the same fixed-point centroids.
+gm_status voxel_downsample(gm_ctx* ctx, const float4* pts, VoxState* vs, size_t n_cap, int key_bits, size_t key_range, const VoxBuffers& o,
+                           int* sorted_buf) {
   const float leaf_f = (float)ctx->prm.voxelGridLeafSize;
   const float inv = 1.0f / leaf_f;
   int blocks = std::min(div_up((long long)n_cap, 256), ctx->num_sms * 16);
+  gm_status s;
+  unsigned epoch = 0;
+  if (ctx->voxel_mode == 0 && key_range > 0 && key_range <= kDenseMaxKeys) {
+    if ((s = ensure_dense(ctx, key_range)) != GM_OK) return s;
+    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
+    { SegTimer seg_(ctx, SEG_VOX_KEYS);
+      if (pts == ctx->d_cloud_c && ctx->have_normals && !ctx->injected) {
+        // the scan's own compacted cloud: accumulate over its cell-sorted copy with warp-combined atomics
+        GM_LAUNCH(ctx, k_voxel_accumulate_sorted, blocks, 256, ctx->d_sorted_valid, &ctx->d_st->n_crop, vs, inv,
+                  ctx->d_dense_cnt, (unsigned long long*)ctx->d_dense_sum, (int)key_range, &ctx->d_st->error);
+      } else {
+        GM_LAUNCH(ctx, k_voxel_accumulate, blocks, 256, pts, vs, inv, ctx->d_dense_cnt, (unsigned long long*)ctx->d_dense_sum,
+                  (int)key_range, &ctx->d_st->error);
+      } }
+    { SegTimer seg_(ctx, SEG_VOX_REDUCE);
+      GM_LAUNCH(ctx, k_voxel_dense_scan, div_up((long long)key_range, CPL_TILE), CP_BLOCK, ctx->d_dense_cnt, ctx->d_dense_sum, ctx->d_dense_id,
+                (int)key_range, o.vox_key, o.vox_count, o.centroid, ctx->d_dense_state, epoch, vs, &ctx->d_st->error);
+      GM_LAUNCH(ctx, k_voxel_assign, blocks, 256, pts, vs, inv, ctx->d_dense_id, (int)key_range, o.key_pt, o.assign); }
+    *sorted_buf = 0;
+    GM_CHECK_LAUNCHES(ctx);
+    return GM_OK;
+  }
   { SegTimer seg_(ctx, SEG_VOX_KEYS);
     GM_LAUNCH(ctx, k_voxel_keys, blocks, 256, pts, vs, inv, ctx->d_keys[0], ctx->d_vals[0], o.key_pt); }
   int buf = 0;
-  gm_status s;
   { SegTimer seg_(ctx, SEG_VOX_SORT);
     s = radix_sort(ctx, &vs->n, n_cap, key_bits, &buf); }
   if (s != GM_OK) return s;
-  unsigned epoch = 0;
   if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
   { SegTimer seg_(ctx, SEG_VOX_REDUCE);
     GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n_cap, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], o.assign, o.vox_start, o.vox_key,
@@ -689,13 +759,14 @@ gm_status voxel_downsample(gm_ctx* ctx, const float4* pts, VoxState* vs, size_t 
 }
 
 // static upper bound of the voxel key range from the crop box (no host round trip for the bbox)
-int voxel_key_bits(const gm_ctx* ctx, size_t n) {
+int voxel_key_bits(const gm_ctx* ctx, size_t n, size_t* key_range) {
+  *key_range = 0;
   if (ctx->injected) return 32;
   const float inv = 1.0f / (float)ctx->prm.voxelGridLeafSize;
   double b = std::fabs(ctx->prm.boxFilterBound) * (double)inv;
   double div = std::floor(b) - std::floor(-b) + 2.0;
   double total = div * div * div;
-  if (total < 2147483647.0 && (double)n < 2147483647.0) return bits_for((unsigned long long)total);
+  if (total < 2147483647.0 && (double)n < 2147483647.0) { *key_range = (size_t)total; return bits_for((unsigned long long)total); }
   return 32;
 }
 }  // namespace
@@ -707,7 +778,8 @@ gm_status gm_voxel(gm_ctx* ctx) {
   if (n) {
     VoxBuffers o{ctx->d_vkey_pt, ctx->d_assign, ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_centroid};
     int buf = 0;
-    int key_bits = voxel_key_bits(ctx, n);
+    size_t key_range = 0;
+    int key_bits = voxel_key_bits(ctx, n, &key_range);
     if (ctx->have_vox_bbox) {
       const float* b = ctx->vox_bbox;
       GM_LAUNCH(ctx, k_set_bbox, 1, 32, &ctx->d_st->vox, b[0], b[1], b[2], b[3], b[4], b[5]);
@@ -715,9 +787,9 @@ gm_status gm_voxel(gm_ctx* ctx) {
       const float inv = 1.0f / (float)ctx->prm.voxelGridLeafSize;
       double total = 1.0;
       for (int a = 0; a < 3; ++a) total *= (double)((long long)std::floor(b[3 + a] * inv) - (long long)std::floor(b[a] * inv) + 1);
-      if (total < 2147483647.0) key_bits = std::min(key_bits, bits_for((unsigned long long)total));
+      if (total < 2147483647.0) { key_bits = std::min(key_bits, bits_for((unsigned long long)total)); key_range = (size_t)total; }
     }
-    gm_status s = voxel_downsample(ctx, ctx->d_cloud_c, &ctx->d_st->vox, n, key_bits, o, &buf);
+    gm_status s = voxel_downsample(ctx, ctx->d_cloud_c, &ctx->d_st->vox, n, key_bits, key_range, o, &buf);
     if (s != GM_OK) return s;
     if (ctx->have_normals) {
       SegTimer seg_(ctx, SEG_VOX_NN);
@@ -924,7 +996,9 @@ gm_status gm_compress(gm_ctx* ctx) {
             ctx->d_comp_part, ctx->d_comp_mm, ctx->d_counters + 12, ctx->d_comp);
   VoxBuffers o{ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start, ctx->d_res_vox_key, ctx->d_res_vox_count, ctx->d_res_centroid};
   int buf = 0;
-  if ((s = voxel_downsample(ctx, ctx->d_res_pts, ctx->d_res_vs, n, voxel_key_bits(ctx, n), o, &buf)) != GM_OK) return s;
+  size_t res_range = 0;
+  const int res_bits = voxel_key_bits(ctx, n, &res_range);
+  if ((s = voxel_downsample(ctx, ctx->d_res_pts, ctx->d_res_vs, n, res_bits, res_range, o, &buf)) != GM_OK) return s;
   GM_LAUNCH(ctx, k_comp_residual_error, ctx->num_sms * 2, CR_BLOCK, ctx->d_res_pts, ctx->d_res_assign, ctx->d_res_centroid, ctx->d_res_vs,
             ctx->d_comp_part, ctx->d_counters + 13, ctx->d_comp);
   GM_CHECK_LAUNCHES(ctx);

@@ -13,7 +13,7 @@ namespace gm {
 constexpr unsigned long long MAP_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int MAP_COORD_BITS = 21;                 // +-2^20 voxels per axis
 constexpr int MAP_COORD_OFF = 1 << 20;
-constexpr float MAP_FX = 1048576.0f;               // 2^20: exact scaling of a float
+constexpr float MAP_FX = GM_FX20;                  // 2^20: exact scaling of a float (same fixed point as the VoxelGrid centroids)
 
 struct MapState { unsigned long long n_points; int n_voxels; int overflow; int out_of_range; int pad_; };
 

@@ -29,6 +29,8 @@ struct DevState {
   int n_input, n_crop, n_valid, n_cells, nn_oor, error;
   int n_sorted_finite;  // cropped points with finite coordinates (sorted before the NaN tail)
   int tab_cells;        // occupied cells currently recorded in the block table (cleared by the next build)
+  unsigned long long n_candidates;  // distance tests of the radius search (sum over points of their stencil population)
+  unsigned long long n_neighbors;   // of which within the radius
   VoxState vox;         // VoxelGrid of the compacted cloud (vox.n mirrors n_valid)
 };
 
@@ -111,6 +113,15 @@ __device__ __forceinline__ bool d_owned(const OwnedRange& o, const float4 p) {
   return v >= o.lo && v < o.hi;
 }
 
+// Coordinate sums of a voxel are kept in 2^-20 m fixed point (x * 2^20 is exact in float, llrint rounds it to
+// an integer): integer addition is associative, so a centroid does not depend on the order in which its
+// members arrive -- bitwise reproducible with atomics, across map slabs, and in the aggregated map.
+// centroid = float(double(sum) / 2^20 / count).  (pcl::VoxelGrid accumulates in float in the unspecified
+// order of an unstable std::sort; this form is within 1e-6 m of any such order.)
+constexpr float GM_FX20 = 1048576.0f;
+__device__ __forceinline__ long long d_fx20(float v) { return __float2ll_rn(v * GM_FX20); }
+__device__ __forceinline__ float d_centroid_of(long long sum, int count) { return (float)((double)sum / 1048576.0 / (double)count); }
+
 constexpr int CP_BLOCK = 256;
 constexpr int CP_IPT = 4;                      // items per thread where each item is register heavy
 constexpr int CP_TILE = CP_BLOCK * CP_IPT;
@@ -124,6 +135,7 @@ __global__ void k_begin_scan(DevState* st, int n_input) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->n_input = n_input; st->n_crop = 0; st->n_valid = 0; st->n_cells = 0;
     st->nn_oor = 0; st->error = 0; st->n_sorted_finite = 0;  // tab_cells survives: it describes the block table
+    st->n_candidates = 0ull; st->n_neighbors = 0ull;
     d_vox_reset(&st->vox);
   }
 }
@@ -406,7 +418,7 @@ constexpr int NRM_BLOCK = 128;
 __global__ void __launch_bounds__(NRM_BLOCK)
 k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs, const int2* __restrict__ cell_info,
           const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count,
-          float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds, OwnedRange own) {
+          float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds, OwnedRange own, DevState* st) {
   const int n = *n_ptr;
   const int i = blockIdx.x * NRM_BLOCK + threadIdx.x;
   if ((i & ~31) >= n) return;  // warp-uniform: the whole leaf is past the end
@@ -415,12 +427,13 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
   const float4 p = active ? sp[i] : make_float4(qnan, qnan, qnan, 0.f);
   const int orig = __float_as_int(p.w);
   float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
-  int cnt = 0;
+  int cnt = 0, ncand = 0;
   if (active && finite3(p.x, p.y, p.z)) {
     const int cid = cell_id[i];
     const int2* rr = runs + (size_t)cid * GRID_RUNS;
     const int2 info = cell_info[cid];
     const int nr = info.x, total = info.y;
+    ncand = total;
     // accumulators as f32x2 pairs: (xx,xy) (xz,yz) (x,y) (z,count); yy and zz stay scalar.  The count is
     // carried as a float (exact below 2^24 neighbours) so that it shares an instruction with the z sum.
     u64 a01 = 0ull, a24 = 0ull, a67 = 0ull, a8c = 0ull;
@@ -481,7 +494,10 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
   }
   const float lx = warp_min(keep ? p.x : CUDART_INF_F), ly = warp_min(keep ? p.y : CUDART_INF_F), lz = warp_min(keep ? p.z : CUDART_INF_F);
   const float hx = warp_max(keep ? p.x : -CUDART_INF_F), hy = warp_max(keep ? p.y : -CUDART_INF_F), hz = warp_max(keep ? p.z : -CUDART_INF_F);
+  const int wc = __reduce_add_sync(FULL, ncand), wn = __reduce_add_sync(FULL, cnt);  // search statistics (diagnostic)
   if (lane_id() == 0) {
+    atomicAdd(&st->n_candidates, (unsigned long long)wc);
+    atomicAdd(&st->n_neighbors, (unsigned long long)wn);
     leaf_bounds[2 * (size_t)(i >> 5)] = make_float4(lx, ly, lz, 0.f);
     leaf_bounds[2 * (size_t)(i >> 5) + 1] = make_float4(hx, hy, hz, 0.f);
   }
@@ -580,11 +596,11 @@ __global__ void k_bbox(const float4* __restrict__ pts, VoxState* vs) {
 // a4 pcl::VoxelGrid lattice: min_b, div_b, divb_mul and the overflow rule, derived
 // from the bounding box by every block (cheap, avoids a 1-thread kernel); block 0 publishes it.
 // Voxel key per compacted point: ijk = int(floor(p*inv) - float(min_b)); key = ijk . divb_mul
-__global__ void k_voxel_keys(const float4* __restrict__ pts, VoxState* st, float inv,
-                             unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point) {
-  __shared__ int s_minb[3], s_mul[3], s_overflow;
-  const int n = st->n;
+struct VoxLattice { int minb[3]; int mul[3]; int overflow; };
+// thread 0 of every block derives the lattice from the bounding box (cheap, avoids a 1-thread kernel); block 0 publishes it
+__device__ __forceinline__ void d_vox_lattice(VoxState* st, float inv, VoxLattice* out /* shared */) {
   if (threadIdx.x == 0) {
+    const int n = st->n;
     float mn[3], mx[3];
     for (int a = 0; a < 3; ++a) { mn[a] = ordered_to_float(st->bbox_min[a]); mx[a] = ordered_to_float(st->bbox_max[a]); }
     int div[3] = {0, 0, 0}, minb[3] = {0, 0, 0}, overflow = 0;
@@ -598,28 +614,147 @@ __global__ void k_voxel_keys(const float4* __restrict__ pts, VoxState* st, float
         minb[a] = lo; div[a] = hi - lo + 1;
       }
     }
-    for (int a = 0; a < 3; ++a) s_minb[a] = minb[a];
-    s_mul[0] = 1; s_mul[1] = div[0]; s_mul[2] = div[0] * div[1];
-    s_overflow = overflow;
+    for (int a = 0; a < 3; ++a) out->minb[a] = minb[a];
+    out->mul[0] = 1; out->mul[1] = div[0]; out->mul[2] = div[0] * div[1];
+    out->overflow = overflow;
     if (blockIdx.x == 0) {
       st->v_inv = inv;
       st->overflow = overflow;
-      for (int a = 0; a < 3; ++a) { st->min_b[a] = minb[a]; st->div_b[a] = div[a]; st->mul[a] = s_mul[a]; }
+      for (int a = 0; a < 3; ++a) { st->min_b[a] = minb[a]; st->div_b[a] = div[a]; st->mul[a] = out->mul[a]; }
     }
   }
   __syncthreads();
-  const float mb0 = (float)s_minb[0], mb1 = (float)s_minb[1], mb2 = (float)s_minb[2];
-  const int m1 = s_mul[1], m2 = s_mul[2];
-  const bool overflow = s_overflow != 0;
+}
+__device__ __forceinline__ int d_vox_key(const VoxLattice& L, float inv, const float4 p) {
+  int ijk0 = (int)(floorf(p.x * inv) - (float)L.minb[0]);
+  int ijk1 = (int)(floorf(p.y * inv) - (float)L.minb[1]);
+  int ijk2 = (int)(floorf(p.z * inv) - (float)L.minb[2]);
+  return ijk0 + ijk1 * L.mul[1] + ijk2 * L.mul[2];
+}
+
+__global__ void k_voxel_keys(const float4* __restrict__ pts, VoxState* st, float inv,
+                             unsigned* __restrict__ keys, unsigned* __restrict__ idx, int* __restrict__ key_of_point) {
+  __shared__ VoxLattice L;
+  d_vox_lattice(st, inv, &L);
+  const int n = st->n;
+  const bool overflow = L.overflow != 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
-    int ijk0 = (int)(floorf(p.x * inv) - mb0);
-    int ijk1 = (int)(floorf(p.y * inv) - mb1);
-    int ijk2 = (int)(floorf(p.z * inv) - mb2);
-    int key = overflow ? i : (ijk0 + ijk1 * m1 + ijk2 * m2);
+    int key = overflow ? i : d_vox_key(L, inv, p);
     keys[i] = (unsigned)key;
     idx[i] = (unsigned)i;
     key_of_point[i] = key;
+  }
+}
+
+// ---- VoxelGrid without a sort ---------------------------------------------------------------------
+// When the key range is known (on the host) to fit the dense tables, a voxel is just the table entry of its
+// key: one pass adds every point to its entry (count + fixed-point sums, integer atomics), one look-back
+// compaction over the table numbers the occupied keys in ascending order (= the voxel order of
+// pcl::VoxelGrid), emits key / count / centroid, remembers the voxel id per key and zeroes the entries it
+// consumed (the tables clean themselves), and one pass maps every point to its voxel id.  3 launches and
+// ~60 B of traffic per point instead of the 12 launches / 132 B of the sort-based path below.
+__global__ void k_voxel_accumulate(const float4* __restrict__ pts, VoxState* st, float inv,
+                                   int* __restrict__ dcnt, unsigned long long* __restrict__ dsum, int capacity, int* err) {
+  __shared__ VoxLattice L;
+  d_vox_lattice(st, inv, &L);
+  const int n = st->n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const int key = d_vox_key(L, inv, p);
+    if ((unsigned)key >= (unsigned)capacity) { atomicExch(err, 4); continue; }  // cannot happen: the host bound covers the crop box
+    atomicAdd(&dcnt[key], 1);
+    atomicAdd(&dsum[3 * (size_t)key + 0], (unsigned long long)d_fx20(p.x));
+    atomicAdd(&dsum[3 * (size_t)key + 1], (unsigned long long)d_fx20(p.y));
+    atomicAdd(&dsum[3 * (size_t)key + 2], (unsigned long long)d_fx20(p.z));
+  }
+}
+
+// The same accumulation over the CELL-SORTED copy of the cloud (dropped points blanked to NaN, .w = cropped
+// index): the sums do not depend on the order, and in this order neighbouring lanes of a warp mostly fall into
+// the same voxel.  Runs of equal keys in consecutive lanes are combined with a segmented warp scan (head flags
+// from one ballot, 5 shuffle steps) and only the last lane of a run issues the atomics: ~5x fewer than one set
+// per point.  (A match.any + redux.sync grouping of ALL equal keys of the warp was measured no faster than plain
+// per-point atomics: 42 us, 425 instructions per warp iteration — the per-group redux loops diverge.)
+__global__ void __launch_bounds__(256)
+k_voxel_accumulate_sorted(const float4* __restrict__ sv, const int* __restrict__ n_ptr, VoxState* st,
+                          float inv, int* __restrict__ dcnt, unsigned long long* __restrict__ dsum, int capacity, int* err) {
+  __shared__ VoxLattice L;
+  d_vox_lattice(st, inv, &L);
+  const int n = *n_ptr;
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // block-uniform trip count
+    const int i = base + threadIdx.x;
+    int key = -1, c = 0;
+    long long fx = 0, fy = 0, fz = 0;
+    if (i < n) {
+      const float4 p = sv[i];
+      if (p.x == p.x) {  // not blanked
+        key = d_vox_key(L, inv, p);
+        if ((unsigned)key >= (unsigned)capacity) { atomicExch(err, 4); key = -1; }
+        else { c = 1; fx = d_fx20(p.x); fy = d_fx20(p.y); fz = d_fx20(p.z); }
+      }
+    }
+    const int prev = __shfl_up_sync(FULL, key, 1);
+    const unsigned heads = __ballot_sync(FULL, lane == 0 || key != prev);
+    const int start = 31 - __clz(heads & (0xFFFFFFFFu >> (31 - lane)));  // first lane of this lane's run
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int tc = __shfl_up_sync(FULL, c, d);
+      const long long tx = __shfl_up_sync(FULL, fx, d), ty = __shfl_up_sync(FULL, fy, d), tz = __shfl_up_sync(FULL, fz, d);
+      if (lane - d >= start) { c += tc; fx += tx; fy += ty; fz += tz; }
+    }
+    const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    if (last && key >= 0) {
+      atomicAdd(&dcnt[key], c);
+      atomicAdd(&dsum[3 * (size_t)key + 0], (unsigned long long)fx);
+      atomicAdd(&dsum[3 * (size_t)key + 1], (unsigned long long)fy);
+      atomicAdd(&dsum[3 * (size_t)key + 2], (unsigned long long)fz);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CP_BLOCK)
+k_voxel_dense_scan(int* __restrict__ dcnt, long long* __restrict__ dsum, int* __restrict__ did, int range,
+                   int* __restrict__ vox_key, int* __restrict__ vox_count, float4* __restrict__ centroids,
+                   unsigned long long* state, unsigned epoch, VoxState* st, int* err) {
+  __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
+  const int tile = blockIdx.x, base = tile * CPL_TILE;
+  bool f[CPL_IPT];
+  int c[CPL_IPT];
+#pragma unroll
+  for (int j = 0; j < CPL_IPT; ++j) {
+    const int k = base + j * CP_BLOCK + threadIdx.x;
+    c[j] = (k < range) ? dcnt[k] : 0;
+    f[j] = c[j] > 0;
+  }
+  unsigned ranks[CPL_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, err, sm);
+#pragma unroll
+  for (int j = 0; j < CPL_IPT; ++j) {
+    if (!f[j]) continue;
+    const int k = base + j * CP_BLOCK + threadIdx.x;
+    const int v = (int)ranks[j];
+    long long* sp = dsum + 3 * (size_t)k;
+    const long long sx = sp[0], sy = sp[1], sz = sp[2];
+    vox_key[v] = k; vox_count[v] = c[j];
+    centroids[v] = make_float4(d_centroid_of(sx, c[j]), d_centroid_of(sy, c[j]), d_centroid_of(sz, c[j]), 1.0f);
+    did[k] = v;
+    dcnt[k] = 0; sp[0] = 0; sp[1] = 0; sp[2] = 0;  // self-cleaning
+  }
+  if (tile == (int)gridDim.x - 1 && threadIdx.x == 0) st->n_voxels = (int)total;
+}
+
+// point -> voxel id (and its key, recomputed from the point: cheaper than carrying it through the sorted pass)
+__global__ void k_voxel_assign(const float4* __restrict__ pts, VoxState* st, float inv, const int* __restrict__ did, int capacity,
+                               int* __restrict__ key_of_point, int* __restrict__ assign) {
+  __shared__ VoxLattice L;
+  d_vox_lattice(st, inv, &L);
+  const int n = st->n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int key = d_vox_key(L, inv, pts[i]);
+    key_of_point[i] = key;
+    assign[i] = ((unsigned)key < (unsigned)capacity) ? did[key] : -1;
   }
 }
 
@@ -658,11 +793,8 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
   if (base + CPL_TILE >= n && threadIdx.x == 0) st->n_voxels = (int)total;
 }
 
-// Centroid per voxel: float sum over the members in ascending original index (stable sort order),
-// divided by float(count)  (bit-reproducible, matches the oracle's canonical order).
-// One warp per voxel: the 32 lanes gather 32 member points at once (the gathers are the cost), then
-// the sum is formed in member order from lane-broadcast shuffles, so the float result is the same
-// sequential sum a single thread would produce.
+// Centroid per voxel (sort-based path): fixed-point sums of the members (same order-independent definition as
+// the dense path above), one warp per voxel, lanes stride over the members, shuffle tree for the totals.
 constexpr int VC_BLOCK = 128;
 __global__ void __launch_bounds__(VC_BLOCK)
 k_voxel_centroids(const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
@@ -673,22 +805,20 @@ k_voxel_centroids(const unsigned* __restrict__ sidx, const float4* __restrict__ 
   const int warps_total = (gridDim.x * VC_BLOCK) >> 5;
   for (int j = (blockIdx.x * VC_BLOCK + threadIdx.x) >> 5; j < V; j += warps_total) {
     const int s = vox_start[j], e = (j + 1 < V) ? vox_start[j + 1] : n;
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (int base = s; base < e; base += 32) {
-      const int t = base + lane;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < e) q = pts[sidx[t]];
-      const int cnt = min(32, e - base);
-      for (int l = 0; l < cnt; ++l) {
-        sx += __shfl_sync(FULL, q.x, l);
-        sy += __shfl_sync(FULL, q.y, l);
-        sz += __shfl_sync(FULL, q.z, l);
-      }
+    long long sx = 0, sy = 0, sz = 0;
+    for (int t = s + lane; t < e; t += 32) {
+      const float4 q = pts[sidx[t]];
+      sx += d_fx20(q.x); sy += d_fx20(q.y); sz += d_fx20(q.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_down_sync(FULL, sx, o); sy += __shfl_down_sync(FULL, sy, o); sz += __shfl_down_sync(FULL, sz, o);
     }
     if (lane == 0) {
-      float c = (float)(e - s);
-      centroids[j] = make_float4(sx / c, sy / c, sz / c, 1.0f);
-      vox_count[j] = e - s;
+      const int c = e - s;
+      // overflow rule (A.5): the output is the input cloud unchanged, not a rounded copy of it
+      centroids[j] = st->overflow ? pts[sidx[s]] : make_float4(d_centroid_of(sx, c), d_centroid_of(sy, c), d_centroid_of(sz, c), 1.0f);
+      vox_count[j] = c;
     }
   }
 }

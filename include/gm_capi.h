@@ -156,6 +156,10 @@ GM_API gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream);
  * scan whenever gm_normals produced one (identical counts, hypotheses whose inlier band provably
  * misses a 32-point tile are skipped for it); 1 = always the brute-force FP32 kernels. */
 GM_API gm_status gm_set_count_mode(gm_ctx* ctx, int32_t mode);
+/* VoxelGrid strategy of gm_voxel / gm_compress: 0 (default) = sort-free dense tables whenever the number of lattice
+ * cells of the crop box (or of the box given with gm_set_voxel_bbox) is at most 2^23, else sort-based; 1 = always
+ * sort-based.  Same voxels, order, counts and centroids either way. */
+GM_API gm_status gm_set_voxel_mode(gm_ctx* ctx, int32_t mode);
 /* ---- map slabs (one large map split along an axis over several contexts / GPUs) ----
  * gm_set_grid_box: build the neighbour grid over this box instead of the whole crop cube (the region
  *   the slab occupies, halo included; points outside it stay correct, only slower).  NULL,NULL = cube.
@@ -246,6 +250,9 @@ GM_API gm_status gm_get_counts(gm_ctx* ctx, gm_counts* out);
 GM_API gm_status gm_download_cloud(gm_ctx* ctx, int32_t which, float* out_xyzw, size_t capacity_points);
 /* normals: which = 0 pre-compaction (M, NaN rows included), 1 compacted (M'); n x 8 floats */
 GM_API gm_status gm_download_normals(gm_ctx* ctx, int32_t which, float* out8, size_t capacity_points);
+/* work of the radius search of the last gm_normals: distance tests executed (population of the 27-cell stencil
+ * summed over the points) and how many of them were within the radius (diagnostic; feeds bench.py's roofline) */
+GM_API gm_status gm_get_search_stats(gm_ctx* ctx, int64_t* candidates, int64_t* neighbors);
 /* neighbour counts of the radius search per cropped point (M int32) */
 GM_API gm_status gm_download_neighbor_counts(gm_ctx* ctx, int32_t* out, size_t capacity_points);
 /* pre-compaction index -> compacted index or -1 (M int32) */

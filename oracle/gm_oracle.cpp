@@ -967,6 +967,26 @@ GMO_API int32_t gmo_polyline(const float* pts4, const float* normals8, const uin
 // ints6   : n_points, n_plane, n_cyl, n_residual, n_residual_voxels, (unused)
 // floats32: plane_u[3], plane_v[3], plane_bounds[4], plane_rms, cyl_t_range[2], cyl_rms, residual_rms, total_rms
 // res_centroids4: capacity n x 4
+// Order-independent centroids of a voxel assignment (the form the CUDA path computes, csrc/gm_stages.cuh):
+// per voxel the sums of llrint(coord * 2^20) and centroid = float(double(sum) / 2^20 / count).  pcl::VoxelGrid
+// itself accumulates in float in the unspecified order of an unstable std::sort (gmo_voxel restates that with the
+// stable order); the two agree within ~1e-6 m, which is the tolerance the tests state.
+GMO_API void gmo_voxel_fx_centroids(const float* pts4, int64_t n, const int32_t* assign, int64_t V, float* centroids4) {
+  const P4* p = (const P4*)pts4;
+  std::vector<int64_t> sum((size_t)std::max<int64_t>(V, 1) * 3, 0), cnt((size_t)std::max<int64_t>(V, 1), 0);
+  for (int64_t i = 0; i < n; ++i) {
+    const size_t v = (size_t)assign[i];
+    sum[3 * v] += (int64_t)std::llrint((double)(p[i].x * 1048576.0f));
+    sum[3 * v + 1] += (int64_t)std::llrint((double)(p[i].y * 1048576.0f));
+    sum[3 * v + 2] += (int64_t)std::llrint((double)(p[i].z * 1048576.0f));
+    cnt[v] += 1;
+  }
+  for (int64_t v = 0; v < V; ++v) {
+    for (int a = 0; a < 3; ++a) centroids4[4 * v + a] = (float)((double)sum[3 * (size_t)v + a] / 1048576.0 / (double)cnt[(size_t)v]);
+    centroids4[4 * v + 3] = 1.0f;
+  }
+}
+
 GMO_API void gmo_compress(const float* pts4, const uint8_t* labels, int64_t n, const float* plane4, const float* cyl7,
                           double tau, double leaf, int32_t* ints6, float* floats32, float* res_centroids4) {
   const P4* p = (const P4*)pts4;
@@ -1001,6 +1021,7 @@ GMO_API void gmo_compress(const float* pts4, const uint8_t* labels, int64_t n, c
   std::vector<float> cen((size_t)std::max<int64_t>(nr, 1) * 4);
   int32_t status = 0;
   int64_t V = gmo_voxel(res.data(), nr, leaf, nullptr, assign.data(), cen.data(), nullptr, nullptr, nullptr, &status);
+  if (status == 0 && V > 0) gmo_voxel_fx_centroids(res.data(), nr, assign.data(), V, cen.data());  // the order-independent form
   double sqr = 0;
   for (int64_t i = 0; i < nr; ++i) {
     const float* c = &cen[(size_t)assign[(size_t)i] * 4];

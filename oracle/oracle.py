@@ -95,8 +95,13 @@ def voxel(pts, leaf):
     status = C.c_int32(0)
     V = lib().gmo_voxel(_p(pts), C.c_int64(n), C.c_double(leaf), _p(keys), _p(assign), _p(cen), _p(vkeys), _p(vcnt),
                         _p(grid6), C.byref(status))
-    return {"V": int(V), "keys": keys, "assign": assign, "centroids": cen[:V].copy(), "voxel_keys": vkeys[:V].copy(),
-            "voxel_counts": vcnt[:V].copy(), "grid6": grid6, "status": status.value}
+    cen_fx = cen[:V].copy()
+    if status.value == 0 and V > 0:
+        lib().gmo_voxel_fx_centroids(_p(pts), C.c_int64(n), _p(assign), C.c_int64(V), _p(cen_fx))
+    # "centroids": pcl::VoxelGrid's float accumulation (stable order); "centroids_fx": the order-independent
+    # fixed-point form the CUDA path computes (equal within ~1e-6 m)
+    return {"V": int(V), "keys": keys, "assign": assign, "centroids": cen[:V].copy(), "centroids_fx": cen_fx,
+            "voxel_keys": vkeys[:V].copy(), "voxel_counts": vcnt[:V].copy(), "grid6": grid6, "status": status.value}
 
 
 def nn1(query, pts, nthreads=0):

@@ -23,6 +23,14 @@ def _ctx(n, **kw):
     return capi.Context(capi.default_params(**kw), max_points=max(n, 1), max_hypotheses=4096)
 
 
+def _centroids_match(got, ref):
+    """VoxelGrid centroids: bit-exact against the order-independent fixed-point restatement (what the CUDA path
+    defines: sums of llrint(coord * 2^20)), and within 1e-6 m + 1e-6 relative of pcl::VoxelGrid's float
+    accumulation (whose own summation order is unspecified: unstable std::sort)."""
+    assert np.array_equal(got.view(np.uint32), ref["centroids_fx"].view(np.uint32))
+    assert np.abs(got[:, :3] - ref["centroids"][:, :3]).max() <= 1e-6 * (1.0 + np.abs(ref["centroids"][:, :3]).max())
+
+
 def _scan_with_junk(n=60_000, seed=11):
     pts = synth.curved_tunnel(n, seed=seed, outlier_frac=0.02)
     g = np.random.Generator(np.random.Philox(seed + 1))
@@ -161,8 +169,7 @@ def test_voxel_bit_exact(leaf, radius):
     assert np.array_equal(assign, ref["assign"])      # point -> voxel rank: bit-exact
     assert np.array_equal(vox["keys"], ref["voxel_keys"])
     assert np.array_equal(vox["counts"], ref["voxel_counts"])
-    # centroids: same summation order as the oracle's canonical (stable) order -> bit-exact
-    assert np.array_equal(vox["centroids"].view(np.uint32), ref["centroids"].view(np.uint32))
+    _centroids_match(vox["centroids"], ref)
     # 1-NN over the PRE-compaction cloud (quirk B.3), exact, ties -> lowest index
     finite = np.isfinite(cropped[:, :3]).all(1)
     search = cropped.copy()
@@ -172,6 +179,42 @@ def test_voxel_bit_exact(leaf, radius):
     inr = ref_idx < c.n_valid
     assert np.array_equal(vox["nn_normal"][inr].view(np.uint32), normals_c[ref_idx[inr]].view(np.uint32))
     assert c.nn_out_of_range == int((~inr).sum())
+
+
+@pytest.mark.parametrize("leaf,bound", [(0.1, 5.0), (0.37, 5.0), (0.05, 3.0)])
+def test_voxel_dense_tables_equal_sort_path(leaf, bound):
+    """gm_voxel without a sort (dense tables, default when the lattice of the crop box fits) and with the
+    radix sort (mode 1) give identical keys, assignments, voxel order, counts and centroids; twice in a row on
+    the same context (the tables clean themselves), and through the compression stage."""
+    pts = _scan_with_junk(50_000, seed=23)
+    out = {}
+    with _ctx(len(pts), neighborRadius=0.15, voxelGridLeafSize=leaf, boxFilterBound=bound) as ctx:
+        for mode in (0, 1, 0):
+            ctx.set_voxel_mode(mode)
+            ctx.upload_scan(pts)
+            ctx.crop()
+            ctx.normals()
+            nv = ctx.counts().n_valid
+            ctx.upload_scan(pts)
+            ctx.process_scan(synth.sample_indices(nv, 128, 3, seed=3), synth.sample_indices(nv, 128, 2, seed=4))
+            ctx.compress()
+            keys, assign, st = ctx.download_voxel_assignment()
+            got = (keys, assign, ctx.download_voxels(), ctx.voxel_grid(), ctx.download_compressed(), ctx.counts())
+            assert st == capi.GM_OK and got[5].device_error == 0
+            if mode in out:
+                prev = out[mode]
+                assert np.array_equal(prev[0], got[0]) and prev[4] == got[4]          # second dense run == first
+            out[mode] = got
+        cloud_c = ctx.download_cloud(1)
+    a, b = out[0], out[1]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    for k in ("keys", "counts", "nn_index"):
+        assert np.array_equal(a[2][k], b[2][k]), k
+    assert np.array_equal(a[2]["centroids"].view(np.uint32), b[2]["centroids"].view(np.uint32))
+    assert a[4] == b[4]                                                                   # compressed blob byte-identical
+    ref = O.voxel(cloud_c, leaf)
+    assert np.array_equal(a[0], ref["keys"]) and np.array_equal(a[1], ref["assign"])
+    _centroids_match(a[2]["centroids"], ref)
 
 
 def test_voxel_fixed_nn_mode_indexes_compacted_cloud():
@@ -205,7 +248,7 @@ def test_voxel_lattice_known_keys_and_overflow_rule():
     ref = O.voxel(pts, 0.25)
     assert np.array_equal(keys, ref["keys"]) and np.array_equal(assign, ref["assign"])
     assert len(np.unique(keys)) == 125 and ref["V"] == 125
-    assert np.array_equal(vox["centroids"].view(np.uint32), ref["centroids"].view(np.uint32))
+    _centroids_match(vox["centroids"], ref)
     # overflow rule: leaf so small that dx*dy*dz > INT32_MAX -> cloud returned unchanged
     big = synth.straight_cylinder(5000, seed=9)
     with _ctx(len(big), voxelGridLeafSize=0.001) as ctx:

@@ -881,7 +881,17 @@ k_voxel_nn(const float4* __restrict__ centroids, const float4* __restrict__ sp,
         const BlockEntry e = tab[ckey >> 6];
         if ((e.mask >> (ckey & 63u)) & 1ull) {
           const int jc = e.first + __popcll(e.mask & ((1ull << (ckey & 63u)) - 1ull));
-          if (lane < cell_info[jc].x) d_nn_scan(sp, valid_map, mode, runs[(size_t)jc * GRID_RUNS + lane], c, best, bi);
+          // 16 runs at a time, each split in two halves over lanes l and l+16: twice the active lanes and half
+          // the longest sequential scan (the (d2, index) minimum does not depend on how the candidates are split)
+          const int nr = cell_info[jc].x;
+          for (int r0 = 0; r0 < nr; r0 += 16) {
+            const int r = r0 + (lane & 15);
+            if (r < nr) {
+              const int2 run = runs[(size_t)jc * GRID_RUNS + r];
+              const int mid = run.x + ((run.y - run.x + 1) >> 1);
+              d_nn_scan(sp, valid_map, mode, (lane < 16) ? make_int2(run.x, mid) : make_int2(mid, run.y), c, best, bi);
+            }
+          }
         } else if (lane < 9) {
           d_nn_scan_row(sp, valid_map, mode, g, tab, ucell_start, U, nf, cx - 1, cx + 1, cy + (lane % 3) - 1, cz + (lane / 3) - 1, c, best, bi);
         }

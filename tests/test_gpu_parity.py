@@ -131,6 +131,47 @@ def test_normals_small_exact_brute_force():
     assert np.quantile(_angle(got[ok, :3].astype(np.float64), ref[ok, :3].astype(np.float64)), 0.99) < 1e-2
 
 
+@pytest.mark.parametrize("bound,radius,box", [
+    (5.0, 0.5, None),                         # the launch-file radius: a 20-cell grid, 3 block bits per axis
+    (2.6, 2.5, None),                         # radius ~ the whole cloud: 2-3 cells per axis
+    (50.0, 0.03, None),                       # crop cube too large for 4-cell blocks of r: the cell grows, still exact
+    (5.0, 0.11, ((-5.0, -3.0, -1.7), (5.0, 3.0, 0.2))),    # flat grid box: unequal block bits (Morton + stacked high bits)
+    (5.0, 0.11, ((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5))),    # box much smaller than the data: border cells take the rest
+    (40.0, 0.2, ((-30.0, -2.0, -2.0), (30.0, 2.0, 2.0))),  # long thin box
+])
+def test_neighbour_grid_shapes_keep_exact_neighbour_sets(bound, radius, box):
+    """Whatever the neighbour grid looks like (cube, flat, tiny, enlarged cells, clamped outliers), the radius
+    search returns the exact FLANN neighbour sets: counts bit-exact, 1-NN of the voxel centroids exact, voxel
+    grid and compaction unchanged."""
+    pts = _scan_with_junk(25_000, seed=88)
+    if bound > 10:
+        pts = pts.copy()
+        pts[::7, 0] *= 5.0                    # stretch part of the cloud along x so that the larger boxes hold data
+    cropped, _ = O.crop(pts, bound, True)
+    ref, ref_cnt, _ = O.normals(cropped, radius, mode=0, order=0)
+    cloud_c_ref, nrm_ref, _ = O.compact(cropped, ref)
+    with _ctx(len(pts), boxFilterBound=bound, neighborRadius=radius, voxelGridLeafSize=0.2, nn_index_mode=1) as ctx:
+        if box is not None:
+            ctx.set_grid_box(box[0], box[1])
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        ctx.voxel()
+        cnt = ctx.download_neighbor_counts()
+        cloud_c = ctx.download_cloud(1)
+        vox = ctx.download_voxels()
+        cand, nbr = ctx.search_stats()
+        assert ctx.counts().device_error == 0
+    assert np.array_equal(cnt, ref_cnt)                                        # neighbour counts: bit-exact
+    assert np.array_equal(cloud_c.view(np.uint32), cloud_c_ref.view(np.uint32))
+    assert nbr == int(ref_cnt.astype(np.int64).sum()) and cand >= nbr
+    refv = O.voxel(cloud_c, 0.2)
+    assert np.array_equal(vox["keys"], refv["voxel_keys"])
+    _centroids_match(vox["centroids"], refv)
+    ref_idx, _ = O.nn1(vox["centroids"], cloud_c)
+    assert np.array_equal(vox["nn_index"], ref_idx)                            # exact nearest neighbour, ties -> lowest index
+
+
 def test_normals_isolated_points_become_nan_and_are_dropped():
     pts = np.array([[0, 0, 0, 1], [0.01, 0, 0, 1], [3, 3, 3, 1], [0, 0.01, 0, 1], [0.01, 0.01, 0.002, 1]], np.float32)
     with _ctx(8, neighborRadius=0.05) as ctx:

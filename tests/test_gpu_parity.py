@@ -958,6 +958,33 @@ def test_voxel_map_capacity_and_range_are_reported():
         assert fine.stats()[:3] == (0, 0, 0)
 
 
+# ---- the C++ mirror of the reference seam (host/): the ROS-free node on one synthetic scan ---------------------
+def test_cpp_host_node_runs_the_reference_callback_flow():
+    """geometric_mapping_node (C++ shim: chopCloud / getNormals / rvizNormals / getLocalFrame / rvizEigens on top of
+    the C-ABI, control flow of cloud_cb) on a straight cylinder along x: the printed center axis is the cylinder
+    axis (the analytic known answer of src/tunnel_processing.cpp:91,139-143) and the publish lines are gated by
+    the display parameters of the launch file."""
+    import os
+    import subprocess
+
+    from geometric_mapping_b200 import build as gm_build
+
+    exe = gm_build.build_host()
+    assert os.path.exists(exe)
+    res = subprocess.run([exe, "--synthetic", "60000", "--set", "neighborRadius=0.15", "--set", "displayNormals=false"],
+                         capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    out = res.stdout.splitlines()
+    i = out.index("Center Axis is:")
+    axis = np.array([float(v) for v in out[i + 1].split()])
+    assert abs(abs(axis[0]) - 1.0) < 1e-3 and np.abs(axis[1:]).max() < 3e-2
+    j = out.index("Eigenvalues are:")
+    vals = np.array([float(v) for v in out[j + 1].split()])
+    assert vals[0] < 0.02 * vals[1] and vals[1] <= vals[2]                      # ascending, smallest ~ 0 for a cylinder
+    assert any(l.startswith("publish cloudOutput:") for l in out) and any(l.startswith("publish eigenBasisOutput: 3 markers") for l in out)
+    assert not any(l.startswith("publish normalsOutput") for l in out)
+
+
 # ---- I/O seams ---------------------------------------------------------------------------------------
 def test_pointcloud2_decode_velodyne_layout():
     """sensor_msgs/PointCloud2 as the Velodyne driver publishes it: point_step 22 (x,y,z,intensity f32 +

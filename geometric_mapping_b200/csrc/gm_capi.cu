@@ -766,8 +766,17 @@ int voxel_key_bits(const gm_ctx* ctx, size_t n, size_t* key_range) {
   double b = std::fabs(ctx->prm.boxFilterBound) * (double)inv;
   double div = std::floor(b) - std::floor(-b) + 2.0;
   double total = div * div * div;
-  if (total < 2147483647.0 && (double)n < 2147483647.0) { *key_range = (size_t)total; return bits_for((unsigned long long)total); }
-  return 32;
+  int bits = 32;
+  if (total < 2147483647.0 && (double)n < 2147483647.0) { *key_range = (size_t)total; bits = bits_for((unsigned long long)total); }
+  if (ctx->have_vox_bbox) {
+    // a caller-supplied box (gm_set_voxel_bbox) holds the whole cloud, hence every sub-cloud: its lattice bounds the key range
+    // (same float expressions as k_voxel_keys)
+    const float* b = ctx->vox_bbox;
+    double t2 = 1.0;
+    for (int a = 0; a < 3; ++a) t2 *= (double)((long long)std::floor(b[3 + a] * inv) - (long long)std::floor(b[a] * inv) + 1);
+    if (t2 >= 1.0 && t2 < 2147483647.0 && (*key_range == 0 || t2 < (double)*key_range)) { *key_range = (size_t)t2; bits = std::min(bits, bits_for((unsigned long long)t2)); }
+  }
+  return bits;
 }
 }  // namespace
 
@@ -783,11 +792,6 @@ gm_status gm_voxel(gm_ctx* ctx) {
     if (ctx->have_vox_bbox) {
       const float* b = ctx->vox_bbox;
       GM_LAUNCH(ctx, k_set_bbox, 1, 32, &ctx->d_st->vox, b[0], b[1], b[2], b[3], b[4], b[5]);
-      // exact key range of the given lattice (same float expressions as k_voxel_keys)
-      const float inv = 1.0f / (float)ctx->prm.voxelGridLeafSize;
-      double total = 1.0;
-      for (int a = 0; a < 3; ++a) total *= (double)((long long)std::floor(b[3 + a] * inv) - (long long)std::floor(b[a] * inv) + 1);
-      if (total < 2147483647.0) { key_bits = std::min(key_bits, bits_for((unsigned long long)total)); key_range = (size_t)total; }
     }
     gm_status s = voxel_downsample(ctx, ctx->d_cloud_c, &ctx->d_st->vox, n, key_bits, key_range, o, &buf);
     if (s != GM_OK) return s;

@@ -384,6 +384,46 @@ def main():
     ms4 = max_over_ranks(e0.elapsed_time(e1)) / steps4
     h4096 = {"hypotheses": H4, "ms_per_step": ms4, "points_per_s": world * n / (ms4 * 1e-3), "steps": steps4,
              "note": "same workload with 2048 plane + 2048 cylinder hypotheses per scan (north-star target count)"}
+    # ---- configs[3]: a batch of 64 frames x 200k points split by frame over the ranks (no collective) ----
+    from geometric_mapping_b200 import distributed as gmd_
+    F_TOTAL, F_PTS = 64, 200_000
+    my_frames = gmd_.frames_of_rank(F_TOTAL, rank, world)
+    fr_dev, fr_smp = [], []
+    for f in my_frames:
+        fp = torch.from_numpy(synth.curved_tunnel(F_PTS, seed=100 + f, advance=1.0 * f)).to(dev)
+        ctx.set_scan_device(fp.data_ptr(), F_PTS)
+        ctx.crop()
+        ctx.normals()
+        nvf = ctx.counts().n_valid
+        fr_dev.append(fp)
+        fr_smp.append((synth.sample_indices(nvf, Hp, 3, seed=300 + f), synth.sample_indices(nvf, Hc, 2, seed=400 + f)))
+
+    def frames_pass():
+        for j in range(len(my_frames)):
+            cx = tctx[j % NFLIGHT]
+            cx.set_scan_device(fr_dev[j].data_ptr(), F_PTS)
+            cx.process_scan(fr_smp[j][0], fr_smp[j][1])
+
+    frames_pass()
+    barrier()
+    for st_ in tstreams[1:]:
+        st_.wait_stream(stream)
+    e0.record(stream)
+    for st_ in tstreams[1:]:
+        st_.wait_event(e0)
+    FREPS = 3
+    for _ in range(FREPS):
+        frames_pass()
+    for st_ in tstreams[1:]:
+        stream.wait_stream(st_)
+    e1.record(stream)
+    barrier()
+    fms = max_over_ranks(e0.elapsed_time(e1)) / FREPS
+    frames_c3 = {"frames": F_TOTAL, "points_per_frame": F_PTS, "ms_per_batch": fms, "frames_per_s": F_TOTAL / (fms * 1e-3),
+                 "points_per_s": F_TOTAL * F_PTS / (fms * 1e-3),
+                 "mode": f"frame f -> rank f mod {world}, {NFLIGHT} frames in flight per rank, full per-frame output incl. the polyline; "
+                         f"{Hp}+{Hc} hypotheses per frame"}
+    del fr_dev
     for cx in tctx[1:]:
         cx.close()
 
@@ -666,6 +706,7 @@ def main():
             "roofline_families": families,
             "segments_ms_per_step": seg_ms,
             "h4096": h4096,
+            "frames_c3": frames_c3,
             "ransac": ransac,
             "compress": compress,
             "map_slabs": map_leg,

@@ -550,11 +550,10 @@ def main():
     nv = ctx.counts().n_valid
     sp, sc = synth.sample_indices(nv, Hs // 2, 3, seed=3), synth.sample_indices(nv, Hs - Hs // 2, 2, seed=4)
     from geometric_mapping_b200 import distributed as gmd
-    key_t = torch.zeros(1, dtype=torch.int64, device=dev)  # torch-owned buffer for the 8-byte collective
+    key_t = torch.zeros(2, dtype=torch.int64, device=dev)  # torch-owned buffer for the 16-byte collective (both keys)
 
     def ransac_step():
-        for kind, smp in ((0, sp), (1, sc)):
-            gmd.sharded_ransac(ctx, kind, smp, rank, world, key_t)
+        gmd.sharded_ransac_pair(ctx, sp, sc, rank, world, key_t)
 
     for _ in range(3):
         ransac_step()
@@ -567,7 +566,8 @@ def main():
     rms = max_over_ranks(e0.elapsed_time(e1))
     mp, mc = ctx.model(0), ctx.model(1)
     ransac = {"hyp_pts_per_sec": Hs * nv * a.steps / (rms * 1e-3), "H": Hs, "points": nv, "ms_per_round": rms / a.steps,
-              "mode": "hypotheses sharded across ranks, NCCL max-allreduce of packed (count,id), refit on every rank",
+              "mode": "hypotheses sharded across ranks, plane and cylinder side by side, ONE NCCL max-allreduce of both packed (count,id) "
+                      "keys, refit on every rank",
               "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
     if a.shard_hyp_large > 0:
         Hl = a.shard_hyp_large

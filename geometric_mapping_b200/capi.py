@@ -123,7 +123,8 @@ SYMBOLS = [
     "gm_inject_compacted", "gm_markers_eigen", "gm_markers_normals", "gm_fetch_async", "gm_profile_enable",
     "gm_profile_num_segments", "gm_profile_segment_name", "gm_profile_read", "gm_compress", "gm_get_compression",
     "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode", "gm_set_grid_box", "gm_set_owned_range", "gm_get_voxel_bbox", "gm_set_voxel_bbox",
-    "gm_get_search_stats", "gm_set_voxel_mode", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
+    "gm_get_search_stats", "gm_set_voxel_mode", "gm_ransac_pair", "gm_ransac_select_pair", "gm_ransac_export_keys",
+    "gm_ransac_import_keys", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
     "gm_map_load", "gm_map_leaf",
 ]
 
@@ -199,6 +200,10 @@ def _lib():
         "gm_set_voxel_bbox": (i32, [vp, vp, vp]),
         "gm_get_search_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "gm_set_voxel_mode": (i32, [vp, i32]),
+        "gm_ransac_pair": (i32, [vp, vp, i32, i32, i32, vp, i32, i32, i32]),
+        "gm_ransac_select_pair": (i32, [vp]),
+        "gm_ransac_export_keys": (i32, [vp, vp]),
+        "gm_ransac_import_keys": (i32, [vp, vp]),
         "gm_map_create": (i32, [C.c_double, sz, C.POINTER(vp)]),
         "gm_map_destroy": (None, [vp]),
         "gm_map_clear": (i32, [vp]),
@@ -390,6 +395,23 @@ class Context:
 
     def ransac_import_key(self, kind: int, src_device_ptr: int):
         self._ck(_lib().gm_ransac_import_key(self._h, kind, C.c_void_p(src_device_ptr)), "gm_ransac_import_key")
+
+    def ransac_pair(self, plane_samples, cyl_samples, p_range=None, c_range=None):
+        """gm_ransac for both primitives side by side; ranges = (begin, end) hypothesis shards (default: all)."""
+        ps = np.ascontiguousarray(plane_samples, dtype=np.int32)
+        cs = np.ascontiguousarray(cyl_samples, dtype=np.int32)
+        pb, pe = p_range if p_range is not None else (0, ps.shape[0])
+        cb, ce = c_range if c_range is not None else (0, cs.shape[0])
+        self._ck(_lib().gm_ransac_pair(self._h, _ptr(ps), ps.shape[0], pb, pe, _ptr(cs), cs.shape[0], cb, ce), "gm_ransac_pair")
+
+    def ransac_select_pair(self):
+        self._ck(_lib().gm_ransac_select_pair(self._h), "gm_ransac_select_pair")
+
+    def ransac_export_keys(self, dst_device_ptr: int):
+        self._ck(_lib().gm_ransac_export_keys(self._h, C.c_void_p(dst_device_ptr)), "gm_ransac_export_keys")
+
+    def ransac_import_keys(self, src_device_ptr: int):
+        self._ck(_lib().gm_ransac_import_keys(self._h, C.c_void_p(src_device_ptr)), "gm_ransac_import_keys")
 
     def ransac_select(self, kind: int):
         self._ck(_lib().gm_ransac_select(self._h, kind), "gm_ransac_select")

@@ -1121,6 +1121,54 @@ gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_
   return GM_OK;
 }
 
+// Plane and cylinder rounds of one RANSAC step side by side (they only read the compacted / cell-sorted cloud and
+// write disjoint outputs): the multi-GPU hand-off runs gm_ransac_pair -> ONE all-reduce of both keys ->
+// gm_ransac_select_pair, so a sharded round costs one collective and the longer of the two refits.
+gm_status gm_ransac_pair(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, int32_t p_begin, int32_t p_end,
+                         const int32_t* cyl_samples_host, int32_t Hc, int32_t c_begin, int32_t c_end) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  gm_status s;
+  if (ctx->concurrent && !ctx->profiling) {
+    GM_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if ((s = run_branch(ctx, 1, [&] { return gm_ransac(ctx, GM_MODEL_PLANE, plane_samples_host, Hp, p_begin, p_end); })) != GM_OK) return s;
+    if ((s = gm_ransac(ctx, GM_MODEL_CYLINDER, cyl_samples_host, Hc, c_begin, c_end)) != GM_OK) return s;
+    GM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
+    return GM_OK;
+  }
+  if ((s = gm_ransac(ctx, GM_MODEL_PLANE, plane_samples_host, Hp, p_begin, p_end)) != GM_OK) return s;
+  return gm_ransac(ctx, GM_MODEL_CYLINDER, cyl_samples_host, Hc, c_begin, c_end);
+}
+
+gm_status gm_ransac_select_pair(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_ransac[0] || !ctx->have_ransac[1]) return GM_ERR_STAGE_ORDER;
+  gm_status s;
+  if (ctx->concurrent && !ctx->profiling) {
+    GM_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if ((s = run_branch(ctx, 1, [&] { return gm_ransac_select(ctx, GM_MODEL_PLANE); })) != GM_OK) return s;
+    if ((s = gm_ransac_select(ctx, GM_MODEL_CYLINDER)) != GM_OK) return s;
+    GM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
+    return GM_OK;
+  }
+  if ((s = gm_ransac_select(ctx, GM_MODEL_PLANE)) != GM_OK) return s;
+  return gm_ransac_select(ctx, GM_MODEL_CYLINDER);
+}
+
+/* both keys (plane, cylinder) as 16 contiguous bytes */
+gm_status gm_ransac_export_keys(gm_ctx* ctx, void* dst_device) {
+  if (!ctx || !dst_device) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_ransac[0] || !ctx->have_ransac[1]) return GM_ERR_STAGE_ORDER;
+  GM_CUDA(cudaMemcpyAsync(dst_device, ctx->d_key, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+  return GM_OK;
+}
+gm_status gm_ransac_import_keys(gm_ctx* ctx, const void* src_device) {
+  if (!ctx || !src_device) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_ransac[0] || !ctx->have_ransac[1]) return GM_ERR_STAGE_ORDER;
+  GM_CUDA(cudaMemcpyAsync(ctx->d_key, src_device, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+  return GM_OK;
+}
+
 // ---- results ---------------------------------------------------------------------------------
 gm_status gm_get_counts(gm_ctx* ctx, gm_counts* out) {
   if (!ctx || !out) return GM_ERR_INVALID_ARG;

@@ -76,6 +76,18 @@ def sharded_ransac(ctx, kind: int, samples, rank: int, world: int, key_tensor, g
     ctx.ransac_select(kind)
 
 
+def sharded_ransac_pair(ctx, plane_samples, cyl_samples, rank: int, world: int, key_tensor2, group=None):
+    """One hypothesis-sharded RANSAC step for both primitives: plane and cylinder shards are counted side by side,
+    ONE all-reduce(MAX) carries both packed keys (`key_tensor2`: 2-element int64 tensor on the ctx's device and
+    stream), then both winners are refitted side by side on every rank."""
+    ctx.ransac_pair(plane_samples, cyl_samples, shard_range(len(plane_samples), rank, world), shard_range(len(cyl_samples), rank, world))
+    if world > 1:
+        ctx.ransac_export_keys(key_tensor2.data_ptr())
+        allreduce_best_key(key_tensor2, group)
+        ctx.ransac_import_keys(key_tensor2.data_ptr())
+    ctx.ransac_select_pair()
+
+
 # ---------------------------------------------------------------------------------------------
 # Map slabs (SURVEY.md section 8e, config C4): one large map cut along an axis, one slab per rank.
 #

@@ -225,6 +225,14 @@ GM_API gm_status gm_ransac_import_key(gm_ctx* ctx, int32_t kind, const void* src
 /* Decode the (possibly all-reduced) key on device, refit the winning primitive (plane: PCA of
  * inliers; cylinder: refitIterations Gauss-Newton steps) and keep the result in ctx. */
 GM_API gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind);
+/* One RANSAC step for both primitives with the plane and cylinder work side by side on two streams of the ctx
+ * (same results as the four separate calls).  Multi-GPU: gm_ransac_pair -> gm_ransac_export_keys -> ONE
+ * all-reduce(MAX) of 2 x int64 -> gm_ransac_import_keys -> gm_ransac_select_pair. */
+GM_API gm_status gm_ransac_pair(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, int32_t p_begin, int32_t p_end,
+                                const int32_t* cyl_samples_host, int32_t Hc, int32_t c_begin, int32_t c_end);
+GM_API gm_status gm_ransac_select_pair(gm_ctx* ctx);
+GM_API gm_status gm_ransac_export_keys(gm_ctx* ctx, void* dst_device_16_bytes);
+GM_API gm_status gm_ransac_import_keys(gm_ctx* ctx, const void* src_device_16_bytes);
 /* Per-point labels from the refined models: 1 plane, 2 cylinder, 0 neither. */
 GM_API gm_status gm_label(gm_ctx* ctx);
 /* Center-axis polyline + cross-sections along the getLocalFrame axis over points with label 2. */

@@ -770,6 +770,46 @@ def test_tile_culled_counts_equal_brute_force_and_oracle(n, radius, tau):
         assert ref_p.max() > 0.1 * nv and ref_c.max() > 0.1 * nv   # the test is not vacuous
 
 
+def test_ransac_pair_equals_separate_calls_and_sharded_keys_compose():
+    """gm_ransac_pair / gm_ransac_select_pair (plane and cylinder side by side on two streams) == the four separate
+    calls; and the max of the per-shard keys, imported as 16 bytes, selects the single-range winners."""
+    import torch
+
+    n = 60_000
+    pts = synth.curved_tunnel(n, seed=41)
+    with _ctx(n, neighborRadius=0.12) as ctx:
+        ctx.upload_scan(pts); ctx.crop(); ctx.normals()
+        nv = ctx.counts().n_valid
+        ps, cs = synth.sample_indices(nv, 640, 3, seed=3), synth.sample_indices(nv, 600, 2, seed=4)
+        ctx.ransac(0, ps); ctx.ransac(1, cs)
+        ref_counts = (ctx.download_hypotheses(0, 640)[2], ctx.download_hypotheses(1, 600)[2])
+        ctx.ransac_select(0); ctx.ransac_select(1)
+        ref_models = (ctx.model(0), ctx.model(1))
+        ctx.ransac_pair(ps, cs)
+        got_counts = (ctx.download_hypotheses(0, 640)[2], ctx.download_hypotheses(1, 600)[2])
+        ctx.ransac_select_pair()
+        got_models = (ctx.model(0), ctx.model(1))
+        # three "ranks" on one GPU: shard, export 16 bytes, max, import, select
+        keys = torch.zeros(2, dtype=torch.int64, device="cuda")
+        best = torch.zeros(2, dtype=torch.int64, device="cuda")
+        from geometric_mapping_b200 import distributed as D
+        for r in range(3):
+            ctx.ransac_pair(ps, cs, D.shard_range(640, r, 3), D.shard_range(600, r, 3))
+            ctx.ransac_export_keys(keys.data_ptr())
+            ctx.synchronize()
+            best = torch.maximum(best, keys)
+        ctx.ransac_import_keys(best.data_ptr())
+        ctx.ransac_select_pair()
+        shard_models = (ctx.model(0), ctx.model(1))
+        assert ctx.counts().device_error == 0
+    for k in (0, 1):
+        assert np.array_equal(got_counts[k], ref_counts[k])
+        for m in (got_models[k], shard_models[k]):
+            assert m["best_id"] == ref_models[k]["best_id"] and m["best_count"] == ref_models[k]["best_count"]
+            assert m["refit_count"] == ref_models[k]["refit_count"]
+            assert np.array_equal(m["coef"].view(np.uint32), ref_models[k]["coef"].view(np.uint32))   # same kernels, same bits
+
+
 def test_count_linearity_over_a_split_cloud():
     """counts(cloud) == counts(first half) + counts(second half) for fixed hypotheses: exact."""
     cloud, nrm = _compacted_scan(60_000, seed=51)

@@ -46,6 +46,8 @@ class gm_params(C.Structure):
         ("refitIterations", C.c_int32),
         ("maxSlices", C.c_int32),
         ("sliceLength", C.c_double),
+        ("weight_mode", C.c_int32),
+        ("arrow_mode", C.c_int32),
     ]
 
 
@@ -113,7 +115,7 @@ _LIB = None
 
 # every symbol include/gm_capi.h declares; tests/test_abi.py checks the list against the header
 SYMBOLS = [
-    "gm_params_default", "gm_create", "gm_destroy", "gm_set_params", "gm_set_stream", "gm_last_error",
+    "gm_params_default", "gm_create", "gm_destroy", "gm_set_params", "gm_get_params", "gm_markers_normals_mode", "gm_set_stream", "gm_last_error",
     "gm_status_string", "gm_version", "gm_launch_count", "gm_reset_launch_count", "gm_synchronize",
     "gm_upload_scan", "gm_set_scan_device", "gm_crop", "gm_normals", "gm_voxel", "gm_local_frame", "gm_ransac",
     "gm_ransac_key_device_ptr", "gm_ransac_select", "gm_label", "gm_axis_polyline", "gm_process_scan",
@@ -147,6 +149,8 @@ def _lib():
         "gm_create": (i32, [C.POINTER(gm_params), sz, i32, C.POINTER(vp)]),
         "gm_destroy": (None, [vp]),
         "gm_set_params": (i32, [vp, C.POINTER(gm_params)]),
+        "gm_get_params": (i32, [vp, C.POINTER(gm_params)]),
+        "gm_markers_normals_mode": (None, [vp, vp, i32, i32, vp]),
         "gm_set_stream": (i32, [vp, vp]),
         "gm_last_error": (C.c_char_p, [vp]),
         "gm_status_string": (C.c_char_p, [i32]),
@@ -569,11 +573,12 @@ def markers_eigen(frame_struct: gm_frame) -> np.ndarray:
     return out
 
 
-def markers_normals(centroids: np.ndarray, nn_normal8: np.ndarray) -> np.ndarray:
+def markers_normals(centroids: np.ndarray, nn_normal8: np.ndarray, arrow_mode: int = 0) -> np.ndarray:
+    """arrow_mode 0 = the reference's arrows (end point = the normal itself, quirk B.4), 1 = end = centroid + normal."""
     cen = np.ascontiguousarray(centroids, np.float32)
     nn = np.ascontiguousarray(nn_normal8, np.float32)
     out = np.zeros(cen.shape[0], ARROW_DTYPE)
-    _lib().gm_markers_normals(_ptr(cen), _ptr(nn), cen.shape[0], _ptr(out))
+    _lib().gm_markers_normals_mode(_ptr(cen), _ptr(nn), cen.shape[0], arrow_mode, _ptr(out))
     return out
 
 

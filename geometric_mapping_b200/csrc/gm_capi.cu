@@ -201,6 +201,14 @@ namespace {
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// src/tunnel_processing.cpp:106: exp((curv + .001/weightingFactor)^2) -- note the precedence (mode 0); mode 1: exp(-(curv/wf)^2)
+inline WeightLaw weight_law(const gm_params& p) {
+  WeightLaw w;
+  if (p.weight_mode == 1) { w.scale = 1.0 / p.weightingFactor; w.shift = 0.0; w.sgn = -1.0; }
+  else { w.scale = 1.0; w.shift = .001 / p.weightingFactor; w.sgn = 1.0; }
+  return w;
+}
+
 template <class T>
 cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
 
@@ -355,6 +363,8 @@ void gm_params_default(gm_params* p) {
   p->refitIterations = 5;
   p->maxSlices = 256;
   p->sliceLength = 1.0;
+  p->weight_mode = 0;
+  p->arrow_mode = 0;
 }
 
 const char* gm_status_string(gm_status s) {
@@ -380,6 +390,7 @@ static gm_status validate_params(const gm_params* p) {
   if (!(p->boxFilterBound > 0.0) || !(p->voxelGridLeafSize > 0.0) || !(p->neighborRadius > 0.0)) return GM_ERR_INVALID_ARG;
   if (p->weightingFactor == 0.0) return GM_ERR_INVALID_ARG;
   if (!(p->ransacThreshold > 0.0) || p->refitIterations < 0 || p->maxSlices < 1 || !(p->sliceLength > 0.0)) return GM_ERR_INVALID_ARG;
+  if (p->weight_mode < 0 || p->weight_mode > 1 || p->arrow_mode < 0 || p->arrow_mode > 1) return GM_ERR_INVALID_ARG;
   return GM_OK;
 }
 
@@ -490,6 +501,12 @@ gm_status gm_set_params(gm_ctx* ctx, const gm_params* p) {
   if (p->maxSlices > ctx->prm.maxSlices) { ctx->err = "maxSlices cannot grow after gm_create"; return GM_ERR_CAPACITY; }
   ctx->prm = *p;
   return regrid(ctx);
+}
+
+gm_status gm_get_params(const gm_ctx* ctx, gm_params* out) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  *out = ctx->prm;
+  return GM_OK;
 }
 
 gm_status gm_set_grid_box(gm_ctx* ctx, const float* min3, const float* max3) {
@@ -811,9 +828,9 @@ gm_status gm_voxel(gm_ctx* ctx) {
 gm_status gm_local_frame(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
-  double shift = .001 / ctx->prm.weightingFactor;  // src/tunnel_processing.cpp:106 precedence
+  const WeightLaw law = weight_law(ctx->prm);
   SegTimer seg_(ctx, SEG_FRAME);
-  GM_LAUNCH(ctx, k_frame, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, shift, ctx->d_partials + 0 * kPartialsRegion, ctx->d_counters + 0,
+  GM_LAUNCH(ctx, k_frame, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, law, ctx->d_partials + 0 * kPartialsRegion, ctx->d_counters + 0,
             ctx->d_frame);
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_frame = true;
@@ -966,7 +983,7 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   if (!ctx->have_frame || !ctx->have_labels) return GM_ERR_STAGE_ORDER;
   const int S = ctx->prm.maxSlices;
   const int* n_ptr = &ctx->d_st->n_valid;
-  double shift = .001 / ctx->prm.weightingFactor;
+  const WeightLaw shift = weight_law(ctx->prm);
   SegTimer seg_(ctx, SEG_POLYLINE);
   {
     // 4 launches: range (+basis, +zeroing, +slice layout) and three accumulation passes, each with the
@@ -1445,11 +1462,16 @@ void gm_markers_eigen(const gm_frame* frame, gm_arrow out[3]) {
 }
 
 void gm_markers_normals(const float* centroids, const float* nn_normal8, int32_t V, gm_arrow* out) {
+  gm_markers_normals_mode(centroids, nn_normal8, V, 0, out);
+}
+
+void gm_markers_normals_mode(const float* centroids, const float* nn_normal8, int32_t V, int32_t arrow_mode, gm_arrow* out) {
   for (int32_t i = 0; i < V; ++i) {
     gm_arrow& a = out[i];
     for (int k = 0; k < 3; ++k) {
       a.start[k] = centroids[(size_t)i * 4 + k];        // src/tunnel_processing.cpp:242-244
       a.end[k] = nn_normal8[(size_t)i * 8 + k];         // :247-249: end = the normal itself (quirk B.4)
+      if (arrow_mode == 1) a.end[k] = a.start[k] + a.end[k];  // "fixed": the arrow points along the normal from the centroid
     }
     a.scale[0] = 0.025f; a.scale[1] = 0.075f; a.scale[2] = 0.0625f;  // :230
     a.color_argb[0] = 1.0f; a.color_argb[1] = 0.0f; a.color_argb[2] = 0.0f; a.color_argb[3] = 1.0f;  // :231 -> a=1,b=1 (quirk B.5)

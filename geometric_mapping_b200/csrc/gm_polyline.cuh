@@ -178,7 +178,7 @@ k_poly_range(const float4* __restrict__ pts, const unsigned char* __restrict__ l
 template <int PASS>
 __global__ void __launch_bounds__(POLY_BLOCK)
 k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, const unsigned char* __restrict__ labels,
-            const int* __restrict__ n_ptr, const PolyState* __restrict__ ps, double shift, long long* __restrict__ acc,
+            const int* __restrict__ n_ptr, const PolyState* __restrict__ ps, WeightLaw law, long long* __restrict__ acc,
             gm_slice* __restrict__ out, unsigned* ticket) {
   constexpr int NS = PASS == 0 ? 9 : (PASS == 1 ? 6 : 1);
   constexpr int SLOT0 = PASS == 0 ? 0 : (PASS == 1 ? 9 : 15);
@@ -213,8 +213,7 @@ k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, 
         double a = u0 * x + u1 * y + u2 * z, b = w0 * x + w1 * y + w2 * z;
         float4 n0 = normals[2 * (size_t)i];
         float curv = normals[2 * (size_t)i + 1].x;
-        double tt = (double)curv + shift;
-        double wt = (double)(float)exp(tt * tt);
+        double wt = (double)d_weight(law, curv);
         double na = wt * (double)n0.x, nb = wt * (double)n0.y, nc = wt * (double)n0.z;
         v[0] = 1; v[1] = d_to_fx(a); v[2] = d_to_fx(b);
         v[3] = d_to_fx(na * na); v[4] = d_to_fx(na * nb); v[5] = d_to_fx(na * nc);

@@ -980,6 +980,15 @@ __device__ void d_jacobi3(const double Ain[9], double vals[3], double vecs[9]) {
   }
 }
 
+// Weight law of getLocalFrame as w = float(exp(sgn * t^2)), t = curv * scale + shift.  Reference (mode 0,
+// src/tunnel_processing.cpp:106): scale 1, shift 0.001/wf, sgn +1 -- the weight GROWS with curvature (quirk B.2).
+// "Fixed" law (mode 1, builder-defined): scale 1/wf, shift 0, sgn -1.
+struct WeightLaw { double scale, shift, sgn; };
+__device__ __forceinline__ float d_weight(const WeightLaw& w, float curv) {
+  const double t = (double)curv * w.scale + w.shift;
+  return (float)exp(w.sgn * t * t);
+}
+
 // a5 getLocalFrame (src/tunnel_processing.cpp:92-148), diagonal form of the dense weights*normals
 // product.  w_i = float(exp((double(curv_i) + 0.001/wf)^2)); Wn = w_i*n_i in float; the 3x3
 // scatter sum is accumulated in double (fixed grid, fixed tree -> reproducible); the last block to
@@ -988,7 +997,7 @@ constexpr int FR_BLOCK = 256;
 struct FrameOut { float vals[3]; float vecs[9]; float scatter[9]; };
 
 __global__ void __launch_bounds__(FR_BLOCK)
-k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, double shift, double* __restrict__ partials,
+k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, WeightLaw law, double* __restrict__ partials,
         unsigned* counter, FrameOut* out) {
   __shared__ double sm[6 * (FR_BLOCK / 32)];
   __shared__ double fin[6];
@@ -997,8 +1006,7 @@ k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, dou
   for (int i = blockIdx.x * FR_BLOCK + threadIdx.x; i < n; i += gridDim.x * FR_BLOCK) {
     float4 n0 = normals_c[2 * (size_t)i];
     float curv = normals_c[2 * (size_t)i + 1].x;
-    double t = (double)curv + shift;
-    float w = (float)exp(t * t);
+    float w = d_weight(law, curv);
     float a = w * n0.x, b = w * n0.y, c = w * n0.z;
     s[0] += (double)a * (double)a; s[1] += (double)a * (double)b; s[2] += (double)a * (double)c;
     s[3] += (double)b * (double)b; s[4] += (double)b * (double)c; s[5] += (double)c * (double)c;

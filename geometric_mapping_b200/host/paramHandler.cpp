@@ -31,6 +31,9 @@ Parameters::Parameters(const ParamSource& node) {
     if (it != node.end()) { *d.dst = std::strtod(it->second.c_str(), nullptr); std::fprintf(stderr, "[ INFO] %s set to:\t %f\n", d.field, *d.dst); }
     else std::fprintf(stderr, "[ INFO] ERROR: %s set to default...\n", d.field);
   }
+  // not parameters of the reference: optional switches for its quirks (absent = reference-faithful, no log line)
+  { auto it = node.find("weightMode"); if (it != node.end()) weightMode = std::atoi(it->second.c_str()); }
+  { auto it = node.find("arrowMode"); if (it != node.end()) arrowMode = std::atoi(it->second.c_str()); }
   for (const B& b : bools) {
     auto it = node.find(b.key);
     if (it != node.end() && it->second.find("$(") == std::string::npos) { *b.dst = toBool(it->second); std::fprintf(stderr, "[ INFO] %s set to:\t %d\n", b.field, (int)*b.dst); }
@@ -43,6 +46,7 @@ gm_params Parameters::toGm() const {
   gm_params_default(&p);
   p.boxFilterBound = boxFilterBound; p.voxelGridLeafSize = leafSize; p.neighborRadius = neighborRadius; p.weightingFactor = weightingFactor;
   p.displayCloud = rvizCloud; p.displayNormals = rvizNormals; p.displayCenterAxis = rvizCenterAxis; p.usePCLViz = pclviz;
+  p.weight_mode = weightMode; p.arrow_mode = arrowMode;
   return p;
 }
 

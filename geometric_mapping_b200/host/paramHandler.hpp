@@ -29,6 +29,7 @@ class Parameters {
  private:
   double boxFilterBound = 5.0, leafSize = .1, neighborRadius = .03, weightingFactor = .2;
   bool rvizCloud = true, rvizNormals = true, rvizCenterAxis = true, pclviz = false;
+  int weightMode = 0, arrowMode = 0;  // quirk switches (gm_params.weight_mode / arrow_mode); 0 = as the reference
 };
 
 }  // namespace gmhost

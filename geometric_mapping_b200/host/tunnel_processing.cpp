@@ -85,7 +85,9 @@ MarkerArray rvizNormals(const double& leafSize, const CloudPtr& cloud, const Sea
   if (s == GM_ERR_NN_INDEX_RANGE) throw GmError(s, "rvizNormals: normals->at(index) out of range (reference quirk B.3)");
   ck(s, "gm_download_voxels", GM_WARN_VOXEL_OVERFLOW);
   std::vector<gm_arrow> arrows(V);
-  gm_markers_normals(cen.data(), nn.data(), (int32_t)V, arrows.data());
+  gm_params prm;
+  ck(gm_get_params(ctx, &prm), "gm_get_params");
+  gm_markers_normals_mode(cen.data(), nn.data(), (int32_t)V, prm.arrow_mode, arrows.data());  // 0 = the reference's arrows (quirk B.4)
   out.reserve(V);
   for (const gm_arrow& a : arrows) out.push_back(fromArrow(a, "normals"));
   return out;

@@ -82,7 +82,7 @@ def rvizNormals(leafSize: float, cloud: np.ndarray, ctx: capi.Context, normals: 
         raise ValueError("rvizNormals: cloud/normals are not the getNormals results held by this Context")
     ctx.voxel()
     vox = ctx.download_voxels()
-    arrows = capi.markers_normals(vox["centroids"], vox["nn_normal"])
+    arrows = capi.markers_normals(vox["centroids"], vox["nn_normal"], int(ctx.params.arrow_mode))
     return [rvizArrow(a["start"], a["end"], a["scale"], a["color_argb"], "normals", int(a["id"])) for a in arrows]
 
 

@@ -68,6 +68,11 @@ typedef struct gm_params {
   int32_t refitIterations;  /* Gauss-Newton steps of the cylinder refit, default 5 */
   int32_t maxSlices;        /* polyline capacity, default 256 */
   double sliceLength;       /* polyline slice length along the center axis, default 1.0 m */
+  /* --- reference quirks as switches: 0 = reference-faithful (default), 1 = "fixed" --- */
+  int32_t weight_mode;      /* getLocalFrame weights: 0 = exp((curv + 0.001/wf)^2), grows with curvature (B.2,
+                               src/tunnel_processing.cpp:106); 1 = exp(-(curv/wf)^2) (builder-defined) */
+  int32_t arrow_mode;       /* normal arrows: 0 = end point is the normal vector itself (B.4, :247-249);
+                               1 = end = centroid + normal.  Read by the host shims; see gm_markers_normals_mode */
 } gm_params;
 
 typedef struct gm_ctx gm_ctx;
@@ -149,6 +154,7 @@ GM_API void gm_params_default(gm_params* p);
 GM_API gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypotheses, gm_ctx** out);
 GM_API void gm_destroy(gm_ctx* ctx);
 GM_API gm_status gm_set_params(gm_ctx* ctx, const gm_params* p);
+GM_API gm_status gm_get_params(const gm_ctx* ctx, gm_params* out);
 /* Use an existing cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own (non-blocking)
  * stream; to run on CUDA's legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1). */
 GM_API gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream);
@@ -324,6 +330,8 @@ GM_API gm_status gm_inject_compacted(gm_ctx* ctx, const float* xyzw_host, const 
 GM_API void gm_markers_eigen(const gm_frame* frame, gm_arrow out[3]);
 /* rvizNormals marker payload: src/tunnel_processing.cpp:228-252 -> V arrows from the voxel results */
 GM_API void gm_markers_normals(const float* centroids_xyzw, const float* nn_normal8, int32_t V, gm_arrow* out);
+/* same with the arrow-end switch of gm_params.arrow_mode (0 = reference quirk B.4, 1 = end = start + normal) */
+GM_API void gm_markers_normals_mode(const float* centroids_xyzw, const float* nn_normal8, int32_t V, int32_t arrow_mode, gm_arrow* out);
 
 /* ---- aggregated voxel map across scans (builder-defined, the reference keeps nothing between
  * callbacks, src/geometric_mapping.cpp:48-125) --------------------------------------------------------

@@ -475,15 +475,24 @@ GMO_API void gmo_nn1_grid(const float* query4, int64_t nq, const float* pts4, in
 //   eig  = ascending eigenvalues / column eigenvectors          :129-137
 // S9 row-major float; vals3/vecs9 float (vecs9[r*3+k] = component r of eigenvector k);
 // S_truth9: same matrix accumulated in double from the float Wn products.
+// Weight law of getLocalFrame.  mode 0 (reference, src/tunnel_processing.cpp:106): w = exp((curv + 0.001/wf)^2), which
+// GROWS with curvature (quirk B.2).  mode 1 (builder-defined "fixed" law): w = exp(-(curv/wf)^2), flat
+// regions dominate and wf is the curvature scale.  Both as w = float(exp(sgn * t^2)), t = curv * scale + shift.
+static inline void weight_law(int mode, double wf, double& scale, double& shift, double& sgn) {
+  if (mode == 1) { scale = 1.0 / wf; shift = 0.0; sgn = -1.0; }
+  else { scale = 1.0; shift = 0.001 / wf; sgn = 1.0; }
+}
+
 GMO_API void gmo_local_frame(const float* normals8, int64_t n, double wf, float* S9, float* vals3,
-                             float* vecs9, double* S_truth9) {
+                             float* vecs9, double* S_truth9, int32_t weight_mode) {
   float S[6] = {0, 0, 0, 0, 0, 0};
   double T[6] = {0, 0, 0, 0, 0, 0};
-  const double shift = 0.001 / wf;
+  double scale, shift, sgn;
+  weight_law(weight_mode, wf, scale, shift, sgn);
   for (int64_t i = 0; i < n; ++i) {
     const float* nr = normals8 + i * 8;
-    double t = (double)nr[4] + shift;
-    float w = (float)std::exp(t * t);
+    double t = (double)nr[4] * scale + shift;
+    float w = (float)std::exp(sgn * t * t);
     float a = w * nr[0], b = w * nr[1], c = w * nr[2];
     S[0] += a * a; S[1] += a * b; S[2] += a * c; S[3] += b * b; S[4] += b * c; S[5] += c * c;
     T[0] += (double)a * a; T[1] += (double)a * b; T[2] += (double)a * c; T[3] += (double)b * b; T[4] += (double)b * c; T[5] += (double)c * c;
@@ -877,7 +886,7 @@ GMO_API void gmo_labels(const float* pts4, int64_t n, const float* plane4, doubl
 // out per slice (12 doubles): cx,cy,cz, dx,dy,dz, radius, count, rms, t_mid, 0, 0
 GMO_API int32_t gmo_polyline(const float* pts4, const float* normals8, const uint8_t* labels,
                              int64_t n, int want, const float* axis3, double wf, double L,
-                             int32_t max_slices, double* out12, double* t0_out) {
+                             int32_t max_slices, double* out12, double* t0_out, int32_t weight_mode) {
   const P4* p = (const P4*)pts4;
   double ax[3] = {axis3[0], axis3[1], axis3[2]};
   double u[3], w[3];
@@ -896,7 +905,8 @@ GMO_API int32_t gmo_polyline(const float* pts4, const float* normals8, const uin
   struct Acc { double n, a, b, aa, ab, bb, N[6]; std::vector<int32_t> idx; };
   std::vector<Acc> acc((size_t)S);
   for (auto& a : acc) { a.n = a.a = a.b = a.aa = a.ab = a.bb = 0; for (double& v : a.N) v = 0; }
-  const double shift = 0.001 / wf;
+  double scale, shift, sgn;
+  weight_law(weight_mode, wf, scale, shift, sgn);
   for (int64_t i = 0; i < n; ++i) {
     if (labels && labels[i] != want) continue;
     double t = ax[0] * p[i].x + ax[1] * p[i].y + ax[2] * p[i].z;
@@ -908,8 +918,8 @@ GMO_API int32_t gmo_polyline(const float* pts4, const float* normals8, const uin
     A.n += 1; A.a += a; A.b += b;
     A.idx.push_back((int32_t)i);
     const float* nr = normals8 + i * 8;
-    double tt = (double)nr[4] + shift;
-    double wt = (double)(float)std::exp(tt * tt);
+    double tt = (double)nr[4] * scale + shift;
+    double wt = (double)(float)std::exp(sgn * tt * tt);
     double na = wt * nr[0], nb = wt * nr[1], nc = wt * nr[2];
     A.N[0] += na * na; A.N[1] += na * nb; A.N[2] += na * nc; A.N[3] += nb * nb; A.N[4] += nb * nc; A.N[5] += nc * nc;
   }

@@ -121,11 +121,12 @@ def nn1_grid(query, pts, cell, nthreads=0):
     return idx, d2
 
 
-def local_frame(normals8, wf):
+def local_frame(normals8, wf, weight_mode=0):
     normals8 = _f32(normals8)
     S, vals, vecs = np.empty(9, np.float32), np.empty(3, np.float32), np.empty(9, np.float32)
     St = np.empty(9, np.float64)
-    lib().gmo_local_frame(_p(normals8), C.c_int64(normals8.shape[0]), C.c_double(wf), _p(S), _p(vals), _p(vecs), _p(St))
+    lib().gmo_local_frame(_p(normals8), C.c_int64(normals8.shape[0]), C.c_double(wf), _p(S), _p(vals), _p(vecs), _p(St),
+                          C.c_int32(weight_mode))
     return {"scatter": S.reshape(3, 3), "vals": vals, "vecs": vecs.reshape(3, 3), "scatter_truth": St.reshape(3, 3)}
 
 
@@ -218,14 +219,14 @@ def labels(pts, plane4, tau, cyl_test12):
     return out
 
 
-def polyline(pts, normals8, labels_u8, want, axis3, wf, L, max_slices):
+def polyline(pts, normals8, labels_u8, want, axis3, wf, L, max_slices, weight_mode=0):
     pts, normals8 = _f32(pts), _f32(normals8)
     lab = None if labels_u8 is None else np.ascontiguousarray(labels_u8, np.uint8)
     ax = _f32(axis3)
     out = np.zeros((max_slices, 12), np.float64)
     t0 = C.c_double(0.0)
     S = lib().gmo_polyline(_p(pts), _p(normals8), _p(lab), C.c_int64(pts.shape[0]), C.c_int(want), _p(ax), C.c_double(wf),
-                           C.c_double(L), C.c_int32(max_slices), _p(out), C.byref(t0))
+                           C.c_double(L), C.c_int32(max_slices), _p(out), C.byref(t0), C.c_int32(weight_mode))
     return out[:S].copy(), t0.value
 
 

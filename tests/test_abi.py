@@ -36,7 +36,8 @@ def test_library_is_in_tree_and_has_sm100a_code():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(capi.gm_params) == 4 * 8 + 6 * 4 + 3 * 8 + 2 * 4 + 8
+    assert C.sizeof(capi.gm_params) == 4 * 8 + 6 * 4 + 3 * 8 + 2 * 4 + 8 + 2 * 4
+    assert capi.gm_params.weight_mode.offset == 96 and capi.gm_params.arrow_mode.offset == 100
     assert C.sizeof(capi.gm_counts) == 32
     assert C.sizeof(capi.gm_frame) == 84
     assert C.sizeof(capi.gm_arrow) == 56 and capi.ARROW_DTYPE.itemsize == 56
@@ -52,6 +53,7 @@ def test_defaults_mirror_paramhandler():
     assert (p.boxFilterBound, p.voxelGridLeafSize, p.neighborRadius, p.weightingFactor) == (5.0, 0.1, 0.03, 0.2)
     assert (p.displayCloud, p.displayNormals, p.displayCenterAxis, p.usePCLViz) == (1, 1, 1, 0)
     assert p.is_dense == 1 and p.nn_index_mode == 0 and p.ransacThreshold == 0.05
+    assert p.weight_mode == 0 and p.arrow_mode == 0     # reference-faithful quirks by default
 
 
 def test_status_strings_and_version():

@@ -357,6 +357,32 @@ def test_local_frame_injected_normals():
     _frame_close(fr, O.local_frame(nr, 0.13))
 
 
+def test_quirk_switches_weight_law_and_arrow_end():
+    """the reference's quirks stay the default; mode 1 of each switch is checked against the oracle's
+    restatement (weights) and by construction (arrows)."""
+    pts = synth.curved_tunnel(40_000, seed=12)
+    out = {}
+    for wm in (0, 1):
+        with _ctx(len(pts), neighborRadius=0.15, weightingFactor=0.13, weight_mode=wm, arrow_mode=wm) as ctx:
+            ctx.upload_scan(pts)
+            ctx.crop()
+            ctx.normals()
+            ctx.voxel()
+            ctx.local_frame()
+            nrm = ctx.download_normals(1)
+            fr = ctx.frame()
+            vox = ctx.download_voxels()
+            arrows = capi.markers_normals(vox["centroids"], vox["nn_normal"], ctx.params.arrow_mode)
+        _frame_close(fr, O.local_frame(nrm, 0.13, weight_mode=wm))
+        out[wm] = (fr, arrows, vox)
+    assert not np.allclose(out[0][0]["scatter"], out[1][0]["scatter"], rtol=1e-3)          # the two laws differ
+    a0, a1, vox = out[0][1], out[1][1], out[0][2]
+    ok = np.isfinite(vox["nn_normal"][:, 0])
+    assert np.array_equal(a0["end"][ok], vox["nn_normal"][ok, :3])                           # quirk B.4: end = the normal itself
+    assert np.array_equal(a1["end"][ok], vox["centroids"][ok, :3] + vox["nn_normal"][ok, :3])  # fixed: start + normal
+    assert np.array_equal(a0["start"], a1["start"])
+
+
 # ---- a8 RANSAC (builder-defined; oracle = builder restatement of the PCL semantics) --------------
 def _compacted_scan(n=80_000, seed=31, radius=0.15):
     pts = synth.curved_tunnel(n, seed=seed)

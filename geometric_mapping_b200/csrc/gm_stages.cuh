@@ -313,20 +313,22 @@ __global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* _
       gm_cell_coords(g, key, cx, cy0, cz0);
       const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
       const int split = x0 | 3;  // last cell of x0's block
-#pragma unroll 1
+      // all 18 segment lookups first (independent loads in flight together), then the in-order merge
+      int2 seg[GRID_RUNS];
+#pragma unroll
       for (int k = 0; k < 9; ++k) {
         const int cy = cy0 + (k % 3) - 1, cz = cz0 + (k / 3) - 1;
-        if (cy < 0 || cz < 0 || cy >= g.dim[1] || cz >= g.dim[2]) continue;
+        const bool in = cy >= 0 && cz >= 0 && cy < g.dim[1] && cz < g.dim[2];
+        seg[2 * k] = in ? cell_segment(g, tab, ucell_start, U, nf, x0, min(x1, split), cy, cz) : make_int2(0, 0);
+        seg[2 * k + 1] = (in && x1 > split) ? cell_segment(g, tab, ucell_start, U, nf, split + 1, x1, cy, cz) : make_int2(0, 0);
+      }
 #pragma unroll
-        for (int seg = 0; seg < 2; ++seg) {
-          if (seg == 1 && x1 <= split) break;
-          const int2 r = (seg == 0) ? cell_segment(g, tab, ucell_start, U, nf, x0, min(x1, split), cy, cz)
-                                    : cell_segment(g, tab, ucell_start, U, nf, split + 1, x1, cy, cz);
-          if (r.y <= r.x) continue;
-          if (cur.y == r.x && cur.y > cur.x) { cur.y = r.y; continue; }  // contiguous with the pending run
-          if (cur.y > cur.x) out[m++] = cur;
-          cur = r;
-        }
+      for (int q = 0; q < GRID_RUNS; ++q) {
+        const int2 r = seg[q];
+        if (r.y <= r.x) continue;
+        if (cur.y == r.x && cur.y > cur.x) { cur.y = r.y; continue; }  // contiguous with the pending run
+        if (cur.y > cur.x) out[m++] = cur;
+        cur = r;
       }
       if (cur.y > cur.x) out[m++] = cur;
     }

@@ -14,7 +14,7 @@
 // Appendix A.1-A.6), and (c) builder-defined RANSAC / refit / polyline / compression
 // definitions (Appendix A.7-A.10) that the reference only stubs
 // (src/tunnel_processing.cpp:149-154).  It is pinned only by analytic known answers
-// (tests/test_oracle_known_answers.py) and by brute-force vs accelerated self-consistency.
+// (tests/test_oracle.py, golden vectors in tests/golden/) and by brute-force vs accelerated self-consistency.
 //
 // Build: see oracle/Makefile  (-O2 -ffp-contract=off: no implicit FMA contraction, matching the
 // reference build which has no -march/-mfma flags, CMakeLists.txt:5).  Explicit fmaf() calls

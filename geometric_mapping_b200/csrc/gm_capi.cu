@@ -288,6 +288,9 @@ gm_status ensure_block_table(gm_ctx* ctx) {
   }
   GM_CUDA(cudaMemset(ctx->d_tab, 0, need * sizeof(BlockEntry)));
   GM_CUDA(cudaMemset(&ctx->d_st->tab_cells, 0, sizeof(int)));
+  // cudaMemset runs on the legacy default stream, which does NOT order with this ctx's non-blocking streams:
+  // without this the first kernels of the next call could run before (or while) the tables are cleared
+  GM_CUDA(cudaDeviceSynchronize());
   return GM_OK;
 }
 
@@ -295,10 +298,11 @@ gm_status ensure_block_table(gm_ctx* ctx) {
 gm_status next_epoch(gm_ctx* ctx, unsigned* out) {
   ctx->epoch = (ctx->epoch + 1) & TS_EPOCH_MASK;
   if (ctx->epoch == 0) {
-    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    GM_CUDA(cudaDeviceSynchronize());
     GM_CUDA(cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
     GM_CUDA(cudaMemset(ctx->d_state64_b, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
     if (ctx->d_dense_state) GM_CUDA(cudaMemset(ctx->d_dense_state, 0, ((size_t)div_up((long long)ctx->dense_cap, CPL_TILE) + 2) * sizeof(unsigned long long)));
+    GM_CUDA(cudaDeviceSynchronize());  // legacy-stream memsets do not order with the ctx's non-blocking streams
     ctx->epoch = 1;
   }
   *out = ctx->epoch;
@@ -465,6 +469,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
     ctx->gn_blocks = std::max(1, std::min(ctx->num_sms, per_sm * ctx->num_sms));
     if ((size_t)ctx->gn_blocks * 2 * GN_NV > kPartialsRegion) return fail(cudaErrorInvalidValue, "partials capacity");
   }
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "sync");  // the memsets above ran on the legacy stream
   ctx->grid = make_grid(ctx->prm, nullptr, nullptr);
   if (ensure_block_table(ctx) != GM_OK) { std::fprintf(stderr, "gm_create: %s\n", ctx->err.c_str()); gm_destroy(ctx); return GM_ERR_CUDA; }
   *out = ctx;
@@ -724,6 +729,7 @@ gm_status ensure_dense(gm_ctx* ctx, size_t range) {
   GM_CUDA(cudaMemset(ctx->d_dense_cnt, 0, range * sizeof(int)));
   GM_CUDA(cudaMemset(ctx->d_dense_id, 0, range * sizeof(int)));
   GM_CUDA(cudaMemset(ctx->d_dense_sum, 0, 3 * range * sizeof(long long)));
+  GM_CUDA(cudaDeviceSynchronize());  // legacy-stream memsets do not order with the ctx's non-blocking streams (this raced: zero centroids)
   ctx->dense_cap = range;
   return GM_OK;
 }
@@ -1502,7 +1508,7 @@ gm_status map_clear_device(gm_map* m) {
   if (cudaMemset(m->d_keys, 0xFF, m->n_slots * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(m->d_cnt, 0, m->n_slots * sizeof(int)) != cudaSuccess ||
       cudaMemset(m->d_sums, 0, 3 * m->n_slots * sizeof(long long)) != cudaSuccess ||
-      cudaMemset(m->d_st, 0, sizeof(MapState)) != cudaSuccess) { m->err = "cudaMemset"; return GM_ERR_CUDA; }
+      cudaMemset(m->d_st, 0, sizeof(MapState)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { m->err = "cudaMemset"; return GM_ERR_CUDA; }
   return GM_OK;
 }
 
@@ -1518,6 +1524,7 @@ gm_status map_dump(gm_map* m, MapDump* out, MapState* st_out) {
     cudaFree(dk); cudaFree(dc); cudaFree(ds); m->err = "cudaMalloc"; return GM_ERR_CUDA;
   }
   cudaMemset(m->d_cursor, 0, sizeof(int));
+  cudaDeviceSynchronize();
   if (V) k_map_export<<<std::min<unsigned long long>((m->n_slots + 255) / 256, (unsigned long long)m->num_sms * 16), 256>>>(
       m->d_keys, m->d_cnt, m->d_sums, m->n_slots, dk, dc, ds, (int)V, m->d_cursor);
   std::vector<unsigned long long> k(V); std::vector<int> c(V); std::vector<long long> su(3 * V);

@@ -261,6 +261,28 @@ def test_voxel_dense_tables_equal_sort_path(leaf, bound):
     _centroids_match(a[2]["centroids"], ref)
 
 
+def test_voxel_dense_tables_grow_on_demand():
+    """The dense VoxelGrid tables are (re)allocated when a parameter change needs a larger lattice; the very first
+    call after that must already be right (a legacy-stream memset once raced with the ctx's non-blocking stream and
+    left zero centroids: found by tools/fuzz_more.py)."""
+    pts = synth.curved_tunnel(3000, seed=3, outlier_frac=0.0)
+    with _ctx(len(pts), neighborRadius=1.1, voxelGridLeafSize=0.3, boxFilterBound=0.75) as ctx:
+        for leaf, bound in ((0.3, 0.75), (0.125, 5.0), (0.05, 5.0), (0.3, 0.75), (0.05, 5.0)):
+            ctx.set_params(capi.default_params(neighborRadius=1.1, voxelGridLeafSize=leaf, boxFilterBound=bound))
+            for rep in range(2):
+                ctx.upload_scan(pts)
+                ctx.crop()
+                ctx.normals()
+                ctx.voxel()
+                keys, assign, st = ctx.download_voxel_assignment()
+                vox = ctx.download_voxels()
+                ref = O.voxel(ctx.download_cloud(1), leaf)
+                assert np.array_equal(keys, ref["keys"]) and np.array_equal(assign, ref["assign"]), (leaf, bound, rep)
+                assert np.array_equal(vox["counts"], ref["voxel_counts"])
+                _centroids_match(vox["centroids"], ref)
+        assert ctx.counts().device_error == 0
+
+
 def test_voxel_fixed_nn_mode_indexes_compacted_cloud():
     pts = _scan_with_junk(30_000, seed=5)
     with _ctx(len(pts), neighborRadius=0.12, voxelGridLeafSize=0.2, nn_index_mode=1) as ctx:

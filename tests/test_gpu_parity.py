@@ -1002,6 +1002,47 @@ def test_fuzz_small_clouds_every_exact_output(seed):
             assert ctx.counts().device_error == 0, tag
 
 
+# ---- scans in flight: the way bench.py measures throughput ------------------------------------------------------
+def test_three_contexts_in_flight_give_the_single_context_results():
+    """Three contexts fed round robin without waiting (their kernels overlap on the GPU, as in bench.py's throughput
+    measurement): every scan's results are bit-identical to the same scan processed alone."""
+    n, rounds = 70_000, 4
+    scans = [synth.curved_tunnel(n, seed=300 + k) for k in range(3)]
+
+    def snapshot(ctx):
+        keys, assign, _ = ctx.download_voxel_assignment()
+        vox = ctx.download_voxels()
+        return (ctx.download_cloud(1), ctx.download_normals(1), keys, vox["centroids"], vox["nn_index"],
+                ctx.download_hypotheses(0, 256)[2], ctx.download_hypotheses(1, 256)[2], ctx.download_labels(),
+                ctx.model(0)["coef"], ctx.model(1)["coef"], ctx.download_polyline())
+
+    params = dict(neighborRadius=0.12, voxelGridLeafSize=0.1)
+    alone, samples = [], []
+    with _ctx(n, **params) as ctx:
+        for k in range(3):
+            ctx.upload_scan(scans[k]); ctx.crop(); ctx.normals()
+            nv = ctx.counts().n_valid
+            samples.append((synth.sample_indices(nv, 256, 3, seed=3 + k), synth.sample_indices(nv, 256, 2, seed=4 + k)))
+            ctx.upload_scan(scans[k])
+            ctx.process_scan(*samples[k])
+            alone.append(snapshot(ctx))
+    ctxs = [_ctx(n, **params) for _ in range(3)]
+    try:
+        for r in range(rounds):
+            for k in range(3):                       # enqueue on all three without synchronising
+                c = ctxs[(k + r) % 3]
+                c.upload_scan(scans[k])
+                c.process_scan(*samples[k])
+            for k in range(3):
+                got = snapshot(ctxs[(k + r) % 3])
+                for a, b in zip(got, alone[k]):
+                    assert np.array_equal(np.asarray(a).view(np.uint8), np.asarray(b).view(np.uint8)), (r, k)
+        assert all(c.counts().device_error == 0 for c in ctxs)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 # ---- map slabs (SURVEY 8e / config C4) ---------------------------------------------------------------
 def test_map_slabs_reproduce_the_whole_map():
     """A map cut into 3 slabs at voxel faces, each processed with a halo on its own context, gives for

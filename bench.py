@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--map-points", type=int, default=10_000_000, help="points of the aggregated-map leg (configs[4]); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-points", type=int, default=0, help="points of the CPU baseline sample (0 = full scan)")
+    ap.add_argument("--knn", type=int, default=0, help="k-nearest-neighbour normals with this k instead of the radius search (0 = radius)")
     return ap.parse_args()
 
 
@@ -60,69 +61,102 @@ def workload_name(a):
             f"cylinder hypotheses, r={a.radius} leaf={a.leaf} tau={TAU}")
 
 
+def workload_config(a):
+    """The `config` object: identical in both arms (b200 and --impl reference), it names the workload only."""
+    return {"workload": workload_name(a), "points_per_scan": a.points, "plane_hypotheses": a.hyp // 2,
+            "cylinder_hypotheses": a.hyp - a.hyp // 2, "radius_m": a.radius, "leaf_m": a.leaf, "tau_m": TAU,
+            "refit_iterations": a.refit_iters, "scans": f"ring of {RING} distinct seeded scans (seeds 2..{1 + RING}) cycled",
+            "l2": f"inputs larger than L2: the ring holds {RING * a.points * 16 / 1e6:.0f} MB of scans, one step = the next scan of the ring"}
+
+
+def host_threads() -> int:
+    """Threads the CPU arm uses: every core this process may run on (torchrun forces OMP_NUM_THREADS=1, which must not
+    decide it: the count is passed to the oracle explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle's restatement of the reference path, stage by stage (used by cpu_baseline
-# and --impl reference; never by the product)
-def cpu_process_scan(O, pts, a, ps, cs, nthreads):
-    cropped, _ = O.crop(pts, 5.0, True)
-    nr, _, _ = O.normals(cropped, a.radius, mode=0, order=0, nthreads=nthreads)
-    cloud, nrm, _ = O.compact(cropped, nr)
-    vox = O.voxel(cloud, a.leaf)
-    O.nn1_grid(vox["centroids"], cropped, a.radius * 1.001, nthreads=nthreads)
-    fr = O.local_frame(nrm, 0.2)
-    out = {"n_valid": len(cloud), "V": vox["V"]}
-    if ps is not None and len(ps):
-        ps = np.minimum(ps, max(len(cloud) - 1, 0))
-        coef, valid = O.plane_hypotheses(cloud, ps)
-        counts = O.count_plane(cloud, coef, valid, TAU, nthreads=nthreads)
-        b = O.argmax(counts)
-        plane, _ = O.refit_plane(cloud, coef[b], TAU) if b >= 0 else (None, 0)
-    else:
-        plane = None
-    if cs is not None and len(cs):
-        cs = np.minimum(cs, max(len(cloud) - 1, 0))
-        m7, t12, cvalid = O.cyl_hypotheses(cloud, nrm, cs, 0.5, 10.0, TAU)
-        counts = O.count_cyl(cloud, t12, cvalid, nthreads=nthreads)
-        b = O.argmax(counts)
-        cyl = O.refit_cylinder(cloud, m7[b], t12[b], 5)[0] if b >= 0 else None
-    else:
-        cyl = None
-    lab = O.labels(cloud, plane, TAU, None if cyl is None else O.cyl_test_params(cyl, TAU)[0])
-    O.polyline(cloud, nrm, lab, 2, fr["vecs"][:, 0], 0.2, 1.0, 256)
-    return out
+# CPU arm: the oracle's restatement of the reference path, the oracle ALONE from raw points (oracle/chain.py;
+# used by cpu_baseline and --impl reference, never by the product)
+def cpu_process_scan(pts, a, ps, cs, nthreads):
+    from oracle import chain
+
+    f = chain.front(pts, bound=5.0, radius=a.radius, leaf=a.leaf, wf=0.2, nthreads=nthreads, knn=a.knn)
+    nv = f["n_valid"]
+    ps = None if ps is None else (ps % max(nv, 1)).astype(np.int32)   # same rule as the GPU arm (ring_samples)
+    cs = None if cs is None else (cs % max(nv, 1)).astype(np.int32)
+    b = chain.back(f, ps, cs, tau=TAU, refit_iters=a.refit_iters, nthreads=nthreads)
+    return f, b
+
+
+def ring_scan(a, s, rank=0):
+    from geometric_mapping_b200 import synth
+
+    return synth.curved_tunnel(a.points, seed=2 + s + 1000 * rank, advance=0.0)
+
+
+def ring_samples(a, s, n_valid=None, hyp=None):
+    """Injected RANSAC sample indices of ring scan s: Philox(seed) draws over the INPUT size, reduced modulo the compacted
+    size of the scan once that is known (n_valid): both arms apply the same rule, so they test the same hypotheses."""
+    from geometric_mapping_b200 import synth
+
+    hyp = a.hyp if hyp is None else hyp
+    ps, cs = synth.sample_indices(a.points, hyp // 2, 3, seed=3 + s), synth.sample_indices(a.points, hyp - hyp // 2, 2, seed=4 + s)
+    if n_valid is not None:
+        ps, cs = (ps % max(n_valid, 1)).astype(np.int32), (cs % max(n_valid, 1)).astype(np.int32)
+    return ps, cs
 
 
 def run_reference(a, rank):
-    """CPU arm: the oracle on all host threads.  A step is a BOUNDED SAMPLE of the workload: a 1 m slab
-    (|x| < 0.5 m, ~1/10 of the points) of the same 1M-point scan, i.e. the same point density, neighbour
-    counts and hypothesis count per point as the full scan, so points/s is comparable."""
+    """CPU arm: the oracle on all host threads, on the SAME workload as the GPU arm: the same ring of full scans, the
+    same hypothesis counts (sample indices drawn with the same seeds from each scan's own compacted size).  A step is
+    one whole scan; when a step takes so long that K steps would not end within a few minutes the run is cut short and
+    `steps` reports what was timed."""
     if rank != 0:
         return
-    from geometric_mapping_b200 import synth
     from oracle import oracle as O
 
-    threads = O.num_threads()
-    full = synth.curved_tunnel(a.points, seed=2)
-    pts = np.ascontiguousarray(full[np.abs(full[:, 0]) < 0.5])
-    n = len(pts)
-    ps = synth.sample_indices(int(0.9 * n), a.hyp // 2, 3, seed=3)
-    cs = synth.sample_indices(int(0.9 * n), a.hyp - a.hyp // 2, 2, seed=4)
-    for _ in range(min(max(a.warmup, 1), 3)):
-        cpu_process_scan(O, pts, a, ps, cs, threads)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        cpu_process_scan(O, pts, a, ps, cs, threads)
-    dt = time.perf_counter() - t0
-    v = n * a.steps / dt
+    threads = host_threads()
+    budget_s = float(os.environ.get("GM_REF_BUDGET_S", "150"))
+    scans, smp = {}, {}
+
+    def get(i):
+        s = i % RING
+        if s not in scans:
+            scans[s] = ring_scan(a, s)
+            smp[s] = ring_samples(a, s)  # reduced modulo n_valid inside cpu_process_scan
+        return scans[s], smp[s]
+
+    nwarm = min(max(a.warmup, 1), 2)
+    for i in range(nwarm):
+        pts, (ps, cs) = get(i)
+        cpu_process_scan(pts, a, ps, cs, threads)
+    for i in range(a.steps):  # generate the ring outside the timed region
+        if i < RING:
+            get(i)
+    done, dt = 0, 0.0
+    for i in range(a.steps):
+        pts, (ps, cs) = get(i)
+        t0 = time.perf_counter()
+        cpu_process_scan(pts, a, ps, cs, threads)
+        dt += time.perf_counter() - t0
+        done += 1
+        if dt > budget_s:
+            break
+    v = a.points * done / dt
     line = {
         "impl": "reference", "metric": "input points/s, per-scan segmentation+fit", "value": v, "unit": "points/s",
-        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+        "n_gpus": a.gpus, "steps": done, "warmup": nwarm, "ms_per_step": 1e3 * dt / done,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "l2": "host"},
+        "config": workload_config(a),
         "cpu_baseline": {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"per step: the {n}-point slab |x| < 0.5 m of the {a.points}-point scan (same density), full "
-                                   f"path; OpenMP over points (normals, 1-NN) and hypotheses (counting), serial elsewhere; "
-                                   f"parity unpinned"},
+                         "sample": f"{done} full scans of {a.points} points (the GPU arm's ring, same seeds and hypothesis counts), whole path "
+                                   f"from raw points on the oracle alone; OpenMP with {threads} threads over points (normals, 1-NN) and "
+                                   f"hypotheses (counting), serial elsewhere; steps requested {a.steps}, time budget {budget_s:.0f} s; "
+                                   f"parity unpinned (the reference cannot be built here: PCL/Eigen/ROS absent)"},
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -264,7 +298,7 @@ def main():
     # ---- synthetic ring of scans: distinct per slot and per rank (frame-parallel = weak scaling)
     host_scans, dev_scans = [], []
     for s in range(RING):
-        pts = synth.curved_tunnel(n, seed=2 + s + 1000 * rank, advance=0.0)
+        pts = ring_scan(a, s, rank)
         hp = torch.from_numpy(pts).pin_memory()
         host_scans.append(hp)
         dev_scans.append(hp.to(dev, non_blocking=False))
@@ -283,7 +317,7 @@ def main():
         n_valid.append(nv)
         if s < 2:
             nbr_sum.append(ctx.search_stats())
-        samples.append((synth.sample_indices(nv, Hp, 3, seed=3 + s), synth.sample_indices(nv, Hc, 2, seed=4 + s)))
+        samples.append(ring_samples(a, s, nv))
 
     def step(i):
         s = i % RING
@@ -358,8 +392,7 @@ def main():
     value = world * n * a.steps / (ms * 1e-3)
     # the same throughput measurement at the north-star's hypothesis count (2048 plane + 2048 cylinder)
     H4 = 4096
-    samples4 = [(synth.sample_indices(n_valid[s], H4 // 2, 3, seed=30 + s), synth.sample_indices(n_valid[s], H4 // 2, 2, seed=40 + s))
-                for s in range(RING)]
+    samples4 = [ring_samples(a, s, n_valid[s], hyp=H4) for s in range(RING)]
 
     def tstep4(i):
         s, cx = i % RING, tctx[i % NFLIGHT]
@@ -494,7 +527,14 @@ def main():
     roofline["dominant_segment"] = dominant
 
     # ---- end to end through the C-ABI with host buffers (NCTX contexts pipelined) --------------------
+    # Per step: H2D of the scan from pinned memory as 12-byte xyz records (what a PointCloud2 of x,y,z float32 carries;
+    # gathered to PointXYZ on the device), the whole per-scan path, and D2H of everything cloud_cb publishes
+    # (src/geometric_mapping.cpp:100-117): the cropped + compacted cloud (cloudOutput), the voxel centroids and their
+    # 1-NN normals (normalsOutput markers), the frame (eigenBasisOutput), plus the builder-defined results
+    # (models, labels, polyline) -- all through gm_fetch_async into pinned buffers.
     NCTX = int(os.environ.get("GM_E2E_CONTEXTS", "4"))
+    host_xyz = [torch.from_numpy(np.ascontiguousarray(h.numpy()[:, :3])).pin_memory() for h in host_scans]
+    VCAP = 1 << 17
     ectx, outs, keep = [], [], []
     for k in range(NCTX):
         cx = capi.Context(params, max_points=n, max_hypotheses=4096)
@@ -503,41 +543,52 @@ def main():
         cloud = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         labels = torch.empty(n, dtype=torch.uint8).pin_memory()
         slices = torch.empty(256 * C.sizeof(capi.gm_slice), dtype=torch.uint8).pin_memory()
-        keep.append((summ, cloud, labels, slices))
+        cen = torch.empty((VCAP, 4), dtype=torch.float32).pin_memory()
+        nnn = torch.empty((VCAP, 8), dtype=torch.float32).pin_memory()
+        keep.append((summ, cloud, labels, slices, cen, nnn))
         o = capi.gm_host_outputs()
         o.summary = summ.data_ptr()
         o.cloud_xyzw, o.cloud_capacity = cloud.data_ptr(), n
         o.labels, o.labels_capacity = labels.data_ptr(), n
         o.slices, o.slices_capacity = slices.data_ptr(), 256
+        o.centroids_xyzw, o.nn_normal8, o.voxel_capacity = cen.data_ptr(), nnn.data_ptr(), VCAP
         outs.append(o)
-    h2d = n * 16
-    d2h = C.sizeof(capi.gm_scan_summary) + n * 16 + n + 256 * C.sizeof(capi.gm_slice)
+    vfetch = min(n, VCAP)
+    h2d = n * 12
+    d2h = C.sizeof(capi.gm_scan_summary) + n * 16 + n + 256 * C.sizeof(capi.gm_slice) + vfetch * 48
 
-    def e2e_step(i):
-        k, s = i % NCTX, i % RING
-        cx = ectx[k]
-        cx.synchronize()  # results of the scan this context processed 3 steps ago are now on the host
-        cx.upload_scan_raw(host_scans[s].data_ptr(), n, 16)
-        cx.process_scan(samples[s][0], samples[s][1])
-        cx.fetch_async(outs[k])
+    def run_e2e(smp, steps):
+        def e2e_step(i):
+            k, s = i % NCTX, i % RING
+            cx = ectx[k]
+            cx.synchronize()  # results of the scan this context processed NCTX steps ago are now on the host
+            cx.upload_pointcloud2_raw(host_xyz[s].data_ptr(), n, 12, 0, 4, 8)
+            cx.process_scan(smp[s][0], smp[s][1])
+            cx.fetch_async(outs[k])
 
-    for i in range(max(a.warmup, 3)):
-        e2e_step(i)
-    for cx in ectx:
-        cx.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        e2e_step(i)
-    for cx in ectx:
-        cx.synchronize()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    if world > 1:
-        dist.barrier()
+        for i in range(max(a.warmup, 3)):
+            e2e_step(i)
+        for cx in ectx:
+            cx.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            e2e_step(i)
+        for cx in ectx:
+            cx.synchronize()
+        torch.cuda.synchronize()
+        secs = max_over_ranks(time.perf_counter() - t0)
+        if world > 1:
+            dist.barrier()
+        last = capi.gm_scan_summary.from_buffer_copy(bytes(keep[(steps - 1) % NCTX][0].numpy()))
+        assert last.counts.n_input == n and last.counts.device_error == 0 and last.counts.n_voxels <= VCAP
+        return secs
+
+    e2e_s = run_e2e(samples, a.steps)
     e2e_value = world * n * a.steps / e2e_s
-    last = capi.gm_scan_summary.from_buffer_copy(bytes(keep[(a.steps - 1) % NCTX][0].numpy()))
-    assert last.counts.n_input == n and last.counts.device_error == 0
+    e2e4_s = run_e2e(samples4, steps4)
+    h4096["e2e_points_per_s"] = world * n * steps4 / e2e4_s
+    h4096["e2e_ms_per_step"] = 1e3 * e2e4_s / steps4
 
     # ---- hypothesis-sharded RANSAC leg (configs[2]) ----------------------------------------------
     ransac = None
@@ -673,33 +724,70 @@ def main():
                            f"cylinder per slab ({Hp}+{Hc} hypotheses each), VoxelGrid on the all-reduced global lattice; strong scaling"}
         mctx.close()
 
-    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
-    cpu = None
+    # ---- CPU baseline + parity of the same scan (rank 0, N=1 only) --------------------------------------
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        from oracle import oracle as O
+        from oracle import chain
         ncpu = a.cpu_points or n
         cp = np.ascontiguousarray(host_scans[0].numpy()[:ncpu])
+        raw_ps, raw_cs = ring_samples(a, 0)
         t0 = time.perf_counter()
-        cpu_process_scan(O, cp, a, samples[0][0], samples[0][1], 1)
+        of, ob = cpu_process_scan(cp, a, raw_ps, raw_cs, 1)
         dt = time.perf_counter() - t0
         cpu = {"value": ncpu / dt, "unit": "points/s", "cores": 1, "kind": "port",
-               "sample": f"1 scan of {ncpu} points, full path, single thread as the reference is "
-                         f"(serial pcl::NormalEstimation + ros::spin); host has {os.cpu_count()} cores; parity unpinned",
+               "sample": f"1 scan of {ncpu} points (ring scan 0), whole path from raw points on the oracle alone, single thread as the "
+                         f"reference is (serial pcl::NormalEstimation + ros::spin); host has {host_threads()} usable cores; "
+                         f"parity unpinned",
                "seconds": dt}
+        # the CUDA path on the same raw points and sample indices, against that oracle run (never timed)
+        parity = {}
+        ps0, cs0 = ring_samples(a, 0, of["n_valid"])
+        for mode, name in ((1, "canonical"), (0, "fast")):
+            with capi.Context(params, max_points=ncpu, max_hypotheses=4096) as pc:
+                pc.set_normals_mode(mode)
+                if a.knn:
+                    pc.set_knn(a.knn)
+                pc.upload_scan(cp)
+                pc.process_scan(ps0, cs0)
+                gc_ = pc.counts()
+                gp_, gy_ = pc.model(0), pc.model(1)
+                gn_ = pc.download_normals(0)
+                _, _, gpc = pc.download_hypotheses(0, len(ps0))
+                _, _, gcc = pc.download_hypotheses(1, len(cs0))
+                gfr = pc.frame()
+            parity[name] = {
+                "n_cropped_equal": gc_.n_cropped == of["n_cropped"], "n_valid_equal": gc_.n_valid == of["n_valid"],
+                "V_equal": gc_.n_voxels == of["vox"]["V"],
+                "normals_bit_identical": bool(np.array_equal(gn_.view(np.uint32), of["normals"].view(np.uint32))),
+                "plane_counts_equal": bool(np.array_equal(gpc, ob["plane_counts"])),
+                "cyl_counts_equal": bool(np.array_equal(gcc, ob["cyl_counts"])),
+                "plane_best_equal": gp_["best_id"] == ob["plane_best"], "cyl_best_equal": gy_["best_id"] == ob["cyl_best"],
+                "plane_best": [gp_["best_id"], gp_["best_count"]], "cyl_best": [gy_["best_id"], gy_["best_count"]],
+                "oracle_plane_best": [int(ob["plane_best"]), int(ob["plane_counts"][ob["plane_best"]])],
+                "oracle_cyl_best": [int(ob["cyl_best"]), int(ob["cyl_counts"][ob["cyl_best"]])],
+                "eigenvalue_rel_diff": float(np.abs(gfr["vals"] - of["frame"]["vals"]).max() / np.abs(of["frame"]["vals"]).max()),
+                "plane_refit_abs_diff": float(np.abs(gp_["coef"] - ob["plane_refit"]).max()),
+                "cyl_refit_abs_diff": float(np.abs(gy_["coef"] - ob["cyl_refit"]).max()),
+            }
+        parity["note"] = ("CUDA path vs the oracle ALONE from the same raw points and sample indices; canonical = "
+                          "gm_set_normals_mode(1) (FLANN summation order, every integer output must be equal), fast = the timed default "
+                          "(neighbour sets equal, float sums differ by rounding, so cylinder counts may move)")
 
     if rank == 0:
         line = {
             "metric": "input points/s, per-scan segmentation+fit", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "parallelism": f"frame-parallel x{world}" if world > 1 else "1 GPU",
-                       "l2": f"inputs larger than L2: ring of {RING} distinct resident scans ({RING * n * 16 / 1e6:.0f} MB) cycled",
-                       "in_flight": f"{NFLIGHT} scans in flight (one context + CUDA stream each); single-scan latency in latency_ms_per_scan",
-                       "mean_valid_points": M, "voxels": int(V)},
+            "config": workload_config(a),
+            "run": {"parallelism": f"frame-parallel x{world} (each rank cycles its own ring of scans)" if world > 1 else "1 GPU",
+                    "in_flight": f"{NFLIGHT} scans in flight (one context + CUDA stream each); single-scan latency in latency_ms_per_scan",
+                    "mean_valid_points": M, "voxels": int(V)},
             "latency_ms_per_scan": latency_ms,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / a.steps, "pipeline": f"{NCTX} contexts / streams, pinned host buffers",
+                    "ms_per_step": 1e3 * e2e_s / a.steps,
+                    "pipeline": f"{NCTX} contexts / streams, pinned host buffers; up: 12-byte xyz records (gm_upload_pointcloud2); down: "
+                                f"summary, compacted cloud (16 B/pt), labels, polyline, voxel centroids + 1-NN normals",
                     "numa_node_rank0": numa_node},
             "gpu_launches": int(launches),
             "roofline": roofline,
@@ -711,6 +799,7 @@ def main():
             "compress": compress,
             "map_slabs": map_leg,
             "cpu_baseline": cpu,
+            "parity": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

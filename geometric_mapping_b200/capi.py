@@ -127,7 +127,7 @@ SYMBOLS = [
     "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode", "gm_set_grid_box", "gm_set_owned_range", "gm_get_voxel_bbox", "gm_set_voxel_bbox",
     "gm_get_search_stats", "gm_set_voxel_mode", "gm_ransac_pair", "gm_ransac_select_pair", "gm_ransac_export_keys",
     "gm_ransac_import_keys", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
-    "gm_map_load", "gm_map_leaf",
+    "gm_map_load", "gm_map_leaf", "gm_set_normals_mode",
 ]
 
 
@@ -198,6 +198,7 @@ def _lib():
         "gm_ransac_export_key": (i32, [vp, i32, vp]),
         "gm_ransac_import_key": (i32, [vp, i32, vp]),
         "gm_set_count_mode": (i32, [vp, i32]),
+        "gm_set_normals_mode": (i32, [vp, i32]),
         "gm_set_grid_box": (i32, [vp, vp, vp]),
         "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
         "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
@@ -308,6 +309,11 @@ class Context:
         """0 = tile-culled inlier counting (default), 1 = brute-force FP32 kernels; identical counts."""
         self._ck(_lib().gm_set_count_mode(self._h, mode), "gm_set_count_mode")
 
+    def set_normals_mode(self, mode: int):
+        """0 = neighbourhood sums in grid order (fast, default); 1 = in FLANN's (d2, index) order: normals bit-identical
+        to the CPU oracle (verification mode, slow)."""
+        self._ck(_lib().gm_set_normals_mode(self._h, mode), "gm_set_normals_mode")
+
     def set_grid_box(self, mn=None, mx=None):
         """Neighbour grid over [mn, mx] instead of the crop cube (map slabs); None clears."""
         if mn is None:
@@ -367,6 +373,10 @@ class Context:
         raw = np.ascontiguousarray(data, dtype=np.uint8)
         self._keepalive = raw
         self._ck(_lib().gm_upload_pointcloud2(self._h, _ptr(raw), n, point_step, offset_x, offset_y, offset_z), "gm_upload_pointcloud2")
+
+    def upload_pointcloud2_raw(self, host_ptr: int, n: int, point_step: int, offset_x: int, offset_y: int, offset_z: int):
+        """Same from a raw host address (e.g. a pinned torch tensor); the caller keeps the buffer alive."""
+        self._ck(_lib().gm_upload_pointcloud2(self._h, C.c_void_p(host_ptr), n, point_step, offset_x, offset_y, offset_z), "gm_upload_pointcloud2")
 
     def set_scan_device(self, device_ptr: int, n: int):
         self._ck(_lib().gm_set_scan_device(self._h, C.c_void_p(device_ptr), n), "gm_set_scan_device")

@@ -112,6 +112,7 @@ struct gm_ctx {
   unsigned long long* d_dense_state = nullptr;  // look-back tile states of the scan over the tables
   size_t dense_cap = 0;
   int voxel_mode = 0;  // 0 = dense tables when the key range fits, 1 = always sort
+  int normals_mode = 0;  // 0 = neighbours summed in cell-run order (fast), 1 = in FLANN's (d2, index) order (bit-identical to the oracle)
   BlockEntry* d_tab = nullptr;  // dense block table of the neighbour grid (1 << (key_bits - 6) entries)
   size_t tab_entries = 0;
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
@@ -459,6 +460,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   { const char* env = std::getenv("GM_SERIAL"); ctx->concurrent = !(env && env[0] == '1'); }
   { const char* env = std::getenv("GM_COUNT_MODE"); ctx->count_mode = (env && env[0] == '1') ? 1 : 0; }
   { const char* env = std::getenv("GM_VOXEL_MODE"); ctx->voxel_mode = (env && env[0] == '1') ? 1 : 0; }
+  { const char* env = std::getenv("GM_NORMALS_MODE"); ctx->normals_mode = (env && env[0] == '1') ? 1 : 0; }
 
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned))) != cudaSuccess) return fail(e, "memset");
@@ -572,6 +574,12 @@ gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream) {
 gm_status gm_set_voxel_mode(gm_ctx* ctx, int32_t mode) {
   if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
   ctx->voxel_mode = mode;
+  return GM_OK;
+}
+
+gm_status gm_set_normals_mode(gm_ctx* ctx, int32_t mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  ctx->normals_mode = mode;
   return GM_OK;
 }
 
@@ -690,11 +698,16 @@ gm_status gm_normals(gm_ctx* ctx) {
               g.sentinel, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_tab, ctx->d_state64, epoch, ctx->d_st);
     GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_ucell_key,
               ctx->d_ucell_start, ctx->d_tab, ctx->d_st, g, ctx->d_runs, ctx->d_cell_nruns); }
-    float rf = (float)ctx->prm.neighborRadius;
-    float r2 = rf * rf;
+    // pcl::KdTreeFLANN::radiusSearch hands FLANN static_cast<float>(radius * radius), the product taken in double
+    const float r2 = (float)(ctx->prm.neighborRadius * ctx->prm.neighborRadius);
     { SegTimer seg_(ctx, SEG_NORMALS);
-      GM_LAUNCH(ctx, k_normals, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
-                ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st); }
+      if (ctx->normals_mode == 1) {
+        GM_LAUNCH(ctx, k_normals<1>, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
+                  ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st);
+      } else {
+        GM_LAUNCH(ctx, k_normals<0>, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
+                  ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st);
+      } }
     if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_COMPACT);
       GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,

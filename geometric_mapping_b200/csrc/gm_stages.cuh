@@ -148,6 +148,11 @@ __global__ void k_decode_pointcloud2(const unsigned char* __restrict__ raw, int 
   const unsigned char* p = raw + (size_t)i * point_step;
   float v[3];
   const int off[3] = {ox, oy, oz};
+  if (((point_step | ox | oy | oz) & 3) == 0) {  // aligned records (the usual case: x,y,z,(intensity,ring) float32 fields)
+    const float* f = reinterpret_cast<const float*>(p);
+    out[i] = make_float4(f[ox >> 2], f[oy >> 2], f[oz >> 2], 1.0f);
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {  // byte-wise: fields need not be 4-byte aligned inside the record
     unsigned u = (unsigned)p[off[k]] | ((unsigned)p[off[k] + 1] << 8) | ((unsigned)p[off[k] + 2] << 16) | ((unsigned)p[off[k] + 3] << 24);
@@ -338,6 +343,69 @@ __global__ void k_cell_runs(const unsigned* __restrict__ ucell_key, const int* _
   }
 }
 
+// ---- libm-independent atan2 / sin / cos for pcl::computeRoots ---------------------------------------
+// pcl::computeRoots calls std::atan2 / std::cos / std::sin on floats; their last bit depends on the libm.
+// Here they are evaluated in double with only + - * / sqrt in a fixed order (no contraction: -fmad=false) and
+// rounded to float once: accurate to ~1e-16 before rounding, hence the correctly rounded float value, on any
+// IEEE-754 machine.  The CPU oracle evaluates the same operation sequence, so given bit-identical covariance
+// matrices the normals are bit-identical (gm_set_normals_mode(1) provides that accumulation order).
+__device__ __forceinline__ double d_atan_unit(double t) {  // t in [0,1]
+  const double t1 = t / (1.0 + sqrt(1.0 + t * t));
+  const double t2 = t1 / (1.0 + sqrt(1.0 + t1 * t1));
+  const double z2 = t2 * t2;
+  double p = 1.0 / 27.0;
+  p = p * z2 - 1.0 / 25.0; p = p * z2 + 1.0 / 23.0; p = p * z2 - 1.0 / 21.0; p = p * z2 + 1.0 / 19.0;
+  p = p * z2 - 1.0 / 17.0; p = p * z2 + 1.0 / 15.0; p = p * z2 - 1.0 / 13.0; p = p * z2 + 1.0 / 11.0;
+  p = p * z2 - 1.0 / 9.0;  p = p * z2 + 1.0 / 7.0;  p = p * z2 - 1.0 / 5.0;  p = p * z2 + 1.0 / 3.0;
+  p = 1.0 - p * z2;
+  return 4.0 * (t2 * p);
+}
+__device__ __forceinline__ float d_atan2f_pos(float yf, float xf) {  // y >= +0
+  const double PI = 3.14159265358979323846, HALF_PI = 1.57079632679489661923;
+  if (isnan(yf) || isnan(xf)) return CUDART_NAN_F;
+  const double y = yf, x = fabs((double)xf);
+  const bool neg = signbit(xf);
+  double a;
+  if (y == 0.0 && x == 0.0) a = 0.0;
+  else if (x >= y) a = d_atan_unit(y / x);
+  else a = HALF_PI - d_atan_unit(x / y);
+  if (neg) a = PI - a;
+  return (float)a;
+}
+__device__ __forceinline__ float d_sinf_small(float xf) {  // x in [0, pi/3]
+  const double x = xf, x2 = x * x;
+  double p = -1.0 / 25852016738884976640000.0;
+  p = p * x2 + 1.0 / 51090942171709440000.0;
+  p = p * x2 - 1.0 / 121645100408832000.0;
+  p = p * x2 + 1.0 / 355687428096000.0;
+  p = p * x2 - 1.0 / 1307674368000.0;
+  p = p * x2 + 1.0 / 6227020800.0;
+  p = p * x2 - 1.0 / 39916800.0;
+  p = p * x2 + 1.0 / 362880.0;
+  p = p * x2 - 1.0 / 5040.0;
+  p = p * x2 + 1.0 / 120.0;
+  p = p * x2 - 1.0 / 6.0;
+  p = p * x2 + 1.0;
+  return (float)(x * p);
+}
+__device__ __forceinline__ float d_cosf_small(float xf) {
+  const double x = xf, x2 = x * x;
+  double p = 1.0 / 620448401733239439360000.0;
+  p = p * x2 - 1.0 / 1124000727777607680000.0;
+  p = p * x2 + 1.0 / 2432902008176640000.0;
+  p = p * x2 - 1.0 / 6402373705728000.0;
+  p = p * x2 + 1.0 / 20922789888000.0;
+  p = p * x2 - 1.0 / 87178291200.0;
+  p = p * x2 + 1.0 / 479001600.0;
+  p = p * x2 - 1.0 / 3628800.0;
+  p = p * x2 + 1.0 / 40320.0;
+  p = p * x2 - 1.0 / 720.0;
+  p = p * x2 + 1.0 / 24.0;
+  p = p * x2 - 1.0 / 2.0;
+  p = p * x2 + 1.0;
+  return (float)p;
+}
+
 // ---- pcl::eigen33 smallest eigenpair, float (common/impl/eigen.hpp) -------------
 __device__ __forceinline__ void d_compute_roots2(float b, float c, float roots[3]) {
   roots[0] = 0.0f;
@@ -366,9 +434,8 @@ __device__ void d_compute_roots(float m00, float m01, float m02, float m11, floa
     float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
     if (q > 0.0f) q = 0.0f;
     float rho = sqrtf(-a_over_3);
-    float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
-    float sin_theta, cos_theta;
-    sincosf(theta, &sin_theta, &cos_theta);
+    const float theta = d_atan2f_pos(sqrtf(-q), half_b) * s_inv3;
+    const float cos_theta = d_cosf_small(theta), sin_theta = d_sinf_small(theta);
     roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
     roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
     roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
@@ -417,6 +484,33 @@ __device__ void d_eigen33_smallest(float c00, float c01, float c02, float c11, f
 // box of the surviving points of every 32-point leaf (= one warp here): leaf_bounds[2*leaf] = min,
 // [2*leaf+1] = max; an empty leaf has min = +inf, max = -inf.
 constexpr int NRM_BLOCK = 128;
+
+// single-pass mean + covariance from the 9 sums (pcl::computeMeanAndCovarianceMatrix), eigen33, curvature and
+// flipNormalTowardsViewpoint(0,0,0) (A.4): the operation order of the oracle, op for op
+__device__ __forceinline__ void d_normal_from_sums(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7, float a8,
+                                                   int cnt, const float4 p, float4& o0, float4& o1) {
+  const float c = (float)cnt;
+  a0 /= c; a1 /= c; a2 /= c; a3 /= c; a4 /= c; a5 /= c; a6 /= c; a7 /= c; a8 /= c;
+  const float c00 = a0 - a6 * a6, c01 = a1 - a6 * a7, c02 = a2 - a6 * a8;
+  const float c11 = a3 - a7 * a7, c12 = a4 - a7 * a8, c22 = a5 - a8 * a8;
+  float ev, nx, ny, nz;
+  d_eigen33_smallest(c00, c01, c02, c11, c12, c22, ev, nx, ny, nz);
+  const float eig_sum = c00 + c11 + c22;
+  const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+  const float vx = 0.0f - p.x, vy = 0.0f - p.y, vz = 0.0f - p.z;
+  const float cos_theta = vx * nx + vy * ny + vz * nz;
+  if (cos_theta < 0.0f) { nx *= -1.0f; ny *= -1.0f; nz *= -1.0f; }
+  o0 = make_float4(nx, ny, nz, 0.f);
+  o1 = make_float4(curv, 0.f, 0.f, 0.f);
+}
+
+// MODE 0 (default): neighbours are accumulated in cell-run order as they are found (fast; the sums differ from the
+//   oracle's by float rounding only -- the neighbour SET and count are exact).
+// MODE 1 (gm_set_normals_mode(1), verification): neighbours are accumulated in FLANN's result order, ascending
+//   (d2, index) -- the order pcl::NormalEstimation sums them in -- by repeated selection of the next smallest pair
+//   over the same candidate runs (O(neighbours x candidates): ~40x slower, no scratch memory).  With the
+//   libm-independent eigen33 above the normals are then bit-identical to the CPU oracle's.
+template <int MODE>
 __global__ void __launch_bounds__(NRM_BLOCK)
 k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs, const int2* __restrict__ cell_info,
           const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count,
@@ -436,55 +530,71 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
     const int2 info = cell_info[cid];
     const int nr = info.x, total = info.y;
     ncand = total;
-    // accumulators as f32x2 pairs: (xx,xy) (xz,yz) (x,y) (z,count); yy and zz stay scalar.  The count is
-    // carried as a float (exact below 2^24 neighbours) so that it shares an instruction with the z sum.
-    u64 a01 = 0ull, a24 = 0ull, a67 = 0ull, a8c = 0ull;
-    float a3 = 0.f, a5 = 0.f;
-    // ONE flat loop over the candidates of all runs (not a loop over runs with a loop over candidates
-    // inside): lanes of a warp are points of neighbouring cells whose run lists differ, and the warp
-    // pays max-over-lanes of the TOTAL candidate count instead of the sum of per-run maxima.
-    // The next run is fetched one switch ahead so the switch itself does not wait on memory.  A hit
-    // adds the candidate, a miss adds +0 (masked operands, no branch): same sums as a skipped add.
-    int k = 0, t = 0, end = 0;
-    int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
+    if (MODE == 0) {
+      // accumulators as f32x2 pairs: (xx,xy) (xz,yz) (x,y) (z,count); yy and zz stay scalar.  The count is
+      // carried as a float (exact below 2^24 neighbours) so that it shares an instruction with the z sum.
+      u64 a01 = 0ull, a24 = 0ull, a67 = 0ull, a8c = 0ull;
+      float a3 = 0.f, a5 = 0.f;
+      // ONE flat loop over the candidates of all runs (not a loop over runs with a loop over candidates
+      // inside): lanes of a warp are points of neighbouring cells whose run lists differ, and the warp
+      // pays max-over-lanes of the TOTAL candidate count instead of the sum of per-run maxima.
+      // The next run is fetched one switch ahead so the switch itself does not wait on memory.  A hit
+      // adds the candidate, a miss adds +0 (masked operands, no branch): same sums as a skipped add.
+      int k = 0, t = 0, end = 0;
+      int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
 #pragma unroll 2
-    for (int i = 0; i < total; ++i) {
-      if (t == end) {  // runs are non-empty by construction
-        t = nxt.x; end = nxt.y;
-        ++k;
-        if (k < nr) nxt = rr[k];
+      for (int i = 0; i < total; ++i) {
+        if (t == end) {  // runs are non-empty by construction
+          t = nxt.x; end = nxt.y;
+          ++k;
+          if (k < nr) nxt = rr[k];
+        }
+        const float4 q = sp[t];
+        ++t;
+        float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+        float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
+        const bool hit = d2 < r2;
+        const float mx = hit ? q.x : 0.f, my = hit ? q.y : 0.f, mz = hit ? q.z : 0.f, m1 = hit ? 1.0f : 0.f;
+        const u64 qxy = d_pack2(q.x, q.y);
+        a01 = d_fma2(d_pack2(mx, mx), qxy, a01);  // xx, xy
+        a24 = d_fma2(d_pack2(mz, mz), qxy, a24);  // xz, yz
+        a3 = fmaf(my, q.y, a3);
+        a5 = fmaf(mz, q.z, a5);
+        a67 = d_add2(a67, d_pack2(mx, my));
+        a8c = d_add2(a8c, d_pack2(mz, m1));
       }
-      const float4 q = sp[t];
-      ++t;
-      float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-      float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
-      const bool hit = d2 < r2;
-      const float mx = hit ? q.x : 0.f, my = hit ? q.y : 0.f, mz = hit ? q.z : 0.f, m1 = hit ? 1.0f : 0.f;
-      const u64 qxy = d_pack2(q.x, q.y);
-      a01 = d_fma2(d_pack2(mx, mx), qxy, a01);  // xx, xy
-      a24 = d_fma2(d_pack2(mz, mz), qxy, a24);  // xz, yz
-      a3 = fmaf(my, q.y, a3);
-      a5 = fmaf(mz, q.z, a5);
-      a67 = d_add2(a67, d_pack2(mx, my));
-      a8c = d_add2(a8c, d_pack2(mz, m1));
-    }
-    float a0, a1, a2, a4, a6, a7, a8, cntf;
-    d_unpack2(a01, a0, a1); d_unpack2(a24, a2, a4); d_unpack2(a67, a6, a7); d_unpack2(a8c, a8, cntf);
-    cnt = (int)cntf;
-    if (cnt >= 3) {
-      float c = (float)cnt;
-      a0 /= c; a1 /= c; a2 /= c; a3 /= c; a4 /= c; a5 /= c; a6 /= c; a7 /= c; a8 /= c;
-      float c00 = a0 - a6 * a6, c01 = a1 - a6 * a7, c02 = a2 - a6 * a8;
-      float c11 = a3 - a7 * a7, c12 = a4 - a7 * a8, c22 = a5 - a8 * a8;
-      float ev, nx, ny, nz;
-      d_eigen33_smallest(c00, c01, c02, c11, c12, c22, ev, nx, ny, nz);
-      float eig_sum = c00 + c11 + c22;
-      float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
-      float vx = 0.0f - p.x, vy = 0.0f - p.y, vz = 0.0f - p.z;
-      float cos_theta = vx * nx + vy * ny + vz * nz;
-      if (cos_theta < 0.0f) { nx *= -1.0f; ny *= -1.0f; nz *= -1.0f; }
-      o0 = make_float4(nx, ny, nz, 0.f);
-      o1 = make_float4(curv, 0.f, 0.f, 0.f);
+      float a0, a1, a2, a4, a6, a7, a8, cntf;
+      d_unpack2(a01, a0, a1); d_unpack2(a24, a2, a4); d_unpack2(a67, a6, a7); d_unpack2(a8c, a8, cntf);
+      cnt = (int)cntf;
+      if (cnt >= 3) d_normal_from_sums(a0, a1, a2, a3, a4, a5, a6, a7, a8, cnt, p, o0, o1);
+    } else {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+      float last_d2 = -1.0f;  // every real d2 is >= 0
+      int last_id = -1;
+      for (;;) {
+        float best_d2 = CUDART_INF_F;
+        int best_id = 0x7FFFFFFF;
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < nr; ++k) {
+          const int2 run = rr[k];
+          for (int t = run.x; t < run.y; ++t) {
+            const float4 q = sp[t];
+            const int id = __float_as_int(q.w);
+            const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+            const float d2 = (dx * dx + dy * dy) + dz * dz;
+            const bool after = d2 > last_d2 || (d2 == last_d2 && id > last_id);
+            const bool better = d2 < best_d2 || (d2 == best_d2 && id < best_id);
+            if (d2 < r2 && after && better) { best_d2 = d2; best_id = id; bq = q; }
+          }
+        }
+        if (best_id == 0x7FFFFFFF) break;
+        a0 += bq.x * bq.x; a1 += bq.x * bq.y; a2 += bq.x * bq.z;
+        a3 += bq.y * bq.y; a4 += bq.y * bq.z; a5 += bq.z * bq.z;
+        a6 += bq.x; a7 += bq.y; a8 += bq.z;
+        ++cnt;
+        last_d2 = best_d2; last_id = best_id;
+      }
+      if (cnt >= 3) d_normal_from_sums(a0, a1, a2, a3, a4, a5, a6, a7, a8, cnt, p, o0, o1);
     }
   }
   const bool keep = active && finite3(o0.x, o0.y, o0.z) && d_owned(own, p);  // the predicate of k_compact_valid

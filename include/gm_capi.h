@@ -162,6 +162,13 @@ GM_API gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream);
  * scan whenever gm_normals produced one (identical counts, hypotheses whose inlier band provably
  * misses a 32-point tile are skipped for it); 1 = always the brute-force FP32 kernels. */
 GM_API gm_status gm_set_count_mode(gm_ctx* ctx, int32_t mode);
+/* Summation order of the neighbourhood sums of gm_normals (pcl::computeMeanAndCovarianceMatrix at
+ * src/tunnel_processing.cpp:70).  0 (default) = neighbours are added in the order the grid search finds them: the
+ * neighbour SET and count are exact, the float sums differ from PCL's by rounding.  1 = neighbours are added in
+ * FLANN's result order (ascending squared distance, ties by index), the order pcl::NormalEstimation sums them in:
+ * normals and curvatures are then bit-identical to the CPU oracle's and every later stage can be checked end to
+ * end from the raw points.  A verification mode: ~40x slower than mode 0. */
+GM_API gm_status gm_set_normals_mode(gm_ctx* ctx, int32_t mode);
 /* VoxelGrid strategy of gm_voxel / gm_compress: 0 (default) = sort-free dense tables whenever the number of lattice
  * cells of the crop box (or of the box given with gm_set_voxel_bbox) is at most 2^23, else sort-based; 1 = always
  * sort-based.  Same voxels, order, counts and centroids either way. */

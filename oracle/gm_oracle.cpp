@@ -60,6 +60,75 @@ inline float flann_d2(const float* a, const float* b) {
   return r;
 }
 
+
+// ---- libm-independent atan2 / sin / cos for pcl::computeRoots ----------------------------------
+// PCL calls std::atan2 / std::cos / std::sin on floats (common/impl/eigen.hpp), whose last bit depends on the
+// libm in use (glibc's float functions are not correctly rounded, CUDA's differ again).  To make the
+// restatement reproducible on any IEEE-754 machine -- and bit-identical to the CUDA path, which evaluates the
+// SAME operation sequence -- the three functions are evaluated here in double with only +, -, *, /, sqrt in
+// a fixed order (no FMA contraction: -ffp-contract=off) and rounded to float once.  The double result is
+// accurate to ~1e-16, so the float result is the correctly rounded value except with probability ~1e-9 per
+// call: a valid libm for the reference, at most 1 float ulp from glibc's (tests/test_oracle.py measures it).
+//   atan(t), t in [0,1]: two half-angle reductions t <- t / (1 + sqrt(1 + t^2)), then the Taylor series
+//   (14 terms, |t| <= tan(pi/16)); sin/cos on [0, pi/3]: Taylor series, 12 terms, Horner.
+inline double gm_atan_unit(double t) {
+  double t1 = t / (1.0 + std::sqrt(1.0 + t * t));
+  double t2 = t1 / (1.0 + std::sqrt(1.0 + t1 * t1));
+  double z2 = t2 * t2;
+  double p = 1.0 / 27.0;
+  p = p * z2 - 1.0 / 25.0; p = p * z2 + 1.0 / 23.0; p = p * z2 - 1.0 / 21.0; p = p * z2 + 1.0 / 19.0;
+  p = p * z2 - 1.0 / 17.0; p = p * z2 + 1.0 / 15.0; p = p * z2 - 1.0 / 13.0; p = p * z2 + 1.0 / 11.0;
+  p = p * z2 - 1.0 / 9.0;  p = p * z2 + 1.0 / 7.0;  p = p * z2 - 1.0 / 5.0;  p = p * z2 + 1.0 / 3.0;
+  p = 1.0 - p * z2;
+  return 4.0 * (t2 * p);
+}
+// atan2(y, x) for y >= +0 (y = sqrt(-q) at the only call site): result in [0, pi]
+inline float gm_atan2f_pos(float yf, float xf) {
+  const double PI = 3.14159265358979323846, HALF_PI = 1.57079632679489661923;
+  if (std::isnan(yf) || std::isnan(xf)) return std::numeric_limits<float>::quiet_NaN();
+  double y = yf, x = std::fabs((double)xf);
+  const bool neg = std::signbit(xf);
+  double a;
+  if (y == 0.0 && x == 0.0) a = 0.0;
+  else if (x >= y) a = gm_atan_unit(y / x);
+  else a = HALF_PI - gm_atan_unit(x / y);
+  if (neg) a = PI - a;
+  return (float)a;
+}
+inline float gm_sinf_small(float xf) {
+  double x = xf, x2 = x * x;
+  double p = -1.0 / 25852016738884976640000.0;          // -1/23!
+  p = p * x2 + 1.0 / 51090942171709440000.0;            // 1/21!
+  p = p * x2 - 1.0 / 121645100408832000.0;              // -1/19!
+  p = p * x2 + 1.0 / 355687428096000.0;                 // 1/17!
+  p = p * x2 - 1.0 / 1307674368000.0;                   // -1/15!
+  p = p * x2 + 1.0 / 6227020800.0;                      // 1/13!
+  p = p * x2 - 1.0 / 39916800.0;                        // -1/11!
+  p = p * x2 + 1.0 / 362880.0;                          // 1/9!
+  p = p * x2 - 1.0 / 5040.0;                            // -1/7!
+  p = p * x2 + 1.0 / 120.0;                             // 1/5!
+  p = p * x2 - 1.0 / 6.0;                               // -1/3!
+  p = p * x2 + 1.0;
+  return (float)(x * p);
+}
+inline float gm_cosf_small(float xf) {
+  double x = xf, x2 = x * x;
+  double p = 1.0 / 620448401733239439360000.0;          // 1/24!
+  p = p * x2 - 1.0 / 1124000727777607680000.0;          // -1/22!
+  p = p * x2 + 1.0 / 2432902008176640000.0;             // 1/20!
+  p = p * x2 - 1.0 / 6402373705728000.0;                // -1/18!
+  p = p * x2 + 1.0 / 20922789888000.0;                  // 1/16!
+  p = p * x2 - 1.0 / 87178291200.0;                     // -1/14!
+  p = p * x2 + 1.0 / 479001600.0;                       // 1/12!
+  p = p * x2 - 1.0 / 3628800.0;                         // -1/10!
+  p = p * x2 + 1.0 / 40320.0;                           // 1/8!
+  p = p * x2 - 1.0 / 720.0;                             // -1/6!
+  p = p * x2 + 1.0 / 24.0;                              // 1/4!
+  p = p * x2 - 1.0 / 2.0;                               // -1/2!
+  p = p * x2 + 1.0;
+  return (float)p;
+}
+
 // ---- pcl::computeRoots2 / computeRoots / eigen33 (common/impl/eigen.hpp, PCL 1.8)
 inline void compute_roots2(float b, float c, float roots[3]) {
   roots[0] = 0.0f;
@@ -89,9 +158,9 @@ inline void compute_roots(const float m[9], float roots[3]) {
     float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
     if (q > 0.0f) q = 0.0f;
     float rho = std::sqrt(-a_over_3);
-    float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
-    float cos_theta = std::cos(theta);
-    float sin_theta = std::sin(theta);
+    float theta = gm_atan2f_pos(std::sqrt(-q), half_b) * s_inv3;  // std::atan2 / cos / sin, libm-independent (see above)
+    float cos_theta = gm_cosf_small(theta);
+    float sin_theta = gm_sinf_small(theta);
     roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
     roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
     roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
@@ -222,7 +291,9 @@ GMO_API void gmo_normals(const float* pts4, int64_t n, double radius, float* nor
                          int32_t* nbr_count, int mode, int order, double* truth4, int nthreads) {
   const P4* p = (const P4*)pts4;
   const float rf = (float)radius;
-  const float r2 = rf * rf;
+  // pcl::KdTreeFLANN::radiusSearch passes static_cast<float>(radius * radius) with the double radius
+  // (kdtree/impl/kdtree_flann.hpp): NOT float(r)*float(r), which differs by 1 ulp for r = 0.05 and 0.1
+  const float r2 = (float)(radius * radius);
   HashGrid grid;
   if (mode == 0) grid.build(p, n, (double)rf * 1.0009765625);
   nthreads = resolve_threads(nthreads);
@@ -1048,6 +1119,16 @@ GMO_API void gmo_compress(const float* pts4, const uint8_t* labels, int64_t n, c
   f[13] = nc ? (float)std::sqrt(sqc / (double)nc) : 0.f;
   f[14] = nr ? (float)std::sqrt(sqr / (double)nr) : 0.f;
   f[15] = n ? (float)std::sqrt((sqp + sqc + sqr) / (double)n) : 0.f;
+}
+
+
+// test hook: the libm-independent functions above, elementwise (tests/test_oracle.py compares them with libm)
+GMO_API void gmo_trig(const float* y, const float* x, int64_t n, float* atan2_out, float* sin_out, float* cos_out) {
+  for (int64_t i = 0; i < n; ++i) {
+    if (atan2_out) atan2_out[i] = gm_atan2f_pos(y[i], x[i]);
+    if (sin_out) sin_out[i] = gm_sinf_small(x[i]);
+    if (cos_out) cos_out[i] = gm_cosf_small(x[i]);
+  }
 }
 
 GMO_API int32_t gmo_num_threads() { return resolve_threads(0); }

@@ -273,3 +273,12 @@ def map_insert(state, pts, leaf, labels=None, label_filter=-1, pose34=None):
     return {"keys": keys, "ijk": ijk, "counts": co[:Vn].copy(), "sums": so[:Vn].copy(), "centroids": ceo[:Vn].copy(),
             "out_of_range": oor0 + int(oor.value)}
 
+
+
+def trig(y, x):
+    """The oracle's libm-independent atan2(y>=0, x), sin(x), cos(x) (x in [0, pi/3] for sin/cos), elementwise."""
+    y, x = _f32(y), _f32(x)
+    n = x.shape[0]
+    a, s, c = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+    lib().gmo_trig(_p(y), _p(x), C.c_int64(n), _p(a), _p(s), _p(c))
+    return a, s, c

@@ -20,15 +20,21 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_v1.npz")
 PARAMS = dict(n=6000, seed=17, bound=5.0, radius=0.3, leaf=0.25, wf=0.2, tau=0.05, H=96)
 
 
-def compute(p=PARAMS):
+def scan(p=PARAMS):
     pts = synth.curved_tunnel(p["n"], seed=p["seed"], outlier_frac=0.03)
     pts[5, 0] = 7.5          # outside the crop box
     pts[6] = [np.nan, 0, 0, 1]  # kept by the dense-cloud quirk, dropped with its NaN normal
+    return pts
+
+
+def compute(p=PARAMS):
+    pts = scan(p)
     cropped, src = O.crop(pts, p["bound"], True)
     nrm, cnt, _ = O.normals(cropped, p["radius"], mode=1, order=0)
     cloud, nrm_c, vmap = O.compact(cropped, nrm)
     vox = O.voxel(cloud, p["leaf"])
-    nn, _ = O.nn1(vox["centroids"], np.where(np.isfinite(cropped), cropped, 1e30).astype(np.float32))
+    # 1-NN query = the order-independent fixed-point centroid (what the CUDA path defines; within 1e-6 m of "centroids")
+    nn, _ = O.nn1(vox["centroids_fx"], np.where(np.isfinite(cropped), cropped, 1e30).astype(np.float32))
     fr = O.local_frame(nrm_c, p["wf"])
     ps = synth.sample_indices(len(cloud), p["H"], 3, seed=3)
     cs = synth.sample_indices(len(cloud), p["H"], 2, seed=4)

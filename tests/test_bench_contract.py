@@ -32,6 +32,15 @@ def test_reference_arm_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_thread_count_ignores_omp_num_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use (and report) every usable core."""
+    res = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--points", "60000", "--hyp", "64"], env={"OMP_NUM_THREADS": "1"})
+    assert res.returncode == 0, res.stderr
+    d = json.loads(res.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["config"]["points_per_scan"] == 60000 and d["config"]["plane_hypotheses"] == 32
+
+
 def test_reference_arm_other_ranks_print_nothing():
     res = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--points", "50000"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert res.returncode == 0 and res.stdout.strip() == ""

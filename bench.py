@@ -591,50 +591,48 @@ def main():
     h4096["e2e_ms_per_step"] = 1e3 * e2e4_s / steps4
 
     # ---- hypothesis-sharded RANSAC leg (configs[2]) ----------------------------------------------
-    ransac = None
-    Hs = a.shard_hyp
+    # Every rank holds the same scan; rank r evaluates its share of the H hypotheses.  "peer" = the library's own
+    # collective (csrc/gm_comm.cuh): the counting kernel's last block stores (key, winner coefficients) into every peer's
+    # mailbox over NVLink, a one-warp kernel picks the winner, the refit follows -- no host code in between.
+    # "nccl" = the same round with torch.distributed's all_reduce(MAX) of the two keys (the portable path / cross-check).
+    from geometric_mapping_b200 import distributed as gmd
+    comm = gmd.connect_peers()
+    ctx.set_comm(comm)
     shared = synth.curved_tunnel(n, seed=2)  # the same scan on every rank
     d_shared = torch.from_numpy(shared).to(dev)
     ctx.set_scan_device(d_shared.data_ptr(), n)
     ctx.crop()
     ctx.normals()
     nv = ctx.counts().n_valid
-    sp, sc = synth.sample_indices(nv, Hs // 2, 3, seed=3), synth.sample_indices(nv, Hs - Hs // 2, 2, seed=4)
-    from geometric_mapping_b200 import distributed as gmd
     key_t = torch.zeros(2, dtype=torch.int64, device=dev)  # torch-owned buffer for the 16-byte collective (both keys)
 
-    def ransac_step():
-        gmd.sharded_ransac_pair(ctx, sp, sc, rank, world, key_t)
+    def ransac_leg(Hs, reps, seed):
+        sp, sc = synth.sample_indices(nv, Hs // 2, 3, seed=seed), synth.sample_indices(nv, Hs - Hs // 2, 2, seed=seed + 1)
+        res = {"H": Hs, "points": nv}
+        for name, fn in (("peer", lambda: ctx.ransac_sharded(sp, sc)), ("nccl", lambda: gmd.sharded_ransac_pair(ctx, sp, sc, rank, world, key_t))):
+            for _ in range(3):
+                fn()
+            barrier()
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            barrier()
+            rms = max_over_ranks(e0.elapsed_time(e1)) / reps
+            mp, mc = ctx.model(0), ctx.model(1)
+            res[name] = {"ms_per_round": rms, "hyp_pts_per_sec": Hs * nv / (rms * 1e-3),
+                         "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
+        res["winners_equal"] = res["peer"]["plane_best"] == res["nccl"]["plane_best"] and res["peer"]["cyl_best"] == res["nccl"]["cyl_best"]
+        res.update(ms_per_round=res["peer"]["ms_per_round"], hyp_pts_per_sec=res["peer"]["hyp_pts_per_sec"],
+                   plane_best=res["peer"]["plane_best"], cyl_best=res["peer"]["cyl_best"])
+        return res
 
-    for _ in range(3):
-        ransac_step()
-    barrier()
-    e0.record(stream)
-    for _ in range(a.steps):
-        ransac_step()
-    e1.record(stream)
-    barrier()
-    rms = max_over_ranks(e0.elapsed_time(e1))
-    mp, mc = ctx.model(0), ctx.model(1)
-    ransac = {"hyp_pts_per_sec": Hs * nv * a.steps / (rms * 1e-3), "H": Hs, "points": nv, "ms_per_round": rms / a.steps,
-              "mode": "hypotheses sharded across ranks, plane and cylinder side by side, ONE NCCL max-allreduce of both packed (count,id) "
-                      "keys, refit on every rank",
-              "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
+    ransac = ransac_leg(a.shard_hyp, a.steps, 3)
+    ransac["mode"] = ("hypotheses sharded across ranks, plane and cylinder side by side; headline = peer-memory exchange of (key, winner "
+                      "coefficients) issued by the counting kernel itself, refit on every rank; 'nccl' = torch.distributed all_reduce(MAX)")
     if a.shard_hyp_large > 0:
-        Hl = a.shard_hyp_large
-        sp, sc = synth.sample_indices(nv, Hl // 2, 3, seed=5), synth.sample_indices(nv, Hl - Hl // 2, 2, seed=6)
-        reps_l = max(3, min(a.steps, 10))
-        ransac_step()
-        barrier()
-        e0.record(stream)
-        for _ in range(reps_l):
-            ransac_step()
-        e1.record(stream)
-        barrier()
-        rms_l = max_over_ranks(e0.elapsed_time(e1))
-        mp, mc = ctx.model(0), ctx.model(1)
-        ransac["large"] = {"hyp_pts_per_sec": Hl * nv * reps_l / (rms_l * 1e-3), "H": Hl, "ms_per_round": rms_l / reps_l,
-                           "plane_best": [mp["best_id"], mp["best_count"]], "cyl_best": [mc["best_id"], mc["best_count"]]}
+        ransac["large"] = ransac_leg(a.shard_hyp_large, max(3, min(a.steps, 10)), 5)
+    ctx.set_comm(None)
 
     # ---- compression of the segmented cloud (extra stage, reported separately) -------------------------
     for i in range(3):
@@ -680,14 +678,23 @@ def main():
         mctx.set_owned_range(0, lo, hi)
         d_slab = torch.from_numpy(slab).to(dev)
 
+        mctx.set_comm(comm)
+        # where the whole map lies (known once, at set-up): only sizes the VoxelGrid tables; the box itself is computed and
+        # all-reduced on the device in every pass
+        mctx.set_scan_device(d_slab.data_ptr(), ns)
+        mctx.crop()
+        mctx.normals()
+        hint = gmd.allreduce_bbox(*mctx.voxel_bbox())   # set-up only (torch.distributed); + 1 m of slack
+        mctx.set_voxel_bbox_hint(np.maximum(np.asarray(hint[0]) - 1.0, -mbound), np.minimum(np.asarray(hint[1]) + 1.0, mbound))
+
         def map_pass(sp_, sc_):
             mctx.set_scan_device(d_slab.data_ptr(), ns)
             mctx.crop()
             mctx.normals()
-            gmn, gmx = gmd.allreduce_bbox(*mctx.voxel_bbox())   # the one collective of this path (6 floats)
-            mctx.set_voxel_bbox(gmn, gmx)
+            mctx.allreduce_voxel_bbox()   # 6 floats over peer memory, one kernel, no host round trip
             mctx.voxel()
             mctx.local_frame()
+            mctx.allreduce_frame()        # the frame of the WHOLE map: sum of the slabs' scatter matrices
             for kind, smp in ((0, sp_), (1, sc_)):
                 if smp is not None:
                     mctx.ransac(kind, smp)
@@ -723,6 +730,7 @@ def main():
                    "mode": f"100 m tunnel map cut into {world} slab(s) at voxel faces, halo = neighbour radius, one plane + one "
                            f"cylinder per slab ({Hp}+{Hc} hypotheses each), VoxelGrid on the all-reduced global lattice; strong scaling"}
         mctx.close()
+    comm.close()
 
     # ---- CPU baseline + parity of the same scan (rank 0, N=1 only) --------------------------------------
     cpu, parity = None, None
@@ -742,33 +750,19 @@ def main():
         # the CUDA path on the same raw points and sample indices, against that oracle run (never timed)
         parity = {}
         ps0, cs0 = ring_samples(a, 0, of["n_valid"])
-        for mode, name in ((1, "canonical"), (0, "fast")):
-            with capi.Context(params, max_points=ncpu, max_hypotheses=4096) as pc:
-                pc.set_normals_mode(mode)
-                if a.knn:
-                    pc.set_knn(a.knn)
-                pc.upload_scan(cp)
-                pc.process_scan(ps0, cs0)
-                gc_ = pc.counts()
-                gp_, gy_ = pc.model(0), pc.model(1)
-                gn_ = pc.download_normals(0)
-                _, _, gpc = pc.download_hypotheses(0, len(ps0))
-                _, _, gcc = pc.download_hypotheses(1, len(cs0))
-                gfr = pc.frame()
-            parity[name] = {
-                "n_cropped_equal": gc_.n_cropped == of["n_cropped"], "n_valid_equal": gc_.n_valid == of["n_valid"],
-                "V_equal": gc_.n_voxels == of["vox"]["V"],
-                "normals_bit_identical": bool(np.array_equal(gn_.view(np.uint32), of["normals"].view(np.uint32))),
-                "plane_counts_equal": bool(np.array_equal(gpc, ob["plane_counts"])),
-                "cyl_counts_equal": bool(np.array_equal(gcc, ob["cyl_counts"])),
-                "plane_best_equal": gp_["best_id"] == ob["plane_best"], "cyl_best_equal": gy_["best_id"] == ob["cyl_best"],
-                "plane_best": [gp_["best_id"], gp_["best_count"]], "cyl_best": [gy_["best_id"], gy_["best_count"]],
-                "oracle_plane_best": [int(ob["plane_best"]), int(ob["plane_counts"][ob["plane_best"]])],
-                "oracle_cyl_best": [int(ob["cyl_best"]), int(ob["cyl_counts"][ob["cyl_best"]])],
-                "eigenvalue_rel_diff": float(np.abs(gfr["vals"] - of["frame"]["vals"]).max() / np.abs(of["frame"]["vals"]).max()),
-                "plane_refit_abs_diff": float(np.abs(gp_["coef"] - ob["plane_refit"]).max()),
-                "cyl_refit_abs_diff": float(np.abs(gy_["coef"] - ob["cyl_refit"]).max()),
-            }
+        for canonical, name in ((True, "canonical"), (False, "fast")):
+            try:
+                g_ = chain.gpu_chain(cp, ps0, cs0, canonical, a.radius, a.leaf, tau=TAU, refit_iters=a.refit_iters, knn=a.knn)
+                m_ = chain.compare(g_, of, ob, exact_normals=canonical)
+                m_["exact_outputs_equal"] = True   # compare() asserts every integer / bit-pattern output
+                m_["plane_best"] = [g_["plane"]["best_id"], g_["plane"]["best_count"]]
+                m_["cyl_best"] = [g_["cyl"]["best_id"], g_["cyl"]["best_count"]]
+            except AssertionError as e:
+                m_ = {"exact_outputs_equal": False, "first_violation": str(e)}
+            parity[name] = m_
+        parity["oracle"] = {"n_cropped": of["n_cropped"], "n_valid": of["n_valid"], "V": of["vox"]["V"],
+                            "plane_best": [int(ob["plane_best"]), int(ob["plane_counts"][ob["plane_best"]])],
+                            "cyl_best": [int(ob["cyl_best"]), int(ob["cyl_counts"][ob["cyl_best"]])]}
         parity["note"] = ("CUDA path vs the oracle ALONE from the same raw points and sample indices; canonical = "
                           "gm_set_normals_mode(1) (FLANN summation order, every integer output must be equal), fast = the timed default "
                           "(neighbour sets equal, float sums differ by rounding, so cylinder counts may move)")

@@ -127,7 +127,8 @@ SYMBOLS = [
     "gm_download_compressed", "gm_upload_pointcloud2", "gm_ransac_export_key", "gm_ransac_import_key", "gm_set_count_mode", "gm_set_grid_box", "gm_set_owned_range", "gm_get_voxel_bbox", "gm_set_voxel_bbox",
     "gm_get_search_stats", "gm_set_voxel_mode", "gm_ransac_pair", "gm_ransac_select_pair", "gm_ransac_export_keys",
     "gm_ransac_import_keys", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
-    "gm_map_load", "gm_map_leaf", "gm_set_normals_mode",
+    "gm_map_load", "gm_map_leaf", "gm_set_normals_mode", "gm_set_graph_mode", "gm_get_graph_stats",
+    "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint",
 ]
 
 
@@ -199,6 +200,22 @@ def _lib():
         "gm_ransac_import_key": (i32, [vp, i32, vp]),
         "gm_set_count_mode": (i32, [vp, i32]),
         "gm_set_normals_mode": (i32, [vp, i32]),
+        "gm_set_graph_mode": (i32, [vp, i32]),
+        "gm_get_graph_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "gm_comm_create": (i32, [i32, i32, C.POINTER(vp)]),
+        "gm_comm_handle": (i32, [vp, vp]),
+        "gm_comm_connect": (i32, [vp, vp]),
+        "gm_comm_mailbox": (i32, [vp, C.POINTER(vp)]),
+        "gm_comm_connect_local": (i32, [vp, C.POINTER(vp)]),
+        "gm_comm_destroy": (None, [vp]),
+        "gm_comm_rank": (i32, [vp]),
+        "gm_comm_world": (i32, [vp]),
+        "gm_comm_last_error": (C.c_char_p, [vp]),
+        "gm_set_comm": (i32, [vp, vp]),
+        "gm_ransac_sharded": (i32, [vp, vp, i32, vp, i32]),
+        "gm_allreduce_voxel_bbox": (i32, [vp]),
+        "gm_allreduce_frame": (i32, [vp]),
+        "gm_set_voxel_bbox_hint": (i32, [vp, vp, vp]),
         "gm_set_grid_box": (i32, [vp, vp, vp]),
         "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
         "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
@@ -313,6 +330,40 @@ class Context:
         """0 = neighbourhood sums in grid order (fast, default); 1 = in FLANN's (d2, index) order: normals bit-identical
         to the CPU oracle (verification mode, slow)."""
         self._ck(_lib().gm_set_normals_mode(self._h, mode), "gm_set_normals_mode")
+
+    def set_comm(self, comm: "PeerComm | None"):
+        """Attach a connected PeerComm: ransac_sharded / allreduce_voxel_bbox / allreduce_frame then run over NVLink peer memory."""
+        self._ck(_lib().gm_set_comm(self._h, comm._h if comm is not None else None), "gm_set_comm")
+        self._comm = comm
+
+    def ransac_sharded(self, plane_samples: np.ndarray, cyl_samples: np.ndarray):
+        ps = np.ascontiguousarray(plane_samples, np.int32)
+        cs = np.ascontiguousarray(cyl_samples, np.int32)
+        self._keepalive = (ps, cs)
+        self._ck(_lib().gm_ransac_sharded(self._h, _ptr(ps), ps.shape[0], _ptr(cs), cs.shape[0]), "gm_ransac_sharded")
+
+    def allreduce_voxel_bbox(self):
+        self._ck(_lib().gm_allreduce_voxel_bbox(self._h), "gm_allreduce_voxel_bbox")
+
+    def allreduce_frame(self):
+        self._ck(_lib().gm_allreduce_frame(self._h), "gm_allreduce_frame")
+
+    def set_voxel_bbox_hint(self, mn=None, mx=None):
+        if mn is None:
+            self._ck(_lib().gm_set_voxel_bbox_hint(self._h, None, None), "gm_set_voxel_bbox_hint")
+        else:
+            a, b = np.ascontiguousarray(mn, np.float32), np.ascontiguousarray(mx, np.float32)
+            self._ck(_lib().gm_set_voxel_bbox_hint(self._h, _ptr(a), _ptr(b)), "gm_set_voxel_bbox_hint")
+
+    def set_graph_mode(self, mode: int):
+        """1 = process_scan replays a captured CUDA graph (default), 0 = plain stream launches."""
+        self._ck(_lib().gm_set_graph_mode(self._h, mode), "gm_set_graph_mode")
+
+    def graph_stats(self):
+        """-> (graphs captured, graph launches) of process_scan since the context was created"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(_lib().gm_get_graph_stats(self._h, C.byref(a), C.byref(b)), "gm_get_graph_stats")
+        return int(a.value), int(b.value)
 
     def set_grid_box(self, mn=None, mx=None):
         """Neighbour grid over [mn, mx] instead of the crop cube (map slabs); None clears."""
@@ -663,3 +714,41 @@ class VoxelMap:
         except Exception:
             pass
 
+
+
+class PeerComm:
+    """Mailbox of one rank for the peer-memory collectives (include/gm_capi.h: gm_comm_*).  world = 1 needs no peers;
+    otherwise exchange `handle()` (64 bytes) between the ranks and call `connect(all_handles)` (world x 64 bytes)."""
+
+    def __init__(self, rank: int = 0, world: int = 1):
+        h = C.c_void_p()
+        st = _lib().gm_comm_create(rank, world, C.byref(h))
+        if st != GM_OK:
+            raise GmError(st, "gm_comm_create")
+        self._h, self.rank, self.world = h, rank, world
+
+    def handle(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        st = _lib().gm_comm_handle(self._h, buf)
+        if st != GM_OK:
+            raise GmError(st, "gm_comm_handle", _lib().gm_comm_last_error(self._h).decode())
+        return bytes(buf)
+
+    def connect(self, handles: bytes):
+        if len(handles) != 64 * self.world:
+            raise ValueError("handles must be world x 64 bytes")
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        st = _lib().gm_comm_connect(self._h, buf)
+        if st != GM_OK:
+            raise GmError(st, "gm_comm_connect", _lib().gm_comm_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().gm_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -6,6 +6,8 @@
 #include "gm_polyline.cuh"
 #include "gm_compress.cuh"
 #include "gm_map.cuh"
+#include "gm_comm.cuh"
+#include <new>
 
 #include <algorithm>
 #include <cmath>
@@ -92,6 +94,7 @@ struct gm_ctx {
   double grid_box_min[3] = {0, 0, 0}, grid_box_max[3] = {0, 0, 0};
   OwnedRange own{-1, 0.f, 0.f};
   bool have_vox_bbox = false;
+  bool vox_bbox_is_hint = false;  // the box only bounds the lattice (dense-table sizing); the real box is computed / all-reduced on the device
   float vox_bbox[6] = {0, 0, 0, 0, 0, 0};
 
   // device buffers
@@ -121,8 +124,8 @@ struct gm_ctx {
   unsigned long long* d_state64_b = nullptr;  // tile states of the cylinder-refit compaction (may run concurrently with the voxel branch)
   unsigned *d_rs_hist = nullptr, *d_rs_totals = nullptr;  // [256][tiles] tile histograms / row prefixes, [256] row totals
   size_t rs_hist_words = 0;
-  unsigned epoch = 0;            // per-launch tag of the look-back tile states (never cleared)
-  unsigned gn_launches = 0;      // parity selects which of the two GN barrier counters a launch uses
+  TileCtl* d_ctl = nullptr;      // [3] launch control of the look-back kernels: d_state64 | d_state64_b | d_dense_state
+  size_t n_grid = 0;             // n_input rounded up to a bucket: what grids are sized by (kernels read the true n on the device)
   DevState* d_st = nullptr;
   double* d_partials = nullptr;
   FrameOut* d_frame = nullptr;
@@ -151,11 +154,28 @@ struct gm_ctx {
   bool have_comp = false;
   unsigned* d_counters = nullptr;  // last-block tickets: [0] frame, [1] plane refit, [2] cylinder GN
   float4* d_inl = nullptr;          // compacted cylinder inliers
+  // CUDA-graph replay of gm_process_scan: the launch sequence of one scan depends only on (bucketed size, hypothesis
+  // counts, parameters / modes), never on per-scan host values (tile epochs, barrier parities and the scan pointer
+  // live in device memory), so it is captured once per key and replayed with ONE cudaGraphLaunch
+  struct ScanGraph { size_t n_grid; int Hp, Hc; unsigned long long gen; int uses; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
+  std::vector<ScanGraph> graphs;
+  unsigned long long graph_gen = 0;   // bumped by every setter that changes what a scan launches
+  unsigned long long graph_clock = 0;
+  int graph_mode = 1;                 // 1 = replay graphs (default), 0 = plain stream launches (GM_GRAPH=0 / gm_set_graph_mode)
+  bool samples_staged = false;        // the sample indices of the current call are already on their way to the device
+  long long graph_replays = 0, graph_captures = 0;
+  std::string graph_note;
+  // peer-memory collectives (gm_comm.cuh); `sharded` marks a RANSAC round whose keys travel through the mailboxes
+  struct gm_comm* comm = nullptr;
+  bool sharded = false;
+  double* d_frame_sums = nullptr;  // [8] the 6 scatter sums of the last gm_local_frame, kept for gm_allreduce_frame
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> seg_events[SEG_COUNT];
 };
+
+static const CommDev* comm_dev(const gm_ctx* ctx);  // device copy of the peer table of the attached gm_comm (or null)
 
 namespace {
 struct SegTimer {
@@ -295,20 +315,10 @@ gm_status ensure_block_table(gm_ctx* ctx) {
   return GM_OK;
 }
 
-// A fresh epoch for the tile states of one launch (30-bit; on wrap the arrays are cleared once).
-gm_status next_epoch(gm_ctx* ctx, unsigned* out) {
-  ctx->epoch = (ctx->epoch + 1) & TS_EPOCH_MASK;
-  if (ctx->epoch == 0) {
-    GM_CUDA(cudaDeviceSynchronize());
-    GM_CUDA(cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
-    GM_CUDA(cudaMemset(ctx->d_state64_b, 0, ((size_t)div_up((long long)ctx->cap, CP_TILE) + 2) * sizeof(unsigned long long)));
-    if (ctx->d_dense_state) GM_CUDA(cudaMemset(ctx->d_dense_state, 0, ((size_t)div_up((long long)ctx->dense_cap, CPL_TILE) + 2) * sizeof(unsigned long long)));
-    GM_CUDA(cudaDeviceSynchronize());  // legacy-stream memsets do not order with the ctx's non-blocking streams
-    ctx->epoch = 1;
-  }
-  *out = ctx->epoch;
-  return GM_OK;
-}
+// Grids are sized by the input size rounded up to a bucket (kernels read the true size from device state), so that
+// scans of slightly different sizes -- a lidar never returns the same number of points twice -- share one CUDA graph.
+constexpr size_t kGridBucket = 32768;
+inline size_t grid_bucket(size_t n, size_t cap) { return n == 0 ? 0 : std::min(cap, (n + kGridBucket - 1) / kGridBucket * kGridBucket); }
 
 // LSD radix sort of (d_keys[0], d_vals[0]) -> returns the buffer index holding the result.
 // Three wait-free kernels per 8-bit pass (see gm_device.cuh); no memsets, no inter-block spinning.
@@ -435,7 +445,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
   ctx->rs_hist_words = (size_t)div_up((long long)N, RS_BLOCK * 4) * 256;  // sized for the smaller tile
   A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256);
-  A(d_st, 1);
+  A(d_st, 1); A(d_ctl, 3); A(d_frame_sums, 8);
   A(d_partials, 3 * kPartialsRegion);  // 3 regions: frame | plane refit | cylinder GN (may run concurrently)
   A(d_frame, 1);
   A(d_samples[0], 3 * H); A(d_samples[1], 2 * H);
@@ -450,6 +460,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   for (int k = 0; k < 2; ++k)
     if ((e = cudaEventCreateWithFlags(&ctx->ev_samples[k], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
   if ((e = cudaMemset(ctx->d_st, 0, sizeof(DevState))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_ctl, 0, 3 * sizeof(TileCtl))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)N, CP_TILE) + 2) * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_state64_b, 0, ((size_t)div_up((long long)N, CP_TILE) + 2) * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   for (int b = 0; b < 3; ++b) {
@@ -460,6 +471,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   { const char* env = std::getenv("GM_SERIAL"); ctx->concurrent = !(env && env[0] == '1'); }
   { const char* env = std::getenv("GM_COUNT_MODE"); ctx->count_mode = (env && env[0] == '1') ? 1 : 0; }
   { const char* env = std::getenv("GM_VOXEL_MODE"); ctx->voxel_mode = (env && env[0] == '1') ? 1 : 0; }
+  { const char* env = std::getenv("GM_GRAPH"); ctx->graph_mode = (env && env[0] == '0') ? 0 : 1; }
   { const char* env = std::getenv("GM_NORMALS_MODE"); ctx->normals_mode = (env && env[0] == '1') ? 1 : 0; }
 
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
@@ -485,7 +497,7 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
-                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_partials, ctx->d_frame,
+                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
                   ctx->d_res_vs, ctx->d_comp, ctx->d_res_pts, ctx->d_res_centroid, ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start,
@@ -495,6 +507,7 @@ void gm_destroy(gm_ctx* ctx) {
     if (ctx->h_samples[k]) cudaFreeHost(ctx->h_samples[k]);
     if (ctx->ev_samples[k]) cudaEventDestroy(ctx->ev_samples[k]);
   }
+  for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& v : ctx->seg_events) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (int b = 0; b < 3; ++b) { if (ctx->branch[b]) cudaStreamDestroy(ctx->branch[b]); if (ctx->ev_join[b]) cudaEventDestroy(ctx->ev_join[b]); }
@@ -505,6 +518,7 @@ void gm_destroy(gm_ctx* ctx) {
 
 gm_status gm_set_params(gm_ctx* ctx, const gm_params* p) {
   if (!ctx || validate_params(p) != GM_OK) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   if (p->maxSlices > ctx->prm.maxSlices) { ctx->err = "maxSlices cannot grow after gm_create"; return GM_ERR_CAPACITY; }
   ctx->prm = *p;
   return regrid(ctx);
@@ -518,6 +532,7 @@ gm_status gm_get_params(const gm_ctx* ctx, gm_params* out) {
 
 gm_status gm_set_grid_box(gm_ctx* ctx, const float* min3, const float* max3) {
   if (!ctx || ((min3 == nullptr) != (max3 == nullptr))) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   ctx->have_grid_box = min3 != nullptr;
   if (min3) {
     for (int a = 0; a < 3; ++a) {
@@ -530,6 +545,7 @@ gm_status gm_set_grid_box(gm_ctx* ctx, const float* min3, const float* max3) {
 
 gm_status gm_set_owned_range(gm_ctx* ctx, int32_t axis, float lo, float hi) {
   if (!ctx || axis > 2 || (axis >= 0 && !(hi >= lo))) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   ctx->own.axis = axis < 0 ? -1 : axis;
   ctx->own.lo = lo; ctx->own.hi = hi;
   return GM_OK;
@@ -537,9 +553,17 @@ gm_status gm_set_owned_range(gm_ctx* ctx, int32_t axis, float lo, float hi) {
 
 gm_status gm_set_voxel_bbox(gm_ctx* ctx, const float* min3, const float* max3) {
   if (!ctx || ((min3 == nullptr) != (max3 == nullptr))) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   ctx->have_vox_bbox = min3 != nullptr;
+  ctx->vox_bbox_is_hint = false;
   if (min3) for (int a = 0; a < 3; ++a) { ctx->vox_bbox[a] = min3[a]; ctx->vox_bbox[3 + a] = max3[a]; }
   return GM_OK;
+}
+
+gm_status gm_set_voxel_bbox_hint(gm_ctx* ctx, const float* min3, const float* max3) {
+  gm_status s = gm_set_voxel_bbox(ctx, min3, max3);
+  if (s == GM_OK) ctx->vox_bbox_is_hint = min3 != nullptr;
+  return s;
 }
 
 gm_status gm_get_search_stats(gm_ctx* ctx, int64_t* candidates, int64_t* neighbors) {
@@ -566,6 +590,7 @@ gm_status gm_get_voxel_bbox(gm_ctx* ctx, float* min3, float* max3) {
 
 gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream) {
   if (!ctx) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return GM_OK;
@@ -573,18 +598,21 @@ gm_status gm_set_stream(gm_ctx* ctx, void* cuda_stream) {
 
 gm_status gm_set_voxel_mode(gm_ctx* ctx, int32_t mode) {
   if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   ctx->voxel_mode = mode;
   return GM_OK;
 }
 
 gm_status gm_set_normals_mode(gm_ctx* ctx, int32_t mode) {
   if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   ctx->normals_mode = mode;
   return GM_OK;
 }
 
 gm_status gm_set_count_mode(gm_ctx* ctx, int32_t mode) {
   if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   ctx->count_mode = mode;
   return GM_OK;
 }
@@ -606,9 +634,10 @@ static void clear_stages(gm_ctx* ctx) {
 
 static gm_status begin_scan(gm_ctx* ctx, size_t n) {
   ctx->n_input = n;
+  ctx->n_grid = grid_bucket(n, ctx->cap);
   ctx->have_scan = true;
   clear_stages(ctx);
-  GM_LAUNCH(ctx, k_begin_scan, 1, 32, ctx->d_st, (int)n);
+  GM_LAUNCH(ctx, k_begin_scan, 1, 32, ctx->d_st, (int)n, ctx->d_scan);
   GM_CHECK_LAUNCHES(ctx);
   return GM_OK;
 }
@@ -659,15 +688,12 @@ gm_status gm_set_scan_device(gm_ctx* ctx, const float* xyzw_device, size_t n) {
 gm_status gm_crop(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
-  const size_t n = ctx->n_input;
+  const size_t n = ctx->n_grid;
   if (n) {
-    unsigned epoch = 0;
-    gm_status s = next_epoch(ctx, &epoch);
-    if (s != GM_OK) return s;
     float hi = (float)ctx->prm.boxFilterBound, lo = (float)(-ctx->prm.boxFilterBound);
     SegTimer seg_(ctx, SEG_CROP);
-    GM_LAUNCH(ctx, k_crop, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_scan, (int)n, lo, hi, ctx->prm.is_dense,
-              ctx->d_crop, ctx->d_state64, epoch, ctx->d_st);
+    GM_LAUNCH(ctx, k_crop, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_st, lo, hi, ctx->prm.is_dense,
+              ctx->d_crop, ctx->d_state64, ctx->d_ctl + 0, ctx->d_st);
     GM_CHECK_LAUNCHES(ctx);
   }
   ctx->have_crop = true;
@@ -678,7 +704,7 @@ gm_status gm_crop(gm_ctx* ctx) {
 gm_status gm_normals(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_crop) return GM_ERR_STAGE_ORDER;
-  const size_t n = ctx->n_input;  // upper bound of M
+  const size_t n = ctx->n_grid;  // upper bound of M (bucketed)
   if (n) {
     const int* n_ptr = &ctx->d_st->n_crop;
     const GridSpec g = ctx->grid;
@@ -690,12 +716,10 @@ gm_status gm_normals(gm_ctx* ctx) {
     { SegTimer seg_(ctx, SEG_GRID_SORT);
       s = radix_sort(ctx, n_ptr, n, g.key_bits, &buf); }
     if (s != GM_OK) return s;
-    unsigned epoch = 0;
-    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_GRID_BUILD);
     GM_LAUNCH(ctx, k_clear_blocks, std::min(div_up((long long)n, 256), ctx->num_sms * 8), 256, ctx->d_ucell_key, ctx->d_st, g.sentinel, ctx->d_tab);
     GM_LAUNCH(ctx, k_cell_heads, div_up((long long)n, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], ctx->d_crop, n_ptr,
-              g.sentinel, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_tab, ctx->d_state64, epoch, ctx->d_st);
+              g.sentinel, ctx->d_sorted, ctx->d_cell_id, ctx->d_ucell_key, ctx->d_ucell_start, ctx->d_tab, ctx->d_state64, ctx->d_ctl + 0, ctx->d_st);
     GM_LAUNCH(ctx, k_cell_runs, std::min(div_up((long long)n, 128), ctx->num_sms * 16), 128, ctx->d_ucell_key,
               ctx->d_ucell_start, ctx->d_tab, ctx->d_st, g, ctx->d_runs, ctx->d_cell_nruns); }
     // pcl::KdTreeFLANN::radiusSearch hands FLANN static_cast<float>(radius * radius), the product taken in double
@@ -708,10 +732,9 @@ gm_status gm_normals(gm_ctx* ctx) {
         GM_LAUNCH(ctx, k_normals<0>, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
                   ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st);
       } }
-    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_COMPACT);
       GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,
-                ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, epoch, ctx->d_st, ctx->own); }
+                ctx->d_normals_c, ctx->d_valid_map, ctx->d_state64, ctx->d_ctl + 0, ctx->d_st, ctx->own); }
     GM_CHECK_LAUNCHES(ctx);
   }
   ctx->have_normals = true;
@@ -756,10 +779,8 @@ gm_status voxel_downsample(gm_ctx* ctx, const float4* pts, VoxState* vs, size_t 
   const float inv = 1.0f / leaf_f;
   int blocks = std::min(div_up((long long)n_cap, 256), ctx->num_sms * 16);
   gm_status s;
-  unsigned epoch = 0;
   if (ctx->voxel_mode == 0 && key_range > 0 && key_range <= kDenseMaxKeys) {
     if ((s = ensure_dense(ctx, key_range)) != GM_OK) return s;
-    if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
     { SegTimer seg_(ctx, SEG_VOX_KEYS);
       if (pts == ctx->d_cloud_c && ctx->have_normals && !ctx->injected) {
         // the scan's own compacted cloud: accumulate over its cell-sorted copy with warp-combined atomics
@@ -771,7 +792,7 @@ gm_status voxel_downsample(gm_ctx* ctx, const float4* pts, VoxState* vs, size_t 
       } }
     { SegTimer seg_(ctx, SEG_VOX_REDUCE);
       GM_LAUNCH(ctx, k_voxel_dense_scan, div_up((long long)key_range, CPL_TILE), CP_BLOCK, ctx->d_dense_cnt, ctx->d_dense_sum, ctx->d_dense_id,
-                (int)key_range, o.vox_key, o.vox_count, o.centroid, ctx->d_dense_state, epoch, vs, &ctx->d_st->error);
+                (int)key_range, o.vox_key, o.vox_count, o.centroid, ctx->d_dense_state, ctx->d_ctl + 2, vs, &ctx->d_st->error);
       GM_LAUNCH(ctx, k_voxel_assign, blocks, 256, pts, vs, inv, ctx->d_dense_id, (int)key_range, o.key_pt, o.assign); }
     *sorted_buf = 0;
     GM_CHECK_LAUNCHES(ctx);
@@ -783,10 +804,9 @@ gm_status voxel_downsample(gm_ctx* ctx, const float4* pts, VoxState* vs, size_t 
   { SegTimer seg_(ctx, SEG_VOX_SORT);
     s = radix_sort(ctx, &vs->n, n_cap, key_bits, &buf); }
   if (s != GM_OK) return s;
-  if ((s = next_epoch(ctx, &epoch)) != GM_OK) return s;
   { SegTimer seg_(ctx, SEG_VOX_REDUCE);
     GM_LAUNCH(ctx, k_voxel_heads, div_up((long long)n_cap, CPL_TILE), CP_BLOCK, ctx->d_keys[buf], ctx->d_vals[buf], o.assign, o.vox_start, o.vox_key,
-              ctx->d_state64, epoch, vs, &ctx->d_st->error);
+              ctx->d_state64, ctx->d_ctl + 0, vs, &ctx->d_st->error);
     GM_LAUNCH(ctx, k_voxel_centroids, std::min(div_up((long long)n_cap * 32, VC_BLOCK), ctx->num_sms * 16), VC_BLOCK, ctx->d_vals[buf], pts,
               o.vox_start, vs, o.centroid, o.vox_count); }
   *sorted_buf = buf;
@@ -819,13 +839,13 @@ int voxel_key_bits(const gm_ctx* ctx, size_t n, size_t* key_range) {
 gm_status gm_voxel(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
-  const size_t n = ctx->n_input;
+  const size_t n = ctx->n_grid;
   if (n) {
     VoxBuffers o{ctx->d_vkey_pt, ctx->d_assign, ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_centroid};
     int buf = 0;
     size_t key_range = 0;
     int key_bits = voxel_key_bits(ctx, n, &key_range);
-    if (ctx->have_vox_bbox) {
+    if (ctx->have_vox_bbox && !ctx->vox_bbox_is_hint) {
       const float* b = ctx->vox_bbox;
       GM_LAUNCH(ctx, k_set_bbox, 1, 32, &ctx->d_st->vox, b[0], b[1], b[2], b[3], b[4], b[5]);
     }
@@ -850,13 +870,25 @@ gm_status gm_local_frame(gm_ctx* ctx) {
   const WeightLaw law = weight_law(ctx->prm);
   SegTimer seg_(ctx, SEG_FRAME);
   GM_LAUNCH(ctx, k_frame, FRAME_BLOCKS, FR_BLOCK, ctx->d_normals_c, &ctx->d_st->n_valid, law, ctx->d_partials + 0 * kPartialsRegion, ctx->d_counters + 0,
-            ctx->d_frame);
+            ctx->d_frame, ctx->d_frame_sums);
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_frame = true;
   return GM_OK;
 }
 
 // ---- a8 --------------------------------------------------------------------------------------
+// injected sample indices: host -> pinned staging -> device (the staging buffer is free again once the copy has run)
+// Only the ids [h_begin, h_end) this call evaluates are copied (a rank of a sharded round never touches the rest).
+static gm_status stage_samples(gm_ctx* ctx, int kind, const int32_t* samples_host, int h_begin, int h_end, int per) {
+  if (h_end <= h_begin) return GM_OK;
+  const size_t off = (size_t)h_begin * per, cnt = (size_t)(h_end - h_begin) * per;
+  GM_CUDA(cudaEventSynchronize(ctx->ev_samples[kind]));
+  std::memcpy(ctx->h_samples[kind] + off, samples_host + off, cnt * sizeof(int));
+  GM_CUDA(cudaMemcpyAsync(ctx->d_samples[kind] + off, ctx->h_samples[kind] + off, cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  GM_CUDA(cudaEventRecord(ctx->ev_samples[kind], ctx->stream));
+  return GM_OK;
+}
+
 gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int32_t H, int32_t h_begin, int32_t h_end) {
   if (!ctx || (kind != 0 && kind != 1) || H < 0 || (H > 0 && !samples_host)) return GM_ERR_INVALID_ARG;
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
@@ -866,19 +898,20 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
   const int per = kind == 0 ? 3 : 2;
   const int* n_ptr = &ctx->d_st->n_valid;
   if (H > 0) {
-    GM_CUDA(cudaEventSynchronize(ctx->ev_samples[kind]));
-    std::memcpy(ctx->h_samples[kind], samples_host, (size_t)H * per * sizeof(int));
-    GM_CUDA(cudaMemcpyAsync(ctx->d_samples[kind], ctx->h_samples[kind], (size_t)H * per * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    GM_CUDA(cudaEventRecord(ctx->ev_samples[kind], ctx->stream));
+    // a peer-memory sharded round ships the winner's coefficients with its key, so only this rank's share is uploaded and
+    // generated; otherwise (single GPU, or keys all-reduced by the caller) every rank generates all H to be able to refit any winner
+    const int gen_all = ctx->sharded ? 0 : 1;
+    if (!ctx->samples_staged) { gm_status st_ = stage_samples(ctx, kind, samples_host, gen_all ? 0 : h_begin, gen_all ? H : h_end, per); if (st_ != GM_OK) return st_; }
+    const CommDev* commdev = ctx->sharded ? comm_dev(ctx) : nullptr;
     int hb = div_up(H, 128);
     { SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_HYP : SEG_CYL_HYP);
     if (kind == 0) {
       GM_LAUNCH(ctx, k_plane_hypotheses, hb, 128, ctx->d_cloud_c, n_ptr, ctx->d_samples[0], H, ctx->d_plane_coef, ctx->d_hvalid[0],
-                ctx->d_counts[0], h_begin, h_end);
+                ctx->d_counts[0], h_begin, h_end, gen_all);
     } else {
       GM_LAUNCH(ctx, k_cyl_hypotheses, hb, 128, ctx->d_cloud_c, ctx->d_normals_c, n_ptr, ctx->d_samples[1], H,
                 (float)ctx->prm.cylinderRadiusMin, (float)ctx->prm.cylinderRadiusMax, (float)ctx->prm.ransacThreshold,
-                ctx->d_model7, ctx->d_test12, ctx->d_hvalid[1], ctx->d_counts[1], h_begin, h_end);
+                ctx->d_model7, ctx->d_test12, ctx->d_hvalid[1], ctx->d_counts[1], h_begin, h_end, gen_all);
     } }
     const int hloc = h_end - h_begin;
     bool argmax_done = false;
@@ -886,15 +919,15 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
       // tile-culled counting over the cell-sorted cloud of this scan (same counts, see gm_ransac.cuh)
       argmax_done = true;
       SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_COUNT : SEG_CYL_COUNT);
-      const int blocks = std::max(1, div_up((long long)ctx->n_input, TC_SUPER));
+      const int blocks = std::max(1, div_up((long long)ctx->n_grid, TC_SUPER));
       if (kind == 0) {
         GM_LAUNCH(ctx, k_count_tiles<0>, blocks, TC_BLOCK, ctx->d_sorted_valid, ctx->d_leaf_bounds, &ctx->d_st->n_crop, ctx->d_plane_coef,
                   ctx->d_test12, ctx->d_hvalid[0], h_begin, h_end, (float)ctx->prm.ransacThreshold, ctx->d_counts[0], H, ctx->d_key + 0,
-                  ctx->d_counters + 3);
+                  ctx->d_counters + 3, commdev, ctx->d_model7);
       } else {
         GM_LAUNCH(ctx, k_count_tiles<1>, blocks, TC_BLOCK, ctx->d_sorted_valid, ctx->d_leaf_bounds, &ctx->d_st->n_crop, ctx->d_plane_coef,
                   ctx->d_test12, ctx->d_hvalid[1], h_begin, h_end, (float)ctx->prm.ransacThreshold, ctx->d_counts[1], H, ctx->d_key + 1,
-                  ctx->d_counters + 4);
+                  ctx->d_counters + 4, commdev, ctx->d_model7);
       }
     } else if (hloc > 0 && ctx->n_input > 0) {
       argmax_done = true;  // folded into the count kernel's last block
@@ -903,19 +936,19 @@ gm_status gm_ransac(gm_ctx* ctx, int32_t kind, const int32_t* samples_host, int3
       int groups = div_up(hloc, RC_BLOCK * K);
       // co-resident 64-thread blocks per SM (register limited to 14), every slice at least half a tile
       static const int kBlocksPerSm = [] { const char* e = std::getenv("GM_COUNT_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 8; }();
-      int slices = std::max(1, std::min(div_up((long long)ctx->n_input, RC_TILE / 2), div_up(ctx->num_sms * kBlocksPerSm, groups)));
+      int slices = std::max(1, std::min(div_up((long long)ctx->n_grid, RC_TILE / 2), div_up(ctx->num_sms * kBlocksPerSm, groups)));
       dim3 grid(slices, groups);
       if (kind == 0) {
         GM_LAUNCH(ctx, k_count_plane<RC_KP>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_plane_coef, ctx->d_hvalid[0], h_begin, h_end,
-                  (float)ctx->prm.ransacThreshold, ctx->d_counts[0], H, ctx->d_key + 0, ctx->d_counters + 3);
+                  (float)ctx->prm.ransacThreshold, ctx->d_counts[0], H, ctx->d_key + 0, ctx->d_counters + 3, commdev);
       } else {
         GM_LAUNCH(ctx, k_count_cyl<RC_KC>, grid, RC_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_test12, h_begin, h_end, ctx->d_counts[1], H,
-                  ctx->d_key + 1, ctx->d_counters + 4);
+                  ctx->d_key + 1, ctx->d_counters + 4, commdev, ctx->d_model7);
       }
     }
     if (!argmax_done) {
       SegTimer seg_(ctx, kind == 0 ? SEG_PLANE_ARGMAX : SEG_CYL_ARGMAX);
-      GM_LAUNCH(ctx, k_argmax, 1, AM_BLOCK, ctx->d_counts[kind], H, ctx->d_key + kind);
+      GM_LAUNCH(ctx, k_argmax, 1, AM_BLOCK, ctx->d_counts[kind], H, ctx->d_key + kind, commdev, kind, ctx->d_plane_coef, ctx->d_model7, ctx->d_test12);
     }
   } else {
     GM_CUDA(cudaMemsetAsync(ctx->d_key + kind, 0, sizeof(unsigned long long), ctx->stream));
@@ -959,21 +992,16 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
     GM_LAUNCH(ctx, k_plane_refit, REFIT_BLOCKS, RF_BLOCK, ctx->d_cloud_c, n_ptr, ctx->d_key + 0, H, ctx->d_plane_coef, ms, tau,
               ctx->d_partials + 1 * kPartialsRegion, ctx->d_counters + 1);
   } else {
-    unsigned epoch = 0;
-    gm_status s = next_epoch(ctx, &epoch);
-    if (s != GM_OK) return s;
-    GM_LAUNCH(ctx, k_cyl_inlier_compact, std::max(1, div_up((long long)ctx->n_input, CPL_TILE)), CP_BLOCK, ctx->d_cloud_c, n_ptr,
-              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64_b, epoch, &ctx->d_st->error);
+    GM_LAUNCH(ctx, k_cyl_inlier_compact, std::max(1, div_up((long long)ctx->n_grid, CPL_TILE)), CP_BLOCK, ctx->d_cloud_c, n_ptr,
+              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64_b, ctx->d_ctl + 1, &ctx->d_st->error);
     // all Gauss-Newton passes in one cooperative launch (grid barrier between passes)
     {
       const float4* inl = ctx->d_inl;
       int iters = ctx->prm.refitIterations;
       double* partials = ctx->d_partials + 2 * kPartialsRegion;
-      unsigned* bar = ctx->d_counters + 5 + (ctx->gn_launches & 1);       // counters [5],[6]: ping-pong
-      unsigned* bar_next = ctx->d_counters + 5 + ((ctx->gn_launches + 1) & 1);
-      ++ctx->gn_launches;
+      unsigned* bars = ctx->d_counters + 5;  // counters [5],[6]: the two barrier counters, [7]: which one the next launch uses
       int* err = &ctx->d_st->error;
-      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bar, (void*)&bar_next, (void*)&err};
+      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bars, (void*)&err};
       GM_CUDA(cudaLaunchCooperativeKernel((const void*)k_cyl_gn_all, dim3(ctx->gn_blocks), dim3(RF_BLOCK), args, 0, ctx->stream));
       ++ctx->launches;
     }
@@ -987,7 +1015,7 @@ gm_status gm_label(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
   if (ctx->n_input) {
-    int blocks = std::min(div_up((long long)ctx->n_input, 256), ctx->num_sms * 16);
+    int blocks = std::min(div_up((long long)ctx->n_grid, 256), ctx->num_sms * 16);
     SegTimer seg_(ctx, SEG_LABEL);
     GM_LAUNCH(ctx, k_label, blocks, 256, ctx->d_cloud_c, &ctx->d_st->n_valid, ctx->d_model + 0, ctx->d_model + 1,
               ctx->have_model[0] ? 1 : 0, ctx->have_model[1] ? 1 : 0, (float)ctx->prm.ransacThreshold, ctx->d_labels);
@@ -1007,7 +1035,7 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   {
     // 4 launches: range (+basis, +zeroing, +slice layout) and three accumulation passes, each with the
     // per-slice step that consumes it folded into its last block
-    int blocks = std::max(1, std::min(div_up((long long)std::max<size_t>(ctx->n_input, 1), POLY_BLOCK), ctx->num_sms * 4));
+    int blocks = std::max(1, std::min(div_up((long long)std::max<size_t>(ctx->n_grid, 1), POLY_BLOCK), ctx->num_sms * 4));
     GM_LAUNCH(ctx, k_poly_range, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_labels, n_ptr, ctx->d_frame, ctx->d_poly, ctx->d_poly_acc,
               POLY_NACC * S, ctx->d_poly_part, ctx->d_counters + 8, ctx->prm.sliceLength, S);
     GM_LAUNCH(ctx, k_poly_pass<0>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift,
@@ -1025,14 +1053,12 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
 gm_status gm_compress(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
   if (!ctx->have_labels || !ctx->have_poly) return GM_ERR_STAGE_ORDER;
-  const size_t n = std::max<size_t>(ctx->n_input, 1);
-  unsigned epoch = 0;
-  gm_status s = next_epoch(ctx, &epoch);
-  if (s != GM_OK) return s;
+  const size_t n = std::max<size_t>(ctx->n_grid, 1);
+  gm_status s;
   GM_LAUNCH(ctx, k_vox_reset, 1, 32, ctx->d_res_vs);
   const int tiles = div_up((long long)n, CP_TILE);
   GM_LAUNCH(ctx, k_comp_split, tiles, CP_BLOCK, ctx->d_cloud_c, ctx->d_labels, &ctx->d_st->n_valid, ctx->d_model + 0, ctx->d_model + 1,
-            ctx->have_model[0] ? 1 : 0, ctx->have_model[1] ? 1 : 0, ctx->d_res_pts, ctx->d_res_vs, ctx->d_state64, epoch, &ctx->d_st->error,
+            ctx->have_model[0] ? 1 : 0, ctx->have_model[1] ? 1 : 0, ctx->d_res_pts, ctx->d_res_vs, ctx->d_state64, ctx->d_ctl + 0, &ctx->d_st->error,
             ctx->d_comp_part, ctx->d_comp_mm, ctx->d_counters + 12, ctx->d_comp);
   VoxBuffers o{ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start, ctx->d_res_vox_key, ctx->d_res_vox_count, ctx->d_res_centroid};
   int buf = 0;
@@ -1119,10 +1145,7 @@ static gm_status run_branch(gm_ctx* ctx, int b, F&& body) {
   return GM_OK;
 }
 
-extern "C" {
-
-gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
-  if (!ctx) return GM_ERR_INVALID_ARG;
+static gm_status process_scan_body(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
   gm_status s;
   if ((s = gm_crop(ctx)) != GM_OK) return s;
   if ((s = gm_normals(ctx)) != GM_OK) return s;
@@ -1154,6 +1177,97 @@ gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_
   }
   if ((s = gm_label(ctx)) != GM_OK) return s;
   if ((s = gm_axis_polyline(ctx)) != GM_OK) return s;
+  return GM_OK;
+}
+
+// host-side stage flags after a whole scan (what process_scan_body leaves behind)
+static void mark_processed(gm_ctx* ctx, int Hp, int Hc) {
+  ctx->have_crop = ctx->have_normals = ctx->have_compacted = true;
+  ctx->injected = false;
+  ctx->have_voxel = ctx->have_frame = ctx->have_labels = ctx->have_poly = true;
+  const int H[2] = {Hp, Hc};
+  for (int k = 0; k < 2; ++k)
+    if (H[k] > 0) { ctx->have_ransac[k] = true; ctx->have_model[k] = true; ctx->ransac_H[k] = H[k]; }
+}
+
+static void drop_graph(gm_ctx::ScanGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  g.exec = nullptr;
+}
+
+extern "C" {
+
+gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
+  if (!ctx || Hp < 0 || Hc < 0 || (Hp > 0 && !plane_samples_host) || (Hc > 0 && !cyl_samples_host)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
+  if (Hp > ctx->hcap || Hc > ctx->hcap) { ctx->err = "H larger than max_hypotheses"; return GM_ERR_CAPACITY; }
+  const bool graphable = ctx->graph_mode == 1 && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;
+  if (!graphable) return process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
+  gm_ctx::ScanGraph* g = nullptr;
+  for (auto& e : ctx->graphs)
+    if (e.n_grid == ctx->n_grid && e.Hp == Hp && e.Hc == Hc && e.gen == ctx->graph_gen) { g = &e; break; }
+  if (!g) {
+    if (ctx->graphs.size() >= 8) {  // evict the least recently used entry
+      size_t v = 0;
+      for (size_t i = 1; i < ctx->graphs.size(); ++i) if (ctx->graphs[i].stamp < ctx->graphs[v].stamp) v = i;
+      drop_graph(ctx->graphs[v]);
+      ctx->graphs.erase(ctx->graphs.begin() + (long)v);
+    }
+    ctx->graphs.push_back(gm_ctx::ScanGraph{ctx->n_grid, Hp, Hc, ctx->graph_gen, 0, nullptr, 0, 0});
+    g = &ctx->graphs.back();
+  }
+  g->stamp = ++ctx->graph_clock;
+  ++g->uses;
+  // first scan of a kind: plain launches (buffers that grow on demand are allocated here, outside any capture)
+  if (!g->exec && g->uses == 1) return process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
+  gm_status s;
+  if (Hp > 0 && (s = stage_samples(ctx, 0, plane_samples_host, 0, Hp, 3)) != GM_OK) return s;
+  if (Hc > 0 && (s = stage_samples(ctx, 1, cyl_samples_host, 0, Hc, 2)) != GM_OK) return s;
+  if (!g->exec) {
+    // second scan of a kind: capture the launch sequence (nothing executes during capture), then launch the graph
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      const long long l0 = ctx->launches;
+      ctx->samples_staged = true;
+      s = process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
+      ctx->samples_staged = false;
+      g->launches = ctx->launches - l0;
+      e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (s != GM_OK && e == cudaSuccess) e = cudaErrorUnknown;
+      if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (e != cudaSuccess) {  // cannot capture on this stream / driver: keep working with plain launches, and say so
+      cudaGetLastError();
+      ctx->graph_note = std::string("graph capture failed, using stream launches: ") + cudaGetErrorString(e);
+      ctx->graph_mode = 0;
+      g->exec = nullptr;
+      ctx->samples_staged = true;  // already staged above
+      s = process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
+      ctx->samples_staged = false;
+      return s;
+    }
+    ++ctx->graph_captures;
+  } else {
+    ctx->launches += g->launches;
+  }
+  GM_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  ++ctx->graph_replays;
+  mark_processed(ctx, Hp, Hc);
+  return GM_OK;
+}
+
+gm_status gm_set_graph_mode(gm_ctx* ctx, int32_t mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  ctx->graph_mode = mode;
+  return GM_OK;
+}
+
+gm_status gm_get_graph_stats(const gm_ctx* ctx, int64_t* captures, int64_t* replays) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (captures) *captures = ctx->graph_captures;
+  if (replays) *replays = ctx->graph_replays;
   return GM_OK;
 }
 
@@ -1438,9 +1552,10 @@ gm_status gm_inject_compacted(gm_ctx* ctx, const float* xyzw_host, const float* 
   if (!ctx || (n && !xyzw_host)) return GM_ERR_INVALID_ARG;
   if (n > ctx->cap) return GM_ERR_CAPACITY;
   ctx->n_input = n;
+  ctx->n_grid = grid_bucket(n, ctx->cap);
   ctx->have_scan = true;
   clear_stages(ctx);
-  GM_LAUNCH(ctx, k_begin_scan, 1, 32, ctx->d_st, (int)n);
+  GM_LAUNCH(ctx, k_begin_scan, 1, 32, ctx->d_st, (int)n, (const float4*)nullptr);
   if (n) {
     GM_CUDA(cudaMemcpyAsync(ctx->d_cloud_c, xyzw_host, n * 16, cudaMemcpyHostToDevice, ctx->stream));
     if (normals8_host) GM_CUDA(cudaMemcpyAsync(ctx->d_normals_c, normals8_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -1496,6 +1611,185 @@ void gm_markers_normals_mode(const float* centroids, const float* nn_normal8, in
     a.color_argb[0] = 1.0f; a.color_argb[1] = 0.0f; a.color_argb[2] = 0.0f; a.color_argb[3] = 1.0f;  // :231 -> a=1,b=1 (quirk B.5)
     a.id = i;
   }
+}
+
+}  // extern "C"
+
+
+// ---- peer-memory collectives (gm_comm.cuh) -----------------------------------------------------------------------
+struct gm_comm {
+  int rank = 0, world = 1, device = 0;
+  CommBox* d_box = nullptr;        // this rank's mailbox
+  CommDev* d_dev = nullptr;        // device copy of the peer table
+  CommDev h_dev{};
+  bool connected = false;
+  void* opened[COMM_MAX_RANKS] = {};
+  std::string err;
+};
+
+static const CommDev* comm_dev(const gm_ctx* ctx) { return ctx->comm ? ctx->comm->d_dev : nullptr; }
+
+extern "C" {
+
+gm_status gm_comm_create(int32_t rank, int32_t world, gm_comm** out) {
+  if (!out) return GM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (world < 1 || world > COMM_MAX_RANKS || rank < 0 || rank >= world) return GM_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GM_ERR_NO_DEVICE; }
+  gm_comm* c = new (std::nothrow) gm_comm();
+  if (!c) return GM_ERR_INTERNAL;
+  c->rank = rank; c->world = world;
+  cudaGetDevice(&c->device);
+  if (cudaMalloc((void**)&c->d_box, sizeof(CommBox)) != cudaSuccess || cudaMalloc((void**)&c->d_dev, sizeof(CommDev)) != cudaSuccess ||
+      cudaMemset(c->d_box, 0, sizeof(CommBox)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    gm_comm_destroy(c);
+    return GM_ERR_CUDA;
+  }
+  c->h_dev.local = c->d_box; c->h_dev.rank = rank; c->h_dev.world = world;
+  c->h_dev.peer[rank] = c->d_box;
+  if (world == 1) {
+    if (cudaMemcpy(c->d_dev, &c->h_dev, sizeof(CommDev), cudaMemcpyHostToDevice) != cudaSuccess) { gm_comm_destroy(c); return GM_ERR_CUDA; }
+    c->connected = true;
+  }
+  *out = c;
+  return GM_OK;
+}
+
+gm_status gm_comm_handle(gm_comm* c, void* handle64) {
+  if (!c || !handle64) return GM_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, c->d_box) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); return GM_ERR_CUDA; }
+  std::memcpy(handle64, &h, 64);
+  return GM_OK;
+}
+
+gm_status gm_comm_connect(gm_comm* c, const void* handles) {
+  if (!c || !handles) return GM_ERR_INVALID_ARG;
+  if (c->connected) return GM_OK;
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const unsigned char*)handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { c->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); return GM_ERR_CUDA; }
+    c->opened[r] = p;
+    c->h_dev.peer[r] = (CommBox*)p;
+  }
+  if (cudaMemcpy(c->d_dev, &c->h_dev, sizeof(CommDev), cudaMemcpyHostToDevice) != cudaSuccess) return GM_ERR_CUDA;
+  c->connected = true;
+  return GM_OK;
+}
+
+/* same-process peers (several contexts / devices driven by one process): mailbox addresses instead of IPC handles */
+gm_status gm_comm_mailbox(gm_comm* c, void** box) {
+  if (!c || !box) return GM_ERR_INVALID_ARG;
+  *box = c->d_box;
+  return GM_OK;
+}
+gm_status gm_comm_connect_local(gm_comm* c, void* const* boxes) {
+  if (!c || !boxes) return GM_ERR_INVALID_ARG;
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    if (!boxes[r]) return GM_ERR_INVALID_ARG;
+    c->h_dev.peer[r] = (CommBox*)boxes[r];
+  }
+  if (cudaMemcpy(c->d_dev, &c->h_dev, sizeof(CommDev), cudaMemcpyHostToDevice) != cudaSuccess) return GM_ERR_CUDA;
+  c->connected = true;
+  return GM_OK;
+}
+
+void gm_comm_destroy(gm_comm* c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < COMM_MAX_RANKS; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
+  if (c->d_box) cudaFree(c->d_box);
+  if (c->d_dev) cudaFree(c->d_dev);
+  cudaGetLastError();
+  delete c;
+}
+
+int32_t gm_comm_rank(const gm_comm* c) { return c ? c->rank : -1; }
+int32_t gm_comm_world(const gm_comm* c) { return c ? c->world : 0; }
+const char* gm_comm_last_error(const gm_comm* c) { return c ? c->err.c_str() : "null comm"; }
+
+gm_status gm_set_comm(gm_ctx* ctx, gm_comm* comm) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (comm && !comm->connected) { ctx->err = "gm_comm is not connected"; return GM_ERR_STAGE_ORDER; }
+  ++ctx->graph_gen;
+  ctx->comm = comm;
+  return GM_OK;
+}
+
+// One hypothesis-sharded RANSAC round for both primitives: this rank generates, counts and arg-maxes its share of the
+// ids [0, H); the last block of each counting kernel stores (key, winner coefficients) into every peer's mailbox; a
+// one-warp kernel per primitive picks the global winner out of this rank's own mailbox; both winners are refitted
+// (every rank holds the same scan, so every rank ends with the same models).  No host synchronisation, no library
+// collective, no copies: 2 x (hypotheses + count/argmax/send + receive) + refits.
+gm_status gm_ransac_sharded(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
+  if (!ctx || Hp <= 0 || Hc <= 0 || !plane_samples_host || !cyl_samples_host) return GM_ERR_INVALID_ARG;
+  if (!ctx->comm) { ctx->err = "gm_ransac_sharded needs gm_set_comm"; return GM_ERR_STAGE_ORDER; }
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  const int W = ctx->comm->world, R = ctx->comm->rank;
+  auto range = [&](int H, int& b, int& e) { const int per = (H + W - 1) / W; b = std::min(R * per, H); e = std::min((R + 1) * per, H); };
+  int pb, pe, cb, ce;
+  range(Hp, pb, pe); range(Hc, cb, ce);
+  gm_status s;
+  ctx->sharded = true;
+  auto recv = [&](int kind, int H) -> gm_status {
+    GM_LAUNCH(ctx, k_comm_recv_model, 1, 32, ctx->comm->h_dev, kind, H, ctx->d_key + kind, ctx->d_plane_coef, ctx->d_model7, ctx->d_test12,
+              ctx->d_counts[kind], &ctx->d_st->error);
+    GM_CHECK_LAUNCHES(ctx);
+    return GM_OK;
+  };
+  auto plane = [&]() -> gm_status {
+    gm_status r = gm_ransac(ctx, GM_MODEL_PLANE, plane_samples_host, Hp, pb, pe);
+    if (r == GM_OK) r = recv(0, Hp);
+    return r != GM_OK ? r : gm_ransac_select(ctx, GM_MODEL_PLANE);
+  };
+  auto cylinder = [&]() -> gm_status {
+    gm_status r = gm_ransac(ctx, GM_MODEL_CYLINDER, cyl_samples_host, Hc, cb, ce);
+    if (r == GM_OK) r = recv(1, Hc);
+    return r != GM_OK ? r : gm_ransac_select(ctx, GM_MODEL_CYLINDER);
+  };
+  if (ctx->concurrent && !ctx->profiling) {
+    cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);
+    if (e != cudaSuccess) { ctx->sharded = false; ctx->err = cudaGetErrorString(e); return GM_ERR_CUDA; }
+    s = run_branch(ctx, 1, plane);
+    if (s == GM_OK) s = cylinder();
+    if (s == GM_OK && cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0) != cudaSuccess) s = GM_ERR_CUDA;
+  } else {
+    s = plane();
+    if (s == GM_OK) s = cylinder();
+  }
+  ctx->sharded = false;
+  return s;
+}
+
+// map slabs: MIN/MAX of the bounding boxes of the compacted clouds of all ranks, in place in device state (after
+// gm_normals, before gm_voxel): every slab then builds its voxels on ONE lattice.  One kernel, no host round trip.
+gm_status gm_allreduce_voxel_bbox(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->comm) { ctx->err = "needs gm_set_comm"; return GM_ERR_STAGE_ORDER; }
+  if (!ctx->have_compacted) return GM_ERR_STAGE_ORDER;
+  GM_LAUNCH(ctx, k_comm_bbox, 1, 32, ctx->comm->h_dev, ctx->d_st->vox.bbox_min, ctx->d_st->vox.bbox_max, &ctx->d_st->error);
+  GM_CHECK_LAUNCHES(ctx);
+  return GM_OK;
+}
+
+// map slabs: the local frame of the WHOLE map = eigen-decomposition of the sum of the slabs' scatter matrices
+// (getLocalFrame, src/tunnel_processing.cpp:92-148, applied to all normals of all ranks).  After gm_local_frame.
+gm_status gm_allreduce_frame(gm_ctx* ctx) {
+  if (!ctx) return GM_ERR_INVALID_ARG;
+  if (!ctx->comm) { ctx->err = "needs gm_set_comm"; return GM_ERR_STAGE_ORDER; }
+  if (!ctx->have_frame) return GM_ERR_STAGE_ORDER;
+  GM_LAUNCH(ctx, k_comm_sum, 1, 32, ctx->comm->h_dev, ctx->d_frame_sums, 6, &ctx->d_st->error);
+  GM_LAUNCH(ctx, k_frame_solve, 1, 32, ctx->d_frame_sums, ctx->d_frame);
+  GM_CHECK_LAUNCHES(ctx);
+  return GM_OK;
 }
 
 }  // extern "C"

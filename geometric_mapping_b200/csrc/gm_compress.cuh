@@ -50,7 +50,7 @@ __device__ __forceinline__ void d_comp_frame(const ModelState* plane, const Mode
 __global__ void __launch_bounds__(CP_BLOCK, 3)
 k_comp_split(const float4* __restrict__ pts, const unsigned char* __restrict__ labels, const int* __restrict__ n_ptr,
              const ModelState* __restrict__ plane, const ModelState* __restrict__ cyl, int have_plane, int have_cyl,
-             float4* __restrict__ res_pts, VoxState* res_vs, unsigned long long* state, unsigned epoch, int* err,
+             float4* __restrict__ res_pts, VoxState* res_vs, unsigned long long* state, TileCtl* ctl, int* err,
              double* __restrict__ part_sum /* CS_NV x grid */, unsigned long long* __restrict__ part_mm /* 6 x grid */,
              unsigned* ticket, CompStats* out) {
   __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
@@ -59,7 +59,8 @@ k_comp_split(const float4* __restrict__ pts, const unsigned char* __restrict__ l
   __shared__ float s_red[6][CP_BLOCK / 32];
   __shared__ double fin[CS_NV];
   const int n = *n_ptr;
-  const int tile = blockIdx.x, base = tile * CP_TILE;
+  unsigned epoch;
+  const int tile = tile_begin(ctl, epoch), base = tile * CP_TILE;
   CompFrame F;
   d_comp_frame(plane, cyl, have_plane, have_cyl, F);
   bool f[CP_IPT];
@@ -104,6 +105,7 @@ k_comp_split(const float4* __restrict__ pts, const unsigned char* __restrict__ l
       if (f[j]) res_pts[ranks[j]] = p[j];
     if (base + CP_TILE >= n && threadIdx.x == 0) res_vs->n = (int)total;
   }
+  tile_end(ctl);
   // residual bounding box (order independent)
   const int w = threadIdx.x >> 5;
 #pragma unroll

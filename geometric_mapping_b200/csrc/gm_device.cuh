@@ -12,9 +12,10 @@ namespace gm {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-// Spin bound for every inter-block wait.  A predecessor tile is always resident or finished
-// (tiles are taken in launch order), so the bound is never reached in a correct run; if it is,
-// the kernel raises device_error instead of hanging the GPU.
+// Spin bound for every inter-block wait.  A predecessor tile is always resident or finished (tile
+// indices are handed out by an atomic ticket, see TileCtl: whoever holds ticket t started after the
+// holders of 0..t-1), so the bound is never reached in a correct run; if it is, the kernel raises
+// device_error instead of hanging the GPU.
 constexpr int SPIN_BOUND = 1 << 22;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -144,6 +145,39 @@ __device__ __forceinline__ unsigned ts_load(const unsigned long long* p, unsigne
   return ((hi >> 2) == (epoch & TS_EPOCH_MASK)) ? (hi & 3u) : TS_EMPTY;
 }
 
+// Launch control of the look-back kernels, one per tile-state array, resident in device memory so that a launch needs
+// no per-launch host argument (the whole scan is replayed as a CUDA graph):
+//  * TILE INDICES come from an atomic ticket, not from blockIdx.x: CUDA does not promise that blocks are dispatched in
+//    index order, and a tile that waits for a predecessor which has not been scheduled yet could spin forever.  With
+//    tickets every predecessor of tile t is, by construction, already running or done.
+//  * The EPOCH of the launch is read from here by every block when it takes its ticket; the last block to FINISH
+//    (all tickets taken, all reads done) resets ticket/done and advances the epoch for the next launch on the stream.
+struct TileCtl { unsigned ticket, done, epoch, pad_; };
+
+// Every block of a look-back kernel: first statement / before every return.  gridDim.x blocks take part.
+__device__ __forceinline__ int tile_begin(TileCtl* c, unsigned& epoch) {
+  __shared__ int s_tile;
+  __shared__ unsigned s_epoch;
+  if (threadIdx.x == 0) {
+    s_tile = (int)atomicAdd(&c->ticket, 1u);
+    s_epoch = *(volatile unsigned*)&c->epoch;
+  }
+  __syncthreads();
+  epoch = s_epoch;
+  return s_tile;
+}
+__device__ __forceinline__ void tile_end(TileCtl* c) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&c->done, 1u) == gridDim.x - 1u) {
+      c->done = 0u; c->ticket = 0u;
+      c->epoch = (*(volatile unsigned*)&c->epoch + 1u) & 0x3FFFFFFFu;
+      __threadfence();
+    }
+  }
+}
+
 // Warp-cooperative look-back: returns the exclusive prefix of tile `tile` (sum of aggregates of
 // all earlier tiles).  Call with all 32 lanes of one warp.  `err` is raised on spin-bound.
 // Each round inspects a window of 128 predecessor tiles: every lane issues 4 independent loads
@@ -187,7 +221,7 @@ __device__ __forceinline__ unsigned lookback_exclusive(const unsigned long long*
 // Tile = BLOCK threads x IPT items, striped (item j of thread t is tile_base + j*BLOCK + t) so
 // that global loads are coalesced.  flags[j] in, ranks[j] out (exclusive rank among the flagged
 // items of the whole input, i.e. the output position), plus the running total.
-// `epoch` must differ from the epoch of the previous launch that used `state`; tiles are blockIdx.x.
+// `epoch` must differ from the epoch of the previous launch that used `state` and `tile` comes from tile_begin().
 template <int BLOCK, int IPT>
 struct CompactSmem {
   unsigned warp_cnt[IPT * (BLOCK / 32)];

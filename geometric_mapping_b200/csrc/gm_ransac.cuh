@@ -6,6 +6,7 @@
 // oracle uses (bit-identical coefficients); the inlier tests are explicit fmaf chains.
 #pragma once
 #include "gm_stages.cuh"
+#include "gm_comm.cuh"
 
 namespace gm {
 
@@ -13,9 +14,12 @@ namespace gm {
 // plane: samples H x 3 -> coef float4 {a,b,c,d}, valid
 __global__ void k_plane_hypotheses(const float4* __restrict__ pts, const int* __restrict__ n_ptr,
                                    const int* __restrict__ samples, int H, float4* __restrict__ coef,
-                                   int* __restrict__ valid, int* __restrict__ counts, int h_begin, int h_end) {
+                                   int* __restrict__ valid, int* __restrict__ counts, int h_begin, int h_end, int gen_all) {
   const int n = *n_ptr;
   for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+    const bool mine = h >= h_begin && h < h_end;
+    // gen_all = 0 (peer-memory sharded round): another rank's hypothesis is not generated, its samples are not even here
+    if (!mine && !gen_all) { counts[h] = -1; valid[h] = 0; continue; }
     int i0 = samples[h * 3], i1 = samples[h * 3 + 1], i2 = samples[h * 3 + 2];
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
     int ok = 0;
@@ -36,7 +40,7 @@ __global__ void k_plane_hypotheses(const float4* __restrict__ pts, const int* __
     }
     coef[h] = c;
     valid[h] = ok;
-    counts[h] = (h >= h_begin && h < h_end && ok) ? 0 : -1;  // -1: degenerate or not this rank's id
+    counts[h] = (mine && ok) ? 0 : -1;  // -1: degenerate or not this rank's id
   }
 }
 
@@ -82,9 +86,11 @@ __global__ void k_cyl_hypotheses(const float4* __restrict__ pts, const float4* _
                                  const int* __restrict__ n_ptr, const int* __restrict__ samples, int H,
                                  float rmin, float rmax, float tau, float* __restrict__ model7,
                                  float* __restrict__ test12, int* __restrict__ valid, int* __restrict__ counts,
-                                 int h_begin, int h_end) {
+                                 int h_begin, int h_end, int gen_all) {
   const int n = *n_ptr;
   for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+    const bool mine = h >= h_begin && h < h_end;
+    if (!mine && !gen_all) { counts[h] = -1; valid[h] = 0; continue; }  // another rank's hypothesis
     float m[7] = {0, 0, 0, 0, 0, 0, 0};
     float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int ok = 0;
@@ -132,7 +138,7 @@ __global__ void k_cyl_hypotheses(const float4* __restrict__ pts, const float4* _
     for (int k = 0; k < 7; ++k) model7[(size_t)h * 7 + k] = m[k];
     for (int k = 0; k < 12; ++k) test12[(size_t)h * 12 + k] = t[k];
     valid[h] = ok;
-    counts[h] = (h >= h_begin && h < h_end && ok) ? 0 : -1;
+    counts[h] = (mine && ok) ? 0 : -1;
   }
 }
 
@@ -176,12 +182,12 @@ __device__ __forceinline__ void d_count_lt(float v, float thr, int& cnt) {
 __device__ __forceinline__ unsigned long long d_key_of(int count, int h) {
   return ((unsigned long long)(unsigned)(count + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
 }
-// block-wide argmax over counts[0..H) (read through L2: other blocks produced them with atomics)
+// block-wide argmax over counts[h_begin..h_end) (read through L2: other blocks produced them with atomics)
 template <int BLOCK>
-__device__ __forceinline__ void d_block_argmax(const int* counts, int H, unsigned long long* key_out) {
+__device__ __forceinline__ void d_block_argmax(const int* counts, int h_begin, int h_end, unsigned long long* key_out) {
   __shared__ unsigned long long s_best[BLOCK / 32];
   unsigned long long best = 0ull;
-  for (int h = threadIdx.x; h < H; h += BLOCK) {
+  for (int h = h_begin + threadIdx.x; h < h_end; h += BLOCK) {
     unsigned long long k = d_key_of(__ldcg(counts + h), h);
     best = (k > best) ? k : best;
   }
@@ -195,6 +201,20 @@ __device__ __forceinline__ void d_block_argmax(const int* counts, int H, unsigne
   if (threadIdx.x == 0) {
     for (int w = 1; w < BLOCK / 32; ++w) best = (s_best[w] > best) ? s_best[w] : best;
     *key_out = best;
+    s_best[0] = best;
+  }
+  __syncthreads();
+}
+// ... and, in a hypothesis-sharded round, straight into the mailboxes of all peers (gm_comm.cuh): the block that
+// reduces the local best model also ships it, with the winner's coefficients
+template <int BLOCK>
+__device__ __forceinline__ void d_block_argmax_send(const int* counts, int h_begin, int h_end, unsigned long long* key_out, const CommDev* comm, int kind,
+                                                    const float4* __restrict__ plane_coef, const float* __restrict__ model7,
+                                                    const float* __restrict__ test12, int H) {
+  d_block_argmax<BLOCK>(counts, h_begin, h_end, key_out);
+  if (comm != nullptr && threadIdx.x < 32) {
+    const unsigned long long key = *(volatile unsigned long long*)key_out;
+    d_comm_send_model(*comm, kind, key, plane_coef, model7, test12, H);
   }
 }
 
@@ -216,7 +236,7 @@ template <int K>
 __global__ void __launch_bounds__(RC_BLOCK)
 k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float4* __restrict__ coef,
               const int* __restrict__ valid, int h_begin, int h_end, float tau, int* __restrict__ counts,
-              int H, unsigned long long* key_out, unsigned* ticket) {
+              int H, unsigned long long* key_out, unsigned* ticket, const CommDev* comm) {
   __shared__ __align__(16) float sx[RC_TILE], sy[RC_TILE], sz[RC_TILE];
   const int n = *n_ptr;
   const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
@@ -261,13 +281,15 @@ k_count_plane(const float4* __restrict__ pts, const int* __restrict__ n_ptr, con
     if (h < h_end && cnt[k]) atomicAdd(&counts[h], cnt[k]);
   }
   // the last block to finish reduces the local best model (saves a launch)
-  if (d_last_block(ticket, gridDim.x * gridDim.y)) d_block_argmax<RC_BLOCK>(counts, H, key_out);
+  if (d_last_block(ticket, gridDim.x * gridDim.y))
+    d_block_argmax_send<RC_BLOCK>(counts, h_begin, h_end, key_out, comm, 0, coef, nullptr, nullptr, H);
 }
 
 template <int K>
 __global__ void __launch_bounds__(RC_BLOCK)
 k_count_cyl(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const float* __restrict__ test12,
-            int h_begin, int h_end, int* __restrict__ counts, int H, unsigned long long* key_out, unsigned* ticket) {
+            int h_begin, int h_end, int* __restrict__ counts, int H, unsigned long long* key_out, unsigned* ticket,
+            const CommDev* comm, const float* __restrict__ model7) {
   __shared__ __align__(16) float sx[RC_TILE], sy[RC_TILE], sz[RC_TILE];
   const int n = *n_ptr;
   const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
@@ -324,7 +346,8 @@ k_count_cyl(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const
     if (h < h_end && cnt[k]) atomicAdd(&counts[h], cnt[k]);
   }
   // the last block to finish reduces the local best model (saves a launch)
-  if (d_last_block(ticket, gridDim.x * gridDim.y)) d_block_argmax<RC_BLOCK>(counts, H, key_out);
+  if (d_last_block(ticket, gridDim.x * gridDim.y))
+    d_block_argmax_send<RC_BLOCK>(counts, h_begin, h_end, key_out, comm, 1, nullptr, model7, test12, H);
 }
 
 // ---- tile-culled inlier counting ---------------------------------------------------------------
@@ -411,7 +434,8 @@ template <int KIND>
 __global__ void __launch_bounds__(TC_BLOCK)
 k_count_tiles(const float4* __restrict__ sv, const float4* __restrict__ leaf_bounds, const int* __restrict__ n_ptr,
               const float4* __restrict__ plane_coef, const float* __restrict__ test12, const int* __restrict__ valid,
-              int h_begin, int h_end, float tau, int* __restrict__ counts, int H, unsigned long long* key_out, unsigned* ticket) {
+              int h_begin, int h_end, float tau, int* __restrict__ counts, int H, unsigned long long* key_out, unsigned* ticket,
+              const CommDev* comm, const float* __restrict__ model7) {
   __shared__ __align__(16) float sx[TC_SUPER], sy[TC_SUPER], sz[TC_SUPER];
   __shared__ TileBox s_leaf[TC_LEAVES];
   __shared__ TileBox s_super;
@@ -565,12 +589,15 @@ k_count_tiles(const float4* __restrict__ sv, const float4* __restrict__ leaf_bou
       // (the next chunk's first barrier orders these reads before the lists / counts are rebuilt)
     }
   }
-  if (d_last_block(ticket, gridDim.x)) d_block_argmax<TC_BLOCK>(counts, H, key_out);
+  if (d_last_block(ticket, gridDim.x))
+    d_block_argmax_send<TC_BLOCK>(counts, h_begin, h_end, key_out, comm, KIND, plane_coef, model7, test12, H);
 }
 
 constexpr int AM_BLOCK = 256;
-__global__ void __launch_bounds__(AM_BLOCK) k_argmax(const int* __restrict__ counts, int H, unsigned long long* key_out) {
-  d_block_argmax<AM_BLOCK>(counts, H, key_out);
+__global__ void __launch_bounds__(AM_BLOCK) k_argmax(const int* __restrict__ counts, int H, unsigned long long* key_out, const CommDev* comm, int kind,
+                                                      const float4* __restrict__ plane_coef, const float* __restrict__ model7,
+                                                      const float* __restrict__ test12) {
+  d_block_argmax_send<AM_BLOCK>(counts, 0, H, key_out, comm, kind, plane_coef, model7, test12, H);
 }
 
 // ---- selection + refit ----------------------------------------------------------------------
@@ -683,13 +710,15 @@ __device__ __forceinline__ void d_perp_basis_d(const double dir[3], double u[3],
 __global__ void __launch_bounds__(CP_BLOCK, 4)
 k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const unsigned long long* __restrict__ key, int H,
                      const float* __restrict__ model7, const float* __restrict__ test12, ModelState* ms,
-                     float4* __restrict__ inl, unsigned long long* state, unsigned epoch, int* err) {
+                     float4* __restrict__ inl, unsigned long long* state, TileCtl* ctl, int* err) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = *n_ptr;
-  const int tile = blockIdx.x, base = tile * CPL_TILE;
+  unsigned epoch;
+  const int tile = tile_begin(ctl, epoch), base = tile * CPL_TILE;
   if (base >= n) {
     // empty cloud: tile 0 still has to publish the (empty) model state
     if (tile == 0 && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = 0; }
+    tile_end(ctl);
     return;
   }
   // every block decodes the winner itself (k_select folded in)
@@ -712,6 +741,7 @@ k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_p
   for (int j = 0; j < CPL_IPT; ++j)
     if (f[j]) inl[ranks[j]] = p[j];
   if (base + CPL_TILE >= n && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = (int)total; }
+  tile_end(ctl);
 }
 
 __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
@@ -760,14 +790,19 @@ __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target,
 
 __global__ void __launch_bounds__(RF_BLOCK)
 k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float tau, double* __restrict__ partials /* 2 x grid x 22 */,
-             unsigned* barrier_count, unsigned* barrier_next, int* err) {
+             unsigned* bars /* [0],[1] barrier counters used alternately, [2] which one this launch uses */, int* err) {
   __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
   __shared__ double fin[GN_NV];
   __shared__ double it_q[3], it_dir[3], it_r;
   __shared__ int s_converged;
   // two barrier counters used alternately by consecutive launches: this launch counts on
   // barrier_count from 0 and clears the other one for the next launch (the number of passes is
-  // data dependent, so the host cannot pre-compute a cumulative target)
+  // data dependent, so a cumulative target cannot be pre-computed).  Which one is whose lives in device
+  // memory too (bars[2], toggled by block 0 after the last barrier, i.e. after every block has read it),
+  // so that consecutive launches need no host-side argument: the launch is replayable from a CUDA graph.
+  const unsigned par = *(volatile unsigned*)&bars[2] & 1u;
+  unsigned* barrier_count = bars + par;
+  unsigned* barrier_next = bars + (par ^ 1u);
   if (blockIdx.x == 0 && threadIdx.x == 0) *barrier_next = 0u;
   const bool have = ms->best_id >= 0;
   const int n = have ? ms->n_inl : 0;
@@ -849,6 +884,7 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
     // every block computed the same step from the same partials, so this is grid-uniform
     if (update && s_converged && it < iters - 1) it = iters - 1;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { bars[2] = par ^ 1u; __threadfence(); }
 }
 
 // labels from the refined models: 1 = plane inlier, else 2 = cylinder inlier, else 0

@@ -26,6 +26,7 @@ __device__ __forceinline__ void d_vox_reset(VoxState* v) {
 }
 
 struct DevState {
+  const float4* scan;   // the input scan of this context (set by k_begin_scan; read by k_crop)
   int n_input, n_crop, n_valid, n_cells, nn_oor, error;
   int n_sorted_finite;  // cropped points with finite coordinates (sorted before the NaN tail)
   int tab_cells;        // occupied cells currently recorded in the block table (cleared by the next build)
@@ -131,8 +132,9 @@ constexpr int CPL_TILE = CP_BLOCK * CPL_IPT;
 __device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_begin_scan(DevState* st, int n_input) {
+__global__ void k_begin_scan(DevState* st, int n_input, const float4* scan) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->scan = scan;
     st->n_input = n_input; st->n_crop = 0; st->n_valid = 0; st->n_cells = 0;
     st->nn_oor = 0; st->error = 0; st->n_sorted_finite = 0;  // tab_cells survives: it describes the block table
     st->n_candidates = 0ull; st->n_neighbors = 0ull;
@@ -169,11 +171,14 @@ __global__ void k_set_w_one(float4* p, int n) {
 // a1 chopCloud / pcl::CropBox (src/tunnel_processing.cpp:39-49): stable compaction of
 // the points with every coordinate in [lo,hi]; NaN handling per is_dense.
 __global__ void __launch_bounds__(CP_BLOCK, 4)
-k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, float4* __restrict__ out,
-       unsigned long long* state, unsigned epoch, DevState* st) {
+k_crop(const DevState* __restrict__ scan, float lo, float hi, int is_dense, float4* __restrict__ out,
+       unsigned long long* state, TileCtl* ctl, DevState* st) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
-  const int tile = blockIdx.x, base = tile * CPL_TILE;
-  if (base >= n) return;
+  unsigned epoch;
+  const int tile = tile_begin(ctl, epoch), base = tile * CPL_TILE;
+  const int n = scan->n_input;                      // written by k_begin_scan: the launch itself carries no per-scan argument
+  const float4* __restrict__ in = scan->scan;
+  if (base >= n) { tile_end(ctl); return; }
   float4 p[CPL_IPT];
   bool f[CPL_IPT];
 #pragma unroll
@@ -193,6 +198,7 @@ k_crop(const float4* __restrict__ in, int n, float lo, float hi, int is_dense, f
   for (int j = 0; j < CPL_IPT; ++j)
     if (f[j]) out[ranks[j]] = p[j];
   if (base + CPL_TILE >= n && threadIdx.x == 0) st->n_crop = (int)total;
+  tile_end(ctl);
 }
 
 // Neighbour-grid cell key of every cropped point (sentinel ncells for non-finite points, which
@@ -219,11 +225,12 @@ __global__ void __launch_bounds__(CP_BLOCK)
 k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, const float4* __restrict__ pts,
              const int* __restrict__ n_ptr, unsigned sentinel, float4* __restrict__ sorted_pts, int* __restrict__ cell_id,
              unsigned* __restrict__ ucell_key, int* __restrict__ ucell_start, BlockEntry* __restrict__ tab,
-             unsigned long long* state, unsigned epoch, DevState* st) {
+             unsigned long long* state, TileCtl* ctl, DevState* st) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = *n_ptr;
-  const int tile = blockIdx.x, base = tile * CPL_TILE;
-  if (base >= n) return;
+  unsigned epoch;
+  const int tile = tile_begin(ctl, epoch), base = tile * CPL_TILE;
+  if (base >= n) { tile_end(ctl); return; }
   bool f[CPL_IPT], bh[CPL_IPT];
   unsigned key[CPL_IPT];
   int nfinite_local = 0;
@@ -267,6 +274,7 @@ k_cell_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ si
     }
   }
   if (base + CPL_TILE >= n && threadIdx.x == 0) { st->n_cells = (int)total; st->tab_cells = (int)total; }
+  tile_end(ctl);
 }
 
 // Clear the block-table entries of the previous build (its sorted cell list is still in ucell_key).
@@ -621,12 +629,13 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 __global__ void __launch_bounds__(CP_BLOCK)
 k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ normals, const int* __restrict__ n_ptr,
                 float4* __restrict__ pts_c, float4* __restrict__ normals_c, int* __restrict__ valid_map,
-                unsigned long long* state, unsigned epoch, DevState* st, OwnedRange own) {
+                unsigned long long* state, TileCtl* ctl, DevState* st, OwnedRange own) {
   __shared__ CompactSmem<CP_BLOCK, CP_IPT> sm;
   __shared__ float s_red[6][CP_BLOCK / 32];
   const int n = *n_ptr;
-  const int tile = blockIdx.x, base = tile * CP_TILE;
-  if (base >= n) return;
+  unsigned epoch;
+  const int tile = tile_begin(ctl, epoch), base = tile * CP_TILE;
+  if (base >= n) { tile_end(ctl); return; }
   bool f[CP_IPT];
   float4 p[CP_IPT], n0[CP_IPT], n1[CP_IPT];
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -676,6 +685,7 @@ k_compact_valid(const float4* __restrict__ pts, const float4* __restrict__ norma
       atomicMax(&st->vox.bbox_max[threadIdx.x], float_to_ordered(hi));
     }
   }
+  tile_end(ctl);
 }
 
 // Replace the bounding box of the compacted cloud (all-reduced box of all map slabs -> one global lattice).
@@ -829,9 +839,10 @@ k_voxel_accumulate_sorted(const float4* __restrict__ sv, const int* __restrict__
 __global__ void __launch_bounds__(CP_BLOCK)
 k_voxel_dense_scan(int* __restrict__ dcnt, long long* __restrict__ dsum, int* __restrict__ did, int range,
                    int* __restrict__ vox_key, int* __restrict__ vox_count, float4* __restrict__ centroids,
-                   unsigned long long* state, unsigned epoch, VoxState* st, int* err) {
+                   unsigned long long* state, TileCtl* ctl, VoxState* st, int* err) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
-  const int tile = blockIdx.x, base = tile * CPL_TILE;
+  unsigned epoch;
+  const int tile = tile_begin(ctl, epoch), base = tile * CPL_TILE;
   bool f[CPL_IPT];
   int c[CPL_IPT];
 #pragma unroll
@@ -855,6 +866,7 @@ k_voxel_dense_scan(int* __restrict__ dcnt, long long* __restrict__ dsum, int* __
     dcnt[k] = 0; sp[0] = 0; sp[1] = 0; sp[2] = 0;  // self-cleaning
   }
   if (tile == (int)gridDim.x - 1 && threadIdx.x == 0) st->n_voxels = (int)total;
+  tile_end(ctl);
 }
 
 // point -> voxel id (and its key, recomputed from the point: cheaper than carrying it through the sorted pass)
@@ -874,12 +886,13 @@ __global__ void k_voxel_assign(const float4* __restrict__ pts, VoxState* st, flo
 // the voxel rank of every point.
 __global__ void __launch_bounds__(CP_BLOCK)
 k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ sidx, int* __restrict__ assign,
-              int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, unsigned epoch, VoxState* st,
+              int* __restrict__ vox_start, int* __restrict__ vox_key, unsigned long long* state, TileCtl* ctl, VoxState* st,
               int* err) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
   const int n = st->n;
-  const int tile = blockIdx.x, base = tile * CPL_TILE;
-  if (base >= n) return;
+  unsigned epoch;
+  const int tile = tile_begin(ctl, epoch), base = tile * CPL_TILE;
+  if (base >= n) { tile_end(ctl); return; }
   bool f[CPL_IPT];
   unsigned key[CPL_IPT];
 #pragma unroll
@@ -903,6 +916,7 @@ k_voxel_heads(const unsigned* __restrict__ skeys, const unsigned* __restrict__ s
     }
   }
   if (base + CPL_TILE >= n && threadIdx.x == 0) st->n_voxels = (int)total;
+  tile_end(ctl);
 }
 
 // Centroid per voxel (sort-based path): fixed-point sums of the members (same order-independent definition as
@@ -1108,9 +1122,19 @@ __device__ __forceinline__ float d_weight(const WeightLaw& w, float curv) {
 constexpr int FR_BLOCK = 256;
 struct FrameOut { float vals[3]; float vecs[9]; float scatter[9]; };
 
+// 6 double sums (xx xy xz yy yz zz) -> float scatter matrix (the reference's is float), eigen-decomposition
+__device__ __forceinline__ void d_frame_solve(const double* fin, FrameOut* out) {
+  float Sf[9] = {(float)fin[0], (float)fin[1], (float)fin[2], (float)fin[1], (float)fin[3], (float)fin[4], (float)fin[2], (float)fin[4], (float)fin[5]};
+  double Sd[9], vals[3], vecs[9];
+  for (int k = 0; k < 9; ++k) { Sd[k] = Sf[k]; out->scatter[k] = Sf[k]; }
+  d_jacobi3(Sd, vals, vecs);
+  for (int k = 0; k < 3; ++k) out->vals[k] = (float)vals[k];
+  for (int k = 0; k < 9; ++k) out->vecs[k] = (float)vecs[k];
+}
+
 __global__ void __launch_bounds__(FR_BLOCK)
 k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, WeightLaw law, double* __restrict__ partials,
-        unsigned* counter, FrameOut* out) {
+        unsigned* counter, FrameOut* out, double* __restrict__ sums_out /* [6] the double sums, for gm_allreduce_frame */) {
   __shared__ double sm[6 * (FR_BLOCK / 32)];
   __shared__ double fin[6];
   const int n = *n_ptr;
@@ -1127,12 +1151,13 @@ k_frame(const float4* __restrict__ normals_c, const int* __restrict__ n_ptr, Wei
   if (!d_last_block(counter, gridDim.x)) return;
   d_reduce_partials<6>(partials, gridDim.x, fin);
   if (threadIdx.x != 0) return;
-  float Sf[9] = {(float)fin[0], (float)fin[1], (float)fin[2], (float)fin[1], (float)fin[3], (float)fin[4], (float)fin[2], (float)fin[4], (float)fin[5]};
-  double Sd[9], vals[3], vecs[9];
-  for (int k = 0; k < 9; ++k) { Sd[k] = Sf[k]; out->scatter[k] = Sf[k]; }
-  d_jacobi3(Sd, vals, vecs);
-  for (int k = 0; k < 3; ++k) out->vals[k] = (float)vals[k];
-  for (int k = 0; k < 9; ++k) out->vecs[k] = (float)vecs[k];
+  for (int k = 0; k < 6; ++k) sums_out[k] = fin[k];
+  d_frame_solve(fin, out);
+}
+
+// the frame of the SUM of the scatter matrices of several contexts / ranks (map slabs): same solve, other sums
+__global__ void k_frame_solve(const double* __restrict__ sums6, FrameOut* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) d_frame_solve(sums6, out);
 }
 
 }  // namespace gm

@@ -7,7 +7,12 @@
   count).  The key fits a signed int64 because count + 1 < 2^31.
 * Multi-frame batches are split by frame (frame f -> rank f mod W); no collective on the data path.
 
-torch.distributed is the transport (NCCL over NVLink on GPUs, gloo on CPU for the tests).
+torch.distributed is the PLUMBING (rendezvous, barriers, the one-off exchange of the mailbox handles, gloo on CPU for
+the tests).  The data-path collectives themselves -- the (count,id) MAX of a sharded RANSAC round, the bounding-box
+MIN/MAX and the scatter-matrix SUM of the map slabs -- are kernels of the library over NVLink peer memory
+(csrc/gm_comm.cuh, `connect_peers` + `Context.ransac_sharded / allreduce_voxel_bbox / allreduce_frame`); the
+torch.distributed forms of the same collectives (`sharded_ransac_pair`, `allreduce_bbox`) remain as the portable path and
+as the cross-check.
 """
 from __future__ import annotations
 
@@ -208,3 +213,106 @@ def process_map_slab(ctx, slab_points, axis: int, lo: float, hi: float, plane_sa
     if compress:
         ctx.compress()
     return gmn, gmx
+
+
+# ---------------------------------------------------------------------------------------------
+# Peer-memory collectives: connect the mailboxes of all ranks once, then the library does the rest on the GPU.
+def connect_peers(group=None):
+    """-> capi.PeerComm connected to every rank of `group` (one process per GPU on one node).  The only use of
+    torch.distributed is one all_gather of the 64-byte IPC handles."""
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return capi.PeerComm(0, 1)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    comm = capi.PeerComm(rank, world)
+    if world == 1:
+        return comm
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor(list(comm.handle()), dtype=torch.uint8, device=dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    comm.connect(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+    dist.barrier(group=group)  # nobody sends before everybody has mapped everybody
+    return comm
+
+
+def merge_slab_voxels(parts):
+    """Whole-map VoxelGrid from the per-slab results.  `parts` = list of (keys int32, centroids n x 4, counts int32) in any
+    order; slabs cut at voxel faces on one lattice own disjoint keys, so the map is their union in ascending key order
+    (= the output order of pcl::VoxelGrid over the whole cloud)."""
+    import numpy as np
+
+    keys = np.concatenate([np.asarray(p[0], np.int32) for p in parts]) if parts else np.empty(0, np.int32)
+    cen = np.concatenate([np.asarray(p[1], np.float32).reshape(-1, 4) for p in parts]) if parts else np.empty((0, 4), np.float32)
+    cnt = np.concatenate([np.asarray(p[2], np.int32) for p in parts]) if parts else np.empty(0, np.int32)
+    order = np.argsort(keys.view(np.uint32), kind="stable")
+    keys, cen, cnt = keys[order], cen[order], cnt[order]
+    if len(keys) > 1 and (keys[1:] == keys[:-1]).any():
+        raise ValueError("slabs share a voxel: they were not cut at voxel faces of one lattice")
+    return keys, cen, cnt
+
+
+def gather_slab_voxels(ctx, group=None):
+    """All-gather of the slabs' voxels (keys, centroids, counts) -> the whole-map VoxelGrid on every rank.
+    Variable sizes: one all_gather of the counts, then padded all_gathers."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    vox = ctx.download_voxels(with_nn=False)
+    mine = (vox["keys"], vox["centroids"], vox["counts"])
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return merge_slab_voxels([mine])
+    world = dist.get_world_size(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    n = torch.tensor([len(mine[0])], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    sizes = [int(t.item()) for t in ns]
+    cap = max(max(sizes), 1)
+    buf = np.zeros((cap, 6), np.float32)  # key and count travel as bit patterns beside the centroid
+    k = len(mine[0])
+    buf[:k, 0:4] = mine[1]
+    buf[:k, 4] = mine[0].view(np.float32)
+    buf[:k, 5] = mine[2].view(np.float32)
+    t = torch.from_numpy(buf).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    parts = []
+    for r in range(world):
+        a = out[r].cpu().numpy()[: sizes[r]]
+        parts.append((np.ascontiguousarray(a[:, 4]).view(np.int32), np.ascontiguousarray(a[:, 0:4]), np.ascontiguousarray(a[:, 5]).view(np.int32)))
+    return merge_slab_voxels(parts)
+
+
+def process_map_slab_peer(ctx, slab_points, axis: int, lo: float, hi: float, map_box, plane_samples=None, cyl_samples=None, grid_box=None,
+                          compress: bool = True):
+    """process_map_slab with the collectives on the device (ctx has a PeerComm attached): the bounding box is
+    all-reduced by one kernel between gm_normals and gm_voxel (no host round trip: `map_box` = (min3, max3) only promises
+    where the whole map lies, for the sizing of the VoxelGrid tables), and the local frame is that of the WHOLE map
+    (sum of all slabs' scatter matrices)."""
+    ctx.set_owned_range(axis, lo, hi)
+    if grid_box is not None:
+        ctx.set_grid_box(grid_box[0], grid_box[1])
+    ctx.set_voxel_bbox_hint(map_box[0], map_box[1])
+    ctx.upload_scan(slab_points)
+    ctx.crop()
+    ctx.normals()
+    ctx.allreduce_voxel_bbox()
+    ctx.voxel()
+    ctx.local_frame()
+    ctx.allreduce_frame()
+    if plane_samples is not None and len(plane_samples):
+        ctx.ransac(0, plane_samples)
+        ctx.ransac_select(0)
+    if cyl_samples is not None and len(cyl_samples):
+        ctx.ransac(1, cyl_samples)
+        ctx.ransac_select(1)
+    ctx.label()
+    ctx.axis_polyline()
+    if compress:
+        ctx.compress()

@@ -187,6 +187,10 @@ GM_API gm_status gm_set_grid_box(gm_ctx* ctx, const float* min3, const float* ma
 GM_API gm_status gm_set_owned_range(gm_ctx* ctx, int32_t axis, float lo, float hi);
 GM_API gm_status gm_get_voxel_bbox(gm_ctx* ctx, float* min3, float* max3);
 GM_API gm_status gm_set_voxel_bbox(gm_ctx* ctx, const float* min3, const float* max3);
+/* Same box used only as a BOUND: the VoxelGrid box is still computed from the cloud (and all-reduced over the ranks by
+ * gm_allreduce_voxel_bbox) on the device, but the promise that it lies inside [min3, max3] lets the sort-free dense
+ * tables be sized without a host round trip.  A point outside the promised box raises device_error. */
+GM_API gm_status gm_set_voxel_bbox_hint(gm_ctx* ctx, const float* min3, const float* max3);
 GM_API const char* gm_last_error(const gm_ctx* ctx);
 GM_API const char* gm_status_string(gm_status s);
 GM_API int32_t gm_version(void);
@@ -264,6 +268,13 @@ GM_API gm_status gm_download_compressed(gm_ctx* ctx, void* buf, size_t capacity,
  * + cylinder(Hc) -> select/refit -> labels -> polyline.  samples may be NULL when H == 0. */
 GM_API gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp,
                                  const int32_t* cyl_samples_host, int32_t Hc);
+
+/* gm_process_scan replays a CUDA graph: the first scan of a given (size bucket of 32768 points, Hp, Hc, parameters)
+ * runs as plain stream launches, the second is captured, every later one is ONE cudaGraphLaunch (33 kernels on three
+ * streams).  mode 0 = always plain launches, 1 = graphs (default; env GM_GRAPH=0 selects 0).  If the stream cannot
+ * be captured the library keeps working with plain launches; gm_get_graph_stats tells which happened. */
+GM_API gm_status gm_set_graph_mode(gm_ctx* ctx, int32_t mode);
+GM_API gm_status gm_get_graph_stats(const gm_ctx* ctx, int64_t* captures, int64_t* replays);
 
 /* ---- results (synchronise the ctx stream) ---------------------------------------------- */
 GM_API gm_status gm_get_counts(gm_ctx* ctx, gm_counts* out);
@@ -360,6 +371,34 @@ GM_API gm_status gm_map_download(gm_map* map, int32_t* ijk, int32_t* counts, flo
 GM_API gm_status gm_map_save(gm_map* map, const char* path);
 GM_API gm_status gm_map_load(const char* path, size_t min_capacity_voxels, gm_map** out);
 GM_API double gm_map_leaf(const gm_map* map);
+
+/* ---- multi-GPU data-path collectives over NVLink peer memory (builder-defined: the reference is one process,
+ * src/geometric_mapping.cpp:128-170) -------------------------------------------------------------------------------
+ * One process per GPU.  Every rank creates a gm_comm (a mailbox in its own HBM), publishes its 64-byte handle
+ * (cudaIpcMemHandle_t) to the others by any means (bench.py: one torch.distributed all_gather at start-up) and connects
+ * with the table of all handles (world x 64 bytes, entry r = rank r).  After that the collectives of the data path are
+ * kernels storing into the peers' mailboxes over NVLink and polling their own: no library call, no host round trip.
+ *   gm_ransac_sharded        hypotheses [0,H) split over the ranks (every rank holds the same scan): count own share,
+ *                            (count,id) MAX with the winner's coefficients through the mailboxes, refit -> same models
+ *                            on every rank.  Replaces gm_ransac_pair + export/all-reduce/import + gm_ransac_select_pair.
+ *   gm_allreduce_voxel_bbox  map slabs: MIN/MAX of the compacted clouds' bounding boxes (one VoxelGrid lattice)
+ *   gm_allreduce_frame       map slabs: SUM of the scatter matrices, re-solved: getLocalFrame of the whole map
+ * All ranks must issue the same sequence of these calls.  world = 1 works without peers (used by the tests). */
+typedef struct gm_comm gm_comm;
+GM_API gm_status gm_comm_create(int32_t rank, int32_t world, gm_comm** out);
+GM_API gm_status gm_comm_handle(gm_comm* comm, void* handle_64_bytes);
+GM_API gm_status gm_comm_connect(gm_comm* comm, const void* handles_world_x_64_bytes);
+/* peers inside one process (several devices driven by one process): mailbox addresses instead of IPC handles */
+GM_API gm_status gm_comm_mailbox(gm_comm* comm, void** mailbox_device_ptr);
+GM_API gm_status gm_comm_connect_local(gm_comm* comm, void* const* mailboxes_world);
+GM_API void gm_comm_destroy(gm_comm* comm);
+GM_API int32_t gm_comm_rank(const gm_comm* comm);
+GM_API int32_t gm_comm_world(const gm_comm* comm);
+GM_API const char* gm_comm_last_error(const gm_comm* comm);
+GM_API gm_status gm_set_comm(gm_ctx* ctx, gm_comm* comm);
+GM_API gm_status gm_ransac_sharded(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc);
+GM_API gm_status gm_allreduce_voxel_bbox(gm_ctx* ctx);
+GM_API gm_status gm_allreduce_frame(gm_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -65,7 +65,43 @@ def back(f, ps, cs, tau=0.05, rmin=0.5, rmax=10.0, refit_iters=5, wf=0.2, slice_
 # same raw points and sample indices (tests/test_gpu_chain.py:gpu_chain builds it).  Integer / index / bit-pattern
 # outputs are asserted exactly; floating-point outputs are measured and returned (the caller asserts the bars).
 def _bits(a):
-    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+    """Bit patterns with every NaN mapped to one canonical pattern (the NaN payload is not part of the contract:
+    the oracle writes 0x7FC00000, CUDA's CUDART_NAN_F is 0x7FFFFFFF)."""
+    b = np.ascontiguousarray(a, np.float32).view(np.uint32).copy()
+    b[np.isnan(np.ascontiguousarray(a, np.float32))] = 0x7FC00000
+    return b
+
+
+def gpu_chain(pts, ps, cs, canonical, radius, leaf, bound=5.0, tau=0.05, slice_len=1.0, refit_iters=5, knn=0):
+    """The same path on the CUDA library through the C-ABI: everything compare() looks at, downloaded."""
+    from geometric_mapping_b200 import capi
+
+    n = len(pts)
+    H = max(len(ps) if ps is not None else 0, len(cs) if cs is not None else 0, 1)
+    prm = capi.default_params(boxFilterBound=bound, neighborRadius=radius, voxelGridLeafSize=leaf, ransacThreshold=tau,
+                              sliceLength=slice_len, refitIterations=refit_iters)
+    with capi.Context(prm, max_points=max(n, 1), max_hypotheses=H) as ctx:
+        ctx.set_normals_mode(1 if canonical else 0)
+        if knn:
+            ctx.set_knn(knn)
+        ctx.upload_scan(pts)
+        ctx.process_scan(ps, cs)
+        c = ctx.counts()
+        assert c.device_error == 0
+        keys, assign, _ = ctx.download_voxel_assignment()
+        vox = ctx.download_voxels()
+        g = {"n_cropped": c.n_cropped, "n_valid": c.n_valid, "n_voxels": c.n_voxels, "cropped": ctx.download_cloud(0),
+             "normals": ctx.download_normals(0), "nbr_count": ctx.download_neighbor_counts(), "valid_map": ctx.download_valid_map(),
+             "cloud": ctx.download_cloud(1), "normals_c": ctx.download_normals(1), "grid6": ctx.voxel_grid(), "vox_key_pt": keys,
+             "vox_assign": assign, "vox_keys": vox["keys"], "vox_counts": vox["counts"], "centroids": vox["centroids"],
+             "nn_index": vox["nn_index"], "frame": ctx.frame(), "labels": ctx.download_labels(), "polyline": ctx.download_polyline()}
+        if ps is not None and len(ps):
+            g["plane_coef"], _, g["plane_counts"] = ctx.download_hypotheses(capi.GM_MODEL_PLANE, len(ps))
+            g["plane"] = ctx.model(capi.GM_MODEL_PLANE)
+        if cs is not None and len(cs):
+            g["cyl_model"], g["cyl_test"], g["cyl_counts"] = ctx.download_hypotheses(capi.GM_MODEL_CYLINDER, len(cs))
+            g["cyl"] = ctx.model(capi.GM_MODEL_CYLINDER)
+    return g
 
 
 def _angle(a, b):
@@ -112,11 +148,19 @@ def compare(g, f, b, exact_normals: bool):
         assert m["normals_bit_identical"], "normals (canonical summation order)"
         assert np.array_equal(_bits(g["normals_c"]), _bits(f["normals_c"])), "compacted normals"
     # ---- local frame (tolerance: the 3x3 reduction order is unspecified in Eigen too) --------------------------
+    # The oracle accumulates S twice from the same float products w_i*n_i: in float, sequentially (the literal
+    # restatement; its own rounding error grows with n: ~5e-4 relative at 1M normals) and in double ("truth").
     fr, orf = g["frame"], f["frame"]
-    sn = float(np.abs(orf["scatter"]).max())
+    St = orf["scatter_truth"]
+    sn = float(np.abs(St).max())
+    tv, tw = np.linalg.eigh(St)
+    m["scatter_rel_diff_vs_double"] = float(np.abs(fr["scatter"].astype(np.float64) - St).max() / sn)
+    m["eigenvalue_rel_diff_vs_double"] = float(np.abs(fr["vals"].astype(np.float64) - tv).max() / np.abs(tv).max())
+    m["axis_angle_rad_vs_double"] = float(_angle(fr["vecs"][:, 0], tw[:, 0]))
     m["scatter_rel_diff"] = float(np.abs(fr["scatter"].astype(np.float64) - orf["scatter"]).max() / sn)
     m["eigenvalue_rel_diff"] = float(np.abs(fr["vals"].astype(np.float64) - orf["vals"]).max() / np.abs(orf["vals"]).max())
     m["axis_angle_rad"] = float(_angle(fr["vecs"][:, 0], orf["vecs"][:, 0]))
+    m["float_oracle_scatter_rel_err_vs_double"] = float(np.abs(orf["scatter"].astype(np.float64) - St).max() / sn)
     # ---- cylinder RANSAC: depends on the normals -----------------------------------------------------------
     if "cyl_counts" in b:
         if exact_normals:

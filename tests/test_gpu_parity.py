@@ -1267,3 +1267,91 @@ def test_fetch_async_matches_synchronous_downloads():
         assert (summ.plane.best_id, summ.plane.best_count, summ.plane.refit_count) == (mp["best_id"], mp["best_count"], mp["refit_count"])
         assert np.array_equal(np.array(summ.plane.coef[:4]), mp["coef"]) and np.array_equal(np.array(summ.cylinder.coef[:7]), mc["coef"])
         assert summ.n_slices == len(poly) and slices[:len(poly)].tobytes() == poly.tobytes()
+
+
+# ---- CUDA-graph replay of gm_process_scan ------------------------------------------------------------------
+def _scan_outputs(ctx):
+    keys, assign, _ = ctx.download_voxel_assignment()
+    vox = ctx.download_voxels()
+    fr = ctx.frame()
+    _, _, pc = ctx.download_hypotheses(capi.GM_MODEL_PLANE, 256)
+    _, _, cc = ctx.download_hypotheses(capi.GM_MODEL_CYLINDER, 256)
+    return [ctx.download_cloud(1), ctx.download_normals(1), keys, assign, vox["centroids"], vox["nn_index"], fr["scatter"], fr["vals"],
+            pc, cc, ctx.model(0)["coef"], ctx.model(1)["coef"], ctx.download_labels(), ctx.download_polyline()]
+
+
+def test_graph_replay_reproduces_stream_launches_bit_for_bit():
+    """Scans of different sizes inside one 32768-point bucket share ONE captured graph; every output of a replayed scan
+    is bit-identical to the same scan processed with plain stream launches."""
+    sizes = [60_000, 58_123, 61_440, 57_001, 60_000]
+    scans = [synth.curved_tunnel(n, seed=40 + i) for i, n in enumerate(sizes)]
+    ps = synth.sample_indices(50_000, 256, 3, seed=3)
+    cs = synth.sample_indices(50_000, 256, 2, seed=4)
+    ref = []
+    with _ctx(65_536, neighborRadius=0.12) as ctx:
+        ctx.set_graph_mode(0)
+        for pts in scans:
+            ctx.upload_scan(pts)
+            ctx.process_scan(ps, cs)
+            ref.append(_scan_outputs(ctx))
+        assert ctx.graph_stats() == (0, 0)
+    with _ctx(65_536, neighborRadius=0.12) as ctx:
+        for i, pts in enumerate(scans):
+            ctx.upload_scan(pts)
+            ctx.process_scan(ps, cs)
+            got = _scan_outputs(ctx)
+            assert ctx.counts().device_error == 0
+            for a, b in zip(got, ref[i]):
+                assert a.tobytes() == b.tobytes(), f"scan {i}"
+        captures, replays = ctx.graph_stats()
+        assert captures == 1 and replays == len(scans) - 1   # scan 0: plain launches; scan 1: captured + launched; 2..: replays
+        # a parameter change starts a new generation: first scan eager again, same results as a fresh context
+        p = ctx.params
+        p.ransacThreshold = 0.08
+        ctx.set_params(p)
+        for _ in range(3):
+            ctx.upload_scan(scans[0])
+            ctx.process_scan(ps, cs)
+        changed = _scan_outputs(ctx)
+        assert ctx.graph_stats()[0] == 2
+    with _ctx(65_536, neighborRadius=0.12, ransacThreshold=0.08) as ctx:
+        ctx.set_graph_mode(0)
+        ctx.upload_scan(scans[0])
+        ctx.process_scan(ps, cs)
+        for a, b in zip(changed, _scan_outputs(ctx)):
+            assert a.tobytes() == b.tobytes()
+
+
+# ---- peer-memory collectives with one rank (the multi-rank path needs one GPU per rank: tools/peer_check.py) -------
+def test_sharded_round_and_map_collectives_with_a_single_rank():
+    cloud, normals = _compacted_scan(60_000, seed=33)
+    pts = synth.curved_tunnel(60_000, seed=33)
+    ps = synth.sample_indices(50_000, 300, 3, seed=3)
+    cs = synth.sample_indices(50_000, 200, 2, seed=4)
+    with _ctx(len(pts), neighborRadius=0.15) as ctx, _ctx(len(pts), neighborRadius=0.15) as ref:
+        comm = capi.PeerComm(0, 1)
+        ctx.set_comm(comm)
+        for c in (ctx, ref):
+            c.upload_scan(pts)
+            c.crop()
+            c.normals()
+        ref.ransac_pair(ps, cs)
+        ref.ransac_select_pair()
+        for _ in range(3):  # sequence numbers advance; slots are reused after 4 rounds
+            ctx.ransac_sharded(ps, cs)
+        for kind in (0, 1):
+            a, b = ctx.model(kind), ref.model(kind)
+            assert a["best_id"] == b["best_id"] and a["best_count"] == b["best_count"] and a["refit_count"] == b["refit_count"]
+            assert np.array_equal(a["coef"].view(np.uint32), b["coef"].view(np.uint32))
+        bb = ctx.voxel_bbox()
+        ctx.allreduce_voxel_bbox()
+        assert np.array_equal(np.concatenate(ctx.voxel_bbox()), np.concatenate(bb))
+        for c in (ctx, ref):
+            c.voxel()
+            c.local_frame()
+        ctx.allreduce_frame()
+        fa, fb = ctx.frame(), ref.frame()
+        assert np.array_equal(fa["scatter"], fb["scatter"]) and np.array_equal(fa["vals"], fb["vals"]) and np.array_equal(fa["vecs"], fb["vecs"])
+        assert ctx.counts().device_error == 0
+        ctx.set_comm(None)
+        comm.close()

@@ -684,8 +684,8 @@ def main():
         mctx.set_scan_device(d_slab.data_ptr(), ns)
         mctx.crop()
         mctx.normals()
-        hint = gmd.allreduce_bbox(*mctx.voxel_bbox())   # set-up only (torch.distributed); + 1 m of slack
-        mctx.set_voxel_bbox_hint(np.maximum(np.asarray(hint[0]) - 1.0, -mbound), np.minimum(np.asarray(hint[1]) + 1.0, mbound))
+        hint = gmd.allreduce_bbox(*mctx.voxel_bbox())   # set-up only (torch.distributed); + 0.25 m of slack
+        mctx.set_voxel_bbox_hint(np.maximum(np.asarray(hint[0]) - 0.25, -mbound), np.minimum(np.asarray(hint[1]) + 0.25, mbound))
 
         def map_pass(sp_, sc_):
             mctx.set_scan_device(d_slab.data_ptr(), ns)

@@ -37,7 +37,8 @@ def _assert_frame(m):
     The yardstick is the oracle's DOUBLE accumulation of the same float products: its float accumulation (the literal
     restatement, Eigen's order being unspecified anyway) carries a rounding error of its own that grows with n -- it is
     reported as float_oracle_scatter_rel_err_vs_double and bounds how far the GPU may sit from the float oracle."""
-    assert m["scatter_rel_diff_vs_double"] <= 1e-5 and m["eigenvalue_rel_diff_vs_double"] <= 1e-4, m
+    # bit-identical normals: only the reduction differs (1e-5); fast normals: the scatter entries move with them (1e-4)
+    assert m["scatter_rel_diff_vs_double"] <= (1e-5 if m["normals_bit_identical"] else 1e-4) and m["eigenvalue_rel_diff_vs_double"] <= 1e-4, m
     assert m["axis_angle_rad_vs_double"] <= 1e-3, m
     assert m["scatter_rel_diff"] <= 1e-4 + 2.0 * m["float_oracle_scatter_rel_err_vs_double"], m
 

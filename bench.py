@@ -160,7 +160,7 @@ def run_reference(a, rank):
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -264,8 +264,31 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE line, the JSON record: libraries that print there (NCCL's version banner at
+    NCCL_DEBUG=VERSION, torch warnings) are sent to stderr for the whole run; emit() writes the record to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     a = parse_args()
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -795,7 +818,7 @@ def main():
             "cpu_baseline": cpu,
             "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

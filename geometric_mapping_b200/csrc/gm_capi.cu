@@ -116,7 +116,6 @@ struct gm_ctx {
   size_t dense_cap = 0;
   int voxel_mode = 0;  // 0 = dense tables when the key range fits, 1 = always sort
   int normals_mode = 0;  // 0 = neighbours summed in cell-run order (fast), 1 = in FLANN's (d2, index) order (bit-identical to the oracle)
-  int normals_kernel = 1;  // fast mode: 1 = staged two-phase kernel, 768 candidates per warp (default), 2 = same with 1024, 0 = direct per-lane loop (env GM_NORMALS_KERNEL; kept for A/B)
   BlockEntry* d_tab = nullptr;  // dense block table of the neighbour grid (1 << (key_bits - 6) entries)
   size_t tab_entries = 0;
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
@@ -473,9 +472,6 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   { const char* env = std::getenv("GM_COUNT_MODE"); ctx->count_mode = (env && env[0] == '1') ? 1 : 0; }
   { const char* env = std::getenv("GM_VOXEL_MODE"); ctx->voxel_mode = (env && env[0] == '1') ? 1 : 0; }
   { const char* env = std::getenv("GM_GRAPH"); ctx->graph_mode = (env && env[0] == '0') ? 0 : 1; }
-  { const char* env = std::getenv("GM_NORMALS_KERNEL"); ctx->normals_kernel = env ? std::max(0, std::min(2, std::atoi(env))) : 1; }
-  if ((e = cudaFuncSetAttribute(k_normals_staged<768, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NsSmem<768, 8>))) != cudaSuccess) return fail(e, "smem attribute");
-  if ((e = cudaFuncSetAttribute(k_normals_staged<1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NsSmem<1024, 12>))) != cudaSuccess) return fail(e, "smem attribute");
   { const char* env = std::getenv("GM_NORMALS_MODE"); ctx->normals_mode = (env && env[0] == '1') ? 1 : 0; }
 
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
@@ -732,19 +728,9 @@ gm_status gm_normals(gm_ctx* ctx) {
       if (ctx->normals_mode == 1) {
         GM_LAUNCH(ctx, k_normals<1>, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
                   ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st);
-      } else if (ctx->normals_kernel == 0) {
+      } else {
         GM_LAUNCH(ctx, k_normals<0>, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
                   ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st);
-      } else {
-        if (ctx->normals_kernel == 2)
-          k_normals_staged<1024, 12><<<div_up((long long)n, NRM_BLOCK), NRM_BLOCK, sizeof(NsSmem<1024, 12>), ctx->stream>>>(
-              ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2, ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid,
-              ctx->d_leaf_bounds, ctx->own, ctx->d_st);
-        else
-          k_normals_staged<768, 8><<<div_up((long long)n, NRM_BLOCK), NRM_BLOCK, sizeof(NsSmem<768, 8>), ctx->stream>>>(
-              ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2, ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid,
-              ctx->d_leaf_bounds, ctx->own, ctx->d_st);
-        ++ctx->launches;
       } }
     { SegTimer seg_(ctx, SEG_COMPACT);
       GM_LAUNCH(ctx, k_compact_valid, div_up((long long)n, CP_TILE), CP_BLOCK, ctx->d_crop, ctx->d_normals, n_ptr, ctx->d_cloud_c,

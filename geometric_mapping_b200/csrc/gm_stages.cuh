@@ -634,193 +634,6 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 }
 
 
-// ---- radius normals, staged + two-phase (the default fast path) ---------------------------------------------------------
-// k_normals<0> above spends ~30 issue slots per stencil candidate: a per-lane global load, the run bookkeeping, the exact
-// distance test and a masked 10-accumulator update for EVERY candidate although only 1 in 4 is a neighbour.  Here a warp
-// (32 consecutive cell-sorted queries = ~4.5 cells)
-//   stages  the candidate runs of each of its cells ONCE into shared memory, as one contiguous structure-of-arrays
-//           list per cell (coalesced loads, all lanes cooperate): the per-lane candidate stream becomes `for j in
-//           [off, off + total)`, no run switching, and four candidates arrive per LDS.128 already paired for f32x2;
-//   phase 1 every lane tests its cell's list with the EXACT FLANN predicate ((dx*dx + dy*dy) + dz*dz < r2, unfused),
-//           two candidates per instruction: sub.f32x2, then fma.rn.f32x2(d, d, +0) -- a product rounded once, which ptxas
-//           cannot contract with the following add.f32x2 (it does contract mul.f32x2 + add.f32x2 into FFMA2 even under
-//           -fmad=false) -- and records the outcome as one bit per candidate: ~7 slots per candidate;
-//   phase 2 every lane walks the set bits of its own masks and accumulates only its neighbours, as offsets from the
-//           query point (d = q - p: the covariance is shift invariant, and sums of small offsets are better conditioned
-//           than PCL's raw single-pass sums; the neighbour SET and the count are exactly the oracle's).
-// A cell whose list does not fit the staging area (NS_CAP candidates) takes the direct loop of k_normals<0>.
-// NS_CAP = staged candidates per warp, NS_MAXCH = mask words per lane and round (longer lists take several rounds)
-constexpr int NS_WARPS = NRM_BLOCK / 32;
-template <int NS_CAP, int NS_MAXCH>
-struct NsSmem {
-  float x[NS_WARPS][NS_CAP + 32], y[NS_WARPS][NS_CAP + 32], z[NS_WARPS][NS_CAP + 32];
-  unsigned mask[NS_WARPS][NS_MAXCH][32];
-};
-
-// the direct (unstaged) neighbourhood sums of k_normals<0> for one query: raw sums, PCL's form
-__device__ __forceinline__ void d_normal_direct(const float4* __restrict__ sp, const int2* __restrict__ rr, int nr, int total, const float4 p, float r2,
-                                                int& cnt, float4& o0, float4& o1) {
-  u64 a01 = 0ull, a24 = 0ull, a67 = 0ull, a8c = 0ull;
-  float a3 = 0.f, a5 = 0.f;
-  int k = 0, t = 0, end = 0;
-  int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
-  for (int i = 0; i < total; ++i) {
-    if (t == end) { t = nxt.x; end = nxt.y; ++k; if (k < nr) nxt = rr[k]; }
-    const float4 q = sp[t];
-    ++t;
-    float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-    float d2 = (dx * dx + dy * dy) + dz * dz;
-    const bool hit = d2 < r2;
-    const float mx = hit ? q.x : 0.f, my = hit ? q.y : 0.f, mz = hit ? q.z : 0.f, m1 = hit ? 1.0f : 0.f;
-    const u64 qxy = d_pack2(q.x, q.y);
-    a01 = d_fma2(d_pack2(mx, mx), qxy, a01);
-    a24 = d_fma2(d_pack2(mz, mz), qxy, a24);
-    a3 = fmaf(my, q.y, a3);
-    a5 = fmaf(mz, q.z, a5);
-    a67 = d_add2(a67, d_pack2(mx, my));
-    a8c = d_add2(a8c, d_pack2(mz, m1));
-  }
-  float a0, a1, a2, a4, a6, a7, a8, cntf;
-  d_unpack2(a01, a0, a1); d_unpack2(a24, a2, a4); d_unpack2(a67, a6, a7); d_unpack2(a8c, a8, cntf);
-  cnt = (int)cntf;
-  if (cnt >= 3) d_normal_from_sums(a0, a1, a2, a3, a4, a5, a6, a7, a8, cnt, p, o0, o1);
-}
-
-// exact FLANN test of the candidate pair (x, y, z as f32x2) against the query (negated, broadcast): bits b0, b0+1 of m
-__device__ __forceinline__ void d_ns_test2(u64 X, u64 Y, u64 Z, u64 npx, u64 npy, u64 npz, float r2, unsigned bit0, unsigned& m) {
-  const u64 dx = d_add2(X, npx), dy = d_add2(Y, npy), dz = d_add2(Z, npz);
-  const u64 s = d_add2(d_add2(d_fma2(dx, dx, 0ull), d_fma2(dy, dy, 0ull)), d_fma2(dz, dz, 0ull));
-  float s0, s1;
-  d_unpack2(s, s0, s1);
-  if (s0 < r2) m |= bit0;
-  if (s1 < r2) m |= bit0 << 1;
-}
-
-template <int NS_CAP, int NS_MAXCH>
-__global__ void __launch_bounds__(NRM_BLOCK)
-k_normals_staged(const float4* __restrict__ sp, const int* __restrict__ cell_id, const int2* __restrict__ runs, const int2* __restrict__ cell_info,
-                 const int* __restrict__ n_ptr, float r2, float4* __restrict__ normals, int* __restrict__ nbr_count,
-                 float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds, OwnedRange own, DevState* st) {
-  extern __shared__ __align__(16) unsigned char ns_raw[];
-  NsSmem<NS_CAP, NS_MAXCH>& S = *reinterpret_cast<NsSmem<NS_CAP, NS_MAXCH>*>(ns_raw);
-  const int n = *n_ptr;
-  const int i = blockIdx.x * NRM_BLOCK + threadIdx.x;
-  if ((i & ~31) >= n) return;  // warp-uniform: the whole leaf is past the end
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool active = i < n;
-  const float qnan = CUDART_NAN_F;
-  const float4 p = active ? sp[i] : make_float4(qnan, qnan, qnan, 0.f);
-  float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
-  int cnt = 0, ncand = 0;
-  const bool fin = active && finite3(p.x, p.y, p.z);
-  const int cid = fin ? cell_id[i] : -1;
-  // the warp's cells are consecutive ids first..last (points are cell sorted); at most 32 of them
-  int first = fin ? cid : 0x7FFFFFFF, last = cid;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { first = min(first, __shfl_xor_sync(FULL, first, o)); last = max(last, __shfl_xor_sync(FULL, last, o)); }
-  if (last >= 0) {
-    // lane l holds {runs, candidates} of cell first + l: read by the whole warp through shuffles
-    const int2 myinfo = (first + lane <= last) ? cell_info[first + lane] : make_int2(0, 0);
-    const int mynr = __shfl_sync(FULL, myinfo.x, max(cid - first, 0));      // of MY cell
-    const int mytotal = __shfl_sync(FULL, myinfo.y, max(cid - first, 0));
-    float* const sx = S.x[w]; float* const sy = S.y[w]; float* const sz = S.z[w];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
-    bool direct_done = false;
-    const u64 npx = d_pack2(-p.x, -p.x), npy = d_pack2(-p.y, -p.y), npz = d_pack2(-p.z, -p.z);
-    int c0 = first;
-    while (c0 <= last) {
-      // ---- a group of cells whose lists fit the staging area together; myoff = offset of MY cell's list if it is in it
-      int used = 0, c1 = c0, myoff = -1;
-      while (c1 <= last) {
-        const int tot = __shfl_sync(FULL, myinfo.y, c1 - first);
-        const int pad = (tot + 3) & ~3;
-        if (used + pad > NS_CAP) break;
-        if (cid == c1) myoff = used;
-        used += pad;
-        ++c1;
-      }
-      if (c1 == c0) {
-        // one cell that does not fit on its own: its queries take the direct loop
-        if (cid == c0) {
-          ncand = mytotal;
-          d_normal_direct(sp, runs + (size_t)c0 * GRID_RUNS, mynr, mytotal, p, r2, cnt, o0, o1);
-          direct_done = true;
-        }
-        __syncwarp();
-        ++c0;
-        continue;
-      }
-      // ---- stage: every run of every cell of the group, coalesced, into the cell's contiguous list
-      {
-        int pos = 0;
-        for (int c = c0; c < c1; ++c) {
-          const int nr = __shfl_sync(FULL, myinfo.x, c - first);
-          const int tot = __shfl_sync(FULL, myinfo.y, c - first);
-          const int2 myrun = (lane < nr) ? runs[(size_t)c * GRID_RUNS + lane] : make_int2(0, 0);
-          int rp = pos;
-          for (int k = 0; k < nr; ++k) {
-            const int rx = __shfl_sync(FULL, myrun.x, k), ry = __shfl_sync(FULL, myrun.y, k);
-            for (int t = rx + lane; t < ry; t += 32) {
-              const float4 q = sp[t];
-              const int j = rp + (t - rx);
-              sx[j] = q.x; sy[j] = q.y; sz[j] = q.z;
-            }
-            rp += ry - rx;
-          }
-          pos += (tot + 3) & ~3;
-        }
-      }
-      __syncwarp();
-      // ---- the queries of these cells
-      if (myoff >= 0) {
-        const int total = mytotal;
-        ncand = total;
-        for (int r0 = 0; r0 < total; r0 += NS_MAXCH * 32) {
-          const int nch = min(NS_MAXCH, (total - r0 + 31) >> 5);
-          // phase 1: exact tests, one bit per candidate
-          for (int ch = 0; ch < nch; ++ch) {
-            const int base = myoff + r0 + 32 * ch;
-            unsigned m = 0u;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float4 X = *reinterpret_cast<const float4*>(sx + base + 4 * u);
-              const float4 Y = *reinterpret_cast<const float4*>(sy + base + 4 * u);
-              const float4 Z = *reinterpret_cast<const float4*>(sz + base + 4 * u);
-              d_ns_test2(d_pack2(X.x, X.y), d_pack2(Y.x, Y.y), d_pack2(Z.x, Z.y), npx, npy, npz, r2, 1u << (4 * u), m);
-              d_ns_test2(d_pack2(X.z, X.w), d_pack2(Y.z, Y.w), d_pack2(Z.z, Z.w), npx, npy, npz, r2, 1u << (4 * u + 2), m);
-            }
-            const int rem = total - r0 - 32 * ch;
-            if (rem < 32) m &= (1u << rem) - 1u;  // the tail of the last word reads the next list / stale data: discard
-            S.mask[w][ch][lane] = m;
-            cnt += __popc(m);
-          }
-          // phase 2: accumulate the neighbours only (one flat loop: a lane either consumes a bit or fetches its next word)
-          int ch = -1, base = myoff + r0 - 32;
-          unsigned m = 0u;
-          for (;;) {
-            if (m == 0u) {
-              if (++ch >= nch) break;
-              m = S.mask[w][ch][lane];
-              base += 32;
-              continue;
-            }
-            const int j = base + __ffs(m) - 1;
-            m &= m - 1u;
-            const float dx = sx[j] - p.x, dy = sy[j] - p.y, dz = sz[j] - p.z;
-            a0 = fmaf(dx, dx, a0); a1 = fmaf(dx, dy, a1); a2 = fmaf(dx, dz, a2);
-            a3 = fmaf(dy, dy, a3); a4 = fmaf(dy, dz, a4); a5 = fmaf(dz, dz, a5);
-            a6 += dx; a7 += dy; a8 += dz;
-          }
-        }
-      }
-      __syncwarp();  // the next group overwrites the staging area
-      c0 = c1;
-    }
-    if (fin && !direct_done && cnt >= 3) d_normal_from_sums(a0, a1, a2, a3, a4, a5, a6, a7, a8, cnt, p, o0, o1);
-  }
-  d_normals_epilogue(i, active, p, o0, o1, cnt, ncand, normals, nbr_count, sorted_valid, leaf_bounds, own, st);
-}
-
 // a3 removeNaNNormalsFromPointCloud + ExtractIndices (src/tunnel_processing.cpp:74-85): stable
 // compaction of cloud and normals by isfinite(nx,ny,nz); also the bounding box of the survivors
 // (pcl::getMinMax3D of the VoxelGrid that follows).

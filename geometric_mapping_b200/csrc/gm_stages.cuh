@@ -634,6 +634,135 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 }
 
 
+
+// ---- a2, k mode: pcl::NormalEstimation with setKSearch(k) (the north-star's "grid-hashed k-NN") ---------------------------
+// The k nearest points (FLANN L2_Simple distance, the query included, ties by ascending index) instead of the points
+// within a radius; the rest of the pipeline (single-pass covariance, eigen33, curvature, flip) is the same.
+// One thread per query keeps its k best (d2, index) pairs as 64-bit keys (d2 >= +0, so the float bits order like the
+// value) in a SORTED list in shared memory: a candidate is offered only if it beats the current k-th key, insertion
+// shifts the tail, and the finished list is already in FLANN's result order -- so the neighbours are summed in exactly
+// the order pcl::NormalEstimation sums them and the normals are bit-identical to the CPU oracle's in this mode.
+//   pass A  the 27-cell stencil (the runs of the radius mode).  Complete iff k keys were found and the k-th distance is
+//           below one cell: nothing outside the stencil can be nearer.
+//   pass B  (sparse neighbourhoods, outliers) restart over whole 4x4x4-cell blocks in growing Chebyshev shells around the
+//           query's block -- a block is ONE contiguous run of the sorted cloud and an empty block costs one table read --
+//           until the k-th distance is below the distance to the nearest unexamined block.
+constexpr int KNN_BLOCK = 64;
+constexpr int KNN_MAX = 64;
+
+struct KnnList {
+  unsigned long long* slot;  // element j of this thread's list is slot[j * KNN_BLOCK]
+  int K, cnt;
+  unsigned long long worst;  // the k-th key once the list is full, else "infinity"
+  __device__ __forceinline__ void reset() { cnt = 0; worst = ~0ull; }
+  __device__ __forceinline__ void offer(float d2, int id) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
+    if (!(key < worst)) return;  // (NaN distances have the largest bit patterns: never accepted once the list is full)
+    int j = (cnt < K) ? cnt : K - 1;  // slot that becomes free: the new end, or the dropped k-th
+    while (j > 0) {
+      const unsigned long long v = slot[(j - 1) * KNN_BLOCK];
+      if (v <= key) break;
+      slot[j * KNN_BLOCK] = v;
+      --j;
+    }
+    slot[j * KNN_BLOCK] = key;
+    if (cnt < K) ++cnt;
+    if (cnt == K) worst = slot[(K - 1) * KNN_BLOCK];
+  }
+};
+
+__global__ void __launch_bounds__(KNN_BLOCK)
+k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, const int* __restrict__ cell_id, const int2* __restrict__ runs,
+              const int2* __restrict__ cell_info, const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start, const int* __restrict__ n_ptr,
+              GridSpec g, int K, float4* __restrict__ normals, int* __restrict__ nbr_count, float4* __restrict__ sorted_valid,
+              float4* __restrict__ leaf_bounds, OwnedRange own, DevState* st, int* __restrict__ knn_idx) {
+  extern __shared__ unsigned long long knn_smem[];  // [K][KNN_BLOCK]
+  const int n = *n_ptr;
+  const int i = blockIdx.x * KNN_BLOCK + threadIdx.x;
+  if ((i & ~31) >= n) return;
+  const bool active = i < n;
+  const float qnan = CUDART_NAN_F;
+  const float4 p = active ? sp[i] : make_float4(qnan, qnan, qnan, 0.f);
+  const int orig = __float_as_int(p.w);
+  float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
+  int cnt = 0, ncand = 0;
+  if (active && finite3(p.x, p.y, p.z)) {
+    KnnList L;
+    L.slot = knn_smem + threadIdx.x;
+    L.K = K;
+    L.reset();
+    const int U = st->n_cells, nf = st->n_sorted_finite;
+    const int cid = cell_id[i];
+    const int2* rr = runs + (size_t)cid * GRID_RUNS;
+    const int nr = cell_info[cid].x;
+    // ---- pass A: the 27-cell stencil; only candidates nearer than one cell can matter if this pass is to be complete
+    const float lim1 = (g.cell * 0.999f) * (g.cell * 0.999f);
+    for (int k = 0; k < nr; ++k) {
+      const int2 run = rr[k];
+      ncand += run.y - run.x;
+      for (int t = run.x; t < run.y; ++t) {
+        const float4 q = sp[t];
+        const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        if (d2 <= lim1) L.offer(d2, __float_as_int(q.w));
+      }
+    }
+    const bool complete = L.cnt == K;  // k keys, all within one cell of the query (the filter above)
+    if (!complete && nf > L.cnt) {
+      // ---- pass B: whole blocks in growing shells (from scratch: the stencil is part of shell 0/1)
+      L.reset();
+      int cx, cy, cz;
+      gm_cell_of(g, p.x, p.y, p.z, cx, cy, cz);
+      const int bx = cx >> 2, by = cy >> 2, bz = cz >> 2;
+      const int nbx = (g.dim[0] + 3) >> 2, nby = (g.dim[1] + 3) >> 2, nbz = (g.dim[2] + 3) >> 2;
+      const int bmax = max(max(max(bx, nbx - 1 - bx), max(by, nby - 1 - by)), max(bz, nbz - 1 - bz));
+      for (int b = 0; b <= bmax; ++b) {
+        for (int dz = -b; dz <= b; ++dz) {
+          const int z = bz + dz;
+          if (z < 0 || z >= nbz) continue;
+          for (int dy = -b; dy <= b; ++dy) {
+            const int y = by + dy;
+            if (y < 0 || y >= nby) continue;
+            const bool face = (dz == -b || dz == b || dy == -b || dy == b);
+            for (int dx = -b; dx <= b; dx += (face || b == 0) ? 1 : 2 * b) {  // inner rows: only the two end blocks
+              const int x = bx + dx;
+              if (x < 0 || x >= nbx) continue;
+              const BlockEntry e = tab[gm_cell_key(g, x << 2, y << 2, z << 2) >> 6];
+              if (e.mask == 0ull) continue;
+              const int c_end = e.first + __popcll(e.mask);
+              const int t0 = min(ucell_start[e.first], nf), t1 = (c_end < U) ? min(ucell_start[c_end], nf) : nf;
+              ncand += t1 - t0;
+              for (int t = t0; t < t1; ++t) {
+                const float4 q = sp[t];
+                const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+                L.offer((ex * ex + ey * ey) + ez * ez, __float_as_int(q.w));
+              }
+            }
+          }
+        }
+        // every unexamined point lies b whole blocks (4 cells each) or more beyond the query's block
+        const float lim = 4.0f * (float)b * g.cell * 0.999f;
+        if (L.cnt == K && __uint_as_float((unsigned)(L.worst >> 32)) <= lim * lim) break;
+      }
+    }
+    cnt = L.cnt;
+    if (knn_idx != nullptr)
+      for (int j = 0; j < K; ++j) knn_idx[(size_t)orig * K + j] = j < cnt ? (int)(unsigned)L.slot[j * KNN_BLOCK] : -1;
+    if (cnt >= 3) {
+      // the list is in FLANN's result order: sum in that order, plain float operations (the oracle's, op for op)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+      for (int j = 0; j < cnt; ++j) {
+        const float4 q = crop[(int)(unsigned)L.slot[j * KNN_BLOCK]];
+        a0 += q.x * q.x; a1 += q.x * q.y; a2 += q.x * q.z;
+        a3 += q.y * q.y; a4 += q.y * q.z; a5 += q.z * q.z;
+        a6 += q.x; a7 += q.y; a8 += q.z;
+      }
+      d_normal_from_sums(a0, a1, a2, a3, a4, a5, a6, a7, a8, cnt, p, o0, o1);
+    }
+  }
+  d_normals_epilogue(i, active, p, o0, o1, cnt, ncand, normals, nbr_count, sorted_valid, leaf_bounds, own, st);
+}
+
 // a3 removeNaNNormalsFromPointCloud + ExtractIndices (src/tunnel_processing.cpp:74-85): stable
 // compaction of cloud and normals by isfinite(nx,ny,nz); also the bounding box of the survivors
 // (pcl::getMinMax3D of the VoxelGrid that follows).

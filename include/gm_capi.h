@@ -169,6 +169,14 @@ GM_API gm_status gm_set_count_mode(gm_ctx* ctx, int32_t mode);
  * normals and curvatures are then bit-identical to the CPU oracle's and every later stage can be checked end to
  * end from the raw points.  A verification mode: ~40x slower than mode 0. */
 GM_API gm_status gm_set_normals_mode(gm_ctx* ctx, int32_t mode);
+/* k-nearest-neighbour normals: pcl::NormalEstimation::setKSearch(k) instead of setRadiusSearch(r) at
+ * src/tunnel_processing.cpp:69 (the reference uses the radius; the k mode is what the north-star calls "grid-hashed k-NN").
+ * k = 0 (default) = radius mode; 1 <= k <= 64: every point takes its k nearest points (itself included, ties by index).
+ * neighborRadius then only sizes the search grid (pick it near the expected distance of the k-th neighbour); the search
+ * is exact whatever its value.  Neighbours are summed in FLANN's result order: normals are bit-identical to the oracle's.
+ * keep_indices = 1 also stores the neighbour lists (M x k, -1 padded) for gm_download_knn_indices. */
+GM_API gm_status gm_set_knn(gm_ctx* ctx, int32_t k, int32_t keep_indices);
+GM_API gm_status gm_download_knn_indices(gm_ctx* ctx, int32_t* out_m_x_k, size_t capacity_points);
 /* VoxelGrid strategy of gm_voxel / gm_compress: 0 (default) = sort-free dense tables whenever the number of lattice
  * cells of the crop box (or of the box given with gm_set_voxel_bbox) is at most 2^23, else sort-based; 1 = always
  * sort-based.  Same voxels, order, counts and centroids either way. */

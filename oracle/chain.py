@@ -16,7 +16,7 @@ def front(pts, bound=5.0, radius=0.05, leaf=0.1, wf=0.2, nthreads=0, knn=0, with
     """crop -> normals -> compaction -> VoxelGrid -> 1-NN -> local frame.  knn > 0: k-nearest-neighbour normals."""
     cropped, src = O.crop(pts, bound, True)
     if knn > 0:
-        nrm, cnt = O.normals_knn(cropped, knn, nthreads=nthreads)
+        nrm, cnt = O.normals_knn(cropped, knn, cell=max(radius, 1e-3), nthreads=nthreads)
     else:
         nrm, cnt, _ = O.normals(cropped, radius, mode=0, order=0, nthreads=nthreads)
     cloud, nrm_c, vmap = O.compact(cropped, nrm)

@@ -385,6 +385,95 @@ GMO_API void gmo_normals(const float* pts4, int64_t n, double radius, float* nor
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// a2 (k mode)  pcl::NormalEstimation with setKSearch(k) instead of setRadiusSearch: the north-star's "k-NN normal
+// estimation".  The reference calls setRadiusSearch (src/tunnel_processing.cpp:69); with setKSearch PCL runs the same
+// pipeline on the result of nearestKSearch(p, k): the k nearest points in FLANN L2_Simple distance, the
+// query itself included (d2 = 0), returned in ascending distance (ties: ascending index, builder-defined as in the
+// radius mode), fewer than k when the cloud has fewer finite points; fewer than 3 -> NaN normal.
+//   knn_idx   optional n x k, the neighbour indices in result order, -1 padded
+//   mode      0 = hash grid with expanding shells (exact), 1 = brute force O(n^2)
+GMO_API void gmo_normals_knn(const float* pts4, int64_t n, int32_t k, double cell, float* normals8, int32_t* nbr_count,
+                             int32_t* knn_idx, int mode, int nthreads) {
+  const P4* p = (const P4*)pts4;
+  HashGrid grid;
+  int64_t lo[3] = {INT64_MAX, INT64_MAX, INT64_MAX}, hi[3] = {INT64_MIN, INT64_MIN, INT64_MIN};
+  if (mode == 0) {
+    grid.build(p, n, cell);
+    for (int64_t i = 0; i < n; ++i) {
+      if (!std::isfinite(p[i].x) || !std::isfinite(p[i].y) || !std::isfinite(p[i].z)) continue;
+      int64_t c[3] = {(int64_t)std::floor(p[i].x * grid.inv), (int64_t)std::floor(p[i].y * grid.inv), (int64_t)std::floor(p[i].z * grid.inv)};
+      for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], c[a]); hi[a] = std::max(hi[a], c[a]); }
+    }
+  }
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<std::pair<float, int>> nb;
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; ++i) {
+      nb.clear();
+      const float* q = &p[i].x;
+      const bool finite = std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]);
+      auto keep_k = [&]() {  // the k smallest (d2, index) pairs, ascending
+        if ((int64_t)nb.size() > k) { std::partial_sort(nb.begin(), nb.begin() + k, nb.end()); nb.resize((size_t)k); }
+        else std::sort(nb.begin(), nb.end());
+      };
+      if (finite && mode == 1) {
+        for (int64_t j = 0; j < n; ++j) {
+          if (!std::isfinite(p[j].x) || !std::isfinite(p[j].y) || !std::isfinite(p[j].z)) continue;
+          nb.emplace_back(flann_d2(q, &p[j].x), (int)j);
+        }
+        keep_k();
+      } else if (finite && lo[0] <= hi[0]) {
+        int64_t c[3] = {(int64_t)std::floor(q[0] * grid.inv), (int64_t)std::floor(q[1] * grid.inv), (int64_t)std::floor(q[2] * grid.inv)};
+        int64_t smax = 0;
+        for (int a = 0; a < 3; ++a) smax = std::max<int64_t>(smax, std::max<int64_t>(std::llabs(c[a] - lo[a]), std::llabs(c[a] - hi[a])));
+        for (int64_t sh = 0; sh <= smax; ++sh) {
+          for (int64_t dz = -sh; dz <= sh; ++dz) for (int64_t dy = -sh; dy <= sh; ++dy) for (int64_t dx = -sh; dx <= sh; ++dx) {
+            if (std::max<int64_t>(std::llabs(dx), std::max<int64_t>(std::llabs(dy), std::llabs(dz))) != sh) continue;
+            auto it = grid.cells.find(HashGrid::key(c[0] + dx, c[1] + dy, c[2] + dz));
+            if (it == grid.cells.end()) continue;
+            for (int j : it->second) nb.emplace_back(flann_d2(q, &p[j].x), j);
+          }
+          keep_k();
+          // every unexplored point is at least sh * cell away (Chebyshev shell sh+1 or beyond)
+          const double lim = (double)sh * grid.cell * 0.999;
+          if ((int64_t)nb.size() >= k && (double)nb.back().first <= lim * lim) break;
+        }
+      }
+      float* out = normals8 + i * 8;
+      for (int t = 0; t < 8; ++t) out[t] = 0.0f;
+      if (nbr_count) nbr_count[i] = (int32_t)nb.size();
+      if (knn_idx) for (int32_t t = 0; t < k; ++t) knn_idx[i * k + t] = t < (int32_t)nb.size() ? nb[(size_t)t].second : -1;
+      const float qnan = std::numeric_limits<float>::quiet_NaN();
+      if (nb.size() < 3) { out[0] = out[1] = out[2] = qnan; out[4] = qnan; continue; }
+      float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (auto& e : nb) {
+        const P4& s = p[e.second];
+        a[0] += s.x * s.x; a[1] += s.x * s.y; a[2] += s.x * s.z;
+        a[3] += s.y * s.y; a[4] += s.y * s.z; a[5] += s.z * s.z;
+        a[6] += s.x; a[7] += s.y; a[8] += s.z;
+      }
+      float cnt = (float)nb.size();
+      for (int t = 0; t < 9; ++t) a[t] = a[t] / cnt;
+      float cov[9];
+      cov[0] = a[0] - a[6] * a[6]; cov[1] = a[1] - a[6] * a[7]; cov[2] = a[2] - a[6] * a[8];
+      cov[4] = a[3] - a[7] * a[7]; cov[5] = a[4] - a[7] * a[8]; cov[8] = a[5] - a[8] * a[8];
+      cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+      float ev, nrm[3];
+      eigen33_smallest(cov, ev, nrm);
+      float eig_sum = cov[0] + cov[4] + cov[8];
+      float curvature = (eig_sum != 0.0f) ? std::fabs(ev / eig_sum) : 0.0f;
+      float vx = 0.0f - q[0], vy = 0.0f - q[1], vz = 0.0f - q[2];
+      float cos_theta = vx * nrm[0] + vy * nrm[1] + vz * nrm[2];
+      if (cos_theta < 0.0f) { nrm[0] *= -1.0f; nrm[1] *= -1.0f; nrm[2] *= -1.0f; }
+      out[0] = nrm[0]; out[1] = nrm[1]; out[2] = nrm[2]; out[4] = curvature;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // a3  removeNaNNormalsFromPointCloud + ExtractIndices (src/tunnel_processing.cpp:74-85)
 // Stable; keeps a point iff nx,ny,nz are all finite.  map[i] = compacted index or -1.

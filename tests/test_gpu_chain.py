@@ -173,3 +173,41 @@ def test_cuda_path_against_the_golden_fixture():
     assert abs(g["cyl"]["coef"][6] - gold["cyl_refit"][6]) <= 1e-4 * gold["cyl_refit"][6]
     assert g["cyl"]["refit_count"] == int(gold["cyl_refit_count"])
     assert (g["labels"] != gold["labels"]).mean() <= 1e-3
+
+
+# ---- k-nearest-neighbour normals (the north-star's "grid-hashed k-NN": pcl::NormalEstimation::setKSearch) ---------
+@pytest.mark.parametrize("n,k,radius,outliers", [(30_000, 16, 0.12, 0.05), (30_000, 32, 0.3, 0.0), (3_000, 8, 0.05, 0.3), (200, 64, 0.5, 0.0), (40, 64, 1.0, 0.0)])
+def test_knn_neighbour_sets_and_normals_bit_exact(n, k, radius, outliers):
+    """Neighbour index lists (in FLANN's result order) against the BRUTE-FORCE oracle, normals bit-identical.  The grid
+    cell (neighborRadius) only sizes the search: dense stencils (pass A), sparse ones and outliers (pass B, block shells),
+    clouds smaller than k."""
+    pts = synth.curved_tunnel(n, seed=61, outlier_frac=outliers)
+    pts[3] = [np.nan, 0, 0, 1]
+    pts[5:8] = pts[9]                      # duplicates: equal distances, tie broken by index
+    cropped, _ = O.crop(pts, 5.0, True)
+    ref_n, ref_c, ref_i = O.normals_knn(cropped, k, cell=radius, mode=1, with_indices=True)
+    with capi.Context(capi.default_params(neighborRadius=radius), max_points=n, max_hypotheses=4) as ctx:
+        ctx.set_knn(k, keep_indices=True)
+        ctx.upload_scan(pts)
+        ctx.crop()
+        ctx.normals()
+        assert ctx.counts().device_error == 0
+        idx, cnt, nrm = ctx.download_knn_indices(), ctx.download_neighbor_counts(), ctx.download_normals(0)
+    fin = np.isfinite(cropped[:, :3]).all(1)
+    assert np.array_equal(cnt[fin], ref_c[fin])
+    assert np.array_equal(idx[fin], ref_i[fin])
+    assert np.array_equal(chain._bits(nrm), chain._bits(ref_n))
+
+
+def test_knn_chain_c1_1m_k32_from_raw_points():
+    """BASELINE configs[1] in k mode (k = 32): the whole chain from raw points against the oracle alone; in this
+    mode the default path already sums in FLANN's order, so everything integer is exact without a special mode."""
+    pts = synth.curved_tunnel(1_000_000, seed=2)
+    f = chain.front(pts, radius=0.07, leaf=0.1, knn=32)
+    nv = f["n_valid"]
+    ps, cs = synth.sample_indices(nv, 512, 3, seed=3), synth.sample_indices(nv, 512, 2, seed=4)
+    b = chain.back(f, ps, cs, tau=TAU)
+    g = gpu_chain(pts, ps, cs, False, 0.07, 0.1, knn=32)
+    m = chain.compare(g, f, b, exact_normals=True)
+    _record("C1_1M_knn32", m)
+    _assert_canonical(m)

@@ -262,3 +262,83 @@ def test_map_insert_known_answers_and_order_independence():
     only = O.map_insert(None, a, leaf, labels=lab, label_filter=2)
     assert only["counts"].sum() == (lab == 2).sum()
 
+
+
+# ---- second source for the oracle (scipy / numpy, double precision): the restatement of the UPSTREAM semantics is a
+# single-author reading of PCL / FLANN / Eigen; these checks compare it with independent library implementations -----
+def test_oracle_against_scipy_and_numpy_second_source():
+    from scipy.spatial import cKDTree
+
+    pts = synth.curved_tunnel(8_000, seed=71, outlier_frac=0.02)
+    cropped, _ = O.crop(pts, 5.0, True)
+    xyz = cropped[:, :3].astype(np.float64)
+    r = 0.25
+    nrm, cnt, truth = O.normals(cropped, r, mode=0, order=0, truth=True)
+    tree = cKDTree(xyz)
+    # radius neighbour sets: FLANN's strict float test vs scipy's double test differ only for pairs within rounding of r
+    lists = tree.query_ball_point(xyz, r * (1 - 1e-6))
+    lists_hi = tree.query_ball_point(xyz, r * (1 + 1e-6))
+    lo = np.array([len(l) for l in lists]); hi = np.array([len(l) for l in lists_hi])
+    assert ((cnt >= lo) & (cnt <= hi)).all()
+    assert (cnt == lo).mean() > 0.999
+    # normals: the double "truth" of the oracle equals numpy's eigh of the two-pass covariance
+    for i in range(0, len(xyz), 97):
+        nb = xyz[lists[i]]
+        if len(nb) != cnt[i] or len(nb) < 3:
+            continue
+        w, v = np.linalg.eigh(np.cov(nb.T, bias=True))
+        n0 = v[:, 0] * (1 if np.dot(v[:, 0], -xyz[i]) >= 0 else -1)
+        assert np.arccos(min(1.0, abs(float(np.dot(n0, truth[i, :3]))))) < 1e-6
+        assert abs(w[0] / w.sum() - truth[i, 3]) < 1e-9
+        # ... and the float single-pass result (PCL's form) is near it
+        assert np.arccos(min(1.0, abs(float(np.dot(n0, nrm[i, :3].astype(np.float64)))))) < 5e-2
+    # exact 1-NN and k-NN sets against cKDTree
+    q = cropped[::7].copy()
+    idx, _ = O.nn1(q, cropped)
+    d, j = tree.query(q[:, :3].astype(np.float64), k=1)
+    assert (idx == j).mean() > 0.999  # (ties / rounding at equal distances aside)
+    _, kc, ki = O.normals_knn(cropped, 12, cell=0.1, mode=0, with_indices=True)
+    dk, jk = tree.query(xyz, k=12)
+    same = sum(set(jk[t]) == set(ki[t]) for t in range(len(xyz)))
+    assert same >= 0.999 * len(xyz)
+    # VoxelGrid keys against a numpy restatement in float32
+    leaf = 0.2
+    vox = O.voxel(cropped, leaf)
+    inv = np.float32(1.0) / np.float32(leaf)
+    mn = cropped[:, :3].min(0); mx = cropped[:, :3].max(0)
+    minb = np.floor(mn * inv).astype(np.int64); maxb = np.floor(mx * inv).astype(np.int64)
+    div = maxb - minb + 1
+    ijk = (np.floor(cropped[:, :3] * inv) - minb.astype(np.float32)).astype(np.int64)
+    keys = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    assert np.array_equal(keys.astype(np.int32), vox["keys"])
+    assert np.array_equal(np.unique(keys).astype(np.int32), vox["voxel_keys"])
+    # getLocalFrame: eigen-decomposition against numpy.linalg.eigh on the oracle's own scatter matrix
+    cloud, nrm_c, _ = O.compact(cropped, nrm)
+    fr = O.local_frame(nrm_c, 0.2)
+    w, v = np.linalg.eigh(fr["scatter"].astype(np.float64))
+    assert np.abs(w - fr["vals"]).max() <= 1e-6 * np.abs(w).max()
+    assert abs(abs(float(np.dot(v[:, 0], fr["vecs"][:, 0]))) - 1.0) < 1e-6
+
+
+def test_oracle_trig_is_correctly_rounded_and_libm_independent():
+    g = np.random.Generator(np.random.Philox(5))
+    n = 200_000
+    y = (np.abs(g.normal(size=n)) * 10.0 ** g.uniform(-6, 2, n)).astype(np.float32)
+    x = (g.normal(size=n) * 10.0 ** g.uniform(-6, 2, n)).astype(np.float32)
+    th = g.uniform(0, np.pi / 3, n).astype(np.float32)
+    a, _, _ = O.trig(y, x)
+    _, s, c = O.trig(y, th)
+    assert np.array_equal(a, np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32))
+    assert np.array_equal(s, np.sin(th.astype(np.float64)).astype(np.float32))
+    assert np.array_equal(c, np.cos(th.astype(np.float64)).astype(np.float32))
+    z = np.zeros(1, np.float32)
+    assert O.trig(z, z)[0][0] == 0.0 and abs(O.trig(z, -z)[0][0] - np.float32(np.pi)) == 0.0   # atan2(+0, -0) = pi
+
+
+def test_knn_oracle_grid_equals_brute_force():
+    pts = synth.curved_tunnel(3_000, seed=9, outlier_frac=0.1)
+    pts[4] = [np.nan, 0, 0, 1]
+    a = O.normals_knn(pts, 20, cell=0.15, mode=0, with_indices=True)
+    b = O.normals_knn(pts, 20, cell=0.15, mode=1, with_indices=True)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))

@@ -128,7 +128,8 @@ SYMBOLS = [
     "gm_get_search_stats", "gm_set_voxel_mode", "gm_ransac_pair", "gm_ransac_select_pair", "gm_ransac_export_keys",
     "gm_ransac_import_keys", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
     "gm_map_load", "gm_map_leaf", "gm_set_normals_mode", "gm_set_graph_mode", "gm_get_graph_stats",
-    "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint", "gm_set_knn", "gm_download_knn_indices",
+    "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint", "gm_set_knn", "gm_download_knn_indices", "gm_pointcloud2_size", "gm_encode_pointcloud2", "gm_marker_array_size",
+    "gm_encode_marker_array",
 ]
 
 
@@ -218,6 +219,10 @@ def _lib():
         "gm_set_voxel_bbox_hint": (i32, [vp, vp, vp]),
         "gm_set_knn": (i32, [vp, i32, i32]),
         "gm_download_knn_indices": (i32, [vp, vp, sz]),
+        "gm_pointcloud2_size": (sz, [sz, C.c_char_p]),
+        "gm_encode_pointcloud2": (i32, [vp, sz, C.c_char_p, C.c_uint32, C.c_uint64, i32, vp, sz, C.POINTER(sz)]),
+        "gm_marker_array_size": (sz, [i32, C.c_char_p, C.c_char_p]),
+        "gm_encode_marker_array": (i32, [vp, i32, C.c_char_p, C.c_char_p, C.c_uint64, vp, sz, C.POINTER(sz)]),
         "gm_set_grid_box": (i32, [vp, vp, vp]),
         "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
         "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
@@ -765,3 +770,27 @@ class PeerComm:
             self.close()
         except Exception:
             pass
+
+
+def encode_pointcloud2(xyzw: np.ndarray, frame_id: str = "/velodyne", seq: int = 0, stamp_ns: int = 0, is_dense: bool = True) -> bytes:
+    """sensor_msgs/PointCloud2 (ROS 1 wire format) of an n x 4 float32 cloud, as pcl::toROSMsg lays it out."""
+    a = _as_xyzw(xyzw)
+    f = frame_id.encode()
+    buf = (C.c_ubyte * _lib().gm_pointcloud2_size(a.shape[0], f))()
+    n = C.c_size_t(0)
+    st = _lib().gm_encode_pointcloud2(_ptr(a), a.shape[0], f, seq, stamp_ns, 1 if is_dense else 0, buf, len(buf), C.byref(n))
+    if st != GM_OK:
+        raise GmError(st, "gm_encode_pointcloud2")
+    return bytes(buf[: n.value])
+
+
+def encode_marker_array(arrows: np.ndarray, ns: str, frame_id: str = "/velodyne", stamp_ns: int = 0) -> bytes:
+    """visualization_msgs/MarkerArray (ROS 1 wire format) of ARROW_DTYPE arrows (markers_eigen / markers_normals)."""
+    a = np.ascontiguousarray(arrows, ARROW_DTYPE)
+    f, s_ = frame_id.encode(), ns.encode()
+    buf = (C.c_ubyte * _lib().gm_marker_array_size(len(a), f, s_))()
+    n = C.c_size_t(0)
+    st = _lib().gm_encode_marker_array(_ptr(a), len(a), f, s_, stamp_ns, buf, len(buf), C.byref(n))
+    if st != GM_OK:
+        raise GmError(st, "gm_encode_marker_array")
+    return bytes(buf[: n.value])

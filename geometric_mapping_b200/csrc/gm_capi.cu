@@ -1660,6 +1660,92 @@ void gm_markers_normals_mode(const float* centroids, const float* nn_normal8, in
 }  // extern "C"
 
 
+// ---- ROS-free encoders of what cloud_cb publishes ------------------------------------------------------
+// ROS 1 wire format (little endian; string / array = uint32 length + payload), written field by field in message order.
+namespace {
+struct Wr {
+  unsigned char* p; size_t cap, n = 0; bool ok = true;
+  Wr(void* b, size_t c) : p((unsigned char*)b), cap(c) {}
+  void raw(const void* src, size_t k) { if (p && n + k <= cap) std::memcpy(p + n, src, k); else if (p) ok = false; n += k; }
+  void u8(uint8_t v) { raw(&v, 1); }
+  void u32(uint32_t v) { raw(&v, 4); }
+  void i32(int32_t v) { raw(&v, 4); }
+  void f32(float v) { raw(&v, 4); }
+  void f64(double v) { raw(&v, 8); }
+  void str(const char* s) { const uint32_t l = s ? (uint32_t)std::strlen(s) : 0u; u32(l); if (l) raw(s, l); }
+  void header(uint32_t seq, uint64_t stamp_ns, const char* frame) { u32(seq); u32((uint32_t)(stamp_ns / 1000000000ull)); u32((uint32_t)(stamp_ns % 1000000000ull)); str(frame); }
+};
+
+// sensor_msgs/PointCloud2 exactly as pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZ>) builds it (src/geometric_mapping.cpp:102-103):
+// unorganised (height 1), fields x,y,z FLOAT32 at offsets 0,4,8, point_step 16 (the PointXYZ padding word travels), is_dense as given
+size_t write_pointcloud2(Wr& w, const float* xyzw, size_t n, const char* frame, uint32_t seq, uint64_t stamp_ns, int is_dense) {
+  w.header(seq, stamp_ns, frame);
+  w.u32(1); w.u32((uint32_t)n);
+  w.u32(3);
+  const char* names[3] = {"x", "y", "z"};
+  for (uint32_t k = 0; k < 3; ++k) { w.str(names[k]); w.u32(4 * k); w.u8(7 /* FLOAT32 */); w.u32(1); }
+  w.u8(0); w.u32(16); w.u32((uint32_t)(16 * n));
+  w.u32((uint32_t)(16 * n));
+  if (n) w.raw(xyzw, 16 * n);
+  w.u8(is_dense ? 1 : 0);
+  return w.n;
+}
+
+// visualization_msgs/Marker as rvizArrow fills it (src/tunnel_processing.cpp:171-203): ARROW (0), ADD (0), two points,
+// default pose / lifetime / frame_locked, colour serialised r,g,b,a from the (a,r,g,b) payload
+void write_marker(Wr& w, const gm_arrow& a, const char* frame, const char* ns, uint64_t stamp_ns) {
+  w.header(0, stamp_ns, frame);
+  w.str(ns); w.i32(a.id); w.i32(0); w.i32(0);
+  for (int k = 0; k < 7; ++k) w.f64(0.0);                       // pose: position + orientation, value-initialised
+  for (int k = 0; k < 3; ++k) w.f64((double)a.scale[k]);
+  w.f32(a.color_argb[1]); w.f32(a.color_argb[2]); w.f32(a.color_argb[3]); w.f32(a.color_argb[0]);
+  w.i32(0); w.i32(0);                                          // lifetime
+  w.u8(0);                                                     // frame_locked
+  w.u32(2);
+  for (int k = 0; k < 3; ++k) w.f64((double)a.start[k]);
+  for (int k = 0; k < 3; ++k) w.f64((double)a.end[k]);
+  w.u32(0);                                                    // colors[]
+  w.str(""); w.str("");                                        // text, mesh_resource
+  w.u8(0);                                                     // mesh_use_embedded_materials
+}
+}  // namespace
+
+extern "C" {
+
+size_t gm_pointcloud2_size(size_t n_points, const char* frame_id) {
+  Wr w(nullptr, 0);
+  return write_pointcloud2(w, nullptr, n_points, frame_id, 0, 0, 1);
+}
+
+gm_status gm_encode_pointcloud2(const float* xyzw, size_t n, const char* frame_id, uint32_t seq, uint64_t stamp_ns, int32_t is_dense, void* buf,
+                                size_t capacity, size_t* bytes) {
+  if ((n && !xyzw) || !buf || n > 0x0FFFFFFFu) return GM_ERR_INVALID_ARG;
+  Wr w(buf, capacity);
+  write_pointcloud2(w, xyzw, n, frame_id, seq, stamp_ns, is_dense);
+  if (bytes) *bytes = w.n;
+  return w.ok ? GM_OK : GM_ERR_CAPACITY;
+}
+
+size_t gm_marker_array_size(int32_t n_markers, const char* frame_id, const char* ns) {
+  Wr w(nullptr, 0);
+  gm_arrow a{};
+  write_marker(w, a, frame_id, ns, 0);
+  return 4 + (size_t)std::max(n_markers, 0) * w.n;
+}
+
+gm_status gm_encode_marker_array(const gm_arrow* arrows, int32_t n, const char* frame_id, const char* ns, uint64_t stamp_ns, void* buf,
+                                 size_t capacity, size_t* bytes) {
+  if (n < 0 || (n && !arrows) || !buf) return GM_ERR_INVALID_ARG;
+  Wr w(buf, capacity);
+  w.u32((uint32_t)n);
+  for (int32_t i = 0; i < n; ++i) write_marker(w, arrows[i], frame_id, ns, stamp_ns);
+  if (bytes) *bytes = w.n;
+  return w.ok ? GM_OK : GM_ERR_CAPACITY;
+}
+
+}  // extern "C"
+
+
 // ---- peer-memory collectives (gm_comm.cuh) -----------------------------------------------------------------------
 struct gm_comm {
   int rank = 0, world = 1, device = 0;

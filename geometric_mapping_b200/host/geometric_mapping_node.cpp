@@ -9,6 +9,7 @@
 #include <fstream>
 #include <random>
 #include <sstream>
+#include <vector>
 
 #include "paramHandler.hpp"
 #include "tunnel_processing.hpp"
@@ -17,29 +18,38 @@ using namespace gmhost;
 
 static Parameters* params = nullptr;
 
-static void cloud_cb(const CloudPtr& cloud, const SearchPtr& gm) {
+// the body of cloud_cb (src/geometric_mapping.cpp:48-125), statement for statement, on the mirrored seam
+static void cloud_cb(const CloudPtr& cloud) {
   std::fprintf(stderr, "[ INFO] Callback started...\n");
-  CloudPtr cloudChopped = chopCloud(params->getBoxFilterBound(), cloud, gm);
+  CloudPtr cloudChopped = chopCloud(params->getBoxFilterBound(), cloud);                       // :57
   std::fprintf(stderr, "[ INFO] Box filter applied...\n");
-  SearchPtr kdtree = gm;
-  NormalsPtr cloudNormals = getNormals(params->getNeighborRadius(), cloudChopped, kdtree);
-  MarkerArray normalsDisp = rvizNormals(params->getLeafSize(), cloudChopped, kdtree, cloudNormals);
+  SearchPtr kdtree;                                                                             // :62
+  NormalsPtr cloudNormals = getNormals(params->getNeighborRadius(), cloudChopped, kdtree);     // :63
+  MarkerArray* normalsDisp = rvizNormals(params->getLeafSize(), cloudChopped, kdtree, cloudNormals);  // :70-75
   std::fprintf(stderr, "[ INFO] Surface normals found...\n");
-  Vector3f eigenVals{};
-  Matrix3f eigenVecs{};
-  getLocalFrame((int)cloudChopped->size(), params->getWeightingFactor(), cloudNormals, gm, eigenVals, eigenVecs);
-  Vector3f centerAxis = eigenVecs.col(0);  // assume that first eigenvec is smallest (ascending order)
-  MarkerArray eigenBasis = rvizEigens(eigenVals, eigenVecs);
+  Vector3f* eigenVals = nullptr;                                                                // :79-80
+  Matrix3f* eigenVecs = nullptr;
+  getLocalFrame((int)cloudChopped->size(), params->getWeightingFactor(), cloudNormals, eigenVals, eigenVecs);  // :82-88
+  Vector3f* centerAxis = new Vector3f(eigenVecs->col(0));  // :91-92 assume that first eigenvec is smallest (ascending order)
+  MarkerArray* eigenBasis = rvizEigens(*eigenVals, *eigenVecs);                                 // :96
   std::printf("Weights made of size:\t%zu\n", cloudChopped->size());
-  std::printf("Eigenvalues are:\n%g %g %g\n", eigenVals[0], eigenVals[1], eigenVals[2]);
+  std::printf("Eigenvalues are:\n%g %g %g\n", (*eigenVals)[0], (*eigenVals)[1], (*eigenVals)[2]);
   std::printf("Eigenvectors are:\n");
-  for (int r = 0; r < 3; ++r) std::printf("%g %g %g\n", eigenVecs(r, 0), eigenVecs(r, 1), eigenVecs(r, 2));
-  std::printf("Center Axis is:\n%g %g %g\n", centerAxis[0], centerAxis[1], centerAxis[2]);
-  if (params->displayCloud()) std::printf("publish cloudOutput: %zu points\n", cloudChopped->size());
-  if (params->displayNormals()) std::printf("publish normalsOutput: %zu markers\n", normalsDisp.size());
-  if (params->displayCenterAxis()) std::printf("publish eigenBasisOutput: %zu markers, E1 scale %g %g %g\n", eigenBasis.size(),
-                                               eigenBasis[0].scale[0], eigenBasis[0].scale[1], eigenBasis[0].scale[2]);
+  for (int r = 0; r < 3; ++r) std::printf("%g %g %g\n", (*eigenVecs)(r, 0), (*eigenVecs)(r, 1), (*eigenVecs)(r, 2));
+  std::printf("Center Axis is:\n%g %g %g\n", (*centerAxis)[0], (*centerAxis)[1], (*centerAxis)[2]);
+  // :100-117: what is published, as the ROS-free byte payloads of the messages (gm_encode_*)
+  if (params->displayCloud()) {
+    std::vector<unsigned char> msg(gm_pointcloud2_size(cloudChopped->size(), "/velodyne"));
+    size_t bytes = 0;
+    gm_encode_pointcloud2(cloudChopped->empty() ? nullptr : &cloudChopped->data()->x, cloudChopped->size(), "/velodyne", 0, 0, 1, msg.data(),
+                          msg.size(), &bytes);
+    std::printf("publish cloudOutput: %zu points, %zu bytes\n", cloudChopped->size(), bytes);
+  }
+  if (params->displayNormals()) std::printf("publish normalsOutput: %zu markers\n", normalsDisp->size());
+  if (params->displayCenterAxis()) std::printf("publish eigenBasisOutput: %zu markers, E1 scale %g %g %g\n", eigenBasis->size(),
+                                               (*eigenBasis)[0].scale[0], (*eigenBasis)[0].scale[1], (*eigenBasis)[0].scale[2]);
   std::fprintf(stderr, "[ INFO] Published...\n");
+  delete normalsDisp; delete eigenBasis; delete eigenVals; delete eigenVecs; delete centerAxis;  // (the reference leaks all five)
 }
 
 int main(int argc, char** argv) {
@@ -79,17 +89,19 @@ int main(int argc, char** argv) {
     for (auto& p : *cloud) { float t = ut(rng), r = 2.5f + nr(rng); p.x = ux(rng); p.y = r * std::cos(t); p.z = r * std::sin(t); p.pad = 1.0f; }
   }
 
-  gm_params gp = param.toGm();
-  gm_ctx* ctx = nullptr;
-  gm_status s = gm_create(&gp, std::max<size_t>(cloud->size(), 1), 16, &ctx);
-  if (s != GM_OK) { std::fprintf(stderr, "gm_create: %s\n", gm_status_string(s)); return 3; }
+  useParameters(param.toGm());  // parameters that are not arguments of the seam functions (quirk switches, is_dense)
   int rc = 0;
   try {
-    cloud_cb(cloud, std::make_shared<SearchHandle>(ctx));
+    cloud_cb(cloud);
   } catch (const GmError& e) {
-    std::fprintf(stderr, "error: %s (%s)\n", e.what(), gm_last_error(ctx));
+    std::fprintf(stderr, "error: %s (%s)\n", e.what(), gm_last_error(context()));
     rc = 4;
   }
-  gm_destroy(ctx);
+  if (rc == 0) {
+    gm_params cur;
+    gm_get_params(context(), &cur);
+    std::printf("context weight_mode %d arrow_mode %d\n", cur.weight_mode, cur.arrow_mode);
+  }
+  releaseContext();
   return rc;
 }

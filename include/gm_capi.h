@@ -359,6 +359,22 @@ GM_API void gm_markers_normals(const float* centroids_xyzw, const float* nn_norm
 /* same with the arrow-end switch of gm_params.arrow_mode (0 = reference quirk B.4, 1 = end = start + normal) */
 GM_API void gm_markers_normals_mode(const float* centroids_xyzw, const float* nn_normal8, int32_t V, int32_t arrow_mode, gm_arrow* out);
 
+/* ---- ROS-free encoders of the published messages: the byte payloads a ROS 1 publisher would put on the
+ * wire for what cloud_cb publishes (src/geometric_mapping.cpp:100-117), so a transport that is not roscpp can ship them
+ * and a subscriber deserialises them as the stock message types.
+ *   cloudOutput       sensor_msgs/PointCloud2 as pcl::toROSMsg(PointCloud<PointXYZ>) lays it out (:102-103): height 1, fields
+ *                     x,y,z FLOAT32 @ 0,4,8, point_step 16
+ *   normalsOutput /   visualization_msgs/MarkerArray of ARROW markers as rvizArrow fills them (src/tunnel_processing.cpp:
+ *   eigenBasisOutput  171-203; frame "/velodyne", include/geometric_mapping/tunnel_processing.hpp:72-73), from the gm_arrow
+ *                     payloads of gm_markers_eigen / gm_markers_normals (ns "eigenBasis" / "normals")
+ * The *_size functions give the exact byte count; GM_ERR_CAPACITY if the buffer is smaller. */
+GM_API size_t gm_pointcloud2_size(size_t n_points, const char* frame_id);
+GM_API gm_status gm_encode_pointcloud2(const float* xyzw, size_t n, const char* frame_id, uint32_t seq, uint64_t stamp_ns, int32_t is_dense,
+                                       void* buf, size_t capacity, size_t* bytes);
+GM_API size_t gm_marker_array_size(int32_t n_markers, const char* frame_id, const char* ns);
+GM_API gm_status gm_encode_marker_array(const gm_arrow* arrows, int32_t n, const char* frame_id, const char* ns, uint64_t stamp_ns, void* buf,
+                                        size_t capacity, size_t* bytes);
+
 /* ---- aggregated voxel map across scans (builder-defined, the reference keeps nothing between
  * callbacks, src/geometric_mapping.cpp:48-125) --------------------------------------------------------
  * A device hash table keyed by the GLOBAL VoxelGrid cell floor(p * inv_leaf) of every inserted point, holding the

@@ -1355,3 +1355,29 @@ def test_sharded_round_and_map_collectives_with_a_single_rank():
         assert ctx.counts().device_error == 0
         ctx.set_comm(None)
         comm.close()
+
+
+def test_cpp_host_shim_keeps_the_quirk_switches_of_the_parameters():
+    """The per-call parameters of the seam (bound, radius, leaf, wf) are written into the context read-modify-write: the
+    quirk switches installed with useParameters() survive them (a thread-local all-defaults cache used to reset them)."""
+    import subprocess
+
+    from geometric_mapping_b200 import build as gm_build
+
+    exe = gm_build.build_host()
+    pts = synth.straight_cylinder(40_000, seed=3, noise=0.01)
+    path = "/tmp/gm_scan_quirk.f32x4"
+    pts.tofile(path)
+    args = [exe, "--set", "neighborRadius=0.2", "--set", "voxelGridLeafSize=0.5", "--set", "weightingFactor=0.25", "--scan", path]
+    vals = {}
+    for wm in (0, 1):
+        res = subprocess.run(args + ["--set", f"weightMode={wm}", "--set", "arrowMode=1"], capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr
+        assert f"context weight_mode {wm} arrow_mode 1" in res.stdout
+        lines = res.stdout.splitlines()
+        vals[wm] = np.array([float(v) for v in lines[lines.index("Eigenvalues are:") + 1].split()])
+        with _ctx(len(pts), neighborRadius=0.2, voxelGridLeafSize=0.5, weightingFactor=0.25, weight_mode=wm) as ctx:
+            ctx.upload_scan(pts)
+            ctx.process_scan(None, None)
+            assert np.allclose(vals[wm], ctx.frame()["vals"], rtol=1e-5)
+    assert not np.allclose(vals[0], vals[1], rtol=1e-3)   # the two weight laws really differ

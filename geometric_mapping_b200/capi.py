@@ -129,7 +129,7 @@ SYMBOLS = [
     "gm_ransac_import_keys", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
     "gm_map_load", "gm_map_leaf", "gm_set_normals_mode", "gm_set_graph_mode", "gm_get_graph_stats",
     "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint", "gm_set_knn", "gm_download_knn_indices", "gm_pointcloud2_size", "gm_encode_pointcloud2", "gm_marker_array_size",
-    "gm_encode_marker_array",
+    "gm_encode_marker_array", "gm_store_open", "gm_store_close", "gm_store_append", "gm_store_append_blob", "gm_store_count", "gm_store_info", "gm_store_read",
 ]
 
 
@@ -223,6 +223,13 @@ def _lib():
         "gm_encode_pointcloud2": (i32, [vp, sz, C.c_char_p, C.c_uint32, C.c_uint64, i32, vp, sz, C.POINTER(sz)]),
         "gm_marker_array_size": (sz, [i32, C.c_char_p, C.c_char_p]),
         "gm_encode_marker_array": (i32, [vp, i32, C.c_char_p, C.c_char_p, C.c_uint64, vp, sz, C.POINTER(sz)]),
+        "gm_store_open": (i32, [C.c_char_p, i32, C.POINTER(vp)]),
+        "gm_store_close": (None, [vp]),
+        "gm_store_append": (i32, [vp, vp, C.c_uint64, C.c_uint64, vp]),
+        "gm_store_append_blob": (i32, [vp, C.c_uint64, C.c_uint64, vp, vp, sz]),
+        "gm_store_count": (i64, [vp]),
+        "gm_store_info": (i32, [vp, i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, C.POINTER(C.c_uint64)]),
+        "gm_store_read": (i32, [vp, i64, vp, sz, C.POINTER(sz)]),
         "gm_set_grid_box": (i32, [vp, vp, vp]),
         "gm_set_owned_range": (i32, [vp, i32, C.c_float, C.c_float]),
         "gm_get_voxel_bbox": (i32, [vp, vp, vp]),
@@ -794,3 +801,66 @@ def encode_marker_array(arrows: np.ndarray, ns: str, frame_id: str = "/velodyne"
     if st != GM_OK:
         raise GmError(st, "gm_encode_marker_array")
     return bytes(buf[: n.value])
+
+
+class PrimitiveStore:
+    """Append-only on-disk store of per-scan compressed primitives (include/gm_capi.h: gm_store_*)."""
+
+    def __init__(self, path: str, create: bool = True):
+        h = C.c_void_p()
+        st = _lib().gm_store_open(path.encode(), 1 if create else 0, C.byref(h))
+        if st != GM_OK:
+            raise GmError(st, "gm_store_open")
+        self._h = h
+
+    def append(self, ctx: "Context", scan_id: int, stamp_ns: int = 0, pose34=None):
+        pose = None if pose34 is None else np.ascontiguousarray(np.asarray(pose34, np.float32).reshape(12))
+        st = _lib().gm_store_append(self._h, ctx._h, scan_id, stamp_ns, _ptr(pose))
+        if st != GM_OK:
+            raise GmError(st, "gm_store_append")
+
+    def append_blob(self, blob: bytes, scan_id: int, stamp_ns: int = 0, pose34=None):
+        pose = None if pose34 is None else np.ascontiguousarray(np.asarray(pose34, np.float32).reshape(12))
+        buf = (C.c_ubyte * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
+        st = _lib().gm_store_append_blob(self._h, scan_id, stamp_ns, _ptr(pose), buf, len(blob))
+        if st != GM_OK:
+            raise GmError(st, "gm_store_append_blob")
+
+    def __len__(self):
+        return int(_lib().gm_store_count(self._h))
+
+    def info(self, i: int):
+        a, b, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        pose = np.zeros(12, np.float32)
+        st = _lib().gm_store_info(self._h, i, C.byref(a), C.byref(b), _ptr(pose), C.byref(n))
+        if st != GM_OK:
+            raise GmError(st, "gm_store_info")
+        return {"scan_id": int(a.value), "stamp_ns": int(b.value), "pose": pose.reshape(3, 4), "bytes": int(n.value)}
+
+    def read(self, i: int) -> bytes:
+        n = C.c_size_t(0)
+        st = _lib().gm_store_read(self._h, i, None, 0, C.byref(n))
+        if st != GM_OK:
+            raise GmError(st, "gm_store_read")
+        buf = (C.c_ubyte * max(n.value, 1))()
+        st = _lib().gm_store_read(self._h, i, buf, n.value, C.byref(n))
+        if st != GM_OK:
+            raise GmError(st, "gm_store_read")
+        return bytes(buf[: n.value])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().gm_store_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -296,6 +296,10 @@ gm_status regrid(gm_ctx* ctx) {
   ctx->grid = make_grid(ctx->prm, ctx->have_grid_box ? ctx->grid_box_min : nullptr, ctx->have_grid_box ? ctx->grid_box_max : nullptr);
   if (!same_grid(old, ctx->grid)) {
     GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    // everything built on the old grid (runs, block table, normals, and whatever consumed them) is stale: the next stage
+    // after gm_crop must be gm_normals again (GM_ERR_STAGE_ORDER otherwise), not a search over an empty table
+    ctx->have_normals = ctx->have_compacted = ctx->have_voxel = ctx->have_frame = ctx->have_labels = ctx->have_poly = ctx->have_comp = false;
+    ctx->have_ransac[0] = ctx->have_ransac[1] = ctx->have_model[0] = ctx->have_model[1] = false;
     ctx->tab_entries = 0;  // forces reallocation + clear
     return ensure_block_table(ctx);
   }
@@ -419,7 +423,8 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   if (validate_params(p) != GM_OK || max_points == 0 || max_points >= (1ull << 30) || max_hypotheses < 0) return GM_ERR_INVALID_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GM_ERR_NO_DEVICE; }
-  gm_ctx* ctx = new gm_ctx();
+  gm_ctx* ctx = new (std::nothrow) gm_ctx();
+  if (!ctx) return GM_ERR_INTERNAL;
   ctx->prm = *p;
   ctx->cap = max_points;
   ctx->hcap = std::max(max_hypotheses, 1);
@@ -524,6 +529,10 @@ gm_status gm_set_params(gm_ctx* ctx, const gm_params* p) {
   if (!ctx || validate_params(p) != GM_OK) return GM_ERR_INVALID_ARG;
   ++ctx->graph_gen;  // what a scan launches may change: captured graphs of older generations are no longer used
   if (p->maxSlices > ctx->prm.maxSlices) { ctx->err = "maxSlices cannot grow after gm_create"; return GM_ERR_CAPACITY; }
+  if (p->boxFilterBound != ctx->prm.boxFilterBound || p->is_dense != ctx->prm.is_dense) {  // the crop itself is stale
+    ctx->have_crop = ctx->have_normals = ctx->have_compacted = ctx->have_voxel = ctx->have_frame = ctx->have_labels = ctx->have_poly = ctx->have_comp = false;
+    ctx->have_ransac[0] = ctx->have_ransac[1] = ctx->have_model[0] = ctx->have_model[1] = false;
+  }
   ctx->prm = *p;
   return regrid(ctx);
 }
@@ -1660,6 +1669,147 @@ void gm_markers_normals_mode(const float* centroids, const float* nn_normal8, in
 }  // extern "C"
 
 
+// ---- on-disk store of the per-scan compressed primitives (builder-defined) --------------------------------
+// Append-only file: 'GMS1' | version u32, then one record per scan:
+//   'GMSR' u32 | scan_id u64 | stamp_ns u64 | pose [R|t] 12 x f32 | blob_bytes u64 | blob (the GMC1 blob of
+//   gm_download_compressed) | crc32(blob) u32
+// The index (offset of every record) is rebuilt by scanning the file when it is opened; a torn last record (crash during an
+// append) fails its length / CRC check, is ignored, and the next append overwrites it.
+struct gm_store {
+  FILE* f = nullptr;
+  std::string path, err;
+  struct Rec { uint64_t scan_id, stamp_ns, blob_bytes; long blob_off; float pose[12]; };
+  std::vector<Rec> recs;
+  long end = 8;  // where the next record goes
+};
+
+namespace {
+uint32_t crc32_of(const unsigned char* p, size_t n) {
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+    init = true;
+  }
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+constexpr uint32_t kStoreMagic = 0x31534D47u /* 'GMS1' */, kRecMagic = 0x52534D47u /* 'GMSR' */;
+constexpr size_t kRecHead = 4 + 8 + 8 + 48 + 8;
+}  // namespace
+
+extern "C" {
+
+gm_status gm_store_open(const char* path, int32_t create, gm_store** out) {
+  if (!path || !out) return GM_ERR_INVALID_ARG;
+  *out = nullptr;
+  gm_store* st = new (std::nothrow) gm_store();
+  if (!st) return GM_ERR_INTERNAL;
+  try {
+    st->path = path;
+    st->f = std::fopen(path, "r+b");
+    if (!st->f && create) {
+      st->f = std::fopen(path, "w+b");
+      const uint32_t hdr[2] = {kStoreMagic, 1u};
+      if (!st->f || std::fwrite(hdr, 4, 2, st->f) != 2 || std::fflush(st->f) != 0) { if (st->f) std::fclose(st->f); delete st; return GM_ERR_INVALID_ARG; }
+    }
+    if (!st->f) { delete st; return GM_ERR_INVALID_ARG; }
+    uint32_t hdr[2] = {0, 0};
+    std::fseek(st->f, 0, SEEK_SET);
+    if (std::fread(hdr, 4, 2, st->f) != 2 || hdr[0] != kStoreMagic || hdr[1] != 1u) { std::fclose(st->f); delete st; return GM_ERR_INVALID_ARG; }
+    std::fseek(st->f, 0, SEEK_END);
+    const long fsize = std::ftell(st->f);
+    long off = 8;
+    std::vector<unsigned char> blob;
+    while (off + (long)kRecHead + 4 <= fsize) {  // rebuild the index; stop at the first record that does not check out
+      unsigned char h[kRecHead];
+      std::fseek(st->f, off, SEEK_SET);
+      if (std::fread(h, 1, kRecHead, st->f) != kRecHead) break;
+      uint32_t magic; gm_store::Rec r;
+      std::memcpy(&magic, h, 4); std::memcpy(&r.scan_id, h + 4, 8); std::memcpy(&r.stamp_ns, h + 12, 8);
+      std::memcpy(r.pose, h + 20, 48); std::memcpy(&r.blob_bytes, h + 68, 8);
+      if (magic != kRecMagic || r.blob_bytes > (uint64_t)(fsize - off - (long)kRecHead - 4)) break;
+      blob.resize((size_t)r.blob_bytes);
+      uint32_t crc = 0;
+      if ((r.blob_bytes && std::fread(blob.data(), 1, blob.size(), st->f) != blob.size()) || std::fread(&crc, 4, 1, st->f) != 1) break;
+      if (crc != crc32_of(blob.data(), blob.size())) break;
+      r.blob_off = off + (long)kRecHead;
+      st->recs.push_back(r);
+      off += (long)kRecHead + (long)r.blob_bytes + 4;
+    }
+    st->end = off;
+  } catch (...) { if (st->f) std::fclose(st->f); delete st; return GM_ERR_INTERNAL; }
+  *out = st;
+  return GM_OK;
+}
+
+void gm_store_close(gm_store* st) {
+  if (!st) return;
+  if (st->f) std::fclose(st->f);
+  delete st;
+}
+
+gm_status gm_store_append_blob(gm_store* st, uint64_t scan_id, uint64_t stamp_ns, const float* pose34, const void* blob, size_t bytes) {
+  if (!st || !st->f || (bytes && !blob)) return GM_ERR_INVALID_ARG;
+  try {
+    gm_store::Rec r{};
+    r.scan_id = scan_id; r.stamp_ns = stamp_ns; r.blob_bytes = bytes; r.blob_off = st->end + (long)kRecHead;
+    const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    std::memcpy(r.pose, pose34 ? pose34 : ident, 48);
+    unsigned char h[kRecHead];
+    std::memcpy(h, &kRecMagic, 4); std::memcpy(h + 4, &r.scan_id, 8); std::memcpy(h + 12, &r.stamp_ns, 8);
+    std::memcpy(h + 20, r.pose, 48); std::memcpy(h + 68, &r.blob_bytes, 8);
+    const uint32_t crc = crc32_of((const unsigned char*)blob, bytes);
+    if (std::fseek(st->f, st->end, SEEK_SET) != 0 || std::fwrite(h, 1, kRecHead, st->f) != kRecHead ||
+        (bytes && std::fwrite(blob, 1, bytes, st->f) != bytes) || std::fwrite(&crc, 4, 1, st->f) != 1 || std::fflush(st->f) != 0) {
+      st->err = "write failed";
+      return GM_ERR_INVALID_ARG;
+    }
+    st->recs.push_back(r);
+    st->end += (long)kRecHead + (long)bytes + 4;
+  } catch (...) { return GM_ERR_INTERNAL; }
+  return GM_OK;
+}
+
+/* compress output of `ctx` (after gm_compress) -> one record */
+gm_status gm_store_append(gm_store* st, gm_ctx* ctx, uint64_t scan_id, uint64_t stamp_ns, const float* pose34) {
+  if (!st || !ctx) return GM_ERR_INVALID_ARG;
+  size_t bytes = 0;
+  gm_status s = gm_download_compressed(ctx, nullptr, 0, &bytes);
+  if (s != GM_OK) return s;
+  try {
+    std::vector<unsigned char> blob(bytes);
+    if ((s = gm_download_compressed(ctx, blob.data(), blob.size(), &bytes)) != GM_OK) return s;
+    return gm_store_append_blob(st, scan_id, stamp_ns, pose34, blob.data(), bytes);
+  } catch (...) { return GM_ERR_INTERNAL; }
+}
+
+int64_t gm_store_count(const gm_store* st) { return st ? (int64_t)st->recs.size() : -1; }
+
+gm_status gm_store_info(const gm_store* st, int64_t i, uint64_t* scan_id, uint64_t* stamp_ns, float* pose34, uint64_t* blob_bytes) {
+  if (!st || i < 0 || i >= (int64_t)st->recs.size()) return GM_ERR_INVALID_ARG;
+  const gm_store::Rec& r = st->recs[(size_t)i];
+  if (scan_id) *scan_id = r.scan_id;
+  if (stamp_ns) *stamp_ns = r.stamp_ns;
+  if (pose34) std::memcpy(pose34, r.pose, 48);
+  if (blob_bytes) *blob_bytes = r.blob_bytes;
+  return GM_OK;
+}
+
+gm_status gm_store_read(gm_store* st, int64_t i, void* buf, size_t capacity, size_t* bytes) {
+  if (!st || !st->f || i < 0 || i >= (int64_t)st->recs.size() || !bytes) return GM_ERR_INVALID_ARG;
+  const gm_store::Rec& r = st->recs[(size_t)i];
+  *bytes = (size_t)r.blob_bytes;
+  if (!buf) return GM_OK;
+  if (capacity < r.blob_bytes) return GM_ERR_CAPACITY;
+  if (std::fseek(st->f, r.blob_off, SEEK_SET) != 0 || (r.blob_bytes && std::fread(buf, 1, (size_t)r.blob_bytes, st->f) != r.blob_bytes)) return GM_ERR_INVALID_ARG;
+  return GM_OK;
+}
+
+}  // extern "C"
+
+
 // ---- ROS-free encoders of what cloud_cb publishes ------------------------------------------------------
 // ROS 1 wire format (little endian; string / array = uint32 length + payload), written field by field in message order.
 namespace {
@@ -2090,12 +2240,21 @@ gm_status gm_map_load(const char* path, size_t min_capacity_voxels, gm_map** out
   uint32_t magic = 0, version = 0; double leaf = 0; uint64_t V = 0;
   bool ok = std::fread(&magic, 4, 1, f) == 1 && std::fread(&version, 4, 1, f) == 1 && std::fread(&leaf, 8, 1, f) == 1 && std::fread(&V, 8, 1, f) == 1 &&
             magic == 0x314D4D47u && version == 1 && leaf > 0.0 && V < (1ull << 31);
-  std::vector<unsigned long long> k; std::vector<int> c; std::vector<long long> su;
-  if (ok && V) {
-    k.resize(V); c.resize(V); su.resize(3 * V);
-    ok = std::fread(k.data(), 8, V, f) == V && std::fread(c.data(), 4, V, f) == V && std::fread(su.data(), 8, 3 * V, f) == 3 * V;
+  if (ok) {  // the header is not trusted: V must match what the file actually holds before anything is allocated
+    const long here = std::ftell(f);
+    ok = here >= 0 && std::fseek(f, 0, SEEK_END) == 0;
+    const long end = ok ? std::ftell(f) : -1;
+    ok = ok && end >= here && (uint64_t)(end - here) == V * 36ull && std::fseek(f, here, SEEK_SET) == 0;
   }
+  std::vector<unsigned long long> k; std::vector<int> c; std::vector<long long> su;
+  try {
+    if (ok && V) {
+      k.resize(V); c.resize(V); su.resize(3 * V);
+      ok = std::fread(k.data(), 8, V, f) == V && std::fread(c.data(), 4, V, f) == V && std::fread(su.data(), 8, 3 * V, f) == 3 * V;
+    }
+  } catch (...) { ok = false; }
   std::fclose(f);
+  for (uint64_t i = 0; ok && i < V; ++i) ok = c[i] > 0 && k[i] != MAP_EMPTY && (i == 0 || k[i] > k[i - 1]);  // sorted, unique, real voxels
   if (!ok) return GM_ERR_INVALID_ARG;
   gm_map* m = nullptr;
   gm_status s = gm_map_create(leaf, std::max<size_t>(std::max<size_t>(min_capacity_voxels, (size_t)V), 1), &m);

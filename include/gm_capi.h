@@ -359,6 +359,20 @@ GM_API void gm_markers_normals(const float* centroids_xyzw, const float* nn_norm
 /* same with the arrow-end switch of gm_params.arrow_mode (0 = reference quirk B.4, 1 = end = start + normal) */
 GM_API void gm_markers_normals_mode(const float* centroids_xyzw, const float* nn_normal8, int32_t V, int32_t arrow_mode, gm_arrow* out);
 
+/* ---- on-disk store of the per-scan compressed primitives (builder-defined: the reference keeps nothing between
+ * callbacks, src/geometric_mapping.cpp:48-125).  Append-only file of the GMC1 blobs of gm_download_compressed, one record per
+ * scan with its id, stamp and pose [R|t] (row-major 3x4, NULL = identity), each protected by a CRC-32; the index is rebuilt
+ * when the file is opened and a torn last record is dropped.  Host-side I/O only. */
+typedef struct gm_store gm_store;
+GM_API gm_status gm_store_open(const char* path, int32_t create_if_missing, gm_store** out);
+GM_API void gm_store_close(gm_store* store);
+GM_API gm_status gm_store_append(gm_store* store, gm_ctx* ctx /* after gm_compress */, uint64_t scan_id, uint64_t stamp_ns, const float* pose34);
+GM_API gm_status gm_store_append_blob(gm_store* store, uint64_t scan_id, uint64_t stamp_ns, const float* pose34, const void* blob, size_t bytes);
+GM_API int64_t gm_store_count(const gm_store* store);
+GM_API gm_status gm_store_info(const gm_store* store, int64_t index, uint64_t* scan_id, uint64_t* stamp_ns, float* pose34, uint64_t* blob_bytes);
+/* buf = NULL queries the size */
+GM_API gm_status gm_store_read(gm_store* store, int64_t index, void* buf, size_t capacity, size_t* bytes);
+
 /* ---- ROS-free encoders of the published messages: the byte payloads a ROS 1 publisher would put on the
  * wire for what cloud_cb publishes (src/geometric_mapping.cpp:100-117), so a transport that is not roscpp can ship them
  * and a subscriber deserialises them as the stock message types.

@@ -96,3 +96,36 @@ def test_marker_arrays_carry_the_reference_arrow_payloads():
     assert len(ms) == 2 and ms[1]["points"] == [(4.0, 5.0, 6.0), (0.0, 1.0, 0.0)] and ms[0]["ns"] == "normals"
     assert np.allclose(ms[0]["scale"], [0.025, 0.075, 0.0625]) and list(ms[0]["rgba"]) == [0.0, 0.0, 1.0, 1.0]
     assert len(b) == capi._lib().gm_marker_array_size(2, b"/velodyne", b"normals")
+
+
+def test_primitive_store_appends_reopens_and_drops_a_torn_record(tmp_path):
+    """gm_store_*: append-only file of per-scan GMC1 blobs; the index is rebuilt on open and a torn tail is ignored."""
+    import os
+
+    path = str(tmp_path / "scans.gms")
+    blobs = [bytes([i]) * (100 + 37 * i) for i in range(5)] + [b""]
+    with capi.PrimitiveStore(path) as st:
+        for i, b in enumerate(blobs):
+            st.append_blob(b, scan_id=1000 + i, stamp_ns=10**9 * i, pose34=None if i % 2 else np.arange(12, dtype=np.float32))
+        assert len(st) == 6
+    with capi.PrimitiveStore(path, create=False) as st:
+        assert len(st) == 6
+        for i, b in enumerate(blobs):
+            info = st.info(i)
+            assert st.read(i) == b and info["scan_id"] == 1000 + i and info["stamp_ns"] == 10**9 * i and info["bytes"] == len(b)
+            want = np.eye(3, 4, dtype=np.float32) if i % 2 else np.arange(12, dtype=np.float32).reshape(3, 4)
+            assert np.array_equal(info["pose"], want)
+    size = os.path.getsize(path)
+    with open(path, "r+b") as f:          # tear the last two records: truncate inside record 4
+        f.truncate(size - 150)
+    with capi.PrimitiveStore(path, create=False) as st:
+        assert len(st) == 4 and st.read(3) == blobs[3]
+        st.append_blob(b"after the crash", scan_id=7)
+        assert len(st) == 5
+    with capi.PrimitiveStore(path, create=False) as st:
+        assert len(st) == 5 and st.read(4) == b"after the crash" and st.info(4)["scan_id"] == 7
+    with open(path, "r+b") as f:          # a flipped byte inside a blob fails the CRC: that record and what follows are dropped
+        f.seek(8 + 76 + 10)
+        f.write(b"\xff")
+    with capi.PrimitiveStore(path, create=False) as st:
+        assert len(st) == 0

@@ -1381,3 +1381,26 @@ def test_cpp_host_shim_keeps_the_quirk_switches_of_the_parameters():
             ctx.process_scan(None, None)
             assert np.allclose(vals[wm], ctx.frame()["vals"], rtol=1e-5)
     assert not np.allclose(vals[0], vals[1], rtol=1e-3)   # the two weight laws really differ
+
+
+def test_primitive_store_persists_the_compressed_scans(tmp_path):
+    """the per-scan GMC1 blobs go to an append-only file and come back byte for byte after a reopen."""
+    path = str(tmp_path / "run.gms")
+    blobs = []
+    with _ctx(60_000, neighborRadius=0.12) as ctx, capi.PrimitiveStore(path) as st:
+        for f in range(3):
+            pts = synth.curved_tunnel(60_000, seed=80 + f, advance=1.0 * f)
+            ctx.upload_scan(pts)
+            ctx.crop()
+            ctx.normals()
+            nv = ctx.counts().n_valid
+            ctx.upload_scan(pts)
+            ctx.process_scan(synth.sample_indices(nv, 128, 3, seed=3), synth.sample_indices(nv, 128, 2, seed=4))
+            ctx.compress()
+            blobs.append(ctx.download_compressed())
+            st.append(ctx, scan_id=f, stamp_ns=100 * f, pose34=_pose(0.1 * f, [1.0 * f, 0, 0]))
+    with capi.PrimitiveStore(path, create=False) as st:
+        assert len(st) == 3
+        for f in range(3):
+            assert st.read(f) == blobs[f] and st.info(f)["scan_id"] == f
+            assert np.allclose(st.info(f)["pose"], np.asarray(_pose(0.1 * f, [1.0 * f, 0, 0]), np.float32).reshape(3, 4))

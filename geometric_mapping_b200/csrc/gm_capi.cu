@@ -161,7 +161,7 @@ struct gm_ctx {
   // CUDA-graph replay of gm_process_scan: the launch sequence of one scan depends only on (bucketed size, hypothesis
   // counts, parameters / modes), never on per-scan host values (tile epochs, barrier parities and the scan pointer
   // live in device memory), so it is captured once per key and replayed with ONE cudaGraphLaunch
-  struct ScanGraph { size_t n_grid; int Hp, Hc; unsigned long long gen; int uses; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
+  struct ScanGraph { int kind; size_t n_grid; int Hp, Hc; unsigned long long gen; int uses; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
   std::vector<ScanGraph> graphs;
   unsigned long long graph_gen = 0;   // bumped by every setter that changes what a scan launches
   unsigned long long graph_clock = 0;
@@ -173,6 +173,7 @@ struct gm_ctx {
   struct gm_comm* comm = nullptr;
   bool sharded = false;
   double* d_frame_sums = nullptr;  // [8] the 6 scatter sums of the last gm_local_frame, kept for gm_allreduce_frame
+  double *d_gn_partials = nullptr, *d_gn_first = nullptr;  // cylinder refit: per-tile partial sums / totals of the first Gauss-Newton step
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -454,7 +455,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
   ctx->rs_hist_words = (size_t)div_up((long long)N, RS_BLOCK * 4) * 256;  // sized for the smaller tile
   A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256);
-  A(d_st, 1); A(d_ctl, 3); A(d_frame_sums, 8);
+  A(d_st, 1); A(d_ctl, 3); A(d_frame_sums, 8); A(d_gn_partials, ((size_t)div_up((long long)N, CPL_TILE) + 2) * GN_NV); A(d_gn_first, GN_NV);
   A(d_partials, 3 * kPartialsRegion);  // 3 regions: frame | plane refit | cylinder GN (may run concurrently)
   A(d_frame, 1);
   A(d_samples[0], 3 * H); A(d_samples[1], 2 * H);
@@ -506,7 +507,7 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
-                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_partials, ctx->d_frame,
+                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_gn_partials, ctx->d_gn_first, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
                   ctx->d_res_vs, ctx->d_comp, ctx->d_res_pts, ctx->d_res_centroid, ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start,
@@ -1046,7 +1047,8 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
               ctx->d_partials + 1 * kPartialsRegion, ctx->d_counters + 1);
   } else {
     GM_LAUNCH(ctx, k_cyl_inlier_compact, std::max(1, div_up((long long)ctx->n_grid, CPL_TILE)), CP_BLOCK, ctx->d_cloud_c, n_ptr,
-              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64_b, ctx->d_ctl + 1, &ctx->d_st->error);
+              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64_b, ctx->d_ctl + 1, &ctx->d_st->error,
+              ctx->d_gn_partials, ctx->d_counters + 14, ctx->d_gn_first);
     // all Gauss-Newton passes in one cooperative launch (grid barrier between passes)
     {
       const float4* inl = ctx->d_inl;
@@ -1054,7 +1056,8 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
       double* partials = ctx->d_partials + 2 * kPartialsRegion;
       unsigned* bars = ctx->d_counters + 5;  // counters [5],[6]: the two barrier counters, [7]: which one the next launch uses
       int* err = &ctx->d_st->error;
-      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bars, (void*)&err};
+      const double* first = ctx->d_gn_first;
+      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bars, (void*)&err, (void*)&first};
       GM_CUDA(cudaLaunchCooperativeKernel((const void*)k_cyl_gn_all, dim3(ctx->gn_blocks), dim3(RF_BLOCK), args, 0, ctx->stream));
       ++ctx->launches;
     }
@@ -1248,17 +1251,15 @@ static void drop_graph(gm_ctx::ScanGraph& g) {
   g.exec = nullptr;
 }
 
-extern "C" {
-
-gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
-  if (!ctx || Hp < 0 || Hc < 0 || (Hp > 0 && !plane_samples_host) || (Hc > 0 && !cyl_samples_host)) return GM_ERR_INVALID_ARG;
-  if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
-  if (Hp > ctx->hcap || Hc > ctx->hcap) { ctx->err = "H larger than max_hypotheses"; return GM_ERR_CAPACITY; }
-  const bool graphable = ctx->graph_mode == 1 && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;
-  if (!graphable) return process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
+// Run `body` (a fixed sequence of launches on the ctx streams) as a CUDA graph keyed by (kind, bucketed size, Hp, Hc,
+// parameter generation): the first call of a key runs `body` as plain launches (buffers that grow on demand are allocated
+// there, outside any capture), the second captures it (nothing executes during capture) and launches the graph, every
+// later one is ONE cudaGraphLaunch.  `stage` copies the per-call host inputs (sample indices) before the graph runs.
+template <class Stage, class Body>
+static gm_status run_graphed(gm_ctx* ctx, int kind, int Hp, int Hc, Stage&& stage, Body&& body) {
   gm_ctx::ScanGraph* g = nullptr;
   for (auto& e : ctx->graphs)
-    if (e.n_grid == ctx->n_grid && e.Hp == Hp && e.Hc == Hc && e.gen == ctx->graph_gen) { g = &e; break; }
+    if (e.kind == kind && e.n_grid == ctx->n_grid && e.Hp == Hp && e.Hc == Hc && e.gen == ctx->graph_gen) { g = &e; break; }
   if (!g) {
     if (ctx->graphs.size() >= 8) {  // evict the least recently used entry
       size_t v = 0;
@@ -1266,24 +1267,21 @@ gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_
       drop_graph(ctx->graphs[v]);
       ctx->graphs.erase(ctx->graphs.begin() + (long)v);
     }
-    ctx->graphs.push_back(gm_ctx::ScanGraph{ctx->n_grid, Hp, Hc, ctx->graph_gen, 0, nullptr, 0, 0});
+    ctx->graphs.push_back(gm_ctx::ScanGraph{kind, ctx->n_grid, Hp, Hc, ctx->graph_gen, 0, nullptr, 0, 0});
     g = &ctx->graphs.back();
   }
   g->stamp = ++ctx->graph_clock;
   ++g->uses;
-  // first scan of a kind: plain launches (buffers that grow on demand are allocated here, outside any capture)
-  if (!g->exec && g->uses == 1) return process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
-  gm_status s;
-  if (Hp > 0 && (s = stage_samples(ctx, 0, plane_samples_host, 0, Hp, 3)) != GM_OK) return s;
-  if (Hc > 0 && (s = stage_samples(ctx, 1, cyl_samples_host, 0, Hc, 2)) != GM_OK) return s;
+  if (!g->exec && g->uses == 1) return body();
+  gm_status s = stage();
+  if (s != GM_OK) return s;
   if (!g->exec) {
-    // second scan of a kind: capture the launch sequence (nothing executes during capture), then launch the graph
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
       const long long l0 = ctx->launches;
       ctx->samples_staged = true;
-      s = process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
+      s = body();
       ctx->samples_staged = false;
       g->launches = ctx->launches - l0;
       e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -1297,7 +1295,7 @@ gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_
       ctx->graph_mode = 0;
       g->exec = nullptr;
       ctx->samples_staged = true;  // already staged above
-      s = process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc);
+      s = body();
       ctx->samples_staged = false;
       return s;
     }
@@ -1307,8 +1305,27 @@ gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_
   }
   GM_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
   ++ctx->graph_replays;
-  mark_processed(ctx, Hp, Hc);
   return GM_OK;
+}
+
+extern "C" {
+
+gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_t Hp, const int32_t* cyl_samples_host, int32_t Hc) {
+  if (!ctx || Hp < 0 || Hc < 0 || (Hp > 0 && !plane_samples_host) || (Hc > 0 && !cyl_samples_host)) return GM_ERR_INVALID_ARG;
+  if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
+  if (Hp > ctx->hcap || Hc > ctx->hcap) { ctx->err = "H larger than max_hypotheses"; return GM_ERR_CAPACITY; }
+  auto body = [&] { return process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc); };
+  const bool graphable = ctx->graph_mode == 1 && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;
+  if (!graphable) return body();
+  auto stage = [&]() -> gm_status {
+    gm_status s;
+    if (Hp > 0 && (s = stage_samples(ctx, 0, plane_samples_host, 0, Hp, 3)) != GM_OK) return s;
+    if (Hc > 0 && (s = stage_samples(ctx, 1, cyl_samples_host, 0, Hc, 2)) != GM_OK) return s;
+    return GM_OK;
+  };
+  gm_status s = run_graphed(ctx, 0, Hp, Hc, stage, body);
+  if (s == GM_OK) mark_processed(ctx, Hp, Hc);
+  return s;
 }
 
 gm_status gm_set_graph_mode(gm_ctx* ctx, int32_t mode) {
@@ -2017,8 +2034,6 @@ gm_status gm_ransac_sharded(gm_ctx* ctx, const int32_t* plane_samples_host, int3
   auto range = [&](int H, int& b, int& e) { const int per = (H + W - 1) / W; b = std::min(R * per, H); e = std::min((R + 1) * per, H); };
   int pb, pe, cb, ce;
   range(Hp, pb, pe); range(Hc, cb, ce);
-  gm_status s;
-  ctx->sharded = true;
   auto recv = [&](int kind, int H) -> gm_status {
     GM_LAUNCH(ctx, k_comm_recv_model, 1, 32, ctx->comm->h_dev, kind, H, ctx->d_key + kind, ctx->d_plane_coef, ctx->d_model7, ctx->d_test12,
               ctx->d_counts[kind], &ctx->d_st->error);
@@ -2035,17 +2050,31 @@ gm_status gm_ransac_sharded(gm_ctx* ctx, const int32_t* plane_samples_host, int3
     if (r == GM_OK) r = recv(1, Hc);
     return r != GM_OK ? r : gm_ransac_select(ctx, GM_MODEL_CYLINDER);
   };
-  if (ctx->concurrent && !ctx->profiling) {
-    cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);
-    if (e != cudaSuccess) { ctx->sharded = false; ctx->err = cudaGetErrorString(e); return GM_ERR_CUDA; }
-    s = run_branch(ctx, 1, plane);
-    if (s == GM_OK) s = cylinder();
-    if (s == GM_OK && cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0) != cudaSuccess) s = GM_ERR_CUDA;
-  } else {
-    s = plane();
-    if (s == GM_OK) s = cylinder();
-  }
-  ctx->sharded = false;
+  auto body = [&]() -> gm_status {
+    gm_status s;
+    ctx->sharded = true;
+    if (ctx->concurrent && !ctx->profiling) {
+      cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);
+      if (e != cudaSuccess) { ctx->sharded = false; ctx->err = cudaGetErrorString(e); return GM_ERR_CUDA; }
+      s = run_branch(ctx, 1, plane);
+      if (s == GM_OK) s = cylinder();
+      if (s == GM_OK && cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0) != cudaSuccess) s = GM_ERR_CUDA;
+    } else {
+      s = plane();
+      if (s == GM_OK) s = cylinder();
+    }
+    ctx->sharded = false;
+    return s;
+  };
+  const bool graphable = ctx->graph_mode == 1 && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;
+  if (!graphable) return body();
+  auto stage = [&]() -> gm_status {
+    gm_status s = stage_samples(ctx, 0, plane_samples_host, pb, pe, 3);
+    return s != GM_OK ? s : stage_samples(ctx, 1, cyl_samples_host, cb, ce, 2);
+  };
+  // (world, rank) are part of what is launched: the comm is attached with gm_set_comm, which starts a new graph generation
+  gm_status s = run_graphed(ctx, 1, Hp, Hc, stage, body);
+  if (s == GM_OK) for (int k = 0; k < 2; ++k) { ctx->have_ransac[k] = true; ctx->have_model[k] = true; ctx->ransac_H[k] = k == 0 ? Hp : Hc; }
   return s;
 }
 

@@ -705,43 +705,86 @@ __device__ __forceinline__ void d_perp_basis_d(const double dir[3], double u[3],
   w[0] = dir[1] * u[2] - dir[2] * u[1]; w[1] = dir[2] * u[0] - dir[0] * u[2]; w[2] = dir[0] * u[1] - dir[1] * u[0];
 }
 
-// The refit set is FIXED (inliers of the winning hypothesis), so it is compacted once (stable
-// look-back compaction) and the Gauss-Newton passes run over the dense array.
-__global__ void __launch_bounds__(CP_BLOCK, 4)
+constexpr int GN_NV = 22;  // J^T J (15) | J^T r (5) | count | sum r^2
+
+// Gauss-Newton terms of one inlier at the iterate (q, dir, r) with (u, w) the perpendicular basis of dir
+__device__ __forceinline__ void d_gn_accumulate(const float4 p, const double q0, const double q1, const double q2, const double* dir,
+                                                const double* u, const double* w, const double r, double (&s)[GN_NV]) {
+  s[20] += 1.0;
+  const double vx = (double)p.x - q0, vy = (double)p.y - q1, vz = (double)p.z - q2;
+  const double A = u[0] * vx + u[1] * vy + u[2] * vz;
+  const double B = w[0] * vx + w[1] * vy + w[2] * vz;
+  const double tt = dir[0] * vx + dir[1] * vy + dir[2] * vz;
+  const double dist = sqrt(A * A + B * B);
+  if (!(dist > 1e-12)) return;
+  const double res = dist - r;
+  s[21] += res * res;
+  const double J[5] = {-A / dist, -B / dist, -A * tt / dist, -B * tt / dist, -1.0};
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+#pragma unroll
+    for (int b = a; b < 5; ++b) s[idx++] += J[a] * J[b];
+  }
+#pragma unroll
+  for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
+}
+
+// The refit set is FIXED (inliers of the winning hypothesis), so it is compacted once (stable look-back compaction) and
+// the Gauss-Newton passes run over the dense array.  The kernel that finds the inliers also accumulates the sums of
+// the FIRST Gauss-Newton step (at the hypothesis itself): per-block partials, reduced in tile order by the last block to
+// finish -> `first_sums`.  k_cyl_gn_all starts from them, so the first update costs no pass over the points.
+__global__ void __launch_bounds__(CP_BLOCK, 2)
 k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const unsigned long long* __restrict__ key, int H,
                      const float* __restrict__ model7, const float* __restrict__ test12, ModelState* ms,
-                     float4* __restrict__ inl, unsigned long long* state, TileCtl* ctl, int* err) {
+                     float4* __restrict__ inl, unsigned long long* state, TileCtl* ctl, int* err,
+                     double* __restrict__ partials /* grid x GN_NV */, unsigned* ticket, double* __restrict__ first_sums /* GN_NV */) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
+  __shared__ double s_red[GN_NV * (CP_BLOCK / 32)];
+  __shared__ double s_fin[GN_NV];
   const int n = *n_ptr;
   unsigned epoch;
   const int tile = tile_begin(ctl, epoch), base = tile * CPL_TILE;
+  double s[GN_NV];
+#pragma unroll
+  for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
   if (base >= n) {
     // empty cloud: tile 0 still has to publish the (empty) model state
     if (tile == 0 && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = 0; }
     tile_end(ctl);
-    return;
-  }
-  // every block decodes the winner itself (k_select folded in)
-  const unsigned long long kk = *key;
-  const int best_count = (int)(unsigned)(kk >> 32) - 1;
-  const int best_id = (int)(0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull));
-  const bool have = best_count >= 0 && best_id >= 0 && best_id < H;
-  const CylTest t = d_load_cyl_test(test12 + (size_t)(have ? best_id : 0) * 12);
-  bool f[CPL_IPT];
-  float4 p[CPL_IPT];
+  } else {
+    // every block decodes the winner itself (k_select folded in)
+    const unsigned long long kk = *key;
+    const int best_count = (int)(unsigned)(kk >> 32) - 1;
+    const int best_id = (int)(0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull));
+    const bool have = best_count >= 0 && best_id >= 0 && best_id < H;
+    const int hid = have ? best_id : 0;
+    const CylTest t = d_load_cyl_test(test12 + (size_t)hid * 12);
+    const float* m7 = model7 + (size_t)hid * 7;
+    const double q0 = m7[0], q1 = m7[1], q2 = m7[2], r = m7[6];
+    double dir[3] = {m7[3], m7[4], m7[5]}, u[3], w[3];
+    if (have) d_perp_basis_d(dir, u, w);
+    bool f[CPL_IPT];
+    float4 p[CPL_IPT];
 #pragma unroll
-  for (int j = 0; j < CPL_IPT; ++j) {
-    int i = base + j * CP_BLOCK + threadIdx.x;
-    f[j] = false;
-    if (i < n) { p[j] = pts[i]; f[j] = have && d_cyl_inlier(t, p[j]); }
-  }
-  unsigned ranks[CPL_IPT], total;
-  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, err, sm);
+    for (int j = 0; j < CPL_IPT; ++j) {
+      int i = base + j * CP_BLOCK + threadIdx.x;
+      f[j] = false;
+      if (i < n) { p[j] = pts[i]; f[j] = have && d_cyl_inlier(t, p[j]); }
+    }
+    unsigned ranks[CPL_IPT], total;
+    tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, err, sm);
 #pragma unroll
-  for (int j = 0; j < CPL_IPT; ++j)
-    if (f[j]) inl[ranks[j]] = p[j];
-  if (base + CPL_TILE >= n && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = (int)total; }
-  tile_end(ctl);
+    for (int j = 0; j < CPL_IPT; ++j)
+      if (f[j]) { inl[ranks[j]] = p[j]; d_gn_accumulate(p[j], q0, q1, q2, dir, u, w, r, s); }
+    if (base + CPL_TILE >= n && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = (int)total; }
+    tile_end(ctl);
+  }
+  // tiles are ticket numbers: tile t's partial goes to row t, so the reduction order does not depend on scheduling
+  block_sum_store<GN_NV, CP_BLOCK>(s, s_red, partials + (size_t)tile * GN_NV);
+  if (!d_last_block(ticket, gridDim.x)) return;
+  d_reduce_partials<GN_NV>(partials, gridDim.x, s_fin);
+  if (threadIdx.x < GN_NV) first_sums[threadIdx.x] = s_fin[threadIdx.x];
 }
 
 __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
@@ -767,14 +810,15 @@ __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
   return true;
 }
 
-// All Gauss-Newton passes of the cylinder refit in ONE cooperative launch (grid <= co-resident
-// capacity, guaranteed by cudaLaunchCooperativeKernel).  Per pass every block reduces its share of
-// the compacted inliers to 22 doubles (J^T J: 15, J^T r: 5, count, sum r^2), publishes them, crosses
-// a grid barrier, and then EVERY block sums the per-block partials in block order and solves the
-// same 5x5 system (redundant but deterministic: no second barrier, no broadcast).  The last pass
-// (update = 0) publishes count / rms / float coefficients / the refined inlier test.
-constexpr int GN_NV = 22;
-
+// All Gauss-Newton passes of the cylinder refit in ONE cooperative launch (grid <= co-resident capacity, guaranteed by
+// cudaLaunchCooperativeKernel).  The sums of the first step arrive from k_cyl_inlier_compact (`first_sums`), so the
+// first update is free.  Per further pass every block reduces its share of the compacted inliers to 22 doubles
+// (J^T J: 15, J^T r: 5, count, sum r^2), publishes them, crosses a grid barrier, and then EVERY block sums the per-block
+// partials in block order and solves the same 5x5 system (redundant but deterministic: no second barrier, no broadcast).
+// The loop ends when the step is below 1e-4 (m / rad; Gauss-Newton converges quadratically here, the next step would be
+// ~1e-8: same rule in the oracle) -- the RMS at the new iterate then follows from the sums already at hand through the
+// Gauss-Newton model, sum (r + J x)^2 = sum r^2 + 2 x.J^T r + x^T J^T J x, exact to O(|x|^2) -- or when `iters` updates were
+// made, in which case the sums of one more pass give the RMS.  Typical scan: ONE pass over the inliers.
 __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target, int* err) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -790,33 +834,71 @@ __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target,
 
 __global__ void __launch_bounds__(RF_BLOCK)
 k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float tau, double* __restrict__ partials /* 2 x grid x 22 */,
-             unsigned* bars /* [0],[1] barrier counters used alternately, [2] which one this launch uses */, int* err) {
+             unsigned* bars /* [0],[1] barrier counters used alternately, [2] which one this launch uses */, int* err,
+             const double* __restrict__ first_sums) {
   __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
   __shared__ double fin[GN_NV];
-  __shared__ double it_q[3], it_dir[3], it_r;
-  __shared__ int s_converged;
+  __shared__ double it_q[3], it_dir[3], it_r, s_rms2;
+  __shared__ int s_state;  // 0 = another pass is needed, 1 = finished
   // two barrier counters used alternately by consecutive launches: this launch counts on
   // barrier_count from 0 and clears the other one for the next launch (the number of passes is
   // data dependent, so a cumulative target cannot be pre-computed).  Which one is whose lives in device
-  // memory too (bars[2], toggled by block 0 after the last barrier, i.e. after every block has read it),
-  // so that consecutive launches need no host-side argument: the launch is replayable from a CUDA graph.
+  // memory too (bars[2], toggled by block 0 at the end of the launch), so that consecutive launches need no
+  // host-side argument: the launch is replayable from a CUDA graph.
   const unsigned par = *(volatile unsigned*)&bars[2] & 1u;
   unsigned* barrier_count = bars + par;
   unsigned* barrier_next = bars + (par ^ 1u);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *barrier_next = 0u;
   const bool have = ms->best_id >= 0;
   const int n = have ? ms->n_inl : 0;
   const int nb = gridDim.x;
   if (threadIdx.x == 0) {
     for (int k = 0; k < 3; ++k) { it_q[k] = ms->q[k]; it_dir[k] = ms->dir[k]; }
     it_r = ms->r;
-    s_converged = 0;
+    s_state = 0; s_rms2 = 0.0;
   }
+  if (threadIdx.x < GN_NV) fin[threadIdx.x] = first_sums[threadIdx.x];
   __syncthreads();
-  bool frozen = false;  // block-uniform: singular system or too few inliers -> iterate no longer moves
-  int pass = 0;         // barriers crossed so far in this launch
-  for (int it = 0; it <= iters; ++it, ++pass) {
-    const int update = it < iters;
+  long long cnt = 0;
+  int pass = 0;  // barriers crossed so far in this launch
+  for (int it = 0;; ++it) {
+    // fin = the sums at the current iterate; every block takes the same decisions from the same numbers
+    if (threadIdx.x == 0) {
+      cnt = (long long)(fin[20] + 0.5);
+      bool done = true;
+      if (cnt > 5) {
+        s_rms2 = fin[21] / (double)cnt;
+        if (it < iters) {
+          double JTJ[5][5], rhs[5], x[5];
+          int idx = 0;
+          for (int a = 0; a < 5; ++a) for (int b = a; b < 5; ++b) { JTJ[a][b] = fin[idx]; JTJ[b][a] = fin[idx]; ++idx; }
+          for (int a = 0; a < 5; ++a) rhs[a] = -fin[15 + a];
+          if (d_solve5(JTJ, rhs, x)) {
+            double dir[3] = {it_dir[0], it_dir[1], it_dir[2]}, u[3], w[3];
+            d_perp_basis_d(dir, u, w);
+            for (int k = 0; k < 3; ++k) it_q[k] += x[0] * u[k] + x[1] * w[k];
+            for (int k = 0; k < 3; ++k) dir[k] += x[2] * u[k] + x[3] * w[k];
+            const double dl = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+            for (int k = 0; k < 3; ++k) it_dir[k] = dir[k] / dl;
+            it_r += x[4];
+            if (x[0] * x[0] + x[1] * x[1] + x[4] * x[4] < 1e-8 && x[2] * x[2] + x[3] * x[3] < 1e-8) {
+              // converged: RMS at the new iterate from the Gauss-Newton model of the residuals
+              double lin = 0.0, quad = 0.0;
+              idx = 0;
+              for (int a = 0; a < 5; ++a) {
+                lin += x[a] * fin[15 + a];
+                for (int b = a; b < 5; ++b) { quad += (a == b ? 1.0 : 2.0) * x[a] * x[b] * fin[idx]; ++idx; }
+              }
+              s_rms2 = fmax((fin[21] + 2.0 * lin + quad) / (double)cnt, 0.0);
+            } else {
+              done = false;  // sums at the new iterate are needed (for the next step, or for the RMS after the last one)
+            }
+          }
+        }
+      }
+      s_state = done ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_state) break;
     double s[GN_NV];
 #pragma unroll
     for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
@@ -824,55 +906,21 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
       const double q0 = it_q[0], q1 = it_q[1], q2 = it_q[2], r = it_r;
       double dir[3] = {it_dir[0], it_dir[1], it_dir[2]}, u[3], w[3];
       d_perp_basis_d(dir, u, w);
-      for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += nb * RF_BLOCK) {
-        float4 p = inl[i];
-        s[20] += 1.0;
-        double vx = (double)p.x - q0, vy = (double)p.y - q1, vz = (double)p.z - q2;
-        double A = u[0] * vx + u[1] * vy + u[2] * vz;
-        double B = w[0] * vx + w[1] * vy + w[2] * vz;
-        double tt = dir[0] * vx + dir[1] * vy + dir[2] * vz;
-        double dist = sqrt(A * A + B * B);
-        if (!(dist > 1e-12)) continue;
-        double res = dist - r;
-        s[21] += res * res;
-        double J[5] = {-A / dist, -B / dist, -A * tt / dist, -B * tt / dist, -1.0};
-        int idx = 0;
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-#pragma unroll
-          for (int b = a; b < 5; ++b) s[idx++] += J[a] * J[b];
-        }
-#pragma unroll
-        for (int a = 0; a < 5; ++a) s[15 + a] += J[a] * res;
-      }
+      for (int i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n; i += nb * RF_BLOCK) d_gn_accumulate(inl[i], q0, q1, q2, dir, u, w, r, s);
     }
     double* buf = partials + (size_t)(pass & 1) * nb * GN_NV;
     block_sum_store<GN_NV, RF_BLOCK>(s, sm, buf + (size_t)blockIdx.x * GN_NV);
-    d_grid_barrier(barrier_count, (unsigned)(pass + 1) * (unsigned)nb, err);
+    ++pass;
+    d_grid_barrier(barrier_count, (unsigned)pass * (unsigned)nb, err);
     d_reduce_partials<GN_NV>(buf, nb, fin);
-    const long long cnt = (long long)(fin[20] + 0.5);
-    if (cnt <= 5) frozen = true;  // model unchanged (same rule as the oracle)
-    if (threadIdx.x == 0 && have) {
-      if (blockIdx.x == 0) ms->refit_count = (int)cnt;
-      if (!frozen && update) {
-        double JTJ[5][5], rhs[5], x[5];
-        int idx = 0;
-        for (int a = 0; a < 5; ++a) for (int b = a; b < 5; ++b) { JTJ[a][b] = fin[idx]; JTJ[b][a] = fin[idx]; ++idx; }
-        for (int a = 0; a < 5; ++a) rhs[a] = -fin[15 + a];
-        if (d_solve5(JTJ, rhs, x)) {
-          double dir[3] = {it_dir[0], it_dir[1], it_dir[2]}, u[3], w[3];
-          d_perp_basis_d(dir, u, w);
-          for (int k = 0; k < 3; ++k) it_q[k] += x[0] * u[k] + x[1] * w[k];
-          for (int k = 0; k < 3; ++k) dir[k] += x[2] * u[k] + x[3] * w[k];
-          double dl = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-          for (int k = 0; k < 3; ++k) it_dir[k] = dir[k] / dl;
-          it_r += x[4];
-          // converged (same rule as the oracle): skip the remaining update passes
-          if (x[0] * x[0] + x[1] * x[1] + x[4] * x[4] < 1e-10 && x[2] * x[2] + x[3] * x[3] < 1e-10) s_converged = 1;
-        }
-      }
-      if (!update && blockIdx.x == 0 && cnt > 5) {
-        ms->rms = (float)sqrt(fin[21] / (double)cnt);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *barrier_next = 0u;
+    bars[2] = par ^ 1u;
+    if (have) {
+      ms->refit_count = (int)cnt;
+      if (cnt > 5) {
+        ms->rms = (float)sqrt(s_rms2);
         for (int k = 0; k < 3; ++k) { ms->q[k] = it_q[k]; ms->dir[k] = it_dir[k]; ms->coef[k] = (float)it_q[k]; ms->coef[3 + k] = (float)it_dir[k]; }
         ms->r = it_r;
         ms->coef[6] = (float)it_r;
@@ -880,11 +928,8 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
         if (d_cyl_test_params(ms->coef, tau, t12)) for (int k = 0; k < 12; ++k) ms->test_coef[k] = t12[k];
       }
     }
-    __syncthreads();
-    // every block computed the same step from the same partials, so this is grid-uniform
-    if (update && s_converged && it < iters - 1) it = iters - 1;
+    __threadfence();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { bars[2] = par ^ 1u; __threadfence(); }
 }
 
 // labels from the refined models: 1 = plane inlier, else 2 = cylinder inlier, else 0

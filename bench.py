@@ -245,13 +245,19 @@ def bind_to_gpu_numa_node(index: int):
     return None
 
 
-def load_traffic():
-    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the main kernels from the
-    committed ncu --set full capture (profiles/r01_traffic.json: {kernel: bytes, "_source": command})."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f)
+def load_traffic(points: int):
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the main kernels from the committed
+    `ncu --set full` captures (profiles/r02_traffic.json: {"1M": {kernel: bytes}, "10M": {...}, "_source": ...}).
+    Only the capture of the same workload size is used; none -> {} (traffic fields are then null)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        d = json.load(f)
+    if 0.7e6 <= points <= 1.5e6:
+        return d.get("1M", {})
+    if 0.7e7 <= points <= 1.5e7:
+        return d.get("10M", {})
     return {}
 
 
@@ -325,7 +331,13 @@ def main():
         hp = torch.from_numpy(pts).pin_memory()
         host_scans.append(hp)
         dev_scans.append(hp.to(dev, non_blocking=False))
-    ctx = capi.Context(params, max_points=n, max_hypotheses=max(4096, a.shard_hyp, a.shard_hyp_large))
+    def new_ctx(max_h):
+        cx = capi.Context(params, max_points=n, max_hypotheses=max_h)
+        if a.knn:
+            cx.set_knn(a.knn)
+        return cx
+
+    ctx = new_ctx(max(4096, a.shard_hyp, a.shard_hyp_large))
     ctx.set_stream(stream.cuda_stream)
 
     # sample indices need the compacted size of each scan: learn it once (untimed)
@@ -377,7 +389,7 @@ def main():
     # a stream of scans is processed.  Timed with CUDA events: e0 on the first context's stream before
     # the first step, e1 on a stream that has waited for every context's last step.
     NFLIGHT = max(1, int(os.environ.get("GM_BENCH_NFLIGHT", "3")))
-    tctx = [ctx] + [capi.Context(params, max_points=n, max_hypotheses=max(4096, a.shard_hyp)) for _ in range(NFLIGHT - 1)]
+    tctx = [ctx] + [new_ctx(max(4096, a.shard_hyp)) for _ in range(NFLIGHT - 1)]
     tstreams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NFLIGHT - 1)]
     for cx, st_ in zip(tctx[1:], tstreams[1:]):
         cx.set_stream(st_.cuda_stream)
@@ -407,6 +419,7 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = sum(cx.launch_count for cx in tctx)
+    graph_stats = ctx.graph_stats()
     clocks = sampler.stop()
     for cx in tctx:
         if cx.counts().device_error:
@@ -484,21 +497,32 @@ def main():
         cx.close()
 
     # ---- per-segment timing of the same steps (roofline) ------------------------------------------
-    ctx.profile_enable(True)
-    for i in range(a.steps):
-        step(i)
-    prof = ctx.profile_read()
-    seg_ms = {k: (v[0] / max(a.steps, 1)) for k, v in prof.items()}
-    # the same inlier counting with the brute-force FP32 kernels (no tile culling): the FP32-pipe roofline
-    ctx.set_count_mode(1)
+    # CUDA-event pairs inside the library around every stage (gm_profile_*: plain stream launches on one stream, so the
+    # segments add up; the timed legs above replay the graph on three streams).
+    def profile_steps(count, knn=0, voxel_mode=0, count_mode=0):
+        ctx.set_voxel_mode(voxel_mode)
+        ctx.set_count_mode(count_mode)
+        ctx.set_knn(knn)
+        for i in range(2):
+            step(i)
+        ctx.profile_enable(True)
+        for i in range(count):
+            step(i)
+        pr = ctx.profile_read()
+        ctx.profile_enable(False)
+        ctx.set_voxel_mode(0)
+        ctx.set_count_mode(0)
+        ctx.set_knn(a.knn)
+        return {k: (v[0] / max(count, 1)) for k, v in pr.items()}
+
     nb = max(4, min(a.steps, 20))
-    for i in range(nb):
-        step(i)
-    prof_b = ctx.profile_read()
-    ctx.set_count_mode(0)
-    ctx.profile_enable(False)
-    brute_ms = (prof_b["plane_count"][0] + prof_b["cyl_count"][0]) / nb
+    seg_ms = profile_steps(a.steps, knn=a.knn)
+    seg_brute = profile_steps(nb, knn=a.knn, count_mode=1)       # every point x hypothesis test executed: the FP32-pipe figure
+    seg_sortvox = profile_steps(nb, knn=a.knn, voxel_mode=1)     # sort-based VoxelGrid (keys -> radix sort -> heads -> centroids)
+    seg_knn = profile_steps(nb, knn=32) if not a.knn else None   # k-NN normals (k = 32) on the same scans
+    brute_ms = seg_brute["plane_count"] + seg_brute["cyl_count"]
     M = float(np.mean(n_valid))
+    Mc = float(c.n_cropped)
     V = float(c.n_voxels)
     hbm_peak, peak_src = load_peaks()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -507,12 +531,8 @@ def main():
     count_ms = seg_ms["plane_count"] + seg_ms["cyl_count"]
     count_flops = M * (Hp * 6.0 + Hc * 16.0)
     count_tflops = count_flops / (count_ms * 1e-3) / 1e12 if count_ms > 0 else 0.0
-    P = 3
-    vox_bytes = 16.0 * n + (68.0 + 16.0 * P) * M + 20.0 * V
-    vox_ms = seg_ms["crop"] + seg_ms["voxel_keys"] + seg_ms["voxel_sort"] + seg_ms["voxel_reduce"]
-    vox_gbs = vox_bytes / (vox_ms * 1e-3) / 1e9 if vox_ms > 0 else 0.0
-    traffic = load_traffic()
-    fp32_src = f"{sms} SMs x 128 lanes x 2 x {clk:.0f} MHz observed"
+    traffic = load_traffic(n)
+    fp32_src = f"{sms} SMs x 128 lanes x 2 x {clk:.0f} MHz observed ({clocks['samples']} NVML samples during the timed region)"
     cand_per_scan = float(np.mean([c_ for c_, _ in nbr_sum])) if nbr_sum else 150.0 * M
     nbr_per_scan = float(np.mean([n_ for _, n_ in nbr_sum])) if nbr_sum else 40.0 * M
     nrm_ms = seg_ms["normals"]
@@ -522,32 +542,76 @@ def main():
     nrm_flops = 8.0 * cand_per_scan + 15.0 * nbr_per_scan + 150.0 * M
     nrm_tflops = nrm_flops / (nrm_ms * 1e-3) / 1e12 if nrm_ms > 0 else 0.0
     brute_tflops = count_flops / (brute_ms * 1e-3) / 1e12 if brute_ms > 0 else 0.0
+
+    def gbs(nbytes, ms_):
+        return nbytes / (ms_ * 1e-3) / 1e9 if (ms_ and nbytes) else None
+
+    def tsum(*names):
+        vals = [traffic.get(k) for k in names]
+        return None if any(v is None for v in vals) else float(sum(vals))
+
+    # ---- HBM-bound families.  Two byte counts each: SURVEY 8(d)'s ALGORITHMIC bytes (what `achieved` / `frac` use) and the
+    # dram__bytes the same kernels move under `ncu --set full` on this workload size (`traffic`, with `achieved_on_traffic`):
+    # at 1M points the working set sits in the 126 MB L2, so the DRAM traffic is far below the algorithmic bytes and neither
+    # figure is an HBM-pipe utilisation -- the 10M-point line (bench.py --points 10000000 --radius 0.02) is the HBM-bound one.
+    key_bits_grid = 24 if n <= 2_000_000 else 32   # neighbour-grid cell key: 18 block bits + 6 at C1 (3 passes of 8 bits)
+    P_grid = (key_bits_grid + 7) // 8
+    sort_bytes = 20.0 * P_grid * Mc                 # per pass: histogram read 4 + (key,index) read 8 + write 8
+    sort_ms = seg_ms["grid_sort"]
+    sort_traffic = None if traffic.get("k_rs_upsweep<8>") is None else P_grid * (traffic["k_rs_upsweep<8>"] + traffic.get("k_rs_scan", 0.0) + traffic["k_rs_downsweep<8>"])
+    P_vox = 3
+    vox8d_bytes = 16.0 * n + (68.0 + 16.0 * P_vox) * M + 20.0 * V     # crop + keys + P-pass sort + heads + centroids
+    voxdense_ms = seg_ms["crop"] + seg_ms["voxel_keys"] + seg_ms["voxel_sort"] + seg_ms["voxel_reduce"]
+    voxsort_ms = seg_sortvox["crop"] + seg_sortvox["voxel_keys"] + seg_sortvox["voxel_sort"] + seg_sortvox["voxel_reduce"]
+    voxdense_traffic = tsum("k_crop", "k_voxel_accumulate_sorted", "k_voxel_dense_scan", "k_voxel_assign")
     families = {
         "normals": {"bound": "fp32", "achieved": nrm_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                     "frac": nrm_tflops / fp32_peak_tflops, "traffic": traffic.get("k_normals"), "ms_per_step": nrm_ms,
-                    "kernels": "k_normals",
+                    "kernels": "k_normals<0>",
                     "algorithmic": f"8 flop x {cand_per_scan:.0f} stencil candidates + 15 flop x {nbr_per_scan:.0f} neighbours + 150 flop x "
-                                   f"{M:.0f} points; the kernel is instruction-issue bound (ncu: 77 % of issue slots active, ~30 "
+                                   f"{M:.0f} points; the kernel is instruction-issue bound (ncu: ~73 % of issue slots active, ~30 "
                                    f"instructions per candidate of which 8 are these flops)",
                     "points_per_s": M / (nrm_ms * 1e-3) if nrm_ms > 0 else 0.0, "peak_source": fp32_src},
         "inlier_count": {"bound": "fp32", "achieved": count_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                         "frac": count_tflops / fp32_peak_tflops, "traffic": traffic.get("k_count_tiles"), "ms_per_step": count_ms,
+                         "frac": count_tflops / fp32_peak_tflops, "traffic": tsum("k_count_tiles<0>", "k_count_tiles<1>"), "ms_per_step": count_ms,
                          "kernels": "k_count_tiles<plane> + k_count_tiles<cylinder> (tile-culled: ~10 % of the point x hypothesis tests "
-                                    "are executed, the rest are proven non-inliers per 32-point tile; identical counts)",
+                                    "are executed, the rest are proven non-inliers per 32-point tile; identical counts) -- an equivalent "
+                                    "rate, NOT a pipe utilisation: see inlier_count_brute",
                          "algorithmic": f"{M:.0f} pts x ({Hp} x 6 + {Hc} x 16) flop", "peak_source": fp32_src},
         "inlier_count_brute": {"bound": "fp32", "achieved": brute_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                               "frac": brute_tflops / fp32_peak_tflops, "traffic": traffic.get("k_count_cyl"), "ms_per_step": brute_ms,
+                               "frac": brute_tflops / fp32_peak_tflops, "traffic": None, "ms_per_step": brute_ms,
                                "kernels": "k_count_plane<8> + k_count_cyl<4> (gm_set_count_mode(1): every test executed)",
                                "algorithmic": f"{M:.0f} pts x ({Hp} x 6 + {Hc} x 16) flop", "peak_source": fp32_src},
-        "voxel_sort": {"bound": "hbm", "achieved": vox_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": vox_gbs / hbm_peak,
-                       "traffic": traffic.get("voxel_stage"), "ms_per_step": vox_ms,
-                       "kernels": "k_crop + k_voxel_keys + radix sort + k_voxel_heads/centroids",
-                       "algorithmic": f"16N + (68+16P)M + 20V bytes, P={P}, working set L2-resident at 1M points",
-                       "peak_source": peak_src},
+        "radix_sort": {"bound": "hbm", "achieved": gbs(sort_bytes, sort_ms), "peak": hbm_peak, "unit": "GB/s",
+                       "frac": (gbs(sort_bytes, sort_ms) or 0.0) / hbm_peak, "traffic": sort_traffic,
+                       "achieved_on_traffic": gbs(sort_traffic, sort_ms), "ms_per_step": sort_ms,
+                       "kernels": f"{P_grid} x (k_rs_upsweep + k_rs_scan + k_rs_downsweep): the neighbour-grid sort of the cropped cloud",
+                       "algorithmic": f"20 B x {P_grid} passes x {Mc:.0f} keys", "peak_source": peak_src},
+        "voxel_dense": {"bound": "hbm", "achieved": gbs(vox8d_bytes, voxdense_ms), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (gbs(vox8d_bytes, voxdense_ms) or 0.0) / hbm_peak, "traffic": voxdense_traffic,
+                        "achieved_on_traffic": gbs(voxdense_traffic, voxdense_ms),
+                        "frac_on_traffic": None if voxdense_traffic is None else gbs(voxdense_traffic, voxdense_ms) / hbm_peak,
+                        "ms_per_step": voxdense_ms,
+                        "kernels": "k_crop + k_voxel_accumulate_sorted + k_voxel_dense_scan + k_voxel_assign (default: sort-free dense tables)",
+                        "algorithmic": f"SURVEY 8(d) sort-based count 16N + (68+16P)M + 20V = {vox8d_bytes / 1e6:.1f} MB with P={P_vox}: the work the "
+                                       f"stage REPLACES; this path itself moves far less, so `frac` is an equivalent rate and "
+                                       f"`frac_on_traffic` is the bandwidth actually drawn",
+                        "peak_source": peak_src},
+        "voxel_sort": {"bound": "hbm", "achieved": gbs(vox8d_bytes, voxsort_ms), "peak": hbm_peak, "unit": "GB/s",
+                       "frac": (gbs(vox8d_bytes, voxsort_ms) or 0.0) / hbm_peak, "traffic": None, "ms_per_step": voxsort_ms,
+                       "kernels": "k_crop + k_voxel_keys + radix sort + k_voxel_heads + k_voxel_centroids (gm_set_voxel_mode(1): the path the "
+                                  "SURVEY 8(d) byte count describes)",
+                       "algorithmic": f"16N + (68+16P)M + 20V = {vox8d_bytes / 1e6:.1f} MB, P={P_vox}", "peak_source": peak_src},
     }
-    dominant = max(("inlier_count", "voxel_sort", "normals"), key=lambda k: families[k]["ms_per_step"])
+    dominant = max(("inlier_count", "voxel_dense", "normals", "radix_sort"), key=lambda k: families[k]["ms_per_step"])
     roofline = dict(families[dominant])
     roofline["dominant_segment"] = dominant
+    knn_leg = None
+    if seg_knn is not None:
+        knn_leg = {"k": 32, "normals_ms": seg_knn["normals"], "points_per_s": M / (seg_knn["normals"] * 1e-3) if seg_knn["normals"] > 0 else 0.0,
+                   "scan_ms_single_stream": float(sum(seg_knn.values())),
+                   "note": "gm_set_knn(32): pcl::NormalEstimation::setKSearch(32) instead of setRadiusSearch; exact k-NN on the same grid, "
+                           "neighbours summed in FLANN's order (normals bit-identical to the oracle's); radius-mode normals_ms above"}
 
     # ---- end to end through the C-ABI with host buffers (NCTX contexts pipelined) --------------------
     # Per step: H2D of the scan from pinned memory as 12-byte xyz records (what a PointCloud2 of x,y,z float32 carries;
@@ -560,7 +624,7 @@ def main():
     VCAP = 1 << 17
     ectx, outs, keep = [], [], []
     for k in range(NCTX):
-        cx = capi.Context(params, max_points=n, max_hypotheses=4096)
+        cx = new_ctx(4096)
         ectx.append(cx)
         summ = torch.empty(C.sizeof(capi.gm_scan_summary), dtype=torch.uint8).pin_memory()
         cloud = torch.empty((n, 4), dtype=torch.float32).pin_memory()
@@ -810,6 +874,9 @@ def main():
             "roofline": roofline,
             "roofline_families": families,
             "segments_ms_per_step": seg_ms,
+            "knn32": knn_leg,
+            "graph": {"captures_ctx0": graph_stats[0], "replays_ctx0": graph_stats[1],
+                      "note": "gm_process_scan replays a captured CUDA graph (one cudaGraphLaunch per scan); gpu_launches counts the kernels inside"},
             "h4096": h4096,
             "frames_c3": frames_c3,
             "ransac": ransac,

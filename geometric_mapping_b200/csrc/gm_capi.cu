@@ -1089,17 +1089,16 @@ gm_status gm_axis_polyline(gm_ctx* ctx) {
   const WeightLaw shift = weight_law(ctx->prm);
   SegTimer seg_(ctx, SEG_POLYLINE);
   {
-    // 4 launches: range (+basis, +zeroing, +slice layout) and three accumulation passes, each with the
-    // per-slice step that consumes it folded into its last block
+    // 3 launches: range (+basis, +zeroing, +slice layout) and two accumulation passes (moments -> means + circle fit;
+    // residuals -> output), each with the per-slice step that consumes it folded into its last block
     int blocks = std::max(1, std::min(div_up((long long)std::max<size_t>(ctx->n_grid, 1), POLY_BLOCK), ctx->num_sms * 4));
     GM_LAUNCH(ctx, k_poly_range, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_labels, n_ptr, ctx->d_frame, ctx->d_poly, ctx->d_poly_acc,
               POLY_NACC * S, ctx->d_poly_part, ctx->d_counters + 8, ctx->prm.sliceLength, S);
+    const ModelState* cylm = ctx->have_model[1] ? ctx->d_model + 1 : nullptr;
     GM_LAUNCH(ctx, k_poly_pass<0>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift,
-              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 9);
-    GM_LAUNCH(ctx, k_poly_pass<1>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift,
-              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 10);
+              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 9, cylm);
     GM_LAUNCH(ctx, k_poly_pass<2>, blocks, POLY_BLOCK, ctx->d_cloud_c, ctx->d_normals_c, ctx->d_labels, n_ptr, ctx->d_poly, shift,
-              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 11);
+              ctx->d_poly_acc, ctx->d_slices, ctx->d_counters + 11, cylm);
   }
   GM_CHECK_LAUNCHES(ctx);
   ctx->have_poly = true;

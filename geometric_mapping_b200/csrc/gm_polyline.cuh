@@ -37,42 +37,6 @@ __device__ __forceinline__ long long d_to_fx(double v) { return __double2ll_rn(v
 __device__ __forceinline__ double d_from_fx(long long v) { return (double)v / POLY_FX; }
 
 // Per-slice epilogues, run by the last block of the pass that produced their inputs.
-__device__ __forceinline__ void d_poly_means(const PolyState* ps, long long* acc) {
-  double* aux = reinterpret_cast<double*>(acc);
-  for (int s = threadIdx.x; s < ps->S; s += blockDim.x) {
-    long long* a = acc + (size_t)s * POLY_NACC;
-    double n = (double)__ldcg(a + 0);
-    double ma = 0.0, mb = 0.0;
-    if (n > 0) { ma = d_from_fx(__ldcg(a + 1)) / n; mb = d_from_fx(__ldcg(a + 2)) / n; }
-    aux[(size_t)s * POLY_NACC + 16] = ma;
-    aux[(size_t)s * POLY_NACC + 17] = mb;
-  }
-}
-
-__device__ __forceinline__ void d_poly_fit(const PolyState* ps, long long* acc) {
-  double* aux = reinterpret_cast<double*>(acc);
-  for (int s = threadIdx.x; s < ps->S; s += blockDim.x) {
-    const long long* a = acc + (size_t)s * POLY_NACC;
-    double n = (double)__ldcg(a + 0);
-    double ca = 0.0, cb = 0.0, rad = 0.0, ok = 0.0;
-    if (n >= 3) {
-      double Saa = d_from_fx(__ldcg(a + 9)), Sab = d_from_fx(__ldcg(a + 10)), Sbb = d_from_fx(__ldcg(a + 11));
-      double Saz = d_from_fx(__ldcg(a + 12)), Sbz = d_from_fx(__ldcg(a + 13)), Sz = d_from_fx(__ldcg(a + 14));
-      double det = Saa * Sbb - Sab * Sab;
-      if (fabs(det) > 1e-300) {
-        double Ac = (Saz * Sbb - Sbz * Sab) / det, Bc = (Sbz * Saa - Saz * Sab) / det;
-        ca = 0.5 * Ac; cb = 0.5 * Bc;
-        rad = sqrt(Sz / n + ca * ca + cb * cb);
-        ok = 1.0;
-      }
-    }
-    aux[(size_t)s * POLY_NACC + 18] = ca;
-    aux[(size_t)s * POLY_NACC + 19] = cb;
-    aux[(size_t)s * POLY_NACC + 20] = rad;
-    aux[(size_t)s * POLY_NACC + 21] = ok;
-  }
-}
-
 __device__ __forceinline__ void d_poly_finish(const PolyState* ps, const long long* acc, gm_slice* out) {
   const double* aux = reinterpret_cast<const double*>(acc);
   for (int s = threadIdx.x; s < ps->S; s += blockDim.x) {
@@ -170,26 +134,70 @@ k_poly_range(const float4* __restrict__ pts, const unsigned char* __restrict__ l
   }
 }
 
-// Launches 2-4: one accumulation pass each, followed (in the last block to finish) by the
-// per-slice step that consumes it.
-// PASS 0: n, sum a, sum b, weighted normal scatter (slots 0..8)            -> slice means
-// PASS 1: centred second/third moments for the algebraic circle fit (9..14)  -> circle fit
-// PASS 2: squared residuals against the fitted circle (slot 15)              -> output slices
+// Means AND circle fit from ONE pass: the moments are taken about a fixed point near every slice's mean -- the axis of
+// the refined cylinder, (ca0, cb0) in the (u, w) plane -- and moved to the slice mean algebraically afterwards (offsets
+// of a few decimetres against a 2.5 m section: no cancellation to speak of, and the sums themselves are exact integers).
+__device__ __forceinline__ void d_poly_means_and_fit(const PolyState* ps, long long* acc, double ca0, double cb0) {
+  double* aux = reinterpret_cast<double*>(acc);
+  for (int s = threadIdx.x; s < ps->S; s += blockDim.x) {
+    const long long* a = acc + (size_t)s * POLY_NACC;
+    const double n = (double)__ldcg(a + 0);
+    double ma = 0.0, mb = 0.0, ca = 0.0, cb = 0.0, rad = 0.0, ok = 0.0;
+    if (n > 0) {
+      const double Sa = d_from_fx(__ldcg(a + 1)), Sb = d_from_fx(__ldcg(a + 2));
+      ma = Sa / n; mb = Sb / n;
+      if (n >= 3) {
+        const double Raa = d_from_fx(__ldcg(a + 9)), Rab = d_from_fx(__ldcg(a + 10)), Rbb = d_from_fx(__ldcg(a + 11));
+        const double Raz = d_from_fx(__ldcg(a + 12)), Rbz = d_from_fx(__ldcg(a + 13)), Rz = d_from_fx(__ldcg(a + 14));
+        const double m2 = ma * ma + mb * mb;
+        const double Saa = Raa - n * ma * ma, Sab = Rab - n * ma * mb, Sbb = Rbb - n * mb * mb;
+        const double Sz = Rz - n * m2;
+        const double Saz = Raz - 2.0 * ma * Raa - 2.0 * mb * Rab + m2 * Sa - ma * Rz + 2.0 * ma * ma * Sa + 2.0 * ma * mb * Sb - n * ma * m2;
+        const double Sbz = Rbz - 2.0 * ma * Rab - 2.0 * mb * Rbb + m2 * Sb - mb * Rz + 2.0 * ma * mb * Sa + 2.0 * mb * mb * Sb - n * mb * m2;
+        const double det = Saa * Sbb - Sab * Sab;
+        if (fabs(det) > 1e-300) {
+          const double Ac = (Saz * Sbb - Sbz * Sab) / det, Bc = (Sbz * Saa - Saz * Sab) / det;
+          ca = 0.5 * Ac; cb = 0.5 * Bc;
+          rad = sqrt(Sz / n + ca * ca + cb * cb);
+          ok = 1.0;
+        }
+      }
+    }
+    aux[(size_t)s * POLY_NACC + 16] = ca0 + ma;   // slice mean in absolute (u, w) coordinates
+    aux[(size_t)s * POLY_NACC + 17] = cb0 + mb;
+    aux[(size_t)s * POLY_NACC + 18] = ca;
+    aux[(size_t)s * POLY_NACC + 19] = cb;
+    aux[(size_t)s * POLY_NACC + 20] = rad;
+    aux[(size_t)s * POLY_NACC + 21] = ok;
+  }
+}
+
+// Accumulation passes, each followed (in the last block to finish) by the per-slice step that consumes it.
+// PASS 0: n, sum a', sum b', weighted normal scatter (slots 0..8) AND the second/third moments of (a', b') for the
+//         algebraic circle fit (9..14), a' = a - ca0, b' = b - cb0                         -> slice means + circle fit
+// PASS 2: squared residuals against the fitted circle (slot 15)                            -> output slices
+// (PASS 1, the separate centred-moment pass of round 1, is gone.)
 template <int PASS>
 __global__ void __launch_bounds__(POLY_BLOCK)
 k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, const unsigned char* __restrict__ labels,
             const int* __restrict__ n_ptr, const PolyState* __restrict__ ps, WeightLaw law, long long* __restrict__ acc,
-            gm_slice* __restrict__ out, unsigned* ticket) {
-  constexpr int NS = PASS == 0 ? 9 : (PASS == 1 ? 6 : 1);
-  constexpr int SLOT0 = PASS == 0 ? 0 : (PASS == 1 ? 9 : 15);
-  __shared__ unsigned long long s_acc[POLY_SMEM_SLICES * NS];
+            gm_slice* __restrict__ out, unsigned* ticket, const ModelState* __restrict__ cyl) {
+  constexpr int NS = PASS == 0 ? 15 : 1;
+  constexpr int SLOT0 = PASS == 0 ? 0 : 15;
+  __shared__ unsigned long long s_acc[POLY_SMEM_SLICES * (PASS == 0 ? 9 : 1)];
   const int n = *n_ptr;
   const int S = ps->S;
-  const bool use_smem = S <= POLY_SMEM_SLICES;
+  const bool use_smem = S * NS <= POLY_SMEM_SLICES * (PASS == 0 ? 9 : 1);
+  // fixed centring point of pass 0: where the refined cylinder's axis meets the (u, w) plane (0 without a model)
+  double ca0 = 0.0, cb0 = 0.0;
+  if (PASS == 0 && cyl != nullptr && cyl->best_id >= 0) {
+    ca0 = ps->u[0] * (double)cyl->coef[0] + ps->u[1] * (double)cyl->coef[1] + ps->u[2] * (double)cyl->coef[2];
+    cb0 = ps->w[0] * (double)cyl->coef[0] + ps->w[1] * (double)cyl->coef[1] + ps->w[2] * (double)cyl->coef[2];
+  }
   // a tunnel scan has few slices (10 at 1 m over a 10 m scan) and every thread adds to one of them: keep
   // up to 16 interleaved copies of the accumulators so that same-address shared-memory atomics are rare
   int copies = 1;
-  while (copies < 16 && 2 * copies * S <= POLY_SMEM_SLICES) copies *= 2;
+  while (copies < 16 && 2 * copies * S * NS <= POLY_SMEM_SLICES * (PASS == 0 ? 9 : 1)) copies *= 2;
   const int my_copy = threadIdx.x & (copies - 1);
   if (S > 0) {
     if (use_smem) {
@@ -210,20 +218,17 @@ k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, 
       if (s < 0 || s >= S) continue;
       long long v[NS];
       if (PASS == 0) {
-        double a = u0 * x + u1 * y + u2 * z, b = w0 * x + w1 * y + w2 * z;
+        double a = u0 * x + u1 * y + u2 * z - ca0, b = w0 * x + w1 * y + w2 * z - cb0;
         float4 n0 = normals[2 * (size_t)i];
         float curv = normals[2 * (size_t)i + 1].x;
         double wt = (double)d_weight(law, curv);
         double na = wt * (double)n0.x, nb = wt * (double)n0.y, nc = wt * (double)n0.z;
+        double zz = a * a + b * b;
         v[0] = 1; v[1] = d_to_fx(a); v[2] = d_to_fx(b);
         v[3] = d_to_fx(na * na); v[4] = d_to_fx(na * nb); v[5] = d_to_fx(na * nc);
         v[6] = d_to_fx(nb * nb); v[7] = d_to_fx(nb * nc); v[8] = d_to_fx(nc * nc);
-      } else if (PASS == 1) {
-        double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
-        double a = u0 * x + u1 * y + u2 * z - ma, b = w0 * x + w1 * y + w2 * z - mb;
-        double zz = a * a + b * b;
-        v[0] = d_to_fx(a * a); v[1] = d_to_fx(a * b); v[2] = d_to_fx(b * b);
-        v[3] = d_to_fx(a * zz); v[4] = d_to_fx(b * zz); v[5] = d_to_fx(zz);
+        v[9] = d_to_fx(a * a); v[10] = d_to_fx(a * b); v[11] = d_to_fx(b * b);
+        v[12] = d_to_fx(a * zz); v[13] = d_to_fx(b * zz); v[14] = d_to_fx(zz);
       } else {
         double ma = aux[(size_t)s * POLY_NACC + 16], mb = aux[(size_t)s * POLY_NACC + 17];
         double ca = aux[(size_t)s * POLY_NACC + 18], cb = aux[(size_t)s * POLY_NACC + 19], rad = aux[(size_t)s * POLY_NACC + 20];
@@ -248,8 +253,7 @@ k_poly_pass(const float4* __restrict__ pts, const float4* __restrict__ normals, 
   }
   __threadfence();
   if (!d_last_block(ticket, gridDim.x)) return;
-  if (PASS == 0) d_poly_means(ps, acc);
-  else if (PASS == 1) d_poly_fit(ps, acc);
+  if (PASS == 0) d_poly_means_and_fit(ps, acc, ca0, cb0);
   else d_poly_finish(ps, acc, out);
 }
 

@@ -133,3 +133,56 @@ def test_bbox_allreduce_gives_every_rank_the_whole_map_box():
         out = m.dict()
         mp.spawn(_bbox_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert out[0] == out[1] == out["ref"]
+
+
+# ---- map slabs: the voxels of all slabs gathered into the whole-map VoxelGrid -----------------
+class _FakeSlabCtx:
+    """Stands in for a capi.Context that has run gm_voxel on one slab: the oracle's VoxelGrid on the GLOBAL lattice,
+    restricted to the slab's owned points (that is what gm_set_owned_range + the all-reduced box produce on the GPU)."""
+
+    def __init__(self, keys, centroids, counts):
+        self._v = {"keys": keys, "centroids": centroids, "counts": counts}
+
+    def download_voxels(self, with_nn=False):
+        return self._v
+
+
+def _slab_voxels(full_vox, pts, lo, hi):
+    own = (pts[:, 0] >= np.float32(lo)) & (pts[:, 0] < np.float32(hi))
+    ids = np.unique(full_vox["assign"][own])
+    return full_vox["voxel_keys"][ids], full_vox["centroids_fx"][ids], full_vox["voxel_counts"][ids]
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+
+    pts = synth.curved_tunnel(30000, seed=4, outlier_frac=0.0)
+    leaf = 0.2
+    full = O.voxel(pts, leaf)
+    lo, hi = D.slab_cuts(pts[:, 0], world, leaf)[rank]
+    keys, cen, cnt = D.gather_slab_voxels(_FakeSlabCtx(*_slab_voxels(full, pts, lo, hi)))
+    out[rank] = bool(np.array_equal(keys, full["voxel_keys"]) and np.array_equal(cnt, full["voxel_counts"])
+                     and cen.tobytes() == full["centroids_fx"].tobytes())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gathered_slab_voxels_are_the_whole_map_voxelgrid(world):
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_gather_worker, args=(world, port, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world))
+
+
+def test_merge_rejects_slabs_that_share_a_voxel():
+    k = np.array([1, 5, 9], np.int32)
+    c = np.zeros((3, 4), np.float32)
+    n = np.ones(3, np.int32)
+    keys, _, _ = D.merge_slab_voxels([(k, c, n), (np.array([2, 7], np.int32), c[:2], n[:2])])
+    assert list(keys) == [1, 2, 5, 7, 9]
+    with pytest.raises(ValueError):
+        D.merge_slab_voxels([(k, c, n), (np.array([5], np.int32), c[:1], n[:1])])

@@ -566,7 +566,7 @@ def main():
     voxdense_traffic = tsum("k_crop", "k_voxel_accumulate_sorted", "k_voxel_dense_scan", "k_voxel_assign")
     families = {
         "normals": {"bound": "fp32", "achieved": nrm_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                    "frac": nrm_tflops / fp32_peak_tflops, "traffic": traffic.get("k_normals"), "ms_per_step": nrm_ms,
+                    "frac": nrm_tflops / fp32_peak_tflops, "traffic": traffic.get("k_normals<0>"), "ms_per_step": nrm_ms,
                     "kernels": "k_normals<0>",
                     "algorithmic": f"8 flop x {cand_per_scan:.0f} stencil candidates + 15 flop x {nbr_per_scan:.0f} neighbours + 150 flop x "
                                    f"{M:.0f} points; the kernel is instruction-issue bound (ncu: ~73 % of issue slots active, ~30 "

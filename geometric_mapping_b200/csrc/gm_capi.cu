@@ -173,7 +173,6 @@ struct gm_ctx {
   struct gm_comm* comm = nullptr;
   bool sharded = false;
   double* d_frame_sums = nullptr;  // [8] the 6 scatter sums of the last gm_local_frame, kept for gm_allreduce_frame
-  double *d_gn_partials = nullptr, *d_gn_first = nullptr;  // cylinder refit: per-tile partial sums / totals of the first Gauss-Newton step
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -455,7 +454,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
   ctx->rs_hist_words = (size_t)div_up((long long)N, RS_BLOCK * 4) * 256;  // sized for the smaller tile
   A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256);
-  A(d_st, 1); A(d_ctl, 3); A(d_frame_sums, 8); A(d_gn_partials, ((size_t)div_up((long long)N, CPL_TILE) + 2) * GN_NV); A(d_gn_first, GN_NV);
+  A(d_st, 1); A(d_ctl, 3); A(d_frame_sums, 8);
   A(d_partials, 3 * kPartialsRegion);  // 3 regions: frame | plane refit | cylinder GN (may run concurrently)
   A(d_frame, 1);
   A(d_samples[0], 3 * H); A(d_samples[1], 2 * H);
@@ -507,7 +506,7 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
-                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_gn_partials, ctx->d_gn_first, ctx->d_partials, ctx->d_frame,
+                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
                   ctx->d_res_vs, ctx->d_comp, ctx->d_res_pts, ctx->d_res_centroid, ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start,
@@ -1047,8 +1046,7 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
               ctx->d_partials + 1 * kPartialsRegion, ctx->d_counters + 1);
   } else {
     GM_LAUNCH(ctx, k_cyl_inlier_compact, std::max(1, div_up((long long)ctx->n_grid, CPL_TILE)), CP_BLOCK, ctx->d_cloud_c, n_ptr,
-              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64_b, ctx->d_ctl + 1, &ctx->d_st->error,
-              ctx->d_gn_partials, ctx->d_counters + 14, ctx->d_gn_first);
+              ctx->d_key + 1, H, ctx->d_model7, ctx->d_test12, ms, ctx->d_inl, ctx->d_state64_b, ctx->d_ctl + 1, &ctx->d_st->error);
     // all Gauss-Newton passes in one cooperative launch (grid barrier between passes)
     {
       const float4* inl = ctx->d_inl;
@@ -1056,8 +1054,7 @@ gm_status gm_ransac_select(gm_ctx* ctx, int32_t kind) {
       double* partials = ctx->d_partials + 2 * kPartialsRegion;
       unsigned* bars = ctx->d_counters + 5;  // counters [5],[6]: the two barrier counters, [7]: which one the next launch uses
       int* err = &ctx->d_st->error;
-      const double* first = ctx->d_gn_first;
-      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bars, (void*)&err, (void*)&first};
+      void* args[] = {(void*)&inl, (void*)&ms, (void*)&iters, (void*)&tau, (void*)&partials, (void*)&bars, (void*)&err};
       GM_CUDA(cudaLaunchCooperativeKernel((const void*)k_cyl_gn_all, dim3(ctx->gn_blocks), dim3(RF_BLOCK), args, 0, ctx->stream));
       ++ctx->launches;
     }

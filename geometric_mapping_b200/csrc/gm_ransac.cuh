@@ -731,60 +731,44 @@ __device__ __forceinline__ void d_gn_accumulate(const float4 p, const double q0,
 }
 
 // The refit set is FIXED (inliers of the winning hypothesis), so it is compacted once (stable look-back compaction) and
-// the Gauss-Newton passes run over the dense array.  The kernel that finds the inliers also accumulates the sums of
-// the FIRST Gauss-Newton step (at the hypothesis itself): per-block partials, reduced in tile order by the last block to
-// finish -> `first_sums`.  k_cyl_gn_all starts from them, so the first update costs no pass over the points.
-__global__ void __launch_bounds__(CP_BLOCK, 2)
+// the Gauss-Newton passes run over the dense array.  (Accumulating the sums of the first Gauss-Newton step here as
+// well was measured: the compaction went from 13 to 44 us -- 128 registers, double-precision chains inside a look-back
+// kernel -- for 35 us saved in k_cyl_gn_all; the sums are taken by k_cyl_gn_all's own first pass instead.)
+__global__ void __launch_bounds__(CP_BLOCK, 4)
 k_cyl_inlier_compact(const float4* __restrict__ pts, const int* __restrict__ n_ptr, const unsigned long long* __restrict__ key, int H,
                      const float* __restrict__ model7, const float* __restrict__ test12, ModelState* ms,
-                     float4* __restrict__ inl, unsigned long long* state, TileCtl* ctl, int* err,
-                     double* __restrict__ partials /* grid x GN_NV */, unsigned* ticket, double* __restrict__ first_sums /* GN_NV */) {
+                     float4* __restrict__ inl, unsigned long long* state, TileCtl* ctl, int* err) {
   __shared__ CompactSmem<CP_BLOCK, CPL_IPT> sm;
-  __shared__ double s_red[GN_NV * (CP_BLOCK / 32)];
-  __shared__ double s_fin[GN_NV];
   const int n = *n_ptr;
   unsigned epoch;
   const int tile = tile_begin(ctl, epoch), base = tile * CPL_TILE;
-  double s[GN_NV];
-#pragma unroll
-  for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;
   if (base >= n) {
     // empty cloud: tile 0 still has to publish the (empty) model state
     if (tile == 0 && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = 0; }
     tile_end(ctl);
-  } else {
-    // every block decodes the winner itself (k_select folded in)
-    const unsigned long long kk = *key;
-    const int best_count = (int)(unsigned)(kk >> 32) - 1;
-    const int best_id = (int)(0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull));
-    const bool have = best_count >= 0 && best_id >= 0 && best_id < H;
-    const int hid = have ? best_id : 0;
-    const CylTest t = d_load_cyl_test(test12 + (size_t)hid * 12);
-    const float* m7 = model7 + (size_t)hid * 7;
-    const double q0 = m7[0], q1 = m7[1], q2 = m7[2], r = m7[6];
-    double dir[3] = {m7[3], m7[4], m7[5]}, u[3], w[3];
-    if (have) d_perp_basis_d(dir, u, w);
-    bool f[CPL_IPT];
-    float4 p[CPL_IPT];
-#pragma unroll
-    for (int j = 0; j < CPL_IPT; ++j) {
-      int i = base + j * CP_BLOCK + threadIdx.x;
-      f[j] = false;
-      if (i < n) { p[j] = pts[i]; f[j] = have && d_cyl_inlier(t, p[j]); }
-    }
-    unsigned ranks[CPL_IPT], total;
-    tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, err, sm);
-#pragma unroll
-    for (int j = 0; j < CPL_IPT; ++j)
-      if (f[j]) { inl[ranks[j]] = p[j]; d_gn_accumulate(p[j], q0, q1, q2, dir, u, w, r, s); }
-    if (base + CPL_TILE >= n && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = (int)total; }
-    tile_end(ctl);
+    return;
   }
-  // tiles are ticket numbers: tile t's partial goes to row t, so the reduction order does not depend on scheduling
-  block_sum_store<GN_NV, CP_BLOCK>(s, s_red, partials + (size_t)tile * GN_NV);
-  if (!d_last_block(ticket, gridDim.x)) return;
-  d_reduce_partials<GN_NV>(partials, gridDim.x, s_fin);
-  if (threadIdx.x < GN_NV) first_sums[threadIdx.x] = s_fin[threadIdx.x];
+  // every block decodes the winner itself (k_select folded in)
+  const unsigned long long kk = *key;
+  const int best_count = (int)(unsigned)(kk >> 32) - 1;
+  const int best_id = (int)(0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull));
+  const bool have = best_count >= 0 && best_id >= 0 && best_id < H;
+  const CylTest t = d_load_cyl_test(test12 + (size_t)(have ? best_id : 0) * 12);
+  bool f[CPL_IPT];
+  float4 p[CPL_IPT];
+#pragma unroll
+  for (int j = 0; j < CPL_IPT; ++j) {
+    int i = base + j * CP_BLOCK + threadIdx.x;
+    f[j] = false;
+    if (i < n) { p[j] = pts[i]; f[j] = have && d_cyl_inlier(t, p[j]); }
+  }
+  unsigned ranks[CPL_IPT], total;
+  tile_compact_ranks<CP_BLOCK, CPL_IPT>(f, ranks, total, state, epoch, tile, err, sm);
+#pragma unroll
+  for (int j = 0; j < CPL_IPT; ++j)
+    if (f[j]) inl[ranks[j]] = p[j];
+  if (base + CPL_TILE >= n && threadIdx.x == 0) { d_select(key, 1, H, nullptr, model7, test12, ms); ms->n_inl = (int)total; }
+  tile_end(ctl);
 }
 
 __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
@@ -811,14 +795,13 @@ __device__ bool d_solve5(double A[5][5], double b[5], double x[5]) {
 }
 
 // All Gauss-Newton passes of the cylinder refit in ONE cooperative launch (grid <= co-resident capacity, guaranteed by
-// cudaLaunchCooperativeKernel).  The sums of the first step arrive from k_cyl_inlier_compact (`first_sums`), so the
-// first update is free.  Per further pass every block reduces its share of the compacted inliers to 22 doubles
+// cudaLaunchCooperativeKernel).  Per pass every block reduces its share of the compacted inliers to 22 doubles
 // (J^T J: 15, J^T r: 5, count, sum r^2), publishes them, crosses a grid barrier, and then EVERY block sums the per-block
 // partials in block order and solves the same 5x5 system (redundant but deterministic: no second barrier, no broadcast).
 // The loop ends when the step is below 1e-4 (m / rad; Gauss-Newton converges quadratically here, the next step would be
 // ~1e-8: same rule in the oracle) -- the RMS at the new iterate then follows from the sums already at hand through the
 // Gauss-Newton model, sum (r + J x)^2 = sum r^2 + 2 x.J^T r + x^T J^T J x, exact to O(|x|^2) -- or when `iters` updates were
-// made, in which case the sums of one more pass give the RMS.  Typical scan: ONE pass over the inliers.
+// made, in which case the sums of one more pass give the RMS.  Typical scan: TWO passes over the inliers (round 1: six).
 __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target, int* err) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -834,8 +817,7 @@ __device__ __forceinline__ void d_grid_barrier(unsigned* count, unsigned target,
 
 __global__ void __launch_bounds__(RF_BLOCK)
 k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float tau, double* __restrict__ partials /* 2 x grid x 22 */,
-             unsigned* bars /* [0],[1] barrier counters used alternately, [2] which one this launch uses */, int* err,
-             const double* __restrict__ first_sums) {
+             unsigned* bars /* [0],[1] barrier counters used alternately, [2] which one this launch uses */, int* err) {
   __shared__ double sm[GN_NV * (RF_BLOCK / 32)];
   __shared__ double fin[GN_NV];
   __shared__ double it_q[3], it_dir[3], it_r, s_rms2;
@@ -856,13 +838,13 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
     it_r = ms->r;
     s_state = 0; s_rms2 = 0.0;
   }
-  if (threadIdx.x < GN_NV) fin[threadIdx.x] = first_sums[threadIdx.x];
   __syncthreads();
   long long cnt = 0;
   int pass = 0;  // barriers crossed so far in this launch
-  for (int it = 0;; ++it) {
-    // fin = the sums at the current iterate; every block takes the same decisions from the same numbers
-    if (threadIdx.x == 0) {
+  for (int it = -1;; ++it) {
+    // it = -1: no sums yet, take the first pass.  Otherwise fin = the sums at the current iterate; every block takes
+    // the same decisions from the same numbers
+    if (it >= 0 && threadIdx.x == 0) {
       cnt = (long long)(fin[20] + 0.5);
       bool done = true;
       if (cnt > 5) {
@@ -898,7 +880,7 @@ k_cyl_gn_all(const float4* __restrict__ inl, ModelState* ms, int iters, float ta
       s_state = done ? 1 : 0;
     }
     __syncthreads();
-    if (s_state) break;
+    if (it >= 0 && s_state) break;
     double s[GN_NV];
 #pragma unroll
     for (int k = 0; k < GN_NV; ++k) s[k] = 0.0;

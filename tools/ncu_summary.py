@@ -5,7 +5,7 @@ import csv, json, sys, collections
 COLS = [("gpu__time_duration.sum", "us", 1.0), ("launch__grid_size", "grid", 1), ("launch__block_size", "block", 1),
         ("launch__registers_per_thread", "regs", 1), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%", 1),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%", 1),
-        ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "fmaheavy%", 1),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma-pipe%", 1), ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%", 1),
         ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu%", 1),
         ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%", 1),
         ("l1tex__t_sector_hit_rate.pct", "l1hit%", 1), ("lts__t_sector_hit_rate.pct", "l2hit%", 1),

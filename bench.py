@@ -400,7 +400,7 @@ def main():
         cx.process_scan(samples[s][0], samples[s][1])
 
     for i in range(max(a.warmup, 3) * NFLIGHT):
-        tstep(i)
+        tstep(i)   # (>= 3 scans per context: plain launches, graph capture, first replay)
     barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
@@ -436,7 +436,7 @@ def main():
         cx.process_scan(samples4[s][0], samples4[s][1])
 
     steps4 = max(6, a.steps // 4)
-    for i in range(2 * NFLIGHT):
+    for i in range(3 * NFLIGHT):
         tstep4(i)
     barrier()
     for st_ in tstreams[1:]:
@@ -473,7 +473,8 @@ def main():
             cx.set_scan_device(fr_dev[j].data_ptr(), F_PTS)
             cx.process_scan(fr_smp[j][0], fr_smp[j][1])
 
-    frames_pass()
+    for _ in range(3):
+        frames_pass()
     barrier()
     for st_ in tstreams[1:]:
         st_.wait_stream(stream)
@@ -499,27 +500,40 @@ def main():
     # ---- per-segment timing of the same steps (roofline) ------------------------------------------
     # CUDA-event pairs inside the library around every stage (gm_profile_*: plain stream launches on one stream, so the
     # segments add up; the timed legs above replay the graph on three streams).
-    def profile_steps(count, knn=0, voxel_mode=0, count_mode=0):
-        ctx.set_voxel_mode(voxel_mode)
-        ctx.set_count_mode(count_mode)
-        ctx.set_knn(knn)
+    def profile_steps(count, knn=0, voxel_mode=0, count_mode=0, cx=None):
+        cx = cx or ctx
+        cx.set_voxel_mode(voxel_mode)
+        cx.set_count_mode(count_mode)
+        cx.set_knn(knn)
+
+        def one(i):
+            s = i % RING
+            cx.set_scan_device(dev_scans[s].data_ptr(), n)
+            cx.process_scan(samples[s][0], samples[s][1])
+
         for i in range(2):
-            step(i)
-        ctx.profile_enable(True)
+            one(i)
+        cx.profile_enable(True)
         for i in range(count):
-            step(i)
-        pr = ctx.profile_read()
-        ctx.profile_enable(False)
-        ctx.set_voxel_mode(0)
-        ctx.set_count_mode(0)
-        ctx.set_knn(a.knn)
+            one(i)
+        pr = cx.profile_read()
+        cx.profile_enable(False)
+        cx.set_voxel_mode(0)
+        cx.set_count_mode(0)
+        cx.set_knn(a.knn)
         return {k: (v[0] / max(count, 1)) for k, v in pr.items()}
 
     nb = max(4, min(a.steps, 20))
     seg_ms = profile_steps(a.steps, knn=a.knn)
     seg_brute = profile_steps(nb, knn=a.knn, count_mode=1)       # every point x hypothesis test executed: the FP32-pipe figure
     seg_sortvox = profile_steps(nb, knn=a.knn, voxel_mode=1)     # sort-based VoxelGrid (keys -> radix sort -> heads -> centroids)
-    seg_knn = profile_steps(nb, knn=32) if not a.knn else None   # k-NN normals (k = 32) on the same scans
+    seg_knn = None
+    KNN_CELL = 0.07   # grid cell of the k-NN leg: near the distance of the 32nd neighbour on this scan (the search is exact for any cell)
+    if not a.knn:      # k-NN normals (k = 32) on the same scans
+        kparams = capi.default_params(neighborRadius=KNN_CELL, voxelGridLeafSize=a.leaf, ransacThreshold=TAU, refitIterations=a.refit_iters)
+        with capi.Context(kparams, max_points=n, max_hypotheses=4096) as kctx:
+            kctx.set_stream(stream.cuda_stream)
+            seg_knn = profile_steps(nb, knn=32, cx=kctx)
     brute_ms = seg_brute["plane_count"] + seg_brute["cyl_count"]
     M = float(np.mean(n_valid))
     Mc = float(c.n_cropped)
@@ -610,8 +624,9 @@ def main():
     if seg_knn is not None:
         knn_leg = {"k": 32, "normals_ms": seg_knn["normals"], "points_per_s": M / (seg_knn["normals"] * 1e-3) if seg_knn["normals"] > 0 else 0.0,
                    "scan_ms_single_stream": float(sum(seg_knn.values())),
-                   "note": "gm_set_knn(32): pcl::NormalEstimation::setKSearch(32) instead of setRadiusSearch; exact k-NN on the same grid, "
-                           "neighbours summed in FLANN's order (normals bit-identical to the oracle's); radius-mode normals_ms above"}
+                   "grid_cell_m": KNN_CELL,
+                   "note": "gm_set_knn(32): pcl::NormalEstimation::setKSearch(32) instead of setRadiusSearch; exact k-NN, neighbours summed in "
+                           "FLANN's order (normals bit-identical to the oracle's: tests/test_gpu_chain.py); the grid cell only sizes the search"}
 
     # ---- end to end through the C-ABI with host buffers (NCTX contexts pipelined) --------------------
     # Per step: H2D of the scan from pinned memory as 12-byte xyz records (what a PointCloud2 of x,y,z float32 carries;
@@ -653,7 +668,7 @@ def main():
             cx.process_scan(smp[s][0], smp[s][1])
             cx.fetch_async(outs[k])
 
-        for i in range(max(a.warmup, 3)):
+        for i in range(max(a.warmup, 3 * NCTX)):   # every context: plain launches, graph capture, first replay
             e2e_step(i)
         for cx in ectx:
             cx.synchronize()

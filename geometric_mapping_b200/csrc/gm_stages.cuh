@@ -642,11 +642,13 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 // value) in a SORTED list in shared memory: a candidate is offered only if it beats the current k-th key, insertion
 // shifts the tail, and the finished list is already in FLANN's result order -- so the neighbours are summed in exactly
 // the order pcl::NormalEstimation sums them and the normals are bit-identical to the CPU oracle's in this mode.
-//   pass A  the 27-cell stencil (the runs of the radius mode).  Complete iff k keys were found and the k-th distance is
-//           below one cell: nothing outside the stencil can be nearer.
-//   pass B  (sparse neighbourhoods, outliers) restart over whole 4x4x4-cell blocks in growing Chebyshev shells around the
-//           query's block -- a block is ONE contiguous run of the sorted cloud and an empty block costs one table read --
-//           until the k-th distance is below the distance to the nearest unexamined block.
+//   pass A   the 27-cell stencil (the runs of the radius mode), only candidates nearer than one cell.  Complete iff k keys
+//            were found: nothing outside the stencil can be nearer.  (Size the grid -- neighborRadius -- near the expected
+//            distance of the k-th neighbour and almost every point ends here.)
+//   pass B1  (sparser neighbourhoods) restart: the stencil unfiltered, then rings 2..3 of cells through the block table;
+//            complete when the k-th distance is below the ring's distance.
+//   pass B2  (isolated points) restart over whole 4x4x4-cell blocks in growing Chebyshev shells around the query's block
+//            -- a block is ONE contiguous run of the sorted cloud and an empty block costs one table read.
 constexpr int KNN_BLOCK = 64;
 constexpr int KNN_MAX = 64;
 
@@ -707,9 +709,63 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
         if (d2 <= lim1) L.offer(d2, __float_as_int(q.w));
       }
     }
-    const bool complete = L.cnt == K;  // k keys, all within one cell of the query (the filter above)
+    bool complete = L.cnt == K;  // k keys, all within one cell of the query (the filter above)
     if (!complete && nf > L.cnt) {
-      // ---- pass B: whole blocks in growing shells (from scratch: the stencil is part of shell 0/1)
+      // ---- pass B1: growing rings of CELLS around the query's cell, unfiltered (ring <= 1 = the stencil again, this time
+      // with every candidate; ring k >= 2 = its rows through the block table).  After ring k every unexamined point is at
+      // least k cells away.  Sparse surface points end here (the k-th neighbour is within 2-3 cells).
+      L.reset();
+      int cx, cy, cz;
+      gm_cell_of(g, p.x, p.y, p.z, cx, cy, cz);
+      for (int k = 0; k < nr; ++k) {
+        const int2 run = rr[k];
+        for (int t = run.x; t < run.y; ++t) {
+          const float4 q = sp[t];
+          const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+          L.offer((dx * dx + dy * dy) + dz * dz, __float_as_int(q.w));
+        }
+      }
+      auto done_at = [&](int ring) {
+        const float lim = (float)ring * g.cell * 0.999f;
+        return L.cnt == K && __uint_as_float((unsigned)(L.worst >> 32)) <= lim * lim;
+      };
+      complete = done_at(1);
+      constexpr int KNN_RINGS = 3;
+      for (int ring = 2; !complete && ring <= KNN_RINGS; ++ring) {
+        const int inner = 2 * ring - 1, T = 8 * ring + 2 * inner * inner;  // perimeter rows (full x span) + inner rows (two end cells)
+        for (int t = 0; t < T; ++t) {
+          int dy, dz, x0, x1;
+          if (t < 8 * ring) {
+            if (t < 2 * ring + 1) { dz = -ring; dy = t - ring; }
+            else if (t < 4 * ring + 2) { dz = ring; dy = t - (2 * ring + 1) - ring; }
+            else if (t < 6 * ring + 1) { dy = -ring; dz = t - (4 * ring + 2) - (ring - 1); }
+            else { dy = ring; dz = t - (6 * ring + 1) - (ring - 1); }
+            x0 = cx - ring; x1 = cx + ring;
+          } else {
+            const int u2 = t - 8 * ring, cell = u2 >> 1;
+            dy = cell % inner - (ring - 1); dz = cell / inner - (ring - 1);
+            x0 = x1 = (u2 & 1) ? cx + ring : cx - ring;
+          }
+          const int yy = cy + dy, zz = cz + dz;
+          if (yy < 0 || zz < 0 || yy >= g.dim[1] || zz >= g.dim[2]) continue;
+          x0 = max(x0, 0); x1 = min(x1, g.dim[0] - 1);
+          for (int xs = x0; xs <= x1;) {
+            const int xe = min(x1, xs | 3);
+            const int2 seg = cell_segment(g, tab, ucell_start, U, nf, xs, xe, yy, zz);
+            ncand += seg.y - seg.x;
+            for (int tt = seg.x; tt < seg.y; ++tt) {
+              const float4 q = sp[tt];
+              const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+              L.offer((ex * ex + ey * ey) + ez * ez, __float_as_int(q.w));
+            }
+            xs = xe + 1;
+          }
+        }
+        complete = done_at(ring);
+      }
+    }
+    if (!complete && nf > L.cnt) {
+      // ---- pass B2 (isolated points): whole blocks in growing shells, from scratch
       L.reset();
       int cx, cy, cz;
       gm_cell_of(g, p.x, p.y, p.z, cx, cy, cz);

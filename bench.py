@@ -32,6 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 TAU = 0.05
+KNN_CAP = 0.25  # radius cap of the k-NN mode (gm_set_knn_max_radius): isolated outliers do not drag the search across the grid
 RING = 12  # distinct resident scans cycled through: 12 x 16 MB = 192 MB > 126 MB L2
 
 
@@ -84,7 +85,7 @@ def host_threads() -> int:
 def cpu_process_scan(pts, a, ps, cs, nthreads):
     from oracle import chain
 
-    f = chain.front(pts, bound=5.0, radius=a.radius, leaf=a.leaf, wf=0.2, nthreads=nthreads, knn=a.knn)
+    f = chain.front(pts, bound=5.0, radius=a.radius, leaf=a.leaf, wf=0.2, nthreads=nthreads, knn=a.knn, knn_max_radius=KNN_CAP if a.knn else 0.0)
     nv = f["n_valid"]
     ps = None if ps is None else (ps % max(nv, 1)).astype(np.int32)   # same rule as the GPU arm (ring_samples)
     cs = None if cs is None else (cs % max(nv, 1)).astype(np.int32)
@@ -334,7 +335,7 @@ def main():
     def new_ctx(max_h):
         cx = capi.Context(params, max_points=n, max_hypotheses=max_h)
         if a.knn:
-            cx.set_knn(a.knn)
+            cx.set_knn(a.knn, max_radius=KNN_CAP)
         return cx
 
     ctx = new_ctx(max(4096, a.shard_hyp, a.shard_hyp_large))
@@ -504,7 +505,7 @@ def main():
         cx = cx or ctx
         cx.set_voxel_mode(voxel_mode)
         cx.set_count_mode(count_mode)
-        cx.set_knn(knn)
+        cx.set_knn(knn, max_radius=KNN_CAP if knn else 0.0)
 
         def one(i):
             s = i % RING
@@ -520,7 +521,7 @@ def main():
         cx.profile_enable(False)
         cx.set_voxel_mode(0)
         cx.set_count_mode(0)
-        cx.set_knn(a.knn)
+        cx.set_knn(a.knn, max_radius=KNN_CAP if a.knn else 0.0)
         return {k: (v[0] / max(count, 1)) for k, v in pr.items()}
 
     nb = max(4, min(a.steps, 20))
@@ -624,7 +625,7 @@ def main():
     if seg_knn is not None:
         knn_leg = {"k": 32, "normals_ms": seg_knn["normals"], "points_per_s": M / (seg_knn["normals"] * 1e-3) if seg_knn["normals"] > 0 else 0.0,
                    "scan_ms_single_stream": float(sum(seg_knn.values())),
-                   "grid_cell_m": KNN_CELL,
+                   "grid_cell_m": KNN_CELL, "max_radius_m": KNN_CAP,
                    "note": "gm_set_knn(32): pcl::NormalEstimation::setKSearch(32) instead of setRadiusSearch; exact k-NN, neighbours summed in "
                            "FLANN's order (normals bit-identical to the oracle's: tests/test_gpu_chain.py); the grid cell only sizes the search"}
 
@@ -636,7 +637,7 @@ def main():
     # (models, labels, polyline) -- all through gm_fetch_async into pinned buffers.
     NCTX = int(os.environ.get("GM_E2E_CONTEXTS", "4"))
     host_xyz = [torch.from_numpy(np.ascontiguousarray(h.numpy()[:, :3])).pin_memory() for h in host_scans]
-    VCAP = 1 << 17
+    VCAP = 49152   # voxels fetched per scan (a 10 m scan at leaf 0.1 has ~30k)
     ectx, outs, keep = [], [], []
     for k in range(NCTX):
         cx = new_ctx(4096)
@@ -854,7 +855,7 @@ def main():
         ps0, cs0 = ring_samples(a, 0, of["n_valid"])
         for canonical, name in ((True, "canonical"), (False, "fast")):
             try:
-                g_ = chain.gpu_chain(cp, ps0, cs0, canonical, a.radius, a.leaf, tau=TAU, refit_iters=a.refit_iters, knn=a.knn)
+                g_ = chain.gpu_chain(cp, ps0, cs0, canonical, a.radius, a.leaf, tau=TAU, refit_iters=a.refit_iters, knn=a.knn, knn_max_radius=KNN_CAP if a.knn else 0.0)
                 m_ = chain.compare(g_, of, ob, exact_normals=canonical)
                 m_["exact_outputs_equal"] = True   # compare() asserts every integer / bit-pattern output
                 m_["plane_best"] = [g_["plane"]["best_id"], g_["plane"]["best_count"]]
@@ -891,7 +892,8 @@ def main():
             "segments_ms_per_step": seg_ms,
             "knn32": knn_leg,
             "graph": {"captures_ctx0": graph_stats[0], "replays_ctx0": graph_stats[1],
-                      "note": "gm_process_scan replays a captured CUDA graph (one cudaGraphLaunch per scan); gpu_launches counts the kernels inside"},
+                      "note": "graph mode auto: scans of up to 524288 points (the 200k-point frames of frames_c3) replay a captured CUDA graph, "
+                              "1M-point scans use plain launches (same device throughput, better overlap with the host copies of e2e)"},
             "h4096": h4096,
             "frames_c3": frames_c3,
             "ransac": ransac,

@@ -128,7 +128,7 @@ SYMBOLS = [
     "gm_get_search_stats", "gm_set_voxel_mode", "gm_ransac_pair", "gm_ransac_select_pair", "gm_ransac_export_keys",
     "gm_ransac_import_keys", "gm_map_create", "gm_map_destroy", "gm_map_clear", "gm_map_insert", "gm_map_stats", "gm_map_download", "gm_map_save",
     "gm_map_load", "gm_map_leaf", "gm_set_normals_mode", "gm_set_graph_mode", "gm_get_graph_stats",
-    "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint", "gm_set_knn", "gm_download_knn_indices", "gm_pointcloud2_size", "gm_encode_pointcloud2", "gm_marker_array_size",
+    "gm_comm_create", "gm_comm_handle", "gm_comm_connect", "gm_comm_mailbox", "gm_comm_connect_local", "gm_comm_destroy", "gm_comm_rank", "gm_comm_world", "gm_comm_last_error", "gm_set_comm", "gm_ransac_sharded", "gm_allreduce_voxel_bbox", "gm_allreduce_frame", "gm_set_voxel_bbox_hint", "gm_set_knn", "gm_download_knn_indices", "gm_set_knn_max_radius", "gm_pointcloud2_size", "gm_encode_pointcloud2", "gm_marker_array_size",
     "gm_encode_marker_array", "gm_store_open", "gm_store_close", "gm_store_append", "gm_store_append_blob", "gm_store_count", "gm_store_info", "gm_store_read",
 ]
 
@@ -219,6 +219,7 @@ def _lib():
         "gm_set_voxel_bbox_hint": (i32, [vp, vp, vp]),
         "gm_set_knn": (i32, [vp, i32, i32]),
         "gm_download_knn_indices": (i32, [vp, vp, sz]),
+        "gm_set_knn_max_radius": (i32, [vp, C.c_double]),
         "gm_pointcloud2_size": (sz, [sz, C.c_char_p]),
         "gm_encode_pointcloud2": (i32, [vp, sz, C.c_char_p, C.c_uint32, C.c_uint64, i32, vp, sz, C.POINTER(sz)]),
         "gm_marker_array_size": (sz, [i32, C.c_char_p, C.c_char_p]),
@@ -369,9 +370,11 @@ class Context:
             a, b = np.ascontiguousarray(mn, np.float32), np.ascontiguousarray(mx, np.float32)
             self._ck(_lib().gm_set_voxel_bbox_hint(self._h, _ptr(a), _ptr(b)), "gm_set_voxel_bbox_hint")
 
-    def set_knn(self, k: int, keep_indices: bool = False):
-        """k > 0: k-nearest-neighbour normals (setKSearch) instead of the radius search; 0 = radius mode."""
+    def set_knn(self, k: int, keep_indices: bool = False, max_radius: float = 0.0):
+        """k > 0: k-nearest-neighbour normals (setKSearch) instead of the radius search; 0 = radius mode.
+        max_radius > 0: only neighbours nearer than that count (the k nearest within the radius)."""
         self._ck(_lib().gm_set_knn(self._h, k, 1 if keep_indices else 0), "gm_set_knn")
+        self._ck(_lib().gm_set_knn_max_radius(self._h, float(max_radius)), "gm_set_knn_max_radius")
         self._knn = k
 
     def download_knn_indices(self) -> np.ndarray:
@@ -381,7 +384,7 @@ class Context:
         return out
 
     def set_graph_mode(self, mode: int):
-        """1 = process_scan replays a captured CUDA graph (default), 0 = plain stream launches."""
+        """2 = auto (default: graphs for scans up to 524288 points), 1 = always replay a captured CUDA graph, 0 = plain launches."""
         self._ck(_lib().gm_set_graph_mode(self._h, mode), "gm_set_graph_mode")
 
     def graph_stats(self):

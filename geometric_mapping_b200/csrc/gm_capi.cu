@@ -117,6 +117,7 @@ struct gm_ctx {
   int voxel_mode = 0;  // 0 = dense tables when the key range fits, 1 = always sort
   int normals_mode = 0;  // 0 = neighbours summed in cell-run order (fast), 1 = in FLANN's (d2, index) order (bit-identical to the oracle)
   int knn_k = 0;         // > 0: k-nearest-neighbour normals (setKSearch) instead of the radius search
+  double knn_max_radius = 0.0;  // > 0: only neighbours nearer than this count (FLANN's radius + max_nn form); 0 = plain k-NN
   int* d_knn_idx = nullptr;  // optional M x k neighbour indices of the last gm_normals (gm_set_knn(.., keep_indices = 1))
   size_t knn_idx_cap = 0;
   bool knn_keep = false;
@@ -165,7 +166,7 @@ struct gm_ctx {
   std::vector<ScanGraph> graphs;
   unsigned long long graph_gen = 0;   // bumped by every setter that changes what a scan launches
   unsigned long long graph_clock = 0;
-  int graph_mode = 1;                 // 1 = replay graphs (default), 0 = plain stream launches (GM_GRAPH=0 / gm_set_graph_mode)
+  int graph_mode = 2;                 // 2 = auto (default): graphs for scans up to kGraphAutoPoints, plain launches above; 1 = always; 0 = never (GM_GRAPH / gm_set_graph_mode)
   bool samples_staged = false;        // the sample indices of the current call are already on their way to the device
   long long graph_replays = 0, graph_captures = 0;
   std::string graph_note;
@@ -480,7 +481,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   { const char* env = std::getenv("GM_SERIAL"); ctx->concurrent = !(env && env[0] == '1'); }
   { const char* env = std::getenv("GM_COUNT_MODE"); ctx->count_mode = (env && env[0] == '1') ? 1 : 0; }
   { const char* env = std::getenv("GM_VOXEL_MODE"); ctx->voxel_mode = (env && env[0] == '1') ? 1 : 0; }
-  { const char* env = std::getenv("GM_GRAPH"); ctx->graph_mode = (env && env[0] == '0') ? 0 : 1; }
+  { const char* env = std::getenv("GM_GRAPH"); ctx->graph_mode = env ? std::max(0, std::min(2, std::atoi(env))) : 2; }
   { const char* env = std::getenv("GM_NORMALS_MODE"); ctx->normals_mode = (env && env[0] == '1') ? 1 : 0; }
 
   if ((e = cudaMemset(ctx->d_key, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
@@ -633,6 +634,13 @@ gm_status gm_set_knn(gm_ctx* ctx, int32_t k, int32_t keep_indices) {
   return GM_OK;
 }
 
+gm_status gm_set_knn_max_radius(gm_ctx* ctx, double max_radius) {
+  if (!ctx || !(max_radius >= 0.0)) return GM_ERR_INVALID_ARG;
+  ++ctx->graph_gen;
+  ctx->knn_max_radius = max_radius;
+  return GM_OK;
+}
+
 gm_status gm_download_knn_indices(gm_ctx* ctx, int32_t* out, size_t capacity_points) {
   if (!ctx || !out) return GM_ERR_INVALID_ARG;
   if (!ctx->have_normals || ctx->knn_k <= 0 || !ctx->knn_keep || !ctx->d_knn_idx) return GM_ERR_STAGE_ORDER;
@@ -775,7 +783,8 @@ gm_status gm_normals(gm_ctx* ctx) {
           idx_out = ctx->d_knn_idx;
         }
         k_normals_knn<<<div_up((long long)n, KNN_BLOCK), KNN_BLOCK, (size_t)K * KNN_BLOCK * sizeof(unsigned long long), ctx->stream>>>(
-            ctx->d_sorted, ctx->d_crop, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, ctx->d_tab, ctx->d_ucell_start, n_ptr, g, K, ctx->d_normals,
+            ctx->d_sorted, ctx->d_crop, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, ctx->d_tab, ctx->d_ucell_start, n_ptr, g, K,
+            ctx->knn_max_radius > 0.0 ? (float)(ctx->knn_max_radius * ctx->knn_max_radius) : HUGE_VALF, ctx->d_normals,
             ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st, idx_out);
         ++ctx->launches;
       } else if (ctx->normals_mode == 1) {
@@ -1247,6 +1256,14 @@ static void drop_graph(gm_ctx::ScanGraph& g) {
   g.exec = nullptr;
 }
 
+// Graph policy of gm_process_scan.  Measured on B200 (bench.py, GM_GRAPH=0/1): replaying the captured graph removes ~100 us
+// of launch calls per scan -- 200k-point frames go from 7.8e3 to 1.37e4 frames/s, single-scan latency at 1M points from
+// 0.68 to 0.65 ms -- while the saturated throughput at 1M points is the same either way (the GPU is the limit), and the
+// end-to-end pipeline with 35 MB of host copies per scan in flight on four streams runs 6-13 % FASTER with plain launches
+// (their pacing interleaves the contexts' kernels and copies better than four resident graphs do).  Hence "auto".
+constexpr size_t kGraphAutoPoints = 524288;
+static bool use_graph(const gm_ctx* ctx) { return ctx->graph_mode == 1 || (ctx->graph_mode == 2 && ctx->n_grid <= kGraphAutoPoints); }
+
 // Run `body` (a fixed sequence of launches on the ctx streams) as a CUDA graph keyed by (kind, bucketed size, Hp, Hc,
 // parameter generation): the first call of a key runs `body` as plain launches (buffers that grow on demand are allocated
 // there, outside any capture), the second captures it (nothing executes during capture) and launches the graph, every
@@ -1311,7 +1328,7 @@ gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_
   if (!ctx->have_scan) return GM_ERR_STAGE_ORDER;
   if (Hp > ctx->hcap || Hc > ctx->hcap) { ctx->err = "H larger than max_hypotheses"; return GM_ERR_CAPACITY; }
   auto body = [&] { return process_scan_body(ctx, plane_samples_host, Hp, cyl_samples_host, Hc); };
-  const bool graphable = ctx->graph_mode == 1 && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;
+  const bool graphable = use_graph(ctx) && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;
   if (!graphable) return body();
   auto stage = [&]() -> gm_status {
     gm_status s;
@@ -1325,7 +1342,7 @@ gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host, int32_
 }
 
 gm_status gm_set_graph_mode(gm_ctx* ctx, int32_t mode) {
-  if (!ctx || (mode != 0 && mode != 1)) return GM_ERR_INVALID_ARG;
+  if (!ctx || mode < 0 || mode > 2) return GM_ERR_INVALID_ARG;
   ctx->graph_mode = mode;
   return GM_OK;
 }
@@ -2062,7 +2079,7 @@ gm_status gm_ransac_sharded(gm_ctx* ctx, const int32_t* plane_samples_host, int3
     ctx->sharded = false;
     return s;
   };
-  const bool graphable = ctx->graph_mode == 1 && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;
+  const bool graphable = ctx->graph_mode != 0 && ctx->concurrent && !ctx->profiling && ctx->n_grid > 0;  // a round is ~10 short launches: always worth it
   if (!graphable) return body();
   auto stage = [&]() -> gm_status {
     gm_status s = stage_samples(ctx, 0, plane_samples_host, pb, pe, 3);

@@ -676,8 +676,9 @@ struct KnnList {
 __global__ void __launch_bounds__(KNN_BLOCK)
 k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, const int* __restrict__ cell_id, const int2* __restrict__ runs,
               const int2* __restrict__ cell_info, const BlockEntry* __restrict__ tab, const int* __restrict__ ucell_start, const int* __restrict__ n_ptr,
-              GridSpec g, int K, float4* __restrict__ normals, int* __restrict__ nbr_count, float4* __restrict__ sorted_valid,
-              float4* __restrict__ leaf_bounds, OwnedRange own, DevState* st, int* __restrict__ knn_idx) {
+              GridSpec g, int K, float max_r2 /* neighbours must be nearer than this (+inf = plain k-NN) */, float4* __restrict__ normals,
+              int* __restrict__ nbr_count, float4* __restrict__ sorted_valid, float4* __restrict__ leaf_bounds, OwnedRange own, DevState* st,
+              int* __restrict__ knn_idx) {
   extern __shared__ unsigned long long knn_smem[];  // [K][KNN_BLOCK]
   const int n = *n_ptr;
   const int i = blockIdx.x * KNN_BLOCK + threadIdx.x;
@@ -706,10 +707,11 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
         const float4 q = sp[t];
         const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
         const float d2 = (dx * dx + dy * dy) + dz * dz;
-        if (d2 <= lim1) L.offer(d2, __float_as_int(q.w));
+        if (d2 <= lim1 && d2 < max_r2) L.offer(d2, __float_as_int(q.w));
       }
     }
-    bool complete = L.cnt == K;  // k keys, all within one cell of the query (the filter above)
+    // k keys, all within one cell of the query (the filter above) -- or the radius cap lies inside the stencil's reach
+    bool complete = L.cnt == K || max_r2 <= lim1;
     if (!complete && nf > L.cnt) {
       // ---- pass B1: growing rings of CELLS around the query's cell, unfiltered (ring <= 1 = the stencil again, this time
       // with every candidate; ring k >= 2 = its rows through the block table).  After ring k every unexamined point is at
@@ -722,16 +724,18 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
         for (int t = run.x; t < run.y; ++t) {
           const float4 q = sp[t];
           const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-          L.offer((dx * dx + dy * dy) + dz * dz, __float_as_int(q.w));
+          const float d2 = (dx * dx + dy * dy) + dz * dz;
+          if (d2 < max_r2) L.offer(d2, __float_as_int(q.w));
         }
       }
-      auto done_at = [&](int ring) {
+      auto done_at = [&](int ring) {  // the k-th neighbour, or the radius cap, lies inside what has been examined
         const float lim = (float)ring * g.cell * 0.999f;
-        return L.cnt == K && __uint_as_float((unsigned)(L.worst >> 32)) <= lim * lim;
+        return (L.cnt == K && __uint_as_float((unsigned)(L.worst >> 32)) <= lim * lim) || max_r2 <= lim * lim;
       };
       complete = done_at(1);
-      constexpr int KNN_RINGS = 3;
-      for (int ring = 2; !complete && ring <= KNN_RINGS; ++ring) {
+      // with a radius cap the rings go as far as the cap (and pass B2 is never needed); without one, 3 rings, then blocks
+      const int max_ring = (max_r2 < CUDART_INF_F) ? (int)ceilf(sqrtf(max_r2) / (g.cell * 0.999f)) + 1 : 3;
+      for (int ring = 2; !complete && ring <= max_ring; ++ring) {
         const int inner = 2 * ring - 1, T = 8 * ring + 2 * inner * inner;  // perimeter rows (full x span) + inner rows (two end cells)
         for (int t = 0; t < T; ++t) {
           int dy, dz, x0, x1;
@@ -756,7 +760,8 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
             for (int tt = seg.x; tt < seg.y; ++tt) {
               const float4 q = sp[tt];
               const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
-              L.offer((ex * ex + ey * ey) + ez * ez, __float_as_int(q.w));
+              const float e2 = (ex * ex + ey * ey) + ez * ez;
+              if (e2 < max_r2) L.offer(e2, __float_as_int(q.w));
             }
             xs = xe + 1;
           }
@@ -764,8 +769,8 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
         complete = done_at(ring);
       }
     }
-    if (!complete && nf > L.cnt) {
-      // ---- pass B2 (isolated points): whole blocks in growing shells, from scratch
+    if (!complete && nf > L.cnt && !(max_r2 < CUDART_INF_F)) {
+      // ---- pass B2 (isolated points, no radius cap): whole blocks in growing shells, from scratch
       L.reset();
       int cx, cy, cz;
       gm_cell_of(g, p.x, p.y, p.z, cx, cy, cz);
@@ -785,13 +790,37 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
               if (x < 0 || x >= nbx) continue;
               const BlockEntry e = tab[gm_cell_key(g, x << 2, y << 2, z << 2) >> 6];
               if (e.mask == 0ull) continue;
-              const int c_end = e.first + __popcll(e.mask);
-              const int t0 = min(ucell_start[e.first], nf), t1 = (c_end < U) ? min(ucell_start[c_end], nf) : nf;
-              ncand += t1 - t0;
-              for (int t = t0; t < t1; ++t) {
-                const float4 q = sp[t];
-                const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
-                L.offer((ex * ex + ey * ey) + ez * ez, __float_as_int(q.w));
+              // prune by geometry once the list is full: a block, then each of its occupied cells, whose box lies farther
+              // from the query than the current k-th neighbour cannot contribute (boxes grown by 0.1 % for the float
+              // rounding of the cell coordinate)
+              const float wd2 = (L.cnt == K) ? __uint_as_float((unsigned)(L.worst >> 32)) : CUDART_INF_F;
+              const float bs = 4.0f * g.cell, slack = 0.001f * g.cell;
+              const float bx0 = g.origin[0] + (float)x * bs, by0 = g.origin[1] + (float)y * bs, bz0 = g.origin[2] + (float)z * bs;
+              {
+                const float ddx = fmaxf(fmaxf(bx0 - slack - p.x, p.x - (bx0 + bs + slack)), 0.f);
+                const float ddy = fmaxf(fmaxf(by0 - slack - p.y, p.y - (by0 + bs + slack)), 0.f);
+                const float ddz = fmaxf(fmaxf(bz0 - slack - p.z, p.z - (bz0 + bs + slack)), 0.f);
+                if ((ddx * ddx + ddy * ddy) + ddz * ddz > wd2) continue;
+              }
+              unsigned long long m = e.mask;
+              int rank = e.first;
+              while (m) {
+                const int lc = __ffsll((long long)m) - 1;  // local cell code: x fastest, then y, then z (2 bits each)
+                m &= m - 1ull;
+                const int c_id = rank++;
+                const float cx0 = bx0 + (float)(lc & 3) * g.cell, cy0 = by0 + (float)((lc >> 2) & 3) * g.cell, cz0 = bz0 + (float)(lc >> 4) * g.cell;
+                const float ddx = fmaxf(fmaxf(cx0 - slack - p.x, p.x - (cx0 + g.cell + slack)), 0.f);
+                const float ddy = fmaxf(fmaxf(cy0 - slack - p.y, p.y - (cy0 + g.cell + slack)), 0.f);
+                const float ddz = fmaxf(fmaxf(cz0 - slack - p.z, p.z - (cz0 + g.cell + slack)), 0.f);
+                const float cur = (L.cnt == K) ? __uint_as_float((unsigned)(L.worst >> 32)) : CUDART_INF_F;
+                if ((ddx * ddx + ddy * ddy) + ddz * ddz > cur) continue;
+                const int t0 = min(ucell_start[c_id], nf), t1 = (c_id + 1 < U) ? min(ucell_start[c_id + 1], nf) : nf;
+                ncand += t1 - t0;
+                for (int t = t0; t < t1; ++t) {
+                  const float4 q = sp[t];
+                  const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+                  L.offer((ex * ex + ey * ey) + ez * ez, __float_as_int(q.w));
+                }
               }
             }
           }

@@ -177,6 +177,11 @@ GM_API gm_status gm_set_normals_mode(gm_ctx* ctx, int32_t mode);
  * keep_indices = 1 also stores the neighbour lists (M x k, -1 padded) for gm_download_knn_indices. */
 GM_API gm_status gm_set_knn(gm_ctx* ctx, int32_t k, int32_t keep_indices);
 GM_API gm_status gm_download_knn_indices(gm_ctx* ctx, int32_t* out_m_x_k, size_t capacity_points);
+/* Optional radius cap of the k mode: only points with d^2 < float(r*r) count as neighbours (FLANN's radiusSearch with max_nn = k:
+ * the k nearest within r).  0 (default) = plain k-NN as pcl::NormalEstimation::setKSearch.  An isolated point (a lidar
+ * outlier metres away from any surface) otherwise drags the exact search through every grid block between it and its k-th
+ * neighbour; with a cap it ends with fewer than 3 neighbours, gets a NaN normal and leaves with the compaction, as in radius mode. */
+GM_API gm_status gm_set_knn_max_radius(gm_ctx* ctx, double max_radius);
 /* VoxelGrid strategy of gm_voxel / gm_compress: 0 (default) = sort-free dense tables whenever the number of lattice
  * cells of the crop box (or of the box given with gm_set_voxel_bbox) is at most 2^23, else sort-based; 1 = always
  * sort-based.  Same voxels, order, counts and centroids either way. */
@@ -279,8 +284,10 @@ GM_API gm_status gm_process_scan(gm_ctx* ctx, const int32_t* plane_samples_host,
 
 /* gm_process_scan replays a CUDA graph: the first scan of a given (size bucket of 32768 points, Hp, Hc, parameters)
  * runs as plain stream launches, the second is captured, every later one is ONE cudaGraphLaunch (33 kernels on three
- * streams).  mode 0 = always plain launches, 1 = graphs (default; env GM_GRAPH=0 selects 0).  If the stream cannot
- * be captured the library keeps working with plain launches; gm_get_graph_stats tells which happened. */
+ * streams).  mode 0 = always plain launches, 1 = always graphs, 2 = auto (default; env GM_GRAPH overrides): graphs for scans of up
+ * to 524288 points, where launch overhead dominates, plain launches above, where the GPU is the limit and host copies
+ * pipeline better without (measured: DESIGN.md section 4).  If the stream cannot be captured the library keeps working with plain
+ * launches; gm_get_graph_stats tells which happened. */
 GM_API gm_status gm_set_graph_mode(gm_ctx* ctx, int32_t mode);
 GM_API gm_status gm_get_graph_stats(const gm_ctx* ctx, int64_t* captures, int64_t* replays);
 

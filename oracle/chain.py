@@ -12,11 +12,11 @@ import numpy as np
 from . import oracle as O
 
 
-def front(pts, bound=5.0, radius=0.05, leaf=0.1, wf=0.2, nthreads=0, knn=0, with_nn=True):
+def front(pts, bound=5.0, radius=0.05, leaf=0.1, wf=0.2, nthreads=0, knn=0, with_nn=True, knn_max_radius=0.0):
     """crop -> normals -> compaction -> VoxelGrid -> 1-NN -> local frame.  knn > 0: k-nearest-neighbour normals."""
     cropped, src = O.crop(pts, bound, True)
     if knn > 0:
-        nrm, cnt = O.normals_knn(cropped, knn, cell=max(radius, 1e-3), nthreads=nthreads)
+        nrm, cnt = O.normals_knn(cropped, knn, cell=max(radius, 1e-3), nthreads=nthreads, max_radius=knn_max_radius)
     else:
         nrm, cnt, _ = O.normals(cropped, radius, mode=0, order=0, nthreads=nthreads)
     cloud, nrm_c, vmap = O.compact(cropped, nrm)
@@ -72,7 +72,7 @@ def _bits(a):
     return b
 
 
-def gpu_chain(pts, ps, cs, canonical, radius, leaf, bound=5.0, tau=0.05, slice_len=1.0, refit_iters=5, knn=0):
+def gpu_chain(pts, ps, cs, canonical, radius, leaf, bound=5.0, tau=0.05, slice_len=1.0, refit_iters=5, knn=0, knn_max_radius=0.0):
     """The same path on the CUDA library through the C-ABI: everything compare() looks at, downloaded."""
     from geometric_mapping_b200 import capi
 
@@ -83,7 +83,7 @@ def gpu_chain(pts, ps, cs, canonical, radius, leaf, bound=5.0, tau=0.05, slice_l
     with capi.Context(prm, max_points=max(n, 1), max_hypotheses=H) as ctx:
         ctx.set_normals_mode(1 if canonical else 0)
         if knn:
-            ctx.set_knn(knn)
+            ctx.set_knn(knn, max_radius=knn_max_radius)
         ctx.upload_scan(pts)
         ctx.process_scan(ps, cs)
         c = ctx.counts()

@@ -394,9 +394,12 @@ GMO_API void gmo_normals(const float* pts4, int64_t n, double radius, float* nor
 // radius mode), fewer than k when the cloud has fewer finite points; fewer than 3 -> NaN normal.
 //   knn_idx   optional n x k, the neighbour indices in result order, -1 padded
 //   mode      0 = hash grid with expanding shells (exact), 1 = brute force O(n^2)
+//   max_radius > 0: only points with d2 < float(max_radius^2) are neighbours (FLANN radiusSearch with max_nn = k)
 GMO_API void gmo_normals_knn(const float* pts4, int64_t n, int32_t k, double cell, float* normals8, int32_t* nbr_count,
-                             int32_t* knn_idx, int mode, int nthreads) {
+                             int32_t* knn_idx, int mode, int nthreads, double max_radius) {
   const P4* p = (const P4*)pts4;
+  const bool capped = max_radius > 0.0;
+  const float max_r2 = capped ? (float)(max_radius * max_radius) : std::numeric_limits<float>::infinity();
   HashGrid grid;
   int64_t lo[3] = {INT64_MAX, INT64_MAX, INT64_MAX}, hi[3] = {INT64_MIN, INT64_MIN, INT64_MIN};
   if (mode == 0) {
@@ -423,7 +426,8 @@ GMO_API void gmo_normals_knn(const float* pts4, int64_t n, int32_t k, double cel
       if (finite && mode == 1) {
         for (int64_t j = 0; j < n; ++j) {
           if (!std::isfinite(p[j].x) || !std::isfinite(p[j].y) || !std::isfinite(p[j].z)) continue;
-          nb.emplace_back(flann_d2(q, &p[j].x), (int)j);
+          const float d2 = flann_d2(q, &p[j].x);
+          if (d2 < max_r2) nb.emplace_back(d2, (int)j);
         }
         keep_k();
       } else if (finite && lo[0] <= hi[0]) {
@@ -435,12 +439,13 @@ GMO_API void gmo_normals_knn(const float* pts4, int64_t n, int32_t k, double cel
             if (std::max<int64_t>(std::llabs(dx), std::max<int64_t>(std::llabs(dy), std::llabs(dz))) != sh) continue;
             auto it = grid.cells.find(HashGrid::key(c[0] + dx, c[1] + dy, c[2] + dz));
             if (it == grid.cells.end()) continue;
-            for (int j : it->second) nb.emplace_back(flann_d2(q, &p[j].x), j);
+            for (int j : it->second) { const float d2 = flann_d2(q, &p[j].x); if (d2 < max_r2) nb.emplace_back(d2, j); }
           }
           keep_k();
           // every unexplored point is at least sh * cell away (Chebyshev shell sh+1 or beyond)
           const double lim = (double)sh * grid.cell * 0.999;
           if ((int64_t)nb.size() >= k && (double)nb.back().first <= lim * lim) break;
+          if (capped && (double)max_r2 <= lim * lim) break;
         }
       }
       float* out = normals8 + i * 8;

@@ -77,14 +77,15 @@ def normals(pts, radius, mode=0, order=0, truth=False, nthreads=0):
     return out, cnt, tr
 
 
-def normals_knn(pts, k, cell=0.05, mode=0, nthreads=0, with_indices=False):
+def normals_knn(pts, k, cell=0.05, mode=0, nthreads=0, with_indices=False, max_radius=0.0):
     """k-nearest-neighbour normals (pcl::NormalEstimation::setKSearch).  -> normals8, count[, n x k neighbour indices]"""
     pts = _f32(pts)
     n = pts.shape[0]
     out = np.empty((n, 8), np.float32)
     cnt = np.empty(n, np.int32)
     idx = np.empty((n, k), np.int32) if with_indices else None
-    lib().gmo_normals_knn(_p(pts), C.c_int64(n), C.c_int32(k), C.c_double(cell), _p(out), _p(cnt), _p(idx), C.c_int(mode), C.c_int(nthreads))
+    lib().gmo_normals_knn(_p(pts), C.c_int64(n), C.c_int32(k), C.c_double(cell), _p(out), _p(cnt), _p(idx), C.c_int(mode), C.c_int(nthreads),
+                          C.c_double(max_radius))
     return (out, cnt, idx) if with_indices else (out, cnt)
 
 

@@ -176,18 +176,20 @@ def test_cuda_path_against_the_golden_fixture():
 
 
 # ---- k-nearest-neighbour normals (the north-star's "grid-hashed k-NN": pcl::NormalEstimation::setKSearch) ---------
-@pytest.mark.parametrize("n,k,radius,outliers", [(30_000, 16, 0.12, 0.05), (30_000, 32, 0.3, 0.0), (3_000, 8, 0.05, 0.3), (200, 64, 0.5, 0.0), (40, 64, 1.0, 0.0)])
-def test_knn_neighbour_sets_and_normals_bit_exact(n, k, radius, outliers):
+@pytest.mark.parametrize("n,k,radius,outliers,cap", [(30_000, 16, 0.12, 0.05, 0.0), (30_000, 32, 0.3, 0.0, 0.0), (3_000, 8, 0.05, 0.3, 0.0),
+                                                     (200, 64, 0.5, 0.0, 0.0), (40, 64, 1.0, 0.0, 0.0), (30_000, 16, 0.1, 0.05, 0.35),
+                                                     (30_000, 32, 0.2, 0.1, 0.15)])
+def test_knn_neighbour_sets_and_normals_bit_exact(n, k, radius, outliers, cap):
     """Neighbour index lists (in FLANN's result order) against the BRUTE-FORCE oracle, normals bit-identical.  The grid
     cell (neighborRadius) only sizes the search: dense stencils (pass A), sparse ones and outliers (pass B, block shells),
-    clouds smaller than k."""
+    clouds smaller than k; with and without a radius cap (the k nearest within `cap`, inside and beyond one cell)."""
     pts = synth.curved_tunnel(n, seed=61, outlier_frac=outliers)
     pts[3] = [np.nan, 0, 0, 1]
     pts[5:8] = pts[9]                      # duplicates: equal distances, tie broken by index
     cropped, _ = O.crop(pts, 5.0, True)
-    ref_n, ref_c, ref_i = O.normals_knn(cropped, k, cell=radius, mode=1, with_indices=True)
+    ref_n, ref_c, ref_i = O.normals_knn(cropped, k, cell=radius, mode=1, with_indices=True, max_radius=cap)
     with capi.Context(capi.default_params(neighborRadius=radius), max_points=n, max_hypotheses=4) as ctx:
-        ctx.set_knn(k, keep_indices=True)
+        ctx.set_knn(k, keep_indices=True, max_radius=cap)
         ctx.upload_scan(pts)
         ctx.crop()
         ctx.normals()
@@ -203,11 +205,12 @@ def test_knn_chain_c1_1m_k32_from_raw_points():
     """BASELINE configs[1] in k mode (k = 32): the whole chain from raw points against the oracle alone; in this
     mode the default path already sums in FLANN's order, so everything integer is exact without a special mode."""
     pts = synth.curved_tunnel(1_000_000, seed=2)
-    f = chain.front(pts, radius=0.07, leaf=0.1, knn=32)
+    f = chain.front(pts, radius=0.07, leaf=0.1, knn=32, knn_max_radius=0.25)
     nv = f["n_valid"]
+    assert nv < f["n_cropped"]   # the isolated outliers end with < 3 neighbours inside the cap and leave with the compaction
     ps, cs = synth.sample_indices(nv, 512, 3, seed=3), synth.sample_indices(nv, 512, 2, seed=4)
     b = chain.back(f, ps, cs, tau=TAU)
-    g = gpu_chain(pts, ps, cs, False, 0.07, 0.1, knn=32)
+    g = gpu_chain(pts, ps, cs, False, 0.07, 0.1, knn=32, knn_max_radius=0.25)
     m = chain.compare(g, f, b, exact_normals=True)
     _record("C1_1M_knn32", m)
     _assert_canonical(m)

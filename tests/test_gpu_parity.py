@@ -1295,7 +1295,7 @@ def test_graph_replay_reproduces_stream_launches_bit_for_bit():
             ctx.process_scan(ps, cs)
             ref.append(_scan_outputs(ctx))
         assert ctx.graph_stats() == (0, 0)
-    with _ctx(65_536, neighborRadius=0.12) as ctx:
+    with _ctx(65_536, neighborRadius=0.12) as ctx:   # default graph mode = auto: these scans are below the size threshold
         for i, pts in enumerate(scans):
             ctx.upload_scan(pts)
             ctx.process_scan(ps, cs)

@@ -638,38 +638,76 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 // ---- a2, k mode: pcl::NormalEstimation with setKSearch(k) (the north-star's "grid-hashed k-NN") ---------------------------
 // The k nearest points (FLANN L2_Simple distance, the query included, ties by ascending index) instead of the points
 // within a radius; the rest of the pipeline (single-pass covariance, eigen33, curvature, flip) is the same.
-// One thread per query keeps its k best (d2, index) pairs as 64-bit keys (d2 >= +0, so the float bits order like the
-// value) in a SORTED list in shared memory: a candidate is offered only if it beats the current k-th key, insertion
-// shifts the tail, and the finished list is already in FLANN's result order -- so the neighbours are summed in exactly
-// the order pcl::NormalEstimation sums them and the normals are bit-identical to the CPU oracle's in this mode.
+// One thread per query keeps its k best (d2, index) pairs as 64-bit keys in a max-heap in shared memory: a candidate is
+// offered only if it beats the current k-th key (the root); the finished heap is sorted into FLANN's result order, so
+// the neighbours are summed in exactly the order pcl::NormalEstimation sums them and the normals are bit-identical to
+// the CPU oracle's in this mode.
 //   pass A   the 27-cell stencil (the runs of the radius mode), only candidates nearer than one cell.  Complete iff k keys
 //            were found: nothing outside the stencil can be nearer.  (Size the grid -- neighborRadius -- near the expected
 //            distance of the k-th neighbour and almost every point ends here.)
-//   pass B1  (sparser neighbourhoods) restart: the stencil unfiltered, then rings 2..3 of cells through the block table;
-//            complete when the k-th distance is below the ring's distance.
+//   pass B1  (sparser neighbourhoods) the rest of the stencil, then rings 2, 3, .. of cells through the block table (as far as
+//            the radius cap, if there is one); complete when the k-th distance is below the ring's distance.
 //   pass B2  (isolated points) restart over whole 4x4x4-cell blocks in growing Chebyshev shells around the query's block
 //            -- a block is ONE contiguous run of the sorted cloud and an empty block costs one table read.
 constexpr int KNN_BLOCK = 64;
 constexpr int KNN_MAX = 64;
+constexpr int KNN_PEND = 8;  // accepted candidates wait here until ANY lane has 8: then the whole warp inserts at once
 
+// The k best (d2, index) keys of one query as a binary MAX-HEAP in shared memory (element j of this thread's heap is
+// slot[j * KNN_BLOCK]): the root is the current k-th key, an accepted candidate costs one sift of <= log2(k) steps -- a
+// sorted list costs up to k shifts per insertion, and with lanes inserting at different depths the warp ran that loop at
+// 4.6 active lanes for 68 % of all instructions (ncu, profiles/r02_knn.md).  sort() heap-sorts in place at the end: the
+// list is then in FLANN's result order (ascending distance, ties by index).
 struct KnnList {
-  unsigned long long* slot;  // element j of this thread's list is slot[j * KNN_BLOCK]
+  unsigned long long* slot;
   int K, cnt;
-  unsigned long long worst;  // the k-th key once the list is full, else "infinity"
+  unsigned long long worst;  // the root once the heap is full, else "infinity"
   __device__ __forceinline__ void reset() { cnt = 0; worst = ~0ull; }
-  __device__ __forceinline__ void offer(float d2, int id) {
-    const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
-    if (!(key < worst)) return;  // (NaN distances have the largest bit patterns: never accepted once the list is full)
-    int j = (cnt < K) ? cnt : K - 1;  // slot that becomes free: the new end, or the dropped k-th
-    while (j > 0) {
-      const unsigned long long v = slot[(j - 1) * KNN_BLOCK];
-      if (v <= key) break;
-      slot[j * KNN_BLOCK] = v;
-      --j;
+  __device__ __forceinline__ static unsigned long long make_key(float d2, int id) {
+    return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;  // d2 >= +0: the float bits order like the value
+  }
+  __device__ __forceinline__ void offer(float d2, int id) { offer_key(make_key(d2, id)); }
+  // sift `key` down from the root of the heap of the first n elements
+  __device__ __forceinline__ void sift_down(const unsigned long long key, int n) {
+    int j = 0;
+    for (;;) {
+      int c = 2 * j + 1;
+      if (c >= n) break;
+      unsigned long long vc = slot[c * KNN_BLOCK];
+      if (c + 1 < n) {
+        const unsigned long long v2 = slot[(c + 1) * KNN_BLOCK];
+        if (v2 > vc) { vc = v2; ++c; }
+      }
+      if (vc <= key) break;
+      slot[j * KNN_BLOCK] = vc;
+      j = c;
     }
     slot[j * KNN_BLOCK] = key;
-    if (cnt < K) ++cnt;
-    if (cnt == K) worst = slot[(K - 1) * KNN_BLOCK];
+  }
+  __device__ __forceinline__ void offer_key(const unsigned long long key) {
+    if (!(key < worst)) return;  // (NaN distances have the largest bit patterns: never accepted once the heap is full)
+    if (cnt < K) {               // grow: sift up
+      int j = cnt++;
+      while (j > 0) {
+        const int par = (j - 1) >> 1;
+        const unsigned long long v = slot[par * KNN_BLOCK];
+        if (v >= key) break;
+        slot[j * KNN_BLOCK] = v;
+        j = par;
+      }
+      slot[j * KNN_BLOCK] = key;
+      if (cnt == K) worst = slot[0];
+    } else {                     // replace the root (the k-th key so far)
+      sift_down(key, K);
+      worst = slot[0];
+    }
+  }
+  __device__ __forceinline__ void sort() {  // in-place heap sort: ascending keys
+    for (int n = cnt - 1; n > 0; --n) {
+      const unsigned long long last = slot[n * KNN_BLOCK];
+      slot[n * KNN_BLOCK] = slot[0];
+      sift_down(last, n);
+    }
   }
 };
 
@@ -689,34 +727,57 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
   const int orig = __float_as_int(p.w);
   float4 o0 = make_float4(qnan, qnan, qnan, 0.f), o1 = make_float4(qnan, 0.f, 0.f, 0.f);
   int cnt = 0, ncand = 0;
-  if (active && finite3(p.x, p.y, p.z)) {
-    KnnList L;
-    L.slot = knn_smem + threadIdx.x;
-    L.K = K;
-    L.reset();
-    const int U = st->n_cells, nf = st->n_sorted_finite;
-    const int cid = cell_id[i];
-    const int2* rr = runs + (size_t)cid * GRID_RUNS;
-    const int nr = cell_info[cid].x;
-    // ---- pass A: the 27-cell stencil; only candidates nearer than one cell can matter if this pass is to be complete
-    const float lim1 = (g.cell * 0.999f) * (g.cell * 0.999f);
-    for (int k = 0; k < nr; ++k) {
-      const int2 run = rr[k];
-      ncand += run.y - run.x;
-      for (int t = run.x; t < run.y; ++t) {
+  const bool work = active && finite3(p.x, p.y, p.z);
+  KnnList L;
+  L.slot = knn_smem + threadIdx.x;
+  L.K = K;
+  L.reset();
+  const int cid = work ? cell_id[i] : 0;
+  const int2* rr = runs + (size_t)cid * GRID_RUNS;
+  const int2 info = work ? cell_info[cid] : make_int2(0, 0);
+  const int nr = info.x, total = info.y;
+  // ---- pass A: the 27-cell stencil; only candidates nearer than one cell can matter if this pass is to be complete.
+  // Sorted insertion shifts up to k entries, and lanes insert at different moments: done naively the warp serialises
+  // them (measured: 68 % of all instructions in the shift loop at 4.6 active lanes).  So a candidate that beats the current
+  // k-th key only goes to a small per-lane pending buffer, and when ANY lane's buffer is full EVERY lane inserts its
+  // pending keys together -- the shifts of 32 lists run side by side.  (One flat, warp-uniform loop over the candidates, as
+  // in k_normals<0>; `worst` is a little stale between flushes, which only lets a few more candidates through.)
+  const float lim1 = (g.cell * 0.999f) * (g.cell * 0.999f);
+  {
+    unsigned long long* pend = knn_smem + (size_t)K * KNN_BLOCK + threadIdx.x;
+    int np = 0, maxtot = total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxtot = max(maxtot, __shfl_xor_sync(FULL, maxtot, o));
+    int k = 0, t = 0, end = 0;
+    int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
+    for (int it = 0; it < maxtot; ++it) {
+      if (it < total) {
+        if (t == end) { t = nxt.x; end = nxt.y; ++k; if (k < nr) nxt = rr[k]; }
         const float4 q = sp[t];
+        ++t;
         const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
         const float d2 = (dx * dx + dy * dy) + dz * dz;
-        if (d2 <= lim1 && d2 < max_r2) L.offer(d2, __float_as_int(q.w));
+        if (d2 <= lim1 && d2 < max_r2) {
+          const unsigned long long key = KnnList::make_key(d2, __float_as_int(q.w));
+          if (key < L.worst) { pend[np * KNN_BLOCK] = key; ++np; }
+        }
+      }
+      if (__any_sync(FULL, np == KNN_PEND)) {
+        for (int e = 0; e < np; ++e) L.offer_key(pend[e * KNN_BLOCK]);
+        np = 0;
       }
     }
+    for (int e = 0; e < np; ++e) L.offer_key(pend[e * KNN_BLOCK]);
+  }
+  if (work) {
+    const int U = st->n_cells, nf = st->n_sorted_finite;
+    ncand = total;
     // k keys, all within one cell of the query (the filter above) -- or the radius cap lies inside the stencil's reach
     bool complete = L.cnt == K || max_r2 <= lim1;
     if (!complete && nf > L.cnt) {
-      // ---- pass B1: growing rings of CELLS around the query's cell, unfiltered (ring <= 1 = the stencil again, this time
-      // with every candidate; ring k >= 2 = its rows through the block table).  After ring k every unexamined point is at
-      // least k cells away.  Sparse surface points end here (the k-th neighbour is within 2-3 cells).
-      L.reset();
+      // ---- pass B1: growing rings of CELLS around the query's cell.  The list was never full in pass A, so it holds EVERY
+      // stencil candidate nearer than one cell; the stencil is walked once more for the farther ones (d2 > lim1), then ring k >= 2 = its rows through the block table.  After ring k every
+      // unexamined point is at least k cells away.  Sparse surface points end here (the k-th neighbour is within 2-3 cells).
       int cx, cy, cz;
       gm_cell_of(g, p.x, p.y, p.z, cx, cy, cz);
       for (int k = 0; k < nr; ++k) {
@@ -725,7 +786,7 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
           const float4 q = sp[t];
           const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
           const float d2 = (dx * dx + dy * dy) + dz * dz;
-          if (d2 < max_r2) L.offer(d2, __float_as_int(q.w));
+          if (d2 > lim1 && d2 < max_r2) L.offer(d2, __float_as_int(q.w));
         }
       }
       auto done_at = [&](int ring) {  // the k-th neighbour, or the radius cap, lies inside what has been examined
@@ -830,6 +891,7 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
         if (L.cnt == K && __uint_as_float((unsigned)(L.worst >> 32)) <= lim * lim) break;
       }
     }
+    L.sort();
     cnt = L.cnt;
     if (knn_idx != nullptr)
       for (int j = 0; j < K; ++j) knn_idx[(size_t)orig * K + j] = j < cnt ? (int)(unsigned)L.slot[j * KNN_BLOCK] : -1;

@@ -25,6 +25,7 @@ ap.add_argument("--scans", type=int, default=4)
 ap.add_argument("--voxel-mode", type=int, default=0)
 ap.add_argument("--count-mode", type=int, default=0)
 ap.add_argument("--knn", type=int, default=0)
+ap.add_argument("--knn-cap", type=float, default=0.0)
 a = ap.parse_args()
 pts = synth.curved_tunnel(a.points, seed=2)
 prm = capi.default_params(neighborRadius=a.radius, voxelGridLeafSize=a.leaf)
@@ -32,7 +33,7 @@ with capi.Context(prm, max_points=a.points, max_hypotheses=max(a.hyp, 16)) as ct
     ctx.set_voxel_mode(a.voxel_mode)
     ctx.set_count_mode(a.count_mode)
     if a.knn:
-        ctx.set_knn(a.knn)
+        ctx.set_knn(a.knn, max_radius=a.knn_cap)
     ctx.upload_scan(pts)
     ctx.crop()
     ctx.normals()

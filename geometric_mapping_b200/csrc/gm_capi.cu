@@ -743,6 +743,7 @@ gm_status gm_crop(gm_ctx* ctx) {
   return GM_OK;
 }
 
+
 // ---- a2 + a3 ---------------------------------------------------------------------------------
 gm_status gm_normals(gm_ctx* ctx) {
   if (!ctx) return GM_ERR_INVALID_ARG;
@@ -782,7 +783,7 @@ gm_status gm_normals(gm_ctx* ctx) {
           }
           idx_out = ctx->d_knn_idx;
         }
-        k_normals_knn<<<div_up((long long)n, KNN_BLOCK), KNN_BLOCK, (size_t)(K + KNN_PEND) * KNN_BLOCK * sizeof(unsigned long long), ctx->stream>>>(
+        k_normals_knn<<<div_up((long long)n, KNN_BLOCK), KNN_BLOCK, (size_t)(K + KNN_AUX) * KNN_BLOCK * sizeof(unsigned long long), ctx->stream>>>(
             ctx->d_sorted, ctx->d_crop, ctx->d_cell_id, ctx->d_runs, ctx->d_cell_nruns, ctx->d_tab, ctx->d_ucell_start, n_ptr, g, K,
             ctx->knn_max_radius > 0.0 ? (float)(ctx->knn_max_radius * ctx->knn_max_radius) : HUGE_VALF, ctx->d_normals,
             ctx->d_nbr, ctx->d_sorted_valid, ctx->d_leaf_bounds, ctx->own, ctx->d_st, idx_out);

@@ -537,6 +537,57 @@ __device__ __forceinline__ void d_normals_epilogue(int i, bool active, const flo
   }
 }
 
+// ONE flat walk over the candidates of all runs of a cell (not a loop over runs with a loop over candidates inside): lanes of
+// a warp are points of neighbouring cells whose run lists differ, and the warp pays max-over-lanes of the TOTAL candidate
+// count instead of the sum of per-run maxima.  The next run is fetched one switch ahead so the switch itself does not wait
+// on memory.  Two candidates of the current run per trip (the second masked off when the run has one left): the run
+// bookkeeping is paid once per pair and the two loads are in flight together.  f(candidate as two 64-bit halves, valid).
+// (Issuing the loads of the NEXT pair before processing the current one
+// was measured on k_normals_knn: no gain.)
+template <class F>
+__device__ __forceinline__ void d_walk_runs(const float4* __restrict__ sp, const int2* __restrict__ rr, int nr, F&& f) {
+  const ulonglong2* __restrict__ sp2 = reinterpret_cast<const ulonglong2*>(sp);
+  int k = 0, t = 0, end = 0;
+  int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
+  for (;;) {
+    if (t >= end) {  // runs are non-empty by construction
+      if (k >= nr) break;
+      t = nxt.x; end = nxt.y;
+      ++k;
+      if (k < nr) nxt = rr[k];
+    }
+    const bool two = t + 1 < end;
+    // an odd run end re-reads the last candidate (masked off by `valid`): what lies past a run may be a non-finite point,
+    // and masked accumulation multiplies by zero -- 0 * NaN would poison the sums
+    const ulonglong2 q0 = __ldg(sp2 + t), q1 = __ldg(sp2 + t + (two ? 1 : 0));
+    t += 2;
+    f(q0, true);
+    f(q1, two);
+  }
+}
+
+// One candidate of the radius search: exact FLANN distance ((dx*dx + dy*dy) + dz*dz, every product and sum rounded on its
+// own: fma(d,d,+0) IS the rounded product), then the nine sums and the count with masked operands: a hit adds the candidate,
+// a miss adds +0 (no branch; same sums as a skipped add).  ptxas turns PREDICATED packed instructions into the packed
+// instruction plus two SELs, so masking three operands is the cheaper form.
+__device__ __forceinline__ void d_normals_accumulate(u64 pxy, float pz, const ulonglong2 q, float r2, bool valid, u64& a01, u64& a24, u64& a67,
+                                                     u64& a8c, float& a3, float& a5) {
+  float qx, qy, qz, qw, sx, sy;
+  d_unpack2(q.x, qx, qy); d_unpack2(q.y, qz, qw);
+  const u64 d = d_sub2(pxy, q.x);
+  d_unpack2(d_fma2(d, d, 0ull), sx, sy);
+  const float dz = pz - qz;
+  const float d2 = (sx + sy) + dz * dz;
+  const bool hit = valid && d2 < r2;
+  const float mx = hit ? qx : 0.f, my = hit ? qy : 0.f, mz = hit ? qz : 0.f, m1 = hit ? 1.0f : 0.f;
+  a01 = d_fma2(d_pack2(mx, mx), q.x, a01);  // xx, xy
+  a24 = d_fma2(d_pack2(mz, mz), q.x, a24);  // xz, yz
+  a3 = fmaf(my, qy, a3);
+  a5 = fmaf(mz, qz, a5);
+  a67 = d_add2(a67, d_pack2(mx, my));
+  a8c = d_add2(a8c, d_pack2(mz, m1));
+}
+
 // MODE 0 (default): neighbours are accumulated in cell-run order as they are found (fast; the sums differ from the
 //   oracle's by float rounding only -- the neighbour SET and count are exact).
 // MODE 1 (gm_set_normals_mode(1), verification): neighbours are accumulated in FLANN's result order, ascending
@@ -568,34 +619,10 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
       // carried as a float (exact below 2^24 neighbours) so that it shares an instruction with the z sum.
       u64 a01 = 0ull, a24 = 0ull, a67 = 0ull, a8c = 0ull;
       float a3 = 0.f, a5 = 0.f;
-      // ONE flat loop over the candidates of all runs (not a loop over runs with a loop over candidates
-      // inside): lanes of a warp are points of neighbouring cells whose run lists differ, and the warp
-      // pays max-over-lanes of the TOTAL candidate count instead of the sum of per-run maxima.
-      // The next run is fetched one switch ahead so the switch itself does not wait on memory.  A hit
-      // adds the candidate, a miss adds +0 (masked operands, no branch): same sums as a skipped add.
-      int k = 0, t = 0, end = 0;
-      int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
-#pragma unroll 2
-      for (int i = 0; i < total; ++i) {
-        if (t == end) {  // runs are non-empty by construction
-          t = nxt.x; end = nxt.y;
-          ++k;
-          if (k < nr) nxt = rr[k];
-        }
-        const float4 q = sp[t];
-        ++t;
-        float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-        float d2 = (dx * dx + dy * dy) + dz * dz;  // ((0+dx*dx)+dy*dy)+dz*dz, unfused
-        const bool hit = d2 < r2;
-        const float mx = hit ? q.x : 0.f, my = hit ? q.y : 0.f, mz = hit ? q.z : 0.f, m1 = hit ? 1.0f : 0.f;
-        const u64 qxy = d_pack2(q.x, q.y);
-        a01 = d_fma2(d_pack2(mx, mx), qxy, a01);  // xx, xy
-        a24 = d_fma2(d_pack2(mz, mz), qxy, a24);  // xz, yz
-        a3 = fmaf(my, q.y, a3);
-        a5 = fmaf(mz, q.z, a5);
-        a67 = d_add2(a67, d_pack2(mx, my));
-        a8c = d_add2(a8c, d_pack2(mz, m1));
-      }
+      const u64 pxy = d_pack2(p.x, p.y);
+      d_walk_runs(sp, rr, nr, [&](const ulonglong2 q, const bool valid) {
+        d_normals_accumulate(pxy, p.z, q, r2, valid, a01, a24, a67, a8c, a3, a5);
+      });
       float a0, a1, a2, a4, a6, a7, a8, cntf;
       d_unpack2(a01, a0, a1); d_unpack2(a24, a2, a4); d_unpack2(a67, a6, a7); d_unpack2(a8c, a8, cntf);
       cnt = (int)cntf;
@@ -649,15 +676,24 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 //            the radius cap, if there is one); complete when the k-th distance is below the ring's distance.
 //   pass B2  (isolated points) restart over whole 4x4x4-cell blocks in growing Chebyshev shells around the query's block
 //            -- a block is ONE contiguous run of the sorted cloud and an empty block costs one table read.
-constexpr int KNN_BLOCK = 64;
+constexpr int KNN_BLOCK = 64;  // 128 / 256 and smaller shared-memory carve-outs (more L1) were measured slower (profiles/r02_knn.md)
 constexpr int KNN_MAX = 64;
-constexpr int KNN_PEND = 8;  // accepted candidates wait here until ANY lane has 8: then the whole warp inserts at once
+constexpr int KNN_BINS = 32;  // histogram bins of pass A (u32 each) ...
+constexpr int KNN_AUX = 16;   // ... overlaid by the boundary buffer (u64 each): the same KNN_BINS * 4 bytes per thread
 
+// the FLANN L2_Simple distance of the radius kernel: ((dx*dx + dy*dy) + dz*dz), every product and sum rounded on its own
+__device__ __forceinline__ float d_flann_d2(u64 pxy, float pz, const ulonglong2 q) {
+  float sx, sy, qz, qw;
+  const u64 d = d_sub2(pxy, q.x);
+  d_unpack2(d_fma2(d, d, 0ull), sx, sy);
+  d_unpack2(q.y, qz, qw);
+  const float dz = pz - qz;
+  return (sx + sy) + dz * dz;
+}
 // The k best (d2, index) keys of one query as a binary MAX-HEAP in shared memory (element j of this thread's heap is
-// slot[j * KNN_BLOCK]): the root is the current k-th key, an accepted candidate costs one sift of <= log2(k) steps -- a
-// sorted list costs up to k shifts per insertion, and with lanes inserting at different depths the warp ran that loop at
-// 4.6 active lanes for 68 % of all instructions (ncu, profiles/r02_knn.md).  sort() heap-sorts in place at the end: the
-// list is then in FLANN's result order (ascending distance, ties by index).
+// slot[j * KNN_BLOCK]): the root is the current k-th key, an accepted candidate costs one sift of <= log2(k) steps (the
+// sparse-neighbourhood passes B1/B2 insert this way; pass A selects without inserting, see the kernel).  sort() heap-sorts
+// in place at the end: the list is then in FLANN's result order (ascending distance, ties by index).
 struct KnnList {
   unsigned long long* slot;
   int K, cnt;
@@ -668,8 +704,7 @@ struct KnnList {
   }
   __device__ __forceinline__ void offer(float d2, int id) { offer_key(make_key(d2, id)); }
   // sift `key` down from the root of the heap of the first n elements
-  __device__ __forceinline__ void sift_down(const unsigned long long key, int n) {
-    int j = 0;
+  __device__ __forceinline__ void sift_down(const unsigned long long key, int n, int j = 0) {
     for (;;) {
       int c = 2 * j + 1;
       if (c >= n) break;
@@ -701,6 +736,10 @@ struct KnnList {
       sift_down(key, K);
       worst = slot[0];
     }
+  }
+  __device__ __forceinline__ void heapify() {  // make the first cnt slots (any order) a heap
+    for (int j = (cnt >> 1) - 1; j >= 0; --j) sift_down(slot[j * KNN_BLOCK], cnt, j);
+    worst = (cnt == K) ? slot[0] : ~0ull;
   }
   __device__ __forceinline__ void sort() {  // in-place heap sort: ascending keys
     for (int n = cnt - 1; n > 0; --n) {
@@ -737,37 +776,75 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
   const int2 info = work ? cell_info[cid] : make_int2(0, 0);
   const int nr = info.x, total = info.y;
   // ---- pass A: the 27-cell stencil; only candidates nearer than one cell can matter if this pass is to be complete.
-  // Sorted insertion shifts up to k entries, and lanes insert at different moments: done naively the warp serialises
-  // them (measured: 68 % of all instructions in the shift loop at 4.6 active lanes).  So a candidate that beats the current
-  // k-th key only goes to a small per-lane pending buffer, and when ANY lane's buffer is full EVERY lane inserts its
-  // pending keys together -- the shifts of 32 lists run side by side.  (One flat, warp-uniform loop over the candidates, as
-  // in k_normals<0>; `worst` is a little stale between flushes, which only lets a few more candidates through.)
+  // Keeping the k best in a heap WHILE walking costs a data-dependent sift per accepted candidate, and the lanes of a warp
+  // accept at different moments: even with per-lane pending buffers the warp ran those loops a few lanes at a time
+  // (profiles/r02_knn.md).  So pass A SELECTS instead, with two uniform walks over the same candidates:
+  //   walk 1  histogram of d2 in KNN_BINS equal bins over [0, one cell]^2 (bin index is monotone in d2, equal d2 -> equal bin);
+  //           the bin b* in which the running count reaches k holds the k-th neighbour: everything in a lower bin is in.
+  //   walk 2  keys of the lower bins go straight into the list, keys of bin b* into a small boundary buffer (it overlays
+  //           the histogram); the k - |lower| smallest boundary keys complete the list.
+  // No walk contains a data-dependent loop.  The list is then made a heap for the later passes / the final sort.
+  // (More than KNN_AUX keys in the boundary bin -- coincident points -- : that lane falls back to heap insertion.)
   const float lim1 = (g.cell * 0.999f) * (g.cell * 0.999f);
   {
-    unsigned long long* pend = knn_smem + (size_t)K * KNN_BLOCK + threadIdx.x;
-    int np = 0, maxtot = total;
+    unsigned long long* bnd = knn_smem + (size_t)K * KNN_BLOCK + threadIdx.x;  // [KNN_AUX][KNN_BLOCK] u64: this thread's words ...
+    unsigned* hist32 = reinterpret_cast<unsigned*>(bnd);                       // ... and the same words as 2 x u32 bins each
+    auto hist_at = [&](int bq) -> unsigned& { return hist32[(((bq >> 1) * KNN_BLOCK) << 1) | (bq & 1)]; };
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxtot = max(maxtot, __shfl_xor_sync(FULL, maxtot, o));
-    int k = 0, t = 0, end = 0;
-    int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
-    for (int it = 0; it < maxtot; ++it) {
-      if (it < total) {
-        if (t == end) { t = nxt.x; end = nxt.y; ++k; if (k < nr) nxt = rr[k]; }
-        const float4 q = sp[t];
-        ++t;
-        const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-        const float d2 = (dx * dx + dy * dy) + dz * dz;
-        if (d2 <= lim1 && d2 < max_r2) {
-          const unsigned long long key = KnnList::make_key(d2, __float_as_int(q.w));
-          if (key < L.worst) { pend[np * KNN_BLOCK] = key; ++np; }
+    for (int j = 0; j < KNN_AUX; ++j) bnd[j * KNN_BLOCK] = 0ull;
+    const float binscale = (float)KNN_BINS / lim1;
+    const u64 pxy = d_pack2(p.x, p.y);
+    d_walk_runs(sp, rr, nr, [&](const ulonglong2 q, const bool valid) {
+      const float d2 = d_flann_d2(pxy, p.z, q);
+      if (valid && d2 <= lim1 && d2 < max_r2) hist_at(min((int)(d2 * binscale), KNN_BINS - 1)) += 1u;
+    });
+    int bstar = KNN_BINS, below = 0, cum = 0;
+#pragma unroll 4
+    for (int bq = 0; bq < KNN_BINS; ++bq) {
+      const int c = (int)hist_at(bq);
+      if (bstar == KNN_BINS && cum + c >= K) { bstar = bq; below = cum; }
+      cum += c;
+    }
+    // fewer than k candidates within one cell: all of them are in (bstar stays KNN_BINS), the later passes go on
+    int c = 0, m = 0;
+    bool ovf = false;
+    d_walk_runs(sp, rr, nr, [&](const ulonglong2 q, const bool valid) {
+      const float d2 = d_flann_d2(pxy, p.z, q);
+      if (valid && d2 <= lim1 && d2 < max_r2) {
+        const int bq = min((int)(d2 * binscale), KNN_BINS - 1);
+        const unsigned long long key = KnnList::make_key(d2, (int)(unsigned)(q.y >> 32));
+        if (bq < bstar) { L.slot[c * KNN_BLOCK] = key; ++c; }
+        else if (bq == bstar) {
+          if (m < KNN_AUX) { bnd[m * KNN_BLOCK] = key; ++m; } else ovf = true;
         }
       }
-      if (__any_sync(FULL, np == KNN_PEND)) {
-        for (int e = 0; e < np; ++e) L.offer_key(pend[e * KNN_BLOCK]);
-        np = 0;
+    });
+    if (!ovf) {
+      const int need = (bstar < KNN_BINS) ? K - below : 0;  // 1 <= need <= m
+      for (int s = 0; s < need; ++s) {                        // the `need` smallest boundary keys, by selection
+        int best = s;
+        unsigned long long bk = bnd[s * KNN_BLOCK];
+        for (int j = s + 1; j < m; ++j) {
+          const unsigned long long v = bnd[j * KNN_BLOCK];
+          if (v < bk) { bk = v; best = j; }
+        }
+        bnd[best * KNN_BLOCK] = bnd[s * KNN_BLOCK];
+        L.slot[(c + s) * KNN_BLOCK] = bk;
+      }
+      L.cnt = c + need;
+      L.heapify();
+    } else {
+      L.reset();
+      for (int k = 0; k < nr; ++k) {
+        const int2 run = rr[k];
+        for (int t = run.x; t < run.y; ++t) {
+          const float4 q = sp[t];
+          const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+          const float d2 = (dx * dx + dy * dy) + dz * dz;
+          if (d2 <= lim1 && d2 < max_r2) L.offer(d2, __float_as_int(q.w));
+        }
       }
     }
-    for (int e = 0; e < np; ++e) L.offer_key(pend[e * KNN_BLOCK]);
   }
   if (work) {
     const int U = st->n_cells, nf = st->n_sorted_finite;

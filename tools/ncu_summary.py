@@ -1,5 +1,5 @@
 """Summarise an `ncu --set full` report (exported with `ncu -i X.ncu-rep --page raw --csv`) as a markdown
-table + per-kernel DRAM traffic JSON.   python tools/ncu_summary.py raw.csv out.md [traffic.json]"""
+table + per-kernel DRAM traffic JSON.   python tools/ncu_summary.py raw.csv out.md [traffic.json] [last_n_launches]"""
 import csv, json, sys, collections
 
 COLS = [("gpu__time_duration.sum", "us", 1.0), ("launch__grid_size", "grid", 1), ("launch__block_size", "block", 1),
@@ -27,9 +27,10 @@ def main():
     idx = {h: i for i, h in enumerate(hdr)}
     out = ["| kernel | " + " | ".join(c[1] for c in COLS) + " |", "|---|" + "---|" * len(COLS)]
     traffic = collections.OrderedDict()
-    for r in rows[2:]:
-        if len(r) < len(hdr):
-            continue
+    body = [r for r in rows[2:] if len(r) >= len(hdr)]
+    if len(sys.argv) > 4:
+        body = body[-int(sys.argv[4]):]   # the last N launches = one steady-state scan
+    for r in body:
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("gm::", "")
         cells = []
         for key, label, _ in COLS:
@@ -51,7 +52,7 @@ def main():
             b = sc(rd, units[idx["dram__bytes_read.sum"]]) + sc(wr, units[idx["dram__bytes_write.sum"]])
             traffic.setdefault(name, []).append(b)
     open(sys.argv[2], "a").write("\n".join(out) + "\n")
-    if len(sys.argv) > 3:
+    if len(sys.argv) > 3 and sys.argv[3] != "-":
         json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(sys.argv[3], "w"), indent=1)
 
 

@@ -444,7 +444,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   ctx->stream = ctx->own_stream;
 #define A(ptr, count) if ((e = dmalloc(&ctx->ptr, (count))) != cudaSuccess) return fail(e, #ptr)
-  A(d_in, N); A(d_crop, N); A(d_sorted, N); A(d_cloud_c, N);
+  A(d_in, N); A(d_crop, N); A(d_sorted, N + 1); A(d_cloud_c, N);  // d_walk_runs reads candidates in pairs: one element of slack
   A(d_sorted_valid, N); A(d_leaf_bounds, 2 * ((N + 31) / 32));
   A(d_normals, 2 * N); A(d_normals_c, 2 * N); A(d_centroid, N); A(d_nn_normal, 2 * N);
   A(d_keys[0], N); A(d_keys[1], N); A(d_vals[0], N); A(d_vals[1], N);

@@ -550,16 +550,18 @@ __device__ __forceinline__ void d_walk_runs(const float4* __restrict__ sp, const
   int k = 0, t = 0, end = 0;
   int2 nxt = (nr > 0) ? rr[0] : make_int2(0, 0);
   for (;;) {
-    if (t >= end) {  // runs are non-empty by construction
-      if (k >= nr) break;
-      t = nxt.x; end = nxt.y;
-      ++k;
-      if (k < nr) nxt = rr[k];
-    }
+    const bool sw = t >= end;  // runs are non-empty by construction
+    if (sw && k >= nr) break;
+    // the switch itself without a branch (lanes switch at different trips: a branch here ran in 42 % of the trips with 9
+    // of 32 lanes active)
+    t = sw ? nxt.x : t;
+    end = sw ? nxt.y : end;
+    k += sw ? 1 : 0;
+    if (sw && k < nr) nxt = __ldg(rr + k);
+    // an odd run end reads one element past the run (masked off by `valid`): `sp` has one element of slack past the last
+    // point, and f must not let the contents of an invalid candidate reach its sums (it may be a non-finite point)
+    const ulonglong2 q0 = __ldg(sp2 + t), q1 = __ldg(sp2 + t + 1);
     const bool two = t + 1 < end;
-    // an odd run end re-reads the last candidate (masked off by `valid`): what lies past a run may be a non-finite point,
-    // and masked accumulation multiplies by zero -- 0 * NaN would poison the sums
-    const ulonglong2 q0 = __ldg(sp2 + t), q1 = __ldg(sp2 + t + (two ? 1 : 0));
     t += 2;
     f(q0, true);
     f(q1, two);
@@ -579,12 +581,15 @@ __device__ __forceinline__ void d_normals_accumulate(u64 pxy, float pz, const ul
   const float dz = pz - qz;
   const float d2 = (sx + sy) + dz * dz;
   const bool hit = valid && d2 < r2;
+  // BOTH factors of every product are the masked values (equal to the candidate's on a hit): whatever an invalid slot
+  // holds -- a non-finite point past the end of a run -- never reaches an accumulator (0 * NaN would poison it)
   const float mx = hit ? qx : 0.f, my = hit ? qy : 0.f, mz = hit ? qz : 0.f, m1 = hit ? 1.0f : 0.f;
-  a01 = d_fma2(d_pack2(mx, mx), q.x, a01);  // xx, xy
-  a24 = d_fma2(d_pack2(mz, mz), q.x, a24);  // xz, yz
-  a3 = fmaf(my, qy, a3);
-  a5 = fmaf(mz, qz, a5);
-  a67 = d_add2(a67, d_pack2(mx, my));
+  const u64 mxy = d_pack2(mx, my);
+  a01 = d_fma2(d_pack2(mx, mx), mxy, a01);  // xx, xy
+  a24 = d_fma2(d_pack2(mz, mz), mxy, a24);  // xz, yz
+  a3 = fmaf(my, my, a3);
+  a5 = fmaf(mz, mz, a5);
+  a67 = d_add2(a67, mxy);
   a8c = d_add2(a8c, d_pack2(mz, m1));
 }
 

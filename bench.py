@@ -584,8 +584,8 @@ def main():
                     "frac": nrm_tflops / fp32_peak_tflops, "traffic": traffic.get("k_normals<0>"), "ms_per_step": nrm_ms,
                     "kernels": "k_normals<0>",
                     "algorithmic": f"8 flop x {cand_per_scan:.0f} stencil candidates + 15 flop x {nbr_per_scan:.0f} neighbours + 150 flop x "
-                                   f"{M:.0f} points; the kernel is instruction-issue bound (ncu: ~73 % of issue slots active, ~30 "
-                                   f"instructions per candidate of which 8 are these flops)",
+                                   f"{M:.0f} points; the kernel is instruction-issue bound (ncu: ~77 % of issue slots active, ~26 "
+                                   f"instructions per candidate slot of which 8 are these flops)",
                     "points_per_s": M / (nrm_ms * 1e-3) if nrm_ms > 0 else 0.0, "peak_source": fp32_src},
         "inlier_count": {"bound": "fp32", "achieved": count_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": count_tflops / fp32_peak_tflops, "traffic": tsum("k_count_tiles<0>", "k_count_tiles<1>"), "ms_per_step": count_ms,

@@ -542,8 +542,8 @@ __device__ __forceinline__ void d_normals_epilogue(int i, bool active, const flo
 // count instead of the sum of per-run maxima.  The next run is fetched one switch ahead so the switch itself does not wait
 // on memory.  Two candidates of the current run per trip (the second masked off when the run has one left): the run
 // bookkeeping is paid once per pair and the two loads are in flight together.  f(candidate as two 64-bit halves, valid).
-// (Issuing the loads of the NEXT pair before processing the current one
-// was measured on k_normals_knn: no gain.)
+// (Issuing the loads of the NEXT pair before processing the current one was measured: k_normals<0> 0.204 -> 0.222 ms, no
+// change for k_normals_knn.)
 template <class F>
 __device__ __forceinline__ void d_walk_runs(const float4* __restrict__ sp, const int2* __restrict__ rr, int nr, F&& f) {
   const ulonglong2* __restrict__ sp2 = reinterpret_cast<const ulonglong2*>(sp);

@@ -684,7 +684,8 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 constexpr int KNN_BLOCK = 64;  // 128 / 256 and smaller shared-memory carve-outs (more L1) were measured slower (profiles/r02_knn.md)
 constexpr int KNN_MAX = 64;
 constexpr int KNN_BINS = 32;  // histogram bins of pass A (u32 each) ...
-constexpr int KNN_AUX = 16;   // ... overlaid by the boundary buffer (u64 each): the same KNN_BINS * 4 bytes per thread
+constexpr int KNN_BND = 16;   // ... overlaid by the boundary buffer (u64 each): the same KNN_BINS * 4 bytes per thread
+constexpr int KNN_AUX = KNN_BND + 1;  // + one word that takes what is not wanted (bin KNN_BINS / slot KNN_BND): no branch in the walks
 
 // the FLANN L2_Simple distance of the radius kernel: ((dx*dx + dy*dy) + dz*dz), every product and sum rounded on its own
 __device__ __forceinline__ float d_flann_d2(u64 pxy, float pz, const ulonglong2 q) {
@@ -789,7 +790,9 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
   //   walk 2  keys of the lower bins go straight into the list, keys of bin b* into a small boundary buffer (it overlays
   //           the histogram); the k - |lower| smallest boundary keys complete the list.
   // No walk contains a data-dependent loop.  The list is then made a heap for the later passes / the final sort.
-  // (More than KNN_AUX keys in the boundary bin -- coincident points -- : that lane falls back to heap insertion.)
+  // Neither walk branches on the candidate: a candidate that does not count increments a spare bin, a key that is not kept is
+  // stored to a spare word (divergent branches in a flat walk cost k_normals<0> 10 %).
+  // (More than KNN_BND keys in the boundary bin -- coincident points -- : that lane falls back to heap insertion.)
   const float lim1 = (g.cell * 0.999f) * (g.cell * 0.999f);
   {
     unsigned long long* bnd = knn_smem + (size_t)K * KNN_BLOCK + threadIdx.x;  // [KNN_AUX][KNN_BLOCK] u64: this thread's words ...
@@ -801,7 +804,8 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
     const u64 pxy = d_pack2(p.x, p.y);
     d_walk_runs(sp, rr, nr, [&](const ulonglong2 q, const bool valid) {
       const float d2 = d_flann_d2(pxy, p.z, q);
-      if (valid && d2 <= lim1 && d2 < max_r2) hist_at(min((int)(d2 * binscale), KNN_BINS - 1)) += 1u;
+      const bool elig = valid && d2 <= lim1 && d2 < max_r2;
+      hist_at(elig ? min((int)(d2 * binscale), KNN_BINS - 1) : KNN_BINS) += 1u;
     });
     int bstar = KNN_BINS, below = 0, cum = 0;
 #pragma unroll 4
@@ -815,14 +819,13 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
     bool ovf = false;
     d_walk_runs(sp, rr, nr, [&](const ulonglong2 q, const bool valid) {
       const float d2 = d_flann_d2(pxy, p.z, q);
-      if (valid && d2 <= lim1 && d2 < max_r2) {
-        const int bq = min((int)(d2 * binscale), KNN_BINS - 1);
-        const unsigned long long key = KnnList::make_key(d2, (int)(unsigned)(q.y >> 32));
-        if (bq < bstar) { L.slot[c * KNN_BLOCK] = key; ++c; }
-        else if (bq == bstar) {
-          if (m < KNN_AUX) { bnd[m * KNN_BLOCK] = key; ++m; } else ovf = true;
-        }
-      }
+      const bool elig = valid && d2 <= lim1 && d2 < max_r2;
+      const int bq = min((int)(d2 * binscale), KNN_BINS - 1);
+      const bool lower = elig && bq < bstar, isb = elig && bq == bstar, fits = isb && m < KNN_BND;
+      L.slot[(lower ? c : K + (fits ? m : KNN_BND)) * KNN_BLOCK] = KnnList::make_key(d2, (int)(unsigned)(q.y >> 32));
+      c += lower ? 1 : 0;
+      m += fits ? 1 : 0;
+      ovf = ovf || (isb && !fits);
     });
     if (!ovf) {
       const int need = (bstar < KNN_BINS) ? K - below : 0;  // 1 <= need <= m

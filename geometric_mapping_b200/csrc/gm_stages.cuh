@@ -681,8 +681,10 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 //            the radius cap, if there is one); complete when the k-th distance is below the ring's distance.
 //   pass B2  (isolated points) restart over whole 4x4x4-cell blocks in growing Chebyshev shells around the query's block
 //            -- a block is ONE contiguous run of the sorted cloud and an empty block costs one table read.
-constexpr int KNN_BLOCK = 64;  // 128 / 256 and smaller shared-memory carve-outs (more L1) were measured slower (profiles/r02_knn.md)
+constexpr int KNN_BLOCK = 32;  // ONE warp per block: a warp held up by a sparse query (pass B) keeps only its own shared memory
+                               // (64: 3.1 ms, 128 / 256: 3.6 / 4.1 ms; smaller carve-outs for more L1: slower, profiles/r02_knn.md)
 constexpr int KNN_MAX = 64;
+constexpr int KNN_WIDE = 4;  // 8: same time at 78 registers
 constexpr int KNN_BINS = 32;  // histogram bins of pass A (u32 each) ...
 constexpr int KNN_BND = 16;   // ... overlaid by the boundary buffer (u64 each): the same KNN_BINS * 4 bytes per thread
 constexpr int KNN_AUX = KNN_BND + 1;  // + one word that takes what is not wanted (bin KNN_BINS / slot KNN_BND): no branch in the walks
@@ -856,6 +858,21 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
   }
   if (work) {
     const int U = st->n_cells, nf = st->n_sorted_finite;
+    // The candidates of a sorted-position range, KNN_WIDE loads in flight at a time: a sparse query runs these loops with the
+    // rest of its warp waiting, and one dependent load per candidate was most of what it cost.
+    auto offer_range = [&](int t0, int t1) {
+      for (int t = t0; t < t1; t += 4) {
+        float4 q4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q4[u] = sp[min(t + u, t1 - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float ex = p.x - q4[u].x, ey = p.y - q4[u].y, ez = p.z - q4[u].z;
+          const float e2 = (ex * ex + ey * ey) + ez * ez;
+          if (t + u < t1 && e2 < max_r2) L.offer(e2, __float_as_int(q4[u].w));
+        }
+      }
+    };
     ncand = total;
     // k keys, all within one cell of the query (the filter above) -- or the radius cap lies inside the stencil's reach
     bool complete = L.cnt == K || max_r2 <= lim1;
@@ -865,14 +882,12 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
       // unexamined point is at least k cells away.  Sparse surface points end here (the k-th neighbour is within 2-3 cells).
       int cx, cy, cz;
       gm_cell_of(g, p.x, p.y, p.z, cx, cy, cz);
-      for (int k = 0; k < nr; ++k) {
-        const int2 run = rr[k];
-        for (int t = run.x; t < run.y; ++t) {
-          const float4 q = sp[t];
-          const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-          const float d2 = (dx * dx + dy * dy) + dz * dz;
-          if (d2 > lim1 && d2 < max_r2) L.offer(d2, __float_as_int(q.w));
-        }
+      {
+        const u64 pxy = d_pack2(p.x, p.y);
+        d_walk_runs(sp, rr, nr, [&](const ulonglong2 q, const bool valid) {
+          const float d2 = d_flann_d2(pxy, p.z, q);
+          if (valid && d2 > lim1 && d2 < max_r2) L.offer(d2, (int)(unsigned)(q.y >> 32));
+        });
       }
       auto done_at = [&](int ring) {  // the k-th neighbour, or the radius cap, lies inside what has been examined
         const float lim = (float)ring * g.cell * 0.999f;
@@ -903,12 +918,7 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
             const int xe = min(x1, xs | 3);
             const int2 seg = cell_segment(g, tab, ucell_start, U, nf, xs, xe, yy, zz);
             ncand += seg.y - seg.x;
-            for (int tt = seg.x; tt < seg.y; ++tt) {
-              const float4 q = sp[tt];
-              const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
-              const float e2 = (ex * ex + ey * ey) + ez * ez;
-              if (e2 < max_r2) L.offer(e2, __float_as_int(q.w));
-            }
+            offer_range(seg.x, seg.y);
             xs = xe + 1;
           }
         }
@@ -962,11 +972,7 @@ k_normals_knn(const float4* __restrict__ sp, const float4* __restrict__ crop, co
                 if ((ddx * ddx + ddy * ddy) + ddz * ddz > cur) continue;
                 const int t0 = min(ucell_start[c_id], nf), t1 = (c_id + 1 < U) ? min(ucell_start[c_id + 1], nf) : nf;
                 ncand += t1 - t0;
-                for (int t = t0; t < t1; ++t) {
-                  const float4 q = sp[t];
-                  const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
-                  L.offer((ex * ex + ey * ey) + ez * ez, __float_as_int(q.w));
-                }
+                offer_range(t0, t1);
               }
             }
           }

@@ -699,7 +699,10 @@ def main():
         assert last.counts.n_input == n and last.counts.device_error == 0 and last.counts.n_voxels <= VCAP
         return secs
 
-    e2e_s = run_e2e(samples, a.steps)
+    # the host side of this leg (pinned-memory traffic of a shared box) is the noisy part of the whole bench: K steps are timed
+    # three times and the MEDIAN is reported (all three are kept in e2e.repeats_ms_per_step)
+    e2e_runs = sorted(run_e2e(samples, a.steps) for _ in range(3))
+    e2e_s = e2e_runs[1]
     e2e_value = world * n * a.steps / e2e_s
     e2e4_s = run_e2e(samples4, steps4)
     e2es_s = run_e2e(samples, a.steps, outs_small)
@@ -898,7 +901,7 @@ def main():
             "latency_ms_per_scan": latency_ms,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / a.steps,
+                    "ms_per_step": 1e3 * e2e_s / a.steps, "repeats_ms_per_step": [1e3 * t / a.steps for t in e2e_runs],
                     "pipeline": f"{NCTX} contexts / streams, pinned host buffers; up: 12-byte xyz records (gm_upload_pointcloud2); down: "
                                 f"summary, compacted cloud (16 B/pt), labels, polyline, voxel centroids + 1-NN normals",
                     "numa_node_rank0": numa_node},

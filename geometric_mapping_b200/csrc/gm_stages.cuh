@@ -684,7 +684,7 @@ k_normals(const float4* __restrict__ sp, const int* __restrict__ cell_id, const 
 constexpr int KNN_BLOCK = 32;  // ONE warp per block: a warp held up by a sparse query (pass B) keeps only its own shared memory
                                // (64: 3.1 ms, 128 / 256: 3.6 / 4.1 ms; smaller carve-outs for more L1: slower, profiles/r02_knn.md)
 constexpr int KNN_MAX = 64;
-constexpr int KNN_WIDE = 4;  // 8: same time at 78 registers
+constexpr int KNN_WIDE = 4;  // 8: same time
 constexpr int KNN_BINS = 32;  // histogram bins of pass A (u32 each) ...
 constexpr int KNN_BND = 16;   // ... overlaid by the boundary buffer (u64 each): the same KNN_BINS * 4 bytes per thread
 constexpr int KNN_AUX = KNN_BND + 1;  // + one word that takes what is not wanted (bin KNN_BINS / slot KNN_BND): no branch in the walks

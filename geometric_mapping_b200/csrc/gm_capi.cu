@@ -2,6 +2,7 @@
 // There is no CPU fallback anywhere in this file: every stage is a sequence of CUDA kernel
 // launches on the ctx stream, and gm_create() fails without a device.
 #include "../../include/gm_capi.h"
+#include "gm_sort.cuh"
 #include "gm_ransac.cuh"
 #include "gm_polyline.cuh"
 #include "gm_compress.cuh"
@@ -127,7 +128,8 @@ struct gm_ctx {
   unsigned char* d_labels = nullptr;
   unsigned long long* d_state64 = nullptr;
   unsigned long long* d_state64_b = nullptr;  // tile states of the cylinder-refit compaction (may run concurrently with the voxel branch)
-  unsigned *d_rs_hist = nullptr, *d_rs_totals = nullptr;  // [256][tiles] tile histograms / row prefixes, [256] row totals
+  unsigned *d_rs_hist = nullptr, *d_rs_totals = nullptr;  // segment histograms [segments][256] (round-1 tile form: [256][tiles] + [256] row totals)
+  Rs2Aux* d_rs_aux = nullptr;                              // group sums / totals / completion counter of one pass; zero between passes
   size_t rs_hist_words = 0;
   TileCtl* d_ctl = nullptr;      // [3] launch control of the look-back kernels: d_state64 | d_state64_b | d_dense_state
   size_t n_grid = 0;             // n_input rounded up to a bucket: what grids are sized by (kernels read the true n on the device)
@@ -350,11 +352,24 @@ gm_status radix_sort_t(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int passes, 
   GM_CHECK_LAUNCHES(ctx);
   return GM_OK;
 }
+// Default: the segment form of gm_sort.cuh (byte-counter histograms, <= 592 segments, balanced digits of <= 8 bits, 2 launches per pass).
+// GM_SORT_V1=1 selects round 1's tile form (kept for A/B timing: tools/microbench/sort_v2.cu, bench.py --sort-v1).
 gm_status radix_sort(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int key_bits, int* result_buf) {
-  int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
-  static const int kForce = [] { const char* e = std::getenv("GM_SORT_IPT"); return e ? std::atoi(e) : 0; }();
-  const bool small = kForce ? kForce == 4 : n_cap <= (size_t)kSmallSortKeys;
-  return small ? radix_sort_t<4>(ctx, n_ptr, n_cap, passes, result_buf) : radix_sort_t<8>(ctx, n_ptr, n_cap, passes, result_buf);
+  static const bool kV1 = [] { const char* e = std::getenv("GM_SORT_V1"); return e && std::atoi(e) != 0; }();
+  if (kV1) {
+    int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
+    static const int kForce = [] { const char* e = std::getenv("GM_SORT_IPT"); return e ? std::atoi(e) : 0; }();
+    const bool small = kForce ? kForce == 4 : n_cap <= (size_t)kSmallSortKeys;
+    return small ? radix_sort_t<4>(ctx, n_ptr, n_cap, passes, result_buf) : radix_sort_t<8>(ctx, n_ptr, n_cap, passes, result_buf);
+  }
+  const Rs2Plan plan = rs2_plan(n_cap, key_bits);
+  if ((size_t)plan.segments * 256 > ctx->rs_hist_words) { ctx->err = "radix histogram capacity"; return GM_ERR_CAPACITY; }
+  unsigned* const keys[2] = {ctx->d_keys[0], ctx->d_keys[1]};
+  unsigned* const vals[2] = {ctx->d_vals[0], ctx->d_vals[1]};
+  *result_buf = rs2_sort(ctx->stream, keys, vals, n_ptr, n_cap, key_bits, ctx->d_rs_hist, ctx->d_rs_aux, nullptr);
+  ctx->launches += 2 * plan.passes;
+  GM_CHECK_LAUNCHES(ctx);
+  return GM_OK;
 }
 
 gm_status sync_state(gm_ctx* ctx, DevState* host) {
@@ -454,7 +469,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_labels, N);
   A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
   ctx->rs_hist_words = (size_t)div_up((long long)N, RS_BLOCK * 4) * 256;  // sized for the smaller tile
-  A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256);
+  A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256); A(d_rs_aux, 1);
   A(d_st, 1); A(d_ctl, 3); A(d_frame_sums, 8);
   A(d_partials, 3 * kPartialsRegion);  // 3 regions: frame | plane refit | cylinder GN (may run concurrently)
   A(d_frame, 1);
@@ -470,6 +485,7 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   for (int k = 0; k < 2; ++k)
     if ((e = cudaEventCreateWithFlags(&ctx->ev_samples[k], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
   if ((e = cudaMemset(ctx->d_st, 0, sizeof(DevState))) != cudaSuccess) return fail(e, "memset");
+  if ((e = cudaMemset(ctx->d_rs_aux, 0, sizeof(Rs2Aux))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_ctl, 0, 3 * sizeof(TileCtl))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_state64, 0, ((size_t)div_up((long long)N, CP_TILE) + 2) * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
   if ((e = cudaMemset(ctx->d_state64_b, 0, ((size_t)div_up((long long)N, CP_TILE) + 2) * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "memset");
@@ -507,7 +523,7 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
-                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_partials, ctx->d_frame,
+                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_rs_aux, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
                   ctx->d_res_vs, ctx->d_comp, ctx->d_res_pts, ctx->d_res_centroid, ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start,

@@ -4,7 +4,7 @@
 // src/tunnel_processing.cpp:215-220) and the kd-tree build of pcl::NormalEstimation (:58-70): both
 // become one stable sort of 32-bit keys with their 32-bit payload.
 //
-// The input is cut into G <= 148*4 contiguous SEGMENTS (a whole number of 256*IPT-key chunks each).
+// The input is cut into G <= 148*4 contiguous SEGMENTS (a whole number of 256*IPT-key chunks each, dealt out evenly).
 // One pass = TWO wait-free kernels, no inter-block spinning, no memsets:
 //   k_rs2_hist  block b: digit histogram of segment b               -> hist[b][256]
 //               per-thread BYTE counters in shared memory: thread t owns byte (d & 3) of word
@@ -36,6 +36,22 @@ constexpr int RS2_GROUPS = (RS2_MAX_SEGMENTS + RS2_GROUP - 1) / RS2_GROUP;
 constexpr int RS2_IPT = 8;
 constexpr int RS2_CHUNK = RS2_DOWN_THREADS * RS2_IPT;
 
+// Segment b covers chunks [b * q + min(b, r), ... + q + (b < r)): the chunks are dealt out as evenly as they go (the first r
+// segments hold one more), so that with 592 segments every SM -- blocks are handed to the SMs round robin -- gets the same
+// number of chunks to within one.  (Equal segments of ceil(chunks / 592) chunks left 49 of the 148 SMs with 3 blocks
+// instead of 4 and idle for the last quarter of the kernel: 35 % of the warp slots active instead of 46 %.)
+struct Rs2Seg {
+  int q, r;
+};
+__device__ __forceinline__ void rs2_segment(const Rs2Seg sg, int n, int& beg, int& end) {
+  const long long b = blockIdx.x;
+  const long long first = b * sg.q + (b < sg.r ? b : sg.r);
+  const long long nch = sg.q + (b < sg.r ? 1 : 0);
+  const long long bb = first * RS2_CHUNK, ee = bb + nch * RS2_CHUNK;
+  beg = (int)(bb < n ? bb : n);
+  end = (int)(ee < n ? ee : n);
+}
+
 // Device-side sums of one pass; all zero between passes and between sorts (cleared by k_rs2_down).
 struct Rs2Aux {
   unsigned group[RS2_GROUPS][256];  // per digit: keys in the 32 segments of group g
@@ -44,7 +60,7 @@ struct Rs2Aux {
 
 // ---- segment histogram --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RS2_HIST_THREADS)
-k_rs2_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int shift, unsigned mask, int seg_keys,
+k_rs2_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int shift, unsigned mask, Rs2Seg seg,
            unsigned* __restrict__ hist /* [G][256] */, Rs2Aux* __restrict__ aux) {
   constexpr int T = RS2_HIST_THREADS;
   constexpr int ROUND = T * 240;  // a byte counter holds 255 keys of one thread; 240 = 15 whole batches of 16
@@ -52,9 +68,8 @@ k_rs2_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int
   unsigned char* s_bytes = reinterpret_cast<unsigned char*>(s_cnt);
   const int n = *n_ptr;
   const int t = threadIdx.x;
-  const long long beg_ll = (long long)blockIdx.x * seg_keys;
-  const int beg = beg_ll < n ? (int)beg_ll : n;
-  const int end = (int)(beg_ll + seg_keys < (long long)n ? beg_ll + seg_keys : (long long)n);
+  int beg, end;
+  rs2_segment(seg, n, beg, end);
   const int q = t >> 1, half = t & 1;
   unsigned tot0 = 0, tot1 = 0, tot2 = 0, tot3 = 0;  // digits 4q .. 4q+3, this thread's half of the columns
   for (int base = beg; base < end; base += ROUND) {
@@ -165,18 +180,16 @@ struct Rs2DownSmem {
 
 __device__ __forceinline__ unsigned rs2_kv_slot(unsigned pos) { return pos + (pos >> 4); }
 
-// warp-private prefetch of the warp's 32 * IPT keys and values of the chunk at `cb` (16-byte copies, zero-filled past `end`)
-__device__ __forceinline__ void rs2_prefetch(Rs2DownSmem& sm, const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
-                                             int cb, int end) {
+// warp-private prefetch of the warp's 32 * IPT keys (or values) of the chunk at `cb` (16-byte copies, zero-filled past `end`)
+__device__ __forceinline__ void rs2_prefetch(unsigned* s_dst, const unsigned* __restrict__ src_arr, int cb, int end) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < RS2_IPT / 4; ++j) {
-    const int off = w * (32 * RS2_IPT) + (j * 32 + l) * 4;  // first of the 4 keys this copy moves
+    const int off = w * (32 * RS2_IPT) + (j * 32 + l) * 4;  // first of the 4 elements this copy moves
     const int left = end - (cb + off);
     const int bytes = left >= 4 ? 16 : (left > 0 ? left * 4 : 0);
     const int src = bytes ? cb + off : cb;  // a copy of 0 bytes reads nothing; keep its address inside the array anyway
-    rs2_cp_async16(&sm.in_keys[off], keys_in + src, bytes);
-    rs2_cp_async16(&sm.in_vals[off], vals_in + src, bytes);
+    rs2_cp_async16(&s_dst[off], src_arr + src, bytes);
   }
 }
 
@@ -198,7 +211,10 @@ __device__ __forceinline__ void rs2_chunk(Rs2DownSmem& sm, const unsigned* __res
     if (!FULL_CHUNK && p >= n_valid) key[i] = 0xFFFFFFFFu;  // tail: the highest digit, after every valid key -> never written out
   }
   __syncwarp();
-  if (FULL_CHUNK && cb + RS2_CHUNK < end) rs2_prefetch(sm, keys_in, vals_in, cb + RS2_CHUNK, end);
+  if (FULL_CHUNK && cb + RS2_CHUNK < end) {  // (leaving the values in shared memory until the scatter -- 48 registers, 5 blocks
+    rs2_prefetch(sm.in_keys, keys_in, cb + RS2_CHUNK, end);  //  per SM -- was measured 3 % slower)
+    rs2_prefetch(sm.in_vals, vals_in, cb + RS2_CHUNK, end);
+  }
 
   // stable ranks inside the warp's 32*IPT keys, order = (i, lane).  peers = lanes holding the same digit: one ballot per
   // digit bit.  The warp's digit counter is read by every peer (one broadcast LDS) and rewritten by the HIGHEST peer, whose
@@ -272,19 +288,19 @@ __device__ __forceinline__ void rs2_chunk(Rs2DownSmem& sm, const unsigned* __res
 template <int BITS>
 __global__ void __launch_bounds__(RS2_DOWN_THREADS, RS2_DOWN_MIN_BLOCKS)
 k_rs2_down(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in, unsigned* __restrict__ keys_out,
-           unsigned* __restrict__ vals_out, const int* __restrict__ n_ptr, int shift, int seg_keys,
+           unsigned* __restrict__ vals_out, const int* __restrict__ n_ptr, int shift, Rs2Seg seg,
            const unsigned* __restrict__ hist /* [G][256] segment histograms */, Rs2Aux* aux) {
   __shared__ __align__(16) Rs2DownSmem sm;
   __shared__ bool s_last;
   const int n = *n_ptr;
-  const long long beg_ll = (long long)blockIdx.x * seg_keys;
-  const bool active = beg_ll < n;
-  const int beg = active ? (int)beg_ll : n;
-  const int end = (int)(beg_ll + seg_keys < (long long)n ? beg_ll + seg_keys : (long long)n);
+  int beg, end;
+  rs2_segment(seg, n, beg, end);
+  const bool active = beg < n;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   unsigned gbase = 0;
   if (active) {
-    rs2_prefetch(sm, keys_in, vals_in, beg, end);
+    rs2_prefetch(sm.in_keys, keys_in, beg, end);
+    rs2_prefetch(sm.in_vals, vals_in, beg, end);
 #pragma unroll
     for (int j = 0; j < 8; ++j) sm.warp_hist[w][j * 32 + l] = 0;
     // thread d: first output position of digit d for this segment = (keys of lower digits) + (keys of digit d in the
@@ -330,7 +346,8 @@ k_rs2_down(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ va
 
 // ---- host side -------------------------------------------------------------------------------------------
 struct Rs2Plan {
-  int passes, bits, seg_keys, segments;
+  int passes, bits, segments;
+  Rs2Seg seg;
 };
 inline Rs2Plan rs2_plan(size_t n_cap, int key_bits) {
   Rs2Plan p;
@@ -338,11 +355,11 @@ inline Rs2Plan rs2_plan(size_t n_cap, int key_bits) {
   p.passes = (key_bits + 7) / 8;
   p.bits = (key_bits + p.passes - 1) / p.passes;
   if (p.bits < 4) p.bits = 4;
-  const long long chunks = ((long long)n_cap + RS2_CHUNK - 1) / RS2_CHUNK;
-  const long long seg_chunks = chunks > 0 ? (chunks + RS2_MAX_SEGMENTS - 1) / RS2_MAX_SEGMENTS : 1;
-  p.seg_keys = (int)(seg_chunks * RS2_CHUNK);
-  p.segments = (int)((chunks + seg_chunks - 1) / seg_chunks);
-  if (p.segments < 1) p.segments = 1;
+  long long chunks = ((long long)n_cap + RS2_CHUNK - 1) / RS2_CHUNK;
+  if (chunks < 1) chunks = 1;
+  p.segments = (int)(chunks < RS2_MAX_SEGMENTS ? chunks : RS2_MAX_SEGMENTS);
+  p.seg.q = (int)(chunks / p.segments);
+  p.seg.r = (int)(chunks % p.segments);
   return p;
 }
 constexpr size_t RS2_HIST_WORDS = (size_t)RS2_MAX_SEGMENTS * 256;
@@ -350,7 +367,7 @@ constexpr size_t RS2_HIST_WORDS = (size_t)RS2_MAX_SEGMENTS * 256;
 template <int BITS>
 inline void rs2_launch_down(cudaStream_t st, const Rs2Plan& p, const unsigned* ki, const unsigned* vi, unsigned* ko, unsigned* vo,
                             const int* n_ptr, int shift, const unsigned* hist, Rs2Aux* aux) {
-  k_rs2_down<BITS><<<p.segments, RS2_DOWN_THREADS, 0, st>>>(ki, vi, ko, vo, n_ptr, shift, p.seg_keys, hist, aux);
+  k_rs2_down<BITS><<<p.segments, RS2_DOWN_THREADS, 0, st>>>(ki, vi, ko, vo, n_ptr, shift, p.seg, hist, aux);
 }
 
 // Sorts (keys[0], vals[0]) using (keys[1], vals[1]) as the other half of the ping-pong; returns the index of the buffer
@@ -363,7 +380,7 @@ inline int rs2_sort(cudaStream_t st, unsigned* const keys[2], unsigned* const va
   int cur = 0;
   for (int pass = 0; pass < p.passes; ++pass) {
     const int shift = pass * p.bits;
-    k_rs2_hist<<<p.segments, RS2_HIST_THREADS, 0, st>>>(keys[cur], n_ptr, shift, mask, p.seg_keys, hist, aux);
+    k_rs2_hist<<<p.segments, RS2_HIST_THREADS, 0, st>>>(keys[cur], n_ptr, shift, mask, p.seg, hist, aux);
     switch (p.bits) {
       case 4: rs2_launch_down<4>(st, p, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n_ptr, shift, hist, aux); break;
       case 5: rs2_launch_down<5>(st, p, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n_ptr, shift, hist, aux); break;

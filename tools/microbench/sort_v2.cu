@@ -49,8 +49,8 @@ static int check(int n, int bits, unsigned seed, int n_cap_extra) {
   long long bad = 0;
   for (int i = 0; i < n; ++i) bad += (ov[i] != idx[i]) || (ok[i] != hk[idx[i]]);
   const Rs2Plan p = rs2_plan((size_t)n + n_cap_extra, bits);
-  printf("check n=%d cap=+%d bits=%d passes=%d digit_bits=%d segments=%d seg_keys=%d mismatches=%lld (%s)\n", n, n_cap_extra, bits, p.passes,
-         p.bits, p.segments, p.seg_keys, bad, cudaGetErrorString(cudaGetLastError()));
+  printf("check n=%d cap=+%d bits=%d passes=%d digit_bits=%d segments=%d q=%d r=%d mismatches=%lld (%s)\n", n, n_cap_extra, bits, p.passes,
+         p.bits, p.segments, p.seg.q, p.seg.r, bad, cudaGetErrorString(cudaGetLastError()));
   return bad != 0;
 }
 
@@ -96,9 +96,9 @@ static void bench(int n, int bits) {
          time_us([&] { k_rs_upsweep<8><<<ntiles, RS_BLOCK>>>(dk[0], d_n, 0, ntiles, d_hist1); }, false),
          time_us([&] { k_rs_upsweep<8><<<ntiles, RS_BLOCK>>>(dk[0], d_n, 0, ntiles, d_hist1); k_rs_scan<<<256, RS_BLOCK>>>(d_hist1, d_n, TILE, ntiles, d_tot); }, false) ,
          time_us([&] { k_rs_downsweep<8><<<ntiles, RS_BLOCK>>>(dk[0], dv[0], dk[1], dv[1], d_n, 0, ntiles, d_hist1, d_tot); }, false),
-         time_us([&] { k_rs2_hist<<<p.segments, RS2_HIST_THREADS>>>(dk[0], d_n, 0, m, p.seg_keys, d_hist2, d_aux); cudaMemsetAsync(d_aux, 0, sizeof(Rs2Aux)); }, false),
+         time_us([&] { k_rs2_hist<<<p.segments, RS2_HIST_THREADS>>>(dk[0], d_n, 0, m, p.seg, d_hist2, d_aux); cudaMemsetAsync(d_aux, 0, sizeof(Rs2Aux)); }, false),
          0.0f,
-         time_us([&] { k_rs2_hist<<<p.segments, RS2_HIST_THREADS>>>(dk[0], d_n, 0, m, p.seg_keys, d_hist2, d_aux); rs2_launch_down<8>(0, p, dk[0], dv[0], dk[1], dv[1], d_n, 0, d_hist2, d_aux); }, false));
+         time_us([&] { k_rs2_hist<<<p.segments, RS2_HIST_THREADS>>>(dk[0], d_n, 0, m, p.seg, d_hist2, d_aux); rs2_launch_down<8>(0, p, dk[0], dv[0], dk[1], dv[1], d_n, 0, d_hist2, d_aux); }, false));
   printf("  (the two 'scan' columns time histogram + scan together: subtract the first column)\n");
 }
 

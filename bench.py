@@ -573,7 +573,8 @@ def main():
     P_grid = (key_bits_grid + 7) // 8
     sort_bytes = 20.0 * P_grid * Mc                 # per pass: histogram read 4 + (key,index) read 8 + write 8
     sort_ms = seg_ms["grid_sort"]
-    sort_traffic = None if traffic.get("k_rs_upsweep<8>") is None else P_grid * (traffic["k_rs_upsweep<8>"] + traffic.get("k_rs_scan", 0.0) + traffic["k_rs_downsweep<8>"])
+    down_keys = [k for k in traffic if k.startswith("k_rs2_down")]
+    sort_traffic = None if (traffic.get("k_rs2_hist") is None or not down_keys) else P_grid * (traffic["k_rs2_hist"] + traffic[down_keys[0]])
     P_vox = 3
     vox8d_bytes = 16.0 * n + (68.0 + 16.0 * P_vox) * M + 20.0 * V     # crop + keys + P-pass sort + heads + centroids
     voxdense_ms = seg_ms["crop"] + seg_ms["voxel_keys"] + seg_ms["voxel_sort"] + seg_ms["voxel_reduce"]
@@ -600,8 +601,10 @@ def main():
         "radix_sort": {"bound": "hbm", "achieved": gbs(sort_bytes, sort_ms), "peak": hbm_peak, "unit": "GB/s",
                        "frac": (gbs(sort_bytes, sort_ms) or 0.0) / hbm_peak, "traffic": sort_traffic,
                        "achieved_on_traffic": gbs(sort_traffic, sort_ms), "ms_per_step": sort_ms,
-                       "kernels": f"{P_grid} x (k_rs_upsweep + k_rs_scan + k_rs_downsweep): the neighbour-grid sort of the cropped cloud",
-                       "algorithmic": f"20 B x {P_grid} passes x {Mc:.0f} keys", "peak_source": peak_src},
+                       "kernels": f"{P_grid} x (k_rs2_hist + k_rs2_down): the neighbour-grid sort of the cropped cloud (segment form, "
+                                  f"csrc/gm_sort.cuh)",
+                       "algorithmic": f"20 B x {P_grid} passes x {Mc:.0f} keys (SURVEY 8(d): histogram read 4 + pair read 8 + pair write 8 per pass)",
+                       "peak_source": peak_src},
         "voxel_dense": {"bound": "hbm", "achieved": gbs(vox8d_bytes, voxdense_ms), "peak": hbm_peak, "unit": "GB/s",
                         "frac": (gbs(vox8d_bytes, voxdense_ms) or 0.0) / hbm_peak, "traffic": voxdense_traffic,
                         "achieved_on_traffic": gbs(voxdense_traffic, voxdense_ms),

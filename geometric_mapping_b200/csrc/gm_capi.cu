@@ -128,7 +128,7 @@ struct gm_ctx {
   unsigned char* d_labels = nullptr;
   unsigned long long* d_state64 = nullptr;
   unsigned long long* d_state64_b = nullptr;  // tile states of the cylinder-refit compaction (may run concurrently with the voxel branch)
-  unsigned *d_rs_hist = nullptr, *d_rs_totals = nullptr;  // segment histograms [segments][256] (round-1 tile form: [256][tiles] + [256] row totals)
+  unsigned* d_rs_hist = nullptr;                           // segment histograms [segments][256]
   Rs2Aux* d_rs_aux = nullptr;                              // group sums / totals / completion counter of one pass; zero between passes
   size_t rs_hist_words = 0;
   TileCtl* d_ctl = nullptr;      // [3] launch control of the look-back kernels: d_state64 | d_state64_b | d_dense_state
@@ -331,37 +331,10 @@ gm_status ensure_block_table(gm_ctx* ctx) {
 constexpr size_t kGridBucket = 32768;
 inline size_t grid_bucket(size_t n, size_t cap) { return n == 0 ? 0 : std::min(cap, (n + kGridBucket - 1) / kGridBucket * kGridBucket); }
 
-// LSD radix sort of (d_keys[0], d_vals[0]) -> returns the buffer index holding the result.
-// Three wait-free kernels per 8-bit pass (see gm_device.cuh); no memsets, no inter-block spinning.
-constexpr int kSmallSortKeys = 0;  // 1024-key tiles were measured SLOWER at 1M keys (73.6 vs 70.6 us per 3-pass sort): the passes are
-                                   // bound by the fixed cost of three dependent launches, not by the per-block chain; kept selectable (GM_SORT_IPT=4)
-template <int IPT>
-gm_status radix_sort_t(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int passes, int* result_buf) {
-  constexpr int TILE = RS_BLOCK * IPT;
-  int ntiles = div_up((long long)n_cap, TILE);
-  if ((size_t)ntiles * 256 > ctx->rs_hist_words) { ctx->err = "radix histogram capacity"; return GM_ERR_CAPACITY; }
-  int cur = 0;
-  for (int p = 0; p < passes; ++p) {
-    GM_LAUNCH(ctx, k_rs_upsweep<IPT>, ntiles, RS_BLOCK, ctx->d_keys[cur], n_ptr, p, ntiles, ctx->d_rs_hist);
-    GM_LAUNCH(ctx, k_rs_scan, 256, RS_BLOCK, ctx->d_rs_hist, n_ptr, TILE, ntiles, ctx->d_rs_totals);
-    GM_LAUNCH(ctx, k_rs_downsweep<IPT>, ntiles, RS_BLOCK, ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1], ctx->d_vals[cur ^ 1], n_ptr,
-              p, ntiles, ctx->d_rs_hist, ctx->d_rs_totals);
-    cur ^= 1;
-  }
-  *result_buf = cur;
-  GM_CHECK_LAUNCHES(ctx);
-  return GM_OK;
-}
-// Default: the segment form of gm_sort.cuh (byte-counter histograms, <= 592 segments, balanced digits of <= 8 bits, 2 launches per pass).
-// GM_SORT_V1=1 selects round 1's tile form (kept for A/B timing: tools/microbench/sort_v2.cu, bench.py --sort-v1).
+// LSD radix sort of (d_keys[0], d_vals[0]) -> returns the buffer index holding the result: the segment form of gm_sort.cuh
+// (byte-counter histograms, <= 592 segments, balanced digits of <= 8 bits, 2 launches per pass, no memsets).  Round 1's tile
+// form (3 launches per pass) is kept as a baseline in tools/microbench/sort_v1.cuh.
 gm_status radix_sort(gm_ctx* ctx, const int* n_ptr, size_t n_cap, int key_bits, int* result_buf) {
-  static const bool kV1 = [] { const char* e = std::getenv("GM_SORT_V1"); return e && std::atoi(e) != 0; }();
-  if (kV1) {
-    int passes = std::min(std::max(div_up(key_bits, 8), 1), RS_MAX_PASSES);
-    static const int kForce = [] { const char* e = std::getenv("GM_SORT_IPT"); return e ? std::atoi(e) : 0; }();
-    const bool small = kForce ? kForce == 4 : n_cap <= (size_t)kSmallSortKeys;
-    return small ? radix_sort_t<4>(ctx, n_ptr, n_cap, passes, result_buf) : radix_sort_t<8>(ctx, n_ptr, n_cap, passes, result_buf);
-  }
   const Rs2Plan plan = rs2_plan(n_cap, key_bits);
   if ((size_t)plan.segments * 256 > ctx->rs_hist_words) { ctx->err = "radix histogram capacity"; return GM_ERR_CAPACITY; }
   unsigned* const keys[2] = {ctx->d_keys[0], ctx->d_keys[1]};
@@ -468,8 +441,8 @@ gm_status gm_create(const gm_params* p, size_t max_points, int32_t max_hypothese
   A(d_vkey_pt, N); A(d_assign, N); A(d_vox_start, N + 1); A(d_vox_key, N); A(d_vox_count, N); A(d_nn_idx, N);
   A(d_labels, N);
   A(d_state64, (size_t)div_up((long long)N, CP_TILE) + 2); A(d_state64_b, (size_t)div_up((long long)N, CP_TILE) + 2);
-  ctx->rs_hist_words = (size_t)div_up((long long)N, RS_BLOCK * 4) * 256;  // sized for the smaller tile
-  A(d_rs_hist, ctx->rs_hist_words); A(d_rs_totals, 256); A(d_rs_aux, 1);
+  ctx->rs_hist_words = RS2_HIST_WORDS;
+  A(d_rs_hist, ctx->rs_hist_words); A(d_rs_aux, 1);
   A(d_st, 1); A(d_ctl, 3); A(d_frame_sums, 8);
   A(d_partials, 3 * kPartialsRegion);  // 3 regions: frame | plane refit | cylinder GN (may run concurrently)
   A(d_frame, 1);
@@ -523,7 +496,7 @@ void gm_destroy(gm_ctx* ctx) {
                   ctx->d_nn_normal, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1], ctx->d_ucell_key,
                   ctx->d_cell_id, ctx->d_ucell_start, ctx->d_nbr, ctx->d_valid_map, ctx->d_runs, ctx->d_vkey_pt, ctx->d_assign,
                   ctx->d_vox_start, ctx->d_vox_key, ctx->d_vox_count, ctx->d_nn_idx, ctx->d_labels, ctx->d_state64, ctx->d_state64_b,
-                  ctx->d_rs_hist, ctx->d_rs_totals, ctx->d_rs_aux, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_partials, ctx->d_frame,
+                  ctx->d_rs_hist, ctx->d_rs_aux, ctx->d_st, ctx->d_ctl, ctx->d_frame_sums, ctx->d_partials, ctx->d_frame,
                   ctx->d_samples[0], ctx->d_samples[1], ctx->d_plane_coef, ctx->d_model7, ctx->d_test12, ctx->d_hvalid[0],
                   ctx->d_hvalid[1], ctx->d_counts[0], ctx->d_counts[1], ctx->d_key, ctx->d_model, ctx->d_poly,
                   ctx->d_res_vs, ctx->d_comp, ctx->d_res_pts, ctx->d_res_centroid, ctx->d_res_key_pt, ctx->d_res_assign, ctx->d_res_vox_start,

@@ -31,7 +31,7 @@ def test_library_is_in_tree_and_has_sm100a_code():
     blob = open(path, "rb").read()
     assert b"sm_100a" in blob
     # the hot kernels are present in the fat binary
-    for k in (b"k_count_plane", b"k_count_cyl", b"k_normals", b"k_rs_downsweep", b"k_crop", b"k_voxel_keys"):
+    for k in (b"k_count_plane", b"k_count_cyl", b"k_normals", b"k_rs2_down", b"k_crop", b"k_voxel_keys"):
         assert k in blob
 
 

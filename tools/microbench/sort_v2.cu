@@ -1,8 +1,9 @@
 // Correctness (against std::stable_sort) and timing of the segment-form radix sort (gm_sort.cuh) beside the round-1
 // tile-form kernels (gm_device.cuh: k_rs_upsweep / k_rs_scan / k_rs_downsweep).
-//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -lineinfo -I../../geometric_mapping_b200/csrc -o sort_v2 sort_v2.cu
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -lineinfo -I../../geometric_mapping_b200/csrc -I. -o sort_v2 sort_v2.cu
 //   run:   ./sort_v2            (prints one line per case; exit code 1 on any mismatch)
 #include "gm_sort.cuh"
+#include "sort_v1.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

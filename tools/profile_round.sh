@@ -13,10 +13,10 @@ run ncu --set full --clock-control none --import-source on -o /tmp/full_1m -f $P
 ncu -i /tmp/full_1m.ncu-rep --page raw --csv > "$OUT/full_1m_raw.csv" 2>> "$OUT/log.txt"
 # ---- 10M points (map size): the HBM-bound kernels, dense and sort-based VoxelGrid ----
 run $PS --scans 2 --points 10000000 --radius 0.02 || exit 1
-run ncu --set full --clock-control none -k 'regex:k_crop|k_voxel|k_rs_|k_normals|k_count|k_compact|k_cell' -o /tmp/full_10m -f $PS --scans 2 --points 10000000 --radius 0.02
+run ncu --set full --clock-control none -k 'regex:k_crop|k_voxel|k_rs2_|k_normals|k_count|k_compact|k_cell' -o /tmp/full_10m -f $PS --scans 2 --points 10000000 --radius 0.02
 ncu -i /tmp/full_10m.ncu-rep --page raw --csv > "$OUT/full_10m_raw.csv" 2>> "$OUT/log.txt"
 run $PS --scans 2 --points 10000000 --radius 0.02 --voxel-mode 1 || exit 1
-run ncu --set full --clock-control none -k 'regex:k_voxel|k_rs_' -o /tmp/full_10m_sv -f $PS --scans 2 --points 10000000 --radius 0.02 --voxel-mode 1
+run ncu --set full --clock-control none -k 'regex:k_voxel|k_rs2_' -o /tmp/full_10m_sv -f $PS --scans 2 --points 10000000 --radius 0.02 --voxel-mode 1
 ncu -i /tmp/full_10m_sv.ncu-rep --page raw --csv > "$OUT/full_10m_sortvox_raw.csv" 2>> "$OUT/log.txt"
 # ---- brute-force counting (FP32-pipe figure) and the k-NN normals ----
 run $PS --scans 2 --count-mode 1 || exit 1

@@ -1,7 +1,7 @@
 """Time the radix sorts inside the real pipeline (neighbour-grid sort, sort-based VoxelGrid) on C1-type scans.
-    python tools/sort_time.py [points] [radius]        (GM_SORT_V1=1 selects round 1's tile-form kernels)
+    python tools/sort_time.py [points] [radius]
 Prints the library's own CUDA-event segment times (gm_profile_*), median over the scans, and a checksum of the outputs
-(equal for both sorts: the sort is stable, so every downstream result is bit-identical)."""
+(a stable sort leaves every downstream result bit-identical: compare with the line of the previous build)."""
 import os
 import sys
 
@@ -49,7 +49,7 @@ def main():
                     chk ^= int(np.ascontiguousarray(cen).view(np.uint32).astype(np.uint64).sum())
             med = {k: float(np.median(v)) for k, v in seg.items()}
             out[vm] = (med, chk, c.n_cropped, c.n_valid, c.n_voxels)
-    tag = "v1 (tile form)" if os.environ.get("GM_SORT_V1") else "v2 (segment form)"
+    tag = "segment-form sort"
     for vm, (med, chk, nc, nv, V) in out.items():
         keys = [k for k in ("grid_sort", "voxel_sort", "grid_keys", "grid_heads", "voxel_keys", "voxel_reduce") if k in med]
         print(f"{tag} points={n} r={radius} voxel_mode={vm} cropped={nc} valid={nv} voxels={V} | " +

@@ -43,14 +43,14 @@ constexpr int RS2_CHUNK = RS2_DOWN_THREADS * RS2_IPT;
 struct Rs2Seg {
   int q, r;
 };
-__device__ __forceinline__ void rs2_segment(const Rs2Seg sg, int n, int& beg, int& end) {
-  const long long b = blockIdx.x;
+__host__ __device__ __forceinline__ void rs2_segment_of(const Rs2Seg sg, long long b, int n, int& beg, int& end) {
   const long long first = b * sg.q + (b < sg.r ? b : sg.r);
   const long long nch = sg.q + (b < sg.r ? 1 : 0);
   const long long bb = first * RS2_CHUNK, ee = bb + nch * RS2_CHUNK;
   beg = (int)(bb < n ? bb : n);
   end = (int)(ee < n ? ee : n);
 }
+__device__ __forceinline__ void rs2_segment(const Rs2Seg sg, int n, int& beg, int& end) { rs2_segment_of(sg, blockIdx.x, n, beg, end); }
 
 // Device-side sums of one pass; all zero between passes and between sorts (cleared by k_rs2_down).
 struct Rs2Aux {

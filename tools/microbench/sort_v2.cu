@@ -113,6 +113,10 @@ int main(int argc, char** argv) {
     check(10000000, 27, 7u, 0);
     return 0;
   }
+  if (argc > 1 && atoi(argv[1]) == 3) {  // profiling mode: uniformly random 32-bit keys, 8-bit digits
+    check(10000000, 32, 8u, 0);
+    return 0;
+  }
   int bad = 0;
   const int sizes[] = {1, 31, 2047, 2048, 2049, 100003, 1000000, 1212416 + 5, 10000000};
   const int bitsv[] = {3, 8, 9, 17, 24, 27, 32};
